@@ -1,0 +1,295 @@
+/* rpg.h -- C ABI of the B200-native RelPose-GNN message-passing library (librpg_b200.so).
+ *
+ * The reference (nianticlabs/relpose-gnn) is pure Python and has no FFI; the boundary it
+ * offers for this path is the Python class API of
+ *     python/niantic/modules/my_gnn_layer.py:277-311   simpleConvEdge_upt(in, edge, out).forward(x, edge_index, edge_attr)
+ *     python/niantic/modules/posenet.py:1053-1091      the GNN part of PoseNetX_R2.forward
+ *     python/niantic/modules/posenet.py:1021-1031      PoseNetX_R2.compute_RP
+ *     python/niantic/modules/criterion.py:42-60        PoseNetCriterion.forward
+ *     python/niantic/training/train.py:236-248         edge-dropout mask
+ * Each entry point below names the reference code it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *  - all memory is owned by the caller (PyTorch); the library keeps no pointer after the
+ *    kernels are enqueued on `stream`; no host synchronisation inside any call;
+ *  - return value: 0 = ok, < 0 = argument error (RPG_E_*), > 0 = cudaError_t / CUresult;
+ *    rpg_last_error_string() describes the last failure on the calling thread;
+ *  - graphs are batched PyG-style: G graphs x N nodes, node row g*N+n, edge row g*Ep+k where
+ *    the per-graph edge template (src[k], dst[k]), k in [0,Ep), is shared by the whole batch
+ *    (the FC enumeration of dataset_7Scenes_multi.py:377-385,418-422, optionally thinned by
+ *    the batch-shared edge-dropout mask of train.py:238-242);
+ *  - "bf16 mode": activations/weights bf16 (uint16_t bit patterns), fp32 accumulation in TMEM.
+ */
+#ifndef RPG_H_
+#define RPG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rpg_stream_t; /* cudaStream_t */
+typedef uint16_t rpg_bf16;
+
+enum {
+  RPG_OK = 0,
+  RPG_E_ARG = -1,       /* bad shape / null pointer / unsupported size */
+  RPG_E_GRAPH = -2,     /* edge_index is not a batched uniform template */
+  RPG_E_UNSUPPORTED = -3,
+  RPG_E_DRIVER = -4     /* could not resolve cuTensorMapEncodeTiled */
+};
+
+const char* rpg_last_error_string(void);
+int rpg_version(void);
+/* Device properties the host side sizes grids with (SM count etc.); also proves the .so loads. */
+int rpg_device_sm_count(int device, int* sm_count);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph structure
+ * ---------------------------------------------------------------------------------------- */
+
+/* Checks that edge_index [2, Et] (int64, device) is G copies of one per-graph template with node
+ * offset g*N, i.e. what PyG batching of the reference datasets produces (train.py:24,132), and
+ * extracts the template of graph 0 into tmpl_src/tmpl_dst [Ep] (int32, device).
+ * *bad_count (device int32, zeroed by the callee) receives the number of violating columns; the
+ * caller reads it back and raises ValueError (SURVEY.md 8b error convention).                    */
+int rpg_validate_edge_index(const int64_t* edge_index, int64_t Et, int G, int N, int Ep,
+                            int32_t* tmpl_src, int32_t* tmpl_dst, int32_t* bad_count, rpg_stream_t stream);
+
+/* Per-graph template tables living in device memory (built on the host by the Python mirror from the
+ * validated template; a few hundred bytes).                                                        */
+typedef struct {
+  int G, N, Ep;               /* graphs, nodes per graph, edges per graph                         */
+  const int32_t* src;         /* [Ep] source node (local index) of template edge k                */
+  const int32_t* dst;         /* [Ep] destination node                                            */
+  const int32_t* in_ptr;      /* [N+1] CSR over destination: in-edges of node n                   */
+  const int32_t* in_idx;      /* [Ep]                                                             */
+  const int32_t* out_ptr;     /* [N+1] CSR over source: out-edges of node n                       */
+  const int32_t* out_idx;     /* [Ep]                                                             */
+  const float* inv_deg;       /* [N] 1 / max(1, in-degree)   (PyG mean aggregation [3p])          */
+  const float* deg;           /* [N] in-degree as float                                           */
+  const int32_t* min_ptr;     /* [N+1] CSR over min(src,dst): edges whose lower endpoint is n     */
+  const int32_t* min_idx;     /* [Ep]                                                             */
+  const int32_t* max_ptr;     /* [N+1] CSR over max(src,dst)                                      */
+  const int32_t* max_idx;     /* [Ep]                                                             */
+} rpg_graph_t;
+
+/* ------------------------------------------------------------------------------------------
+ * Generic tcgen05 GEMM with fused epilogue (the workhorse; exposed for unit tests)
+ *   C[M,N] = epilogue( sum_s A_s[M,K_s] * B[N, K_0+K_1+..]^T )            (mode NT, K-major)
+ *   C[M,N] = sum over rows r of A[r, M]^T B[r, N]   split over `splits`    (mode TN, MN-major)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int mode;                   /* 0 = NT (A [M,K] row-major, B [N,K] row-major), 1 = TN (A [R,M], B [R,N]) */
+  int M, N;                   /* output shape                                                       */
+  int n_seg;                  /* NT: number of A segments (1..3) concatenated along K                */
+  const rpg_bf16* A[3];       /* NT: segment s is [M, K[s]] with row pitch lda[s] (elements)          */
+  int K[3];
+  int lda[3];
+  const rpg_bf16* B;          /* NT: [N, sum K] pitch ldb;   TN: [R, N] pitch ldb                     */
+  int ldb;
+  int R;                      /* TN: number of contracted rows                                       */
+  int splits;                 /* TN: split-R factor; partial s is written at out_f32 + s*split_stride */
+  int64_t split_stride;
+  int block_n;                /* UMMA N tile: multiple of 16 in [16,256]; 0 = library default        */
+  /* ---- epilogue (NT mode), applied in this order ---- */
+  const float* bias;          /* [N] or NULL                                                         */
+  const rpg_bf16* gadd[2];    /* + gadd[i][ node_row(row, gmap[i]) , col ]  (row pitch gadd_ld[i])    */
+  const int32_t* gmap[2];     /* template table (rpg_graph_t.src or .dst), node_row = (row/Ep)*N + gmap[row%Ep] */
+  int gadd_ld[2];
+  int Ep, Nn;
+  const rpg_bf16* resid;      /* + resid[row, col] (pitch resid_ld) or NULL                           */
+  int resid_ld;
+  const float* row_scale;     /* * row_scale[row % row_scale_mod] or NULL (e.g. 1/deg)               */
+  int row_scale_mod;
+  const rpg_bf16* mask;       /* * (mask[row, col] > 0)  (ReLU backward) or NULL                      */
+  int mask_ld;
+  int relu;                   /* max(.,0) on the stored value                                        */
+  rpg_bf16* out;              /* bf16 output (pitch ldo) or NULL                                      */
+  rpg_bf16* out_relu;         /* second bf16 output holding max(value,0) or NULL                      */
+  int ldo;
+  float* out_f32;             /* fp32 output (pitch ldo_f32) or NULL                                  */
+  int ldo_f32;
+} rpg_gemm_t;
+
+int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream);
+
+/* Weight gradient dW[M,N] += A[R,M]^T B[R,N] (fp32, pitch ldo): TN GEMM split over R into `ws`
+ * (rpg_layer_bwd_ws_floats elements) followed by the deterministic reduction below.                 */
+int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R,
+              float* ws, float* out, int ldo, rpg_stream_t stream);
+/* sizeof / offsetof probes so a foreign-language mirror of the structs can verify its layout.      */
+void rpg_struct_sizes(int32_t* out8);
+
+/* out[r, c] (+)= sum_s partial[s, r, c]  -- deterministic second stage of the TN split.            */
+int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols,
+                      float* out, int ldo, int accumulate, rpg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weights: fp32 master parameters (reference state_dict layout) -> packed bf16 operands
+ * ---------------------------------------------------------------------------------------- */
+
+/* dst[r, c] = bf16(src[r0 + r, c0 + c]) for a rows x cols window of a row-major fp32 matrix;
+ * transpose != 0 writes dst[c, r] instead.  Used to cut the concatenated-input weights of
+ * my_gnn_layer.py:232,280,284 into per-source blocks and to build the dgrad (transposed) copies. */
+int rpg_pack_weight(const float* src, int ld_src, int r0, int c0, int rows, int cols,
+                    rpg_bf16* dst, int ld_dst, int transpose, rpg_stream_t stream);
+
+int rpg_cast_f32_to_bf16(const float* src, rpg_bf16* dst, int64_t n, rpg_stream_t stream);
+int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bandwidth-bound kernels of the path
+ * ---------------------------------------------------------------------------------------- */
+
+/* AttentionBlock core, att.py:25-30: y[e,i] = sum_j softmax_j(phi[e,i]*theta[e,j]) * g[e,j].
+ * gtp [Et, 3c] fp32 holds (g | theta | phi) rows; y [Et, ldy] bf16 (only the first c columns written). */
+int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_stream_t stream);
+/* Backward of the above with dy[e,:] = dyn[node(dst(e)), :] gathered through the template:
+ * dgtp [Et, ld_dgtp] bf16 = (dg | dtheta | dphi) in the first 3c columns.                          */
+int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph,
+                      int64_t Et, int c, rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream);
+
+/* PyG mean aggregation over destination [3p], reached from my_gnn_layer.py:301:
+ * a[g*N+n, :] = inv_deg[n] * sum_{k in in-edges(n)} z[g*Ep+k, :]   (fixed order, no atomics).       */
+int rpg_aggregate_mean(const rpg_bf16* z, int ldz, const rpg_graph_t* graph, int D,
+                       rpg_bf16* a, int lda, rpg_stream_t stream);
+/* Segment sums edge rows -> node rows, by source (by_src=1) or destination (0), fp32 accumulate:
+ * out[g*N+n, :] = sum_{k in out/in-edges(n)} v[g*Ep+k, :]                                          */
+int rpg_edge_to_node_sum(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, int D, int by_src,
+                         rpg_bf16* out, int ldo, rpg_stream_t stream);
+/* General form over any CSR of the template, with an optional ReLU mask (mask[row,c] > 0) on the edge
+ * rows and an optional per-node scale: out[g*N+n,:] = scale[n] * sum_{k in csr(n)} (v * [mask>0])[g*Ep+k,:] */
+int rpg_segment_sum(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, const int32_t* csr_ptr,
+                    const int32_t* csr_idx, const float* scale, const rpg_graph_t* graph, int D,
+                    rpg_bf16* out, int ldo, rpg_stream_t stream);
+
+/* Edge-feature initialiser, posenet.py:1014-1017 + :1053-1055 in factorised form:
+ * e0[g*Ep+k, :] = relu(pmin[node(min(s,t)), :] + pmax[node(max(s,t)), :] + bias), where
+ * pminmax [Nt, 2D] = x * [W_min; W_max]^T (proj_edge.weight[:, 0:D] and [:, D:2D]).
+ * Backward = rpg_segment_sum over min_ptr/max_ptr with mask = e0, then node-level GEMMs.             */
+int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D,
+                      rpg_bf16* e0, int lde, rpg_stream_t stream);
+
+/* Feature dropout + pose heads, posenet.py:1073-1086: pose[r, 0:3] = fc_xyz(drop(f[r])), [3:6] = fc_wpqr(..).
+ * Dropout follows F.dropout (kept entries scaled by 1/(1-p)).  The keep decision is either an explicit
+ * uint8 [rows, D] mask `keep` (parity tests: ATen's Philox stream cannot be reproduced) or, when keep is
+ * NULL and p_drop > 0, a counter-based hash of (seed, row, col) evaluated in-kernel (no mask traffic);
+ * rpg_dropout_mask materialises that same decision so an oracle can consume it.                      */
+int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream);
+int rpg_head_fwd(const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed,
+                 float p_drop, const float* w6, const float* b6, float* pose, rpg_stream_t stream);
+/* dfeat = (dpose * W6) * keep * scale * (feat > 0 if mask_relu); dW6 [6, D] and db6 [6] (+)= ... ;
+ * ws: rpg_head_bwd_ws_floats(rows, D) floats of scratch for the deterministic two-stage reduction.   */
+int64_t rpg_head_bwd_ws_floats(int64_t rows, int D);
+int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep,
+                 uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf,
+                 float* dw6, float* db6, int accumulate, float* ws, rpg_stream_t stream);
+
+/* compute_RP (posenet.py:1021-1031) + the L1 sums of PoseNetCriterion (criterion.py:51-52) fused:
+ * target[e] = poses[src(e)] - poses[dst(e)];  sums[0] = sum|pred_t - targ_t|, sums[1] = sum|pred_q - targ_q|
+ * (fp32, deterministic two-stage reduction); dpred[e,j] = sign(pred - target) * grad_scale[j<3 ? 0 : 1]
+ * (grad_scale: device [2], e.g. exp(-sax)/(3 Et), exp(-saq)/(3 Et); NULL = 1).  target/dpred may be NULL. */
+int64_t rpg_pose_loss_ws_floats(int64_t Et);
+int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et,
+                  const float* grad_scale, float* target, float* sums, float* dpred, float* ws,
+                  rpg_stream_t stream);
+
+/* Column sums (bias gradients): out[c] (+)= sum_r w[r % mod] * v[r, c]; deterministic; row_w may be NULL. */
+int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod,
+                    float* out, int accumulate, float* scratch, rpg_stream_t stream);
+int64_t rpg_colsum_scratch_floats(int64_t rows, int cols);
+
+/* ------------------------------------------------------------------------------------------
+ * The layer: simpleConvEdge_upt.forward (my_gnn_layer.py:293-311) and its backward
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int D;                          /* in = edge = out channels (every reference call site)  */
+  /* packed bf16 operands, forward */
+  const rpg_bf16* Wn;             /* [3D, D]  rows: edge_mlp.0[:,0:D] | edge_mlp.0[:,D:2D] | mlp.0[:,0:D] */
+  const rpg_bf16* W1e_e;          /* [D, D]   edge_mlp.0[:, 2D:3D]                                       */
+  const rpg_bf16* W2e;            /* [D, D]   edge_mlp.2                                                 */
+  const rpg_bf16* W1m_e;          /* [D, D]   mlp.0[:, D:2D]                                             */
+  const rpg_bf16* W2m;            /* [D, D]   mlp.2                                                      */
+  const rpg_bf16* Wgtp;           /* [3c, D]  att.g | att.theta | att.phi                                */
+  const rpg_bf16* WW;             /* [D, c]   att.W                                                      */
+  const rpg_bf16* W1u;            /* [D, 2D]  mlp_updating.0                                             */
+  const rpg_bf16* W2u;            /* [D, D]   mlp_updating.2                                             */
+  /* transposed copies, backward (dgrad) */
+  const rpg_bf16* WnT;            /* [D, 3D] */
+  const rpg_bf16* W1e_eT, *W2eT, *W1m_eT, *W2mT, *W2uT;   /* [D, D]                                      */
+  const rpg_bf16* WgtpT;          /* [D, 3c] */
+  const rpg_bf16* WWT;            /* [c, D]  */
+  const rpg_bf16* W1uT;           /* [2D, D] */
+  /* fp32 biases */
+  const float* b1e, *b2e, *b1m, *b2m, *bgtp, *bW, *b1u, *b2u;
+} rpg_layer_weights_t;
+
+typedef struct {                  /* activations of one layer call; all bf16 unless noted               */
+  const rpg_bf16* x;              /* [Nt, D] in                                                         */
+  const rpg_bf16* e;              /* [Et, D] in                                                         */
+  rpg_bf16* P;                    /* [Nt, 3D] scratch: x*Wn^T                                           */
+  rpg_bf16* h1;                   /* [Et, D]                                                            */
+  rpg_bf16* e_new;                /* [Et, D] out (pre-ReLU)                                             */
+  rpg_bf16* e_new_relu;           /* [Et, D] optional: relu(e_new) for the caller (posenet.py:1065)     */
+  rpg_bf16* h2;                   /* [Et, D]                                                            */
+  rpg_bf16* m;                    /* [Et, D]                                                            */
+  float* gtp;                     /* [Et, 3c] fp32                                                      */
+  rpg_bf16* y;                    /* [Et, max(c,64)]                                                    */
+  rpg_bf16* z;                    /* [Et, D] scratch                                                    */
+  rpg_bf16* a;                    /* [Nt, D]                                                            */
+  rpg_bf16* h3;                   /* [Nt, D]                                                            */
+  rpg_bf16* out;                  /* [Nt, D] out (pre-ReLU)                                             */
+  rpg_bf16* out_relu;             /* [Nt, D] optional relu(out) (posenet.py:1064)                       */
+} rpg_layer_acts_t;
+
+int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,
+                  rpg_stream_t stream);
+
+typedef struct {
+  const rpg_bf16* d_out;          /* [Nt, D] grad wrt out (pre-ReLU) or NULL (= zeros)                  */
+  const rpg_bf16* d_e_new;        /* [Et, D] grad wrt e_new (pre-ReLU) or NULL                          */
+  int mask_dx;                    /* multiply dx by (x > 0): the caller's x is a ReLU output            */
+  int mask_de;                    /* multiply de by (e > 0)                                             */
+  rpg_bf16* dx;                   /* [Nt, D] out                                                        */
+  rpg_bf16* de;                   /* [Et, D] out                                                        */
+  /* scratch */
+  rpg_bf16* dh3;                  /* [Nt, D]    */
+  rpg_bf16* dxu;                  /* [Nt, D]    */
+  rpg_bf16* dan;                  /* [Nt, D]    */
+  float* dyn;                     /* [Nt, c] fp32 */
+  rpg_bf16* dgtp;                 /* [Et, 3c]   */
+  rpg_bf16* dm;                   /* [Et, D]    */
+  rpg_bf16* dh2;                  /* [Et, D]    */
+  rpg_bf16* de_tot;               /* [Et, D]    */
+  rpg_bf16* dh1;                  /* [Et, D]    */
+  rpg_bf16* dP;                   /* [Nt, 3D]   */
+  rpg_bf16* ysum;                 /* [Nt, max(c,64)] */
+  float* split_ws;                /* fp32 split-R workspace, rpg_layer_bwd_ws_floats() elements         */
+  float* colsum_ws;               /* rpg_colsum_scratch_floats(Et, D) floats                            */
+  float* gtp_bias_tmp;            /* [pad64(3c)] fp32                                                   */
+  /* fp32 weight gradients in the reference's state_dict layout, accumulated (+=) */
+  float* g_mlp0_w;  float* g_mlp0_b;      /* [D, 2D], [D]   mlp.0            */
+  float* g_mlp2_w;  float* g_mlp2_b;      /* [D, D]         mlp.2            */
+  float* g_upd0_w;  float* g_upd0_b;      /* [D, 2D]        mlp_updating.0   */
+  float* g_upd2_w;  float* g_upd2_b;      /* [D, D]         mlp_updating.2   */
+  float* g_edge0_w; float* g_edge0_b;     /* [D, 3D]        edge_model.edge_mlp.0 */
+  float* g_edge2_w; float* g_edge2_b;     /* [D, D]         edge_model.edge_mlp.2 */
+  float* g_att_g_w; float* g_att_g_b;     /* [c, D]         att.g / theta / phi */
+  float* g_att_theta_w; float* g_att_theta_b;
+  float* g_att_phi_w; float* g_att_phi_b;
+  float* g_att_W_w; float* g_att_W_b;     /* [D, c], [D]    att.W            */
+} rpg_layer_grads_t;
+
+int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt);
+int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,
+                  const rpg_layer_grads_t* g, rpg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPG_H_ */

@@ -1,0 +1,142 @@
+"""ctypes binding of librpg_b200.so (C ABI: include/rpg.h).
+
+There is NO fallback: if the shared library is missing and cannot be built, importing any op raises.
+Structures mirror include/rpg.h field for field; `_check_layout()` compares sizeof/offsetof probes
+exported by the library (`rpg_struct_sizes`) against the ctypes mirrors at load time.
+"""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librpg_b200.so")
+
+P = C.c_void_p
+I = C.c_int
+I64 = C.c_int64
+U64 = C.c_uint64
+F = C.c_float
+
+
+class RpgError(RuntimeError):
+    pass
+
+
+class Graph(C.Structure):
+    _fields_ = [("G", I), ("N", I), ("Ep", I),
+                ("src", P), ("dst", P), ("in_ptr", P), ("in_idx", P), ("out_ptr", P), ("out_idx", P),
+                ("inv_deg", P), ("deg", P), ("min_ptr", P), ("min_idx", P), ("max_ptr", P), ("max_idx", P)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [("mode", I), ("M", I), ("N", I), ("n_seg", I),
+                ("A", P * 3), ("K", I * 3), ("lda", I * 3),
+                ("B", P), ("ldb", I), ("R", I), ("splits", I), ("split_stride", I64), ("block_n", I),
+                ("bias", P), ("gadd", P * 2), ("gmap", P * 2), ("gadd_ld", I * 2), ("Ep", I), ("Nn", I),
+                ("resid", P), ("resid_ld", I), ("row_scale", P), ("row_scale_mod", I),
+                ("mask", P), ("mask_ld", I), ("relu", I),
+                ("out", P), ("out_relu", P), ("ldo", I), ("out_f32", P), ("ldo_f32", I)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [("D", I)] + [(n, P) for n in (
+        "Wn", "W1e_e", "W2e", "W1m_e", "W2m", "Wgtp", "WW", "W1u", "W2u",
+        "WnT", "W1e_eT", "W2eT", "W1m_eT", "W2mT", "W2uT", "WgtpT", "WWT", "W1uT",
+        "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")]
+
+
+class LayerActs(C.Structure):
+    _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
+                                 "h3", "out", "out_relu")]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [("d_out", P), ("d_e_new", P), ("mask_dx", I), ("mask_de", I)] + [(n, P) for n in (
+        "dx", "de", "dh3", "dxu", "dan", "dyn", "dgtp", "dm", "dh2", "de_tot", "dh1", "dP", "ysum",
+        "split_ws", "colsum_ws", "gtp_bias_tmp",
+        "g_mlp0_w", "g_mlp0_b", "g_mlp2_w", "g_mlp2_b", "g_upd0_w", "g_upd0_b", "g_upd2_w", "g_upd2_b",
+        "g_edge0_w", "g_edge0_b", "g_edge2_w", "g_edge2_b",
+        "g_att_g_w", "g_att_g_b", "g_att_theta_w", "g_att_theta_b", "g_att_phi_w", "g_att_phi_b",
+        "g_att_W_w", "g_att_W_b")]
+
+
+# name -> (restype, argtypes); every symbol include/rpg.h declares
+SIGNATURES = {
+    "rpg_last_error_string": (C.c_char_p, []),
+    "rpg_version": (I, []),
+    "rpg_device_sm_count": (I, [I, C.POINTER(I)]),
+    "rpg_validate_edge_index": (I, [P, I64, I, I, I, P, P, P, P]),
+    "rpg_gemm": (I, [C.POINTER(Gemm), P]),
+    "rpg_wgrad": (I, [P, I, I, P, I, I, I64, P, P, I, P]),
+    "rpg_struct_sizes": (None, [C.POINTER(C.c_int32)]),
+    "rpg_reduce_splits": (I, [P, I, I64, I, I, P, I, I, P]),
+    "rpg_pack_weight": (I, [P, I, I, I, I, I, P, I, I, P]),
+    "rpg_cast_f32_to_bf16": (I, [P, P, I64, P]),
+    "rpg_cast_bf16_to_f32": (I, [P, P, I64, P]),
+    "rpg_attention_fwd": (I, [P, I64, I, P, I, P]),
+    "rpg_attention_bwd": (I, [P, P, I, C.POINTER(Graph), I64, I, P, I, P]),
+    "rpg_aggregate_mean": (I, [P, I, C.POINTER(Graph), I, P, I, P]),
+    "rpg_edge_to_node_sum": (I, [P, I, C.POINTER(Graph), I, I, P, I, P]),
+    "rpg_segment_sum": (I, [P, I, P, I, P, P, P, C.POINTER(Graph), I, P, I, P]),
+    "rpg_edge_init_fwd": (I, [P, I, P, C.POINTER(Graph), I, P, I, P]),
+    "rpg_dropout_mask": (I, [U64, F, I64, I, P, P]),
+    "rpg_head_fwd": (I, [P, I, I64, I, P, U64, F, P, P, P, P]),
+    "rpg_head_bwd_ws_floats": (I64, [I64, I]),
+    "rpg_head_bwd": (I, [P, P, I, I64, I, P, U64, F, P, I, P, I, P, P, I, P, P]),
+    "rpg_pose_loss_ws_floats": (I64, [I64]),
+    "rpg_pose_loss": (I, [P, P, C.POINTER(Graph), I64, P, P, P, P, P, P]),
+    "rpg_colsum_bf16": (I, [P, I, I64, I, P, I, P, I, P, P]),
+    "rpg_colsum_scratch_floats": (I64, [I64, I]),
+    "rpg_layer_fwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs), P]),
+    "rpg_layer_bwd_ws_floats": (I64, [I, I64, I64]),
+    "rpg_layer_bwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs),
+                          C.POINTER(LayerGrads), P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _check_layout(lib):
+    probe = (C.c_int32 * 8)()
+    lib.rpg_struct_sizes(probe)
+    want = [C.sizeof(Graph), C.sizeof(Gemm), C.sizeof(LayerWeights), C.sizeof(LayerActs), C.sizeof(LayerGrads),
+            Gemm.out_f32.offset, LayerGrads.g_mlp0_w.offset, LayerWeights.b1e.offset]
+    if list(probe) != want:
+        raise RpgError(f"ctypes mirrors out of sync with include/rpg.h: library {list(probe)} vs python {want}")
+
+
+def load(build_if_missing=True):
+    """Returns the loaded library; raises RpgError if it is missing (no CPU/PyTorch fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) and build_if_missing:
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise RpgError(f"{LIB_PATH} is missing: build it with `python -m relpose_gnn_b200.build` "
+                           "(the CUDA extension is the only implementation; there is no fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _check_layout(lib)
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().rpg_last_error_string().decode(errors="replace")
+        kind = "argument error" if rc < 0 else "CUDA error"
+        raise RpgError(f"{what}: {kind} {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,732 @@
+// Bandwidth-bound kernels of the RelPose-GNN path: graph validation, weight packing, channel attention
+// (MUFU-bound), deterministic segment reductions over the per-graph edge template, edge-feature initialiser,
+// dropout + pose heads, pose loss, column sums.  All accesses are 16-byte vectorised and coalesced along the
+// feature dimension; no atomics on floating-point data (fixed summation order => bitwise reproducible).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/rpg.h"
+#include "rpg_internal.h"
+#include "rpg_ptx.cuh"
+
+namespace rpg {
+
+typedef __nv_bfloat16 bf16;
+
+static inline int grid_for(long long work, int block, int cap = 148 * 16) {
+    long long g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    return (int)(g > cap ? cap : g);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge_index validation (replaces PyG's generic gather/scatter indexing with an implicit template)
+// ------------------------------------------------------------------------------------------------
+__global__ void validate_edge_index_kernel(const long long* __restrict__ ei, long long Et, int G, int N, int Ep,
+                                           int* __restrict__ tsrc, int* __restrict__ tdst, int* __restrict__ bad) {
+    int local_bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Et; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i / Ep;
+        const int k = (int)(i - g * Ep);
+        const long long s = ei[i], d = ei[Et + i];
+        const long long ts = ei[k], td = ei[Et + k];
+        if (ts < 0 || ts >= N || td < 0 || td >= N || s != ts + g * N || d != td + g * N) ++local_bad;
+        if (g == 0) { tsrc[k] = (int)ts; tdst[k] = (int)td; }
+    }
+    if (local_bad) atomicAdd(bad, local_bad);   // integer atomic: result is order-independent
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights / casts
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ src, int ld_src, int r0, int c0, int rows, int cols,
+                                   bf16* __restrict__ dst, int ld_dst, int transpose) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // bx: column block, by: row block (source window coords)
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = by + j, c = bx + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)(r0 + r) * ld_src + c0 + c] : 0.f;
+    }
+    __syncthreads();
+    if (!transpose) {
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int r = by + j, c = bx + threadIdx.x;
+            if (r < rows && c < cols) dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(tile[j][threadIdx.x]);
+        }
+    } else {
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int c = bx + j, r = by + threadIdx.x;     // dst[c, r]
+            if (r < rows && c < cols) dst[(size_t)c * ld_dst + r] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+        }
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 8;
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+        if (i + 8 <= n) {
+            const float4 a = *reinterpret_cast<const float4*>(src + i);
+            const float4 b = *reinterpret_cast<const float4*>(src + i + 4);
+            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            *reinterpret_cast<uint4*>(dst + i) = pack8(f);
+        } else {
+            for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+        }
+    }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 8;
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+        if (i + 8 <= n) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(src + i), f);
+            *reinterpret_cast<float4*>(dst + i) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+            for (long long j = i; j < n; ++j) dst[j] = __bfloat162float(src[j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Channel attention (att.py:25-30).  Logits are rank-1 (phi_i * theta_j), so the row maximum is
+// phi_i * max_j(theta) or phi_i * min_j(theta): no c x c tensor is ever stored.  One warp per edge row.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_WARPS = 8;
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int C_MAX>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy) {
+    __shared__ __align__(16) float s_g[ATT_WARPS][C_MAX];
+    __shared__ __align__(16) float s_t[ATT_WARPS][C_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sg = s_g[warp];
+    float* st = s_t[warp];
+    for (long long row = blockIdx.x * (long long)ATT_WARPS + warp; row < Et; row += (long long)gridDim.x * ATT_WARPS) {
+        const float* r = gtp + row * 3 * c;
+        float tmax = -INFINITY, tmin = INFINITY;
+        for (int j = lane; j < c; j += 32) {
+            const float g = r[j], t = r[c + j];
+            sg[j] = g; st[j] = t;
+            tmax = fmaxf(tmax, t); tmin = fminf(tmin, t);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        }
+        __syncwarp();
+        for (int i0 = 2 * lane; i0 < c; i0 += 64) {
+            const float2 ph = *reinterpret_cast<const float2*>(r + 2 * c + i0);
+            const float p0 = ph.x * LOG2E, p1 = ph.y * LOG2E;
+            const float m0 = p0 >= 0.f ? p0 * tmax : p0 * tmin;
+            const float m1 = p1 >= 0.f ? p1 * tmax : p1 * tmin;
+            float num0 = 0.f, den0 = 0.f, num1 = 0.f, den1 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < c; j += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(st + j);
+                const float4 g4 = *reinterpret_cast<const float4*>(sg + j);
+                const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+                const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float e0 = exp2f(fmaf(p0, tt[q], -m0));
+                    const float e1 = exp2f(fmaf(p1, tt[q], -m1));
+                    num0 = fmaf(e0, gg[q], num0); den0 += e0;
+                    num1 = fmaf(e1, gg[q], num1); den1 += e1;
+                }
+            }
+            *reinterpret_cast<uint32_t*>(y + row * ldy + i0) = pack_bf16x2(num0 / den0, num1 / den1);
+        }
+        __syncwarp();
+    }
+}
+
+// Backward.  Pass 1 (lane owns i): p_ij = exp(phi_i theta_j - max_i) -> smem, den_i, y_i, and
+//   dphi_i = dy_i (sum_j p_ij g_j theta_j - y_i sum_j p_ij theta_j) / den_i.
+// Pass 2 (lane owns j): with w_i = dy_i / den_i:  dg_j = sum_i w_i p_ij,
+//   dtheta_j = g_j sum_i w_i phi_i p_ij - sum_i w_i y_i phi_i p_ij.      c^2 exps, same as forward.
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dyn, int ld_dyn,
+                     const int* __restrict__ tdst, int Ep, int Nn, long long Et, int c, int warps,
+                     bf16* __restrict__ dgtp, int ld_dgtp) {
+    extern __shared__ __align__(16) float att_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= warps) return;
+    const int pitch = c + 1;
+    float* base = att_smem + (size_t)warp * (c * pitch + 6 * c);
+    float* P = base;                       // [c][c+1]
+    float* sg = base + c * pitch;          // g_j
+    float* st = sg + c;                    // theta_j
+    float* sw = st + c;                    // w_i
+    float* swp = sw + c;                   // w_i * phi_i
+    float* swyp = swp + c;                 // w_i * y_i * phi_i
+    float* sdy = swyp + c;                 // dy_i
+    for (long long row = blockIdx.x * (long long)warps + warp; row < Et; row += (long long)gridDim.x * warps) {
+        const float* r = gtp + row * 3 * c;
+        const long long gi = row / Ep;
+        const int k = (int)(row - gi * Ep);
+        const float* dy = dyn + (gi * Nn + __ldg(tdst + k)) * ld_dyn;
+        float tmax = -INFINITY, tmin = INFINITY;
+        for (int j = lane; j < c; j += 32) {
+            const float g = r[j], t = r[c + j];
+            sg[j] = g; st[j] = t; sdy[j] = dy[j];
+            tmax = fmaxf(tmax, t); tmin = fminf(tmin, t);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+            tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        }
+        __syncwarp();
+        for (int i = lane; i < c; i += 32) {
+            const float phi = r[2 * c + i];
+            const float p = phi * LOG2E;
+            const float m = p >= 0.f ? p * tmax : p * tmin;
+            float num = 0.f, den = 0.f, agt = 0.f, at = 0.f;
+            float* Pi = P + i * pitch;
+            for (int j = 0; j < c; ++j) {
+                const float e = exp2f(fmaf(p, st[j], -m));
+                Pi[j] = e;
+                den += e;
+                num = fmaf(e, sg[j], num);
+                at = fmaf(e, st[j], at);
+                agt = fmaf(e * sg[j], st[j], agt);
+            }
+            const float inv = 1.f / den;
+            const float yi = num * inv;
+            const float w = sdy[i] * inv;
+            sw[i] = w; swp[i] = w * phi; swyp[i] = w * yi * phi;
+            dgtp[row * ld_dgtp + 2 * c + i] = __float2bfloat16_rn(w * (agt - yi * at));   // dphi_i
+        }
+        __syncwarp();
+        for (int j = lane; j < c; j += 32) {
+            float dg = 0.f, t1 = 0.f, t2 = 0.f;
+            for (int i = 0; i < c; ++i) {
+                const float pij = P[i * pitch + j];
+                dg = fmaf(sw[i], pij, dg);
+                t1 = fmaf(swp[i], pij, t1);
+                t2 = fmaf(swyp[i], pij, t2);
+            }
+            dgtp[row * ld_dgtp + j] = __float2bfloat16_rn(dg);
+            dgtp[row * ld_dgtp + c + j] = __float2bfloat16_rn(sg[j] * t1 - t2);            // dtheta_j
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segment reductions over the per-graph template (mean aggregation, dgrad scatters): gather formulation,
+// fixed order, one thread per 8 feature columns.
+//   out[g*N+n, c] = scale[n] * sum_{k in csr(n)} v[g*Ep+k, c] * (mask ? mask[g*Ep+k, c] > 0 : 1)
+// ------------------------------------------------------------------------------------------------
+__global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf16* __restrict__ mask, int ldm,
+                                   const int* __restrict__ ptr, const int* __restrict__ idx,
+                                   const float* __restrict__ scale, long long Nt, int N, int Ep, int D,
+                                   bf16* __restrict__ out, int ldo) {
+    const int tpr = D >> 3;                                   // threads per row
+    const long long total = Nt * tpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / tpr;
+        const int c = (int)(t - row * tpr) << 3;
+        const long long g = row / N;
+        const int n = (int)(row - g * N);
+        const int k0 = __ldg(ptr + n), k1 = __ldg(ptr + n + 1);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int kk = k0; kk < k1; ++kk) {
+            const long long er = g * Ep + __ldg(idx + kk);
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(v + er * ldv + c)), f);
+            if (mask) {
+                float mf[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(mask + er * ldm + c)), mf);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (!(mf[q] > 0.f)) f[q] = 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+        }
+        if (scale) {
+            const float s = __ldg(scale + n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] *= s;
+        }
+        *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(acc);
+    }
+}
+
+// e0 = relu(pmin[node(min(s,t))] + pmax[node(max(s,t))] + bias)      (posenet.py:1014-1017, 1053-1055)
+__global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, const float* __restrict__ bias,
+                                     const int* __restrict__ tsrc, const int* __restrict__ tdst, long long Et, int N,
+                                     int Ep, int D, bf16* __restrict__ e0, int lde) {
+    const int tpr = D >> 3;
+    const long long total = Et * tpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / tpr;
+        const int c = (int)(t - row * tpr) << 3;
+        const long long g = row / Ep;
+        const int k = (int)(row - g * Ep);
+        const int s = __ldg(tsrc + k), d = __ldg(tdst + k);
+        const long long nlo = g * N + min(s, d), nhi = g * N + max(s, d);
+        float a[8], b[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pmm + nlo * ldp + c)), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pmm + nhi * ldp + D + c)), b);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = fmaxf(a[q] + b[q] + bb[q], 0.f);
+        *reinterpret_cast<uint4*>(e0 + row * lde + c) = pack8(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dropout keep decision: explicit uint8 mask (parity tests) or a counter-based hash of (seed,row,col)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {   // lowbias32 finaliser
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ bool keep_from_seed(unsigned long long seed, long long row, int col, uint32_t thresh) {
+    const uint32_t h = mix32(mix32((uint32_t)seed ^ (uint32_t)(row * 0x9E3779B1ull)) ^ (uint32_t)(seed >> 32) ^
+                             (uint32_t)col * 0x85EBCA77u ^ (uint32_t)(row >> 32));
+    return h >= thresh;        // P(drop) = thresh / 2^32
+}
+
+__global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long rows, int D,
+                                    uint8_t* __restrict__ keep) {
+    const long long total = rows * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / D;
+        keep[i] = keep_from_seed(seed, r, (int)(i - r * D), thresh) ? 1 : 0;
+    }
+}
+
+// pose[r, j] = sum_c drop(feat[r, c]) * w6[j, c] + b6[j]   (posenet.py:1073-1086).  One warp per row.
+constexpr int HEAD_WARPS = 8;
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, const uint8_t* __restrict__ keep,
+                unsigned long long seed, uint32_t thresh, int use_seed, float scale, const float* __restrict__ w6,
+                const float* __restrict__ b6, float* __restrict__ pose) {
+    extern __shared__ __align__(16) float s_w[];   // [6][D]
+    for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) s_w[i] = w6[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long row = blockIdx.x * (long long)HEAD_WARPS + warp; row < rows; row += (long long)gridDim.x * HEAD_WARPS) {
+        float acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = lane * 8; c < D; c += 256) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
+            if (keep) {
+                const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
+                const uint32_t kw[2] = {k8.x, k8.y};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? f[q] * scale : 0.f;
+            } else if (use_seed) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] = keep_from_seed(seed, row, c + q, thresh) ? f[q] * scale : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + j * D + c);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + j * D + c + 4);
+                acc[j] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                          f[6] * w1.z + f[7] * w1.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        }
+        if (lane < 6) {
+            float v = acc[0];
+            if (lane == 1) v = acc[1]; else if (lane == 2) v = acc[2]; else if (lane == 3) v = acc[3];
+            else if (lane == 4) v = acc[4]; else if (lane == 5) v = acc[5];
+            pose[row * 6 + lane] = v + b6[lane];
+        }
+    }
+}
+
+// Backward of the head.  Thread owns 8 columns; a block walks a contiguous row range, accumulating
+// dW6[j, c] = sum_r dpose[r, j] * drop(feat)[r, c] in registers (deterministic), partials per block.
+constexpr int HEADB_ROWS_PER_BLOCK = 256;
+__global__ void head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, int ldf, long long rows,
+                                int D, const uint8_t* __restrict__ keep, unsigned long long seed, uint32_t thresh,
+                                int use_seed, float scale, const float* __restrict__ w6, int mask_relu,
+                                bf16* __restrict__ dfeat, int lddf, float* __restrict__ dw6_part,
+                                float* __restrict__ db6_part) {
+    const int c = threadIdx.x * 8;
+    if (c >= D) return;
+    float w[6][8];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w6 + j * D + c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w6 + j * D + c + 4));
+        w[j][0] = w0.x; w[j][1] = w0.y; w[j][2] = w0.z; w[j][3] = w0.w;
+        w[j][4] = w1.x; w[j][5] = w1.y; w[j][6] = w1.z; w[j][7] = w1.w;
+    }
+    float gw[6][8];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gw[j][q] = 0.f;
+    float gb[6] = {0, 0, 0, 0, 0, 0};
+    const long long r0 = (long long)blockIdx.x * HEADB_ROWS_PER_BLOCK;
+    const long long r1 = min(r0 + HEADB_ROWS_PER_BLOCK, rows);
+    for (long long row = r0; row < r1; ++row) {
+        float dp[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dp[j] = __ldg(dpose + row * 6 + j);
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
+        float km[8];
+        if (keep) {
+            const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
+            const uint32_t kw[2] = {k8.x, k8.y};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) km[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? scale : 0.f;
+        } else if (use_seed) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) km[q] = keep_from_seed(seed, row, c + q, thresh) ? scale : 0.f;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) km[q] = 1.f;
+        }
+        float d[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s = fmaf(dp[j], w[j][q], s);
+            d[q] = s * km[q];
+            if (mask_relu && !(f[q] > 0.f)) d[q] = 0.f;
+            const float fd = f[q] * km[q];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) gw[j][q] = fmaf(dp[j], fd, gw[j][q]);
+        }
+        if (dfeat) *reinterpret_cast<uint4*>(dfeat + row * lddf + c) = pack8(d);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) gb[j] += dp[j];
+        }
+    }
+    float* o = dw6_part + (size_t)blockIdx.x * 6 * D;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        *reinterpret_cast<float4*>(o + j * D + c) = make_float4(gw[j][0], gw[j][1], gw[j][2], gw[j][3]);
+        *reinterpret_cast<float4*>(o + j * D + c + 4) = make_float4(gw[j][4], gw[j][5], gw[j][6], gw[j][7]);
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) db6_part[blockIdx.x * 6 + j] = gb[j];
+    }
+}
+
+// out[i] (+)= sum_b part[b, i]
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, long long stride, long long n,
+                                       float* __restrict__ out, int accumulate) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < nparts; ++b) s += part[(size_t)b * stride + i];
+        out[i] = accumulate ? out[i] + s : s;
+    }
+}
+// 2-D variant for strided outputs: out[r*ldo + c] (+)= sum_s part[s*stride + r*cols + c]
+__global__ void reduce_splits_kernel(const float* __restrict__ part, int splits, long long stride, int rows, int cols,
+                                     float* __restrict__ out, int ldo, int accumulate) {
+    const long long n = (long long)rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+        float s = 0.f;
+        for (int b = 0; b < splits; ++b) s += part[(size_t)b * stride + i];
+        float* o = out + (size_t)r * ldo + c;
+        *o = accumulate ? *o + s : s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_RP (posenet.py:1021-1031) + L1 sums of PoseNetCriterion (criterion.py:51-52) + sign gradient
+// ------------------------------------------------------------------------------------------------
+constexpr int LOSS_THREADS = 256;
+__global__ void __launch_bounds__(LOSS_THREADS)
+pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses, const int* __restrict__ tsrc,
+                 const int* __restrict__ tdst, long long Et, int N, int Ep, const float* __restrict__ grad_scale,
+                 float* __restrict__ target, float* __restrict__ dpred, float* __restrict__ partial) {
+    float st = 0.f, sq = 0.f;
+    const float gs_t = grad_scale ? grad_scale[0] : 1.f, gs_q = grad_scale ? grad_scale[1] : 1.f;
+    for (long long e = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; e < Et; e += (long long)gridDim.x * LOSS_THREADS) {
+        const long long g = e / Ep;
+        const int k = (int)(e - g * Ep);
+        const float* ps = poses + (g * N + __ldg(tsrc + k)) * 6;
+        const float* pd = poses + (g * N + __ldg(tdst + k)) * 6;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float t = ps[j] - pd[j];
+            const float diff = pred[e * 6 + j] - t;
+            if (target) target[e * 6 + j] = t;
+            if (j < 3) st += fabsf(diff); else sq += fabsf(diff);
+            if (dpred) dpred[e * 6 + j] = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * (j < 3 ? gs_t : gs_q);
+        }
+    }
+    __shared__ float s_t[LOSS_THREADS / 32], s_q[LOSS_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        st += __shfl_xor_sync(0xffffffffu, st, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_t[threadIdx.x >> 5] = st; s_q[threadIdx.x >> 5] = sq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < LOSS_THREADS / 32; ++i) { a += s_t[i]; b += s_q[i]; }
+        partial[blockIdx.x * 2] = a;
+        partial[blockIdx.x * 2 + 1] = b;
+    }
+}
+__global__ void pose_loss_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ sums) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < nblocks; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+        sums[0] = a; sums[1] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums of a bf16 matrix (bias gradients): stage 1 per row-slab, stage 2 over slabs.
+// ------------------------------------------------------------------------------------------------
+constexpr int COLSUM_ROWS = 512;
+__global__ void colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int cols,
+                                     const float* __restrict__ row_w, int row_w_mod, float* __restrict__ part) {
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+    if (c >= cols) return;
+    const long long r0 = (long long)blockIdx.x * COLSUM_ROWS, r1 = min(r0 + COLSUM_ROWS, rows);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long r = r0; r < r1; ++r) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v + r * ldv + c)), f);
+        const float wgt = row_w ? __ldg(row_w + (r % row_w_mod)) : 1.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(wgt, f[q], acc[q]);
+    }
+    float* o = part + (size_t)blockIdx.x * cols + c;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+}  // namespace rpg
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace rpg;
+
+extern "C" {
+
+int rpg_validate_edge_index(const int64_t* edge_index, int64_t Et, int G, int N, int Ep, int32_t* tmpl_src,
+                            int32_t* tmpl_dst, int32_t* bad_count, rpg_stream_t stream) {
+    if (!edge_index || !tmpl_src || !tmpl_dst || !bad_count) return set_error(RPG_E_ARG, "validate: null pointer");
+    if (G <= 0 || N <= 0 || Ep <= 0 || Et != (int64_t)G * Ep) return set_error(RPG_E_GRAPH, "validate: Et != G * Ep");
+    cudaStream_t s = as_stream(stream);
+    cudaMemsetAsync(bad_count, 0, sizeof(int32_t), s);
+    validate_edge_index_kernel<<<grid_for(Et, 256), 256, 0, s>>>(reinterpret_cast<const long long*>(edge_index), Et, G, N,
+                                                                  Ep, tmpl_src, tmpl_dst, bad_count);
+    return check_launch("validate_edge_index_kernel");
+}
+
+int rpg_pack_weight(const float* src, int ld_src, int r0, int c0, int rows, int cols, rpg_bf16* dst, int ld_dst,
+                    int transpose, rpg_stream_t stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "pack_weight: bad arguments");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    pack_weight_kernel<<<grid, block, 0, as_stream(stream)>>>(src, ld_src, r0, c0, rows, cols,
+                                                              reinterpret_cast<bf16*>(dst), ld_dst, transpose);
+    return check_launch("pack_weight_kernel");
+}
+
+int rpg_cast_f32_to_bf16(const float* src, rpg_bf16* dst, int64_t n, rpg_stream_t stream) {
+    if (!src || !dst || n < 0) return set_error(RPG_E_ARG, "cast: bad arguments");
+    if (n == 0) return 0;
+    cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+    return check_launch("cast_f32_bf16_kernel");
+}
+int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_t stream) {
+    if (!src || !dst || n < 0) return set_error(RPG_E_ARG, "cast: bad arguments");
+    if (n == 0) return 0;
+    cast_bf16_f32_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n);
+    return check_launch("cast_bf16_f32_kernel");
+}
+
+int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_stream_t stream) {
+    if (!gtp || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd: bad arguments");
+    if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
+    const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
+    attention_fwd_kernel<256><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy);
+    return check_launch("attention_fwd_kernel");
+}
+
+int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
+                      rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream) {
+    if (!gtp || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd: bad arguments");
+    const size_t per_warp = ((size_t)c * (c + 1) + 6 * (size_t)c) * sizeof(float);
+    int warps = (int)((200 * 1024) / per_warp);
+    if (warps > ATT_WARPS) warps = ATT_WARPS;
+    if (warps < 1) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c too large for the shared-memory formulation");
+    const size_t smem = per_warp * warps;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int grid = grid_for(Et, warps, 148 * 4);
+    attention_bwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
+                                                                           Et, c, warps, reinterpret_cast<bf16*>(dgtp), ld_dgtp);
+    return check_launch("attention_bwd_kernel");
+}
+
+static int launch_segment(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, const int32_t* ptr, const int32_t* idx,
+                          const float* scale, const rpg_graph_t* g, int D, rpg_bf16* out, int ldo, cudaStream_t s) {
+    if (!v || !g || !out || !ptr || !idx || D % 8 || ldv % 8 || ldo % 8) return set_error(RPG_E_ARG, "segment_sum: bad arguments");
+    const long long Nt = (long long)g->G * g->N;
+    segment_sum_kernel<<<grid_for(Nt * (D / 8), 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv,
+                                                                  reinterpret_cast<const bf16*>(mask), ldm, ptr, idx, scale,
+                                                                  Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out), ldo);
+    return check_launch("segment_sum_kernel");
+}
+
+int rpg_aggregate_mean(const rpg_bf16* z, int ldz, const rpg_graph_t* graph, int D, rpg_bf16* a, int lda,
+                       rpg_stream_t stream) {
+    if (!graph) return set_error(RPG_E_ARG, "aggregate_mean: null graph");
+    return launch_segment(z, ldz, nullptr, 0, graph->in_ptr, graph->in_idx, graph->inv_deg, graph, D, a, lda, as_stream(stream));
+}
+
+int rpg_edge_to_node_sum(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, int D, int by_src, rpg_bf16* out, int ldo,
+                         rpg_stream_t stream) {
+    if (!graph) return set_error(RPG_E_ARG, "edge_to_node_sum: null graph");
+    return launch_segment(v, ldv, nullptr, 0, by_src ? graph->out_ptr : graph->in_ptr, by_src ? graph->out_idx : graph->in_idx,
+                          nullptr, graph, D, out, ldo, as_stream(stream));
+}
+
+int rpg_segment_sum(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, const int32_t* csr_ptr, const int32_t* csr_idx,
+                    const float* scale, const rpg_graph_t* graph, int D, rpg_bf16* out, int ldo, rpg_stream_t stream) {
+    return launch_segment(v, ldv, mask, ldm, csr_ptr, csr_idx, scale, graph, D, out, ldo, as_stream(stream));
+}
+
+int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e0,
+                      int lde, rpg_stream_t stream) {
+    if (!pminmax || !bias || !graph || !e0 || D % 8 || ldp % 8 || lde % 8) return set_error(RPG_E_ARG, "edge_init_fwd: bad arguments");
+    const long long Et = (long long)graph->G * graph->Ep;
+    edge_init_fwd_kernel<<<grid_for(Et * (D / 8), 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const bf16*>(pminmax), ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D,
+        reinterpret_cast<bf16*>(e0), lde);
+    return check_launch("edge_init_fwd_kernel");
+}
+
+int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream) {
+    if (!keep || rows <= 0 || D <= 0 || p_drop < 0.f || p_drop >= 1.f) return set_error(RPG_E_ARG, "dropout_mask: bad arguments");
+    const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
+    dropout_mask_kernel<<<grid_for(rows * D, 256), 256, 0, as_stream(stream)>>>(seed, thresh, rows, D, keep);
+    return check_launch("dropout_mask_kernel");
+}
+
+int rpg_head_fwd(const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed, float p_drop,
+                 const float* w6, const float* b6, float* pose, rpg_stream_t stream) {
+    if (!feat || !w6 || !b6 || !pose || rows <= 0 || D % 8 || ldf % 8) return set_error(RPG_E_ARG, "head_fwd: bad arguments");
+    const size_t smem = (size_t)6 * D * sizeof(float);
+    if (smem > 48 * 1024) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+    }
+    const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
+    const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
+    const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
+    head_fwd_kernel<<<grid_for(rows, HEAD_WARPS, 148 * 8), HEAD_WARPS * 32, smem, as_stream(stream)>>>(
+        reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose);
+    return check_launch("head_fwd_kernel");
+}
+
+int64_t rpg_head_bwd_ws_floats(int64_t rows, int D) {
+    const int64_t blocks = (rows + HEADB_ROWS_PER_BLOCK - 1) / HEADB_ROWS_PER_BLOCK;
+    return blocks * (6 * (int64_t)D + 6);
+}
+
+int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed,
+                 float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf, float* dw6, float* db6,
+                 int accumulate, float* ws, rpg_stream_t stream) {
+    if (!dpose || !feat || !w6 || !dw6 || !db6 || !ws || rows <= 0 || D % 8 || ldf % 8 || D > 8 * 1024)
+        return set_error(RPG_E_ARG, "head_bwd: bad arguments");
+    const int blocks = (int)((rows + HEADB_ROWS_PER_BLOCK - 1) / HEADB_ROWS_PER_BLOCK);
+    float* dw_part = ws;
+    float* db_part = ws + (size_t)blocks * 6 * D;
+    const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
+    const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
+    const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
+    const int threads = ((D / 8 + 31) / 32) * 32;
+    cudaStream_t s = as_stream(stream);
+    head_bwd_kernel<<<blocks, threads, 0, s>>>(dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh,
+                                               use_seed, scale, w6, mask_relu, reinterpret_cast<bf16*>(dfeat), lddf, dw_part,
+                                               db_part);
+    int rc = check_launch("head_bwd_kernel");
+    if (rc) return rc;
+    reduce_partials_kernel<<<grid_for(6 * D, 256), 256, 0, s>>>(dw_part, blocks, 6 * (long long)D, 6 * (long long)D, dw6, accumulate);
+    reduce_partials_kernel<<<1, 32, 0, s>>>(db_part, blocks, 6, 6, db6, accumulate);
+    return check_launch("reduce_partials_kernel");
+}
+
+int64_t rpg_pose_loss_ws_floats(int64_t Et) { return 2 * (int64_t)grid_for(Et, LOSS_THREADS, 1024); }
+
+int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* grad_scale,
+                  float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream) {
+    if (!pred || !poses || !graph || !sums || !ws || Et <= 0) return set_error(RPG_E_ARG, "pose_loss: bad arguments");
+    const int blocks = grid_for(Et, LOSS_THREADS, 1024);
+    cudaStream_t s = as_stream(stream);
+    pose_loss_kernel<<<blocks, LOSS_THREADS, 0, s>>>(pred, poses, graph->src, graph->dst, Et, graph->N, graph->Ep, grad_scale,
+                                                     target, dpred, ws);
+    int rc = check_launch("pose_loss_kernel");
+    if (rc) return rc;
+    pose_loss_final_kernel<<<1, 32, 0, s>>>(ws, blocks, sums);
+    return check_launch("pose_loss_final_kernel");
+}
+
+int64_t rpg_colsum_scratch_floats(int64_t rows, int cols) {
+    return ((rows + COLSUM_ROWS - 1) / COLSUM_ROWS) * (int64_t)cols;
+}
+
+int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod, float* out,
+                    int accumulate, float* scratch, rpg_stream_t stream) {
+    if (!v || !out || !scratch || rows <= 0 || cols % 8 || ldv % 8) return set_error(RPG_E_ARG, "colsum: bad arguments");
+    const int slabs = (int)((rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
+    const int threads = 64;
+    dim3 grid(slabs, (cols / 8 + threads - 1) / threads);
+    cudaStream_t s = as_stream(stream);
+    colsum_stage1_kernel<<<grid, threads, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
+                                                  row_w_mod > 0 ? row_w_mod : 1, scratch);
+    int rc = check_launch("colsum_stage1_kernel");
+    if (rc) return rc;
+    reduce_partials_kernel<<<grid_for(cols, 128), 128, 0, s>>>(scratch, slabs, cols, cols, out, accumulate);
+    return check_launch("reduce_partials_kernel");
+}
+
+int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols, float* out, int ldo,
+                      int accumulate, rpg_stream_t stream) {
+    if (!partial || !out || splits < 1 || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "reduce_splits: bad arguments");
+    reduce_splits_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, as_stream(stream)>>>(partial, splits, split_stride, rows,
+                                                                                              cols, out, ldo, accumulate);
+    return check_launch("reduce_splits_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// Internal declarations shared by the translation units of librpg_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rpg.h"
+
+namespace rpg {
+
+// Records a message for rpg_last_error_string() (thread-local) and returns `code`.
+int set_error(int code, const char* msg);
+// cudaGetLastError() after a launch; returns 0 or the cudaError_t (recorded with the kernel name).
+int check_launch(const char* what);
+
+int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream);
+
+inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace rpg

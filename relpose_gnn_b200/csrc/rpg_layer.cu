@@ -1,0 +1,325 @@
+// Host-side sequencing of one simpleConvEdge_upt call (my_gnn_layer.py:293-311) and its backward over the
+// tcgen05 GEMM and the bandwidth kernels, plus the small C-ABI utilities.  No host synchronisation: every
+// kernel is enqueued on the caller's stream.
+//
+// Concatenated inputs are never materialised.  [x_src | x_dst | e] W^T is evaluated as
+//   P_s[src] + P_d[dst] + e W_e^T   with   [P_s | P_d | P_m] = x [W_s; W_d; W_m]^T   computed once per NODE,
+// which is algebraically identical to the reference formulation and removes the gathers and 40 % of the FLOPs.
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "../../include/rpg.h"
+#include "rpg_internal.h"
+
+namespace rpg {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg ? msg : "");
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+static inline int pad64(int v) { return (v + 63) / 64 * 64; }
+
+// Convenience builder for the NT GEMM  out = epi(A[M,K] * B[N,K]^T)
+static rpg_gemm_t nt(int M, int N, const rpg_bf16* A, int K, int lda, const rpg_bf16* B, int ldb) {
+    rpg_gemm_t g;
+    memset(&g, 0, sizeof g);
+    g.mode = 0; g.M = M; g.N = N; g.n_seg = 1;
+    g.A[0] = A; g.K[0] = K; g.lda[0] = lda; g.B = B; g.ldb = ldb;
+    return g;
+}
+
+// Partial products of dW[M,N] = A[R,M]^T B[R,N] through the split-R TN kernel; returns the split count (> 0)
+// or an error (< 0 / cudaError as negative is impossible, so errors are reported through *rc).
+static int wgrad_partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* ws,
+                          int sm_count, cudaStream_t s, int* splits_out) {
+    rpg_gemm_t g;
+    memset(&g, 0, sizeof g);
+    g.mode = 1; g.M = M; g.N = N; g.A[0] = A; g.lda[0] = lda; g.B = B; g.ldb = ldb; g.R = (int)R;
+    const int block_n = N >= 256 ? 256 : pad64(N);
+    g.block_n = block_n;
+    const int tiles = ((M + 127) / 128) * ((N + block_n - 1) / block_n);
+    const long long kb = (R + 63) / 64;
+    long long splits = (2LL * sm_count + tiles - 1) / tiles;          // ~2 waves of work items
+    if (splits > kb) splits = kb;
+    if (splits < 1) splits = 1;
+    g.splits = (int)splits;
+    g.split_stride = (long long)M * N;
+    g.out_f32 = ws; g.ldo_f32 = N;
+    *splits_out = g.splits;
+    return gemm_launch(&g, s);
+}
+
+// dW[M,N] += A^T B, deterministic (fixed split order).
+static int wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* ws,
+                 float* out, int ldo, int sm_count, cudaStream_t s) {
+    int splits = 0;
+    int rc = wgrad_partials(A, lda, M, B, ldb, N, R, ws, sm_count, s, &splits);
+    if (rc) return rc;
+    return rpg_reduce_splits(ws, splits, (long long)M * N, M, N, out, ldo, /*accumulate=*/1, s);
+}
+
+static int sm_count_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+}  // namespace rpg
+
+using namespace rpg;
+
+extern "C" {
+
+const char* rpg_last_error_string(void) { return g_err; }
+int rpg_version(void) { return 100; }
+
+int rpg_device_sm_count(int device, int* sm_count) {
+    if (!sm_count) return set_error(RPG_E_ARG, "sm_count: null");
+    cudaError_t e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+    return 0;
+}
+
+int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream) { return gemm_launch(g, as_stream(stream)); }
+
+int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R, float* ws, float* out, int ldo,
+              rpg_stream_t stream) {
+    if (!A || !B || !ws || !out) return set_error(RPG_E_ARG, "wgrad: null pointer");
+    return wgrad(A, lda, M, B, ldb, N, R, ws, out, ldo, sm_count_cached(), as_stream(stream));
+}
+
+void rpg_struct_sizes(int32_t* out) {
+    out[0] = (int32_t)sizeof(rpg_graph_t);
+    out[1] = (int32_t)sizeof(rpg_gemm_t);
+    out[2] = (int32_t)sizeof(rpg_layer_weights_t);
+    out[3] = (int32_t)sizeof(rpg_layer_acts_t);
+    out[4] = (int32_t)sizeof(rpg_layer_grads_t);
+    out[5] = (int32_t)offsetof(rpg_gemm_t, out_f32);
+    out[6] = (int32_t)offsetof(rpg_layer_grads_t, g_mlp0_w);
+    out[7] = (int32_t)offsetof(rpg_layer_weights_t, b1e);
+}
+
+#define RPG_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__) return rc__;   \
+    } while (0)
+
+int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg_layer_acts_t* t, rpg_stream_t stream) {
+    if (!w || !gr || !t) return set_error(RPG_E_ARG, "layer_fwd: null argument");
+    const int D = w->D, c = D / 8, c3 = 3 * c;
+    if (D % 128) return set_error(RPG_E_UNSUPPORTED, "layer_fwd: channel count must be a multiple of 128");
+    const long long Nt = (long long)gr->G * gr->N, Et = (long long)gr->G * gr->Ep;
+    if (Nt > 0x7fffffff || Et > 0x7fffffff) return set_error(RPG_E_UNSUPPORTED, "layer_fwd: more than 2^31 rows");
+    cudaStream_t s = as_stream(stream);
+    const int cp = pad64(c);
+    rpg_gemm_t g;
+
+    // (1) per-node projections  P = x [W1e_src; W1e_dst; W1m_src]^T                      [Nt, 3D]
+    g = nt((int)Nt, 3 * D, t->x, D, D, w->Wn, D);
+    g.out = t->P; g.ldo = 3 * D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (2) edge MLP layer 1 (my_gnn_layer.py:232,237-238): h1 = relu(e W1e_e^T + P_s[src] + P_d[dst] + b)
+    g = nt((int)Et, D, t->e, D, D, w->W1e_e, D);
+    g.bias = w->b1e;
+    g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
+    g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = 3 * D;
+    g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
+    g.out = t->h1; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (3) edge MLP layer 2 (my_gnn_layer.py:234): e' = h1 W2e^T + b  (+ relu'd copy for the caller, posenet.py:1065)
+    g = nt((int)Et, D, t->h1, D, D, w->W2e, D);
+    g.bias = w->b2e; g.out = t->e_new; g.out_relu = t->e_new_relu; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (4) message MLP layer 1 (my_gnn_layer.py:280,305): h2 = relu(e' W1m_e^T + P_m[src] + b)   (x_j = source)
+    g = nt((int)Et, D, t->e_new, D, D, w->W1m_e, D);
+    g.bias = w->b1m;
+    g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
+    g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
+    g.out = t->h2; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (5) message MLP layer 2 (my_gnn_layer.py:282): m = h2 W2m^T + b
+    g = nt((int)Et, D, t->h2, D, D, w->W2m, D);
+    g.bias = w->b2m; g.out = t->m; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (6) attention projections (att.py:20-24): (g | theta | phi) = m [Wg; Wtheta; Wphi]^T + b   fp32 [Et, 3c]
+    g = nt((int)Et, c3, t->m, D, D, w->Wgtp, D);
+    g.bias = w->bgtp; g.out_f32 = t->gtp; g.ldo_f32 = c3;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (7) rank-1 softmax attention (att.py:25-30)
+    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, stream));
+
+    // (8) z = y WW^T + bW + m (att.py:32-33)
+    g = nt((int)Et, D, t->y, cp, cp, w->WW, cp);
+    g.bias = w->bW; g.resid = t->m; g.resid_ld = D; g.out = t->z; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // (9) mean over incoming edges (PyG aggregate [3p], my_gnn_layer.py:301)
+    RPG_TRY(rpg_aggregate_mean(t->z, D, gr, D, t->a, D, stream));
+
+    // (10) update MLP (my_gnn_layer.py:284-286,309-311): out = relu([x | a] W1u^T + b) W2u^T + b
+    g = nt((int)Nt, D, t->x, D, D, w->W1u, 2 * D);
+    g.n_seg = 2; g.A[1] = t->a; g.K[1] = D; g.lda[1] = D;
+    g.bias = w->b1u; g.relu = 1; g.out = t->h3; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    g = nt((int)Nt, D, t->h3, D, D, w->W2u, D);
+    g.bias = w->b2u; g.out = t->out; g.out_relu = t->out_relu; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    return 0;
+}
+
+int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt) {
+    (void)Et; (void)Nt;
+    // largest split workspace: (2 * sm_count / tiles + 1) splits of a [D, 3D] partial; bound with 2*148+tiles items
+    // splits * M * N <= 2 * sm_count * (128 * 256) + M * N, with M * N <= 3 D^2; sized for up to 256 SMs
+    return 2LL * 256 * 128 * 256 + 3LL * D * D;
+}
+
+int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg_layer_acts_t* t,
+                  const rpg_layer_grads_t* b, rpg_stream_t stream) {
+    if (!w || !gr || !t || !b) return set_error(RPG_E_ARG, "layer_bwd: null argument");
+    const int D = w->D, c = D / 8, c3 = 3 * c, cp = pad64(c), c3p = pad64(c3);
+    if (D % 128) return set_error(RPG_E_UNSUPPORTED, "layer_bwd: channel count must be a multiple of 128");
+    const long long Nt = (long long)gr->G * gr->N, Et = (long long)gr->G * gr->Ep;
+    cudaStream_t s = as_stream(stream);
+    const int sms = sm_count_cached();
+    rpg_gemm_t g;
+    const bool have_out = b->d_out != nullptr;
+
+    // ---- update MLP backward (only when a gradient reaches `out`)
+    if (have_out) {
+        // dh3 = (d_out W2u) * [h3 > 0]
+        g = nt((int)Nt, D, b->d_out, D, D, w->W2uT, D);
+        g.mask = t->h3; g.mask_ld = D; g.out = b->dh3; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+        // [dx_u | da] = dh3 W1u ; da is scaled by 1/deg (mean backward) -> dan
+        g = nt((int)Nt, D, b->dh3, D, D, w->W1uT, D);
+        g.out = b->dxu; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+        g = nt((int)Nt, D, b->dh3, D, D, w->W1uT + (size_t)D * D, D);
+        g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; g.out = b->dan; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+        // dy per destination node: dyn = dan WW   fp32 [Nt, c]
+        g = nt((int)Nt, c, b->dan, D, D, w->WWT, D);
+        g.out_f32 = b->dyn; g.ldo_f32 = c;
+        RPG_TRY(gemm_launch(&g, s));
+        // attention backward -> dgtp [Et, 3c]
+        RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, stream));
+        // dm = dgtp Wgtp + dan[dst]
+        g = nt((int)Et, D, b->dgtp, c3p, c3p, w->WgtpT, c3p);
+        g.gadd[0] = b->dan; g.gmap[0] = gr->dst; g.gadd_ld[0] = D; g.Ep = gr->Ep; g.Nn = gr->N;
+        g.out = b->dm; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+        // dh2 = (dm W2m) * [h2 > 0]
+        g = nt((int)Et, D, b->dm, D, D, w->W2mT, D);
+        g.mask = t->h2; g.mask_ld = D; g.out = b->dh2; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+        // de'_tot = dh2 W1m_e + d_e_new
+        g = nt((int)Et, D, b->dh2, D, D, w->W1m_eT, D);
+        g.resid = b->d_e_new; g.resid_ld = D; g.out = b->de_tot; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+    }
+    const rpg_bf16* de_tot = have_out ? b->de_tot : b->d_e_new;
+    if (!de_tot) return set_error(RPG_E_ARG, "layer_bwd: neither d_out nor d_e_new given");
+
+    // ---- edge MLP backward
+    // dh1 = (de'_tot W2e) * [h1 > 0]
+    g = nt((int)Et, D, de_tot, D, D, w->W2eT, D);
+    g.mask = t->h1; g.mask_ld = D; g.out = b->dh1; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    // de = dh1 W1e_e  (optionally * [e > 0] for a ReLU'd input)
+    g = nt((int)Et, D, b->dh1, D, D, w->W1e_eT, D);
+    if (b->mask_de) { g.mask = t->e; g.mask_ld = D; }
+    g.out = b->de; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // ---- node side: dP = [sum_src dh1 | sum_dst dh1 | sum_src dh2], dx = dP Wn + dx_u
+    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 1, b->dP, 3 * D, stream));
+    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 0, b->dP + D, 3 * D, stream));
+    if (have_out) {
+        RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 1, b->dP + 2 * D, 3 * D, stream));
+        g = nt((int)Nt, D, b->dP, 3 * D, 3 * D, w->WnT, 3 * D);
+        g.resid = b->dxu; g.resid_ld = D;
+    } else {
+        g = nt((int)Nt, D, b->dP, 2 * D, 3 * D, w->WnT, 3 * D);
+    }
+    if (b->mask_dx) { g.mask = t->x; g.mask_ld = D; }
+    g.out = b->dx; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+
+    // ---- weight gradients (fp32, accumulated into the reference's state_dict layout)
+    float* ws = b->split_ws;
+    int splits = 0;
+    // edge_model.edge_mlp.2: dW = de'_tot^T h1 ; db = colsum(de'_tot)
+    RPG_TRY(wgrad(de_tot, D, D, t->h1, D, D, Et, ws, b->g_edge2_w, D, sms, s));
+    RPG_TRY(rpg_colsum_bf16(de_tot, D, Et, D, nullptr, 0, b->g_edge2_b, 1, b->colsum_ws, stream));
+    // edge_model.edge_mlp.0, edge columns [2D,3D): dW = dh1^T e ; db = colsum(dh1)
+    RPG_TRY(wgrad(b->dh1, D, D, t->e, D, D, Et, ws, b->g_edge0_w + 2 * D, 3 * D, sms, s));
+    RPG_TRY(rpg_colsum_bf16(b->dh1, D, Et, D, nullptr, 0, b->g_edge0_b, 1, b->colsum_ws, stream));
+    // node-side blocks in one launch: dP^T x = [edge_mlp.0[:,0:D]; edge_mlp.0[:,D:2D]; mlp.0[:,0:D]]
+    {
+        const int Mp = have_out ? 3 * D : 2 * D;
+        RPG_TRY(wgrad_partials(b->dP, 3 * D, Mp, t->x, D, D, Nt, ws, sms, s, &splits));
+        const long long stride = (long long)Mp * D;
+        RPG_TRY(rpg_reduce_splits(ws, splits, stride, D, D, b->g_edge0_w, 3 * D, 1, stream));
+        RPG_TRY(rpg_reduce_splits(ws + (size_t)D * D, splits, stride, D, D, b->g_edge0_w + D, 3 * D, 1, stream));
+        if (have_out)
+            RPG_TRY(rpg_reduce_splits(ws + 2 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w, 2 * D, 1, stream));
+    }
+    if (have_out) {
+        // mlp.2: dW = dm^T h2 ; mlp.0 edge columns [D,2D): dW = dh2^T e'
+        RPG_TRY(wgrad(b->dm, D, D, t->h2, D, D, Et, ws, b->g_mlp2_w, D, sms, s));
+        RPG_TRY(rpg_colsum_bf16(b->dm, D, Et, D, nullptr, 0, b->g_mlp2_b, 1, b->colsum_ws, stream));
+        RPG_TRY(wgrad(b->dh2, D, D, t->e_new, D, D, Et, ws, b->g_mlp0_w + D, 2 * D, sms, s));
+        RPG_TRY(rpg_colsum_bf16(b->dh2, D, Et, D, nullptr, 0, b->g_mlp0_b, 1, b->colsum_ws, stream));
+        // att.g / theta / phi: one launch dgtp^T m [3c, D], three reductions ; biases = colsum(dgtp)
+        RPG_TRY(wgrad_partials(b->dgtp, c3p, c3, t->m, D, D, Et, ws, sms, s, &splits));
+        {
+            const long long stride = (long long)c3 * D;
+            RPG_TRY(rpg_reduce_splits(ws, splits, stride, c, D, b->g_att_g_w, D, 1, stream));
+            RPG_TRY(rpg_reduce_splits(ws + (size_t)c * D, splits, stride, c, D, b->g_att_theta_w, D, 1, stream));
+            RPG_TRY(rpg_reduce_splits(ws + 2 * (size_t)c * D, splits, stride, c, D, b->g_att_phi_w, D, 1, stream));
+        }
+        RPG_TRY(rpg_colsum_bf16(b->dgtp, c3p, Et, c3p, nullptr, 0, b->gtp_bias_tmp, 0, b->colsum_ws, stream));
+        RPG_TRY(rpg_reduce_splits(b->gtp_bias_tmp, 1, 0, 1, c, b->g_att_g_b, c, 1, stream));
+        RPG_TRY(rpg_reduce_splits(b->gtp_bias_tmp + c, 1, 0, 1, c, b->g_att_theta_b, c, 1, stream));
+        RPG_TRY(rpg_reduce_splits(b->gtp_bias_tmp + 2 * c, 1, 0, 1, c, b->g_att_phi_b, c, 1, stream));
+        // att.W: dW = sum_e dz[e]^T y[e] = dan^T ysum with ysum[n] = sum_{in-edges(n)} y[e];
+        //        db = sum_e dz[e] = sum_n indeg(n) * dan[n]
+        RPG_TRY(rpg_edge_to_node_sum(t->y, cp, gr, cp, 0, b->ysum, cp, stream));
+        RPG_TRY(wgrad(b->dan, D, D, b->ysum, cp, c, Nt, ws, b->g_att_W_w, c, sms, s));
+        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
+        // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
+        RPG_TRY(wgrad(b->d_out, D, D, t->h3, D, D, Nt, ws, b->g_upd2_w, D, sms, s));
+        RPG_TRY(rpg_colsum_bf16(b->d_out, D, Nt, D, nullptr, 0, b->g_upd2_b, 1, b->colsum_ws, stream));
+        RPG_TRY(wgrad(b->dh3, D, D, t->x, D, D, Nt, ws, b->g_upd0_w, 2 * D, sms, s));
+        RPG_TRY(wgrad(b->dh3, D, D, t->a, D, D, Nt, ws, b->g_upd0_w + D, 2 * D, sms, s));
+        RPG_TRY(rpg_colsum_bf16(b->dh3, D, Nt, D, nullptr, 0, b->g_upd0_b, 1, b->colsum_ws, stream));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Host-side graph structure: the implicit per-graph edge template that replaces PyG's generic
+gather/scatter indexing.
+
+The reference batches G graphs of N nodes PyG-style (train.py:24,132): node row g*N+n, edge row
+g*Ep+k, edge_index[:, g*Ep+k] = template[:, k] + g*N, where the template is the fully connected
+enumeration of dataset_7Scenes_multi.py:377-385,418-422 (dataset_Cambridge_multi.py:240-248,273-278),
+optionally thinned by the batch-shared edge-dropout mask of train.py:238-242.  `GraphBatch` validates
+that property on the device (rpg_validate_edge_index) and holds the small per-template tables
+(CSR by destination / source / min / max endpoint, degrees) the kernels index with.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def fc_template(n_nodes):
+    """Closed form of the reference FC enumeration: forward half by offset d,
+    then the same list with source and destination swapped.  Returns (src, dst) int32 arrays."""
+    src, dst = [], []
+    for d in range(1, n_nodes):
+        s = np.arange(0, n_nodes - d, dtype=np.int32)
+        src.append(s)
+        dst.append(s + d)
+    src = np.concatenate(src) if src else np.zeros(0, np.int32)
+    dst = np.concatenate(dst) if dst else np.zeros(0, np.int32)
+    return np.concatenate([src, dst]), np.concatenate([dst, src])
+
+
+def edge_dropout_keep(n_undirected, rng, keep_factor=0.5):
+    """Batch-shared edge-dropout mask, train.py:238-242: undirected edge u survives iff its uniform draw
+    is < keep_factor; if none survive, all are kept.  `rng` is a numpy RandomState/Generator-like with
+    .random_sample or .random.  Directed rows u and u + n_undirected share bit u."""
+    draws = rng.random_sample(n_undirected) if hasattr(rng, "random_sample") else rng.random(n_undirected)
+    keep = draws < keep_factor
+    if keep.sum() == 0:
+        keep = np.ones_like(keep)
+    return keep.astype(bool)
+
+
+def thin_template(src, dst, keep_undirected):
+    keep = np.concatenate([keep_undirected, keep_undirected])
+    return src[keep], dst[keep]
+
+
+def batched_edge_index(src, dst, n_graphs, n_nodes, device=None):
+    """int64 [2, G*Ep] edge_index of G template copies (what PyG's Batch produces)."""
+    t = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+    if device is not None:
+        t = t.to(device)
+    offs = torch.arange(n_graphs, dtype=torch.long, device=t.device) * n_nodes
+    return (t.unsqueeze(1) + offs.view(1, -1, 1)).reshape(2, -1).contiguous()
+
+
+def _csr(keys, n):
+    order = np.argsort(keys, kind="stable").astype(np.int32)
+    counts = np.bincount(keys, minlength=n)
+    ptr = np.zeros(n + 1, np.int32)
+    ptr[1:] = np.cumsum(counts)
+    return ptr, order
+
+
+class GraphBatch:
+    """G graphs x N nodes sharing one edge template; owns the device tables and the rpg_graph_t struct."""
+
+    _table_cache = {}
+
+    def __init__(self, src, dst, n_graphs, n_nodes, device):
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        dst = np.ascontiguousarray(dst, dtype=np.int32)
+        if src.shape != dst.shape or src.ndim != 1 or src.size == 0:
+            raise ValueError("template must be two equal-length 1-D index arrays with at least one edge")
+        if src.min() < 0 or dst.min() < 0 or src.max() >= n_nodes or dst.max() >= n_nodes:
+            raise ValueError("template node index out of range")
+        self.G, self.N, self.Ep = int(n_graphs), int(n_nodes), int(src.size)
+        self.device = torch.device(device)
+        self.src_np, self.dst_np = src, dst
+        key = (self.N, src.tobytes(), dst.tobytes(), str(self.device))
+        tables = GraphBatch._table_cache.get(key)
+        if tables is None:
+            tables = self._build_tables(src, dst, self.N, self.device)
+            GraphBatch._table_cache[key] = tables
+        self._tables = tables
+        s = _lib.Graph()
+        s.G, s.N, s.Ep = self.G, self.N, self.Ep
+        for name, t in tables.items():
+            setattr(s, name, t.data_ptr())
+        self.struct = s
+
+    @staticmethod
+    def _build_tables(src, dst, n, device):
+        in_ptr, in_idx = _csr(dst, n)
+        out_ptr, out_idx = _csr(src, n)
+        min_ptr, min_idx = _csr(np.minimum(src, dst), n)
+        max_ptr, max_idx = _csr(np.maximum(src, dst), n)
+        deg = np.bincount(dst, minlength=n).astype(np.float32)
+        host = {"src": src, "dst": dst, "in_ptr": in_ptr, "in_idx": in_idx, "out_ptr": out_ptr,
+                "out_idx": out_idx, "inv_deg": (1.0 / np.maximum(deg, 1.0)).astype(np.float32), "deg": deg,
+                "min_ptr": min_ptr, "min_idx": min_idx, "max_ptr": max_ptr, "max_idx": max_idx}
+        return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in host.items()}
+
+    @property
+    def n_node_rows(self):
+        return self.G * self.N
+
+    @property
+    def n_edge_rows(self):
+        return self.G * self.Ep
+
+    def byref(self):
+        return C.byref(self.struct)
+
+    def edge_index(self):
+        return batched_edge_index(self.src_np, self.dst_np, self.G, self.N, self.device)
+
+    def with_graphs(self, n_graphs):
+        return GraphBatch(self.src_np, self.dst_np, n_graphs, self.N, self.device)
+
+    @classmethod
+    def fully_connected(cls, n_graphs, n_nodes, device, keep_undirected=None):
+        src, dst = fc_template(n_nodes)
+        if keep_undirected is not None:
+            src, dst = thin_template(src, dst, np.asarray(keep_undirected, bool))
+        return cls(src, dst, n_graphs, n_nodes, device)
+
+
+def attach(edge_index, graph):
+    """Annotates an edge_index tensor with its (already validated) GraphBatch so that modules skip the
+    device-side validation and its host read-back."""
+    edge_index.rpg_graph = graph
+    edge_index.rpg_graph_version = edge_index._version
+    return edge_index
+
+
+def from_edge_index(edge_index, n_node_rows):
+    """Infers (G, N, Ep), validates on the device that edge_index is a batched uniform template and returns
+    the GraphBatch.  Raises ValueError otherwise (no PyG-scatter fallback).  One small
+    device->host read per distinct edge_index tensor; the result is cached as an attribute of the tensor."""
+    g = getattr(edge_index, "rpg_graph", None)
+    if g is not None and getattr(edge_index, "rpg_graph_version", edge_index._version) == edge_index._version:
+        if g.n_node_rows != n_node_rows or g.n_edge_rows != edge_index.size(1):
+            raise ValueError("attached GraphBatch does not match x / edge_index shapes")
+        return g
+    if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64:
+        raise TypeError("edge_index must be an int64 tensor of shape [2, E]")
+    if not edge_index.is_cuda:
+        raise ValueError("edge_index must live on the CUDA device (no CPU path exists)")
+    if edge_index.size(1) == 0:
+        raise ValueError("empty edge_index: the layer needs at least one edge per graph")
+    ei = edge_index.contiguous()
+    Et = ei.size(1)
+    # Column Ep of a batched template equals column 0 shifted by N on both rows.  Candidates are the columns
+    # with an equal, positive shift on both rows; the first one consistent with (Et, n_node_rows) is validated
+    # in full on the device.
+    d0 = ei[0] - ei[0, 0]
+    d1 = ei[1] - ei[1, 0]
+    cand = ((d0 == d1) & (d0 > 0)).nonzero().flatten()
+    cand_host = torch.stack([cand, d0[cand]]).cpu().numpy() if cand.numel() else np.zeros((2, 0), np.int64)
+    options = []
+    for j, shift in zip(cand_host[0].tolist(), cand_host[1].tolist()):
+        if Et % j == 0 and n_node_rows % (Et // j) == 0 and n_node_rows // (Et // j) == shift:
+            options.append((j, Et // j, shift))
+        if len(options) == 4:
+            break
+    options.append((Et, 1, n_node_rows))          # a single graph
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(ei.device).cuda_stream
+    g, bad = None, None
+    for Ep, G, N in options:
+        buf = torch.empty(2 * Ep + 1, dtype=torch.int32, device=ei.device)
+        _lib.check(lib.rpg_validate_edge_index(ei.data_ptr(), Et, G, N, Ep, buf.data_ptr(), buf[Ep:].data_ptr(),
+                                               buf[2 * Ep:].data_ptr(), stream), "rpg_validate_edge_index")
+        host = buf.cpu().numpy()
+        bad = int(host[2 * Ep])
+        if bad == 0:
+            g = GraphBatch(host[:Ep].copy(), host[Ep:2 * Ep].copy(), G, N, ei.device)
+            break
+    if g is None:
+        raise ValueError("edge_index is not a batch of G copies of one per-graph edge template with node offset "
+                         f"g*N ({bad} violating columns for the last candidate); per-graph edge sets are not "
+                         "supported (no PyG-scatter fallback exists)")
+    edge_index.rpg_graph = g                      # cached on the tensor object itself
+    edge_index.rpg_graph_version = edge_index._version
+    return g

@@ -1,0 +1,282 @@
+"""Drop-in replacement for `niantic.modules.my_gnn_layer.simpleConvEdge_upt` (my_gnn_layer.py:277-311).
+
+Same constructor arguments, same `forward(x, edge_index, edge_attr) -> (out, edge_attr_new)` signature, same
+`state_dict` layout (20 tensors), so a reference checkpoint loads unchanged and the
+module can be assigned to `PoseNetX_R2.gnn1` in place of the torch_geometric layer.  All arithmetic runs
+in hand-written sm_100a kernels behind the C ABI of include/rpg.h; there is no PyG / PyTorch fallback.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+from torch.nn import Linear, ReLU, Sequential as Seq
+
+from . import _lib, graph as graph_mod, ops
+from .ops import BF16, pad64
+
+# order in which parameter gradients are returned (== reference state_dict order)
+PARAM_ORDER = (
+    "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias",
+    "mlp_updating.0.weight", "mlp_updating.0.bias", "mlp_updating.2.weight", "mlp_updating.2.bias",
+    "edge_model.edge_mlp.0.weight", "edge_model.edge_mlp.0.bias",
+    "edge_model.edge_mlp.2.weight", "edge_model.edge_mlp.2.bias",
+    "att.g.weight", "att.g.bias", "att.theta.weight", "att.theta.bias", "att.phi.weight", "att.phi.bias",
+    "att.W.weight", "att.W.bias",
+)
+_GRAD_FIELDS = (
+    "g_mlp0_w", "g_mlp0_b", "g_mlp2_w", "g_mlp2_b", "g_upd0_w", "g_upd0_b", "g_upd2_w", "g_upd2_b",
+    "g_edge0_w", "g_edge0_b", "g_edge2_w", "g_edge2_b",
+    "g_att_g_w", "g_att_g_b", "g_att_theta_w", "g_att_theta_b", "g_att_phi_w", "g_att_phi_b",
+    "g_att_W_w", "g_att_W_b",
+)
+
+
+class simpleEdgeModel(nn.Module):
+    """Parameter container mirroring my_gnn_layer.py:224-239 (keeps the `edge_model.edge_mlp.*` keys)."""
+
+    def __init__(self, in_channels, edge_channels, out_channels):
+        super().__init__()
+        self.in_channels = in_channels
+        self.edge_mlp = Seq(Linear(2 * in_channels + edge_channels, out_channels), ReLU(),
+                            Linear(out_channels, out_channels))
+
+
+class AttentionBlock(nn.Module):
+    """Parameter container mirroring att.py:7-14 (keeps the `att.{g,theta,phi,W}.*` keys)."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.g = Linear(in_channels, in_channels // 8)
+        self.theta = Linear(in_channels, in_channels // 8)
+        self.phi = Linear(in_channels, in_channels // 8)
+        self.W = Linear(in_channels // 8, in_channels)
+
+
+class PackedLayerWeights:
+    """bf16 operand copies of the fp32 master parameters, cut per input source and transposed for dgrad.
+    Re-packed whenever any parameter's version counter changes (optimizer.step() bumps it in place)."""
+
+    def __init__(self, D, device):
+        self.D, self.device = D, device
+        c = D // 8
+        self.c, self.cp, self.c3p = c, pad64(c), pad64(3 * c)
+        shapes = {
+            "Wn": (3 * D, D), "W1e_e": (D, D), "W2e": (D, D), "W1m_e": (D, D), "W2m": (D, D),
+            "Wgtp": (3 * c, D), "WW": (D, self.cp), "W1u": (D, 2 * D), "W2u": (D, D),
+            "WnT": (D, 3 * D), "W1e_eT": (D, D), "W2eT": (D, D), "W1m_eT": (D, D), "W2mT": (D, D), "W2uT": (D, D),
+            "WgtpT": (D, self.c3p), "WWT": (c, D), "W1uT": (2 * D, D),
+        }
+        total = sum(r * k for r, k in shapes.values())
+        self.flat = torch.zeros(total, dtype=BF16, device=device)     # zero padding columns stay zero
+        self.t = {}
+        off = 0
+        for name, (r, k) in shapes.items():
+            self.t[name] = self.flat[off:off + r * k].view(r, k)
+            off += r * k
+        self.bgtp = torch.zeros(3 * c, dtype=torch.float32, device=device)
+        self.versions = None
+        self.struct = _lib.LayerWeights()
+
+    def refresh(self, mod):
+        p = {n: mod.get_parameter(n) for n in PARAM_ORDER}
+        versions = tuple((q.data_ptr(), q._version) for q in p.values())
+        if versions == self.versions:
+            return self.struct
+        for q in p.values():
+            if q.dtype != torch.float32 or not q.is_cuda or not q.is_contiguous():
+                raise TypeError("layer parameters must be contiguous float32 CUDA tensors (fp32 master weights)")
+        D, c, t = self.D, self.c, self.t
+        W1e, W1m, W1u = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data, p["mlp_updating.0.weight"].data
+        W2e, W2m, W2u = p["edge_model.edge_mlp.2.weight"].data, p["mlp.2.weight"].data, p["mlp_updating.2.weight"].data
+        pk = ops.pack_weight
+        # forward operands
+        pk(W1e, t["Wn"][0:D], c0=0, cols=D)
+        pk(W1e, t["Wn"][D:2 * D], c0=D, cols=D)
+        pk(W1m, t["Wn"][2 * D:3 * D], c0=0, cols=D)
+        pk(W1e, t["W1e_e"], c0=2 * D, cols=D)
+        pk(W2e, t["W2e"])
+        pk(W1m, t["W1m_e"], c0=D, cols=D)
+        pk(W2m, t["W2m"])
+        for i, nm in enumerate(("g", "theta", "phi")):
+            pk(p[f"att.{nm}.weight"].data, t["Wgtp"][i * c:(i + 1) * c])
+            pk(p[f"att.{nm}.weight"].data, t["WgtpT"][:, i * c:(i + 1) * c], transpose=True)
+            self.bgtp[i * c:(i + 1) * c].copy_(p[f"att.{nm}.bias"].data)
+        pk(p["att.W.weight"].data, t["WW"][:, :c])
+        pk(W1u, t["W1u"])
+        pk(W2u, t["W2u"])
+        # dgrad operands (transposes)
+        pk(W1e, t["WnT"][:, 0:D], c0=0, cols=D, transpose=True)
+        pk(W1e, t["WnT"][:, D:2 * D], c0=D, cols=D, transpose=True)
+        pk(W1m, t["WnT"][:, 2 * D:3 * D], c0=0, cols=D, transpose=True)
+        pk(W1e, t["W1e_eT"], c0=2 * D, cols=D, transpose=True)
+        pk(W2e, t["W2eT"], transpose=True)
+        pk(W1m, t["W1m_eT"], c0=D, cols=D, transpose=True)
+        pk(W2m, t["W2mT"], transpose=True)
+        pk(W2u, t["W2uT"], transpose=True)
+        pk(p["att.W.weight"].data, t["WWT"], transpose=True)
+        pk(W1u, t["W1uT"], transpose=True)
+        s = self.struct
+        s.D = D
+        for name, tensor in t.items():
+            setattr(s, name, tensor.data_ptr())
+        s.b1e = p["edge_model.edge_mlp.0.bias"].data_ptr()
+        s.b2e = p["edge_model.edge_mlp.2.bias"].data_ptr()
+        s.b1m = p["mlp.0.bias"].data_ptr()
+        s.b2m = p["mlp.2.bias"].data_ptr()
+        s.bgtp = self.bgtp.data_ptr()
+        s.bW = p["att.W.bias"].data_ptr()
+        s.b1u = p["mlp_updating.0.bias"].data_ptr()
+        s.b2u = p["mlp_updating.2.bias"].data_ptr()
+        self.versions = versions
+        return s
+
+
+def layer_forward_raw(weights, graph, x, e, want_relu_copies=False):
+    """Runs rpg_layer_fwd on bf16 inputs; returns the dict of activation tensors (kept for backward)."""
+    D = weights.D
+    dev = x.device
+    Nt, Et = graph.n_node_rows, graph.n_edge_rows
+    c = D // 8
+    cp = pad64(c)
+
+    def new(rows, cols, dtype=BF16):
+        return torch.empty(rows, cols, dtype=dtype, device=dev)
+
+    a = {"x": x, "e": e, "P": new(Nt, 3 * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
+         "m": new(Et, D), "gtp": new(Et, 3 * c, torch.float32),
+         "y": torch.zeros(Et, cp, dtype=BF16, device=dev) if cp != c else new(Et, cp),
+         "z": new(Et, D), "a": new(Nt, D), "h3": new(Nt, D), "out": new(Nt, D)}
+    if want_relu_copies:
+        a["e_new_relu"] = new(Et, D)
+        a["out_relu"] = new(Nt, D)
+    s = _lib.LayerActs()
+    for k, v in a.items():
+        setattr(s, k, v.data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().rpg_layer_fwd(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd")
+    a["_struct"] = s
+    return a
+
+
+def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=False, mask_de=False):
+    """Runs rpg_layer_bwd.  `grads`: dict name (PARAM_ORDER) -> fp32 tensor, accumulated in place.
+    Returns (dx, de) in bf16."""
+    D = weights.D
+    dev = acts["x"].device
+    Nt, Et = graph.n_node_rows, graph.n_edge_rows
+    c = D // 8
+    cp, c3p = pad64(c), pad64(3 * c)
+    lib = _lib.load()
+
+    def new(rows, cols, dtype=BF16):
+        return torch.empty(rows, cols, dtype=dtype, device=dev)
+
+    b = _lib.LayerGrads()
+    have_out = d_out is not None
+    keep = {"dx": new(Nt, D), "de": new(Et, D), "dh1": new(Et, D), "dP": new(Nt, 3 * D),
+            "split_ws": ops.wgrad_ws(D, dev),
+            "colsum_ws": torch.empty(lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), dtype=torch.float32, device=dev)}
+    if have_out:
+        keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D), "dan": new(Nt, D), "dyn": new(Nt, c, torch.float32),
+                     "dgtp": torch.zeros(Et, c3p, dtype=BF16, device=dev) if c3p != 3 * c else new(Et, c3p),
+                     "dm": new(Et, D), "dh2": new(Et, D), "de_tot": new(Et, D),
+                     "ysum": new(Nt, cp), "gtp_bias_tmp": torch.empty(c3p, dtype=torch.float32, device=dev)})
+    for k, v in keep.items():
+        setattr(b, k, v.data_ptr())
+    b.d_out = ops.ptr(d_out)
+    b.d_e_new = ops.ptr(d_e_new)
+    b.mask_dx, b.mask_de = int(mask_dx), int(mask_de)
+    for name, field in zip(PARAM_ORDER, _GRAD_FIELDS):
+        setattr(b, field, grads[name].data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib.rpg_layer_bwd(C.byref(weights), graph.byref(), C.byref(acts["_struct"]), C.byref(b), stream),
+               "rpg_layer_bwd")
+    return keep["dx"], keep["de"]
+
+
+class _LayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, e, module, graph, *params):
+        weights = module._packed(x.device).refresh(module)
+        acts = layer_forward_raw(weights, graph, ops.to_bf16(x), ops.to_bf16(e))
+        ctx.module, ctx.graph, ctx.acts, ctx.weights = module, graph, acts, weights
+        ctx.in_dtypes = (x.dtype, e.dtype)
+        ctx.param_shapes = [p.shape for p in params]
+        out, e_new = acts["out"], acts["e_new"]
+        if x.dtype == torch.float32:
+            out = ops.to_f32(out)
+        if e.dtype == torch.float32:
+            e_new = ops.to_f32(e_new)
+        return out, e_new
+
+    @staticmethod
+    def backward(ctx, d_out, d_e_new):
+        dev = ctx.acts["x"].device
+        grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(PARAM_ORDER, ctx.param_shapes)}
+        d_out = ops.to_bf16(d_out) if d_out is not None else None
+        d_e_new = ops.to_bf16(d_e_new) if d_e_new is not None else None
+        dx, de = layer_backward_raw(ctx.weights, ctx.graph, ctx.acts, d_out, d_e_new, grads)
+        if ctx.in_dtypes[0] == torch.float32:
+            dx = ops.to_f32(dx)
+        if ctx.in_dtypes[1] == torch.float32:
+            de = ops.to_f32(de)
+        return (dx, de, None, None) + tuple(grads[n] for n in PARAM_ORDER)
+
+
+class simpleConvEdge_upt(nn.Module):
+    """B200-native `simpleConvEdge_upt` (my_gnn_layer.py:277-311): edge MLP -> message MLP + channel attention
+    -> mean aggregation over incoming edges -> node-update MLP.
+
+    forward(x [Nn, C] float32|bfloat16 CUDA, edge_index [2, Et] int64 CUDA, edge_attr [Et, C]) ->
+    (out [Nn, C], edge_attr_new [Et, C]), both pre-ReLU, fresh tensors in the dtype of the inputs.
+    Arithmetic: bf16 operands, fp32 accumulation (tcgen05 / TMEM).  `edge_index` must be a batch of identical
+    per-graph templates (PyG batching of the reference datasets); anything else raises ValueError.
+    """
+
+    def __init__(self, in_channels, edge_channels, out_channels, use_attention=True):
+        super().__init__()
+        if not use_attention:
+            # the reference leaves self.att undefined and then fails in message() (my_gnn_layer.py:290-291,306)
+            raise AttributeError("simpleConvEdge_upt without attention is undefined in the reference")
+        if not (in_channels == edge_channels == out_channels):
+            raise ValueError("every reference call site uses in == edge == out channels (SURVEY.md 3.4); "
+                             "AttentionBlock(in_channels) on an out_channels-wide message requires it")
+        if in_channels % 128:
+            raise ValueError("channel count must be a multiple of 128 (tcgen05 tile / attention group constraints)")
+        self.in_channels = in_channels
+        self.aggr = "mean"
+        # construction order == reference, so default initialisation consumes the RNG identically
+        self.mlp = Seq(Linear(in_channels + edge_channels, out_channels), ReLU(), Linear(out_channels, out_channels))
+        self.mlp_updating = Seq(Linear(2 * in_channels, out_channels), ReLU(), Linear(out_channels, out_channels))
+        self.edge_model = simpleEdgeModel(in_channels, edge_channels, edge_channels)
+        self.att = AttentionBlock(in_channels)
+        self._pack_cache = {}
+
+    def _packed(self, device):
+        key = str(device)
+        pw = self._pack_cache.get(key)
+        if pw is None:
+            pw = self._pack_cache[key] = PackedLayerWeights(self.in_channels, device)
+        return pw
+
+    def _ordered_params(self):
+        return [self.get_parameter(n) for n in PARAM_ORDER]
+
+    def _check_inputs(self, x, edge_index, edge_attr):
+        D = self.in_channels
+        for name, t in (("x", x), ("edge_attr", edge_attr)):
+            if not torch.is_tensor(t) or t.dim() != 2 or t.size(1) != D:
+                raise ValueError(f"{name} must be a [rows, {D}] tensor")
+            if t.dtype not in (torch.float32, BF16):
+                raise TypeError(f"{name} must be float32 or bfloat16, got {t.dtype}")
+            if not t.is_cuda:
+                raise ValueError(f"{name} must be a CUDA tensor: the sm_100a kernels are the only implementation")
+        if edge_attr.size(0) != edge_index.size(1):
+            raise ValueError("edge_attr rows must equal edge_index columns")
+        if x.device != edge_attr.device or x.device != edge_index.device:
+            raise ValueError("x, edge_index and edge_attr must be on the same device")
+
+    def forward(self, x, edge_index, edge_attr):
+        self._check_inputs(x, edge_index, edge_attr)
+        graph = graph_mod.from_edge_index(edge_index, x.size(0))
+        return _LayerFn.apply(x, edge_attr, self, graph, *self._ordered_params())

@@ -1,0 +1,220 @@
+"""The GNN part of `PoseNetX_R2` (posenet.py:920-1091) as one fused stack on the B200 kernels.
+
+`RelPoseGNN` mirrors the reference model's parameter names for this path -- `proj_edge`, `gnn1..gnnL`
+(only `gnn1` is ever called, posenet.py:1060-1069), `fc_xyz`, `fc_wpqr`, `fc_xyz_R`, `fc_wpqr_R` -- so
+`load_state_dict(reference_checkpoint['model_state_dict'], strict=False)` fills it.  The ResNet34 feature
+extractor is NOT part of this path; `forward` takes the node embeddings it would produce.
+
+    forward(x [G*N, D], edge_index [2, G*Ep]) -> (pose_nodes [G*N, 6], pose_edges [G*Ep, 6], edge_index)
+
+as posenet.py:1091.  `training_step` adds compute_RP (posenet.py:1021-1031), PoseNetCriterion
+(criterion.py:42-60) and the whole backward, i.e. what train.py:256-274 differentiates for the GNN.
+"""
+import torch
+from torch import nn
+
+from . import graph as graph_mod, ops
+from .layers import PARAM_ORDER, layer_backward_raw, layer_forward_raw, simpleConvEdge_upt
+from .ops import BF16
+
+_HEADS = ("fc_xyz", "fc_wpqr", "fc_xyz_R", "fc_wpqr_R")
+
+
+class _StackFn(torch.autograd.Function):
+    """proj_edge init -> R x (gnn1, ReLU, ReLU) -> feature dropout -> 4 pose heads, with a hand-written backward.
+    ReLUs are folded into GEMM epilogues (forward: second store; backward: mask on the input that was a ReLU)."""
+
+    @staticmethod
+    def forward(ctx, x, model, graph, drop, *params):
+        D, R = model.node_dim, model.gnn_recursion
+        dev = x.device
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        xb = ops.to_bf16(x)
+        lw = model.gnn1._packed(dev).refresh(model.gnn1)
+        sw = model._packed_stack(dev)
+        # edge-feature initialiser (posenet.py:1014-1017,1053-1055), factorised per node
+        pmm = torch.empty(Nt, 2 * D, dtype=BF16, device=dev)
+        ops.gemm_nt(xb, sw["Wmm"], out=pmm)
+        e = torch.empty(Et, D, dtype=BF16, device=dev)
+        ops.edge_init_fwd(pmm, model.proj_edge.bias.data, graph, D, e)
+        acts = []
+        xin = xb
+        for _ in range(R):                                       # same gnn1 weights each round (posenet.py:1060-1069)
+            a = layer_forward_raw(lw, graph, xin, e, want_relu_copies=True)
+            acts.append(a)
+            xin, e = a["out_relu"], a["e_new_relu"]
+        p_drop, keep_x, keep_e, seed = drop
+        pose_n = ops.head_fwd(xin, sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop)
+        pose_e = ops.head_fwd(e, sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop)
+        ctx.model, ctx.graph, ctx.drop = model, graph, drop
+        ctx.saved = (xb, pmm, acts, xin, e, lw, sw)
+        ctx.x_dtype = x.dtype
+        ctx.set_materialize_grads(False)
+        return pose_n, pose_e
+
+    @staticmethod
+    def backward(ctx, d_pose_n, d_pose_e):
+        model, graph = ctx.model, ctx.graph
+        xb, pmm, acts, x_last, e_last, lw, sw = ctx.saved
+        p_drop, keep_x, keep_e, seed = ctx.drop
+        D, R = model.node_dim, model.gnn_recursion
+        dev = xb.device
+        names = model._param_names()
+        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in zip(names, model._ordered_params())}
+        lgrads = {n: grads["gnn1." + n] for n in PARAM_ORDER}
+        ws = ops.wgrad_ws(D, dev)
+
+        # heads (posenet.py:1077-1086): gradient w.r.t. the pre-ReLU layer outputs (mask_relu)
+        d_e = d_x = None
+        if d_pose_e is not None:
+            dw6, db6 = torch.zeros(6, D, device=dev), torch.zeros(6, device=dev)
+            d_e = ops.head_bwd(d_pose_e.contiguous().float(), e_last, sw["w6e"], dw6, db6, keep=keep_e, seed=seed + 1,
+                               p_drop=p_drop, mask_relu=True)
+            grads["fc_xyz_R.weight"] += dw6[:3]
+            grads["fc_wpqr_R.weight"] += dw6[3:]
+            grads["fc_xyz_R.bias"] += db6[:3]
+            grads["fc_wpqr_R.bias"] += db6[3:]
+        if d_pose_n is not None:
+            dw6, db6 = torch.zeros(6, D, device=dev), torch.zeros(6, device=dev)
+            d_x = ops.head_bwd(d_pose_n.contiguous().float(), x_last, sw["w6n"], dw6, db6, keep=keep_x, seed=seed,
+                               p_drop=p_drop, mask_relu=True)
+            grads["fc_xyz.weight"] += dw6[:3]
+            grads["fc_wpqr.weight"] += dw6[3:]
+            grads["fc_xyz.bias"] += db6[:3]
+            grads["fc_wpqr.bias"] += db6[3:]
+
+        for r in range(R - 1, -1, -1):
+            d_x, d_e = layer_backward_raw(lw, graph, acts[r], d_x, d_e, lgrads, mask_dx=(r > 0), mask_de=True)
+            acts[r] = None                                      # free this round's activations
+
+        # edge-feature initialiser backward: d_e is already masked by (e0 > 0)
+        Nt = graph.n_node_rows
+        dpmm = torch.empty(Nt, 2 * D, dtype=BF16, device=dev)
+        ops.segment_sum(d_e, graph, "min", dpmm[:, :D])
+        ops.segment_sum(d_e, graph, "max", dpmm[:, D:])
+        dx = torch.empty(Nt, D, dtype=BF16, device=dev)
+        ops.gemm_nt(dpmm, sw["WmmT"], resid=d_x, out=dx)
+        gw = grads["proj_edge.weight"]
+        ops.wgrad(dpmm[:, :D], xb, gw[:, :D], ws)
+        ops.wgrad(dpmm[:, D:], xb, gw[:, D:], ws)
+        ops.colsum(dpmm[:, :D], grads["proj_edge.bias"])        # every edge has exactly one lower endpoint
+        dx = ops.to_f32(dx) if ctx.x_dtype == torch.float32 else dx
+        return (dx, None, None, None) + tuple(grads[n] for n in names)
+
+
+class RelPoseGNN(nn.Module):
+    """GNN stack of PoseNetX_R2 (constructor arguments as posenet.py:923-930 where they concern this path)."""
+
+    def __init__(self, feat_dim=1024, edge_feat_dim=1024, node_dim=1024, droprate=0.5, gnn_recursion=2, L=1):
+        super().__init__()
+        if not (feat_dim == edge_feat_dim == node_dim):
+            raise ValueError("the reference instantiates feat_dim == edge_feat_dim == node_dim (train.py:174-189)")
+        self.node_dim, self.droprate, self.gnn_recursion, self.n_layers = node_dim, droprate, gnn_recursion, L
+        self.proj_edge = nn.Linear(feat_dim * 2, edge_feat_dim)
+        for layer in range(L):
+            setattr(self, f"gnn{layer + 1}", simpleConvEdge_upt(node_dim, edge_feat_dim, node_dim))
+        for h in _HEADS:
+            setattr(self, h, nn.Linear(node_dim, 3))
+        # initialisation as posenet.py:981-997: kaiming_normal_ + zero bias on the bare Linear modules listed there
+        for m in [self.proj_edge] + [getattr(self, h) for h in _HEADS]:
+            nn.init.kaiming_normal_(m.weight.data)
+            nn.init.constant_(m.bias.data, 0)
+        self._stack_cache = {}
+        self.dropout_seed = 0x5EED
+
+    def _param_names(self):
+        return (["proj_edge.weight", "proj_edge.bias"] + ["gnn1." + n for n in PARAM_ORDER] +
+                [f"{h}.{s}" for h in _HEADS for s in ("weight", "bias")])
+
+    def _ordered_params(self):
+        return [self.get_parameter(n) for n in self._param_names()]
+
+    def _packed_stack(self, device):
+        """bf16 proj_edge operands and the [6, D] fp32 head matrices; refreshed when parameters change."""
+        D = self.node_dim
+        ps = [self.proj_edge.weight] + [getattr(self, h).weight for h in _HEADS] + [getattr(self, h).bias for h in _HEADS]
+        versions = tuple((p.data_ptr(), p._version) for p in ps)
+        ent = self._stack_cache.get(str(device))
+        if ent is not None and ent["versions"] == versions:
+            return ent
+        if ent is None:
+            ent = {"Wmm": torch.empty(2 * D, D, dtype=BF16, device=device),
+                   "WmmT": torch.empty(D, 2 * D, dtype=BF16, device=device)}
+            self._stack_cache[str(device)] = ent
+        W = self.proj_edge.weight.data                                     # [D, 2D]: columns (min node | max node)
+        ops.pack_weight(W, ent["Wmm"][:D], c0=0, cols=D)
+        ops.pack_weight(W, ent["Wmm"][D:], c0=D, cols=D)
+        ops.pack_weight(W, ent["WmmT"][:, :D], c0=0, cols=D, transpose=True)
+        ops.pack_weight(W, ent["WmmT"][:, D:], c0=D, cols=D, transpose=True)
+        ent["w6n"] = torch.cat([self.fc_xyz.weight.data, self.fc_wpqr.weight.data]).contiguous()
+        ent["b6n"] = torch.cat([self.fc_xyz.bias.data, self.fc_wpqr.bias.data]).contiguous()
+        ent["w6e"] = torch.cat([self.fc_xyz_R.weight.data, self.fc_wpqr_R.weight.data]).contiguous()
+        ent["b6e"] = torch.cat([self.fc_xyz_R.bias.data, self.fc_wpqr_R.bias.data]).contiguous()
+        ent["versions"] = versions
+        return ent
+
+    def _drop_args(self, keep_x, keep_e):
+        # F.dropout's default training=True keeps dropout active under eval() too (posenet.py:1073-1075)
+        if self.droprate <= 0:
+            return (0.0, None, None, 0)
+        if (keep_x is None) != (keep_e is None):
+            raise ValueError("give both keep masks or neither")
+        if keep_x is not None:
+            keep_x = keep_x.to(torch.uint8).contiguous()
+            keep_e = keep_e.to(torch.uint8).contiguous()
+            return (float(self.droprate), keep_x, keep_e, 0)
+        self.dropout_seed += 2
+        return (float(self.droprate), None, None, self.dropout_seed)
+
+    def forward(self, x, edge_index, keep_x=None, keep_e=None):
+        """x: node embeddings [G*N, D] (what feature_extractor returns, posenet.py:1037).  keep_x / keep_e: optional
+        explicit Bernoulli keep masks for the feature dropout (parity tests); otherwise a counter-based in-kernel RNG."""
+        if not x.is_cuda:
+            raise ValueError("RelPoseGNN needs CUDA tensors: the sm_100a kernels are the only implementation")
+        if x.dim() != 2 or x.size(1) != self.node_dim:
+            raise ValueError(f"x must be [rows, {self.node_dim}]")
+        graph = graph_mod.from_edge_index(edge_index, x.size(0))
+        drop = self._drop_args(keep_x, keep_e)
+        pose_n, pose_e = _StackFn.apply(x, self, graph, drop, *self._ordered_params())
+        return pose_n, pose_e, edge_index
+
+    @staticmethod
+    def compute_RP(p, edge_index):
+        """posenet.py:1021-1031 without the per-edge Python loop."""
+        return p[edge_index[0]] - p[edge_index[1]]
+
+
+class PoseNetCriterion(nn.Module):
+    """criterion.py:33-60 with L1 losses; the L1 sums and the target gather run in one fused kernel."""
+
+    def __init__(self, sax=0.0, saq=0.0, learn_beta=True):
+        super().__init__()
+        self.sax = nn.Parameter(torch.tensor([float(sax)]), requires_grad=learn_beta)
+        self.saq = nn.Parameter(torch.tensor([float(saq)]), requires_grad=learn_beta)
+
+    def forward(self, pred_edges, poses, edge_index):
+        """loss(pred_R, compute_RP(poses, edge_index)) -> (loss, t_loss, q_loss), differentiable w.r.t. pred, sax, saq."""
+        graph = graph_mod.from_edge_index(edge_index, poses.size(0))
+        return _PoseLossFn.apply(pred_edges, poses.float().contiguous(), graph, self.sax, self.saq)
+
+
+class _PoseLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, poses, graph, sax, saq):
+        pred = pred.float().contiguous()
+        n = 3.0 * pred.size(0)
+        scale = torch.cat([torch.exp(-sax.detach()), torch.exp(-saq.detach())]).float() / n
+        sums, _, dsign = ops.pose_loss(pred, poses, graph, grad_scale=scale, want_grad=True)
+        t_loss, q_loss = sums[0] / n, sums[1] / n
+        loss = torch.exp(-sax) * t_loss + sax + torch.exp(-saq) * q_loss + saq
+        ctx.save_for_backward(dsign, t_loss, q_loss, sax, saq)
+        return loss.reshape(1), t_loss, q_loss
+
+    @staticmethod
+    def backward(ctx, g_loss, g_t, g_q):
+        dsign, t_loss, q_loss, sax, saq = ctx.saved_tensors
+        g = g_loss.reshape(())
+        d_pred = dsign * g
+        d_sax = (g * (1.0 - torch.exp(-sax) * t_loss)).reshape(1)
+        d_saq = (g * (1.0 - torch.exp(-saq) * q_loss)).reshape(1)
+        return d_pred, None, None, d_sax, d_saq

@@ -1,0 +1,204 @@
+"""Thin tensor-level wrappers over the C ABI (include/rpg.h).  Every function enqueues on the current
+CUDA stream of the tensors' device and returns immediately; there is no CPU or PyTorch fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Gemm, check, ptr
+
+BF16 = torch.bfloat16
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def pad64(v):
+    return (v + 63) // 64 * 64
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("relpose_gnn_b200 ops need CUDA tensors: the sm_100a kernels are the only implementation")
+
+
+def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, row_scale=None, mask=None,
+            relu=False, out=None, out_relu=None, out_f32=None, graph=None, block_n=0):
+    """C = epilogue(sum_s A_s @ B^T).  A: bf16 [M, K] (or `segs`: list of up to 3 such tensors concatenated along
+    K); B: bf16 [N, sum K].  Row pitches are taken from stride(0), so column-sliced views are fine.
+    gadd: up to two (tensor [rows, >=N] bf16, 'src'|'dst') pairs added through the graph template."""
+    lib = _lib.load()
+    segs = segs if segs is not None else [A]
+    _require_cuda(B, *segs)
+    g = Gemm()
+    g.mode = 0
+    g.M = M if M is not None else segs[0].size(0)
+    g.N = N if N is not None else B.size(0)
+    g.n_seg = len(segs)
+    for i, a in enumerate(segs):
+        g.A[i] = a.data_ptr()
+        g.K[i] = a.size(1)
+        g.lda[i] = a.stride(0)
+    g.B = B.data_ptr()
+    g.ldb = B.stride(0)
+    g.block_n = block_n
+    g.bias = ptr(bias)
+    for i, (t, which) in enumerate(gadd):
+        g.gadd[i] = t.data_ptr()
+        g.gmap[i] = getattr(graph.struct, which)
+        g.gadd_ld[i] = t.stride(0)
+    if gadd:
+        g.Ep, g.Nn = graph.Ep, graph.N
+    if resid is not None:
+        g.resid, g.resid_ld = resid.data_ptr(), resid.stride(0)
+    if row_scale is not None:
+        g.row_scale, g.row_scale_mod = row_scale.data_ptr(), row_scale.numel()
+    if mask is not None:
+        g.mask, g.mask_ld = mask.data_ptr(), mask.stride(0)
+    g.relu = int(relu)
+    ldo = None
+    for t in (out, out_relu):
+        if t is not None:
+            ldo = t.stride(0) if ldo is None else ldo
+            if t.stride(0) != ldo:
+                raise ValueError("out and out_relu must share a row pitch")
+    g.out, g.out_relu, g.ldo = ptr(out), ptr(out_relu), ldo or 0
+    if out_f32 is not None:
+        g.out_f32, g.ldo_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    check(lib.rpg_gemm(C.byref(g), _stream(B)), "rpg_gemm")
+
+
+def gemm_tn_partials(A, B, ws, M, N, splits, block_n=0):
+    """Raw split-R TN GEMM (unit tests): ws[s] = A[rows_s, :M]^T @ B[rows_s, :N]."""
+    lib = _lib.load()
+    g = Gemm()
+    g.mode = 1
+    g.M, g.N = M, N
+    g.A[0], g.lda[0] = A.data_ptr(), A.stride(0)
+    g.B, g.ldb = B.data_ptr(), B.stride(0)
+    g.R = A.size(0)
+    g.splits, g.split_stride = splits, M * N
+    g.block_n = block_n
+    g.out_f32, g.ldo_f32 = ws.data_ptr(), N
+    check(lib.rpg_gemm(C.byref(g), _stream(A)), "rpg_gemm(TN)")
+
+
+def wgrad_ws(D, device):
+    n = _lib.load().rpg_layer_bwd_ws_floats(D, 0, 0)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
+def wgrad(A, B, out, ws, M=None, N=None):
+    """out[M, N] += A[:, :M]^T @ B[:, :N]  (fp32 `out`, pitch from stride(0); deterministic)."""
+    lib = _lib.load()
+    M = M if M is not None else A.size(1)
+    N = N if N is not None else B.size(1)
+    check(lib.rpg_wgrad(A.data_ptr(), A.stride(0), M, B.data_ptr(), B.stride(0), N, A.size(0), ws.data_ptr(),
+                        out.data_ptr(), out.stride(0), _stream(A)), "rpg_wgrad")
+
+
+def pack_weight(src, dst, r0=0, c0=0, rows=None, cols=None, transpose=False):
+    lib = _lib.load()
+    rows = rows if rows is not None else src.size(0) - r0
+    cols = cols if cols is not None else src.size(1) - c0
+    check(lib.rpg_pack_weight(src.data_ptr(), src.stride(0), r0, c0, rows, cols, dst.data_ptr(), dst.stride(0),
+                              int(transpose), _stream(src)), "rpg_pack_weight")
+
+
+def to_bf16(t):
+    if t.dtype == BF16:
+        return t.contiguous()
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32 or bfloat16, got {t.dtype}")
+    _require_cuda(t)
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=BF16, device=t.device)
+    check(_lib.load().rpg_cast_f32_to_bf16(t.data_ptr(), out.data_ptr(), t.numel(), _stream(t)), "cast")
+    return out
+
+
+def to_f32(t):
+    if t.dtype == torch.float32:
+        return t
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    check(_lib.load().rpg_cast_bf16_to_f32(t.data_ptr(), out.data_ptr(), t.numel(), _stream(t)), "cast")
+    return out
+
+
+def attention_fwd(gtp, c, y):
+    check(_lib.load().rpg_attention_fwd(gtp.data_ptr(), gtp.size(0), c, y.data_ptr(), y.stride(0), _stream(gtp)),
+          "rpg_attention_fwd")
+
+
+def attention_bwd(gtp, dyn, graph, c, dgtp):
+    check(_lib.load().rpg_attention_bwd(gtp.data_ptr(), dyn.data_ptr(), dyn.stride(0), graph.byref(), gtp.size(0), c,
+                                        dgtp.data_ptr(), dgtp.stride(0), _stream(gtp)), "rpg_attention_bwd")
+
+
+def aggregate_mean(z, graph, a):
+    check(_lib.load().rpg_aggregate_mean(z.data_ptr(), z.stride(0), graph.byref(), z.size(1), a.data_ptr(),
+                                         a.stride(0), _stream(z)), "rpg_aggregate_mean")
+
+
+def segment_sum(v, graph, which, out, mask=None, scale=None, D=None):
+    """out[node] = scale * sum over the template CSR `which` in {'in','out','min','max'} of v rows."""
+    s = graph.struct
+    D = D if D is not None else v.size(1)
+    check(_lib.load().rpg_segment_sum(v.data_ptr(), v.stride(0), ptr(mask), mask.stride(0) if mask is not None else 0,
+                                      getattr(s, which + "_ptr"), getattr(s, which + "_idx"), ptr(scale),
+                                      graph.byref(), D, out.data_ptr(), out.stride(0), _stream(v)), "rpg_segment_sum")
+
+
+def edge_init_fwd(pmm, bias, graph, D, e0):
+    check(_lib.load().rpg_edge_init_fwd(pmm.data_ptr(), pmm.stride(0), bias.data_ptr(), graph.byref(), D,
+                                        e0.data_ptr(), e0.stride(0), _stream(pmm)), "rpg_edge_init_fwd")
+
+
+def dropout_mask(seed, p_drop, rows, D, device):
+    keep = torch.empty(rows, D, dtype=torch.uint8, device=device)
+    check(_lib.load().rpg_dropout_mask(seed, p_drop, rows, D, keep.data_ptr(), _stream(keep)), "rpg_dropout_mask")
+    return keep
+
+
+def head_fwd(feat, w6, b6, keep=None, seed=0, p_drop=0.0):
+    pose = torch.empty(feat.size(0), 6, dtype=torch.float32, device=feat.device)
+    check(_lib.load().rpg_head_fwd(feat.data_ptr(), feat.stride(0), feat.size(0), feat.size(1), ptr(keep), seed,
+                                   p_drop, w6.data_ptr(), b6.data_ptr(), pose.data_ptr(), _stream(feat)), "rpg_head_fwd")
+    return pose
+
+
+def head_bwd(dpose, feat, w6, dw6, db6, keep=None, seed=0, p_drop=0.0, mask_relu=True, want_dfeat=True,
+             accumulate=True):
+    lib = _lib.load()
+    rows, D = feat.shape
+    ws = torch.empty(lib.rpg_head_bwd_ws_floats(rows, D), dtype=torch.float32, device=feat.device)
+    dfeat = torch.empty(rows, D, dtype=BF16, device=feat.device) if want_dfeat else None
+    check(lib.rpg_head_bwd(dpose.data_ptr(), feat.data_ptr(), feat.stride(0), rows, D, ptr(keep), seed, p_drop,
+                           w6.data_ptr(), int(mask_relu), ptr(dfeat), D, dw6.data_ptr(), db6.data_ptr(),
+                           int(accumulate), ws.data_ptr(), _stream(feat)), "rpg_head_bwd")
+    return dfeat
+
+
+def pose_loss(pred, poses, graph, grad_scale=None, want_target=False, want_grad=True):
+    """Returns (sums[2] = L1 sums over (t, q) columns, target or None, dpred or None)."""
+    lib = _lib.load()
+    Et = pred.size(0)
+    ws = torch.empty(lib.rpg_pose_loss_ws_floats(Et), dtype=torch.float32, device=pred.device)
+    sums = torch.empty(2, dtype=torch.float32, device=pred.device)
+    target = torch.empty(Et, 6, dtype=torch.float32, device=pred.device) if want_target else None
+    dpred = torch.empty(Et, 6, dtype=torch.float32, device=pred.device) if want_grad else None
+    check(lib.rpg_pose_loss(pred.data_ptr(), poses.data_ptr(), graph.byref(), Et, ptr(grad_scale), ptr(target),
+                            sums.data_ptr(), ptr(dpred), ws.data_ptr(), _stream(pred)), "rpg_pose_loss")
+    return sums, target, dpred
+
+
+def colsum(v, out, cols=None, row_w=None, accumulate=True):
+    lib = _lib.load()
+    rows = v.size(0)
+    cols = cols if cols is not None else v.size(1)
+    scratch = torch.empty(lib.rpg_colsum_scratch_floats(rows, cols), dtype=torch.float32, device=v.device)
+    check(lib.rpg_colsum_bf16(v.data_ptr(), v.stride(0), rows, cols, ptr(row_w), row_w.numel() if row_w is not None else 0,
+                              out.data_ptr(), int(accumulate), scratch.data_ptr(), _stream(v)), "rpg_colsum_bf16")

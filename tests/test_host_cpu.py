@@ -1,0 +1,133 @@
+"""CPU-only checks of the host logic and of the C-ABI library's surface (no compute calls, no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import relpose_gnn_b200 as rpg
+from oracle import restatement as R
+from relpose_gnn_b200 import _lib, graph as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "rpg.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rpg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/rpg.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.rpg_version() >= 100
+    assert isinstance(lib.rpg_last_error_string(), bytes)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    rc = lib.rpg_gemm(None, None)
+    assert rc == -1 and b"null" in lib.rpg_last_error_string()
+    with pytest.raises(_lib.RpgError):
+        _lib.check(rc, "rpg_gemm")
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8, 9, 17])
+def test_fc_template_is_the_reference_enumeration(n):
+    fx = np.load(os.path.join(GOLD, "fc_enumeration.npz"))
+    src, dst = G.fc_template(n)
+    assert np.array_equal(np.stack([src, dst]), fx[f"fc_N{n}"])
+    ei = G.batched_edge_index(src, dst, 3, n)
+    assert torch.equal(ei, R.batched_edge_index(R.fc_edge_index(n), 3, n))
+
+
+def test_edge_dropout_mask_matches_reference():
+    fx = np.load(os.path.join(GOLD, "edge_dropout.npz"))
+    for case in range(4):
+        n, batch, seed = [int(v) for v in fx[f"case{case}_meta"]]
+        keep = G.edge_dropout_keep(n * (n - 1) // 2, np.random.RandomState(seed))
+        assert np.array_equal(np.tile(keep, 2 * batch).astype(np.int64), fx[f"case{case}_tiled"])
+    class AllOnes:
+        def random_sample(self, k):
+            return np.ones(k)
+    assert G.edge_dropout_keep(5, AllOnes()).all()        # nothing survives -> keep everything (train.py:240-241)
+
+
+def test_graph_tables():
+    src, dst = G.fc_template(5)
+    keep = np.array([1, 0, 1, 1, 0, 0, 1, 0, 1, 1], bool)
+    s, d = G.thin_template(src, dst, keep)
+    g = G.GraphBatch(s, d, 4, 5, "cpu")
+    t = g._tables
+    for n in range(5):
+        ins = t["in_idx"][t["in_ptr"][n]:t["in_ptr"][n + 1]].numpy()
+        assert sorted(ins) == sorted(np.nonzero(d == n)[0]) and list(ins) == sorted(ins)   # fixed (ascending) order
+        outs = t["out_idx"][t["out_ptr"][n]:t["out_ptr"][n + 1]].numpy()
+        assert sorted(outs) == sorted(np.nonzero(s == n)[0])
+        lo = t["min_idx"][t["min_ptr"][n]:t["min_ptr"][n + 1]].numpy()
+        assert sorted(lo) == sorted(np.nonzero(np.minimum(s, d) == n)[0])
+        assert t["deg"][n].item() == (d == n).sum()
+        assert t["inv_deg"][n].item() == pytest.approx(1.0 / max(1, (d == n).sum()))
+    assert g.n_edge_rows == 4 * s.size and g.n_node_rows == 20
+    assert torch.equal(g.edge_index(), R.batched_edge_index(torch.from_numpy(np.stack([s, d]).astype(np.int64)), 4, 5))
+    with pytest.raises(ValueError):
+        G.GraphBatch(np.array([0, 7]), np.array([1, 2]), 1, 5, "cpu")
+
+
+def test_state_dict_layout_matches_reference():
+    m = rpg.simpleConvEdge_upt(128, 128, 128)
+    sd = m.state_dict()
+    want = R.LAYER_SHAPES(128)
+    assert list(sd.keys()) == list(want.keys())          # same names, same order
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == shp, k
+    m.load_state_dict(R.synth_params(want, 3, torch.float32))
+    s = rpg.RelPoseGNN(128, 128, 128)
+    names = set(s.state_dict().keys())
+    assert set(R.stack_shapes(128)) <= names
+
+
+def test_default_init_consumes_rng_like_the_reference_constructor():
+    """Same construction order => same default-initialised weights as torch builds for the reference class."""
+    from torch.nn import Linear
+    torch.manual_seed(11)
+    m = rpg.simpleConvEdge_upt(128, 128, 128)
+    torch.manual_seed(11)
+    D = 128
+    ref = [Linear(2 * D, D), Linear(D, D), Linear(2 * D, D), Linear(D, D), Linear(3 * D, D), Linear(D, D),
+           Linear(D, D // 8), Linear(D, D // 8), Linear(D, D // 8), Linear(D // 8, D)]
+    got = [m.mlp[0], m.mlp[2], m.mlp_updating[0], m.mlp_updating[2], m.edge_model.edge_mlp[0],
+           m.edge_model.edge_mlp[2], m.att.g, m.att.theta, m.att.phi, m.att.W]
+    for a, b in zip(got, ref):
+        assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)
+
+
+def test_constructor_and_input_errors():
+    with pytest.raises(AttributeError):
+        rpg.simpleConvEdge_upt(128, 128, 128, use_attention=False)
+    with pytest.raises(ValueError):
+        rpg.simpleConvEdge_upt(128, 256, 128)
+    with pytest.raises(ValueError):
+        rpg.simpleConvEdge_upt(96, 96, 96)
+    m = rpg.simpleConvEdge_upt(128, 128, 128)
+    ei = R.batched_edge_index(R.fc_edge_index(4), 2, 4)
+    with pytest.raises(ValueError, match="CUDA"):        # no CPU fallback: fails loudly
+        m(torch.zeros(8, 128), ei, torch.zeros(24, 128))
+    with pytest.raises(ValueError):
+        m(torch.zeros(8, 64), ei, torch.zeros(24, 128))
+    with pytest.raises(ValueError, match="CUDA"):
+        rpg.RelPoseGNN(128, 128, 128)(torch.zeros(8, 128), ei)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "relpose_gnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f
