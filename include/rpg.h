@@ -45,6 +45,13 @@ enum {
 
 const char* rpg_last_error_string(void);
 int rpg_version(void);
+/* Number of kernels this library has launched in this process (bench.py reports the per-step delta). */
+int64_t rpg_launch_count(void);
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel between begin/end (bench.py roofline leg):
+ * summed durations (ms), launch counts and executed FLOPs for the NT and TN modes.  end() synchronises. */
+int rpg_profile_begin(void);
+int rpg_profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches,
+                    double* nt_flops, double* tn_flops);
 /* Device properties the host side sizes grids with (SM count etc.); also proves the .so loads. */
 int rpg_device_sm_count(int device, int* sm_count);
 

@@ -84,10 +84,17 @@ def _linear(x, w, b):
     return x @ w.t() + b
 
 
-def edge_model_forward(p, x_src, x_dst, e, prefix="edge_model.edge_mlp."):
+def _relu(t, mask=None):
+    """ReLU; with `mask` (bool, same shape) the activation pattern is imposed instead of recomputed.  Used by the
+    gradient parity tests: a reduced-precision forward flips the sign of a few near-zero pre-activations, which
+    changes d(relu) on those entries by O(1); imposing the kernel's own pattern isolates the backward arithmetic."""
+    return torch.relu(t) if mask is None else t * mask.to(t.dtype)
+
+
+def edge_model_forward(p, x_src, x_dst, e, prefix="edge_model.edge_mlp.", mask=None):
     """simpleEdgeModel.forward, my_gnn_layer.py:236-239 (ctor :229-234)."""
     h = torch.cat([x_src, x_dst, e], dim=1)
-    h = torch.relu(_linear(h, p[prefix + "0.weight"], p[prefix + "0.bias"]))
+    h = _relu(_linear(h, p[prefix + "0.weight"], p[prefix + "0.bias"]), mask)
     return _linear(h, p[prefix + "2.weight"], p[prefix + "2.bias"])
 
 
@@ -109,17 +116,19 @@ def scatter_mean(msg, dst, n_rows):
     return out / cnt.clamp(min=1).unsqueeze(1)
 
 
-def layer_forward(p, x, edge_index, e, return_intermediates=False):
-    """simpleConvEdge_upt.forward, my_gnn_layer.py:293-311.  Returns (out, e_new), both pre-ReLU."""
+def layer_forward(p, x, edge_index, e, return_intermediates=False, relu_masks=None):
+    """simpleConvEdge_upt.forward, my_gnn_layer.py:293-311.  Returns (out, e_new), both pre-ReLU.
+    relu_masks: optional {'h1','h2','h3'} activation patterns to impose (see _relu)."""
+    rm = relu_masks or {}
     row, col = edge_index[0], edge_index[1]
-    e_new = edge_model_forward(p, x[row], x[col], e)                        # :295-297
+    e_new = edge_model_forward(p, x[row], x[col], e, mask=rm.get("h1"))     # :295-297
     h = torch.cat([x[row], e_new], dim=1)                                   # message, :304-305 (x_j = source)
-    h = torch.relu(_linear(h, p["mlp.0.weight"], p["mlp.0.bias"]))
+    h = _relu(_linear(h, p["mlp.0.weight"], p["mlp.0.bias"]), rm.get("h2"))
     m = _linear(h, p["mlp.2.weight"], p["mlp.2.bias"])
     z = attention_block(p, m)                                               # :306
     a = scatter_mean(z, col, x.size(0))                                     # propagate/aggregate, :301
     u = torch.cat([x, a], dim=1)                                            # update, :309-311
-    u = torch.relu(_linear(u, p["mlp_updating.0.weight"], p["mlp_updating.0.bias"]))
+    u = _relu(_linear(u, p["mlp_updating.0.weight"], p["mlp_updating.0.bias"]), rm.get("h3"))
     out = _linear(u, p["mlp_updating.2.weight"], p["mlp_updating.2.bias"])
     if return_intermediates:
         return out, e_new, {"m": m, "z": z, "a": a}
@@ -138,7 +147,7 @@ def compute_edge_features(x, edge_index):
     return torch.cat([x[lo], x[hi]], dim=1)
 
 
-def stack_forward(p, x, edge_index, gnn_recursion=2, droprate=0.0, keep_x=None, keep_e=None):
+def stack_forward(p, x, edge_index, gnn_recursion=2, droprate=0.0, keep_x=None, keep_e=None, relu_masks=None):
     """The GNN portion of PoseNetX_R2.forward, posenet.py:1053-1091.
 
     ``p`` holds 'proj_edge.*', 'gnn1.*', 'fc_xyz.*', 'fc_wpqr.*', 'fc_xyz_R.*', 'fc_wpqr_R.*'.
@@ -147,12 +156,14 @@ def stack_forward(p, x, edge_index, gnn_recursion=2, droprate=0.0, keep_x=None, 
     ``keep_e`` [Et, D] with entries in {0,1}; the kept entries are scaled by 1/(1-droprate)
     exactly as F.dropout does.  Returns (pose_nodes [Nn,6], pose_edges [Et,6], x_last, e_last).
     """
+    rm = relu_masks or {}
     g = {k[len("gnn1."):]: v for k, v in p.items() if k.startswith("gnn1.")}
-    e = torch.relu(_linear(compute_edge_features(x, edge_index),
-                           p["proj_edge.weight"], p["proj_edge.bias"]))     # :1053-1055
-    for _ in range(gnn_recursion):                                          # :1060-1069 (same gnn1 weights)
-        x, e = layer_forward(g, x, edge_index, e)
-        x, e = torch.relu(x), torch.relu(e)
+    e = _relu(_linear(compute_edge_features(x, edge_index),
+                      p["proj_edge.weight"], p["proj_edge.bias"]), rm.get("e0"))   # :1053-1055
+    for r in range(gnn_recursion):                                          # :1060-1069 (same gnn1 weights)
+        rr = rm.get("rounds", [{}] * gnn_recursion)[r]
+        x, e = layer_forward(g, x, edge_index, e, relu_masks=rr)
+        x, e = _relu(x, rr.get("x")), _relu(e, rr.get("e"))
     if droprate > 0:                                                        # :1073-1075
         scale = 1.0 / (1.0 - droprate)
         x = x * keep_x.to(x.dtype) * scale

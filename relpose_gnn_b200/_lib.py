@@ -65,6 +65,10 @@ SIGNATURES = {
     "rpg_last_error_string": (C.c_char_p, []),
     "rpg_version": (I, []),
     "rpg_device_sm_count": (I, [I, C.POINTER(I)]),
+    "rpg_launch_count": (I64, []),
+    "rpg_profile_begin": (I, []),
+    "rpg_profile_end": (I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I), C.POINTER(I),
+                            C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rpg_validate_edge_index": (I, [P, I64, I, I, I, P, P, P, P]),
     "rpg_gemm": (I, [C.POINTER(Gemm), P]),
     "rpg_wgrad": (I, [P, I, I, P, I, I, I64, P, P, I, P]),

@@ -683,6 +683,7 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     int rc = check_launch("head_bwd_kernel");
     if (rc) return rc;
     reduce_partials_kernel<<<grid_for(6 * D, 256), 256, 0, s>>>(dw_part, blocks, 6 * (long long)D, 6 * (long long)D, dw6, accumulate);
+    if ((rc = check_launch("reduce_partials_kernel"))) return rc;
     reduce_partials_kernel<<<1, 32, 0, s>>>(db_part, blocks, 6, 6, db6, accumulate);
     return check_launch("reduce_partials_kernel");
 }

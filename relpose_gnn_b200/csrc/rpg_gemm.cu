@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <vector>
 
 #include "../../include/rpg.h"
 #include "rpg_internal.h"
@@ -371,6 +372,41 @@ static int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t
     return 0;
 }
 
+// ---- per-launch event timing (enabled only between rpg_profile_begin / rpg_profile_end)
+struct ProfRec { cudaEvent_t e0, e1; int mode; double flops; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+int profile_begin() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.clear();
+    g_prof_on = true;
+    return 0;
+}
+
+int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    double ms[2] = {0, 0}, fl[2] = {0, 0};
+    int n[2] = {0, 0};
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        ms[r.mode] += t; fl[r.mode] += r.flops; n[r.mode]++;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    if (nt_ms) *nt_ms = ms[0];
+    if (tn_ms) *tn_ms = ms[1];
+    if (nt_launches) *nt_launches = n[0];
+    if (tn_launches) *tn_launches = n[1];
+    if (nt_flops) *nt_flops = fl[0];
+    if (tn_flops) *tn_flops = fl[1];
+    return 0;
+}
+
 static int g_sm_count = 0;
 static std::once_flag g_attr_once;
 
@@ -455,10 +491,27 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
     const int items = num_m_blocks * num_n_blocks * p.splits;
     const int grid = items < g_sm_count ? items : g_sm_count;
+    ProfRec rec;
+    bool prof = false;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        prof = g_prof_on;
+    }
+    if (prof) {
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+        rec.mode = g->mode;
+        rec.flops = 2.0 * p.M * p.N * (g->mode == 0 ? (double)p.total_kb * BLOCK_K : (double)g->R);
+        cudaEventRecord(rec.e0, stream);
+    }
     if (g->mode == 0)
         gemm_tc_kernel<0><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
     else
         gemm_tc_kernel<1><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
+    if (prof) {
+        cudaEventRecord(rec.e1, stream);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
     return check_launch("gemm_tc_kernel");
 }
 

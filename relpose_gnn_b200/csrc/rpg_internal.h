@@ -15,6 +15,9 @@ int set_error(int code, const char* msg);
 int check_launch(const char* what);
 
 int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream);
+// Optional per-launch CUDA-event timing of the GEMM kernel (bench.py roofline leg); off by default.
+int profile_begin();
+int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops);
 
 inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

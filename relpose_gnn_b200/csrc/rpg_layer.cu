@@ -7,7 +7,10 @@
 // which is algebraically identical to the reference formulation and removes the gathers and 40 % of the FLOPs.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
+#include <mutex>
+#include <vector>
 
 #include "../../include/rpg.h"
 #include "rpg_internal.h"
@@ -21,7 +24,10 @@ int set_error(int code, const char* msg) {
     return code;
 }
 
+static std::atomic<long long> g_launches{0};
+
 int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
@@ -98,6 +104,13 @@ int rpg_device_sm_count(int device, int* sm_count) {
 }
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream) { return gemm_launch(g, as_stream(stream)); }
+
+int64_t rpg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int rpg_profile_begin(void) { return profile_begin(); }
+int rpg_profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops) {
+    return profile_end(nt_ms, tn_ms, nt_launches, tn_launches, nt_flops, tn_flops);
+}
 
 int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R, float* ws, float* out, int ldo,
               rpg_stream_t stream) {

@@ -49,6 +49,8 @@ class _StackFn(torch.autograd.Function):
         ctx.model, ctx.graph, ctx.drop = model, graph, drop
         ctx.saved = (xb, pmm, acts, xin, e, lw, sw)
         ctx.x_dtype = x.dtype
+        if model.keep_debug_activations:
+            model.debug_activations = {"e0": acts[0]["e"], "rounds": acts[:]}
         ctx.set_materialize_grads(False)
         return pose_n, pose_e
 
@@ -121,6 +123,7 @@ class RelPoseGNN(nn.Module):
             nn.init.constant_(m.bias.data, 0)
         self._stack_cache = {}
         self.dropout_seed = 0x5EED
+        self.keep_debug_activations = False      # tests: keep the saved activations of the last forward
 
     def _param_names(self):
         return (["proj_edge.weight", "proj_edge.bias"] + ["gnn1." + n for n in PARAM_ORDER] +

@@ -17,8 +17,14 @@ from relpose_gnn_b200.layers import PARAM_ORDER
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL_BF16 = 2e-2
-# weight gradients are sums over thousands of bf16-rounded products: same 2e-2 budget, measured ~5e-3
-TOL_GRAD = 2e-2
+# Gradients against the plain fp64 reference: a bf16 forward flips the sign of ~0.3 % of the near-zero ReLU
+# pre-activations, and each flip changes d(relu) by O(1) => relative Frobenius error ~ sqrt(flip fraction) = 3-6 %
+# (measured, tools/layer_diag.py; drops to the 3e-3 arithmetic floor before the first ReLU).  This is a property
+# of bf16 arithmetic, not of the kernels, so the fixture comparison is loose ...
+TOL_GRAD_FLIP = 1e-1
+TOL_GRAD_SMALL = 2.5e-1        # per-tensor bound for tiny gradients (attention biases) dominated by flip noise
+# ... and the rigorous gradient check imposes the kernel's own activation pattern on the oracle (R._relu):
+TOL_GRAD = 1.5e-2
 
 
 def rel(a, b):
@@ -51,52 +57,72 @@ def test_layer_against_reference_fixture(tag):
     assert rel(out, fx["out_f64"]) < TOL_BF16
     assert rel(e_new, fx["e_new_f64"]) < TOL_BF16
     ((out * case["ct_out"].float().to(dev())).sum() + (e_new * case["ct_e"].float().to(dev())).sum()).backward()
-    assert rel(x.grad, fx["dx"]) < TOL_GRAD
-    assert rel(e.grad, fx["de"]) < TOL_GRAD
+    assert rel(x.grad, fx["dx"]) < TOL_GRAD_FLIP
+    assert rel(e.grad, fx["de"]) < TOL_GRAD_FLIP
+    num = den = 0.0
+    errs = {}
     for k in PARAM_ORDER:
         g = m.get_parameter(k).grad
         if "grad." + k in fx.files:
-            assert rel(g, fx["grad." + k]) < TOL_GRAD, k
+            ref = torch.from_numpy(fx["grad." + k])
+            errs[k] = rel(g, ref)
+            num += (g.double().cpu() - ref).norm().item() ** 2
+            den += ref.norm().item() ** 2
         else:
             u, w = R.grad_probe_vectors(g.shape)
             g64 = g.double().cpu().numpy()
-            full_scale = np.linalg.norm(g64) * np.linalg.norm(w)      # projection error relative to |g||w|
-            assert np.linalg.norm(g64 @ w - fx["gradrows." + k]) < TOL_GRAD * full_scale, k
-            assert np.linalg.norm(u @ g64 - fx["gradcols." + k]) < TOL_GRAD * np.linalg.norm(g64) * np.linalg.norm(u), k
+            errs[k + "@v"] = np.linalg.norm(g64 @ w - fx["gradrows." + k]) / np.linalg.norm(fx["gradrows." + k])
+            errs[k + "u@"] = np.linalg.norm(u @ g64 - fx["gradcols." + k]) / np.linalg.norm(fx["gradcols." + k])
+    # the attention projections receive tiny gradients (|g| ~ 1e-2 of the MLP ones) that the flip noise dominates
+    bad = {k: v for k, v in errs.items() if v > (2 * TOL_GRAD_SMALL if k.startswith("att.") else TOL_GRAD_SMALL)}
+    assert not bad, bad
+    if den:
+        assert (num / den) ** 0.5 < TOL_GRAD_FLIP      # all parameter gradients as one vector
 
 
 @pytest.mark.parametrize("D,N,Gn,drop_edges", [(512, 9, 5, False), (512, 17, 3, False), (512, 8, 16, True),
-                                               (256, 9, 33, True), (128, 3, 50, False)])
+                                               (256, 9, 33, True), (128, 3, 50, False), (1024, 8, 2, False)])
 def test_layer_against_oracle(D, N, Gn, drop_edges):
+    """Forward against the plain oracle; backward against the oracle with the kernel's activation pattern imposed.
+    Inputs, weights and cotangents are bf16-representable so that only the kernel arithmetic is measured."""
+    from relpose_gnn_b200 import ops
+    from relpose_gnn_b200.layers import layer_backward_raw, layer_forward_raw
     seed = 1000 + D + N + Gn
-    params = R.synth_params(R.LAYER_SHAPES(D), seed, torch.float64)
-    x, _ = R.synth_inputs(Gn, N, D, seed + 1, torch.float64)
+    q = lambda t: t.bfloat16().double()                                         # noqa: E731
+    params = {k: (q(v) if k.endswith("weight") else v.float().double())
+              for k, v in R.synth_params(R.LAYER_SHAPES(D), seed, torch.float64).items()}
+    x = q(R.synth_inputs(Gn, N, D, seed + 1, torch.float64)[0])
     tmpl = R.fc_edge_index(N)
     if drop_edges:
         keep = R.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(seed).random_sample(N * (N - 1) // 2))
         tmpl = R.apply_edge_dropout(tmpl, keep)
     ei = R.batched_edge_index(tmpl, Gn, N)
     gen = torch.Generator().manual_seed(seed + 2)
-    e = torch.relu(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64))
-    ct_o = torch.randn(Gn * N, D, generator=gen, dtype=torch.float64)
-    ct_e = torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64)
+    e = q(torch.relu(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64)))
+    ct_o = q(torch.randn(Gn * N, D, generator=gen, dtype=torch.float64))
+    ct_e = q(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64))
+    # CUDA path through the raw C-ABI wrappers (bf16 in / bf16 out)
+    m = make_layer(D, params)
+    graph = G.from_edge_index(ei.to(dev()), Gn * N)
+    assert graph.G == Gn and graph.N == N and graph.Ep == tmpl.size(1)
+    lw = m._packed(dev()).refresh(m)
+    acts = layer_forward_raw(lw, graph, x.to(dev()).bfloat16(), e.to(dev()).bfloat16())
+    grads = {k: torch.zeros_like(m.get_parameter(k)) for k in PARAM_ORDER}
+    dx, de = layer_backward_raw(lw, graph, acts, ct_o.to(dev()).bfloat16(), ct_e.to(dev()).bfloat16(), grads)
     # oracle (fp64 CPU)
+    out_o, en_o = R.layer_forward(params, x, ei, e)
+    assert rel(acts["out"].float(), out_o) < TOL_BF16 and rel(acts["e_new"].float(), en_o) < TOL_BF16
+    masks = {k: (acts[k] > 0).cpu() for k in ("h1", "h2", "h3")}
     p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     xo, eo = x.clone().requires_grad_(True), e.clone().requires_grad_(True)
-    out_o, en_o = R.layer_forward(p, xo, ei, eo)
-    ((out_o * ct_o).sum() + (en_o * ct_e).sum()).backward()
-    # CUDA path, bf16 tensors in -> bf16 out
-    m = make_layer(D, params)
-    xg = x.to(dev()).bfloat16().requires_grad_(True)
-    eg = e.to(dev()).bfloat16().requires_grad_(True)
-    out, en = m(xg, ei.to(dev()), eg)
-    assert out.dtype == torch.bfloat16
-    assert rel(out.float(), out_o) < TOL_BF16 and rel(en.float(), en_o) < TOL_BF16
-    ((out.float() * ct_o.float().to(dev())).sum() + (en.float() * ct_e.float().to(dev())).sum()).backward()
-    assert rel(xg.grad.float(), xo.grad) < TOL_GRAD
-    assert rel(eg.grad.float(), eo.grad) < TOL_GRAD
-    for k in PARAM_ORDER:
-        assert rel(m.get_parameter(k).grad, p[k].grad) < TOL_GRAD, k
+    out_m, en_m = R.layer_forward(p, xo, ei, eo, relu_masks=masks)
+    ((out_m * ct_o).sum() + (en_m * ct_e).sum()).backward()
+    assert rel(dx.float(), xo.grad) < TOL_GRAD
+    assert rel(de.float(), eo.grad) < TOL_GRAD
+    errs = {k: rel(grads[k], p[k].grad) for k in PARAM_ORDER}
+    # attention bias gradients are sums of strongly cancelling terms (each dg_j ~ mean of dy): allow 4x
+    bad = {k: v for k, v in errs.items() if v > (4 * TOL_GRAD if k.startswith("att.") and k.endswith("bias") else TOL_GRAD)}
+    assert not bad, bad
 
 
 def test_layer_is_deterministic_and_inputs_untouched():
@@ -149,21 +175,33 @@ def test_graph_permutation_equivariance_at_full_size():
     assert rel(en.view(Gn, g.Ep, D)[idx].reshape(-1, D).float(), e_ref) < TOL_BF16
 
 
-def test_edge_index_validation_errors():
+def test_edge_index_validation_and_generality():
     D, N, Gn = 128, 4, 3
-    m = make_layer(D, R.synth_params(R.LAYER_SHAPES(D), 1, torch.float32))
-    x = torch.zeros(Gn * N, D, device=dev())
+    params = R.synth_params(R.LAYER_SHAPES(D), 1, torch.float64)
+    m = make_layer(D, params)
+    x = torch.randn(Gn * N, D, device=dev())
     ei = R.batched_edge_index(R.fc_edge_index(N), Gn, N).to(dev())
-    bad = ei.clone()
-    bad[0, 17] = (bad[0, 17] + 1) % (Gn * N)                  # one edge differs between graphs
-    with pytest.raises(ValueError, match="template"):
-        m(x, bad, torch.zeros(bad.size(1), D, device=dev()))
+    e = torch.randn(ei.size(1), D, device=dev()).relu()
     with pytest.raises(TypeError):
-        m(x, ei.int(), torch.zeros(ei.size(1), D, device=dev()))
+        m(x, ei.int(), e)
     with pytest.raises(ValueError):
-        m(x, ei[:, :0], torch.zeros(0, D, device=dev()))
-    out, en = m(x, ei, torch.zeros(ei.size(1), D, device=dev()))   # the good one passes and is cached on the tensor
+        m(x, ei[:, :0], e[:0])
+    oob = ei.clone()
+    oob[1, 5] = Gn * N                                         # node index out of range
+    with pytest.raises(ValueError, match="template"):
+        m(x, oob, e)
+    out, en = m(x, ei, e)                                      # the good one passes and is cached on the tensor
     assert ei.rpg_graph.G == Gn and ei.rpg_graph.N == N and ei.rpg_graph.Ep == N * (N - 1)
+    # a batch whose graphs differ is not a uniform template of 3 graphs; it is still ONE valid graph of 12 nodes,
+    # so it runs as G=1 with its own template and must agree with the oracle's generic gather/scatter
+    odd = ei.clone()
+    odd[0, 17] = (odd[0, 17] + 1) % (Gn * N)
+    out2, en2 = m(x, odd, e)
+    assert odd.rpg_graph.G == 1 and odd.rpg_graph.N == Gn * N and odd.rpg_graph.Ep == odd.size(1)
+    o_ref, e_ref = R.layer_forward(params, x.double().cpu(), odd.cpu(), e.double().cpu())
+    assert rel(out2, o_ref) < TOL_BF16 and rel(en2, e_ref) < TOL_BF16
+    o_ref, e_ref = R.layer_forward(params, x.double().cpu(), ei.cpu(), e.double().cpu())
+    assert rel(out, o_ref) < TOL_BF16 and rel(en, e_ref) < TOL_BF16
 
 
 @pytest.mark.parametrize("tag,droprate,edrop", [("D128_N9_G2", 0.0, False), ("D128_N8_G3_drop", 0.5, True)])
@@ -186,15 +224,52 @@ def test_stack_against_reference_fixture(tag, droprate, edrop):
     loss, t_loss, q_loss = crit(pe, case["poses"].float().to(dev()), ei)
     assert np.allclose([loss.item(), t_loss.item(), q_loss.item()], fx["loss"], rtol=TOL_BF16, atol=2e-3)
     loss.backward()
-    assert rel(x.grad, fx["dx"]) < 5e-2          # L1 sign flips on near-zero residuals add to the bf16 budget
+    assert rel(x.grad, fx["dx"]) < 1.5e-1        # ReLU / L1 sign flips (see TOL_GRAD_FLIP), two rounds deep
     assert abs(crit.sax.grad.item() - fx["dsax"][0]) < 2e-2 and abs(crit.saq.grad.item() - fx["dsaq"][0]) < 2e-2
+    num = den = 0.0
     for k in case["params"]:
-        ref = fx["grad." + k]
+        ref = torch.from_numpy(fx["grad." + k])
         g = model.get_parameter(k).grad
-        if np.abs(ref).max() == 0:
+        if ref.abs().max() == 0:
             assert g is None or g.abs().max().item() == 0, k     # node heads / last node update get no gradient
         else:
-            assert rel(g, ref) < 5e-2, k
+            assert rel(g, ref) < 3e-1, k
+            num += (g.double().cpu() - ref).norm().item() ** 2
+            den += ref.norm().item() ** 2
+    assert (num / den) ** 0.5 < 1.5e-1
+
+
+def test_stack_backward_against_mask_matched_oracle():
+    """Whole-stack gradients with the kernel's activation patterns imposed on the oracle (bf16-representable inputs);
+    node AND edge pose heads receive cotangents so every parameter of the path gets a gradient."""
+    D, N, Gn = 256, 9, 7
+    q = lambda t: t.bfloat16().double()                                         # noqa: E731
+    case = R.synth_stack_case(D, N, Gn, 999, droprate=0.5, edge_dropout=True)
+    params = {k: (q(v) if k.endswith("weight") and not k.startswith("fc_") else v.float().double())
+              for k, v in case["params"].items()}
+    x = q(case["x"])
+    ei = case["edge_index"]
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.5).to(dev())
+    model.load_state_dict({k: v.float() for k, v in params.items()}, strict=False)
+    model.keep_debug_activations = True
+    xg = x.to(dev()).bfloat16().requires_grad_(True)
+    pn, pe, _ = model(xg, ei.to(dev()), keep_x=case["keep_x"].to(dev()), keep_e=case["keep_e"].to(dev()))
+    gen = torch.Generator().manual_seed(5)
+    ct_n = torch.randn(pn.shape, generator=gen).double()
+    ct_e = torch.randn(pe.shape, generator=gen).double()
+    ((pn * ct_n.float().to(dev())).sum() + (pe * ct_e.float().to(dev())).sum()).backward()
+    dbg = model.debug_activations
+    masks = {"e0": (dbg["e0"] > 0).cpu(),
+             "rounds": [{"h1": (a["h1"] > 0).cpu(), "h2": (a["h2"] > 0).cpu(), "h3": (a["h3"] > 0).cpu(),
+                         "x": (a["out_relu"] > 0).cpu(), "e": (a["e_new_relu"] > 0).cpu()} for a in dbg["rounds"]]}
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xo = x.clone().requires_grad_(True)
+    pn_o, pe_o, _, _ = R.stack_forward(p, xo, ei, 2, 0.5, case["keep_x"], case["keep_e"], relu_masks=masks)
+    assert rel(pn, pn_o) < TOL_BF16 and rel(pe, pe_o) < TOL_BF16
+    ((pn_o * ct_n).sum() + (pe_o * ct_e).sum()).backward()
+    assert rel(xg.grad.float(), xo.grad) < 2e-2
+    for k in params:
+        assert rel(model.get_parameter(k).grad, p[k].grad) < 2e-2, k
 
 
 def test_stack_against_oracle_full_width_with_dropout():
