@@ -1,0 +1,295 @@
+"""bench.py -- RelPose-GNN message-passing hot path on B200: graphs/s forward+backward.
+
+    python bench.py --gpus N --steps K --warmup W [--workload train_4096x9|train_2048x17|infer_4096x9]
+    python bench.py --impl reference ...      (the reference algorithm on the host CPU, oracle port)
+
+Default workload = BASELINE.json configs[2]: training step (forward + pose loss + backward, train-time edge
+dropout, feature dropout 0.5) on 4096 graphs x 9 nodes, D = 512, bf16, per GPU (weak scaling: N GPUs process
+N x 4096 graphs and all-reduce the gradients once per step).  Prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (graphs per GPU, nodes, D, mode)
+    "train_4096x9": (4096, 9, 512, "train"),
+    "train_2048x17": (2048, 17, 512, "train"),
+    "infer_4096x9": (4096, 9, 512, "infer"),
+}
+METRIC = "GNN graphs/sec fwd+bwd"
+R_ROUNDS = 2
+
+
+def algorithmic_flops_per_graph(D, N, E, R=R_ROUNDS, train=True):
+    """BASELINE.md section 3 / SURVEY.md 8d: reference formulation with concatenated inputs, multiply-add = 2."""
+    fwd = 4 * D * D * E + R * (15 * D * D * E + 6 * D * D * N) + 12 * D * (E + N)
+    return fwd * (3 if train else 1)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_throughput(G_sample, N, D, train, steps, warmup, threads=None):
+    """The reference algorithm (oracle/restatement.py, pinned to the real reference by tests/golden) on the host
+    CPU in fp32 with all threads, on `G_sample` graphs per step; graphs/s = G_sample / median step time."""
+    from oracle import restatement as R
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    case = R.synth_stack_case(D, N, G_sample, 4242, droprate=0.5, edge_dropout=train, dtype=torch.float32)
+    params = {k: v.clone().requires_grad_(train) for k, v in case["params"].items()}
+    sax = torch.zeros(1, requires_grad=train)
+    saq = torch.full((1,), -2.0, requires_grad=train)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        if train:
+            loss = R.training_loss(params, case["x"].clone().requires_grad_(True), case["edge_index"], case["poses"], sax,
+                                   saq, R_ROUNDS, 0.5, case["keep_x"], case["keep_e"])
+            loss.backward()
+            for p in params.values():
+                p.grad = None
+        else:
+            with torch.no_grad():
+                R.stack_forward(params, case["x"], case["edge_index"], R_ROUNDS, 0.5, case["keep_x"], case["keep_e"])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = float(np.median(times))
+    return G_sample / med, med, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    G, N, D, mode = WORKLOADS[args.workload]
+    sample = args.cpu_sample
+    value, med, threads = cpu_reference_throughput(sample, N, D, mode == "train", args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "graphs_per_step": sample, "nodes": N, "D": D, "mode": mode,
+                       "note": "reference algorithm (oracle port) on host CPU; bounded sample of the workload per step"},
+            "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} graphs x {N} nodes per step, {mode}, fp32, torch CPU"},
+            "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- our arm (B200)
+def run_ours(args):
+    import torch.distributed as dist
+
+    import relpose_gnn_b200 as rpg
+    from relpose_gnn_b200 import _lib, parallel
+    from relpose_gnn_b200.graph import GraphBatch, attach, edge_dropout_keep
+
+    rank, local_rank, world = parallel.init_distributed("nccl")
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    G, N, D, mode = WORKLOADS[args.workload]
+    train = mode == "train"
+    H = N * (N - 1) // 2
+    peaks = load_peaks()
+
+    torch.manual_seed(0)
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.5, gnn_recursion=R_ROUNDS).to(dev)
+    crit = rpg.PoseNetCriterion(sax=0.0, saq=-2.0).to(dev)
+    params = list(model.parameters()) + list(crit.parameters())
+    if world > 1:      # identical replicas
+        for p in params:
+            dist.broadcast(p.data, 0)
+    bucket = parallel.FlatGradBucket(params) if train else None
+
+    # synthetic inputs of the named shape: ResNet34 embeddings ~ N(0,1) in bf16, poses ~ N(0, 0.1)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(G * N, D, generator=gen).bfloat16().pin_memory()
+    poses_host = (0.1 * torch.randn(G * N, 6, generator=gen)).pin_memory()
+    x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
+    mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
+    masks = [edge_dropout_keep(H, mask_rng) if train else np.ones(H, bool) for _ in range(4 * (args.warmup + args.steps) + 8)]
+    mask_iter = iter(masks)
+
+    def step(x, poses, read_back):
+        keep = next(mask_iter)
+        graph = GraphBatch.fully_connected(G, N, dev, keep)
+        ei = attach(graph.edge_index(), graph)                   # what the PyG loader + train.py:238-245 hand the model
+        if train:
+            bucket.zero()
+            pn, pe, _ = model(x, ei)
+            loss, t_loss, q_loss = crit(pe, poses, ei)
+            loss.backward()
+            bucket.allreduce()
+            return loss.item() if read_back else loss
+        with torch.no_grad():
+            pn, pe, _ = model(x, ei)
+        return pe.cpu() if read_back else pe
+
+    def timed(n_steps, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n_steps):
+            if e2e:
+                x = x_host.to(dev, non_blocking=True)
+                poses = poses_host.to(dev, non_blocking=True)
+                step(x, poses, True)
+            else:
+                step(x_dev, poses_dev, False)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item() / n_steps
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, poses_dev, False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.rpg_launch_count()
+    ms_step = timed(args.steps, e2e=False)
+    launches = (lib.rpg_launch_count() - launches0) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, e2e=True)
+
+    # roofline leg: per-launch CUDA events on the tcgen05 GEMM kernel during one more step (same stream)
+    keep_prof = masks[0]
+    mask_iter = iter([keep_prof] + masks)
+    Ep_prof = 2 * int(keep_prof.sum())
+    lib.rpg_profile_begin()
+    step(x_dev, poses_dev, False)
+    torch.cuda.synchronize()
+    nt_ms, tn_ms, nt_fl, tn_fl = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    nt_n, tn_n = C.c_int(), C.c_int()
+    lib.rpg_profile_end(C.byref(nt_ms), C.byref(tn_ms), C.byref(nt_n), C.byref(tn_n), C.byref(nt_fl), C.byref(tn_fl))
+    gemm_ms = nt_ms.value + tn_ms.value
+    alg_flops = algorithmic_flops_per_graph(D, N, Ep_prof, train=train) * G
+    mean_Ep = float(np.mean([2 * m.sum() for m in masks[:args.steps]]))
+
+    if rank == 0:
+        value = world * G / (ms_step * 1e-3)
+        e2e_value = world * G / (ms_e2e * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "graphs_per_gpu": G, "nodes_per_graph": N, "D": D, "mode": mode,
+                       "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if train else 1.0,
+                       "mean_edges_per_graph": mean_Ep, "feature_dropout": 0.5,
+                       "step": "forward + compute_RP/L1 criterion + backward" + (" + 1 NCCL all-reduce" if world > 1 else "") if train else "forward",
+                       "parallelism": f"dp{world} over graphs", "l2": "activations per step (>1 GB) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 2 + poses_host.numel() * 4,
+                    "d2h_bytes_per_step": 4 if train else G * 2 * int(np.mean([m.sum() for m in masks[:4]])) * 6 * 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<NT|TN> (tcgen05)",
+                         "achieved": alg_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": alg_flops / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + ", sustained bf16",
+                         "algorithmic_flops_per_launch": alg_flops / max(nt_n.value + tn_n.value, 1),
+                         "avg_launch_ms": gemm_ms / max(nt_n.value + tn_n.value, 1),
+                         "launches_per_step": nt_n.value + tn_n.value,
+                         "executed_tflops": (nt_fl.value + tn_fl.value) / (gemm_ms * 1e-3) / 1e12,
+                         "executed_frac": (nt_fl.value + tn_fl.value) / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                         "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_step,
+                         "edges_per_graph_profiled_step": Ep_prof},
+        }
+        if args.cpu_baseline and world == 1:
+            v, med, threads = cpu_reference_throughput(args.cpu_sample, N, D, train, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_sample} graphs x {N} nodes, {mode}, fp32 torch CPU, median of 3 "
+                                              f"({med * 1e3:.0f} ms per sample)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train_4096x9", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=128, help="graphs per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -193,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (kb == n_kb - 1) umma_commit(&acc_full[acc]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (n_kb == 0) umma_commit(&acc_full[acc]);   // degenerate split: nothing to accumulate
+                if (n_kb <= 0) umma_commit(&acc_full[acc]);   // empty split: nothing to accumulate (epilogue writes zeros)
             }
         }
     } else {

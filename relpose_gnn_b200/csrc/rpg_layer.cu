@@ -61,6 +61,8 @@ static int wgrad_partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, 
     long long splits = (2LL * sm_count + tiles - 1) / tiles;          // ~2 waves of work items
     if (splits > kb) splits = kb;
     if (splits < 1) splits = 1;
+    const long long per = (kb + splits - 1) / splits;
+    splits = (kb + per - 1) / per;                                    // no empty splits
     g.splits = (int)splits;
     g.split_stride = (long long)M * N;
     g.out_f32 = ws; g.ldo_f32 = N;

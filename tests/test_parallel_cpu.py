@@ -1,0 +1,62 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: graph sharding and the single flat-gradient
+all-reduce.  The kernels are not involved (no GPU here); the GPU path is exercised by bench.py --gpus N."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from relpose_gnn_b200 import parallel
+
+
+def test_shard_range_partitions_contiguously():
+    for total, world in [(4096, 8), (65536, 8), (10, 3), (7, 8), (2048, 2)]:
+        spans = [parallel.shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, lr, w = parallel.init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)                                   # identical replicas
+    lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    bucket = parallel.FlatGradBucket(lin.parameters())
+    assert bucket.numel == sum(p.numel() for p in lin.parameters())
+    # each rank owns a contiguous block of "graphs"; loss = mean over the rank's block
+    data = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    lo, hi = parallel.shard_range(8, rank, world)
+    for _ in range(2):                                      # second step checks zero() + in-place accumulation
+        bucket.zero()
+        lin(data[lo:hi]).pow(2).mean().backward()
+        assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())   # still views
+        bucket.allreduce()
+    if rank == 0:
+        torch.save(bucket.flat.clone(), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_matches_single_process(tmp_path):
+    out = str(tmp_path / "flat.pt")
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    data = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+    lin(data).pow(2).mean().backward()                     # equal shards + mean loss => averaged grads == full-batch grads
+    want = torch.cat([p.grad.flatten() for p in lin.parameters()])
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)

@@ -101,7 +101,8 @@ def nt_cases():
 def tn_cases():
     ok = True
     for (R, M, N, splits) in [(64, 128, 64, 1), (64, 128, 256, 1), (256, 128, 256, 1), (1000, 192, 256, 3),
-                              (5000, 512, 512, 7), (777, 48, 128, 2), (4096, 1536, 512, 4), (300, 512, 16, 2)]:
+                              (5000, 512, 512, 7), (777, 48, 128, 2), (4096, 1536, 512, 4), (300, 512, 16, 2),
+                              (640, 128, 64, 7), (36864, 512, 64, 74)]:   # last two: splits with no k-blocks at all
         A, B = rnd(R, M), rnd(R, N)
         ws = torch.empty(splits, M, N, dtype=torch.float32, device=dev)
         print(f"... TN R={R} M={M} N={N} splits={splits}", flush=True)
