@@ -164,6 +164,8 @@ def run_ours(args):
         for p in params:
             dist.broadcast(p.data, 0)
     bucket = parallel.FlatGradBucket(params) if train else None
+    if train:
+        model.attach_grad_bucket(bucket)
 
     # synthetic inputs of the named shape: ResNet34 embeddings ~ N(0,1) in bf16, poses ~ N(0, 0.1)
     gen = torch.Generator().manual_seed(1234 + rank)

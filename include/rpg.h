@@ -190,12 +190,14 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
 int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream);
 int rpg_head_fwd(const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed,
                  float p_drop, const float* w6, const float* b6, float* pose, rpg_stream_t stream);
-/* dfeat = (dpose * W6) * keep * scale * (feat > 0 if mask_relu); dW6 [6, D] and db6 [6] (+)= ... ;
+/* dfeat = (dpose * W6) * keep * scale * (feat > 0 if mask_relu); weight/bias gradients of the translation head
+ * (rows 0..2 of W6: dw_t [3, D], db_t [3]) and of the rotation head (rows 3..5: dw_q, db_q), (+)= if accumulate;
  * ws: rpg_head_bwd_ws_floats(rows, D) floats of scratch for the deterministic two-stage reduction.   */
 int64_t rpg_head_bwd_ws_floats(int64_t rows, int D);
 int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep,
                  uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf,
-                 float* dw6, float* db6, int accumulate, float* ws, rpg_stream_t stream);
+                 float* dw_t, float* dw_q, float* db_t, float* db_q, int accumulate, float* ws,
+                 rpg_stream_t stream);
 
 /* compute_RP (posenet.py:1021-1031) + the L1 sums of PoseNetCriterion (criterion.py:51-52) fused:
  * target[e] = poses[src(e)] - poses[dst(e)];  sums[0] = sum|pred_t - targ_t|, sums[1] = sum|pred_q - targ_q|

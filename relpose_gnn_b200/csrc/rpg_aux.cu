@@ -154,27 +154,26 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
     }
 }
 
-// Backward.  Pass 1 (lane owns i): p_ij = exp(phi_i theta_j - max_i) -> smem, den_i, y_i, and
-//   dphi_i = dy_i (sum_j p_ij g_j theta_j - y_i sum_j p_ij theta_j) / den_i.
-// Pass 2 (lane owns j): with w_i = dy_i / den_i:  dg_j = sum_i w_i p_ij,
-//   dtheta_j = g_j sum_i w_i phi_i p_ij - sum_i w_i y_i phi_i p_ij.      c^2 exps, same as forward.
+// Backward, two sweeps of c^2 exps each, nothing of size c x c is stored:
+//  sweep 1 (lane owns i): den_i, y_i and  dphi_i = w_i (sum_j p_ij g_j theta_j - y_i sum_j p_ij theta_j),  w_i = dy_i / den_i
+//  sweep 2 (lane owns j): p_ij recomputed;  dg_j = sum_i w_i p_ij,  dtheta_j = g_j sum_i w_i phi_i p_ij - sum_i w_i y_i phi_i p_ij
+// with p_ij = exp2(phi_i log2e theta_j - m_i), m_i the rank-1 row maximum.  One warp per edge row.
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dyn, int ld_dyn,
-                     const int* __restrict__ tdst, int Ep, int Nn, long long Et, int c, int warps,
+                     const int* __restrict__ tdst, int Ep, int Nn, long long Et, int c,
                      bf16* __restrict__ dgtp, int ld_dgtp) {
     extern __shared__ __align__(16) float att_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= warps) return;
-    const int pitch = c + 1;
-    float* base = att_smem + (size_t)warp * (c * pitch + 6 * c);
-    float* P = base;                       // [c][c+1]
-    float* sg = base + c * pitch;          // g_j
-    float* st = sg + c;                    // theta_j
-    float* sw = st + c;                    // w_i
-    float* swp = sw + c;                   // w_i * phi_i
-    float* swyp = swp + c;                 // w_i * y_i * phi_i
-    float* sdy = swyp + c;                 // dy_i
-    for (long long row = blockIdx.x * (long long)warps + warp; row < Et; row += (long long)gridDim.x * warps) {
+    float* base = att_smem + (size_t)warp * 8 * c;
+    float* sg = base;             // g_j
+    float* st = sg + c;           // theta_j
+    float* sgt = st + c;          // g_j * theta_j
+    float* sp = sgt + c;          // phi_i * log2e
+    float* sm = sp + c;           // row maximum (log2 domain)
+    float* sw = sm + c;           // w_i
+    float* swp = sw + c;          // w_i * phi_i
+    float* swyp = swp + c;        // w_i * y_i * phi_i
+    for (long long row = blockIdx.x * (long long)ATT_WARPS + warp; row < Et; row += (long long)gridDim.x * ATT_WARPS) {
         const float* r = gtp + row * 3 * c;
         const long long gi = row / Ep;
         const int k = (int)(row - gi * Ep);
@@ -182,7 +181,7 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
         float tmax = -INFINITY, tmin = INFINITY;
         for (int j = lane; j < c; j += 32) {
             const float g = r[j], t = r[c + j];
-            sg[j] = g; st[j] = t; sdy[j] = dy[j];
+            sg[j] = g; st[j] = t; sgt[j] = g * t;
             tmax = fmaxf(tmax, t); tmin = fminf(tmin, t);
         }
 #pragma unroll
@@ -191,37 +190,72 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
             tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
         }
         __syncwarp();
-        for (int i = lane; i < c; i += 32) {
-            const float phi = r[2 * c + i];
-            const float p = phi * LOG2E;
-            const float m = p >= 0.f ? p * tmax : p * tmin;
-            float num = 0.f, den = 0.f, agt = 0.f, at = 0.f;
-            float* Pi = P + i * pitch;
-            for (int j = 0; j < c; ++j) {
-                const float e = exp2f(fmaf(p, st[j], -m));
-                Pi[j] = e;
-                den += e;
-                num = fmaf(e, sg[j], num);
-                at = fmaf(e, st[j], at);
-                agt = fmaf(e * sg[j], st[j], agt);
+        // ---- sweep 1: two i per lane share the broadcast loads of (theta, g, g*theta)
+        for (int ib = 0; ib < c; ib += 64) {
+            const int i0 = ib + lane, i1 = i0 + 32;
+            const bool v0 = i0 < c, v1 = i1 < c;
+            const float phi0 = v0 ? r[2 * c + i0] : 0.f, phi1 = v1 ? r[2 * c + i1] : 0.f;
+            const float p0 = phi0 * LOG2E, p1 = phi1 * LOG2E;
+            const float m0 = p0 >= 0.f ? p0 * tmax : p0 * tmin;
+            const float m1 = p1 >= 0.f ? p1 * tmax : p1 * tmin;
+            float den0 = 0.f, num0 = 0.f, at0 = 0.f, agt0 = 0.f, den1 = 0.f, num1 = 0.f, at1 = 0.f, agt1 = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < c; j += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(st + j);
+                const float4 g4 = *reinterpret_cast<const float4*>(sg + j);
+                const float4 x4 = *reinterpret_cast<const float4*>(sgt + j);
+                const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float e0 = exp2f(fmaf(p0, tt[u], -m0));
+                    const float e1 = exp2f(fmaf(p1, tt[u], -m1));
+                    den0 += e0; num0 = fmaf(e0, gg[u], num0); at0 = fmaf(e0, tt[u], at0); agt0 = fmaf(e0, xx[u], agt0);
+                    den1 += e1; num1 = fmaf(e1, gg[u], num1); at1 = fmaf(e1, tt[u], at1); agt1 = fmaf(e1, xx[u], agt1);
+                }
             }
-            const float inv = 1.f / den;
-            const float yi = num * inv;
-            const float w = sdy[i] * inv;
-            sw[i] = w; swp[i] = w * phi; swyp[i] = w * yi * phi;
-            dgtp[row * ld_dgtp + 2 * c + i] = __float2bfloat16_rn(w * (agt - yi * at));   // dphi_i
+            if (v0) {
+                const float inv = 1.f / den0, y = num0 * inv, w = dy[i0] * inv;
+                sp[i0] = p0; sm[i0] = m0; sw[i0] = w; swp[i0] = w * phi0; swyp[i0] = w * y * phi0;
+                dgtp[row * ld_dgtp + 2 * c + i0] = __float2bfloat16_rn(w * (agt0 - y * at0));
+            }
+            if (v1) {
+                const float inv = 1.f / den1, y = num1 * inv, w = dy[i1] * inv;
+                sp[i1] = p1; sm[i1] = m1; sw[i1] = w; swp[i1] = w * phi1; swyp[i1] = w * y * phi1;
+                dgtp[row * ld_dgtp + 2 * c + i1] = __float2bfloat16_rn(w * (agt1 - y * at1));
+            }
         }
         __syncwarp();
-        for (int j = lane; j < c; j += 32) {
-            float dg = 0.f, t1 = 0.f, t2 = 0.f;
-            for (int i = 0; i < c; ++i) {
-                const float pij = P[i * pitch + j];
-                dg = fmaf(sw[i], pij, dg);
-                t1 = fmaf(swp[i], pij, t1);
-                t2 = fmaf(swyp[i], pij, t2);
+        // ---- sweep 2: two j per lane share the broadcast loads of (p, m, w, w phi, w y phi)
+        for (int jb = 0; jb < c; jb += 64) {
+            const int j0 = jb + lane, j1 = j0 + 32;
+            const bool v0 = j0 < c, v1 = j1 < c;
+            const float th0 = v0 ? st[j0] : 0.f, th1 = v1 ? st[j1] : 0.f;
+            float dg0 = 0.f, a0 = 0.f, b0 = 0.f, dg1 = 0.f, a1 = 0.f, b1 = 0.f;
+#pragma unroll 2
+            for (int i = 0; i < c; i += 4) {
+                const float4 p4 = *reinterpret_cast<const float4*>(sp + i);
+                const float4 m4 = *reinterpret_cast<const float4*>(sm + i);
+                const float4 w4 = *reinterpret_cast<const float4*>(sw + i);
+                const float4 q4 = *reinterpret_cast<const float4*>(swp + i);
+                const float4 z4 = *reinterpret_cast<const float4*>(swyp + i);
+                const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, qq[4] = {q4.x, q4.y, q4.z, q4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float e0 = exp2f(fmaf(pp[u], th0, -mm[u]));
+                    const float e1 = exp2f(fmaf(pp[u], th1, -mm[u]));
+                    dg0 = fmaf(ww[u], e0, dg0); a0 = fmaf(qq[u], e0, a0); b0 = fmaf(zz[u], e0, b0);
+                    dg1 = fmaf(ww[u], e1, dg1); a1 = fmaf(qq[u], e1, a1); b1 = fmaf(zz[u], e1, b1);
+                }
             }
-            dgtp[row * ld_dgtp + j] = __float2bfloat16_rn(dg);
-            dgtp[row * ld_dgtp + c + j] = __float2bfloat16_rn(sg[j] * t1 - t2);            // dtheta_j
+            if (v0) {
+                dgtp[row * ld_dgtp + j0] = __float2bfloat16_rn(dg0);
+                dgtp[row * ld_dgtp + c + j0] = __float2bfloat16_rn(sg[j0] * a0 - b0);
+            }
+            if (v1) {
+                dgtp[row * ld_dgtp + j1] = __float2bfloat16_rn(dg1);
+                dgtp[row * ld_dgtp + c + j1] = __float2bfloat16_rn(sg[j1] * a1 - b1);
+            }
         }
         __syncwarp();
     }
@@ -507,23 +541,57 @@ __global__ void pose_loss_final_kernel(const float* __restrict__ partial, int nb
 // ------------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix (bias gradients): stage 1 per row-slab, stage 2 over slabs.
 // ------------------------------------------------------------------------------------------------
-constexpr int COLSUM_ROWS = 512;
-__global__ void colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int cols,
-                                     const float* __restrict__ row_w, int row_w_mod, float* __restrict__ part) {
-    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-    if (c >= cols) return;
+constexpr int COLSUM_ROWS = 256;
+constexpr int COLSUM_THREADS = 256;
+// A block owns COLSUM_ROWS rows and all columns: thread = (column group of 8, row phase); phases are folded in smem.
+__global__ void __launch_bounds__(COLSUM_THREADS)
+colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int cols,
+                     const float* __restrict__ row_w, int row_w_mod, float* __restrict__ part) {
+    __shared__ float red[8][COLSUM_THREADS];
+    const int cg = cols >> 3;                                   // <= COLSUM_THREADS (host-checked)
+    const int phases = COLSUM_THREADS / cg;
+    const int my_cg = threadIdx.x % cg, my_ph = threadIdx.x / cg;
     const long long r0 = (long long)blockIdx.x * COLSUM_ROWS, r1 = min(r0 + COLSUM_ROWS, rows);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long r = r0; r < r1; ++r) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(v + r * ldv + c)), f);
-        const float wgt = row_w ? __ldg(row_w + (r % row_w_mod)) : 1.f;
+    if (my_ph < phases) {
+#pragma unroll 4
+        for (long long r = r0 + my_ph; r < r1; r += phases) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(v + r * ldv + my_cg * 8)), f);
+            const float wgt = row_w ? __ldg(row_w + (r % row_w_mod)) : 1.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = fmaf(wgt, f[q], acc[q]);
+            for (int q = 0; q < 8; ++q) acc[q] = fmaf(wgt, f[q], acc[q]);
+        }
     }
-    float* o = part + (size_t)blockIdx.x * cols + c;
-    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) red[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    if (my_ph == 0) {
+        for (int ph = 1; ph < phases; ++ph) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += red[q][ph * cg + my_cg];
+        }
+        float* o = part + (size_t)blockIdx.x * cols + my_cg * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
+// out[i] (+)= sum_b part[b, i] with the parts spread over 8 phases per column (fixed order => deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_wide_kernel(const float* __restrict__ part, int nparts, long long stride, int n,
+                            float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][32];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), ph = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < n)
+        for (int b = ph; b < nparts; b += 8) s += part[(size_t)b * stride + col];
+    red[ph][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ph == 0 && col < n) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s += red[k][threadIdx.x & 31];
+        out[col] = accumulate ? out[col] + s : s;
+    }
 }
 
 }  // namespace rpg
@@ -579,19 +647,16 @@ int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy,
 int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
                       rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream) {
     if (!gtp || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd: bad arguments");
-    const size_t per_warp = ((size_t)c * (c + 1) + 6 * (size_t)c) * sizeof(float);
-    int warps = (int)((200 * 1024) / per_warp);
-    if (warps > ATT_WARPS) warps = ATT_WARPS;
-    if (warps < 1) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c too large for the shared-memory formulation");
-    const size_t smem = per_warp * warps;
-    static size_t configured = 0;
+    if (c % 4 || c < 4 || c > 512) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c must be a multiple of 4 in [4,512]");
+    const size_t smem = (size_t)ATT_WARPS * 8 * c * sizeof(float);
+    static size_t configured = 48 * 1024;
     if (smem > configured) {
         cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    const int grid = grid_for(Et, warps, 148 * 4);
+    const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
     attention_bwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
-                                                                           Et, c, warps, reinterpret_cast<bf16*>(dgtp), ld_dgtp);
+                                                                           Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp);
     return check_launch("attention_bwd_kernel");
 }
 
@@ -665,9 +730,9 @@ int64_t rpg_head_bwd_ws_floats(int64_t rows, int D) {
 }
 
 int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed,
-                 float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf, float* dw6, float* db6,
-                 int accumulate, float* ws, rpg_stream_t stream) {
-    if (!dpose || !feat || !w6 || !dw6 || !db6 || !ws || rows <= 0 || D % 8 || ldf % 8 || D > 8 * 1024)
+                 float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf, float* dw_t, float* dw_q,
+                 float* db_t, float* db_q, int accumulate, float* ws, rpg_stream_t stream) {
+    if (!dpose || !feat || !w6 || !dw_t || !dw_q || !db_t || !db_q || !ws || rows <= 0 || D % 8 || ldf % 8 || D > 8 * 1024)
         return set_error(RPG_E_ARG, "head_bwd: bad arguments");
     const int blocks = (int)((rows + HEADB_ROWS_PER_BLOCK - 1) / HEADB_ROWS_PER_BLOCK);
     float* dw_part = ws;
@@ -682,10 +747,15 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
                                                db_part);
     int rc = check_launch("head_bwd_kernel");
     if (rc) return rc;
-    reduce_partials_kernel<<<grid_for(6 * D, 256), 256, 0, s>>>(dw_part, blocks, 6 * (long long)D, 6 * (long long)D, dw6, accumulate);
-    if ((rc = check_launch("reduce_partials_kernel"))) return rc;
-    reduce_partials_kernel<<<1, 32, 0, s>>>(db_part, blocks, 6, 6, db6, accumulate);
-    return check_launch("reduce_partials_kernel");
+    // rows 0..2 -> translation head (fc_xyz*), rows 3..5 -> rotation head (fc_wpqr*)
+    reduce_partials_wide_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(dw_part, blocks, 6 * (long long)D, 3 * D, dw_t, accumulate);
+    if ((rc = check_launch("reduce_partials_wide_kernel"))) return rc;
+    reduce_partials_wide_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(dw_part + 3 * D, blocks, 6 * (long long)D, 3 * D, dw_q, accumulate);
+    if ((rc = check_launch("reduce_partials_wide_kernel"))) return rc;
+    reduce_partials_wide_kernel<<<1, 256, 0, s>>>(db_part, blocks, 6, 3, db_t, accumulate);
+    if ((rc = check_launch("reduce_partials_wide_kernel"))) return rc;
+    reduce_partials_wide_kernel<<<1, 256, 0, s>>>(db_part + 3, blocks, 6, 3, db_q, accumulate);
+    return check_launch("reduce_partials_wide_kernel");
 }
 
 int64_t rpg_pose_loss_ws_floats(int64_t Et) { return 2 * (int64_t)grid_for(Et, LOSS_THREADS, 1024); }
@@ -709,17 +779,16 @@ int64_t rpg_colsum_scratch_floats(int64_t rows, int cols) {
 
 int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod, float* out,
                     int accumulate, float* scratch, rpg_stream_t stream) {
-    if (!v || !out || !scratch || rows <= 0 || cols % 8 || ldv % 8) return set_error(RPG_E_ARG, "colsum: bad arguments");
+    if (!v || !out || !scratch || rows <= 0 || cols % 8 || ldv % 8 || cols / 8 > COLSUM_THREADS)
+        return set_error(RPG_E_ARG, "colsum: bad arguments (cols must be a multiple of 8, at most 2048)");
     const int slabs = (int)((rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
-    const int threads = 64;
-    dim3 grid(slabs, (cols / 8 + threads - 1) / threads);
     cudaStream_t s = as_stream(stream);
-    colsum_stage1_kernel<<<grid, threads, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
-                                                  row_w_mod > 0 ? row_w_mod : 1, scratch);
+    colsum_stage1_kernel<<<slabs, COLSUM_THREADS, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
+                                                          row_w_mod > 0 ? row_w_mod : 1, scratch);
     int rc = check_launch("colsum_stage1_kernel");
     if (rc) return rc;
-    reduce_partials_kernel<<<grid_for(cols, 128), 128, 0, s>>>(scratch, slabs, cols, cols, out, accumulate);
-    return check_launch("reduce_partials_kernel");
+    reduce_partials_wide_kernel<<<(cols + 31) / 32, 256, 0, s>>>(scratch, slabs, cols, cols, out, accumulate);
+    return check_launch("reduce_partials_wide_kernel");
 }
 
 int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols, float* out, int ldo,

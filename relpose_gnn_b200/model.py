@@ -62,28 +62,31 @@ class _StackFn(torch.autograd.Function):
         D, R = model.node_dim, model.gnn_recursion
         dev = xb.device
         names = model._param_names()
-        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in zip(names, model._ordered_params())}
+        params = model._ordered_params()
+        direct = model.fused_grad_accumulation and all(p.grad is not None for p in params)
+        if direct:      # accumulate straight into param.grad (views of one flat bucket): no per-parameter torch kernels
+            grads = {n: p.grad for n, p in zip(names, params)}
+        else:
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+            grads, off = {}, 0
+            for n, p in zip(names, params):
+                grads[n] = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
         lgrads = {n: grads["gnn1." + n] for n in PARAM_ORDER}
         ws = ops.wgrad_ws(D, dev)
 
         # heads (posenet.py:1077-1086): gradient w.r.t. the pre-ReLU layer outputs (mask_relu)
         d_e = d_x = None
         if d_pose_e is not None:
-            dw6, db6 = torch.zeros(6, D, device=dev), torch.zeros(6, device=dev)
-            d_e = ops.head_bwd(d_pose_e.contiguous().float(), e_last, sw["w6e"], dw6, db6, keep=keep_e, seed=seed + 1,
-                               p_drop=p_drop, mask_relu=True)
-            grads["fc_xyz_R.weight"] += dw6[:3]
-            grads["fc_wpqr_R.weight"] += dw6[3:]
-            grads["fc_xyz_R.bias"] += db6[:3]
-            grads["fc_wpqr_R.bias"] += db6[3:]
+            d_e = ops.head_bwd(d_pose_e.contiguous().float(), e_last, sw["w6e"], grads["fc_xyz_R.weight"],
+                               grads["fc_wpqr_R.weight"], grads["fc_xyz_R.bias"], grads["fc_wpqr_R.bias"],
+                               keep=keep_e, seed=seed + 1, p_drop=p_drop, mask_relu=True)
         if d_pose_n is not None:
-            dw6, db6 = torch.zeros(6, D, device=dev), torch.zeros(6, device=dev)
-            d_x = ops.head_bwd(d_pose_n.contiguous().float(), x_last, sw["w6n"], dw6, db6, keep=keep_x, seed=seed,
-                               p_drop=p_drop, mask_relu=True)
-            grads["fc_xyz.weight"] += dw6[:3]
-            grads["fc_wpqr.weight"] += dw6[3:]
-            grads["fc_xyz.bias"] += db6[:3]
-            grads["fc_wpqr.bias"] += db6[3:]
+            d_x = ops.head_bwd(d_pose_n.contiguous().float(), x_last, sw["w6n"], grads["fc_xyz.weight"],
+                               grads["fc_wpqr.weight"], grads["fc_xyz.bias"], grads["fc_wpqr.bias"],
+                               keep=keep_x, seed=seed, p_drop=p_drop, mask_relu=True)
+        if d_e is None and d_x is None:
+            return (None,) * (4 + len(names))
 
         for r in range(R - 1, -1, -1):
             d_x, d_e = layer_backward_raw(lw, graph, acts[r], d_x, d_e, lgrads, mask_dx=(r > 0), mask_de=True)
@@ -101,6 +104,8 @@ class _StackFn(torch.autograd.Function):
         ops.wgrad(dpmm[:, D:], xb, gw[:, D:], ws)
         ops.colsum(dpmm[:, :D], grads["proj_edge.bias"])        # every edge has exactly one lower endpoint
         dx = ops.to_f32(dx) if ctx.x_dtype == torch.float32 else dx
+        if direct:
+            return (dx, None, None, None) + (None,) * len(names)
         return (dx, None, None, None) + tuple(grads[n] for n in names)
 
 
@@ -124,6 +129,18 @@ class RelPoseGNN(nn.Module):
         self._stack_cache = {}
         self.dropout_seed = 0x5EED
         self.keep_debug_activations = False      # tests: keep the saved activations of the last forward
+        self.fused_grad_accumulation = False     # see attach_grad_bucket
+
+    def attach_grad_bucket(self, bucket):
+        """Makes backward accumulate every gradient of this module directly into `param.grad` (which a
+        parallel.FlatGradBucket has pointed at one flat buffer) instead of returning fresh tensors to autograd:
+        the weight-gradient kernels already accumulate (+=), so a step needs no per-parameter add kernels."""
+        mine = {id(p) for p in self.parameters()}
+        have = {id(p) for p in bucket.params}
+        if not mine <= have:
+            raise ValueError("the bucket must cover every parameter of this module")
+        self.fused_grad_accumulation = True
+        return self
 
     def _param_names(self):
         return (["proj_edge.weight", "proj_edge.bias"] + ["gnn1." + n for n in PARAM_ORDER] +

@@ -170,15 +170,16 @@ def head_fwd(feat, w6, b6, keep=None, seed=0, p_drop=0.0):
     return pose
 
 
-def head_bwd(dpose, feat, w6, dw6, db6, keep=None, seed=0, p_drop=0.0, mask_relu=True, want_dfeat=True,
+def head_bwd(dpose, feat, w6, dw_t, dw_q, db_t, db_q, keep=None, seed=0, p_drop=0.0, mask_relu=True, want_dfeat=True,
              accumulate=True):
+    """Backward of head_fwd; dw_t/db_t (translation head) and dw_q/db_q (rotation head) are accumulated in place."""
     lib = _lib.load()
     rows, D = feat.shape
     ws = torch.empty(lib.rpg_head_bwd_ws_floats(rows, D), dtype=torch.float32, device=feat.device)
     dfeat = torch.empty(rows, D, dtype=BF16, device=feat.device) if want_dfeat else None
     check(lib.rpg_head_bwd(dpose.data_ptr(), feat.data_ptr(), feat.stride(0), rows, D, ptr(keep), seed, p_drop,
-                           w6.data_ptr(), int(mask_relu), ptr(dfeat), D, dw6.data_ptr(), db6.data_ptr(),
-                           int(accumulate), ws.data_ptr(), _stream(feat)), "rpg_head_bwd")
+                           w6.data_ptr(), int(mask_relu), ptr(dfeat), D, dw_t.data_ptr(), dw_q.data_ptr(),
+                           db_t.data_ptr(), db_q.data_ptr(), int(accumulate), ws.data_ptr(), _stream(feat)), "rpg_head_bwd")
     return dfeat
 
 

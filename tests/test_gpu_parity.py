@@ -303,3 +303,34 @@ def test_gemm_probes():
     spec.loader.exec_module(mod)
     assert mod.nt_cases()
     assert mod.tn_cases()
+
+
+def test_fused_gradient_accumulation_matches_autograd_path():
+    """attach_grad_bucket: kernels accumulate straight into the flat bucket; must equal the grads autograd returns."""
+    from relpose_gnn_b200 import parallel
+    D, N, Gn = 256, 9, 11
+    case = R.synth_stack_case(D, N, Gn, 77, droprate=0.5, edge_dropout=True)
+    sd = {k: v.float() for k, v in case["params"].items()}
+    x = case["x"].float().to(dev())
+    ei = case["edge_index"].to(dev())
+    poses = case["poses"].float().to(dev())
+    kx, ke = case["keep_x"].to(dev()), case["keep_e"].to(dev())
+
+    def run(fused):
+        model = rpg.RelPoseGNN(D, D, D, droprate=0.5).to(dev())
+        model.load_state_dict(sd, strict=False)
+        crit = rpg.PoseNetCriterion(0.0, -2.0).to(dev())
+        params = list(model.parameters()) + list(crit.parameters())
+        if fused:
+            bucket = parallel.FlatGradBucket(params)
+            model.attach_grad_bucket(bucket)
+        for _ in range(2):                      # two steps: accumulation semantics (+=) must match too
+            pn, pe, _ = model(x, ei, keep_x=kx, keep_e=ke)
+            loss, _, _ = crit(pe, poses, ei)
+            loss.backward()
+        return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for p in params])
+
+    a, b = run(False), run(True)
+    # same kernels, different association of the two steps' sums ((g1 + a) + b vs g1 + (a + b)): not bitwise
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert (a - b).norm() / b.norm() < 1e-6
