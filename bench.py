@@ -173,7 +173,8 @@ def run_ours(args):
     poses_host = (0.1 * torch.randn(G * N, 6, generator=gen)).pin_memory()
     x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
     mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
-    masks = [edge_dropout_keep(H, mask_rng) if train else np.ones(H, bool) for _ in range(4 * (args.warmup + args.steps) + 8)]
+    masks = [edge_dropout_keep(H, mask_rng) if train else np.ones(H, bool)
+             for _ in range(2 * args.trials * args.steps + max(args.warmup, 3) + 8)]
     mask_iter = iter(masks)
 
     def step(x, poses, read_back):
@@ -216,13 +217,15 @@ def run_ours(args):
         step(x_dev, poses_dev, False)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and args.clocks:
         sampler.start()
     launches0 = lib.rpg_launch_count()
-    ms_step = timed(args.steps, e2e=False)
-    launches = (lib.rpg_launch_count() - launches0) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(args.steps, e2e=True)
+    trials = [timed(args.steps, e2e=False) for _ in range(args.trials)]      # each trial: exactly K steps, max over ranks
+    launches = (lib.rpg_launch_count() - launches0) / (args.steps * args.trials)
+    clocks = sampler.stop() if (rank == 0 and args.clocks) else None
+    ms_step = float(np.median(trials))
+    trials_e2e = [timed(args.steps, e2e=True) for _ in range(args.trials)]
+    ms_e2e = float(np.median(trials_e2e))
 
     # roofline leg: per-launch CUDA events on the tcgen05 GEMM kernel during one more step (same stream)
     keep_prof = masks[0]
@@ -245,6 +248,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "trials_ms_per_step": trials, "trials_e2e_ms_per_step": trials_e2e,
             "config": {"workload": args.workload, "graphs_per_gpu": G, "nodes_per_graph": N, "D": D, "mode": mode,
                        "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if train else 1.0,
                        "mean_edges_per_graph": mean_Ep, "feature_dropout": 0.5,
@@ -282,10 +286,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--trials", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_4096x9", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=128, help="graphs per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-clocks", dest="clocks", action="store_false", help="(experiments) skip the nvidia-smi sampler")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -121,9 +121,17 @@ typedef struct {
   int ldo;
   float* out_f32;             /* fp32 output (pitch ldo_f32) or NULL                                  */
   int ldo_f32;
+  /* ReLU patterns as bit matrices [M, ld bytes], bit (col & 7) of byte (col >> 3): 16x less traffic than a bf16 mask */
+  const uint8_t* mask_bits;   /* * pattern bit (applied where `mask` would be) or NULL                */
+  int mask_bits_ld;
+  uint8_t* out_bits;          /* receives (stored value > 0) or NULL; needs N % 64 == 0               */
+  int out_bits_ld;
 } rpg_gemm_t;
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream);
+/* Tuning knob: CTAs per thread-block cluster of the GEMM kernel (1, or 2 = weight tiles fetched once per pair
+ * and TMA-multicast into both shared memories; the default).                                        */
+int rpg_set_gemm_cluster(int ctas_per_cluster);
 
 /* Weight gradient dW[M,N] += A[R,M]^T B[R,N] (fp32, pitch ldo): TN GEMM split over R into `ws`
  * (rpg_layer_bwd_ws_floats elements) followed by the deterministic reduction below.                 */
@@ -180,7 +188,7 @@ int rpg_segment_sum(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, c
  * pminmax [Nt, 2D] = x * [W_min; W_max]^T (proj_edge.weight[:, 0:D] and [:, D:2D]).
  * Backward = rpg_segment_sum over min_ptr/max_ptr with mask = e0, then node-level GEMMs.             */
 int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D,
-                      rpg_bf16* e0, int lde, rpg_stream_t stream);
+                      rpg_bf16* e0, int lde, uint8_t* e0_bits, rpg_stream_t stream);
 
 /* Feature dropout + pose heads, posenet.py:1073-1086: pose[r, 0:3] = fc_xyz(drop(f[r])), [3:6] = fc_wpqr(..).
  * Dropout follows F.dropout (kept entries scaled by 1/(1-p)).  The keep decision is either an explicit
@@ -226,6 +234,8 @@ typedef struct {
   const rpg_bf16* W2m;            /* [D, D]   mlp.2                                                      */
   const rpg_bf16* Wgtp;           /* [3c, D]  att.g | att.theta | att.phi                                */
   const rpg_bf16* WW;             /* [D, c]   att.W                                                      */
+  const rpg_bf16* WWI;            /* [D, pad64(c) + D] = [att.W | I]: z = [y | m] [W | I]^T carries the residual
+                                     of att.py:33 through the TMA/MMA pipeline instead of the epilogue         */
   const rpg_bf16* W1u;            /* [D, 2D]  mlp_updating.0                                             */
   const rpg_bf16* W2u;            /* [D, D]   mlp_updating.2                                             */
   /* transposed copies, backward (dgrad) */
@@ -254,6 +264,14 @@ typedef struct {                  /* activations of one layer call; all bf16 unl
   rpg_bf16* h3;                   /* [Nt, D]                                                            */
   rpg_bf16* out;                  /* [Nt, D] out (pre-ReLU)                                             */
   rpg_bf16* out_relu;             /* [Nt, D] optional relu(out) (posenet.py:1064)                       */
+  /* ReLU bit patterns [rows, D/8 bytes] written by the forward and consumed by the backward epilogues    */
+  uint8_t* h1_bits;               /* [Et, D/8] */
+  uint8_t* h2_bits;               /* [Et, D/8] */
+  uint8_t* h3_bits;               /* [Nt, D/8] */
+  uint8_t* e_new_bits;            /* [Et, D/8] optional: (e_new > 0) for the next round's mask_de        */
+  uint8_t* out_bits;              /* [Nt, D/8] optional: (out > 0) for the next round's mask_dx          */
+  const uint8_t* x_bits;          /* [Nt, D/8] optional pattern of the input x (used when mask_dx)       */
+  const uint8_t* e_bits;          /* [Et, D/8] optional pattern of the input e (used when mask_de)       */
 } rpg_layer_acts_t;
 
 int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,

@@ -35,19 +35,21 @@ class Gemm(C.Structure):
                 ("bias", P), ("gadd", P * 2), ("gmap", P * 2), ("gadd_ld", I * 2), ("Ep", I), ("Nn", I),
                 ("resid", P), ("resid_ld", I), ("row_scale", P), ("row_scale_mod", I),
                 ("mask", P), ("mask_ld", I), ("relu", I),
-                ("out", P), ("out_relu", P), ("ldo", I), ("out_f32", P), ("ldo_f32", I)]
+                ("out", P), ("out_relu", P), ("ldo", I), ("out_f32", P), ("ldo_f32", I),
+                ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I)]
 
 
 class LayerWeights(C.Structure):
     _fields_ = [("D", I)] + [(n, P) for n in (
-        "Wn", "W1e_e", "W2e", "W1m_e", "W2m", "Wgtp", "WW", "W1u", "W2u",
+        "Wn", "W1e_e", "W2e", "W1m_e", "W2m", "Wgtp", "WW", "WWI", "W1u", "W2u",
         "WnT", "W1e_eT", "W2eT", "W1m_eT", "W2mT", "W2uT", "WgtpT", "WWT", "W1uT",
         "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")]
 
 
 class LayerActs(C.Structure):
     _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
-                                 "h3", "out", "out_relu")]
+                                 "h3", "out", "out_relu", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
+                                 "x_bits", "e_bits")]
 
 
 class LayerGrads(C.Structure):
@@ -71,6 +73,7 @@ SIGNATURES = {
                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rpg_validate_edge_index": (I, [P, I64, I, I, I, P, P, P, P]),
     "rpg_gemm": (I, [C.POINTER(Gemm), P]),
+    "rpg_set_gemm_cluster": (I, [I]),
     "rpg_wgrad": (I, [P, I, I, P, I, I, I64, P, P, I, P]),
     "rpg_struct_sizes": (None, [C.POINTER(C.c_int32)]),
     "rpg_reduce_splits": (I, [P, I, I64, I, I, P, I, I, P]),
@@ -82,7 +85,7 @@ SIGNATURES = {
     "rpg_aggregate_mean": (I, [P, I, C.POINTER(Graph), I, P, I, P]),
     "rpg_edge_to_node_sum": (I, [P, I, C.POINTER(Graph), I, I, P, I, P]),
     "rpg_segment_sum": (I, [P, I, P, I, P, P, P, C.POINTER(Graph), I, P, I, P]),
-    "rpg_edge_init_fwd": (I, [P, I, P, C.POINTER(Graph), I, P, I, P]),
+    "rpg_edge_init_fwd": (I, [P, I, P, C.POINTER(Graph), I, P, I, P, P]),
     "rpg_dropout_mask": (I, [U64, F, I64, I, P, P]),
     "rpg_head_fwd": (I, [P, I, I64, I, P, U64, F, P, P, P, P]),
     "rpg_head_bwd_ws_floats": (I64, [I64, I]),
@@ -130,6 +133,9 @@ def load(build_if_missing=True):
             fn.restype = res
             fn.argtypes = args
         _check_layout(lib)
+        if os.environ.get("RPG_GEMM_CLUSTER"):          # tuning / A-B knob: 1 = no clusters, 2 = multicast pairs
+            if lib.rpg_set_gemm_cluster(int(os.environ["RPG_GEMM_CLUSTER"])) != 0:
+                raise RpgError("RPG_GEMM_CLUSTER must be 1 or 2")
         _lib = lib
     return _lib
 

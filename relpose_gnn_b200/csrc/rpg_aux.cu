@@ -304,7 +304,7 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
 // e0 = relu(pmin[node(min(s,t))] + pmax[node(max(s,t))] + bias)      (posenet.py:1014-1017, 1053-1055)
 __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, const float* __restrict__ bias,
                                      const int* __restrict__ tsrc, const int* __restrict__ tdst, long long Et, int N,
-                                     int Ep, int D, bf16* __restrict__ e0, int lde) {
+                                     int Ep, int D, bf16* __restrict__ e0, int lde, uint8_t* __restrict__ bits) {
     const int tpr = D >> 3;
     const long long total = Et * tpr;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -323,6 +323,12 @@ __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, cons
 #pragma unroll
         for (int q = 0; q < 8; ++q) a[q] = fmaxf(a[q] + b[q] + bb[q], 0.f);
         *reinterpret_cast<uint4*>(e0 + row * lde + c) = pack8(a);
+        if (bits) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m |= (uint32_t)(a[q] > 0.f) << q;
+            bits[row * (D >> 3) + (c >> 3)] = (uint8_t)m;
+        }
     }
 }
 
@@ -689,12 +695,12 @@ int rpg_segment_sum(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, c
 }
 
 int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e0,
-                      int lde, rpg_stream_t stream) {
+                      int lde, uint8_t* e0_bits, rpg_stream_t stream) {
     if (!pminmax || !bias || !graph || !e0 || D % 8 || ldp % 8 || lde % 8) return set_error(RPG_E_ARG, "edge_init_fwd: bad arguments");
     const long long Et = (long long)graph->G * graph->Ep;
     edge_init_fwd_kernel<<<grid_for(Et * (D / 8), 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const bf16*>(pminmax), ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D,
-        reinterpret_cast<bf16*>(e0), lde);
+        reinterpret_cast<bf16*>(e0), lde, e0_bits);
     return check_launch("edge_init_fwd_kernel");
 }
 

@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -33,7 +34,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int SMEM_RING_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-constexpr int SMEM_BYTES = SMEM_RING_BYTES + 256 + 1024;    // + barriers + alignment slack
+constexpr int SMEM_BAR_BYTES = 1024;                        // barriers + TMEM slot (keeps the staging 1024-aligned)
+constexpr int EPI_STAGE_BYTES = 32 * 128;                   // per epilogue warp: 32 rows x 128 B, TMA 128B-swizzle layout
+constexpr int SMEM_BYTES = SMEM_RING_BYTES + SMEM_BAR_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;   // + align slack
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct GemmKParams {
     int mode, M, N, block_n;
@@ -58,6 +62,10 @@ struct GemmKParams {
     int ldo;
     float* out_f32;
     int ldo_f32;
+    const uint8_t* mask_bits;      // ReLU pattern as 1 bit per element: [M, mask_bits_ld bytes]
+    int mask_bits_ld;
+    uint8_t* out_bits;             // pattern (value > 0) of the stored result
+    int out_bits_ld;
 };
 
 __device__ __forceinline__ void add_bf16x8(float* f, const uint4& u) {
@@ -75,11 +83,15 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& u) {
     }
 }
 
-template <int MODE>
+// CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on adjacent 128-row blocks of the same column
+// block and each fetches HALF of every weight (B) tile, multicast into both shared memories: the L2 -> SM traffic for
+// B, which dominates at the small N, K of this path (every tile re-reads the whole weight panel), is halved.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-               const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutRelu,
+               const __grid_constant__ CUtensorMap tmOutF32, const GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -97,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
         fence_mbar_init();
     }
@@ -106,24 +118,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    const int cta_rank = CL == 1 ? 0 : (int)cluster_ctarank();
+    const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;     // a worker = one cluster
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_m_units = (num_m_blocks + CL - 1) / CL;                  // CL adjacent row blocks per work item
     const int num_n_blocks = (p.N + p.block_n - 1) / p.block_n;
-    const int num_tiles = num_m_blocks * num_n_blocks;
+    const int num_tiles = num_m_units * num_n_blocks;
     const int num_items = MODE == 0 ? num_tiles : num_tiles * p.splits;
     const uint32_t stage_tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+    constexpr uint16_t kAllCtas = (1u << CL) - 1;
 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            for (int item = worker; item < num_items; item += num_workers) {
                 const int tile = MODE == 0 ? item : item / p.splits;
-                const int m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
+                const int m_blk = (tile / num_n_blocks) * CL + cta_rank, n_blk = tile % num_n_blocks;
                 if (MODE == 0) {
                     int kb_global = 0;
                     for (int s = 0; s < 3; ++s) {
@@ -133,8 +149,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
                             tma_load_2d(tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K,
                                         m_blk * BLOCK_M);
-                            tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb_global * BLOCK_K,
-                                        n_blk * p.block_n);
+                            if (CL == 1) {
+                                tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb_global * BLOCK_K,
+                                            n_blk * p.block_n);
+                            } else {       // my half of the weight rows, delivered to both CTAs
+                                const int half_rows = p.block_n / CL;
+                                tma_load_2d_mc(&tmB, &full_bar[stage],
+                                               smem_b + stage * B_STAGE_BYTES + cta_rank * half_rows * (BLOCK_K * 2),
+                                               kb_global * BLOCK_K, n_blk * p.block_n + cta_rank * half_rows, kAllCtas);
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -149,9 +172,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         for (int j = 0; j < BLOCK_M / 64; ++j)
                             tma_load_2d(&tmA0, &full_bar[stage], smem_a + stage * A_STAGE_BYTES + j * 8192,
                                         m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
-                        for (int j = 0; j < p.block_n / 64; ++j)
-                            tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
-                                        n_blk * p.block_n + j * 64, kb * BLOCK_K);
+                        for (int j = 0; j < p.block_n / 64; ++j) {
+                            if (CL == 1)
+                                tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
+                                            n_blk * p.block_n + j * 64, kb * BLOCK_K);
+                            else if (j % CL == cta_rank)
+                                tma_load_2d_mc(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
+                                               n_blk * p.block_n + j * 64, kb * BLOCK_K, kAllCtas);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -168,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            for (int item = worker; item < num_items; item += num_workers, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 int n_kb;
@@ -189,7 +217,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                         umma_bf16(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
-                    umma_commit(&empty_bar[stage]);           // frees the smem slot when these MMAs retire
+                    if (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    else umma_commit_mc(&empty_bar[stage], kAllCtas);   // ... in every CTA that multicasts into it
                     if (kb == n_kb - 1) umma_commit(&acc_full[acc]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -198,134 +227,231 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
     } else {
         // ---------------------------------------------------------------- epilogue warps
+        // Each thread owns one accumulator row (TMEM lane).  Row-per-thread global accesses would touch 32 different
+        // lines per instruction (measured: 37 % of all stall samples behind those stores), so everything goes through a
+        // per-warp staging tile [32 rows][128 B] in the TMA 128-byte-swizzle layout (16-byte chunk c of row r lives at
+        // chunk c ^ (r & 7): conflict-free for the row view and for the coalesced view):
+        //   results  : registers -> staging -> ONE TMA store per 32 x 64 tile (asynchronous, clipped at the tensor edge)
+        //   operands : coalesced 4-rows-x-128-B loads -> staging -> each thread reads back its own row
         const int ew = warp - 2;
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;                  // column interleave between the two warps of a quadrant
-        const int n_chunks = (p.block_n + 31) / 32;
+        const int half = ew >> 2;                  // the two warps of a quadrant alternate 64-column chunks
+        const int n_chunks = (p.block_n + 63) / 64;
+        uint8_t* stg = smem + SMEM_RING_BYTES + SMEM_BAR_BYTES + ew * EPI_STAGE_BYTES;
+        const int sub = lane >> 3, q8 = lane & 7;  // coalesced view: instruction i covers rows 4i + sub, chunk q8
+        uint8_t* my_row = stg + lane * 128;
+        const int my_sw = lane & 7;
         int it = 0;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        for (int item = worker; item < num_items; item += num_workers, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int tile = MODE == 0 ? item : item / p.splits;
-            const int m_blk = tile / num_n_blocks, n_blk = tile % num_n_blocks;
-            const int row = m_blk * BLOCK_M + quad * 32 + lane;
+            const int m_blk = (tile / num_n_blocks) * CL + cta_rank, n_blk = tile % num_n_blocks;
+            const int row0 = m_blk * BLOCK_M + quad * 32;
+            const int row = row0 + lane;
             const bool row_ok = row < p.M;
             bool zero_acc = false;
             if (MODE == 1) {
                 const int kb0 = (item % p.splits) * p.kb_per_split;
                 zero_acc = kb0 >= p.total_kb;
             }
-            mbar_wait(&acc_full[acc], acc_phase);
-            tc_fence_after();
-
-            const __nv_bfloat16* g0 = nullptr;
-            const __nv_bfloat16* g1 = nullptr;
+            int gnode0 = -1, gnode1 = -1;
             float rscale = 1.f;
             if (MODE == 0 && row_ok) {
                 if (p.gadd[0] || p.gadd[1]) {
                     const int gidx = row / p.Ep, k = row - gidx * p.Ep;
-                    if (p.gadd[0]) g0 = p.gadd[0] + (size_t)(gidx * p.Nn + __ldg(p.gmap[0] + k)) * p.gadd_ld[0];
-                    if (p.gadd[1]) g1 = p.gadd[1] + (size_t)(gidx * p.Nn + __ldg(p.gmap[1] + k)) * p.gadd_ld[1];
+                    if (p.gadd[0]) gnode0 = gidx * p.Nn + __ldg(p.gmap[0] + k);
+                    if (p.gadd[1]) gnode1 = gidx * p.Nn + __ldg(p.gmap[1] + k);
                 }
                 if (p.row_scale) rscale = __ldg(p.row_scale + (row % p.row_scale_mod));
             }
+            // ---- everything that does not need the accumulator is requested BEFORE waiting for it: the ReLU bit
+            // patterns of both chunks (8 bytes each) and the first two operand tiles of the first chunk.
+            unsigned long long mbits0 = ~0ull, mbits1 = ~0ull;
+            if (MODE == 0 && p.mask_bits && row_ok) {
+                const int n0a = n_blk * p.block_n + half * 64, n0b = n0a + 128;
+                if (half < n_chunks && n0a < p.N)
+                    mbits0 = __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits + (size_t)row * p.mask_bits_ld + (n0a >> 3)));
+                if (half + 2 < n_chunks && n0b < p.N)
+                    mbits1 = __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits + (size_t)row * p.mask_bits_ld + (n0b >> 3)));
+            }
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            bool released = false;
 
-            for (int c = half; c < n_chunks; c += 2) {
-                const int n0 = n_blk * p.block_n + c * 32;
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + c * 32, v);
-                tmem_ld_wait();
-                if (!row_ok || n0 >= p.N) continue;
-                const int nvalid = min(32, min(p.N - n0, p.block_n - c * 32));   // multiple of 8
-                float f[32];
+            for (int c = half, ci = 0; c < n_chunks; c += 2, ++ci) {
+                const int n0 = n_blk * p.block_n + c * 64;
+                const int ncols = min(64, min(p.N - n0, p.block_n - c * 64));   // multiple of 8 (host-checked)
+                if (ncols <= 0 || row0 >= p.M) break;
+                const int nq = ncols >> 3;                                       // valid 16-byte bf16 chunks per row
+
+                // ---- operand prefetch (coalesced view), issued before the TMEM read so the latencies overlap
+                uint4 bufA[8], bufB[8];
+                auto load_rows = [&](uint4 (&buf)[8], const __nv_bfloat16* base, int ld, int gnode, bool gathered) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = zero_acc ? 0.f : __uint_as_float(v[j]);
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + sub;
+                        long long rr = row0 + r;
+                        if (gathered) rr = __shfl_sync(0xffffffffu, gnode, r);   // node row of the owner lane r
+                        const bool ok = (row0 + r < p.M) && rr >= 0 && q8 < nq;
+                        buf[i] = ok ? __ldg(reinterpret_cast<const uint4*>(base + rr * ld + n0 + q8 * 8))
+                                    : make_uint4(0, 0, 0, 0);
+                    }
+                };
+                int nextop = 0;       // 0 gadd0, 1 gadd1, 2 resid, 3 mask, 4 none
+                auto issue = [&](uint4 (&buf)[8]) -> int {      // loads the next present operand into buf, returns its id
+                    while (nextop < 4) {
+                        const bool present = nextop == 0 ? p.gadd[0] != nullptr : nextop == 1 ? p.gadd[1] != nullptr
+                                           : nextop == 2 ? p.resid != nullptr : p.mask != nullptr;
+                        if (present) break;
+                        ++nextop;
+                    }
+                    const int op = nextop;
+                    if (op == 0) load_rows(buf, p.gadd[0], p.gadd_ld[0], gnode0, true);
+                    else if (op == 1) load_rows(buf, p.gadd[1], p.gadd_ld[1], gnode1, true);
+                    else if (op == 2) load_rows(buf, p.resid, p.resid_ld, 0, false);
+                    else if (op == 3) load_rows(buf, p.mask, p.mask_ld, 0, false);
+                    if (op < 4) ++nextop;
+                    return op;
+                };
+                int opA = 4, opB = 4;
+                if (MODE == 0) { opA = issue(bufA); opB = issue(bufB); }
+
+                // ---- accumulator -> registers
+                float f[64];
+                const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * ACC_STRIDE + c * 64;
+                tmem_ld_32x32(taddr, reinterpret_cast<uint32_t(&)[32]>(f[0]));
+                tmem_ld_32x32(taddr + 32, reinterpret_cast<uint32_t(&)[32]>(f[32]));
+                tmem_ld_wait();
+                if (c + 2 >= n_chunks) {          // last TMEM read of this tile by this warp: hand the stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    released = true;
+                }
+                if (zero_acc) {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) f[j] = 0.f;
+                }
+                // the staging tile is free once the previous TMA store of this warp has read it
+                if (lane == 0) bulk_wait_read_all();
+                __syncwarp();
 
                 if (MODE == 0) {
                     if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (j < nvalid) {
+                        for (int j = 0; j < 64; j += 4) {
+                            if (j < ncols) {
                                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
                                 f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
                             }
                         }
                     }
-                    if (g0) {
+                    bool scaled = p.row_scale == nullptr;
+                    auto stage_and_consume = [&](const uint4 (&buf)[8], int op) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            if (j < nvalid) add_bf16x8(f + j, __ldg(reinterpret_cast<const uint4*>(g0 + n0 + j)));
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 4 * i + sub;
+                            *reinterpret_cast<uint4*>(stg + r * 128 + ((q8 ^ (r & 7)) << 4)) = buf[i];
+                        }
+                        __syncwarp();
+                        if (op == 3 && !scaled) {                 // epilogue order: ... resid, row_scale, mask
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) f[j] *= rscale;
+                            scaled = true;
+                        }
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((qq ^ my_sw) << 4));
+                            if (op == 3) mask_bf16x8(f + 8 * qq, u); else add_bf16x8(f + 8 * qq, u);
+                        }
+                        __syncwarp();
+                    };
+                    while (opA < 4 || opB < 4) {
+                        if (opA < 4) { stage_and_consume(bufA, opA); opA = issue(bufA); }
+                        if (opB < 4) { stage_and_consume(bufB, opB); opB = issue(bufB); }
                     }
-                    if (g1) {
+                    if (!scaled) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            if (j < nvalid) add_bf16x8(f + j, __ldg(reinterpret_cast<const uint4*>(g1 + n0 + j)));
+                        for (int j = 0; j < 64; ++j) f[j] *= rscale;
                     }
-                    if (p.resid) {
-                        const __nv_bfloat16* r = p.resid + (size_t)row * p.resid_ld + n0;
+                    if (p.mask_bits) {
+                        const unsigned long long mb = ci == 0 ? mbits0 : mbits1;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            if (j < nvalid) add_bf16x8(f + j, __ldg(reinterpret_cast<const uint4*>(r + j)));
-                    }
-                    if (p.row_scale) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] *= rscale;
-                    }
-                    if (p.mask) {
-                        const __nv_bfloat16* mk = p.mask + (size_t)row * p.mask_ld + n0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            if (j < nvalid) mask_bf16x8(f + j, __ldg(reinterpret_cast<const uint4*>(mk + j)));
+                        for (int j = 0; j < 64; ++j) if (!((mb >> j) & 1ull)) f[j] = 0.f;
                     }
                     if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (p.out_bits && row_ok) {
+                        unsigned long long ob = 0ull;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) ob |= (unsigned long long)(f[j] > 0.f) << j;
+                        *reinterpret_cast<unsigned long long*>(p.out_bits + (size_t)row * p.out_bits_ld + (n0 >> 3)) = ob;
                     }
                     if (p.out) {
-                        __nv_bfloat16* o = p.out + (size_t)row * p.ldo + n0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (j < nvalid) {
-                                uint4 u;
-                                u.x = pack_bf16x2(f[j], f[j + 1]); u.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                                u.z = pack_bf16x2(f[j + 4], f[j + 5]); u.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                                *reinterpret_cast<uint4*>(o + j) = u;
-                            }
+                        for (int qq = 0; qq < 8; ++qq) {
+                            uint4 u;
+                            u.x = pack_bf16x2(f[8 * qq], f[8 * qq + 1]); u.y = pack_bf16x2(f[8 * qq + 2], f[8 * qq + 3]);
+                            u.z = pack_bf16x2(f[8 * qq + 4], f[8 * qq + 5]); u.w = pack_bf16x2(f[8 * qq + 6], f[8 * qq + 7]);
+                            *reinterpret_cast<uint4*>(my_row + ((qq ^ my_sw) << 4)) = u;
                         }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_2d(&tmOut, stg, n0, row0); bulk_commit(); }
                     }
                     if (p.out_relu) {
-                        __nv_bfloat16* o = p.out_relu + (size_t)row * p.ldo + n0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (j < nvalid) {
-                                uint4 u;
-                                u.x = pack_bf16x2(fmaxf(f[j], 0.f), fmaxf(f[j + 1], 0.f));
-                                u.y = pack_bf16x2(fmaxf(f[j + 2], 0.f), fmaxf(f[j + 3], 0.f));
-                                u.z = pack_bf16x2(fmaxf(f[j + 4], 0.f), fmaxf(f[j + 5], 0.f));
-                                u.w = pack_bf16x2(fmaxf(f[j + 6], 0.f), fmaxf(f[j + 7], 0.f));
-                                *reinterpret_cast<uint4*>(o + j) = u;
-                            }
+                        if (p.out) {
+                            if (lane == 0) bulk_wait_read_all();
+                            __syncwarp();
                         }
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq) {
+                            uint4 u;
+                            u.x = pack_bf16x2(fmaxf(f[8 * qq], 0.f), fmaxf(f[8 * qq + 1], 0.f));
+                            u.y = pack_bf16x2(fmaxf(f[8 * qq + 2], 0.f), fmaxf(f[8 * qq + 3], 0.f));
+                            u.z = pack_bf16x2(fmaxf(f[8 * qq + 4], 0.f), fmaxf(f[8 * qq + 5], 0.f));
+                            u.w = pack_bf16x2(fmaxf(f[8 * qq + 6], 0.f), fmaxf(f[8 * qq + 7], 0.f));
+                            *reinterpret_cast<uint4*>(my_row + ((qq ^ my_sw) << 4)) = u;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_2d(&tmOutRelu, stg, n0, row0); bulk_commit(); }
                     }
                 }
                 if (p.out_f32) {
-                    float* o = p.out_f32 + (MODE == 1 ? (size_t)(item % p.splits) * p.split_stride : 0) +
-                               (size_t)row * p.ldo_f32 + n0;
+                    const int split = MODE == 1 ? item % p.splits : 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (j < nvalid) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    for (int h = 0; h < 2; ++h) {               // 32 fp32 columns = 128 B per row per pass
+                        if (h * 32 >= ncols) break;
+                        if (h == 1 || (MODE == 0 && (p.out || p.out_relu))) {
+                            if (lane == 0) bulk_wait_read_all();
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq)
+                            *reinterpret_cast<float4*>(my_row + ((qq ^ my_sw) << 4)) =
+                                make_float4(f[h * 32 + 4 * qq], f[h * 32 + 4 * qq + 1], f[h * 32 + 4 * qq + 2], f[h * 32 + 4 * qq + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { tma_store_3d(&tmOutF32, stg, n0 + h * 32, row0, split); bulk_commit(); }
+                    }
                 }
             }
-            // all tcgen05.ld of this accumulator stage have completed (wait::ld above): hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (!released) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            }
         }
+        if (lane == 0) bulk_wait_all();            // all results are in global memory before the CTA retires
     }
 
     __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    if (CL == 1) __syncthreads(); else cluster_sync_all();   // no CTA may exit while its peer can still signal it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -372,8 +498,29 @@ static int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t
     return 0;
 }
 
+// 3-D fp32 tensor map [planes][rows][cols] for the epilogue's fp32 results (split-R partials are the planes).
+static int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t planes, uint64_t ld,
+                            uint64_t plane_stride) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return set_error(RPG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {cols, rows, planes};
+    cuuint64_t strides[2] = {ld * 4, (planes > 1 ? plane_stride : ld * rows) * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(f32 out) failed (%d): cols=%llu rows=%llu planes=%llu ld=%llu", (int)r,
+                 (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)planes, (unsigned long long)ld);
+        return set_error((int)r, msg);
+    }
+    return 0;
+}
+
 // ---- per-launch event timing (enabled only between rpg_profile_begin / rpg_profile_end)
-struct ProfRec { cudaEvent_t e0, e1; int mode; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; int mode; double flops; int M, N, K, flags; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -395,6 +542,11 @@ int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches
         float t = 0.f;
         cudaEventElapsedTime(&t, r.e0, r.e1);
         ms[r.mode] += t; fl[r.mode] += r.flops; n[r.mode]++;
+        if (getenv("RPG_PROFILE_VERBOSE"))
+            fprintf(stderr, "[rpg gemm] %s M=%d N=%d K=%d flags=%s%s%s%s%s%s%s%s  %.1f us  %.0f TFLOP/s\n", r.mode ? "TN" : "NT", r.M, r.N,
+                    r.K, r.flags & 1 ? "bias " : "", r.flags & 2 ? "gadd0 " : "", r.flags & 4 ? "gadd1 " : "",
+                    r.flags & 8 ? "resid " : "", r.flags & 16 ? "mask " : "", r.flags & 32 ? "out " : "",
+                    r.flags & 64 ? "out_relu " : "", r.flags & 128 ? "out_f32 " : "", t * 1e3, r.flops / (t * 1e-3) / 1e12);
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
     g_prof.clear();
@@ -409,6 +561,13 @@ int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches
 
 static int g_sm_count = 0;
 static std::once_flag g_attr_once;
+static int g_cluster = 2;       // CTAs per cluster (1 or 2); see rpg_set_gemm_cluster
+
+int set_gemm_cluster(int cl) {
+    if (cl != 1 && cl != 2) return set_error(RPG_E_ARG, "gemm cluster size must be 1 or 2");
+    g_cluster = cl;
+    return 0;
+}
 
 static int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -425,6 +584,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (g->mode == 1 && block_n % 64) return set_error(RPG_E_ARG, "rpg_gemm: TN mode needs block_n % 64 == 0");
     if (!g->B || !aligned16(g->B) || g->ldb % 8) return set_error(RPG_E_ARG, "rpg_gemm: B pointer/pitch alignment");
 
+    const int cl = g_cluster;
     GemmKParams p;
     memset(&p, 0, sizeof p);
     p.mode = g->mode; p.M = g->M; p.N = g->N; p.block_n = block_n;
@@ -443,11 +603,11 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         }
         for (int s = g->n_seg; s < 3; ++s) tmA[s] = tmA[0];
         p.total_kb = ktot / BLOCK_K;
-        if ((rc = make_tmap(&tmB, g->B, ktot, g->N, g->ldb, BLOCK_K, block_n))) return rc;
+        if ((rc = make_tmap(&tmB, g->B, ktot, g->N, g->ldb, BLOCK_K, block_n / cl))) return rc;
         p.splits = 1;
         if ((g->gadd[0] && !g->gmap[0]) || (g->gadd[1] && !g->gmap[1]) || ((g->gadd[0] || g->gadd[1]) && (g->Ep <= 0 || g->Nn <= 0)))
             return set_error(RPG_E_ARG, "rpg_gemm: gathered add needs gmap, Ep, Nn");
-        if (!g->out && !g->out_relu && !g->out_f32) return set_error(RPG_E_ARG, "rpg_gemm: no output");
+        if (!g->out && !g->out_relu && !g->out_f32 && !g->out_bits) return set_error(RPG_E_ARG, "rpg_gemm: no output");
     } else if (g->mode == 1) {
         if (!g->A[0] || !aligned16(g->A[0]) || g->lda[0] % 8 || g->R <= 0)
             return set_error(RPG_E_ARG, "rpg_gemm: TN operand A");
@@ -477,20 +637,39 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     p.out_relu = reinterpret_cast<__nv_bfloat16*>(g->out_relu);
     p.ldo = g->ldo;
     p.out_f32 = g->out_f32; p.ldo_f32 = g->ldo_f32;
+    p.mask_bits = g->mask_bits; p.mask_bits_ld = g->mask_bits_ld;
+    p.out_bits = g->out_bits; p.out_bits_ld = g->out_bits_ld;
+    if ((p.mask_bits || p.out_bits) && (g->mode != 0 || p.N % 64 || block_n % 64))
+        return set_error(RPG_E_ARG, "rpg_gemm: bit patterns need NT mode and N, block_n multiples of 64");
+    if ((p.mask_bits && (p.mask_bits_ld % 8 || (reinterpret_cast<uintptr_t>(p.mask_bits) & 7))) ||
+        (p.out_bits && (p.out_bits_ld % 8 || (reinterpret_cast<uintptr_t>(p.out_bits) & 7))))
+        return set_error(RPG_E_ARG, "rpg_gemm: bit-pattern pointers and pitches must be 8-byte aligned");
     if ((p.out || p.out_relu) && p.ldo % 8) return set_error(RPG_E_ARG, "rpg_gemm: ldo must be a multiple of 8");
     if (p.out_f32 && p.ldo_f32 % 4) return set_error(RPG_E_ARG, "rpg_gemm: ldo_f32 must be a multiple of 4");
+    if ((p.out && !aligned16(p.out)) || (p.out_relu && !aligned16(p.out_relu)) || (p.out_f32 && !aligned16(p.out_f32)))
+        return set_error(RPG_E_ARG, "rpg_gemm: output pointers must be 16-byte aligned");
+    // result tiles leave through TMA stores: 32 rows x 64 bf16 (or 32 fp32) columns per box, clipped at the tensor edge
+    CUtensorMap tmOut, tmOutRelu, tmOutF32;
+    memset(&tmOut, 0, sizeof tmOut);
+    tmOutRelu = tmOutF32 = tmOut;
+    if (p.out && (rc = make_tmap(&tmOut, p.out, p.N, p.M, p.ldo, 64, 32))) return rc;
+    if (p.out_relu && (rc = make_tmap(&tmOutRelu, p.out_relu, p.N, p.M, p.ldo, 64, 32))) return rc;
+    if (p.out_f32 && (rc = make_tmap_f32_3d(&tmOutF32, p.out_f32, p.N, p.M, p.splits, p.ldo_f32, p.split_stride))) return rc;
 
     std::call_once(g_attr_once, [] {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
-    const int items = num_m_blocks * num_n_blocks * p.splits;
-    const int grid = items < g_sm_count ? items : g_sm_count;
+    const int items = ((num_m_blocks + cl - 1) / cl) * num_n_blocks * p.splits;      // one item per cluster
+    const int max_workers = g_sm_count / cl;
+    const int grid = (items < max_workers ? items : max_workers) * cl;
     ProfRec rec;
     bool prof = false;
     {
@@ -501,12 +680,32 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
         rec.mode = g->mode;
         rec.flops = 2.0 * p.M * p.N * (g->mode == 0 ? (double)p.total_kb * BLOCK_K : (double)g->R);
+        rec.M = p.M; rec.N = p.N; rec.K = g->mode == 0 ? p.total_kb * BLOCK_K : g->R;
+        rec.flags = (p.bias ? 1 : 0) | (p.gadd[0] ? 2 : 0) | (p.gadd[1] ? 4 : 0) | (p.resid ? 8 : 0) | (p.mask ? 16 : 0) |
+                    (p.out ? 32 : 0) | (p.out_relu ? 64 : 0) | (p.out_f32 ? 128 : 0);
         cudaEventRecord(rec.e0, stream);
     }
-    if (g->mode == 0)
-        gemm_tc_kernel<0><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
-    else
-        gemm_tc_kernel<1><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, p);
+    if (cl == 1) {
+        if (g->mode == 0)
+            gemm_tc_kernel<0, 1><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
+        else
+            gemm_tc_kernel<1, 1><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = g->mode == 0 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 2>, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p)
+                                     : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 2>, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
+        (void)e;
+    }
     if (prof) {
         cudaEventRecord(rec.e1, stream);
         std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -15,6 +15,7 @@ int set_error(int code, const char* msg);
 int check_launch(const char* what);
 
 int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream);
+int set_gemm_cluster(int cl);
 // Optional per-launch CUDA-event timing of the GEMM kernel (bench.py roofline leg); off by default.
 int profile_begin();
 int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops);

@@ -107,6 +107,8 @@ int rpg_device_sm_count(int device, int* sm_count) {
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream) { return gemm_launch(g, as_stream(stream)); }
 
+int rpg_set_gemm_cluster(int cl) { return set_gemm_cluster(cl); }
+
 int64_t rpg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int rpg_profile_begin(void) { return profile_begin(); }
@@ -158,12 +160,13 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
     g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = 3 * D;
     g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
-    g.out = t->h1; g.ldo = D;
+    g.out = t->h1; g.ldo = D; g.out_bits = t->h1_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
 
     // (3) edge MLP layer 2 (my_gnn_layer.py:234): e' = h1 W2e^T + b  (+ relu'd copy for the caller, posenet.py:1065)
     g = nt((int)Et, D, t->h1, D, D, w->W2e, D);
     g.bias = w->b2e; g.out = t->e_new; g.out_relu = t->e_new_relu; g.ldo = D;
+    g.out_bits = t->e_new_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
 
     // (4) message MLP layer 1 (my_gnn_layer.py:280,305): h2 = relu(e' W1m_e^T + P_m[src] + b)   (x_j = source)
@@ -171,7 +174,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g.bias = w->b1m;
     g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
     g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
-    g.out = t->h2; g.ldo = D;
+    g.out = t->h2; g.ldo = D; g.out_bits = t->h2_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
 
     // (5) message MLP layer 2 (my_gnn_layer.py:282): m = h2 W2m^T + b
@@ -187,9 +190,11 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // (7) rank-1 softmax attention (att.py:25-30)
     RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, stream));
 
-    // (8) z = y WW^T + bW + m (att.py:32-33)
-    g = nt((int)Et, D, t->y, cp, cp, w->WW, cp);
-    g.bias = w->bW; g.resid = t->m; g.resid_ld = D; g.out = t->z; g.ldo = D;
+    // (8) z = y WW^T + bW + m (att.py:32-33) as [y | m] [WW | I]^T: the residual is a second K segment (exact in the
+    //     fp32 accumulator) so it streams through TMA with the operands instead of being fetched by the epilogue
+    g = nt((int)Et, D, t->y, cp, cp, w->WWI, cp + D);
+    g.n_seg = 2; g.A[1] = t->m; g.K[1] = D; g.lda[1] = D;
+    g.bias = w->bW; g.out = t->z; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
 
     // (9) mean over incoming edges (PyG aggregate [3p], my_gnn_layer.py:301)
@@ -198,10 +203,11 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // (10) update MLP (my_gnn_layer.py:284-286,309-311): out = relu([x | a] W1u^T + b) W2u^T + b
     g = nt((int)Nt, D, t->x, D, D, w->W1u, 2 * D);
     g.n_seg = 2; g.A[1] = t->a; g.K[1] = D; g.lda[1] = D;
-    g.bias = w->b1u; g.relu = 1; g.out = t->h3; g.ldo = D;
+    g.bias = w->b1u; g.relu = 1; g.out = t->h3; g.ldo = D; g.out_bits = t->h3_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
     g = nt((int)Nt, D, t->h3, D, D, w->W2u, D);
     g.bias = w->b2u; g.out = t->out; g.out_relu = t->out_relu; g.ldo = D;
+    g.out_bits = t->out_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
     return 0;
 }
@@ -228,7 +234,8 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     if (have_out) {
         // dh3 = (d_out W2u) * [h3 > 0]
         g = nt((int)Nt, D, b->d_out, D, D, w->W2uT, D);
-        g.mask = t->h3; g.mask_ld = D; g.out = b->dh3; g.ldo = D;
+        if (t->h3_bits) { g.mask_bits = t->h3_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->h3; g.mask_ld = D; }
+        g.out = b->dh3; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
         // [dx_u | da] = dh3 W1u ; da is scaled by 1/deg (mean backward) -> dan
         g = nt((int)Nt, D, b->dh3, D, D, w->W1uT, D);
@@ -250,7 +257,8 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         RPG_TRY(gemm_launch(&g, s));
         // dh2 = (dm W2m) * [h2 > 0]
         g = nt((int)Et, D, b->dm, D, D, w->W2mT, D);
-        g.mask = t->h2; g.mask_ld = D; g.out = b->dh2; g.ldo = D;
+        if (t->h2_bits) { g.mask_bits = t->h2_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->h2; g.mask_ld = D; }
+        g.out = b->dh2; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
         // de'_tot = dh2 W1m_e + d_e_new
         g = nt((int)Et, D, b->dh2, D, D, w->W1m_eT, D);
@@ -263,11 +271,14 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // ---- edge MLP backward
     // dh1 = (de'_tot W2e) * [h1 > 0]
     g = nt((int)Et, D, de_tot, D, D, w->W2eT, D);
-    g.mask = t->h1; g.mask_ld = D; g.out = b->dh1; g.ldo = D;
+    if (t->h1_bits) { g.mask_bits = t->h1_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->h1; g.mask_ld = D; }
+    g.out = b->dh1; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
     // de = dh1 W1e_e  (optionally * [e > 0] for a ReLU'd input)
     g = nt((int)Et, D, b->dh1, D, D, w->W1e_eT, D);
-    if (b->mask_de) { g.mask = t->e; g.mask_ld = D; }
+    if (b->mask_de) {
+        if (t->e_bits) { g.mask_bits = t->e_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->e; g.mask_ld = D; }
+    }
     g.out = b->de; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
 
@@ -281,7 +292,9 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     } else {
         g = nt((int)Nt, D, b->dP, 2 * D, 3 * D, w->WnT, 3 * D);
     }
-    if (b->mask_dx) { g.mask = t->x; g.mask_ld = D; }
+    if (b->mask_dx) {
+        if (t->x_bits) { g.mask_bits = t->x_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->x; g.mask_ld = D; }
+    }
     g.out = b->dx; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
 

@@ -77,6 +77,45 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+// Multicast variant: the tile lands at the same CTA-relative offset of every CTA in `cta_mask`, and each of those
+// CTAs' mbarrier at the same offset receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(const void* desc, uint64_t* bar, void* dst, int c_inner, int c_outer,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer),
+          "h"(cta_mask)
+        : "memory");
+}
+
+// Tiled stores shared -> global (bulk async-group completion).  Out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* desc, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Wait until the bulk stores committed by this thread have finished READING their shared-memory source.
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------ clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
@@ -101,6 +140,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 // Arrive on `bar` once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// Same, arriving on the barrier at this offset in every CTA of `cta_mask` (a stage shared through multicast TMA
+// may only be refilled once every consumer CTA has drained it).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t), columns [col, col+32).

@@ -62,7 +62,7 @@ class PackedLayerWeights:
         self.c, self.cp, self.c3p = c, pad64(c), pad64(3 * c)
         shapes = {
             "Wn": (3 * D, D), "W1e_e": (D, D), "W2e": (D, D), "W1m_e": (D, D), "W2m": (D, D),
-            "Wgtp": (3 * c, D), "WW": (D, self.cp), "W1u": (D, 2 * D), "W2u": (D, D),
+            "Wgtp": (3 * c, D), "WW": (D, self.cp), "WWI": (D, self.cp + D), "W1u": (D, 2 * D), "W2u": (D, D),
             "WnT": (D, 3 * D), "W1e_eT": (D, D), "W2eT": (D, D), "W1m_eT": (D, D), "W2mT": (D, D), "W2uT": (D, D),
             "WgtpT": (D, self.c3p), "WWT": (c, D), "W1uT": (2 * D, D),
         }
@@ -73,6 +73,7 @@ class PackedLayerWeights:
         for name, (r, k) in shapes.items():
             self.t[name] = self.flat[off:off + r * k].view(r, k)
             off += r * k
+        self.t["WWI"][:, self.cp:].copy_(torch.eye(D, dtype=BF16, device=device))   # identity panel (residual)
         self.bgtp = torch.zeros(3 * c, dtype=torch.float32, device=device)
         self.versions = None
         self.struct = _lib.LayerWeights()
@@ -102,6 +103,7 @@ class PackedLayerWeights:
             pk(p[f"att.{nm}.weight"].data, t["WgtpT"][:, i * c:(i + 1) * c], transpose=True)
             self.bgtp[i * c:(i + 1) * c].copy_(p[f"att.{nm}.bias"].data)
         pk(p["att.W.weight"].data, t["WW"][:, :c])
+        pk(p["att.W.weight"].data, t["WWI"][:, :c])
         pk(W1u, t["W1u"])
         pk(W2u, t["W2u"])
         # dgrad operands (transposes)
@@ -131,24 +133,33 @@ class PackedLayerWeights:
         return s
 
 
-def layer_forward_raw(weights, graph, x, e, want_relu_copies=False):
-    """Runs rpg_layer_fwd on bf16 inputs; returns the dict of activation tensors (kept for backward)."""
+def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None, e_bits=None, arena=None):
+    """Runs rpg_layer_fwd on bf16 inputs; returns the dict of activation tensors (kept for backward).
+    x_bits / e_bits: optional ReLU bit patterns of the inputs (when they are ReLU outputs of a previous op)."""
     D = weights.D
     dev = x.device
     Nt, Et = graph.n_node_rows, graph.n_edge_rows
     c = D // 8
     cp = pad64(c)
 
-    def new(rows, cols, dtype=BF16):
-        return torch.empty(rows, cols, dtype=dtype, device=dev)
+    arena = arena if arena is not None else ops.Arena(dev, ops.layer_fwd_bytes(D, Nt, Et))
+    new = arena.take
 
     a = {"x": x, "e": e, "P": new(Nt, 3 * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
          "m": new(Et, D), "gtp": new(Et, 3 * c, torch.float32),
-         "y": torch.zeros(Et, cp, dtype=BF16, device=dev) if cp != c else new(Et, cp),
+         "y": new(Et, cp, zero=(cp != c)),
          "z": new(Et, D), "a": new(Nt, D), "h3": new(Nt, D), "out": new(Nt, D)}
+    u8 = torch.uint8
+    a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8), "h3_bits": new(Nt, D // 8, u8)})
     if want_relu_copies:
         a["e_new_relu"] = new(Et, D)
         a["out_relu"] = new(Nt, D)
+        a["e_new_bits"] = new(Et, D // 8, u8)
+        a["out_bits"] = new(Nt, D // 8, u8)
+    if x_bits is not None:
+        a["x_bits"] = x_bits
+    if e_bits is not None:
+        a["e_bits"] = e_bits
     s = _lib.LayerActs()
     for k, v in a.items():
         setattr(s, k, v.data_ptr())
@@ -158,7 +169,7 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False):
     return a
 
 
-def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=False, mask_de=False):
+def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=False, mask_de=False, arena=None):
     """Runs rpg_layer_bwd.  `grads`: dict name (PARAM_ORDER) -> fp32 tensor, accumulated in place.
     Returns (dx, de) in bf16."""
     D = weights.D
@@ -168,19 +179,20 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
     cp, c3p = pad64(c), pad64(3 * c)
     lib = _lib.load()
 
-    def new(rows, cols, dtype=BF16):
-        return torch.empty(rows, cols, dtype=dtype, device=dev)
+    arena = arena if arena is not None else ops.Arena(dev, ops.layer_bwd_bytes(D, Nt, Et))
+    new = arena.take
+    f32 = torch.float32
 
     b = _lib.LayerGrads()
     have_out = d_out is not None
     keep = {"dx": new(Nt, D), "de": new(Et, D), "dh1": new(Et, D), "dP": new(Nt, 3 * D),
-            "split_ws": ops.wgrad_ws(D, dev),
-            "colsum_ws": torch.empty(lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), dtype=torch.float32, device=dev)}
+            "split_ws": new(1, lib.rpg_layer_bwd_ws_floats(D, 0, 0), f32),
+            "colsum_ws": new(1, lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), f32)}
     if have_out:
-        keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D), "dan": new(Nt, D), "dyn": new(Nt, c, torch.float32),
-                     "dgtp": torch.zeros(Et, c3p, dtype=BF16, device=dev) if c3p != 3 * c else new(Et, c3p),
+        keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D), "dan": new(Nt, D), "dyn": new(Nt, c, f32),
+                     "dgtp": new(Et, c3p, zero=(c3p != 3 * c)),
                      "dm": new(Et, D), "dh2": new(Et, D), "de_tot": new(Et, D),
-                     "ysum": new(Nt, cp), "gtp_bias_tmp": torch.empty(c3p, dtype=torch.float32, device=dev)})
+                     "ysum": new(Nt, cp), "gtp_bias_tmp": new(1, c3p, f32)})
     for k, v in keep.items():
         setattr(b, k, v.data_ptr())
     b.d_out = ops.ptr(d_out)

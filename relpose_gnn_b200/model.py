@@ -20,6 +20,11 @@ from .ops import BF16
 _HEADS = ("fc_xyz", "fc_wpqr", "fc_xyz_R", "fc_wpqr_R")
 
 
+def _lib_ws_floats(D):
+    from . import _lib
+    return _lib.load().rpg_layer_bwd_ws_floats(D, 0, 0)
+
+
 class _StackFn(torch.autograd.Function):
     """proj_edge init -> R x (gnn1, ReLU, ReLU) -> feature dropout -> 4 pose heads, with a hand-written backward.
     ReLUs are folded into GEMM epilogues (forward: second store; backward: mask on the input that was a ReLU)."""
@@ -32,17 +37,20 @@ class _StackFn(torch.autograd.Function):
         xb = ops.to_bf16(x)
         lw = model.gnn1._packed(dev).refresh(model.gnn1)
         sw = model._packed_stack(dev)
+        # one allocation for every activation of the forward (sizes change with the edge-dropout mask)
+        arena = ops.Arena(dev, R * ops.layer_fwd_bytes(D, Nt, Et) + Nt * 2 * D * 2 + Et * (D * 2 + D // 8) + 4096)
         # edge-feature initialiser (posenet.py:1014-1017,1053-1055), factorised per node
-        pmm = torch.empty(Nt, 2 * D, dtype=BF16, device=dev)
+        pmm = arena.take(Nt, 2 * D)
         ops.gemm_nt(xb, sw["Wmm"], out=pmm)
-        e = torch.empty(Et, D, dtype=BF16, device=dev)
-        ops.edge_init_fwd(pmm, model.proj_edge.bias.data, graph, D, e)
+        e = arena.take(Et, D)
+        e_bits = arena.take(Et, D // 8, torch.uint8)
+        ops.edge_init_fwd(pmm, model.proj_edge.bias.data, graph, D, e, e_bits)
         acts = []
-        xin = xb
+        xin, x_bits = xb, None
         for _ in range(R):                                       # same gnn1 weights each round (posenet.py:1060-1069)
-            a = layer_forward_raw(lw, graph, xin, e, want_relu_copies=True)
+            a = layer_forward_raw(lw, graph, xin, e, want_relu_copies=True, x_bits=x_bits, e_bits=e_bits, arena=arena)
             acts.append(a)
-            xin, e = a["out_relu"], a["e_new_relu"]
+            xin, e, x_bits, e_bits = a["out_relu"], a["e_new_relu"], a["out_bits"], a["e_new_bits"]
         p_drop, keep_x, keep_e, seed = drop
         pose_n = ops.head_fwd(xin, sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop)
         pose_e = ops.head_fwd(e, sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop)
@@ -73,7 +81,9 @@ class _StackFn(torch.autograd.Function):
                 grads[n] = flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
         lgrads = {n: grads["gnn1." + n] for n in PARAM_ORDER}
-        ws = ops.wgrad_ws(D, dev)
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        arena = ops.Arena(dev, R * ops.layer_bwd_bytes(D, Nt, Et) + 4 * _lib_ws_floats(D) + Nt * 3 * D * 2 + 4096)
+        ws = arena.take(1, _lib_ws_floats(D), torch.float32)
 
         # heads (posenet.py:1077-1086): gradient w.r.t. the pre-ReLU layer outputs (mask_relu)
         d_e = d_x = None
@@ -89,15 +99,14 @@ class _StackFn(torch.autograd.Function):
             return (None,) * (4 + len(names))
 
         for r in range(R - 1, -1, -1):
-            d_x, d_e = layer_backward_raw(lw, graph, acts[r], d_x, d_e, lgrads, mask_dx=(r > 0), mask_de=True)
+            d_x, d_e = layer_backward_raw(lw, graph, acts[r], d_x, d_e, lgrads, mask_dx=(r > 0), mask_de=True, arena=arena)
             acts[r] = None                                      # free this round's activations
 
         # edge-feature initialiser backward: d_e is already masked by (e0 > 0)
-        Nt = graph.n_node_rows
-        dpmm = torch.empty(Nt, 2 * D, dtype=BF16, device=dev)
+        dpmm = arena.take(Nt, 2 * D)
         ops.segment_sum(d_e, graph, "min", dpmm[:, :D])
         ops.segment_sum(d_e, graph, "max", dpmm[:, D:])
-        dx = torch.empty(Nt, D, dtype=BF16, device=dev)
+        dx = arena.take(Nt, D)
         ops.gemm_nt(dpmm, sw["WmmT"], resid=d_x, out=dx)
         gw = grads["proj_edge.weight"]
         ops.wgrad(dpmm[:, :D], xb, gw[:, :D], ws)

@@ -10,6 +10,39 @@ from ._lib import Gemm, check, ptr
 BF16 = torch.bfloat16
 
 
+class Arena:
+    """One caching-allocator block per forward (or backward) carved into 256-byte-aligned views.  A training step
+    otherwise makes ~60 allocations whose sizes change with the edge-dropout mask; with the host running ahead of
+    the device that fragments the caching allocator and ends in synchronous cudaMalloc/cudaFree calls."""
+
+    def __init__(self, device, nbytes):
+        self.device = device
+        self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        self.off = 0
+
+    def take(self, rows, cols, dtype=BF16, zero=False):
+        n = rows * cols * torch.empty((), dtype=dtype).element_size()
+        if self.off + n > self.buf.numel():                       # estimate too small: fall back to the allocator
+            t = torch.empty(rows, cols, dtype=dtype, device=self.device)
+        else:
+            t = self.buf[self.off:self.off + n].view(dtype).view(rows, cols)
+            self.off = (self.off + n + 255) & ~255
+        return t.zero_() if zero else t
+
+
+def layer_fwd_bytes(D, Nt, Et):
+    c = D // 8
+    return Et * (6 * D * 2 + 3 * c * 4 + pad64(c) * 2 + 3 * (D // 8)) + Nt * (3 * D * 2 + 4 * D * 2 + 2 * (D // 8)) + 64 * 256
+
+
+def layer_bwd_bytes(D, Nt, Et):
+    c = D // 8
+    lib = _lib.load()
+    return (Et * (5 * D * 2 + pad64(3 * c) * 2) + Nt * (3 * D * 2 + 4 * D * 2 + c * 4 + pad64(c) * 2) +
+            4 * lib.rpg_layer_bwd_ws_floats(D, 0, 0) +
+            4 * lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, pad64(3 * c))) + 64 * 256)
+
+
 def _stream(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -25,7 +58,7 @@ def _require_cuda(*ts):
 
 
 def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, row_scale=None, mask=None,
-            relu=False, out=None, out_relu=None, out_f32=None, graph=None, block_n=0):
+            relu=False, out=None, out_relu=None, out_f32=None, graph=None, block_n=0, mask_bits=None, out_bits=None):
     """C = epilogue(sum_s A_s @ B^T).  A: bf16 [M, K] (or `segs`: list of up to 3 such tensors concatenated along
     K); B: bf16 [N, sum K].  Row pitches are taken from stride(0), so column-sliced views are fine.
     gadd: up to two (tensor [rows, >=N] bf16, 'src'|'dst') pairs added through the graph template."""
@@ -67,6 +100,10 @@ def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, 
     g.out, g.out_relu, g.ldo = ptr(out), ptr(out_relu), ldo or 0
     if out_f32 is not None:
         g.out_f32, g.ldo_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if mask_bits is not None:
+        g.mask_bits, g.mask_bits_ld = mask_bits.data_ptr(), mask_bits.stride(0)
+    if out_bits is not None:
+        g.out_bits, g.out_bits_ld = out_bits.data_ptr(), out_bits.stride(0)
     check(lib.rpg_gemm(C.byref(g), _stream(B)), "rpg_gemm")
 
 
@@ -152,9 +189,9 @@ def segment_sum(v, graph, which, out, mask=None, scale=None, D=None):
                                       graph.byref(), D, out.data_ptr(), out.stride(0), _stream(v)), "rpg_segment_sum")
 
 
-def edge_init_fwd(pmm, bias, graph, D, e0):
+def edge_init_fwd(pmm, bias, graph, D, e0, e0_bits=None):
     check(_lib.load().rpg_edge_init_fwd(pmm.data_ptr(), pmm.stride(0), bias.data_ptr(), graph.byref(), D,
-                                        e0.data_ptr(), e0.stride(0), _stream(pmm)), "rpg_edge_init_fwd")
+                                        e0.data_ptr(), e0.stride(0), ptr(e0_bits), _stream(pmm)), "rpg_edge_init_fwd")
 
 
 def dropout_mask(seed, p_drop, rows, D, device):

@@ -66,6 +66,23 @@ def nt_cases():
     out2 = torch.empty(M, N, dtype=BF, device=dev)
     ops.gemm_nt(None, B, segs=[A0, A1, A2], bias=bias, relu=True, out=out2)
     ok &= report("NT relu", out2, (torch.cat([A0, A1, A2], 1).float() @ B.float().t() + bias).clamp(min=0), 1e-2)
+    # bit patterns: out_bits == packbits(out > 0); mask_bits has the same effect as the bf16 mask
+    M2, N2 = 72 * 5, 256
+    bits = torch.zeros(M2, N2 // 8, dtype=torch.uint8, device=dev)
+    out3 = torch.empty(M2, N2, dtype=BF, device=dev)
+    ops.gemm_nt(None, B, segs=[A0, A1, A2], bias=bias, relu=True, out=out3, out_bits=bits)
+    want = (out3.float() > 0).view(M2, N2 // 8, 8).to(torch.uint8)
+    want = (want << torch.arange(8, device=dev, dtype=torch.uint8)).sum(-1).to(torch.uint8)
+    okb = bool(torch.equal(bits, want))
+    print(("PASS" if okb else "FAIL") + " NT out_bits", flush=True)
+    ok &= okb
+    o_m = torch.empty(M2, N2, dtype=BF, device=dev)
+    o_b = torch.empty(M2, N2, dtype=BF, device=dev)
+    ops.gemm_nt(None, B, segs=[A0, A1, A2], resid=resid, mask=out3, out=o_m)
+    ops.gemm_nt(None, B, segs=[A0, A1, A2], resid=resid, mask_bits=bits, out=o_b)
+    okb = bool(torch.equal(o_m, o_b))
+    print(("PASS" if okb else "FAIL") + " NT mask_bits == bf16 mask", flush=True)
+    ok &= okb
     # timing of the big shape
     M, N, K = 294912, 512, 512
     A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
