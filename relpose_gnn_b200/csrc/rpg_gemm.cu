@@ -86,7 +86,9 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& u) {
 // CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on adjacent 128-row blocks of the same column
 // block and each fetches HALF of every weight (B) tile, multicast into both shared memories: the L2 -> SM traffic for
 // B, which dominates at the small N, K of this path (every tile re-reads the whole weight panel), is halved.
-template <int MODE, int CL>
+// OPS = the epilogue reads tensor operands (gathered node rows / residual / bf16 mask); compiled separately so that the
+// plain epilogue keeps its smaller register footprint and schedule.
+template <int MODE, int CL, bool OPS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -232,13 +234,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // per-warp staging tile [32 rows][128 B] in the TMA 128-byte-swizzle layout (16-byte chunk c of row r lives at
         // chunk c ^ (r & 7): conflict-free for the row view and for the coalesced view):
         //   results  : registers -> staging -> ONE TMA store per 32 x 64 tile (asynchronous, clipped at the tensor edge)
-        //   operands : coalesced 4-rows-x-128-B loads -> staging -> each thread reads back its own row
+        //   operands : ReLU patterns arrive as 8 bytes of bits per row and chunk; tensor operands (gathered node rows,
+        //              residuals) are read row-per-thread, issued ahead of the TMEM read
         const int ew = warp - 2;
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                  // the two warps of a quadrant alternate 64-column chunks
         const int n_chunks = (p.block_n + 63) / 64;
         uint8_t* stg = smem + SMEM_RING_BYTES + SMEM_BAR_BYTES + ew * EPI_STAGE_BYTES;
-        const int sub = lane >> 3, q8 = lane & 7;  // coalesced view: instruction i covers rows 4i + sub, chunk q8
         uint8_t* my_row = stg + lane * 128;
         const int my_sw = lane & 7;
         int it = 0;
@@ -257,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             int gnode0 = -1, gnode1 = -1;
             float rscale = 1.f;
-            if (MODE == 0 && row_ok) {
+            if (OPS && MODE == 0 && row_ok) {
                 if (p.gadd[0] || p.gadd[1]) {
                     const int gidx = row / p.Ep, k = row - gidx * p.Ep;
                     if (p.gadd[0]) gnode0 = gidx * p.Nn + __ldg(p.gmap[0] + k);
@@ -265,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 if (p.row_scale) rscale = __ldg(p.row_scale + (row % p.row_scale_mod));
             }
+            if (!OPS && MODE == 0 && row_ok && p.row_scale) rscale = __ldg(p.row_scale + (row % p.row_scale_mod));
             // ---- everything that does not need the accumulator is requested BEFORE waiting for it: the ReLU bit
             // patterns of both chunks (8 bytes each) and the first two operand tiles of the first chunk.
             unsigned long long mbits0 = ~0ull, mbits1 = ~0ull;
@@ -285,37 +288,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (ncols <= 0 || row0 >= p.M) break;
                 const int nq = ncols >> 3;                                       // valid 16-byte bf16 chunks per row
 
-                // ---- operand prefetch (coalesced view), issued before the TMEM read so the latencies overlap
-                uint4 bufA[8], bufB[8];
-                auto load_rows = [&](uint4 (&buf)[8], const __nv_bfloat16* base, int ld, int gnode, bool gathered) {
+                // ---- epilogue operands: each thread fetches its own row (64 bf16 = 8 x 16 B) directly, issued before the
+                // TMEM read so the latencies overlap.  (Staging them through shared memory for coalescing was measured
+                // slower: the extra warp-synchronous round trip outweighs the saved L1 tag cycles.)
+                uint4 opr0[8], opr1[8];
+                const __nv_bfloat16* src0 = nullptr;
+                const __nv_bfloat16* src1 = nullptr;
+                int kind0 = 0, kind1 = 0;                                        // 1 = add, 2 = bf16 ReLU mask
+                if (OPS && MODE == 0 && row_ok) {
+                    const __nv_bfloat16* cand[4] = {
+                        gnode0 >= 0 ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
+                        gnode1 >= 0 ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
+                        p.resid ? p.resid + (size_t)row * p.resid_ld : nullptr,
+                        p.mask ? p.mask + (size_t)row * p.mask_ld : nullptr};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + sub;
-                        long long rr = row0 + r;
-                        if (gathered) rr = __shfl_sync(0xffffffffu, gnode, r);   // node row of the owner lane r
-                        const bool ok = (row0 + r < p.M) && rr >= 0 && q8 < nq;
-                        buf[i] = ok ? __ldg(reinterpret_cast<const uint4*>(base + rr * ld + n0 + q8 * 8))
-                                    : make_uint4(0, 0, 0, 0);
+                    for (int o = 0; o < 4; ++o) {
+                        if (!cand[o]) continue;
+                        if (!src0) { src0 = cand[o] + n0; kind0 = o == 3 ? 2 : 1; }
+                        else if (!src1) { src1 = cand[o] + n0; kind1 = o == 3 ? 2 : 1; }
                     }
-                };
-                int nextop = 0;       // 0 gadd0, 1 gadd1, 2 resid, 3 mask, 4 none
-                auto issue = [&](uint4 (&buf)[8]) -> int {      // loads the next present operand into buf, returns its id
-                    while (nextop < 4) {
-                        const bool present = nextop == 0 ? p.gadd[0] != nullptr : nextop == 1 ? p.gadd[1] != nullptr
-                                           : nextop == 2 ? p.resid != nullptr : p.mask != nullptr;
-                        if (present) break;
-                        ++nextop;
+                    if (src0) {
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq)
+                            opr0[qq] = qq < nq ? __ldg(reinterpret_cast<const uint4*>(src0) + qq) : make_uint4(0, 0, 0, 0);
                     }
-                    const int op = nextop;
-                    if (op == 0) load_rows(buf, p.gadd[0], p.gadd_ld[0], gnode0, true);
-                    else if (op == 1) load_rows(buf, p.gadd[1], p.gadd_ld[1], gnode1, true);
-                    else if (op == 2) load_rows(buf, p.resid, p.resid_ld, 0, false);
-                    else if (op == 3) load_rows(buf, p.mask, p.mask_ld, 0, false);
-                    if (op < 4) ++nextop;
-                    return op;
-                };
-                int opA = 4, opB = 4;
-                if (MODE == 0) { opA = issue(bufA); opB = issue(bufB); }
+                    if (src1) {
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq)
+                            opr1[qq] = qq < nq ? __ldg(reinterpret_cast<const uint4*>(src1) + qq) : make_uint4(0, 0, 0, 0);
+                    }
+                }
 
                 // ---- accumulator -> registers
                 float f[64];
@@ -347,29 +349,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             }
                         }
                     }
+                    // order: gathered adds, residual, row scale, ReLU mask (at most two tensor operands per GEMM here;
+                    // a third/fourth one is fetched late)
+                    int used = 0;
                     bool scaled = p.row_scale == nullptr;
-                    auto stage_and_consume = [&](const uint4 (&buf)[8], int op) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 4 * i + sub;
-                            *reinterpret_cast<uint4*>(stg + r * 128 + ((q8 ^ (r & 7)) << 4)) = buf[i];
-                        }
-                        __syncwarp();
-                        if (op == 3 && !scaled) {                 // epilogue order: ... resid, row_scale, mask
+                    auto apply = [&](const uint4 (&o)[8], int kind) {
+                        if (kind == 2 && !scaled) {
 #pragma unroll
                             for (int j = 0; j < 64; ++j) f[j] *= rscale;
                             scaled = true;
                         }
 #pragma unroll
                         for (int qq = 0; qq < 8; ++qq) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((qq ^ my_sw) << 4));
-                            if (op == 3) mask_bf16x8(f + 8 * qq, u); else add_bf16x8(f + 8 * qq, u);
+                            if (kind == 2) mask_bf16x8(f + 8 * qq, o[qq]); else add_bf16x8(f + 8 * qq, o[qq]);
                         }
-                        __syncwarp();
                     };
-                    while (opA < 4 || opB < 4) {
-                        if (opA < 4) { stage_and_consume(bufA, opA); opA = issue(bufA); }
-                        if (opB < 4) { stage_and_consume(bufB, opB); opB = issue(bufB); }
+                    if (OPS && src0) { apply(opr0, kind0); ++used; }
+                    if (OPS && src1) { apply(opr1, kind1); ++used; }
+                    if (OPS && row_ok) {                             // rare: more than two tensor operands
+                        const __nv_bfloat16* cand[4] = {
+                            gnode0 >= 0 ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
+                            gnode1 >= 0 ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
+                            p.resid ? p.resid + (size_t)row * p.resid_ld : nullptr,
+                            p.mask ? p.mask + (size_t)row * p.mask_ld : nullptr};
+                        int seen = 0;
+                        for (int o = 0; o < 4; ++o) {
+                            if (!cand[o]) continue;
+                            if (seen++ < 2) continue;
+                            uint4 late[8];
+#pragma unroll
+                            for (int qq = 0; qq < 8; ++qq)
+                                late[qq] = qq < nq ? __ldg(reinterpret_cast<const uint4*>(cand[o] + n0) + qq) : make_uint4(0, 0, 0, 0);
+                            apply(late, o == 3 ? 2 : 1);
+                        }
                     }
                     if (!scaled) {
 #pragma unroll
@@ -660,10 +672,12 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
@@ -685,12 +699,11 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
                     (p.out ? 32 : 0) | (p.out_relu ? 64 : 0) | (p.out_f32 ? 128 : 0);
         cudaEventRecord(rec.e0, stream);
     }
-    if (cl == 1) {
-        if (g->mode == 0)
-            gemm_tc_kernel<0, 1><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
-        else
-            gemm_tc_kernel<1, 1><<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
-    } else {
+    const bool ops = g->mode == 0 && (p.gadd[0] || p.gadd[1] || p.resid || p.mask);
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKParams);
+    if (cl == 1) kern = g->mode == 1 ? gemm_tc_kernel<1, 1, false> : (ops ? gemm_tc_kernel<0, 1, true> : gemm_tc_kernel<0, 1, false>);
+    else kern = g->mode == 1 ? gemm_tc_kernel<1, 2, false> : (ops ? gemm_tc_kernel<0, 2, true> : gemm_tc_kernel<0, 2, false>);
+    {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(grid);
@@ -702,8 +715,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = g->mode == 0 ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 2>, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p)
-                                     : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 2>, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
         (void)e;
     }
     if (prof) {
