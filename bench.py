@@ -27,6 +27,7 @@ WORKLOADS = {
     "train_4096x9": (4096, 9, 512, "train"),
     "train_2048x17": (2048, 17, 512, "train"),
     "infer_4096x9": (4096, 9, 512, "infer"),
+    "infer_fp32_4096x9": (4096, 9, 512, "infer_fp32"),     # BASELINE configs[1]: fp32 mode (split-bf16 arithmetic)
 }
 METRIC = "GNN graphs/sec fwd+bwd"
 R_ROUNDS = 2
@@ -153,11 +154,14 @@ def run_ours(args):
     lib = _lib.load()
     G, N, D, mode = WORKLOADS[args.workload]
     train = mode == "train"
+    fp32_mode = mode == "infer_fp32"
     H = N * (N - 1) // 2
     peaks = load_peaks()
 
     torch.manual_seed(0)
     model = rpg.RelPoseGNN(D, D, D, droprate=0.5, gnn_recursion=R_ROUNDS).to(dev)
+    if fp32_mode:
+        model.precision = "fp32"
     crit = rpg.PoseNetCriterion(sax=0.0, saq=-2.0).to(dev)
     params = list(model.parameters()) + list(crit.parameters())
     if world > 1:      # identical replicas
@@ -169,7 +173,8 @@ def run_ours(args):
 
     # synthetic inputs of the named shape: ResNet34 embeddings ~ N(0,1) in bf16, poses ~ N(0, 0.1)
     gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(G * N, D, generator=gen).bfloat16().pin_memory()
+    x_host = torch.randn(G * N, D, generator=gen)
+    x_host = (x_host if fp32_mode else x_host.bfloat16()).pin_memory()
     poses_host = (0.1 * torch.randn(G * N, 6, generator=gen)).pin_memory()
     x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
     mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
@@ -247,7 +252,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 (split-bf16 x3 on the bf16 tensor pipe)" if fp32_mode else "bf16",
+            "data": "synthetic",
             "trials_ms_per_step": trials, "trials_e2e_ms_per_step": trials_e2e,
             "config": {"workload": args.workload, "graphs_per_gpu": G, "nodes_per_graph": N, "D": D, "mode": mode,
                        "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if train else 1.0,
@@ -255,7 +261,7 @@ def run_ours(args):
                        "step": "forward + compute_RP/L1 criterion + backward" + (" + 1 NCCL all-reduce" if world > 1 else "") if train else "forward",
                        "parallelism": f"dp{world} over graphs", "l2": "activations per step (>1 GB) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": x_host.numel() * 2 + poses_host.numel() * 4,
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + poses_host.numel() * 4,
                     "d2h_bytes_per_step": 4 if train else G * 2 * int(np.mean([m.sum() for m in masks[:4]])) * 6 * 4},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -93,10 +93,10 @@ typedef struct {
 typedef struct {
   int mode;                   /* 0 = NT (A [M,K] row-major, B [N,K] row-major), 1 = TN (A [R,M], B [R,N]) */
   int M, N;                   /* output shape                                                       */
-  int n_seg;                  /* NT: number of A segments (1..3) concatenated along K                */
-  const rpg_bf16* A[3];       /* NT: segment s is [M, K[s]] with row pitch lda[s] (elements)          */
-  int K[3];
-  int lda[3];
+  int n_seg;                  /* NT: number of A segments (1..6) concatenated along K                */
+  const rpg_bf16* A[6];       /* NT: segment s is [M, K[s]] with row pitch lda[s] (elements)          */
+  int K[6];
+  int lda[6];
   const rpg_bf16* B;          /* NT: [N, sum K] pitch ldb;   TN: [R, N] pitch ldb                     */
   int ldb;
   int R;                      /* TN: number of contracted rows                                       */
@@ -126,6 +126,13 @@ typedef struct {
   int mask_bits_ld;
   uint8_t* out_bits;          /* receives (stored value > 0) or NULL; needs N % 64 == 0               */
   int out_bits_ld;
+  /* fp32 mode ("split bf16"): an fp32 value travels as a (hi, lo) bf16 pair, v = hi + lo, and a Linear is
+   * evaluated as [A_hi | A_lo | A_hi] [W_hi | W_hi | W_lo]^T (K segments) with fp32 accumulation: ~2^-16 relative. */
+  const float* gadd_f32[2];   /* gathered fp32 node rows (uses gmap[i]) or NULL                        */
+  int gadd_f32_ld[2];
+  const rpg_bf16* resid_lo;   /* low plane of resid (pitch resid_ld) or NULL                          */
+  rpg_bf16* out_lo;           /* low plane of out: bf16(v - float(bf16(v))) (pitch ldo) or NULL        */
+  rpg_bf16* out_relu_lo;      /* low plane of out_relu or NULL                                        */
 } rpg_gemm_t;
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream);
@@ -138,7 +145,7 @@ int rpg_set_gemm_cluster(int ctas_per_cluster);
 int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R,
               float* ws, float* out, int ldo, rpg_stream_t stream);
 /* sizeof / offsetof probes so a foreign-language mirror of the structs can verify its layout.      */
-void rpg_struct_sizes(int32_t* out8);
+void rpg_struct_sizes(int32_t* out10);
 
 /* out[r, c] (+)= sum_s partial[s, r, c]  -- deterministic second stage of the TN split.            */
 int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols,
@@ -163,7 +170,8 @@ int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_
 
 /* AttentionBlock core, att.py:25-30: y[e,i] = sum_j softmax_j(phi[e,i]*theta[e,j]) * g[e,j].
  * gtp [Et, 3c] fp32 holds (g | theta | phi) rows; y [Et, ldy] bf16 (only the first c columns written). */
-int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_stream_t stream);
+int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo /* NULL in bf16 mode */,
+                      rpg_stream_t stream);
 /* Backward of the above with dy[e,:] = dyn[node(dst(e)), :] gathered through the template:
  * dgtp [Et, ld_dgtp] bf16 = (dg | dtheta | dphi) in the first 3c columns.                          */
 int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph,
@@ -196,8 +204,9 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
  * NULL and p_drop > 0, a counter-based hash of (seed, row, col) evaluated in-kernel (no mask traffic);
  * rpg_dropout_mask materialises that same decision so an oracle can consume it.                      */
 int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream);
-int rpg_head_fwd(const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed,
-                 float p_drop, const float* w6, const float* b6, float* pose, rpg_stream_t stream);
+int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo /* fp32 mode: low plane, else NULL */, int ldf,
+                 int64_t rows, int D, const uint8_t* keep, uint64_t seed, float p_drop, const float* w6,
+                 const float* b6, float* pose, rpg_stream_t stream);
 /* dfeat = (dpose * W6) * keep * scale * (feat > 0 if mask_relu); weight/bias gradients of the translation head
  * (rows 0..2 of W6: dw_t [3, D], db_t [3]) and of the rotation head (rows 3..5: dw_q, db_q), (+)= if accumulate;
  * ws: rpg_head_bwd_ws_floats(rows, D) floats of scratch for the deterministic two-stage reduction.   */
@@ -311,6 +320,41 @@ typedef struct {
   float* g_att_phi_w; float* g_att_phi_b;
   float* g_att_W_w; float* g_att_W_b;     /* [D, c], [D]    att.W            */
 } rpg_layer_grads_t;
+
+/* ------------------------------------------------------------------------------------------
+ * fp32 mode ("split bf16", BASELINE config B; forward / inference in this round)
+ * An fp32 value is carried as two bf16 planes (hi = bf16(v), lo = bf16(v - hi)); a Linear becomes
+ * [A_hi | A_lo | A_hi] [W_hi | W_hi | W_lo]^T on the same tcgen05 kernel (fp32 accumulation), which keeps
+ * ~16 mantissa bits per operand (single-pass TF32 keeps 10 and cannot meet the 1e-4 tolerance).
+ * ---------------------------------------------------------------------------------------- */
+int rpg_cast_f32_to_split(const float* src, rpg_bf16* hi, rpg_bf16* lo, int64_t n, rpg_stream_t stream);
+int rpg_split_to_f32(const rpg_bf16* hi, const rpg_bf16* lo, float* dst, int64_t n, rpg_stream_t stream);
+/* low plane of a weight window (the high plane is rpg_pack_weight's output)                          */
+int rpg_pack_weight_lo(const float* src, int ld_src, int r0, int c0, int rows, int cols, rpg_bf16* dst,
+                       int ld_dst, rpg_stream_t stream);
+int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D,
+                          rpg_bf16* e_hi, rpg_bf16* e_lo, int lde, rpg_stream_t stream);
+int rpg_aggregate_mean_split(const rpg_bf16* z_hi, const rpg_bf16* z_lo, int ldz, const rpg_graph_t* graph, int D,
+                             rpg_bf16* a_hi, rpg_bf16* a_lo, int lda, rpg_stream_t stream);
+
+typedef struct {
+  int D;
+  /* every operand is [N, 3K] = [W_hi | W_hi | W_lo] along K (W1u3: [D, 6D] = x part then a part)      */
+  const rpg_bf16 *Wn3, *W1e_e3, *W2e3, *W1m_e3, *W2m3, *Wgtp3, *WW3, *W1u3, *W2u3;
+  const float *b1e, *b2e, *b1m, *b2m, *bgtp, *bW, *b1u, *b2u;
+} rpg_layer_weights_split_t;
+
+typedef struct {
+  const rpg_bf16 *x_hi, *x_lo, *e_hi, *e_lo;        /* inputs  [Nt, D], [Et, D]                          */
+  float* P;                                        /* [Nt, 3D] fp32 node projections                    */
+  rpg_bf16 *h1_hi, *h1_lo, *e_new_hi, *e_new_lo, *e_new_relu_hi, *e_new_relu_lo, *h2_hi, *h2_lo, *m_hi, *m_lo;
+  float* gtp;                                      /* [Et, 3c] fp32                                     */
+  rpg_bf16 *y_hi, *y_lo;                           /* [Et, pad64(c)]                                    */
+  rpg_bf16 *z_hi, *z_lo, *a_hi, *a_lo, *h3_hi, *h3_lo, *out_hi, *out_lo, *out_relu_hi, *out_relu_lo;
+} rpg_layer_acts_split_t;
+
+int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* graph,
+                        const rpg_layer_acts_split_t* t, rpg_stream_t stream);
 
 int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt);
 int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,

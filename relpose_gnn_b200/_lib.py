@@ -30,13 +30,14 @@ class Graph(C.Structure):
 
 class Gemm(C.Structure):
     _fields_ = [("mode", I), ("M", I), ("N", I), ("n_seg", I),
-                ("A", P * 3), ("K", I * 3), ("lda", I * 3),
+                ("A", P * 6), ("K", I * 6), ("lda", I * 6),
                 ("B", P), ("ldb", I), ("R", I), ("splits", I), ("split_stride", I64), ("block_n", I),
                 ("bias", P), ("gadd", P * 2), ("gmap", P * 2), ("gadd_ld", I * 2), ("Ep", I), ("Nn", I),
                 ("resid", P), ("resid_ld", I), ("row_scale", P), ("row_scale_mod", I),
                 ("mask", P), ("mask_ld", I), ("relu", I),
                 ("out", P), ("out_relu", P), ("ldo", I), ("out_f32", P), ("ldo_f32", I),
-                ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I)]
+                ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I),
+                ("gadd_f32", P * 2), ("gadd_f32_ld", I * 2), ("resid_lo", P), ("out_lo", P), ("out_relu_lo", P)]
 
 
 class LayerWeights(C.Structure):
@@ -50,6 +51,18 @@ class LayerActs(C.Structure):
     _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
                                  "h3", "out", "out_relu", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
                                  "x_bits", "e_bits")]
+
+
+class LayerWeightsSplit(C.Structure):
+    _fields_ = [("D", I)] + [(n, P) for n in ("Wn3", "W1e_e3", "W2e3", "W1m_e3", "W2m3", "Wgtp3", "WW3", "W1u3", "W2u3",
+                                              "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")]
+
+
+class LayerActsSplit(C.Structure):
+    _fields_ = [(n, P) for n in ("x_hi", "x_lo", "e_hi", "e_lo", "P", "h1_hi", "h1_lo", "e_new_hi", "e_new_lo",
+                                 "e_new_relu_hi", "e_new_relu_lo", "h2_hi", "h2_lo", "m_hi", "m_lo", "gtp", "y_hi", "y_lo",
+                                 "z_hi", "z_lo", "a_hi", "a_lo", "h3_hi", "h3_lo", "out_hi", "out_lo", "out_relu_hi",
+                                 "out_relu_lo")]
 
 
 class LayerGrads(C.Structure):
@@ -80,14 +93,20 @@ SIGNATURES = {
     "rpg_pack_weight": (I, [P, I, I, I, I, I, P, I, I, P]),
     "rpg_cast_f32_to_bf16": (I, [P, P, I64, P]),
     "rpg_cast_bf16_to_f32": (I, [P, P, I64, P]),
-    "rpg_attention_fwd": (I, [P, I64, I, P, I, P]),
+    "rpg_attention_fwd": (I, [P, I64, I, P, I, P, P]),
+    "rpg_cast_f32_to_split": (I, [P, P, P, I64, P]),
+    "rpg_split_to_f32": (I, [P, P, P, I64, P]),
+    "rpg_pack_weight_lo": (I, [P, I, I, I, I, I, P, I, P]),
+    "rpg_edge_init_fwd_f32": (I, [P, I, P, C.POINTER(Graph), I, P, P, I, P]),
+    "rpg_aggregate_mean_split": (I, [P, P, I, C.POINTER(Graph), I, P, P, I, P]),
+    "rpg_layer_fwd_split": (I, [C.POINTER(LayerWeightsSplit), C.POINTER(Graph), C.POINTER(LayerActsSplit), P]),
     "rpg_attention_bwd": (I, [P, P, I, C.POINTER(Graph), I64, I, P, I, P]),
     "rpg_aggregate_mean": (I, [P, I, C.POINTER(Graph), I, P, I, P]),
     "rpg_edge_to_node_sum": (I, [P, I, C.POINTER(Graph), I, I, P, I, P]),
     "rpg_segment_sum": (I, [P, I, P, I, P, P, P, C.POINTER(Graph), I, P, I, P]),
     "rpg_edge_init_fwd": (I, [P, I, P, C.POINTER(Graph), I, P, I, P, P]),
     "rpg_dropout_mask": (I, [U64, F, I64, I, P, P]),
-    "rpg_head_fwd": (I, [P, I, I64, I, P, U64, F, P, P, P, P]),
+    "rpg_head_fwd": (I, [P, P, I, I64, I, P, U64, F, P, P, P, P]),
     "rpg_head_bwd_ws_floats": (I64, [I64, I]),
     "rpg_head_bwd": (I, [P, P, I, I64, I, P, U64, F, P, I, P, I, P, P, P, P, I, P, P]),
     "rpg_pose_loss_ws_floats": (I64, [I64]),
@@ -105,10 +124,11 @@ _lock = threading.Lock()
 
 
 def _check_layout(lib):
-    probe = (C.c_int32 * 8)()
+    probe = (C.c_int32 * 10)()
     lib.rpg_struct_sizes(probe)
     want = [C.sizeof(Graph), C.sizeof(Gemm), C.sizeof(LayerWeights), C.sizeof(LayerActs), C.sizeof(LayerGrads),
-            Gemm.out_f32.offset, LayerGrads.g_mlp0_w.offset, LayerWeights.b1e.offset]
+            Gemm.out_f32.offset, LayerGrads.g_mlp0_w.offset, LayerWeights.b1e.offset,
+            C.sizeof(LayerWeightsSplit), C.sizeof(LayerActsSplit)]
     if list(probe) != want:
         raise RpgError(f"ctypes mirrors out of sync with include/rpg.h: library {list(probe)} vs python {want}")
 

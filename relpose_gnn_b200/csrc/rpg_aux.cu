@@ -99,6 +99,29 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
     }
 }
 
+// fp32 mode: v -> (hi, lo) = (bf16(v), bf16(v - hi)) and back
+__global__ void cast_f32_split_kernel(const float* __restrict__ src, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+__global__ void split_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+// window of an fp32 weight -> low plane bf16(w - float(bf16(w)))   (the high plane is pack_weight_kernel's output)
+__global__ void pack_weight_lo_kernel(const float* __restrict__ src, int ld_src, int r0, int c0, int rows, int cols,
+                                      bf16* __restrict__ dst, int ld_dst) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < cols && r < rows) {
+        const float v = src[(size_t)(r0 + r) * ld_src + c0 + c];
+        dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Channel attention (att.py:25-30).  Logits are rank-1 (phi_i * theta_j), so the row maximum is
 // phi_i * max_j(theta) or phi_i * min_j(theta): no c x c tensor is ever stored.  One warp per edge row.
@@ -108,7 +131,8 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 template <int C_MAX>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy) {
+attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy,
+                     bf16* __restrict__ y_lo) {
     __shared__ __align__(16) float s_g[ATT_WARPS][C_MAX];
     __shared__ __align__(16) float s_t[ATT_WARPS][C_MAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,7 +172,11 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
                     num1 = fmaf(e1, gg[q], num1); den1 += e1;
                 }
             }
-            *reinterpret_cast<uint32_t*>(y + row * ldy + i0) = pack_bf16x2(num0 / den0, num1 / den1);
+            const float y0 = num0 / den0, y1 = num1 / den1;
+            *reinterpret_cast<uint32_t*>(y + row * ldy + i0) = pack_bf16x2(y0, y1);
+            if (y_lo)
+                *reinterpret_cast<uint32_t*>(y_lo + row * ldy + i0) =
+                    pack_bf16x2(y0 - __bfloat162float(__float2bfloat16_rn(y0)), y1 - __bfloat162float(__float2bfloat16_rn(y1)));
         }
         __syncwarp();
     }
@@ -269,7 +297,8 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
 __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf16* __restrict__ mask, int ldm,
                                    const int* __restrict__ ptr, const int* __restrict__ idx,
                                    const float* __restrict__ scale, long long Nt, int N, int Ep, int D,
-                                   bf16* __restrict__ out, int ldo) {
+                                   bf16* __restrict__ out, int ldo, const bf16* __restrict__ v_lo,
+                                   bf16* __restrict__ out_lo) {
     const int tpr = D >> 3;                                   // threads per row
     const long long total = Nt * tpr;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -291,6 +320,11 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            if (v_lo) {                                       // fp32 mode: value = hi + lo
+                unpack8(__ldg(reinterpret_cast<const uint4*>(v_lo + er * ldv + c)), f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            }
         }
         if (scale) {
             const float s = __ldg(scale + n);
@@ -298,6 +332,12 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
             for (int q = 0; q < 8; ++q) acc[q] *= s;
         }
         *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(acc);
+        if (out_lo) {
+            float r[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = acc[q] - __bfloat162float(__float2bfloat16_rn(acc[q]));
+            *reinterpret_cast<uint4*>(out_lo + row * ldo + c) = pack8(r);
+        }
     }
 }
 
@@ -332,6 +372,35 @@ __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, cons
     }
 }
 
+// fp32 mode: pmm fp32 [Nt, 2D] -> e0 (hi, lo)
+__global__ void edge_init_fwd_f32_kernel(const float* __restrict__ pmm, int ldp, const float* __restrict__ bias,
+                                         const int* __restrict__ tsrc, const int* __restrict__ tdst, long long Et, int N,
+                                         int Ep, int D, bf16* __restrict__ e_hi, bf16* __restrict__ e_lo, int lde) {
+    const int tpr = D >> 2;
+    const long long total = Et * tpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / tpr;
+        const int c = (int)(t - row * tpr) << 2;
+        const long long g = row / Ep;
+        const int k = (int)(row - g * Ep);
+        const int s = __ldg(tsrc + k), d = __ldg(tdst + k);
+        const long long nlo = g * N + min(s, d), nhi = g * N + max(s, d);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pmm + nlo * ldp + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pmm + nhi * ldp + D + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c));
+        const float v[4] = {fmaxf(a.x + b.x + bb.x, 0.f), fmaxf(a.y + b.y + bb.y, 0.f), fmaxf(a.z + b.z + bb.z, 0.f),
+                            fmaxf(a.w + b.w + bb.w, 0.f)};
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+        uint2 h, l;
+        h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+        l.x = pack_bf16x2(r[0], r[1]); l.y = pack_bf16x2(r[2], r[3]);
+        *reinterpret_cast<uint2*>(e_hi + row * lde + c) = h;
+        *reinterpret_cast<uint2*>(e_lo + row * lde + c) = l;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dropout keep decision: explicit uint8 mask (parity tests) or a counter-based hash of (seed,row,col)
 // ------------------------------------------------------------------------------------------------
@@ -359,7 +428,7 @@ constexpr int HEAD_WARPS = 8;
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, const uint8_t* __restrict__ keep,
                 unsigned long long seed, uint32_t thresh, int use_seed, float scale, const float* __restrict__ w6,
-                const float* __restrict__ b6, float* __restrict__ pose) {
+                const float* __restrict__ b6, float* __restrict__ pose, const bf16* __restrict__ feat_lo) {
     extern __shared__ __align__(16) float s_w[];   // [6][D]
     for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) s_w[i] = w6[i];
     __syncthreads();
@@ -369,6 +438,12 @@ head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, c
         for (int c = lane * 8; c < D; c += 256) {
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
+            if (feat_lo) {                                    // fp32 mode: value = hi + lo
+                float fl[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(feat_lo + row * ldf + c)), fl);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] += fl[q];
+            }
             if (keep) {
                 const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
                 const uint32_t kw[2] = {k8.x, k8.y};
@@ -642,11 +717,39 @@ int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_
     return check_launch("cast_bf16_f32_kernel");
 }
 
-int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_stream_t stream) {
+int rpg_cast_f32_to_split(const float* src, rpg_bf16* hi, rpg_bf16* lo, int64_t n, rpg_stream_t stream) {
+    if (!src || !hi || !lo || n <= 0) return set_error(RPG_E_ARG, "cast_f32_to_split: bad arguments");
+    cast_f32_split_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo), n);
+    return check_launch("cast_f32_split_kernel");
+}
+int rpg_split_to_f32(const rpg_bf16* hi, const rpg_bf16* lo, float* dst, int64_t n, rpg_stream_t stream) {
+    if (!dst || !hi || !lo || n <= 0) return set_error(RPG_E_ARG, "split_to_f32: bad arguments");
+    split_to_f32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(hi), reinterpret_cast<const bf16*>(lo), dst, n);
+    return check_launch("split_to_f32_kernel");
+}
+int rpg_pack_weight_lo(const float* src, int ld_src, int r0, int c0, int rows, int cols, rpg_bf16* dst, int ld_dst,
+                       rpg_stream_t stream) {
+    if (!src || !dst || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "pack_weight_lo: bad arguments");
+    dim3 grid((cols + 127) / 128, rows);
+    pack_weight_lo_kernel<<<grid, 128, 0, as_stream(stream)>>>(src, ld_src, r0, c0, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
+    return check_launch("pack_weight_lo_kernel");
+}
+int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e_hi,
+                          rpg_bf16* e_lo, int lde, rpg_stream_t stream) {
+    if (!pminmax || !bias || !graph || !e_hi || !e_lo || D % 4 || ldp % 4 || lde % 4) return set_error(RPG_E_ARG, "edge_init_fwd_f32: bad arguments");
+    const long long Et = (long long)graph->G * graph->Ep;
+    edge_init_fwd_f32_kernel<<<grid_for(Et * (D / 4), 256), 256, 0, as_stream(stream)>>>(
+        pminmax, ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D, reinterpret_cast<bf16*>(e_hi),
+        reinterpret_cast<bf16*>(e_lo), lde);
+    return check_launch("edge_init_fwd_f32_kernel");
+}
+
+int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, rpg_stream_t stream) {
     if (!gtp || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd: bad arguments");
     if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
-    attention_fwd_kernel<256><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy);
+    attention_fwd_kernel<256><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
+                                                                              reinterpret_cast<bf16*>(y_lo));
     return check_launch("attention_fwd_kernel");
 }
 
@@ -667,12 +770,14 @@ int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_
 }
 
 static int launch_segment(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, const int32_t* ptr, const int32_t* idx,
-                          const float* scale, const rpg_graph_t* g, int D, rpg_bf16* out, int ldo, cudaStream_t s) {
+                          const float* scale, const rpg_graph_t* g, int D, rpg_bf16* out, int ldo, cudaStream_t s,
+                          const rpg_bf16* v_lo = nullptr, rpg_bf16* out_lo = nullptr) {
     if (!v || !g || !out || !ptr || !idx || D % 8 || ldv % 8 || ldo % 8) return set_error(RPG_E_ARG, "segment_sum: bad arguments");
     const long long Nt = (long long)g->G * g->N;
     segment_sum_kernel<<<grid_for(Nt * (D / 8), 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv,
                                                                   reinterpret_cast<const bf16*>(mask), ldm, ptr, idx, scale,
-                                                                  Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out), ldo);
+                                                                  Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out), ldo,
+                                                                  reinterpret_cast<const bf16*>(v_lo), reinterpret_cast<bf16*>(out_lo));
     return check_launch("segment_sum_kernel");
 }
 
@@ -680,6 +785,13 @@ int rpg_aggregate_mean(const rpg_bf16* z, int ldz, const rpg_graph_t* graph, int
                        rpg_stream_t stream) {
     if (!graph) return set_error(RPG_E_ARG, "aggregate_mean: null graph");
     return launch_segment(z, ldz, nullptr, 0, graph->in_ptr, graph->in_idx, graph->inv_deg, graph, D, a, lda, as_stream(stream));
+}
+
+int rpg_aggregate_mean_split(const rpg_bf16* z_hi, const rpg_bf16* z_lo, int ldz, const rpg_graph_t* graph, int D,
+                             rpg_bf16* a_hi, rpg_bf16* a_lo, int lda, rpg_stream_t stream) {
+    if (!graph || !z_lo || !a_lo) return set_error(RPG_E_ARG, "aggregate_mean_split: null argument");
+    return launch_segment(z_hi, ldz, nullptr, 0, graph->in_ptr, graph->in_idx, graph->inv_deg, graph, D, a_hi, lda,
+                          as_stream(stream), z_lo, a_lo);
 }
 
 int rpg_edge_to_node_sum(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, int D, int by_src, rpg_bf16* out, int ldo,
@@ -711,8 +823,8 @@ int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* 
     return check_launch("dropout_mask_kernel");
 }
 
-int rpg_head_fwd(const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed, float p_drop,
-                 const float* w6, const float* b6, float* pose, rpg_stream_t stream) {
+int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t rows, int D, const uint8_t* keep,
+                 uint64_t seed, float p_drop, const float* w6, const float* b6, float* pose, rpg_stream_t stream) {
     if (!feat || !w6 || !b6 || !pose || rows <= 0 || D % 8 || ldf % 8) return set_error(RPG_E_ARG, "head_fwd: bad arguments");
     const size_t smem = (size_t)6 * D * sizeof(float);
     if (smem > 48 * 1024) {
@@ -726,7 +838,8 @@ int rpg_head_fwd(const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8
     const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
     const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
     head_fwd_kernel<<<grid_for(rows, HEAD_WARPS, 148 * 8), HEAD_WARPS * 32, smem, as_stream(stream)>>>(
-        reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose);
+        reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose,
+        reinterpret_cast<const bf16*>(feat_lo));
     return check_launch("head_fwd_kernel");
 }
 

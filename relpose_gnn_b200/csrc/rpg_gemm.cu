@@ -41,7 +41,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct GemmKParams {
     int mode, M, N, block_n;
-    int num_kb[3];                 // NT: 64-wide k-blocks per A segment
+    int num_kb[6];                 // NT: 64-wide k-blocks per A segment
     int total_kb;                  // NT: sum; TN: ceil(R / 64)
     int splits, kb_per_split;      // TN
     long long split_stride;
@@ -66,6 +66,18 @@ struct GemmKParams {
     int mask_bits_ld;
     uint8_t* out_bits;             // pattern (value > 0) of the stored result
     int out_bits_ld;
+    // fp32 ("split bf16") mode: values are (hi, lo) bf16 pairs, v = hi + lo
+    const float* gadd_f32[2];      // gathered fp32 node rows (same gmap as gadd)
+    int gadd_f32_ld[2];
+    const __nv_bfloat16* resid_lo; // low plane of resid
+    __nv_bfloat16* out_lo;         // low plane of out:      bf16(v - float(bf16(v)))
+    __nv_bfloat16* out_relu_lo;    // low plane of out_relu
+};
+
+struct GemmTmaps {
+    CUtensorMap a[6];              // A segments (NT) / a[0] = A (TN)
+    CUtensorMap b;
+    CUtensorMap out, out_relu, out_f32, out_lo, out_relu_lo;
 };
 
 __device__ __forceinline__ void add_bf16x8(float* f, const uint4& u) {
@@ -88,12 +100,16 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& u) {
 // B, which dominates at the small N, K of this path (every tile re-reads the whole weight panel), is halved.
 // OPS = the epilogue reads tensor operands (gathered node rows / residual / bf16 mask); compiled separately so that the
 // plain epilogue keeps its smaller register footprint and schedule.
-template <int MODE, int CL, bool OPS>
+// EPI = 2 additionally handles the fp32 ("split bf16") mode: fp32 gathered rows, (hi, lo) residuals and outputs.
+template <int MODE, int CL, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutRelu,
-               const __grid_constant__ CUtensorMap tmOutF32, const GemmKParams p) {
+gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
+    constexpr bool OPS = EPI >= 1;
+    const CUtensorMap& tmA0 = tm.a[0];
+    const CUtensorMap& tmB = tm.b;
+    const CUtensorMap& tmOut = tm.out;
+    const CUtensorMap& tmOutRelu = tm.out_relu;
+    const CUtensorMap& tmOutF32 = tm.out_f32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -144,8 +160,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int m_blk = (tile / num_n_blocks) * CL + cta_rank, n_blk = tile % num_n_blocks;
                 if (MODE == 0) {
                     int kb_global = 0;
-                    for (int s = 0; s < 3; ++s) {
-                        const CUtensorMap* tmA = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+                    for (int s = 0; s < 6; ++s) {
+                        const CUtensorMap* tmA = &tm.a[s];
                         for (int kb = 0; kb < p.num_kb[s]; ++kb, ++kb_global) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
@@ -260,10 +276,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int gnode0 = -1, gnode1 = -1;
             float rscale = 1.f;
             if (OPS && MODE == 0 && row_ok) {
-                if (p.gadd[0] || p.gadd[1]) {
+                if (p.gadd[0] || p.gadd[1] || (EPI == 2 && (p.gadd_f32[0] || p.gadd_f32[1]))) {
                     const int gidx = row / p.Ep, k = row - gidx * p.Ep;
-                    if (p.gadd[0]) gnode0 = gidx * p.Nn + __ldg(p.gmap[0] + k);
-                    if (p.gadd[1]) gnode1 = gidx * p.Nn + __ldg(p.gmap[1] + k);
+                    if (p.gmap[0]) gnode0 = gidx * p.Nn + __ldg(p.gmap[0] + k);
+                    if (p.gmap[1]) gnode1 = gidx * p.Nn + __ldg(p.gmap[1] + k);
                 }
                 if (p.row_scale) rscale = __ldg(p.row_scale + (row % p.row_scale_mod));
             }
@@ -297,8 +313,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 int kind0 = 0, kind1 = 0;                                        // 1 = add, 2 = bf16 ReLU mask
                 if (OPS && MODE == 0 && row_ok) {
                     const __nv_bfloat16* cand[4] = {
-                        gnode0 >= 0 ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
-                        gnode1 >= 0 ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
+                        (gnode0 >= 0 && p.gadd[0]) ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
+                        (gnode1 >= 0 && p.gadd[1]) ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
                         p.resid ? p.resid + (size_t)row * p.resid_ld : nullptr,
                         p.mask ? p.mask + (size_t)row * p.mask_ld : nullptr};
 #pragma unroll
@@ -368,8 +384,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (OPS && src1) { apply(opr1, kind1); ++used; }
                     if (OPS && row_ok) {                             // rare: more than two tensor operands
                         const __nv_bfloat16* cand[4] = {
-                            gnode0 >= 0 ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
-                            gnode1 >= 0 ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
+                            (gnode0 >= 0 && p.gadd[0]) ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
+                            (gnode1 >= 0 && p.gadd[1]) ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
                             p.resid ? p.resid + (size_t)row * p.resid_ld : nullptr,
                             p.mask ? p.mask + (size_t)row * p.mask_ld : nullptr};
                         int seen = 0;
@@ -381,6 +397,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             for (int qq = 0; qq < 8; ++qq)
                                 late[qq] = qq < nq ? __ldg(reinterpret_cast<const uint4*>(cand[o] + n0) + qq) : make_uint4(0, 0, 0, 0);
                             apply(late, o == 3 ? 2 : 1);
+                        }
+                    }
+                    if (EPI == 2 && row_ok) {            // fp32 mode: fp32 gathered node rows, low plane of the residual
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) {
+                            const int gn = o == 0 ? gnode0 : gnode1;
+                            if (p.gadd_f32[o] && gn >= 0) {
+                                const float4* src = reinterpret_cast<const float4*>(p.gadd_f32[o] + (size_t)gn * p.gadd_f32_ld[o] + n0);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    if (4 * j < ncols) {
+                                        const float4 v = __ldg(src + j);
+                                        f[4 * j] += v.x; f[4 * j + 1] += v.y; f[4 * j + 2] += v.z; f[4 * j + 3] += v.w;
+                                    }
+                                }
+                            }
+                        }
+                        if (p.resid_lo) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.resid_lo + (size_t)row * p.resid_ld + n0);
+#pragma unroll
+                            for (int qq = 0; qq < 8; ++qq) if (qq < nq) add_bf16x8(f + 8 * qq, __ldg(src + qq));
                         }
                     }
                     if (!scaled) {
@@ -431,6 +468,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) { tma_store_2d(&tmOutRelu, stg, n0, row0); bulk_commit(); }
+                    }
+                    if (EPI == 2) {                      // low planes: lo = bf16(v - float(bf16(v)))
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            if (pass == 0 ? p.out_lo == nullptr : p.out_relu_lo == nullptr) continue;
+                            if (lane == 0) bulk_wait_read_all();
+                            __syncwarp();
+#pragma unroll
+                            for (int qq = 0; qq < 8; ++qq) {
+                                float r[8];
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) {
+                                    const float v = pass == 0 ? f[8 * qq + t] : fmaxf(f[8 * qq + t], 0.f);
+                                    r[t] = v - __bfloat162float(__float2bfloat16_rn(v));
+                                }
+                                uint4 u;
+                                u.x = pack_bf16x2(r[0], r[1]); u.y = pack_bf16x2(r[2], r[3]);
+                                u.z = pack_bf16x2(r[4], r[5]); u.w = pack_bf16x2(r[6], r[7]);
+                                *reinterpret_cast<uint4*>(my_row + ((qq ^ my_sw) << 4)) = u;
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) { tma_store_2d(pass == 0 ? &tm.out_lo : &tm.out_relu_lo, stg, n0, row0); bulk_commit(); }
+                        }
                     }
                 }
                 if (p.out_f32) {
@@ -600,11 +661,14 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     GemmKParams p;
     memset(&p, 0, sizeof p);
     p.mode = g->mode; p.M = g->M; p.N = g->N; p.block_n = block_n;
-    CUtensorMap tmA[3], tmB;
-    memset(tmA, 0, sizeof tmA);
+    static_assert(sizeof(GemmTmaps) + sizeof(GemmKParams) < 4000, "kernel parameter space");
+    GemmTmaps tmaps;
+    memset(&tmaps, 0, sizeof tmaps);
+    CUtensorMap* tmA = tmaps.a;
+    CUtensorMap& tmB = tmaps.b;
     int rc;
     if (g->mode == 0) {
-        if (g->n_seg < 1 || g->n_seg > 3) return set_error(RPG_E_ARG, "rpg_gemm: n_seg must be 1..3");
+        if (g->n_seg < 1 || g->n_seg > 6) return set_error(RPG_E_ARG, "rpg_gemm: n_seg must be 1..6");
         int ktot = 0;
         for (int s = 0; s < g->n_seg; ++s) {
             if (!g->A[s] || !aligned16(g->A[s]) || g->lda[s] % 8 || g->K[s] <= 0 || g->K[s] % BLOCK_K)
@@ -613,7 +677,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
             ktot += g->K[s];
             if ((rc = make_tmap(&tmA[s], g->A[s], g->K[s], g->M, g->lda[s], BLOCK_K, BLOCK_M))) return rc;
         }
-        for (int s = g->n_seg; s < 3; ++s) tmA[s] = tmA[0];
+        for (int s = g->n_seg; s < 6; ++s) tmA[s] = tmA[0];
         p.total_kb = ktot / BLOCK_K;
         if ((rc = make_tmap(&tmB, g->B, ktot, g->N, g->ldb, BLOCK_K, block_n / cl))) return rc;
         p.splits = 1;
@@ -629,7 +693,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         p.kb_per_split = (p.total_kb + g->splits - 1) / g->splits;
         p.split_stride = g->split_stride;
         if ((rc = make_tmap(&tmA[0], g->A[0], g->M, g->R, g->lda[0], 64, BLOCK_K))) return rc;
-        tmA[1] = tmA[2] = tmA[0];
+        for (int s = 1; s < 6; ++s) tmA[s] = tmA[0];
         if ((rc = make_tmap(&tmB, g->B, g->N, g->R, g->ldb, 64, BLOCK_K))) return rc;
     } else {
         return set_error(RPG_E_ARG, "rpg_gemm: mode must be 0 (NT) or 1 (TN)");
@@ -661,23 +725,35 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if ((p.out && !aligned16(p.out)) || (p.out_relu && !aligned16(p.out_relu)) || (p.out_f32 && !aligned16(p.out_f32)))
         return set_error(RPG_E_ARG, "rpg_gemm: output pointers must be 16-byte aligned");
     // result tiles leave through TMA stores: 32 rows x 64 bf16 (or 32 fp32) columns per box, clipped at the tensor edge
-    CUtensorMap tmOut, tmOutRelu, tmOutF32;
-    memset(&tmOut, 0, sizeof tmOut);
-    tmOutRelu = tmOutF32 = tmOut;
-    if (p.out && (rc = make_tmap(&tmOut, p.out, p.N, p.M, p.ldo, 64, 32))) return rc;
-    if (p.out_relu && (rc = make_tmap(&tmOutRelu, p.out_relu, p.N, p.M, p.ldo, 64, 32))) return rc;
-    if (p.out_f32 && (rc = make_tmap_f32_3d(&tmOutF32, p.out_f32, p.N, p.M, p.splits, p.ldo_f32, p.split_stride))) return rc;
+    for (int i = 0; i < 2; ++i) { p.gadd_f32[i] = g->gadd_f32[i]; p.gadd_f32_ld[i] = g->gadd_f32_ld[i]; }
+    p.resid_lo = reinterpret_cast<const __nv_bfloat16*>(g->resid_lo);
+    p.out_lo = reinterpret_cast<__nv_bfloat16*>(g->out_lo);
+    p.out_relu_lo = reinterpret_cast<__nv_bfloat16*>(g->out_relu_lo);
+    const bool split_mode = p.gadd_f32[0] || p.gadd_f32[1] || p.resid_lo || p.out_lo || p.out_relu_lo;
+    if (split_mode && g->mode != 0) return set_error(RPG_E_ARG, "rpg_gemm: fp32 (split) operands need NT mode");
+    if ((p.out_lo && !p.out) || (p.out_relu_lo && !p.out_relu) || (p.resid_lo && !p.resid))
+        return set_error(RPG_E_ARG, "rpg_gemm: a low plane needs its high plane");
+    if ((p.gadd_f32[0] && (!g->gmap[0] || g->gadd_f32_ld[0] % 4)) || (p.gadd_f32[1] && (!g->gmap[1] || g->gadd_f32_ld[1] % 4)) ||
+        ((p.gadd_f32[0] || p.gadd_f32[1]) && (g->Ep <= 0 || g->Nn <= 0)))
+        return set_error(RPG_E_ARG, "rpg_gemm: fp32 gathered add needs gmap, Ep, Nn and a pitch that is a multiple of 4");
+    if (p.out && (rc = make_tmap(&tmaps.out, p.out, p.N, p.M, p.ldo, 64, 32))) return rc;
+    if (p.out_relu && (rc = make_tmap(&tmaps.out_relu, p.out_relu, p.N, p.M, p.ldo, 64, 32))) return rc;
+    if (p.out_lo && (rc = make_tmap(&tmaps.out_lo, p.out_lo, p.N, p.M, p.ldo, 64, 32))) return rc;
+    if (p.out_relu_lo && (rc = make_tmap(&tmaps.out_relu_lo, p.out_relu_lo, p.N, p.M, p.ldo, 64, 32))) return rc;
+    if (p.out_f32 && (rc = make_tmap_f32_3d(&tmaps.out_f32, p.out_f32, p.N, p.M, p.splits, p.ldo_f32, p.split_stride))) return rc;
 
     std::call_once(g_attr_once, [] {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
@@ -700,9 +776,13 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cudaEventRecord(rec.e0, stream);
     }
     const bool ops = g->mode == 0 && (p.gadd[0] || p.gadd[1] || p.resid || p.mask);
-    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKParams);
-    if (cl == 1) kern = g->mode == 1 ? gemm_tc_kernel<1, 1, false> : (ops ? gemm_tc_kernel<0, 1, true> : gemm_tc_kernel<0, 1, false>);
-    else kern = g->mode == 1 ? gemm_tc_kernel<1, 2, false> : (ops ? gemm_tc_kernel<0, 2, true> : gemm_tc_kernel<0, 2, false>);
+    void (*kern)(GemmTmaps, GemmKParams);
+    if (cl == 1)
+        kern = g->mode == 1 ? gemm_tc_kernel<1, 1, 0>
+                            : (split_mode ? gemm_tc_kernel<0, 1, 2> : (ops ? gemm_tc_kernel<0, 1, 1> : gemm_tc_kernel<0, 1, 0>));
+    else
+        kern = g->mode == 1 ? gemm_tc_kernel<1, 2, 0>
+                            : (split_mode ? gemm_tc_kernel<0, 2, 2> : (ops ? gemm_tc_kernel<0, 2, 1> : gemm_tc_kernel<0, 2, 0>));
     {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
@@ -715,7 +795,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA[0], tmA[1], tmA[2], tmB, tmOut, tmOutRelu, tmOutF32, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmaps, p);
         (void)e;
     }
     if (prof) {

@@ -131,6 +131,8 @@ void rpg_struct_sizes(int32_t* out) {
     out[5] = (int32_t)offsetof(rpg_gemm_t, out_f32);
     out[6] = (int32_t)offsetof(rpg_layer_grads_t, g_mlp0_w);
     out[7] = (int32_t)offsetof(rpg_layer_weights_t, b1e);
+    out[8] = (int32_t)sizeof(rpg_layer_weights_split_t);
+    out[9] = (int32_t)sizeof(rpg_layer_acts_split_t);
 }
 
 #define RPG_TRY(expr)            \
@@ -188,7 +190,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     RPG_TRY(gemm_launch(&g, s));
 
     // (7) rank-1 softmax attention (att.py:25-30)
-    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, stream));
+    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, stream));
 
     // (8) z = y WW^T + bW + m (att.py:32-33) as [y | m] [WW | I]^T: the residual is a second K segment (exact in the
     //     fp32 accumulator) so it streams through TMA with the operands instead of being fetched by the epilogue
@@ -208,6 +210,78 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g = nt((int)Nt, D, t->h3, D, D, w->W2u, D);
     g.bias = w->b2u; g.out = t->out; g.out_relu = t->out_relu; g.ldo = D;
     g.out_bits = t->out_bits; g.out_bits_ld = D / 8;
+    RPG_TRY(gemm_launch(&g, s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 mode (forward only in this round): every activation is a (hi, lo) bf16 pair and every Linear is evaluated as
+//   [A_hi | A_lo | A_hi] [W_hi | W_hi | W_lo]^T   (the lo*lo term, 2^-18 relative, is dropped)
+// on the same tcgen05 kernel with fp32 accumulation; node projections stay fp32.  Same sequence as rpg_layer_fwd.
+static void set3(rpg_gemm_t& g, int first, const rpg_bf16* hi, const rpg_bf16* lo, int K, int ld) {
+    g.A[first] = hi; g.A[first + 1] = lo; g.A[first + 2] = hi;
+    for (int i = 0; i < 3; ++i) { g.K[first + i] = K; g.lda[first + i] = ld; }
+}
+
+int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* gr, const rpg_layer_acts_split_t* t,
+                        rpg_stream_t stream) {
+    if (!w || !gr || !t) return set_error(RPG_E_ARG, "layer_fwd_split: null argument");
+    const int D = w->D, c = D / 8, c3 = 3 * c, cp = pad64(c);
+    if (D % 128) return set_error(RPG_E_UNSUPPORTED, "layer_fwd_split: channel count must be a multiple of 128");
+    const long long Nt = (long long)gr->G * gr->N, Et = (long long)gr->G * gr->Ep;
+    if (Nt > 0x7fffffff || Et > 0x7fffffff) return set_error(RPG_E_UNSUPPORTED, "layer_fwd_split: more than 2^31 rows");
+    cudaStream_t s = as_stream(stream);
+    rpg_gemm_t g;
+    auto base = [&](int M, int N, const rpg_bf16* B, int ldb) {
+        memset(&g, 0, sizeof g);
+        g.mode = 0; g.M = M; g.N = N; g.B = B; g.ldb = ldb;
+    };
+    // (1) P = x Wn^T  -> fp32 [Nt, 3D]
+    base((int)Nt, 3 * D, w->Wn3, 3 * D); g.n_seg = 3; set3(g, 0, t->x_hi, t->x_lo, D, D);
+    g.out_f32 = t->P; g.ldo_f32 = 3 * D;
+    RPG_TRY(gemm_launch(&g, s));
+    // (2) h1 = relu(e W1e_e^T + P_s[src] + P_d[dst] + b)
+    base((int)Et, D, w->W1e_e3, 3 * D); g.n_seg = 3; set3(g, 0, t->e_hi, t->e_lo, D, D);
+    g.bias = w->b1e; g.relu = 1; g.Ep = gr->Ep; g.Nn = gr->N;
+    g.gadd_f32[0] = t->P;     g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
+    g.gadd_f32[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_f32_ld[1] = 3 * D;
+    g.out = t->h1_hi; g.out_lo = t->h1_lo; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    // (3) e' = h1 W2e^T + b  (+ relu'd copy)
+    base((int)Et, D, w->W2e3, 3 * D); g.n_seg = 3; set3(g, 0, t->h1_hi, t->h1_lo, D, D);
+    g.bias = w->b2e; g.out = t->e_new_hi; g.out_lo = t->e_new_lo; g.ldo = D;
+    g.out_relu = t->e_new_relu_hi; g.out_relu_lo = t->e_new_relu_lo;
+    RPG_TRY(gemm_launch(&g, s));
+    // (4) h2 = relu(e' W1m_e^T + P_m[src] + b)
+    base((int)Et, D, w->W1m_e3, 3 * D); g.n_seg = 3; set3(g, 0, t->e_new_hi, t->e_new_lo, D, D);
+    g.bias = w->b1m; g.relu = 1; g.Ep = gr->Ep; g.Nn = gr->N;
+    g.gadd_f32[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
+    g.out = t->h2_hi; g.out_lo = t->h2_lo; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    // (5) m = h2 W2m^T + b
+    base((int)Et, D, w->W2m3, 3 * D); g.n_seg = 3; set3(g, 0, t->h2_hi, t->h2_lo, D, D);
+    g.bias = w->b2m; g.out = t->m_hi; g.out_lo = t->m_lo; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    // (6) (g | theta | phi) fp32
+    base((int)Et, c3, w->Wgtp3, 3 * D); g.n_seg = 3; set3(g, 0, t->m_hi, t->m_lo, D, D);
+    g.bias = w->bgtp; g.out_f32 = t->gtp; g.ldo_f32 = c3;
+    RPG_TRY(gemm_launch(&g, s));
+    // (7) attention -> y (hi, lo)
+    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y_hi, cp, t->y_lo, stream));
+    // (8) z = y WW^T + bW + m
+    base((int)Et, D, w->WW3, 3 * cp); g.n_seg = 3; set3(g, 0, t->y_hi, t->y_lo, cp, cp);
+    g.bias = w->bW; g.resid = t->m_hi; g.resid_lo = t->m_lo; g.resid_ld = D;
+    g.out = t->z_hi; g.out_lo = t->z_lo; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    // (9) mean over incoming edges
+    RPG_TRY(rpg_aggregate_mean_split(t->z_hi, t->z_lo, D, gr, D, t->a_hi, t->a_lo, D, stream));
+    // (10) out = relu([x | a] W1u^T + b) W2u^T + b
+    base((int)Nt, D, w->W1u3, 6 * D); g.n_seg = 6; set3(g, 0, t->x_hi, t->x_lo, D, D); set3(g, 3, t->a_hi, t->a_lo, D, D);
+    g.bias = w->b1u; g.relu = 1; g.out = t->h3_hi; g.out_lo = t->h3_lo; g.ldo = D;
+    RPG_TRY(gemm_launch(&g, s));
+    base((int)Nt, D, w->W2u3, 3 * D); g.n_seg = 3; set3(g, 0, t->h3_hi, t->h3_lo, D, D);
+    g.bias = w->b2u; g.out = t->out_hi; g.out_lo = t->out_lo; g.ldo = D;
+    g.out_relu = t->out_relu_hi; g.out_relu_lo = t->out_relu_lo;
     RPG_TRY(gemm_launch(&g, s));
     return 0;
 }

@@ -133,6 +133,88 @@ class PackedLayerWeights:
         return s
 
 
+class PackedLayerWeightsSplit:
+    """fp32 mode: every forward operand as [W_hi | W_hi | W_lo] along K (see include/rpg.h, rpg_layer_fwd_split)."""
+
+    def __init__(self, D, device):
+        self.D, self.device = D, device
+        c = D // 8
+        self.c, self.cp = c, pad64(c)
+        shapes = {"Wn3": (3 * D, 3 * D), "W1e_e3": (D, 3 * D), "W2e3": (D, 3 * D), "W1m_e3": (D, 3 * D), "W2m3": (D, 3 * D),
+                  "Wgtp3": (3 * c, 3 * D), "WW3": (D, 3 * self.cp), "W1u3": (D, 6 * D), "W2u3": (D, 3 * D)}
+        self.t = {n: torch.zeros(r, k, dtype=BF16, device=device) for n, (r, k) in shapes.items()}
+        self.bgtp = torch.zeros(3 * c, dtype=torch.float32, device=device)
+        self.versions = None
+        self.struct = _lib.LayerWeightsSplit()
+
+    def refresh(self, mod):
+        p = {n: mod.get_parameter(n) for n in PARAM_ORDER}
+        versions = tuple((q.data_ptr(), q._version) for q in p.values())
+        if versions == self.versions:
+            return self.struct
+        D, c, t = self.D, self.c, self.t
+        W1e, W1m, W1u = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data, p["mlp_updating.0.weight"].data
+        pk3 = ops.pack_weight3
+        pk3(W1e, t["Wn3"][0:D], c0=0, cols=D)
+        pk3(W1e, t["Wn3"][D:2 * D], c0=D, cols=D)
+        pk3(W1m, t["Wn3"][2 * D:3 * D], c0=0, cols=D)
+        pk3(W1e, t["W1e_e3"], c0=2 * D, cols=D)
+        pk3(p["edge_model.edge_mlp.2.weight"].data, t["W2e3"])
+        pk3(W1m, t["W1m_e3"], c0=D, cols=D)
+        pk3(p["mlp.2.weight"].data, t["W2m3"])
+        for i, nm in enumerate(("g", "theta", "phi")):
+            pk3(p[f"att.{nm}.weight"].data, t["Wgtp3"][i * c:(i + 1) * c])
+            self.bgtp[i * c:(i + 1) * c].copy_(p[f"att.{nm}.bias"].data)
+        pk3(p["att.W.weight"].data, t["WW3"], cols=c)        # K padded to pad64(c): the padding columns stay zero
+        pk3(W1u, t["W1u3"][:, :3 * D], c0=0, cols=D)
+        pk3(W1u, t["W1u3"][:, 3 * D:], c0=D, cols=D)
+        pk3(p["mlp_updating.2.weight"].data, t["W2u3"])
+        s = self.struct
+        s.D = D
+        for name, tensor in t.items():
+            setattr(s, name, tensor.data_ptr())
+        s.b1e = p["edge_model.edge_mlp.0.bias"].data_ptr()
+        s.b2e = p["edge_model.edge_mlp.2.bias"].data_ptr()
+        s.b1m = p["mlp.0.bias"].data_ptr()
+        s.b2m = p["mlp.2.bias"].data_ptr()
+        s.bgtp = self.bgtp.data_ptr()
+        s.bW = p["att.W.bias"].data_ptr()
+        s.b1u = p["mlp_updating.0.bias"].data_ptr()
+        s.b2u = p["mlp_updating.2.bias"].data_ptr()
+        self.versions = versions
+        return s
+
+
+def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
+    """fp32 mode forward.  x, e: (hi, lo) bf16 plane pairs.  Returns the dict of activation planes."""
+    D = weights.D
+    dev = x[0].device
+    Nt, Et = graph.n_node_rows, graph.n_edge_rows
+    c = D // 8
+    cp = pad64(c)
+
+    def pair(rows, cols, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(rows, cols, dtype=BF16, device=dev), f(rows, cols, dtype=BF16, device=dev)
+
+    a = {"x": x, "e": e, "h1": pair(Et, D), "e_new": pair(Et, D), "h2": pair(Et, D), "m": pair(Et, D),
+         "y": pair(Et, cp, zero=(cp != c)), "z": pair(Et, D), "a": pair(Nt, D), "h3": pair(Nt, D), "out": pair(Nt, D)}
+    if want_relu_copies:
+        a["e_new_relu"] = pair(Et, D)
+        a["out_relu"] = pair(Nt, D)
+    P = torch.empty(Nt, 3 * D, dtype=torch.float32, device=dev)
+    gtp = torch.empty(Et, 3 * c, dtype=torch.float32, device=dev)
+    s = _lib.LayerActsSplit()
+    for k, (hi, lo) in a.items():
+        setattr(s, k + "_hi", hi.data_ptr())
+        setattr(s, k + "_lo", lo.data_ptr())
+    s.P, s.gtp = P.data_ptr(), gtp.data_ptr()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(_lib.load().rpg_layer_fwd_split(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd_split")
+    a["_keep"] = (P, gtp, s)
+    return a
+
+
 def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None, e_bits=None, arena=None):
     """Runs rpg_layer_fwd on bf16 inputs; returns the dict of activation tensors (kept for backward).
     x_bits / e_bits: optional ReLU bit patterns of the inputs (when they are ReLU outputs of a previous op)."""
@@ -263,12 +345,21 @@ class simpleConvEdge_upt(nn.Module):
         self.edge_model = simpleEdgeModel(in_channels, edge_channels, edge_channels)
         self.att = AttentionBlock(in_channels)
         self._pack_cache = {}
+        # "bf16" (default; forward + backward) or "fp32" (split-bf16 arithmetic, ~1e-5 relative; inference only for now)
+        self.precision = "bf16"
 
     def _packed(self, device):
         key = str(device)
         pw = self._pack_cache.get(key)
         if pw is None:
             pw = self._pack_cache[key] = PackedLayerWeights(self.in_channels, device)
+        return pw
+
+    def _packed_split(self, device):
+        key = "split:" + str(device)
+        pw = self._pack_cache.get(key)
+        if pw is None:
+            pw = self._pack_cache[key] = PackedLayerWeightsSplit(self.in_channels, device)
         return pw
 
     def _ordered_params(self):
@@ -291,4 +382,14 @@ class simpleConvEdge_upt(nn.Module):
     def forward(self, x, edge_index, edge_attr):
         self._check_inputs(x, edge_index, edge_attr)
         graph = graph_mod.from_edge_index(edge_index, x.size(0))
+        if self.precision == "fp32":
+            if torch.is_grad_enabled() and (x.requires_grad or edge_attr.requires_grad or
+                                            any(p.requires_grad for p in self.parameters())):
+                raise NotImplementedError("precision='fp32' is inference-only in this version: call under torch.no_grad() "
+                                          "(training runs in the bf16 mode)")
+            w = self._packed_split(x.device).refresh(self)
+            acts = layer_forward_split_raw(w, graph, ops.to_split(x.float()), ops.to_split(edge_attr.float()))
+            return ops.from_split(*acts["out"]), ops.from_split(*acts["e_new"])
+        if self.precision != "bf16":
+            raise ValueError("precision must be 'bf16' or 'fp32'")
         return _LayerFn.apply(x, edge_attr, self, graph, *self._ordered_params())

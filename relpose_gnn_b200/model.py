@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import graph as graph_mod, ops
-from .layers import PARAM_ORDER, layer_backward_raw, layer_forward_raw, simpleConvEdge_upt
+from .layers import PARAM_ORDER, layer_backward_raw, layer_forward_raw, layer_forward_split_raw, simpleConvEdge_upt
 from .ops import BF16
 
 _HEADS = ("fc_xyz", "fc_wpqr", "fc_xyz_R", "fc_wpqr_R")
@@ -139,6 +139,7 @@ class RelPoseGNN(nn.Module):
         self.dropout_seed = 0x5EED
         self.keep_debug_activations = False      # tests: keep the saved activations of the last forward
         self.fused_grad_accumulation = False     # see attach_grad_bucket
+        self.precision = "bf16"                  # or "fp32": split-bf16 arithmetic, inference only for now
 
     def attach_grad_bucket(self, bucket):
         """Makes backward accumulate every gradient of this module directly into `param.grad` (which a
@@ -204,8 +205,39 @@ class RelPoseGNN(nn.Module):
             raise ValueError(f"x must be [rows, {self.node_dim}]")
         graph = graph_mod.from_edge_index(edge_index, x.size(0))
         drop = self._drop_args(keep_x, keep_e)
+        if self.precision == "fp32":
+            pose_n, pose_e = self._forward_fp32(x, graph, drop)
+            return pose_n, pose_e, edge_index
         pose_n, pose_e = _StackFn.apply(x, self, graph, drop, *self._ordered_params())
         return pose_n, pose_e, edge_index
+
+    def _forward_fp32(self, x, graph, drop):
+        """fp32 mode (BASELINE config B): split-bf16 arithmetic end to end; inference only in this version."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("precision='fp32' is inference-only in this version: call under torch.no_grad()")
+        D, R = self.node_dim, self.gnn_recursion
+        dev = x.device
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        lw = self.gnn1._packed_split(dev).refresh(self.gnn1)
+        sw = self._packed_stack(dev)
+        if "Wmm3" not in sw or sw.get("Wmm3_versions") != sw["versions"]:
+            sw["Wmm3"] = torch.zeros(2 * D, 3 * D, dtype=BF16, device=dev)
+            W = self.proj_edge.weight.data
+            ops.pack_weight3(W, sw["Wmm3"][:D], c0=0, cols=D)
+            ops.pack_weight3(W, sw["Wmm3"][D:], c0=D, cols=D)
+            sw["Wmm3_versions"] = sw["versions"]
+        xs = ops.to_split(x.float())
+        pmm = torch.empty(Nt, 2 * D, dtype=torch.float32, device=dev)
+        ops.gemm_nt(None, sw["Wmm3"], segs=[xs[0], xs[1], xs[0]], out_f32=pmm)
+        e = (torch.empty(Et, D, dtype=BF16, device=dev), torch.empty(Et, D, dtype=BF16, device=dev))
+        ops.edge_init_fwd_f32(pmm, self.proj_edge.bias.data, graph, D, e[0], e[1])
+        for _ in range(R):
+            a = layer_forward_split_raw(lw, graph, xs, e, want_relu_copies=True)
+            xs, e = a["out_relu"], a["e_new_relu"]
+        p_drop, keep_x, keep_e, seed = drop
+        pose_n = ops.head_fwd(xs[0], sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop, feat_lo=xs[1])
+        pose_e = ops.head_fwd(e[0], sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop, feat_lo=e[1])
+        return pose_n, pose_e
 
     @staticmethod
     def compute_RP(p, edge_index):

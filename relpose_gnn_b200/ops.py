@@ -165,9 +165,38 @@ def to_f32(t):
     return out
 
 
-def attention_fwd(gtp, c, y):
-    check(_lib.load().rpg_attention_fwd(gtp.data_ptr(), gtp.size(0), c, y.data_ptr(), y.stride(0), _stream(gtp)),
+def attention_fwd(gtp, c, y, y_lo=None):
+    check(_lib.load().rpg_attention_fwd(gtp.data_ptr(), gtp.size(0), c, y.data_ptr(), y.stride(0), ptr(y_lo), _stream(gtp)),
           "rpg_attention_fwd")
+
+
+def to_split(t):
+    """fp32 [rows, C] -> (hi, lo) bf16 planes with t = hi + lo to ~2^-17 relative."""
+    t = t.contiguous()
+    if t.dtype != torch.float32:
+        raise TypeError("to_split expects float32")
+    hi = torch.empty(t.shape, dtype=BF16, device=t.device)
+    lo = torch.empty(t.shape, dtype=BF16, device=t.device)
+    check(_lib.load().rpg_cast_f32_to_split(t.data_ptr(), hi.data_ptr(), lo.data_ptr(), t.numel(), _stream(t)), "to_split")
+    return hi, lo
+
+
+def from_split(hi, lo):
+    out = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
+    check(_lib.load().rpg_split_to_f32(hi.data_ptr(), lo.data_ptr(), out.data_ptr(), hi.numel(), _stream(hi)), "from_split")
+    return out
+
+
+def pack_weight3(src, dst, c0=0, cols=None):
+    """dst[:, 0:3*cols] = [W_hi | W_hi | W_lo] of the column window [c0, c0+cols) of the fp32 weight `src`."""
+    lib = _lib.load()
+    rows = src.size(0)
+    cols = cols if cols is not None else src.size(1) - c0
+    kp = dst.size(1) // 3
+    pack_weight(src, dst[:, 0:kp], c0=c0, cols=cols)
+    pack_weight(src, dst[:, kp:2 * kp], c0=c0, cols=cols)
+    check(lib.rpg_pack_weight_lo(src.data_ptr(), src.stride(0), 0, c0, rows, cols, dst[:, 2 * kp:].data_ptr(), dst.stride(0),
+                                 _stream(src)), "rpg_pack_weight_lo")
 
 
 def attention_bwd(gtp, dyn, graph, c, dgtp):
@@ -194,15 +223,21 @@ def edge_init_fwd(pmm, bias, graph, D, e0, e0_bits=None):
                                         e0.data_ptr(), e0.stride(0), ptr(e0_bits), _stream(pmm)), "rpg_edge_init_fwd")
 
 
+def edge_init_fwd_f32(pmm, bias, graph, D, e_hi, e_lo):
+    check(_lib.load().rpg_edge_init_fwd_f32(pmm.data_ptr(), pmm.stride(0), bias.data_ptr(), graph.byref(), D,
+                                            e_hi.data_ptr(), e_lo.data_ptr(), e_hi.stride(0), _stream(pmm)),
+          "rpg_edge_init_fwd_f32")
+
+
 def dropout_mask(seed, p_drop, rows, D, device):
     keep = torch.empty(rows, D, dtype=torch.uint8, device=device)
     check(_lib.load().rpg_dropout_mask(seed, p_drop, rows, D, keep.data_ptr(), _stream(keep)), "rpg_dropout_mask")
     return keep
 
 
-def head_fwd(feat, w6, b6, keep=None, seed=0, p_drop=0.0):
+def head_fwd(feat, w6, b6, keep=None, seed=0, p_drop=0.0, feat_lo=None):
     pose = torch.empty(feat.size(0), 6, dtype=torch.float32, device=feat.device)
-    check(_lib.load().rpg_head_fwd(feat.data_ptr(), feat.stride(0), feat.size(0), feat.size(1), ptr(keep), seed,
+    check(_lib.load().rpg_head_fwd(feat.data_ptr(), ptr(feat_lo), feat.stride(0), feat.size(0), feat.size(1), ptr(keep), seed,
                                    p_drop, w6.data_ptr(), b6.data_ptr(), pose.data_ptr(), _stream(feat)), "rpg_head_fwd")
     return pose
 

@@ -334,3 +334,64 @@ def test_fused_gradient_accumulation_matches_autograd_path():
     # same kernels, different association of the two steps' sums ((g1 + a) + b vs g1 + (a + b)): not bitwise
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
     assert (a - b).norm() / b.norm() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ fp32 mode
+TOL_FP32 = 1e-4      # BASELINE.json north_star: fp32/TF32 mode within 1e-4 relative
+
+
+@pytest.mark.parametrize("D,N,Gn,drop_edges", [(512, 9, 5, False), (512, 17, 2, True), (128, 8, 9, False)])
+def test_fp32_mode_layer_against_oracle(D, N, Gn, drop_edges):
+    """fp32 mode (split-bf16 operands, fp32 accumulation) against the fp64 oracle AND against the reference fixture's
+    own fp32 run where one exists; bf16 mode on the same inputs for contrast."""
+    seed = 5000 + D + N
+    params = R.synth_params(R.LAYER_SHAPES(D), seed, torch.float64)
+    x, _ = R.synth_inputs(Gn, N, D, seed + 1, torch.float64)
+    tmpl = R.fc_edge_index(N)
+    if drop_edges:
+        keep = R.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(seed).random_sample(N * (N - 1) // 2))
+        tmpl = R.apply_edge_dropout(tmpl, keep)
+    ei = R.batched_edge_index(tmpl, Gn, N)
+    gen = torch.Generator().manual_seed(seed + 2)
+    e = torch.relu(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64))
+    out_o, en_o = R.layer_forward(params, x, ei, e)
+    m = make_layer(D, params)
+    m.precision = "fp32"
+    with torch.no_grad():
+        out, en = m(x.float().to(dev()), ei.to(dev()), e.float().to(dev()))
+    assert out.dtype == torch.float32
+    assert rel(out, out_o) < TOL_FP32 and rel(en, en_o) < TOL_FP32, (rel(out, out_o), rel(en, en_o))
+    with pytest.raises(NotImplementedError):
+        m(x.float().to(dev()).requires_grad_(True), ei.to(dev()), e.float().to(dev()))
+    m.precision = "bf16"
+    with torch.no_grad():
+        out_b, _ = m(x.float().to(dev()), ei.to(dev()), e.float().to(dev()))
+    assert rel(out_b, out_o) > 10 * rel(out, out_o)          # the fp32 mode really is a different, tighter arithmetic
+
+
+def test_fp32_mode_layer_against_reference_fixture():
+    fx = np.load(os.path.join(GOLD, "layer_D512_N8_G2.npz"))
+    D, N, Gn, seed = [int(v) for v in fx["meta"]]
+    case = R.synth_layer_case(D, N, Gn, seed)
+    m = make_layer(D, case["params"])
+    m.precision = "fp32"
+    with torch.no_grad():
+        out, en = m(case["x"].float().to(dev()), case["edge_index"].to(dev()), case["e"].float().to(dev()))
+    assert rel(out, fx["out_f64"]) < TOL_FP32 and rel(en, fx["e_new_f64"]) < TOL_FP32
+    assert rel(out, fx["out_f32"]) < TOL_FP32                 # the reference's own fp32 CPU run
+
+
+@pytest.mark.parametrize("droprate", [0.0, 0.5])
+def test_fp32_mode_stack_against_oracle(droprate):
+    """BASELINE config-B shape in miniature: the whole GNN stack in fp32 mode, poses within 1e-4."""
+    D, N, Gn = 512, 9, 6
+    case = R.synth_stack_case(D, N, Gn, 6100, droprate=droprate, edge_dropout=False)
+    model = rpg.RelPoseGNN(D, D, D, droprate=droprate).to(dev())
+    model.load_state_dict({k: v.float() for k, v in case["params"].items()}, strict=False)
+    model.precision = "fp32"
+    kx = case["keep_x"].to(dev()) if droprate > 0 else None
+    ke = case["keep_e"].to(dev()) if droprate > 0 else None
+    with torch.no_grad():
+        pn, pe, _ = model(case["x"].float().to(dev()), case["edge_index"].to(dev()), keep_x=kx, keep_e=ke)
+    pn_o, pe_o, _, _ = R.stack_forward(case["params"], case["x"], case["edge_index"], 2, droprate, case["keep_x"], case["keep_e"])
+    assert rel(pn, pn_o) < TOL_FP32 and rel(pe, pe_o) < TOL_FP32, (rel(pn, pn_o), rel(pe, pe_o))
