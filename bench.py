@@ -39,6 +39,15 @@ def algorithmic_flops_per_graph(D, N, E, R=R_ROUNDS, train=True):
     return fwd * (3 if train else 1)
 
 
+def load_traffic():
+    """DRAM bytes per gemm_tc_kernel launch from the committed ncu launch list (profiles/, tools/summarize_launches.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -267,7 +276,9 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<NT|TN> (tcgen05)",
                          "achieved": alg_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": alg_flops / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None,
+                         "frac": alg_flops / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                         "traffic": (load_traffic() or {}).get("dram_bytes_per_launch") if args.workload == "train_4096x9" else None,
+                         "traffic_source": "profiles/r1_gemm_traffic.json (ncu dram__bytes_read+write per launch, train_4096x9)",
                          "peak_source": peaks["source"] + ", sustained bf16",
                          "algorithmic_flops_per_launch": alg_flops / max(nt_n.value + tn_n.value, 1),
                          "avg_launch_ms": gemm_ms / max(nt_n.value + tn_n.value, 1),
