@@ -188,7 +188,7 @@ def run_ours(args):
     x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
     mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
     masks = [edge_dropout_keep(H, mask_rng) if train else np.ones(H, bool)
-             for _ in range(2 * args.trials * args.steps + max(args.warmup, 3) + 8)]
+             for _ in range(2 * args.trials * args.steps + max(args.warmup, 3) + 16)]
     mask_iter = iter(masks)
 
     def step(x, poses, read_back):
@@ -227,7 +227,10 @@ def run_ours(args):
             dist.barrier()
         return ms.item() / n_steps
 
-    for _ in range(max(args.warmup, 3)):
+    # untimed warm-up: first two steps with the full template (largest activation arenas, so the caching allocator
+    # holds blocks big enough for every later edge-dropout mask), then W steps of the real mask sequence
+    mask_iter = iter([np.ones(H, bool)] * 2 + masks)
+    for _ in range(2 + max(args.warmup, 3)):
         step(x_dev, poses_dev, False)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
@@ -302,7 +305,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--trials", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_4096x9", choices=sorted(WORKLOADS))

@@ -83,7 +83,18 @@ typedef struct {
   const int32_t* min_idx;     /* [Ep]                                                             */
   const int32_t* max_ptr;     /* [N+1] CSR over max(src,dst)                                      */
   const int32_t* max_idx;     /* [Ep]                                                             */
+  /* optional one-hot selection patterns for the K-panel gathers (NULL => gathers run in the epilogue):
+   * [sel_patterns * 128, 64] bf16 each, see rpg_gemm_t.gsel                                          */
+  const rpg_bf16* sel_src;
+  const rpg_bf16* sel_dst;
+  int sel_patterns, sel_div;
 } rpg_graph_t;
+
+/* Builds the one-hot selection tiles of rpg_graph_t.sel_src / sel_dst on the device from a template endpoint table
+ * (src or dst): sel [patterns * 128, 64] bf16, div = gcd(128, Ep), patterns = Ep / div.  The caller checks first
+ * that no 128-row block references more than 64 node rows.                                             */
+int rpg_selection_patterns(const int32_t* endpoint, int Ep, int N, int div, int patterns, rpg_bf16* sel,
+                           rpg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Generic tcgen05 GEMM with fused epilogue (the workhorse; exposed for unit tests)
@@ -133,6 +144,17 @@ typedef struct {
   const rpg_bf16* resid_lo;   /* low plane of resid (pitch resid_ld) or NULL                          */
   rpg_bf16* out_lo;           /* low plane of out: bf16(v - float(bf16(v))) (pitch ldo) or NULL        */
   rpg_bf16* out_relu_lo;      /* low plane of out_relu or NULL                                        */
+  /* Gathered node adds as one-hot K panels (preferred over gadd): for each of n_gseg (0..2) operands one extra
+   * 64-wide k-block is multiplied, A = the 128 x 64 one-hot selection tile of the row block -- which for a batch of
+   * identical graph templates depends only on (row0 mod Ep), so gsel holds gsel_patterns tiles, pattern index
+   * ((row0 % Ep) / gsel_div) -- and B = rows [(row0 / Ep) * Nn, +64) of gsrc [gsrc_rows, >= N] (pitch gsrc_ld),
+   * loaded MN-major.  Exact: 1.0 * bf16 accumulates in fp32.  The epilogue stays the plain one.        */
+  int n_gseg;
+  const rpg_bf16* gsel[2];
+  int gsel_patterns, gsel_div;
+  const rpg_bf16* gsrc[2];
+  int gsrc_ld[2];
+  int gsrc_rows;
 } rpg_gemm_t;
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream);
@@ -201,7 +223,8 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
 /* Feature dropout + pose heads, posenet.py:1073-1086: pose[r, 0:3] = fc_xyz(drop(f[r])), [3:6] = fc_wpqr(..).
  * Dropout follows F.dropout (kept entries scaled by 1/(1-p)).  The keep decision is either an explicit
  * uint8 [rows, D] mask `keep` (parity tests: ATen's Philox stream cannot be reproduced) or, when keep is
- * NULL and p_drop > 0, a counter-based hash of (seed, row, col) evaluated in-kernel (no mask traffic);
+ * NULL and p_drop > 0, a counter-based hash of (seed, row, col / 4) evaluated in-kernel, 8 bits per element,
+ * i.e. the drop probability is quantised to multiples of 1/256 (no mask traffic);
  * rpg_dropout_mask materialises that same decision so an oracle can consume it.                      */
 int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream);
 int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo /* fp32 mode: low plane, else NULL */, int ldf,

@@ -25,7 +25,8 @@ class RpgError(RuntimeError):
 class Graph(C.Structure):
     _fields_ = [("G", I), ("N", I), ("Ep", I),
                 ("src", P), ("dst", P), ("in_ptr", P), ("in_idx", P), ("out_ptr", P), ("out_idx", P),
-                ("inv_deg", P), ("deg", P), ("min_ptr", P), ("min_idx", P), ("max_ptr", P), ("max_idx", P)]
+                ("inv_deg", P), ("deg", P), ("min_ptr", P), ("min_idx", P), ("max_ptr", P), ("max_idx", P),
+                ("sel_src", P), ("sel_dst", P), ("sel_patterns", I), ("sel_div", I)]
 
 
 class Gemm(C.Structure):
@@ -37,7 +38,9 @@ class Gemm(C.Structure):
                 ("mask", P), ("mask_ld", I), ("relu", I),
                 ("out", P), ("out_relu", P), ("ldo", I), ("out_f32", P), ("ldo_f32", I),
                 ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I),
-                ("gadd_f32", P * 2), ("gadd_f32_ld", I * 2), ("resid_lo", P), ("out_lo", P), ("out_relu_lo", P)]
+                ("gadd_f32", P * 2), ("gadd_f32_ld", I * 2), ("resid_lo", P), ("out_lo", P), ("out_relu_lo", P),
+                ("n_gseg", I), ("gsel", P * 2), ("gsel_patterns", I), ("gsel_div", I), ("gsrc", P * 2), ("gsrc_ld", I * 2),
+                ("gsrc_rows", I)]
 
 
 class LayerWeights(C.Structure):
@@ -85,6 +88,7 @@ SIGNATURES = {
     "rpg_profile_end": (I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I), C.POINTER(I),
                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rpg_validate_edge_index": (I, [P, I64, I, I, I, P, P, P, P]),
+    "rpg_selection_patterns": (I, [P, I, I, I, I, P, P]),
     "rpg_gemm": (I, [C.POINTER(Gemm), P]),
     "rpg_set_gemm_cluster": (I, [I]),
     "rpg_wgrad": (I, [P, I, I, P, I, I, I64, P, P, I, P]),

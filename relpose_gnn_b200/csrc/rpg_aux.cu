@@ -47,6 +47,25 @@ __global__ void validate_edge_index_kernel(const long long* __restrict__ ei, lon
     if (local_bad) atomicAdd(bad, local_bad);   // integer atomic: result is order-independent
 }
 
+// One-hot selection tiles for the K-panel gathers (rpg_gemm_t.gsel): tile p, row i selects node column
+// ((p*g+i) / Ep) * N + endpoint[(p*g+i) % Ep].  One thread per (tile row, 8 columns).
+__global__ void selection_patterns_kernel(const int* __restrict__ endpoint, int Ep, int N, int g, int npat,
+                                          bf16* __restrict__ sel) {
+    const int total = npat * 128 * 8;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int row = t >> 3, c8 = (t & 7) << 3;
+        const int p = row >> 7, i = row & 127;
+        const int le = p * g + i;
+        const int col = (le / Ep) * N + __ldg(endpoint + le % Ep);
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (col >= c8 && col < c8 + 8) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+            w[(col - c8) >> 1] = ((col - c8) & 1) ? 0x3F800000u : 0x00003F80u;     // bf16 1.0 = 0x3F80
+        }
+        *reinterpret_cast<uint4*>(sel + (size_t)row * 64 + c8) = u;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // weights / casts
 // ------------------------------------------------------------------------------------------------
@@ -408,10 +427,13 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {   // lowbias32 finaliser
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
-__device__ __forceinline__ bool keep_from_seed(unsigned long long seed, long long row, int col, uint32_t thresh) {
-    const uint32_t h = mix32(mix32((uint32_t)seed ^ (uint32_t)(row * 0x9E3779B1ull)) ^ (uint32_t)(seed >> 32) ^
-                             (uint32_t)col * 0x85EBCA77u ^ (uint32_t)(row >> 32));
-    return h >= thresh;        // P(drop) = thresh / 2^32
+// One 32-bit hash serves 4 consecutive columns (8 bits each): keep iff byte >= thresh8, P(drop) = thresh8 / 256.
+__device__ __forceinline__ uint32_t keep_hash4(unsigned long long seed, long long row, int col4) {
+    return mix32(mix32((uint32_t)seed ^ (uint32_t)(row * 0x9E3779B1ull)) ^ (uint32_t)(seed >> 32) ^
+                 (uint32_t)col4 * 0x85EBCA77u ^ (uint32_t)(row >> 32));
+}
+__device__ __forceinline__ bool keep_from_hash(uint32_t h, int q, uint32_t thresh8) {
+    return ((h >> (8 * (q & 3))) & 0xFFu) >= thresh8;
 }
 
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long rows, int D,
@@ -419,7 +441,8 @@ __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, lo
     const long long total = rows * D;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D;
-        keep[i] = keep_from_seed(seed, r, (int)(i - r * D), thresh) ? 1 : 0;
+        const int c = (int)(i - r * D);
+        keep[i] = keep_from_hash(keep_hash4(seed, r, c >> 2), c, thresh) ? 1 : 0;
     }
 }
 
@@ -450,8 +473,9 @@ head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, c
 #pragma unroll
                 for (int q = 0; q < 8; ++q) f[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? f[q] * scale : 0.f;
             } else if (use_seed) {
+                const uint32_t h0 = keep_hash4(seed, row, c >> 2), h1 = keep_hash4(seed, row, (c >> 2) + 1);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = keep_from_seed(seed, row, c + q, thresh) ? f[q] * scale : 0.f;
+                for (int q = 0; q < 8; ++q) f[q] = keep_from_hash(q < 4 ? h0 : h1, q, thresh) ? f[q] * scale : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
@@ -477,7 +501,7 @@ head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, c
 
 // Backward of the head.  Thread owns 8 columns; a block walks a contiguous row range, accumulating
 // dW6[j, c] = sum_r dpose[r, j] * drop(feat)[r, c] in registers (deterministic), partials per block.
-constexpr int HEADB_ROWS_PER_BLOCK = 256;
+constexpr int HEADB_ROWS_PER_BLOCK = 64;     // short slabs => enough blocks to fill the machine; partials are reduced afterwards
 __global__ void head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, int ldf, long long rows,
                                 int D, const uint8_t* __restrict__ keep, unsigned long long seed, uint32_t thresh,
                                 int use_seed, float scale, const float* __restrict__ w6, int mask_relu,
@@ -514,8 +538,9 @@ __global__ void head_bwd_kernel(const float* __restrict__ dpose, const bf16* __r
 #pragma unroll
             for (int q = 0; q < 8; ++q) km[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? scale : 0.f;
         } else if (use_seed) {
+            const uint32_t h0 = keep_hash4(seed, row, c >> 2), h1 = keep_hash4(seed, row, (c >> 2) + 1);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) km[q] = keep_from_seed(seed, row, c + q, thresh) ? scale : 0.f;
+            for (int q = 0; q < 8; ++q) km[q] = keep_from_hash(q < 4 ? h0 : h1, q, thresh) ? scale : 0.f;
         } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q) km[q] = 1.f;
@@ -695,6 +720,13 @@ int rpg_validate_edge_index(const int64_t* edge_index, int64_t Et, int G, int N,
     return check_launch("validate_edge_index_kernel");
 }
 
+int rpg_selection_patterns(const int32_t* endpoint, int Ep, int N, int div, int patterns, rpg_bf16* sel, rpg_stream_t stream) {
+    if (!endpoint || !sel || Ep <= 0 || N <= 0 || div <= 0 || patterns <= 0) return set_error(RPG_E_ARG, "selection_patterns: bad arguments");
+    selection_patterns_kernel<<<grid_for((long long)patterns * 128 * 8, 256), 256, 0, as_stream(stream)>>>(
+        endpoint, Ep, N, div, patterns, reinterpret_cast<bf16*>(sel));
+    return check_launch("selection_patterns_kernel");
+}
+
 int rpg_pack_weight(const float* src, int ld_src, int r0, int c0, int rows, int cols, rpg_bf16* dst, int ld_dst,
                     int transpose, rpg_stream_t stream) {
     if (!src || !dst || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "pack_weight: bad arguments");
@@ -818,7 +850,7 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
 
 int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream) {
     if (!keep || rows <= 0 || D <= 0 || p_drop < 0.f || p_drop >= 1.f) return set_error(RPG_E_ARG, "dropout_mask: bad arguments");
-    const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
+    const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
     dropout_mask_kernel<<<grid_for(rows * D, 256), 256, 0, as_stream(stream)>>>(seed, thresh, rows, D, keep);
     return check_launch("dropout_mask_kernel");
 }
@@ -836,7 +868,7 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
     }
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
     const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
-    const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
+    const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
     head_fwd_kernel<<<grid_for(rows, HEAD_WARPS, 148 * 8), HEAD_WARPS * 32, smem, as_stream(stream)>>>(
         reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose,
         reinterpret_cast<const bf16*>(feat_lo));
@@ -858,7 +890,7 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     float* db_part = ws + (size_t)blocks * 6 * D;
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
     const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
-    const uint32_t thresh = (uint32_t)((double)p_drop * 4294967296.0);
+    const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
     const int threads = ((D / 8 + 31) / 32) * 32;
     cudaStream_t s = as_stream(stream);
     head_bwd_kernel<<<blocks, threads, 0, s>>>(dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh,

@@ -72,12 +72,18 @@ struct GemmKParams {
     const __nv_bfloat16* resid_lo; // low plane of resid
     __nv_bfloat16* out_lo;         // low plane of out:      bf16(v - float(bf16(v)))
     __nv_bfloat16* out_relu_lo;    // low plane of out_relu
+    // gathered node adds as one-hot K panels (one extra 64-wide k-block each): A = selection pattern of this row block,
+    // B = the node rows of the gathered matrix (MN-major)
+    int n_gseg;                    // 0..2
+    int gsel_div;                  // pattern index of row block = ((m_blk * 128) % Ep) / gsel_div
 };
 
 struct GemmTmaps {
     CUtensorMap a[6];              // A segments (NT) / a[0] = A (TN)
     CUtensorMap b;
     CUtensorMap out, out_relu, out_f32, out_lo, out_relu_lo;
+    CUtensorMap ga[2];             // one-hot selection patterns [npat * 128, 64] (K-major A tiles)
+    CUtensorMap gb[2];             // gathered matrix [rows, N] (MN-major B tiles: 64 rows x 64 columns per box)
 };
 
 __device__ __forceinline__ void add_bf16x8(float* f, const uint4& u) {
@@ -179,6 +185,20 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
+                    // one-hot K panels: selection pattern (A) + the node rows this row block can reference (B, MN-major).
+                    // The two CTAs of a cluster own different row blocks => different node windows: no multicast here.
+                    for (int gs = 0; gs < p.n_gseg; ++gs) {
+                        const int r0 = m_blk * BLOCK_M;
+                        const int pat = (r0 % p.Ep) / p.gsel_div;
+                        const int win = (r0 / p.Ep) * p.Nn;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
+                        tma_load_2d(&tm.ga[gs], &full_bar[stage], smem_a + stage * A_STAGE_BYTES, 0, pat * BLOCK_M);
+                        for (int j = 0; j < p.block_n / 64; ++j)
+                            tma_load_2d(&tm.gb[gs], &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
+                                        n_blk * p.block_n + j * 64, win);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                 } else {
                     const int split = item % p.splits;
                     const int kb0 = split * p.kb_per_split;
@@ -219,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                 const uint32_t acc_phase = (it >> 1) & 1;
                 int n_kb;
                 if (MODE == 0) {
-                    n_kb = p.total_kb;
+                    n_kb = p.total_kb + p.n_gseg;
                 } else {
                     const int kb0 = (item % p.splits) * p.kb_per_split;
                     n_kb = min(kb0 + p.kb_per_split, p.total_kb) - kb0;
@@ -231,10 +251,19 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), lbo, sbo);
-                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), lbo, sbo);
+                    if (MODE == 0 && kb >= n_kb - p.n_gseg) {
+                        // one-hot panel: A K-major (selection), B MN-major (node rows): only the B side changes layout
+                        const uint64_t bg_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), 8192u, 1024u);
+                        const uint32_t idesc_g = make_idesc_bf16(BLOCK_M, p.block_n, 0, 1);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(d_tmem, a_desc + k * k_step, bg_desc + k * ((UMMA_K * 128) >> 4), idesc_g, (kb | k) != 0);
+                    } else {
+                        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), lbo, sbo);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
+                    }
                     if (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                     else umma_commit_mc(&empty_bar[stage], kAllCtas);   // ... in every CTA that multicasts into it
                     if (kb == n_kb - 1) umma_commit(&acc_full[acc]);
@@ -616,8 +645,8 @@ int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches
         cudaEventElapsedTime(&t, r.e0, r.e1);
         ms[r.mode] += t; fl[r.mode] += r.flops; n[r.mode]++;
         if (getenv("RPG_PROFILE_VERBOSE"))
-            fprintf(stderr, "[rpg gemm] %s M=%d N=%d K=%d flags=%s%s%s%s%s%s%s%s  %.1f us  %.0f TFLOP/s\n", r.mode ? "TN" : "NT", r.M, r.N,
-                    r.K, r.flags & 1 ? "bias " : "", r.flags & 2 ? "gadd0 " : "", r.flags & 4 ? "gadd1 " : "",
+            fprintf(stderr, "[rpg gemm] %s M=%d N=%d K=%d flags=%s%s%s%s%s%s%s%s%s  %.1f us  %.0f TFLOP/s\n", r.mode ? "TN" : "NT", r.M, r.N,
+                    r.K, (r.flags >> 8) ? "onehot-gather " : "", r.flags & 1 ? "bias " : "", r.flags & 2 ? "gadd0 " : "", r.flags & 4 ? "gadd1 " : "",
                     r.flags & 8 ? "resid " : "", r.flags & 16 ? "mask " : "", r.flags & 32 ? "out " : "",
                     r.flags & 64 ? "out_relu " : "", r.flags & 128 ? "out_f32 " : "", t * 1e3, r.flops / (t * 1e-3) / 1e12);
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
@@ -725,6 +754,18 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if ((p.out && !aligned16(p.out)) || (p.out_relu && !aligned16(p.out_relu)) || (p.out_f32 && !aligned16(p.out_f32)))
         return set_error(RPG_E_ARG, "rpg_gemm: output pointers must be 16-byte aligned");
     // result tiles leave through TMA stores: 32 rows x 64 bf16 (or 32 fp32) columns per box, clipped at the tensor edge
+    if (g->n_gseg) {
+        if (g->mode != 0 || g->n_gseg < 0 || g->n_gseg > 2 || block_n % 64 || g->Ep <= 0 || g->Nn <= 0 || g->gsel_div <= 0 ||
+            g->gsel_patterns <= 0 || g->gsrc_rows <= 0)
+            return set_error(RPG_E_ARG, "rpg_gemm: one-hot gather panels need NT mode, block_n % 64 == 0, Ep, Nn, gsel_div, patterns");
+        for (int i = 0; i < g->n_gseg; ++i) {
+            if (!g->gsel[i] || !g->gsrc[i] || !aligned16(g->gsel[i]) || !aligned16(g->gsrc[i]) || g->gsrc_ld[i] % 8)
+                return set_error(RPG_E_ARG, "rpg_gemm: one-hot gather panel pointers / pitch");
+            if ((rc = make_tmap(&tmaps.ga[i], g->gsel[i], BLOCK_K, (uint64_t)g->gsel_patterns * BLOCK_M, BLOCK_K, BLOCK_K, BLOCK_M))) return rc;
+            if ((rc = make_tmap(&tmaps.gb[i], g->gsrc[i], g->N, g->gsrc_rows, g->gsrc_ld[i], 64, BLOCK_K))) return rc;
+        }
+        p.n_gseg = g->n_gseg; p.gsel_div = g->gsel_div; p.Ep = g->Ep; p.Nn = g->Nn;
+    }
     for (int i = 0; i < 2; ++i) { p.gadd_f32[i] = g->gadd_f32[i]; p.gadd_f32_ld[i] = g->gadd_f32_ld[i]; }
     p.resid_lo = reinterpret_cast<const __nv_bfloat16*>(g->resid_lo);
     p.out_lo = reinterpret_cast<__nv_bfloat16*>(g->out_lo);
@@ -769,10 +810,10 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (prof) {
         cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
         rec.mode = g->mode;
-        rec.flops = 2.0 * p.M * p.N * (g->mode == 0 ? (double)p.total_kb * BLOCK_K : (double)g->R);
-        rec.M = p.M; rec.N = p.N; rec.K = g->mode == 0 ? p.total_kb * BLOCK_K : g->R;
+        rec.flops = 2.0 * p.M * p.N * (g->mode == 0 ? (double)(p.total_kb + p.n_gseg) * BLOCK_K : (double)g->R);
+        rec.M = p.M; rec.N = p.N; rec.K = g->mode == 0 ? (p.total_kb + p.n_gseg) * BLOCK_K : g->R;
         rec.flags = (p.bias ? 1 : 0) | (p.gadd[0] ? 2 : 0) | (p.gadd[1] ? 4 : 0) | (p.resid ? 8 : 0) | (p.mask ? 16 : 0) |
-                    (p.out ? 32 : 0) | (p.out_relu ? 64 : 0) | (p.out_f32 ? 128 : 0);
+                    (p.out ? 32 : 0) | (p.out_relu ? 64 : 0) | (p.out_f32 ? 128 : 0) | (p.n_gseg << 8);
         cudaEventRecord(rec.e0, stream);
     }
     const bool ops = g->mode == 0 && (p.gadd[0] || p.gadd[1] || p.resid || p.mask);

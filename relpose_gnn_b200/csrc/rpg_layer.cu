@@ -159,8 +159,14 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // (2) edge MLP layer 1 (my_gnn_layer.py:232,237-238): h1 = relu(e W1e_e^T + P_s[src] + P_d[dst] + b)
     g = nt((int)Et, D, t->e, D, D, w->W1e_e, D);
     g.bias = w->b1e;
-    g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
-    g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = 3 * D;
+    if (gr->sel_src && gr->sel_dst) {            // gathers as one-hot K panels (plain epilogue)
+        g.n_gseg = 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
+        g.gsel[0] = gr->sel_src; g.gsrc[0] = t->P;     g.gsrc_ld[0] = 3 * D;
+        g.gsel[1] = gr->sel_dst; g.gsrc[1] = t->P + D; g.gsrc_ld[1] = 3 * D;
+    } else {
+        g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
+        g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = 3 * D;
+    }
     g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
     g.out = t->h1; g.ldo = D; g.out_bits = t->h1_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
@@ -174,7 +180,12 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // (4) message MLP layer 1 (my_gnn_layer.py:280,305): h2 = relu(e' W1m_e^T + P_m[src] + b)   (x_j = source)
     g = nt((int)Et, D, t->e_new, D, D, w->W1m_e, D);
     g.bias = w->b1m;
-    g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
+    if (gr->sel_src) {
+        g.n_gseg = 1; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
+        g.gsel[0] = gr->sel_src; g.gsrc[0] = t->P + 2 * D; g.gsrc_ld[0] = 3 * D;
+    } else {
+        g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
+    }
     g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
     g.out = t->h2; g.ldo = D; g.out_bits = t->h2_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
@@ -326,7 +337,13 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, stream));
         // dm = dgtp Wgtp + dan[dst]
         g = nt((int)Et, D, b->dgtp, c3p, c3p, w->WgtpT, c3p);
-        g.gadd[0] = b->dan; g.gmap[0] = gr->dst; g.gadd_ld[0] = D; g.Ep = gr->Ep; g.Nn = gr->N;
+        g.Ep = gr->Ep; g.Nn = gr->N;
+        if (gr->sel_dst) {
+            g.n_gseg = 1; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
+            g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->dan; g.gsrc_ld[0] = D;
+        } else {
+            g.gadd[0] = b->dan; g.gmap[0] = gr->dst; g.gadd_ld[0] = D;
+        }
         g.out = b->dm; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
         // dh2 = (dm W2m) * [h2 > 0]

@@ -81,16 +81,24 @@ class GraphBatch:
         tables = GraphBatch._table_cache.get(key)
         if tables is None:
             tables = self._build_tables(src, dst, self.N, self.device)
+            if len(GraphBatch._table_cache) >= 128:                 # a new dropout mask every step: keep the cache bounded
+                GraphBatch._table_cache.pop(next(iter(GraphBatch._table_cache)))
             GraphBatch._table_cache[key] = tables
         self._tables = tables
         s = _lib.Graph()
         s.G, s.N, s.Ep = self.G, self.N, self.Ep
         for name, t in tables.items():
+            if name in ("sel_src", "sel_dst", "_buf"):
+                continue
             setattr(s, name, t.data_ptr())
+        if "sel_src" in tables:
+            s.sel_src, s.sel_dst = tables["sel_src"].data_ptr(), tables["sel_dst"].data_ptr()
+            s.sel_patterns, s.sel_div = tables["sel_src"].size(0) // 128, int(np.gcd(128, self.Ep))
         self.struct = s
 
     @staticmethod
     def _build_tables(src, dst, n, device):
+        """All template tables in ONE host buffer / one upload (a training loop sees a new dropout mask every step)."""
         in_ptr, in_idx = _csr(dst, n)
         out_ptr, out_idx = _csr(src, n)
         min_ptr, min_idx = _csr(np.minimum(src, dst), n)
@@ -99,7 +107,35 @@ class GraphBatch:
         host = {"src": src, "dst": dst, "in_ptr": in_ptr, "in_idx": in_idx, "out_ptr": out_ptr,
                 "out_idx": out_idx, "inv_deg": (1.0 / np.maximum(deg, 1.0)).astype(np.float32), "deg": deg,
                 "min_ptr": min_ptr, "min_idx": min_idx, "max_ptr": max_ptr, "max_idx": max_idx}
-        return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in host.items()}
+        offs, total = {}, 0
+        for k, v in host.items():
+            offs[k] = total
+            total += (v.size + 3) // 4 * 4                          # keep every table 16-byte aligned
+        packed = np.zeros(total, np.int32)
+        for k, v in host.items():
+            packed[offs[k]:offs[k] + v.size] = np.ascontiguousarray(v).view(np.int32)
+        dev_buf = torch.from_numpy(packed).to(device)
+        out = {}
+        for k, v in host.items():
+            t = dev_buf[offs[k]:offs[k] + v.size]
+            out[k] = t.view(torch.float32) if v.dtype == np.float32 else t
+        out["_buf"] = dev_buf
+        # one-hot selection tiles for the K-panel gathers (rpg_gemm_t.gsel), generated on the device.  A 128-row block
+        # starting at local edge offset o (a multiple of gcd(128, Ep)) touches graphs 0 .. (o+127)//Ep of its window;
+        # the panel holds 64 node rows, so every referenced node column must stay below 64.
+        Ep = src.size
+        g = int(np.gcd(128, Ep))
+        npat = Ep // g
+        worst = ((Ep - g + 127) // Ep) * n + n                      # upper bound of (graph index) * N + node + 1
+        if worst <= 64 and torch.device(device).type == "cuda":
+            lib = _lib.load()
+            stream = torch.cuda.current_stream(device).cuda_stream
+            for name, tab in (("sel_src", "src"), ("sel_dst", "dst")):
+                sel = torch.empty(npat * 128, 64, dtype=torch.bfloat16, device=device)
+                _lib.check(lib.rpg_selection_patterns(out[tab].data_ptr(), Ep, n, g, npat, sel.data_ptr(), stream),
+                           "rpg_selection_patterns")
+                out[name] = sel
+        return out
 
     @property
     def n_node_rows(self):

@@ -58,7 +58,8 @@ def _require_cuda(*ts):
 
 
 def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, row_scale=None, mask=None,
-            relu=False, out=None, out_relu=None, out_f32=None, graph=None, block_n=0, mask_bits=None, out_bits=None):
+            relu=False, out=None, out_relu=None, out_f32=None, graph=None, block_n=0, mask_bits=None, out_bits=None,
+            gpanel=()):
     """C = epilogue(sum_s A_s @ B^T).  A: bf16 [M, K] (or `segs`: list of up to 3 such tensors concatenated along
     K); B: bf16 [N, sum K].  Row pitches are taken from stride(0), so column-sliced views are fine.
     gadd: up to two (tensor [rows, >=N] bf16, 'src'|'dst') pairs added through the graph template."""
@@ -100,6 +101,15 @@ def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, 
     g.out, g.out_relu, g.ldo = ptr(out), ptr(out_relu), ldo or 0
     if out_f32 is not None:
         g.out_f32, g.ldo_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    for i, (t, which) in enumerate(gpanel):        # gathered adds as one-hot K panels (needs graph selection patterns)
+        sel = getattr(graph.struct, "sel_" + which)
+        if not sel:
+            raise ValueError("this graph template has no selection patterns (row blocks reference > 64 nodes)")
+        g.gsel[i], g.gsrc[i], g.gsrc_ld[i] = sel, t.data_ptr(), t.stride(0)
+    if gpanel:
+        g.n_gseg = len(gpanel)
+        g.gsel_patterns, g.gsel_div = graph.struct.sel_patterns, graph.struct.sel_div
+        g.gsrc_rows, g.Ep, g.Nn = graph.n_node_rows, graph.Ep, graph.N
     if mask_bits is not None:
         g.mask_bits, g.mask_bits_ld = mask_bits.data_ptr(), mask_bits.stride(0)
     if out_bits is not None:

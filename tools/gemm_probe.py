@@ -66,6 +66,19 @@ def nt_cases():
     out2 = torch.empty(M, N, dtype=BF, device=dev)
     ops.gemm_nt(None, B, segs=[A0, A1, A2], bias=bias, relu=True, out=out2)
     ok &= report("NT relu", out2, (torch.cat([A0, A1, A2], 1).float() @ B.float().t() + bias).clamp(min=0), 1e-2)
+    # gathered adds as one-hot K panels == the epilogue gather path
+    for (Gn, Nn, keepmask) in [(5, 9, None), (40, 9, np.array([1, 0, 1, 1, 0, 0, 1, 0, 1, 0] * 3 + [1] * 6, bool)), (3, 17, None)]:
+        gg = GraphBatch.fully_connected(Gn, Nn, dev, keepmask)
+        Mg = gg.n_edge_rows
+        Ag = rnd(Mg, 128)
+        Bg = rnd(256, 128, scale=0.1)
+        Pg = rnd(gg.n_node_rows, 512)
+        refg = Ag.float() @ Bg.float().t() + bias
+        eig = gg.edge_index()
+        refg = (refg + Pg[:, :256].float()[eig[0]] + Pg[:, 256:].float()[eig[1]]).clamp(min=0)
+        o1 = torch.empty(Mg, 256, dtype=BF, device=dev)
+        ops.gemm_nt(Ag, Bg, bias=bias, gpanel=[(Pg[:, :256], "src"), (Pg[:, 256:], "dst")], graph=gg, relu=True, out=o1)
+        ok &= report(f"NT one-hot gather panels G={Gn} N={Nn} Ep={gg.Ep}", o1, refg, 1e-2)
     # bit patterns: out_bits == packbits(out > 0); mask_bits has the same effect as the bf16 mask
     M2, N2 = 72 * 5, 256
     bits = torch.zeros(M2, N2 // 8, dtype=torch.uint8, device=dev)
