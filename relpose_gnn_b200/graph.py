@@ -54,6 +54,38 @@ def batched_edge_index(src, dst, n_graphs, n_nodes, device=None):
     return (t.unsqueeze(1) + offs.view(1, -1, 1)).reshape(2, -1).contiguous()
 
 
+class _PinnedUploader:
+    """Asynchronous host->device upload of small int32 tables: a ring of pinned staging buffers, each guarded by a
+    CUDA event, so that building a new template every step (edge dropout) never issues a pageable -- i.e. stream-
+    synchronising -- copy."""
+
+    def __init__(self, slots=32, capacity=8192):
+        self.slots, self.capacity, self.next = slots, capacity, 0
+        self.bufs, self.events = [], []
+
+    def upload(self, packed_np, device):
+        n = packed_np.size
+        if n > self.capacity or not torch.cuda.is_available() or torch.device(device).type != "cuda":
+            return torch.from_numpy(packed_np).to(device)
+        if not self.bufs:
+            self.bufs = [torch.empty(self.capacity, dtype=torch.int32).pin_memory() for _ in range(self.slots)]
+            self.events = [None] * self.slots
+        i = self.next
+        self.next = (i + 1) % self.slots
+        if self.events[i] is not None:
+            self.events[i].synchronize()                # the previous copy out of this slot has completed
+        self.bufs[i][:n].copy_(torch.from_numpy(packed_np))
+        dev = torch.empty(n, dtype=torch.int32, device=device)
+        dev.copy_(self.bufs[i][:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+        return dev
+
+
+_uploader = _PinnedUploader()
+
+
 def _csr(keys, n):
     order = np.argsort(keys, kind="stable").astype(np.int32)
     counts = np.bincount(keys, minlength=n)
@@ -81,7 +113,8 @@ class GraphBatch:
         tables = GraphBatch._table_cache.get(key)
         if tables is None:
             tables = self._build_tables(src, dst, self.N, self.device)
-            if len(GraphBatch._table_cache) >= 128:                 # a new dropout mask every step: keep the cache bounded
+            if len(GraphBatch._table_cache) >= 8:                   # a new dropout mask every step: keep the cache small so
+                                                                    # that its buffers recycle inside the caching allocator
                 GraphBatch._table_cache.pop(next(iter(GraphBatch._table_cache)))
             GraphBatch._table_cache[key] = tables
         self._tables = tables
@@ -114,7 +147,7 @@ class GraphBatch:
         packed = np.zeros(total, np.int32)
         for k, v in host.items():
             packed[offs[k]:offs[k] + v.size] = np.ascontiguousarray(v).view(np.int32)
-        dev_buf = torch.from_numpy(packed).to(device)
+        dev_buf = _uploader.upload(packed, device)
         out = {}
         for k, v in host.items():
             t = dev_buf[offs[k]:offs[k] + v.size]
@@ -149,7 +182,12 @@ class GraphBatch:
         return C.byref(self.struct)
 
     def edge_index(self):
-        return batched_edge_index(self.src_np, self.dst_np, self.G, self.N, self.device)
+        """int64 [2, G*Ep] PyG-style batched edge_index, built on the device from the template tables."""
+        if self.device.type != "cuda":
+            return batched_edge_index(self.src_np, self.dst_np, self.G, self.N, self.device)
+        t = torch.stack([self._tables["src"], self._tables["dst"]]).long()
+        offs = torch.arange(self.G, dtype=torch.long, device=self.device) * self.N
+        return (t.unsqueeze(1) + offs.view(1, -1, 1)).reshape(2, -1)
 
     def with_graphs(self, n_graphs):
         return GraphBatch(self.src_np, self.dst_np, n_graphs, self.N, self.device)
