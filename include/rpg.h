@@ -155,6 +155,10 @@ typedef struct {
   const rpg_bf16* gsrc[2];
   int gsrc_ld[2];
   int gsrc_rows;
+  /* TN mode: per-split column sums of A, i.e. sum_r A[r, m] (the bias gradient when A is dY), written to
+   * a_colsum [splits, M]; accumulated from the shared-memory operand tiles by the warps that are idle during the
+   * main loop, so the gradient tensor is not read a second time.  NULL = off.                          */
+  float* a_colsum;
 } rpg_gemm_t;
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream);
@@ -166,6 +170,9 @@ int rpg_set_gemm_cluster(int ctas_per_cluster);
  * (rpg_layer_bwd_ws_floats elements) followed by the deterministic reduction below.                 */
 int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R,
               float* ws, float* out, int ldo, rpg_stream_t stream);
+/* Same, and bias[m] += sum_r A[r, m] from the same pass (bias may be NULL).                            */
+int rpg_wgrad_bias(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R,
+                   float* ws, float* out, int ldo, float* bias, rpg_stream_t stream);
 /* sizeof / offsetof probes so a foreign-language mirror of the structs can verify its layout.      */
 void rpg_struct_sizes(int32_t* out10);
 

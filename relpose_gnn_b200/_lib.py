@@ -40,7 +40,7 @@ class Gemm(C.Structure):
                 ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I),
                 ("gadd_f32", P * 2), ("gadd_f32_ld", I * 2), ("resid_lo", P), ("out_lo", P), ("out_relu_lo", P),
                 ("n_gseg", I), ("gsel", P * 2), ("gsel_patterns", I), ("gsel_div", I), ("gsrc", P * 2), ("gsrc_ld", I * 2),
-                ("gsrc_rows", I)]
+                ("gsrc_rows", I), ("a_colsum", P)]
 
 
 class LayerWeights(C.Structure):
@@ -92,6 +92,7 @@ SIGNATURES = {
     "rpg_gemm": (I, [C.POINTER(Gemm), P]),
     "rpg_set_gemm_cluster": (I, [I]),
     "rpg_wgrad": (I, [P, I, I, P, I, I, I64, P, P, I, P]),
+    "rpg_wgrad_bias": (I, [P, I, I, P, I, I, I64, P, P, I, P, P]),
     "rpg_struct_sizes": (None, [C.POINTER(C.c_int32)]),
     "rpg_reduce_splits": (I, [P, I, I64, I, I, P, I, I, P]),
     "rpg_pack_weight": (I, [P, I, I, I, I, I, P, I, I, P]),

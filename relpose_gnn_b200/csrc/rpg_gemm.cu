@@ -76,6 +76,8 @@ struct GemmKParams {
     // B = the node rows of the gathered matrix (MN-major)
     int n_gseg;                    // 0..2
     int gsel_div;                  // pattern index of row block = ((m_blk * 128) % Ep) / gsel_div
+    // TN mode: column sums of A (= bias gradient when A is dY) accumulated by the otherwise idle epilogue warps
+    float* a_colsum;               // [splits, M] partial sums, or NULL
 };
 
 struct GemmTmaps {
@@ -133,7 +135,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
+        // a stage is free when every CTA's MMAs have drained it (+ the local column-sum warps in TN mode)
+        const uint32_t empty_count = CL + ((MODE == 1 && p.a_colsum) ? EPI_WARPS : 0);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], empty_count); }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
         fence_mbar_init();
     }
@@ -289,11 +293,56 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
         uint8_t* my_row = stg + lane * 128;
         const int my_sw = lane & 7;
         int it = 0;
+        int cs_stage = 0;                          // TN column sums: this role walks the smem ring like the MMA warp
+        uint32_t cs_phase = 0;
         for (int item = worker; item < num_items; item += num_workers, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int tile = MODE == 0 ? item : item / p.splits;
             const int m_blk = (tile / num_n_blocks) * CL + cta_rank, n_blk = tile % num_n_blocks;
+            if (MODE == 1 && p.a_colsum) {
+                // While the tensor core works through this item's k-blocks the epilogue warps have nothing to do: they
+                // sum the A tile (dY^T, 64 rows x 128 columns, MN-major 128B-swizzled) over its rows.  Thread = (16-byte
+                // column chunk, row group); 4 LDS.128 + 32 FADD per stage.  Fixed order => deterministic.
+                const int kb0 = (item % p.splits) * p.kb_per_split;
+                const int n_kb = min(kb0 + p.kb_per_split, p.total_kb) - kb0;
+                const int et = threadIdx.x - 64;                 // 0..255 over the epilogue warps
+                const int c16 = et & 15, rg = et >> 4;
+                float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&full_bar[cs_stage], cs_phase);
+                    if (n_blk == 0) {
+                        const uint8_t* a_tile = smem_a + cs_stage * A_STAGE_BYTES + (c16 >> 3) * 8192;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int r = rg + 16 * j;
+                            const uint4 u = *reinterpret_cast<const uint4*>(a_tile + r * 128 + (((c16 & 7) ^ (r & 7)) << 4));
+                            cs[0] += bf16_lo(u.x); cs[1] += bf16_hi(u.x); cs[2] += bf16_lo(u.y); cs[3] += bf16_hi(u.y);
+                            cs[4] += bf16_lo(u.z); cs[5] += bf16_hi(u.z); cs[6] += bf16_lo(u.w); cs[7] += bf16_hi(u.w);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[cs_stage]);
+                    if (++cs_stage == STAGES) { cs_stage = 0; cs_phase ^= 1; }
+                }
+                if (n_blk == 0) {
+                    // fold the 16 row groups through the (idle) staging area, then one thread per column writes
+                    float* red = reinterpret_cast<float*>(smem + SMEM_RING_BYTES + SMEM_BAR_BYTES);   // [16][128]
+                    if (lane == 0) bulk_wait_read_all();                         // earlier TMA stores have left the staging area
+                    __syncwarp();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");               // previous item's readers are done
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) red[rg * 128 + c16 * 8 + q] = cs[q];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et < 128) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int g2 = 0; g2 < 16; ++g2) t += red[g2 * 128 + et];
+                        const int col = m_blk * BLOCK_M + et;
+                        if (col < p.M) p.a_colsum[(size_t)(item % p.splits) * p.M + col] = t;
+                    }
+                }
+            }
             const int row0 = m_blk * BLOCK_M + quad * 32;
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
@@ -742,6 +791,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     p.out_relu = reinterpret_cast<__nv_bfloat16*>(g->out_relu);
     p.ldo = g->ldo;
     p.out_f32 = g->out_f32; p.ldo_f32 = g->ldo_f32;
+    p.a_colsum = g->mode == 1 ? g->a_colsum : nullptr;
     p.mask_bits = g->mask_bits; p.mask_bits_ld = g->mask_bits_ld;
     p.out_bits = g->out_bits; p.out_bits_ld = g->out_bits_ld;
     if ((p.mask_bits || p.out_bits) && (g->mode != 0 || p.N % 64 || block_n % 64))

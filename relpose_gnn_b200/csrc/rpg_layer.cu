@@ -50,7 +50,7 @@ static rpg_gemm_t nt(int M, int N, const rpg_bf16* A, int K, int lda, const rpg_
 // Partial products of dW[M,N] = A[R,M]^T B[R,N] through the split-R TN kernel; returns the split count (> 0)
 // or an error (< 0 / cudaError as negative is impossible, so errors are reported through *rc).
 static int wgrad_partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* ws,
-                          int sm_count, cudaStream_t s, int* splits_out) {
+                          int sm_count, cudaStream_t s, int* splits_out, bool with_colsum = false) {
     rpg_gemm_t g;
     memset(&g, 0, sizeof g);
     g.mode = 1; g.M = M; g.N = N; g.A[0] = A; g.lda[0] = lda; g.B = B; g.ldb = ldb; g.R = (int)R;
@@ -66,17 +66,20 @@ static int wgrad_partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, 
     g.splits = (int)splits;
     g.split_stride = (long long)M * N;
     g.out_f32 = ws; g.ldo_f32 = N;
+    if (with_colsum) g.a_colsum = ws + (size_t)g.splits * M * N;       // [splits, M] right after the dW partials
     *splits_out = g.splits;
     return gemm_launch(&g, s);
 }
 
-// dW[M,N] += A^T B, deterministic (fixed split order).
+// dW[M,N] += A^T B, deterministic (fixed split order); optionally bias[M] += column sums of A from the same pass.
 static int wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* ws,
-                 float* out, int ldo, int sm_count, cudaStream_t s) {
+                 float* out, int ldo, int sm_count, cudaStream_t s, float* bias = nullptr) {
     int splits = 0;
-    int rc = wgrad_partials(A, lda, M, B, ldb, N, R, ws, sm_count, s, &splits);
+    int rc = wgrad_partials(A, lda, M, B, ldb, N, R, ws, sm_count, s, &splits, bias != nullptr);
     if (rc) return rc;
-    return rpg_reduce_splits(ws, splits, (long long)M * N, M, N, out, ldo, /*accumulate=*/1, s);
+    rc = rpg_reduce_splits(ws, splits, (long long)M * N, M, N, out, ldo, /*accumulate=*/1, s);
+    if (rc || !bias) return rc;
+    return rpg_reduce_splits(ws + (size_t)splits * M * N, splits, M, 1, M, bias, M, /*accumulate=*/1, s);
 }
 
 static int sm_count_cached() {
@@ -120,6 +123,12 @@ int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int
               rpg_stream_t stream) {
     if (!A || !B || !ws || !out) return set_error(RPG_E_ARG, "wgrad: null pointer");
     return wgrad(A, lda, M, B, ldb, N, R, ws, out, ldo, sm_count_cached(), as_stream(stream));
+}
+
+int rpg_wgrad_bias(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R, float* ws, float* out,
+                   int ldo, float* bias, rpg_stream_t stream) {
+    if (!A || !B || !ws || !out) return set_error(RPG_E_ARG, "wgrad_bias: null pointer");
+    return wgrad(A, lda, M, B, ldb, N, R, ws, out, ldo, sm_count_cached(), as_stream(stream), bias);
 }
 
 void rpg_struct_sizes(int32_t* out) {
@@ -300,8 +309,9 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
 int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt) {
     (void)Et; (void)Nt;
     // largest split workspace: (2 * sm_count / tiles + 1) splits of a [D, 3D] partial; bound with 2*148+tiles items
-    // splits * M * N <= 2 * sm_count * (128 * 256) + M * N, with M * N <= 3 D^2; sized for up to 256 SMs
-    return 2LL * 256 * 128 * 256 + 3LL * D * D;
+    // splits * M * N <= 2 * sm_count * (128 * 256) + M * N, with M * N <= 3 D^2; sized for up to 256 SMs;
+    // + [splits, M] column sums (splits <= 2 * sm_count, M <= 3 D)
+    return 2LL * 256 * 128 * 256 + 3LL * D * D + 2LL * 256 * 3 * D;
 }
 
 int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg_layer_acts_t* t,
@@ -393,11 +403,9 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     float* ws = b->split_ws;
     int splits = 0;
     // edge_model.edge_mlp.2: dW = de'_tot^T h1 ; db = colsum(de'_tot)
-    RPG_TRY(wgrad(de_tot, D, D, t->h1, D, D, Et, ws, b->g_edge2_w, D, sms, s));
-    RPG_TRY(rpg_colsum_bf16(de_tot, D, Et, D, nullptr, 0, b->g_edge2_b, 1, b->colsum_ws, stream));
+    RPG_TRY(wgrad(de_tot, D, D, t->h1, D, D, Et, ws, b->g_edge2_w, D, sms, s, b->g_edge2_b));
     // edge_model.edge_mlp.0, edge columns [2D,3D): dW = dh1^T e ; db = colsum(dh1)
-    RPG_TRY(wgrad(b->dh1, D, D, t->e, D, D, Et, ws, b->g_edge0_w + 2 * D, 3 * D, sms, s));
-    RPG_TRY(rpg_colsum_bf16(b->dh1, D, Et, D, nullptr, 0, b->g_edge0_b, 1, b->colsum_ws, stream));
+    RPG_TRY(wgrad(b->dh1, D, D, t->e, D, D, Et, ws, b->g_edge0_w + 2 * D, 3 * D, sms, s, b->g_edge0_b));
     // node-side blocks in one launch: dP^T x = [edge_mlp.0[:,0:D]; edge_mlp.0[:,D:2D]; mlp.0[:,0:D]]
     {
         const int Mp = have_out ? 3 * D : 2 * D;
@@ -410,33 +418,29 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     }
     if (have_out) {
         // mlp.2: dW = dm^T h2 ; mlp.0 edge columns [D,2D): dW = dh2^T e'
-        RPG_TRY(wgrad(b->dm, D, D, t->h2, D, D, Et, ws, b->g_mlp2_w, D, sms, s));
-        RPG_TRY(rpg_colsum_bf16(b->dm, D, Et, D, nullptr, 0, b->g_mlp2_b, 1, b->colsum_ws, stream));
-        RPG_TRY(wgrad(b->dh2, D, D, t->e_new, D, D, Et, ws, b->g_mlp0_w + D, 2 * D, sms, s));
-        RPG_TRY(rpg_colsum_bf16(b->dh2, D, Et, D, nullptr, 0, b->g_mlp0_b, 1, b->colsum_ws, stream));
+        RPG_TRY(wgrad(b->dm, D, D, t->h2, D, D, Et, ws, b->g_mlp2_w, D, sms, s, b->g_mlp2_b));
+        RPG_TRY(wgrad(b->dh2, D, D, t->e_new, D, D, Et, ws, b->g_mlp0_w + D, 2 * D, sms, s, b->g_mlp0_b));
         // att.g / theta / phi: one launch dgtp^T m [3c, D], three reductions ; biases = colsum(dgtp)
-        RPG_TRY(wgrad_partials(b->dgtp, c3p, c3, t->m, D, D, Et, ws, sms, s, &splits));
+        RPG_TRY(wgrad_partials(b->dgtp, c3p, c3, t->m, D, D, Et, ws, sms, s, &splits, /*with_colsum=*/true));
         {
             const long long stride = (long long)c3 * D;
             RPG_TRY(rpg_reduce_splits(ws, splits, stride, c, D, b->g_att_g_w, D, 1, stream));
             RPG_TRY(rpg_reduce_splits(ws + (size_t)c * D, splits, stride, c, D, b->g_att_theta_w, D, 1, stream));
             RPG_TRY(rpg_reduce_splits(ws + 2 * (size_t)c * D, splits, stride, c, D, b->g_att_phi_w, D, 1, stream));
+            const float* cs = ws + (size_t)splits * c3 * D;            // [splits, 3c] column sums of dgtp
+            RPG_TRY(rpg_reduce_splits(cs, splits, c3, 1, c, b->g_att_g_b, c, 1, stream));
+            RPG_TRY(rpg_reduce_splits(cs + c, splits, c3, 1, c, b->g_att_theta_b, c, 1, stream));
+            RPG_TRY(rpg_reduce_splits(cs + 2 * c, splits, c3, 1, c, b->g_att_phi_b, c, 1, stream));
         }
-        RPG_TRY(rpg_colsum_bf16(b->dgtp, c3p, Et, c3p, nullptr, 0, b->gtp_bias_tmp, 0, b->colsum_ws, stream));
-        RPG_TRY(rpg_reduce_splits(b->gtp_bias_tmp, 1, 0, 1, c, b->g_att_g_b, c, 1, stream));
-        RPG_TRY(rpg_reduce_splits(b->gtp_bias_tmp + c, 1, 0, 1, c, b->g_att_theta_b, c, 1, stream));
-        RPG_TRY(rpg_reduce_splits(b->gtp_bias_tmp + 2 * c, 1, 0, 1, c, b->g_att_phi_b, c, 1, stream));
         // att.W: dW = sum_e dz[e]^T y[e] = dan^T ysum with ysum[n] = sum_{in-edges(n)} y[e];
         //        db = sum_e dz[e] = sum_n indeg(n) * dan[n]
         RPG_TRY(rpg_edge_to_node_sum(t->y, cp, gr, cp, 0, b->ysum, cp, stream));
         RPG_TRY(wgrad(b->dan, D, D, b->ysum, cp, c, Nt, ws, b->g_att_W_w, c, sms, s));
         RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
         // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
-        RPG_TRY(wgrad(b->d_out, D, D, t->h3, D, D, Nt, ws, b->g_upd2_w, D, sms, s));
-        RPG_TRY(rpg_colsum_bf16(b->d_out, D, Nt, D, nullptr, 0, b->g_upd2_b, 1, b->colsum_ws, stream));
-        RPG_TRY(wgrad(b->dh3, D, D, t->x, D, D, Nt, ws, b->g_upd0_w, 2 * D, sms, s));
+        RPG_TRY(wgrad(b->d_out, D, D, t->h3, D, D, Nt, ws, b->g_upd2_w, D, sms, s, b->g_upd2_b));
+        RPG_TRY(wgrad(b->dh3, D, D, t->x, D, D, Nt, ws, b->g_upd0_w, 2 * D, sms, s, b->g_upd0_b));
         RPG_TRY(wgrad(b->dh3, D, D, t->a, D, D, Nt, ws, b->g_upd0_w + D, 2 * D, sms, s));
-        RPG_TRY(rpg_colsum_bf16(b->dh3, D, Nt, D, nullptr, 0, b->g_upd0_b, 1, b->colsum_ws, stream));
     }
     return 0;
 }

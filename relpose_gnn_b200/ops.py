@@ -137,13 +137,14 @@ def wgrad_ws(D, device):
     return torch.empty(n, dtype=torch.float32, device=device)
 
 
-def wgrad(A, B, out, ws, M=None, N=None):
-    """out[M, N] += A[:, :M]^T @ B[:, :N]  (fp32 `out`, pitch from stride(0); deterministic)."""
+def wgrad(A, B, out, ws, M=None, N=None, bias=None):
+    """out[M, N] += A[:, :M]^T @ B[:, :N]  (fp32 `out`, pitch from stride(0); deterministic).
+    bias (optional, fp32 [M]) += column sums of A, accumulated inside the same kernel."""
     lib = _lib.load()
     M = M if M is not None else A.size(1)
     N = N if N is not None else B.size(1)
-    check(lib.rpg_wgrad(A.data_ptr(), A.stride(0), M, B.data_ptr(), B.stride(0), N, A.size(0), ws.data_ptr(),
-                        out.data_ptr(), out.stride(0), _stream(A)), "rpg_wgrad")
+    check(lib.rpg_wgrad_bias(A.data_ptr(), A.stride(0), M, B.data_ptr(), B.stride(0), N, A.size(0), ws.data_ptr(),
+                             out.data_ptr(), out.stride(0), ptr(bias), _stream(A)), "rpg_wgrad")
 
 
 def pack_weight(src, dst, r0=0, c0=0, rows=None, cols=None, transpose=False):

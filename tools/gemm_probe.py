@@ -146,6 +146,13 @@ def tn_cases():
     ops.wgrad(A, B, out[:, N:], ws)
     ref = A.float().t() @ B.float() + 1
     ok &= report("wgrad accumulate strided", out[:, N:], ref, 2e-3)
+    for (R2, M2) in [(5000, 512), (777, 192), (36864, 48)]:
+        A2, B2 = rnd(R2, M2), rnd(R2, 256)
+        o2 = torch.zeros(M2, 256, dtype=torch.float32, device=dev)
+        bias2 = torch.ones(M2, dtype=torch.float32, device=dev)
+        ops.wgrad(A2, B2, o2, ws, bias=bias2)
+        ok &= report(f"wgrad fused column sums R={R2} M={M2}", bias2, A2.float().sum(0) + 1, 1e-3)
+        ok &= report(f"wgrad with column sums: dW R={R2} M={M2}", o2, A2.float().t() @ B2.float(), 2e-3)
     ok &= report("wgrad untouched half", out[:, :N], torch.ones(M, N, device=dev), 1e-6)
     for _ in range(2):
         ops.wgrad(A, B, out[:, N:], ws)
