@@ -3,6 +3,7 @@
 // dropout + pose heads, pose loss, column sums.  All accesses are 16-byte vectorised and coalesced along the
 // feature dimension; no atomics on floating-point data (fixed summation order => bitwise reproducible).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/rpg.h"
@@ -148,6 +149,10 @@ __global__ void pack_weight_lo_kernel(const float* __restrict__ src, int ld_src,
 constexpr int ATT_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
+// The attention kernels are bound by the MUFU.EX2 pipe (c^2 exps per edge row; forward measured at ~70 % of the
+// 16/clk/SM limit).  Two ways around it were tried and measured neutral on sm_100a: an FMA-pipe polynomial exp2 (~9 issue
+// slots per exp: the 1 instruction/clk/scheduler issue limit binds) and the packed ex2.approx.f16x2 form (ptxas lowers
+// it to two scalar MUFU.EX2.F16).
 template <int C_MAX>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy,
@@ -327,22 +332,34 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
         const int n = (int)(row - g * N);
         const int k0 = __ldg(ptr + n), k1 = __ldg(ptr + n + 1);
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int kk = k0; kk < k1; ++kk) {
-            const long long er = g * Ep + __ldg(idx + kk);
-            float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(v + er * ldv + c)), f);
-            if (mask) {
-                float mf[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(mask + er * ldm + c)), mf);
+        for (int kb = k0; kb < k1; kb += 4) {                 // 4 independent row loads in flight per thread
+            uint4 u[4], um[4], ul[4];
+            bool ok[4];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) if (!(mf[q] > 0.f)) f[q] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                ok[j] = kb + j < k1;
+                const long long er = g * Ep + (ok[j] ? __ldg(idx + kb + j) : 0);
+                u[j] = ok[j] ? __ldg(reinterpret_cast<const uint4*>(v + er * ldv + c)) : make_uint4(0, 0, 0, 0);
+                if (mask) um[j] = ok[j] ? __ldg(reinterpret_cast<const uint4*>(mask + er * ldm + c)) : make_uint4(0, 0, 0, 0);
+                if (v_lo) ul[j] = ok[j] ? __ldg(reinterpret_cast<const uint4*>(v_lo + er * ldv + c)) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] += f[q];
-            if (v_lo) {                                       // fp32 mode: value = hi + lo
-                unpack8(__ldg(reinterpret_cast<const uint4*>(v_lo + er * ldv + c)), f);
+            for (int j = 0; j < 4; ++j) {                     // fixed summation order: deterministic
+                float f[8];
+                unpack8(u[j], f);
+                if (mask) {
+                    float mf[8];
+                    unpack8(um[j], mf);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (!(mf[q] > 0.f)) f[q] = 0.f;
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] += f[q];
+                if (v_lo) {                                   // fp32 mode: value = hi + lo
+                    unpack8(ul[j], f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] += f[q];
+                }
             }
         }
         if (scale) {
@@ -446,19 +463,40 @@ __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, lo
     }
 }
 
-// pose[r, j] = sum_c drop(feat[r, c]) * w6[j, c] + b6[j]   (posenet.py:1073-1086).  One warp per row.
+// pose[r, j] = sum_c drop(feat[r, c]) * w6[j, c] + b6[j]   (posenet.py:1073-1086).  One warp per row; lane owns
+// columns [lane*8, +8) of every 256-column pass and keeps its slice of the six weight rows in registers (PASSES <= 2,
+// i.e. D <= 512; wider layers read the weights from shared memory).
 constexpr int HEAD_WARPS = 8;
+template <int PASSES>
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, const uint8_t* __restrict__ keep,
                 unsigned long long seed, uint32_t thresh, int use_seed, float scale, const float* __restrict__ w6,
                 const float* __restrict__ b6, float* __restrict__ pose, const bf16* __restrict__ feat_lo) {
-    extern __shared__ __align__(16) float s_w[];   // [6][D]
-    for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) s_w[i] = w6[i];
-    __syncthreads();
+    extern __shared__ __align__(16) float s_w[];   // [6][D], only used when PASSES == 0
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NP = PASSES > 0 ? PASSES : 1;
+    float wr[NP][6][8];
+    if (PASSES > 0) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+            const int c = ps * 256 + lane * 8;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) wr[ps][j][q] = c < D ? __ldg(w6 + j * D + c + q) : 0.f;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) s_w[i] = w6[i];
+        __syncthreads();
+    }
+    const int n_pass = PASSES > 0 ? PASSES : (D + 255) / 256;
     for (long long row = blockIdx.x * (long long)HEAD_WARPS + warp; row < rows; row += (long long)gridDim.x * HEAD_WARPS) {
         float acc[6] = {0, 0, 0, 0, 0, 0};
-        for (int c = lane * 8; c < D; c += 256) {
+#pragma unroll
+        for (int ps = 0; ps < (PASSES > 0 ? PASSES : 8); ++ps) {
+            if (ps >= n_pass) break;
+            const int c = ps * 256 + lane * 8;
+            if (c >= D) continue;
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
             if (feat_lo) {                                    // fp32 mode: value = hi + lo
@@ -479,10 +517,15 @@ head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, c
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const float4 w0 = *reinterpret_cast<const float4*>(s_w + j * D + c);
-                const float4 w1 = *reinterpret_cast<const float4*>(s_w + j * D + c + 4);
-                acc[j] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
-                          f[6] * w1.z + f[7] * w1.w;
+                if (PASSES > 0) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[j] = fmaf(f[q], wr[ps < NP ? ps : 0][j][q], acc[j]);
+                } else {
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_w + j * D + c);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_w + j * D + c + 4);
+                    acc[j] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                              f[6] * w1.z + f[7] * w1.w;
+                }
             }
         }
 #pragma unroll
@@ -858,20 +901,27 @@ int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* 
 int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t rows, int D, const uint8_t* keep,
                  uint64_t seed, float p_drop, const float* w6, const float* b6, float* pose, rpg_stream_t stream) {
     if (!feat || !w6 || !b6 || !pose || rows <= 0 || D % 8 || ldf % 8) return set_error(RPG_E_ARG, "head_fwd: bad arguments");
-    const size_t smem = (size_t)6 * D * sizeof(float);
-    if (smem > 48 * 1024) {
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
-    }
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
     const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
     const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
-    head_fwd_kernel<<<grid_for(rows, HEAD_WARPS, 148 * 8), HEAD_WARPS * 32, smem, as_stream(stream)>>>(
-        reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose,
-        reinterpret_cast<const bf16*>(feat_lo));
+    const int grid = grid_for(rows, HEAD_WARPS, 148 * 8);
+    const bf16* f = reinterpret_cast<const bf16*>(feat);
+    const bf16* fl = reinterpret_cast<const bf16*>(feat_lo);
+    cudaStream_t st = as_stream(stream);
+    if (D <= 256) {
+        head_fwd_kernel<1><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+    } else if (D <= 512) {
+        head_fwd_kernel<2><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+    } else {
+        const size_t smem = (size_t)6 * D * sizeof(float);
+        if (D > 2048) return set_error(RPG_E_UNSUPPORTED, "head_fwd: D > 2048");
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            cudaFuncSetAttribute(head_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        head_fwd_kernel<0><<<grid, HEAD_WARPS * 32, smem, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+    }
     return check_launch("head_fwd_kernel");
 }
 
