@@ -200,11 +200,14 @@ int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_
 /* AttentionBlock core, att.py:25-30: y[e,i] = sum_j softmax_j(phi[e,i]*theta[e,j]) * g[e,j].
  * gtp [Et, 3c] fp32 holds (g | theta | phi) rows; y [Et, ldy] bf16 (only the first c columns written). */
 int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo /* NULL in bf16 mode */,
+                      float* aux /* optional [Et, 4c] fp32 row statistics for the backward, or NULL */,
                       rpg_stream_t stream);
 /* Backward of the above with dy[e,:] = dyn[node(dst(e)), :] gathered through the template:
  * dgtp [Et, ld_dgtp] bf16 = (dg | dtheta | dphi) in the first 3c columns.                          */
 int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph,
-                      int64_t Et, int c, rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream);
+                      int64_t Et, int c, rpg_bf16* dgtp, int ld_dgtp,
+                      const float* aux /* the forward's statistics: c^2 instead of 2 c^2 exps per row; or NULL */,
+                      rpg_stream_t stream);
 
 /* PyG mean aggregation over destination [3p], reached from my_gnn_layer.py:301:
  * a[g*N+n, :] = inv_deg[n] * sum_{k in in-edges(n)} z[g*Ep+k, :]   (fixed order, no atomics).       */
@@ -304,6 +307,7 @@ typedef struct {                  /* activations of one layer call; all bf16 unl
   rpg_bf16* out;                  /* [Nt, D] out (pre-ReLU)                                             */
   rpg_bf16* out_relu;             /* [Nt, D] optional relu(out) (posenet.py:1064)                       */
   /* ReLU bit patterns [rows, D/8 bytes] written by the forward and consumed by the backward epilogues    */
+  float* att_aux;                 /* [Et, 4c] fp32 optional: attention row statistics kept for the backward  */
   uint8_t* h1_bits;               /* [Et, D/8] */
   uint8_t* h2_bits;               /* [Et, D/8] */
   uint8_t* h3_bits;               /* [Nt, D/8] */

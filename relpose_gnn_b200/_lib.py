@@ -52,7 +52,7 @@ class LayerWeights(C.Structure):
 
 class LayerActs(C.Structure):
     _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
-                                 "h3", "out", "out_relu", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
+                                 "h3", "out", "out_relu", "att_aux", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
                                  "x_bits", "e_bits")]
 
 
@@ -98,14 +98,14 @@ SIGNATURES = {
     "rpg_pack_weight": (I, [P, I, I, I, I, I, P, I, I, P]),
     "rpg_cast_f32_to_bf16": (I, [P, P, I64, P]),
     "rpg_cast_bf16_to_f32": (I, [P, P, I64, P]),
-    "rpg_attention_fwd": (I, [P, I64, I, P, I, P, P]),
+    "rpg_attention_fwd": (I, [P, I64, I, P, I, P, P, P]),
     "rpg_cast_f32_to_split": (I, [P, P, P, I64, P]),
     "rpg_split_to_f32": (I, [P, P, P, I64, P]),
     "rpg_pack_weight_lo": (I, [P, I, I, I, I, I, P, I, P]),
     "rpg_edge_init_fwd_f32": (I, [P, I, P, C.POINTER(Graph), I, P, P, I, P]),
     "rpg_aggregate_mean_split": (I, [P, P, I, C.POINTER(Graph), I, P, P, I, P]),
     "rpg_layer_fwd_split": (I, [C.POINTER(LayerWeightsSplit), C.POINTER(Graph), C.POINTER(LayerActsSplit), P]),
-    "rpg_attention_bwd": (I, [P, P, I, C.POINTER(Graph), I64, I, P, I, P]),
+    "rpg_attention_bwd": (I, [P, P, I, C.POINTER(Graph), I64, I, P, I, P, P]),
     "rpg_aggregate_mean": (I, [P, I, C.POINTER(Graph), I, P, I, P]),
     "rpg_edge_to_node_sum": (I, [P, I, C.POINTER(Graph), I, I, P, I, P]),
     "rpg_segment_sum": (I, [P, I, P, I, P, P, P, C.POINTER(Graph), I, P, I, P]),

@@ -153,10 +153,12 @@ constexpr float LOG2E = 1.4426950408889634f;
 // 16/clk/SM limit).  Two ways around it were tried and measured neutral on sm_100a: an FMA-pipe polynomial exp2 (~9 issue
 // slots per exp: the 1 instruction/clk/scheduler issue limit binds) and the packed ex2.approx.f16x2 form (ptxas lowers
 // it to two scalar MUFU.EX2.F16).
-template <int C_MAX>
+// AUX: also store the per-row statistics [1/den | y | sum_j S_ij theta_j | sum_j S_ij g_j theta_j] (fp32 [Et, 4c]) that
+// let the backward skip its first sweep; the extra FMAs hide under the MUFU bound.
+template <int C_MAX, bool AUX>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy,
-                     bf16* __restrict__ y_lo) {
+                     bf16* __restrict__ y_lo, float* __restrict__ aux) {
     __shared__ __align__(16) float s_g[ATT_WARPS][C_MAX];
     __shared__ __align__(16) float s_t[ATT_WARPS][C_MAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,6 +184,7 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
             const float m0 = p0 >= 0.f ? p0 * tmax : p0 * tmin;
             const float m1 = p1 >= 0.f ? p1 * tmax : p1 * tmin;
             float num0 = 0.f, den0 = 0.f, num1 = 0.f, den1 = 0.f;
+            float at0 = 0.f, agt0 = 0.f, at1 = 0.f, agt1 = 0.f;
 #pragma unroll 4
             for (int j = 0; j < c; j += 4) {
                 const float4 t4 = *reinterpret_cast<const float4*>(st + j);
@@ -194,9 +197,21 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
                     const float e1 = exp2f(fmaf(p1, tt[q], -m1));
                     num0 = fmaf(e0, gg[q], num0); den0 += e0;
                     num1 = fmaf(e1, gg[q], num1); den1 += e1;
+                    if (AUX) {
+                        at0 = fmaf(e0, tt[q], at0); agt0 = fmaf(e0 * gg[q], tt[q], agt0);
+                        at1 = fmaf(e1, tt[q], at1); agt1 = fmaf(e1 * gg[q], tt[q], agt1);
+                    }
                 }
             }
             const float y0 = num0 / den0, y1 = num1 / den1;
+            if (AUX) {
+                const float inv0 = 1.f / den0, inv1 = 1.f / den1;
+                float* a = aux + row * 4 * c;
+                *reinterpret_cast<float2*>(a + i0) = make_float2(inv0, inv1);
+                *reinterpret_cast<float2*>(a + c + i0) = make_float2(y0, y1);
+                *reinterpret_cast<float2*>(a + 2 * c + i0) = make_float2(at0 * inv0, at1 * inv1);
+                *reinterpret_cast<float2*>(a + 3 * c + i0) = make_float2(agt0 * inv0, agt1 * inv1);
+            }
             *reinterpret_cast<uint32_t*>(y + row * ldy + i0) = pack_bf16x2(y0, y1);
             if (y_lo)
                 *reinterpret_cast<uint32_t*>(y_lo + row * ldy + i0) =
@@ -213,7 +228,7 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dyn, int ld_dyn,
                      const int* __restrict__ tdst, int Ep, int Nn, long long Et, int c,
-                     bf16* __restrict__ dgtp, int ld_dgtp) {
+                     bf16* __restrict__ dgtp, int ld_dgtp, const float* __restrict__ aux) {
     extern __shared__ __align__(16) float att_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* base = att_smem + (size_t)warp * 8 * c;
@@ -242,8 +257,20 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
             tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
         }
         __syncwarp();
-        // ---- sweep 1: two i per lane share the broadcast loads of (theta, g, g*theta)
-        for (int ib = 0; ib < c; ib += 64) {
+        // ---- sweep 1 from the forward's saved statistics (no exps): [1/den | y | sum S theta | sum S g theta]
+        if (aux) {
+            const float* a = aux + row * 4 * c;
+            for (int i = lane; i < c; i += 32) {
+                const float phi = r[2 * c + i];
+                const float pl = phi * LOG2E;
+                const float w = dy[i] * a[i], yi = a[c + i];
+                sp[i] = pl; sm[i] = pl >= 0.f ? pl * tmax : pl * tmin;
+                sw[i] = w; swp[i] = w * phi; swyp[i] = w * yi * phi;
+                dgtp[row * ld_dgtp + 2 * c + i] = __float2bfloat16_rn(dy[i] * (a[3 * c + i] - yi * a[2 * c + i]));
+            }
+        }
+        // ---- sweep 1 (recompute): two i per lane share the broadcast loads of (theta, g, g*theta)
+        for (int ib = 0; ib < (aux ? 0 : c); ib += 64) {
             const int i0 = ib + lane, i1 = i0 + 32;
             const bool v0 = i0 < c, v1 = i1 < c;
             const float phi0 = v0 ? r[2 * c + i0] : 0.f, phi1 = v1 ? r[2 * c + i1] : 0.f;
@@ -819,17 +846,22 @@ int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, cons
     return check_launch("edge_init_fwd_f32_kernel");
 }
 
-int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, rpg_stream_t stream) {
+int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, float* aux,
+                      rpg_stream_t stream) {
     if (!gtp || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd: bad arguments");
     if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
-    attention_fwd_kernel<256><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
-                                                                              reinterpret_cast<bf16*>(y_lo));
+    if (aux)
+        attention_fwd_kernel<256, true><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
+                                                                                      reinterpret_cast<bf16*>(y_lo), aux);
+    else
+        attention_fwd_kernel<256, false><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
+                                                                                       reinterpret_cast<bf16*>(y_lo), nullptr);
     return check_launch("attention_fwd_kernel");
 }
 
 int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
-                      rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream) {
+                      rpg_bf16* dgtp, int ld_dgtp, const float* aux, rpg_stream_t stream) {
     if (!gtp || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd: bad arguments");
     if (c % 4 || c < 4 || c > 512) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c must be a multiple of 4 in [4,512]");
     const size_t smem = (size_t)ATT_WARPS * 8 * c * sizeof(float);
@@ -840,7 +872,7 @@ int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_
     }
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
     attention_bwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
-                                                                           Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp);
+                                                                           Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp, aux);
     return check_launch("attention_bwd_kernel");
 }
 

@@ -210,7 +210,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     RPG_TRY(gemm_launch(&g, s));
 
     // (7) rank-1 softmax attention (att.py:25-30)
-    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, stream));
+    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, t->att_aux, stream));
 
     // (8) z = y WW^T + bW + m (att.py:32-33) as [y | m] [WW | I]^T: the residual is a second K segment (exact in the
     //     fp32 accumulator) so it streams through TMA with the operands instead of being fetched by the epilogue
@@ -287,7 +287,7 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     g.bias = w->bgtp; g.out_f32 = t->gtp; g.ldo_f32 = c3;
     RPG_TRY(gemm_launch(&g, s));
     // (7) attention -> y (hi, lo)
-    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y_hi, cp, t->y_lo, stream));
+    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y_hi, cp, t->y_lo, nullptr, stream));
     // (8) z = y WW^T + bW + m
     base((int)Et, D, w->WW3, 3 * cp); g.n_seg = 3; set3(g, 0, t->y_hi, t->y_lo, cp, cp);
     g.bias = w->bW; g.resid = t->m_hi; g.resid_lo = t->m_lo; g.resid_ld = D;
@@ -344,7 +344,7 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         g.out_f32 = b->dyn; g.ldo_f32 = c;
         RPG_TRY(gemm_launch(&g, s));
         // attention backward -> dgtp [Et, 3c]
-        RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, stream));
+        RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, t->att_aux, stream));
         // dm = dgtp Wgtp + dan[dst]
         g = nt((int)Et, D, b->dgtp, c3p, c3p, w->WgtpT, c3p);
         g.Ep = gr->Ep; g.Nn = gr->N;

@@ -215,7 +215,8 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
     return a
 
 
-def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None, e_bits=None, arena=None):
+def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None, e_bits=None, arena=None,
+                      for_backward=True):
     """Runs rpg_layer_fwd on bf16 inputs; returns the dict of activation tensors (kept for backward).
     x_bits / e_bits: optional ReLU bit patterns of the inputs (when they are ReLU outputs of a previous op)."""
     D = weights.D
@@ -233,6 +234,8 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
          "z": new(Et, D), "a": new(Nt, D), "h3": new(Nt, D), "out": new(Nt, D)}
     u8 = torch.uint8
     a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8), "h3_bits": new(Nt, D // 8, u8)})
+    if for_backward:
+        a["att_aux"] = new(Et, 4 * c, torch.float32)           # attention row statistics: the backward skips a sweep
     if want_relu_copies:
         a["e_new_relu"] = new(Et, D)
         a["out_relu"] = new(Nt, D)
@@ -292,7 +295,7 @@ class _LayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, e, module, graph, *params):
         weights = module._packed(x.device).refresh(module)
-        acts = layer_forward_raw(weights, graph, ops.to_bf16(x), ops.to_bf16(e))
+        acts = layer_forward_raw(weights, graph, ops.to_bf16(x), ops.to_bf16(e), for_backward=any(ctx.needs_input_grad))
         ctx.module, ctx.graph, ctx.acts, ctx.weights = module, graph, acts, weights
         ctx.in_dtypes = (x.dtype, e.dtype)
         ctx.param_shapes = [p.shape for p in params]

@@ -48,7 +48,8 @@ class _StackFn(torch.autograd.Function):
         acts = []
         xin, x_bits = xb, None
         for _ in range(R):                                       # same gnn1 weights each round (posenet.py:1060-1069)
-            a = layer_forward_raw(lw, graph, xin, e, want_relu_copies=True, x_bits=x_bits, e_bits=e_bits, arena=arena)
+            a = layer_forward_raw(lw, graph, xin, e, want_relu_copies=True, x_bits=x_bits, e_bits=e_bits, arena=arena,
+                                  for_backward=any(ctx.needs_input_grad))
             acts.append(a)
             xin, e, x_bits, e_bits = a["out_relu"], a["e_new_relu"], a["out_bits"], a["e_new_bits"]
         p_drop, keep_x, keep_e, seed = drop

@@ -32,7 +32,8 @@ class Arena:
 
 def layer_fwd_bytes(D, Nt, Et):
     c = D // 8
-    return Et * (6 * D * 2 + 3 * c * 4 + pad64(c) * 2 + 3 * (D // 8)) + Nt * (3 * D * 2 + 4 * D * 2 + 2 * (D // 8)) + 64 * 256
+    return (Et * (6 * D * 2 + 3 * c * 4 + 4 * c * 4 + pad64(c) * 2 + 3 * (D // 8)) +
+            Nt * (3 * D * 2 + 4 * D * 2 + 2 * (D // 8)) + 64 * 256)
 
 
 def layer_bwd_bytes(D, Nt, Et):
@@ -176,9 +177,9 @@ def to_f32(t):
     return out
 
 
-def attention_fwd(gtp, c, y, y_lo=None):
-    check(_lib.load().rpg_attention_fwd(gtp.data_ptr(), gtp.size(0), c, y.data_ptr(), y.stride(0), ptr(y_lo), _stream(gtp)),
-          "rpg_attention_fwd")
+def attention_fwd(gtp, c, y, y_lo=None, aux=None):
+    check(_lib.load().rpg_attention_fwd(gtp.data_ptr(), gtp.size(0), c, y.data_ptr(), y.stride(0), ptr(y_lo), ptr(aux),
+                                        _stream(gtp)), "rpg_attention_fwd")
 
 
 def to_split(t):
@@ -210,9 +211,9 @@ def pack_weight3(src, dst, c0=0, cols=None):
                                  _stream(src)), "rpg_pack_weight_lo")
 
 
-def attention_bwd(gtp, dyn, graph, c, dgtp):
+def attention_bwd(gtp, dyn, graph, c, dgtp, aux=None):
     check(_lib.load().rpg_attention_bwd(gtp.data_ptr(), dyn.data_ptr(), dyn.stride(0), graph.byref(), gtp.size(0), c,
-                                        dgtp.data_ptr(), dgtp.stride(0), _stream(gtp)), "rpg_attention_bwd")
+                                        dgtp.data_ptr(), dgtp.stride(0), ptr(aux), _stream(gtp)), "rpg_attention_bwd")
 
 
 def aggregate_mean(z, graph, a):

@@ -28,7 +28,8 @@ def attention_check(c=64, Et=500, N=9):
     gtp = torch.randn(Et, 3 * c, device=dev, generator=gen, requires_grad=True)
     dyn = torch.randn(g.n_node_rows, c, device=dev, generator=gen)
     y = torch.zeros(Et, max(c, 64), dtype=torch.bfloat16, device=dev)
-    ops.attention_fwd(gtp.detach(), c, y)
+    aux = torch.empty(Et, 4 * c, device=dev)
+    ops.attention_fwd(gtp.detach(), c, y, aux=aux)
     gg, th, ph = gtp[:, :c], gtp[:, c:2 * c], gtp[:, 2 * c:]
     s = torch.softmax(ph.unsqueeze(2) * th.unsqueeze(1), -1)
     y_ref = (s * gg.unsqueeze(1)).sum(-1)
@@ -40,6 +41,10 @@ def attention_check(c=64, Et=500, N=9):
     ops.attention_bwd(gtp.detach(), dyn, g, c, dgtp)
     for nm, sl in (("dg", slice(0, c)), ("dtheta", slice(c, 2 * c)), ("dphi", slice(2 * c, 3 * c))):
         print(f"attention bwd c={c} {nm}: rel {rel(dgtp[:, sl].float(), gtp.grad[:, sl]):.3e}")
+    dgtp2 = torch.zeros_like(dgtp)
+    ops.attention_bwd(gtp.detach(), dyn, g, c, dgtp2, aux=aux)
+    for nm, sl in (("dg", slice(0, c)), ("dtheta", slice(c, 2 * c)), ("dphi", slice(2 * c, 3 * c))):
+        print(f"attention bwd (saved statistics) c={c} {nm}: rel {rel(dgtp2[:, sl].float(), gtp.grad[:, sl]):.3e}")
 
 
 def layer_check(D, N, Gn, seed, ct_out_scale=1.0, ct_e_scale=1.0, quantize_inputs=False):
