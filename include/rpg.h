@@ -180,6 +180,21 @@ void rpg_struct_sizes(int32_t* out10);
 int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols,
                       float* out, int ldo, int accumulate, rpg_stream_t stream);
 
+/* Several folds in ONE launch (a layer backward queues all of its weight-gradient folds): every descriptor is an
+ * accumulating rpg_reduce_splits; outputs of different descriptors must not overlap. */
+#define RPG_REDUCE_BATCH_MAX 32
+typedef struct rpg_reduce_desc {
+    const float* part;      /* [splits][rows*cols] partials, split stride `stride` floats */
+    float* out;             /* [rows, ldo] accumulated into */
+    int64_t stride;
+    int32_t splits, rows, cols, ldo;
+} rpg_reduce_desc_t;
+typedef struct rpg_reduce_batch {
+    rpg_reduce_desc_t d[RPG_REDUCE_BATCH_MAX];
+    int32_t n;
+} rpg_reduce_batch_t;
+int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Weights: fp32 master parameters (reference state_dict layout) -> packed bf16 operands
  * ---------------------------------------------------------------------------------------- */
@@ -257,6 +272,12 @@ int64_t rpg_pose_loss_ws_floats(int64_t Et);
 int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et,
                   const float* grad_scale, float* target, float* sums, float* dpred, float* ws,
                   rpg_stream_t stream);
+/* The same with the learned loss weights of PoseNetCriterion folded in (criterion.py:55-57; sax, saq: device
+ * scalars): out7 = [sum_t, sum_q, loss, t_loss, q_loss, dloss/dsax, dloss/dsaq] with t_loss = sum_t / (3 Et),
+ * loss = exp(-sax) t_loss + sax + exp(-saq) q_loss + saq; dpred = dloss/dpred.  No host round trip. */
+int rpg_pose_criterion(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et,
+                       const float* sax, const float* saq, float* target, float* out7, float* dpred, float* ws,
+                       rpg_stream_t stream);
 
 /* Column sums (bias gradients): out[c] (+)= sum_r w[r % mod] * v[r, c]; deterministic; row_w may be NULL. */
 int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod,

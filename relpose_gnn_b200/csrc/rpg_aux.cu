@@ -2,6 +2,7 @@
 // (MUFU-bound), deterministic segment reductions over the per-graph edge template, edge-feature initialiser,
 // dropout + pose heads, pose loss, column sums.  All accesses are 16-byte vectorised and coalesced along the
 // feature dimension; no atomics on floating-point data (fixed summation order => bitwise reproducible).
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -149,27 +150,35 @@ __global__ void pack_weight_lo_kernel(const float* __restrict__ src, int ld_src,
 constexpr int ATT_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
-// The attention kernels are bound by the MUFU.EX2 pipe (c^2 exps per edge row; forward measured at ~70 % of the
-// 16/clk/SM limit).  Two ways around it were tried and measured neutral on sm_100a: an FMA-pipe polynomial exp2 (~9 issue
-// slots per exp: the 1 instruction/clk/scheduler issue limit binds) and the packed ex2.approx.f16x2 form (ptxas lowers
-// it to two scalar MUFU.EX2.F16).
+// The attention kernels are bound by the MUFU.EX2 pipe (c^2 exps per edge row, 16/clk/SM).  Everything around the exps
+// is packed fp32x2 math (FFMA2/FADD2, sm_100+): a lane owns two rows (forward) or two columns (backward sweep 2) of the
+// c x c score matrix as one 64-bit register pair and the broadcast operand is a scalar, so a pair of exps costs
+// 5-7 issue slots and 3-5 FMA-pipe instructions against 16 MUFU cycles.  (Scalar FFMA issues every other cycle on this
+// part, which made the scalar form FMA-pipe bound.)  Tried and measured neutral: an FMA-pipe polynomial exp2 and the
+// packed ex2.approx.f16x2 form (ptxas lowers it to two scalar MUFU.EX2.F16).
 // AUX: also store the per-row statistics [1/den | y | sum_j S_ij theta_j | sum_j S_ij g_j theta_j] (fp32 [Et, 4c]) that
-// let the backward skip its first sweep; the extra FMAs hide under the MUFU bound.
+// let the backward skip its first sweep.
+__device__ __forceinline__ float2 ex2_pair(float2 a) { return make_float2(exp2f(a.x), exp2f(a.y)); }
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
 template <int C_MAX, bool AUX>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy,
                      bf16* __restrict__ y_lo, float* __restrict__ aux) {
     __shared__ __align__(16) float s_g[ATT_WARPS][C_MAX];
     __shared__ __align__(16) float s_t[ATT_WARPS][C_MAX];
+    __shared__ __align__(16) float s_gt[AUX ? ATT_WARPS : 1][AUX ? C_MAX : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* sg = s_g[warp];
     float* st = s_t[warp];
+    float* sgt = s_gt[AUX ? warp : 0];
     for (long long row = blockIdx.x * (long long)ATT_WARPS + warp; row < Et; row += (long long)gridDim.x * ATT_WARPS) {
         const float* r = gtp + row * 3 * c;
         float tmax = -INFINITY, tmin = INFINITY;
         for (int j = lane; j < c; j += 32) {
             const float g = r[j], t = r[c + j];
             sg[j] = g; st[j] = t;
+            if (AUX) sgt[j] = g * t;
             tmax = fmaxf(tmax, t); tmin = fminf(tmin, t);
         }
 #pragma unroll
@@ -180,37 +189,37 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
         __syncwarp();
         for (int i0 = 2 * lane; i0 < c; i0 += 64) {
             const float2 ph = *reinterpret_cast<const float2*>(r + 2 * c + i0);
-            const float p0 = ph.x * LOG2E, p1 = ph.y * LOG2E;
-            const float m0 = p0 >= 0.f ? p0 * tmax : p0 * tmin;
-            const float m1 = p1 >= 0.f ? p1 * tmax : p1 * tmin;
-            float num0 = 0.f, den0 = 0.f, num1 = 0.f, den1 = 0.f;
-            float at0 = 0.f, agt0 = 0.f, at1 = 0.f, agt1 = 0.f;
+            const float2 P = make_float2(ph.x * LOG2E, ph.y * LOG2E);
+            const float2 nM = make_float2(-(P.x >= 0.f ? P.x * tmax : P.x * tmin), -(P.y >= 0.f ? P.y * tmax : P.y * tmin));
+            float2 num = make_float2(0.f, 0.f), den = num, at = num, agt = num;
 #pragma unroll 4
             for (int j = 0; j < c; j += 4) {
                 const float4 t4 = *reinterpret_cast<const float4*>(st + j);
                 const float4 g4 = *reinterpret_cast<const float4*>(sg + j);
+                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (AUX) x4 = *reinterpret_cast<const float4*>(sgt + j);
                 const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
                 const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+                const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float e0 = exp2f(fmaf(p0, tt[q], -m0));
-                    const float e1 = exp2f(fmaf(p1, tt[q], -m1));
-                    num0 = fmaf(e0, gg[q], num0); den0 += e0;
-                    num1 = fmaf(e1, gg[q], num1); den1 += e1;
+                    const float2 e = ex2_pair(__ffma2_rn(P, bcast2(tt[q]), nM));
+                    num = __ffma2_rn(e, bcast2(gg[q]), num);
+                    den = __fadd2_rn(den, e);
                     if (AUX) {
-                        at0 = fmaf(e0, tt[q], at0); agt0 = fmaf(e0 * gg[q], tt[q], agt0);
-                        at1 = fmaf(e1, tt[q], at1); agt1 = fmaf(e1 * gg[q], tt[q], agt1);
+                        at = __ffma2_rn(e, bcast2(tt[q]), at);
+                        agt = __ffma2_rn(e, bcast2(xx[q]), agt);
                     }
                 }
             }
-            const float y0 = num0 / den0, y1 = num1 / den1;
+            const float y0 = num.x / den.x, y1 = num.y / den.y;
             if (AUX) {
-                const float inv0 = 1.f / den0, inv1 = 1.f / den1;
+                const float inv0 = 1.f / den.x, inv1 = 1.f / den.y;
                 float* a = aux + row * 4 * c;
                 *reinterpret_cast<float2*>(a + i0) = make_float2(inv0, inv1);
                 *reinterpret_cast<float2*>(a + c + i0) = make_float2(y0, y1);
-                *reinterpret_cast<float2*>(a + 2 * c + i0) = make_float2(at0 * inv0, at1 * inv1);
-                *reinterpret_cast<float2*>(a + 3 * c + i0) = make_float2(agt0 * inv0, agt1 * inv1);
+                *reinterpret_cast<float2*>(a + 2 * c + i0) = make_float2(at.x * inv0, at.y * inv1);
+                *reinterpret_cast<float2*>(a + 3 * c + i0) = make_float2(agt.x * inv0, agt.y * inv1);
             }
             *reinterpret_cast<uint32_t*>(y + row * ldy + i0) = pack_bf16x2(y0, y1);
             if (y_lo)
@@ -221,8 +230,9 @@ attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* _
     }
 }
 
-// Backward, two sweeps of c^2 exps each, nothing of size c x c is stored:
+// Backward, nothing of size c x c is stored:
 //  sweep 1 (lane owns i): den_i, y_i and  dphi_i = w_i (sum_j p_ij g_j theta_j - y_i sum_j p_ij theta_j),  w_i = dy_i / den_i
+//          -- read from the forward's saved statistics when `aux` is given, recomputed (c^2 more exps) otherwise
 //  sweep 2 (lane owns j): p_ij recomputed;  dg_j = sum_i w_i p_ij,  dtheta_j = g_j sum_i w_i phi_i p_ij - sum_i w_i y_i phi_i p_ij
 // with p_ij = exp2(phi_i log2e theta_j - m_i), m_i the rank-1 row maximum.  One warp per edge row.
 __global__ void __launch_bounds__(ATT_WARPS * 32)
@@ -236,7 +246,7 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
     float* st = sg + c;           // theta_j
     float* sgt = st + c;          // g_j * theta_j
     float* sp = sgt + c;          // phi_i * log2e
-    float* sm = sp + c;           // row maximum (log2 domain)
+    float* sm = sp + c;           // -(row maximum) (log2 domain)
     float* sw = sm + c;           // w_i
     float* swp = sw + c;          // w_i * phi_i
     float* swyp = swp + c;        // w_i * y_i * phi_i
@@ -264,20 +274,19 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
                 const float phi = r[2 * c + i];
                 const float pl = phi * LOG2E;
                 const float w = dy[i] * a[i], yi = a[c + i];
-                sp[i] = pl; sm[i] = pl >= 0.f ? pl * tmax : pl * tmin;
+                sp[i] = pl; sm[i] = -(pl >= 0.f ? pl * tmax : pl * tmin);
                 sw[i] = w; swp[i] = w * phi; swyp[i] = w * yi * phi;
                 dgtp[row * ld_dgtp + 2 * c + i] = __float2bfloat16_rn(dy[i] * (a[3 * c + i] - yi * a[2 * c + i]));
             }
         }
-        // ---- sweep 1 (recompute): two i per lane share the broadcast loads of (theta, g, g*theta)
+        // ---- sweep 1 (recompute): a lane owns rows i0 = ib + lane and i1 = i0 + 32 as one fp32x2 pair
         for (int ib = 0; ib < (aux ? 0 : c); ib += 64) {
             const int i0 = ib + lane, i1 = i0 + 32;
             const bool v0 = i0 < c, v1 = i1 < c;
             const float phi0 = v0 ? r[2 * c + i0] : 0.f, phi1 = v1 ? r[2 * c + i1] : 0.f;
-            const float p0 = phi0 * LOG2E, p1 = phi1 * LOG2E;
-            const float m0 = p0 >= 0.f ? p0 * tmax : p0 * tmin;
-            const float m1 = p1 >= 0.f ? p1 * tmax : p1 * tmin;
-            float den0 = 0.f, num0 = 0.f, at0 = 0.f, agt0 = 0.f, den1 = 0.f, num1 = 0.f, at1 = 0.f, agt1 = 0.f;
+            const float2 P = make_float2(phi0 * LOG2E, phi1 * LOG2E);
+            const float2 nM = make_float2(-(P.x >= 0.f ? P.x * tmax : P.x * tmin), -(P.y >= 0.f ? P.y * tmax : P.y * tmin));
+            float2 den = make_float2(0.f, 0.f), num = den, at = den, agt = den;
 #pragma unroll 2
             for (int j = 0; j < c; j += 4) {
                 const float4 t4 = *reinterpret_cast<const float4*>(st + j);
@@ -286,30 +295,31 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
                 const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float e0 = exp2f(fmaf(p0, tt[u], -m0));
-                    const float e1 = exp2f(fmaf(p1, tt[u], -m1));
-                    den0 += e0; num0 = fmaf(e0, gg[u], num0); at0 = fmaf(e0, tt[u], at0); agt0 = fmaf(e0, xx[u], agt0);
-                    den1 += e1; num1 = fmaf(e1, gg[u], num1); at1 = fmaf(e1, tt[u], at1); agt1 = fmaf(e1, xx[u], agt1);
+                    const float2 e = ex2_pair(__ffma2_rn(P, bcast2(tt[u]), nM));
+                    den = __fadd2_rn(den, e);
+                    num = __ffma2_rn(e, bcast2(gg[u]), num);
+                    at = __ffma2_rn(e, bcast2(tt[u]), at);
+                    agt = __ffma2_rn(e, bcast2(xx[u]), agt);
                 }
             }
             if (v0) {
-                const float inv = 1.f / den0, y = num0 * inv, w = dy[i0] * inv;
-                sp[i0] = p0; sm[i0] = m0; sw[i0] = w; swp[i0] = w * phi0; swyp[i0] = w * y * phi0;
-                dgtp[row * ld_dgtp + 2 * c + i0] = __float2bfloat16_rn(w * (agt0 - y * at0));
+                const float inv = 1.f / den.x, y = num.x * inv, w = dy[i0] * inv;
+                sp[i0] = P.x; sm[i0] = nM.x; sw[i0] = w; swp[i0] = w * phi0; swyp[i0] = w * y * phi0;
+                dgtp[row * ld_dgtp + 2 * c + i0] = __float2bfloat16_rn(w * (agt.x - y * at.x));
             }
             if (v1) {
-                const float inv = 1.f / den1, y = num1 * inv, w = dy[i1] * inv;
-                sp[i1] = p1; sm[i1] = m1; sw[i1] = w; swp[i1] = w * phi1; swyp[i1] = w * y * phi1;
-                dgtp[row * ld_dgtp + 2 * c + i1] = __float2bfloat16_rn(w * (agt1 - y * at1));
+                const float inv = 1.f / den.y, y = num.y * inv, w = dy[i1] * inv;
+                sp[i1] = P.y; sm[i1] = nM.y; sw[i1] = w; swp[i1] = w * phi1; swyp[i1] = w * y * phi1;
+                dgtp[row * ld_dgtp + 2 * c + i1] = __float2bfloat16_rn(w * (agt.y - y * at.y));
             }
         }
         __syncwarp();
-        // ---- sweep 2: two j per lane share the broadcast loads of (p, m, w, w phi, w y phi)
+        // ---- sweep 2: a lane owns columns j0 = jb + lane and j1 = j0 + 32 as one fp32x2 pair
         for (int jb = 0; jb < c; jb += 64) {
             const int j0 = jb + lane, j1 = j0 + 32;
             const bool v0 = j0 < c, v1 = j1 < c;
-            const float th0 = v0 ? st[j0] : 0.f, th1 = v1 ? st[j1] : 0.f;
-            float dg0 = 0.f, a0 = 0.f, b0 = 0.f, dg1 = 0.f, a1 = 0.f, b1 = 0.f;
+            const float2 TH = make_float2(v0 ? st[j0] : 0.f, v1 ? st[j1] : 0.f);
+            float2 dg = make_float2(0.f, 0.f), sa = dg, sb = dg;
 #pragma unroll 2
             for (int i = 0; i < c; i += 4) {
                 const float4 p4 = *reinterpret_cast<const float4*>(sp + i);
@@ -321,19 +331,19 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
                 const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, qq[4] = {q4.x, q4.y, q4.z, q4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float e0 = exp2f(fmaf(pp[u], th0, -mm[u]));
-                    const float e1 = exp2f(fmaf(pp[u], th1, -mm[u]));
-                    dg0 = fmaf(ww[u], e0, dg0); a0 = fmaf(qq[u], e0, a0); b0 = fmaf(zz[u], e0, b0);
-                    dg1 = fmaf(ww[u], e1, dg1); a1 = fmaf(qq[u], e1, a1); b1 = fmaf(zz[u], e1, b1);
+                    const float2 e = ex2_pair(__ffma2_rn(TH, bcast2(pp[u]), bcast2(mm[u])));
+                    dg = __ffma2_rn(e, bcast2(ww[u]), dg);
+                    sa = __ffma2_rn(e, bcast2(qq[u]), sa);
+                    sb = __ffma2_rn(e, bcast2(zz[u]), sb);
                 }
             }
             if (v0) {
-                dgtp[row * ld_dgtp + j0] = __float2bfloat16_rn(dg0);
-                dgtp[row * ld_dgtp + c + j0] = __float2bfloat16_rn(sg[j0] * a0 - b0);
+                dgtp[row * ld_dgtp + j0] = __float2bfloat16_rn(dg.x);
+                dgtp[row * ld_dgtp + c + j0] = __float2bfloat16_rn(sg[j0] * sa.x - sb.x);
             }
             if (v1) {
-                dgtp[row * ld_dgtp + j1] = __float2bfloat16_rn(dg1);
-                dgtp[row * ld_dgtp + c + j1] = __float2bfloat16_rn(sg[j1] * a1 - b1);
+                dgtp[row * ld_dgtp + j1] = __float2bfloat16_rn(dg.y);
+                dgtp[row * ld_dgtp + c + j1] = __float2bfloat16_rn(sg[j1] * sa.y - sb.y);
             }
         }
         __syncwarp();
@@ -491,42 +501,129 @@ __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, lo
 }
 
 // pose[r, j] = sum_c drop(feat[r, c]) * w6[j, c] + b6[j]   (posenet.py:1073-1086).  One warp per row; lane owns
-// columns [lane*8, +8) of every 256-column pass and keeps its slice of the six weight rows in registers (PASSES <= 2,
-// i.e. D <= 512; wider layers read the weights from shared memory).
+// columns [lane*8, +8) of every 256-column pass.
+//  * PASSES 1, 2 (D <= 512): the lane's slice of the six weight rows lives in registers as fp32x2 pairs, the products
+//    are FFMA2 (two columns per instruction), a warp walks two rows per iteration so four 16-byte loads are in flight
+//    per lane, and the six lane-partials are reduced with an 8-shuffle transposing butterfly.
+//  * PASSES 0 (wider layers): weights from shared memory, scalar math.
 constexpr int HEAD_WARPS = 8;
-template <int PASSES>
-__global__ void __launch_bounds__(HEAD_WARPS * 32)
-head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, const uint8_t* __restrict__ keep,
+
+// Transposing butterfly: v[0..5] per lane -> every lane of quad q holds the full sum of value j(q):
+// q = lane >> 2:  0 -> 0, 1 -> 1, 2 -> 2, 4 -> 3, 5 -> 4, 6 -> 5  (quads 3 and 7 hold padding).
+__device__ __forceinline__ float head_reduce6(const float* v, int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float mine = h16 ? v[k + 3] : v[k], theirs = h16 ? v[k] : v[k + 3];
+        r[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+    }
+    r[3] = 0.f;
+    float s[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float mine = h8 ? r[k + 2] : r[k], theirs = h8 ? r[k] : r[k + 2];
+        s[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+    }
+    float t = (h4 ? s[1] : s[0]) + __shfl_xor_sync(0xffffffffu, h4 ? s[0] : s[1], 4);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+
+// PLAIN: no fp32-mode lo plane and no explicit keep bytes (the production path) -- fewer live registers.
+template <int PASSES, bool PLAIN>
+__global__ void __launch_bounds__(HEAD_WARPS * 32, PASSES > 0 ? 2 : 1)
+head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, const uint8_t* __restrict__ keep_,
                 unsigned long long seed, uint32_t thresh, int use_seed, float scale, const float* __restrict__ w6,
-                const float* __restrict__ b6, float* __restrict__ pose, const bf16* __restrict__ feat_lo) {
+                const float* __restrict__ b6, float* __restrict__ pose, const bf16* __restrict__ feat_lo_) {
+    const uint8_t* __restrict__ keep = PLAIN ? nullptr : keep_;
+    const bf16* __restrict__ feat_lo = PLAIN ? nullptr : feat_lo_;
     extern __shared__ __align__(16) float s_w[];   // [6][D], only used when PASSES == 0
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NP = PASSES > 0 ? PASSES : 1;
-    float wr[NP][6][8];
-    if (PASSES > 0) {
+    if constexpr (PASSES > 0) {
+        constexpr int NP = PASSES > 0 ? PASSES : 1;
+        float2 wr[NP][6][4];
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
             const int c = ps * 256 + lane * 8;
 #pragma unroll
             for (int j = 0; j < 6; ++j)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) wr[ps][j][q] = c < D ? __ldg(w6 + j * D + c + q) : 0.f;
+                for (int q = 0; q < 4; ++q)
+                    wr[ps][j][q] = c < D ? __ldg(reinterpret_cast<const float2*>(w6 + j * D + c + 2 * q)) : make_float2(0.f, 0.f);
+        }
+        const int quad = lane >> 2;
+        const int jout = (quad >> 2) * 3 + (quad & 3);
+        const bool writer = (lane & 3) == 0 && (quad & 3) != 3;
+        const float bj = writer ? b6[jout] : 0.f;
+        const long long stride = (long long)gridDim.x * HEAD_WARPS * 2;
+        for (long long row0 = (blockIdx.x * (long long)HEAD_WARPS + warp) * 2; row0 < rows; row0 += stride) {
+            uint4 u[2][NP], ul[2][NP];
+            uint2 k8[2][NP];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const long long row = row0 + rr < rows ? row0 + rr : row0;
+#pragma unroll
+                for (int ps = 0; ps < NP; ++ps) {
+                    const int c = ps * 256 + lane * 8;
+                    const bool ok = c < D;
+                    u[rr][ps] = ok ? __ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)) : make_uint4(0, 0, 0, 0);
+                    if (feat_lo) ul[rr][ps] = ok ? __ldg(reinterpret_cast<const uint4*>(feat_lo + row * ldf + c)) : make_uint4(0, 0, 0, 0);
+                    if (keep) k8[rr][ps] = ok ? __ldg(reinterpret_cast<const uint2*>(keep + row * D + c)) : make_uint2(0, 0);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const long long row = row0 + rr < rows ? row0 + rr : row0;
+                float2 acc[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int ps = 0; ps < NP; ++ps) {
+                    const int c = ps * 256 + lane * 8;
+                    float f[8];
+                    unpack8(u[rr][ps], f);
+                    if (feat_lo) {                                // fp32 mode: value = hi + lo
+                        float fl[8];
+                        unpack8(ul[rr][ps], fl);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) f[q] += fl[q];
+                    }
+                    if (keep) {
+                        const uint32_t kw[2] = {k8[rr][ps].x, k8[rr][ps].y};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (!((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF)) f[q] = 0.f;
+                    } else if (use_seed) {
+                        const uint32_t h0 = keep_hash4(seed, row, c >> 2), h1 = keep_hash4(seed, row, (c >> 2) + 1);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (!keep_from_hash(q < 4 ? h0 : h1, q, thresh)) f[q] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            acc[j] = __ffma2_rn(make_float2(f[2 * q], f[2 * q + 1]), wr[ps][j][q], acc[j]);
+                }
+                float v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = acc[j].x + acc[j].y;
+                const float t = head_reduce6(v, lane);
+                if (writer && row0 + rr < rows) pose[row * 6 + jout] = fmaf(t, scale, bj);
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) s_w[i] = w6[i];
-        __syncthreads();
-    }
-    const int n_pass = PASSES > 0 ? PASSES : (D + 255) / 256;
+    for (int i = threadIdx.x; i < 6 * D; i += blockDim.x) s_w[i] = w6[i];
+    __syncthreads();
+    const int n_pass = (D + 255) / 256;
     for (long long row = blockIdx.x * (long long)HEAD_WARPS + warp; row < rows; row += (long long)gridDim.x * HEAD_WARPS) {
         float acc[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int ps = 0; ps < (PASSES > 0 ? PASSES : 8); ++ps) {
-            if (ps >= n_pass) break;
+        for (int ps = 0; ps < n_pass; ++ps) {
             const int c = ps * 256 + lane * 8;
             if (c >= D) continue;
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
-            if (feat_lo) {                                    // fp32 mode: value = hi + lo
+            if (feat_lo) {
                 float fl[8];
                 unpack8(__ldg(reinterpret_cast<const uint4*>(feat_lo + row * ldf + c)), fl);
 #pragma unroll
@@ -536,112 +633,181 @@ head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, c
                 const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
                 const uint32_t kw[2] = {k8.x, k8.y};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? f[q] * scale : 0.f;
+                for (int q = 0; q < 8; ++q) if (!((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF)) f[q] = 0.f;
             } else if (use_seed) {
                 const uint32_t h0 = keep_hash4(seed, row, c >> 2), h1 = keep_hash4(seed, row, (c >> 2) + 1);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) f[q] = keep_from_hash(q < 4 ? h0 : h1, q, thresh) ? f[q] * scale : 0.f;
+                for (int q = 0; q < 8; ++q) if (!keep_from_hash(q < 4 ? h0 : h1, q, thresh)) f[q] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                if (PASSES > 0) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[j] = fmaf(f[q], wr[ps < NP ? ps : 0][j][q], acc[j]);
-                } else {
-                    const float4 w0 = *reinterpret_cast<const float4*>(s_w + j * D + c);
-                    const float4 w1 = *reinterpret_cast<const float4*>(s_w + j * D + c + 4);
-                    acc[j] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
-                              f[6] * w1.z + f[7] * w1.w;
-                }
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + j * D + c);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + j * D + c + 4);
+                acc[j] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                          f[6] * w1.z + f[7] * w1.w;
             }
         }
+        const float t = head_reduce6(acc, lane);
+        const int quad = lane >> 2;
+        if ((lane & 3) == 0 && (quad & 3) != 3) {
+            const int jout = (quad >> 2) * 3 + (quad & 3);
+            pose[row * 6 + jout] = fmaf(t, scale, b6[jout]);
+        }
+    }
+    }
+}
+
+// Backward of the head.  A block is (row phase) x (column thread); a thread owns 8 columns and walks the rows of its
+// phase inside the block's slab, accumulating dW6[j, c] = sum_r dpose[r, j] * drop(feat)[r, c] in registers as fp32x2
+// pairs (FFMA2).  Phases are folded through shared memory in a fixed order, slabs through head_bwd_reduce_kernel:
+// deterministic.
+constexpr int HEADB_THREADS = 256;
+constexpr int HEADB_ROWS_PER_BLOCK = 256;
+__global__ void __launch_bounds__(HEADB_THREADS, 2)
+head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, int ldf, long long rows,
+                int D, const uint8_t* __restrict__ keep, unsigned long long seed, uint32_t thresh,
+                int use_seed, float scale, const float* __restrict__ w6, int mask_relu,
+                bf16* __restrict__ dfeat, int lddf, float* __restrict__ dw6_part,
+                float* __restrict__ db6_part) {
+    extern __shared__ __align__(16) float hb_smem[];   // [phases-1][48][ct] + [phases][6]
+    const int ct = D >> 3;                              // column threads
+    const int phases = HEADB_THREADS / ct;
+    const int tx = threadIdx.x % ct, ty = threadIdx.x / ct;
+    const int c = tx * 8;
+    float2 gw[6][4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gw[j][q] = make_float2(0.f, 0.f);
+    float gb[6] = {0, 0, 0, 0, 0, 0};
+    if (ty < phases) {
+        float2 w[6][4];
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[j][q] = __ldg(reinterpret_cast<const float2*>(w6 + j * D + c + 2 * q));
+        const long long r0 = (long long)blockIdx.x * HEADB_ROWS_PER_BLOCK;
+        const long long r1 = min(r0 + HEADB_ROWS_PER_BLOCK, rows);
+#pragma unroll 2
+        for (long long row = r0 + ty; row < r1; row += phases) {
+            float dp[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) dp[j] = __ldg(dpose + row * 6 + j);
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
+            float km[8];
+            if (keep) {
+                const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
+                const uint32_t kw[2] = {k8.x, k8.y};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) km[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? scale : 0.f;
+            } else if (use_seed) {
+                const uint32_t h0 = keep_hash4(seed, row, c >> 2), h1 = keep_hash4(seed, row, (c >> 2) + 1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) km[q] = keep_from_hash(q < 4 ? h0 : h1, q, thresh) ? scale : 0.f;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) km[q] = 1.f;
+            }
+            float d[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float2 sacc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) sacc = __ffma2_rn(w[j][q], make_float2(dp[j], dp[j]), sacc);
+                const float2 k2 = make_float2(km[2 * q], km[2 * q + 1]);
+                const float2 dd = __fmul2_rn(sacc, k2);
+                d[2 * q] = (mask_relu && !(f[2 * q] > 0.f)) ? 0.f : dd.x;
+                d[2 * q + 1] = (mask_relu && !(f[2 * q + 1] > 0.f)) ? 0.f : dd.y;
+                const float2 fd = __fmul2_rn(make_float2(f[2 * q], f[2 * q + 1]), k2);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) gw[j][q] = __ffma2_rn(fd, make_float2(dp[j], dp[j]), gw[j][q]);
+            }
+            if (dfeat) *reinterpret_cast<uint4*>(dfeat + row * lddf + c) = pack8(d);
+            if (tx == 0) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) gb[j] += dp[j];
+            }
+        }
+    }
+    // fold the phases (fixed order)
+    float* red = hb_smem;
+    float* redb = hb_smem + (size_t)(phases - 1) * 48 * ct;
+    if (ty >= 1 && ty < phases) {
+        float* o = red + (size_t)(ty - 1) * 48 * ct;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                o[(j * 8 + 2 * q) * ct + tx] = gw[j][q].x;
+                o[(j * 8 + 2 * q + 1) * ct + tx] = gw[j][q].y;
+            }
+    }
+    if (tx == 0 && ty < phases) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) redb[ty * 6 + j] = gb[j];
+    }
+    __syncthreads();
+    if (ty == 0) {
+        for (int ph = 1; ph < phases; ++ph) {
+            const float* o = red + (size_t)(ph - 1) * 48 * ct;
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    gw[j][q].x += o[(j * 8 + 2 * q) * ct + tx];
+                    gw[j][q].y += o[(j * 8 + 2 * q + 1) * ct + tx];
+                }
+        }
+        float* o = dw6_part + (size_t)blockIdx.x * 6 * D;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+            *reinterpret_cast<float4*>(o + j * D + c) = make_float4(gw[j][0].x, gw[j][0].y, gw[j][1].x, gw[j][1].y);
+            *reinterpret_cast<float4*>(o + j * D + c + 4) = make_float4(gw[j][2].x, gw[j][2].y, gw[j][3].x, gw[j][3].y);
         }
-        if (lane < 6) {
-            float v = acc[0];
-            if (lane == 1) v = acc[1]; else if (lane == 2) v = acc[2]; else if (lane == 3) v = acc[3];
-            else if (lane == 4) v = acc[4]; else if (lane == 5) v = acc[5];
-            pose[row * 6 + lane] = v + b6[lane];
+        if (tx < 6) {
+            float sb = 0.f;
+            for (int ph = 0; ph < phases; ++ph) sb += redb[ph * 6 + tx];
+            db6_part[blockIdx.x * 6 + tx] = sb;
         }
     }
 }
 
-// Backward of the head.  Thread owns 8 columns; a block walks a contiguous row range, accumulating
-// dW6[j, c] = sum_r dpose[r, j] * drop(feat)[r, c] in registers (deterministic), partials per block.
-constexpr int HEADB_ROWS_PER_BLOCK = 64;     // short slabs => enough blocks to fill the machine; partials are reduced afterwards
-__global__ void head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, int ldf, long long rows,
-                                int D, const uint8_t* __restrict__ keep, unsigned long long seed, uint32_t thresh,
-                                int use_seed, float scale, const float* __restrict__ w6, int mask_relu,
-                                bf16* __restrict__ dfeat, int lddf, float* __restrict__ dw6_part,
-                                float* __restrict__ db6_part) {
-    const int c = threadIdx.x * 8;
-    if (c >= D) return;
-    float w[6][8];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w6 + j * D + c));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w6 + j * D + c + 4));
-        w[j][0] = w0.x; w[j][1] = w0.y; w[j][2] = w0.z; w[j][3] = w0.w;
-        w[j][4] = w1.x; w[j][5] = w1.y; w[j][6] = w1.z; w[j][7] = w1.w;
-    }
-    float gw[6][8];
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) gw[j][q] = 0.f;
-    float gb[6] = {0, 0, 0, 0, 0, 0};
-    const long long r0 = (long long)blockIdx.x * HEADB_ROWS_PER_BLOCK;
-    const long long r1 = min(r0 + HEADB_ROWS_PER_BLOCK, rows);
-    for (long long row = r0; row < r1; ++row) {
-        float dp[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) dp[j] = __ldg(dpose + row * 6 + j);
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
-        float km[8];
-        if (keep) {
-            const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
-            const uint32_t kw[2] = {k8.x, k8.y};
-#pragma unroll
-            for (int q = 0; q < 8; ++q) km[q] = ((kw[q >> 2] >> ((q & 3) * 8)) & 0xFF) ? scale : 0.f;
-        } else if (use_seed) {
-            const uint32_t h0 = keep_hash4(seed, row, c >> 2), h1 = keep_hash4(seed, row, (c >> 2) + 1);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) km[q] = keep_from_hash(q < 4 ? h0 : h1, q, thresh) ? scale : 0.f;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) km[q] = 1.f;
+// Folds the slab partials of head_bwd_kernel: columns [0, 6D) are dW6 (rows 0..2 -> dw_t, 3..5 -> dw_q), the last block
+// handles the 6 bias sums.  32 columns x 8 part-phases per block, fixed order.
+__global__ void __launch_bounds__(256)
+head_bwd_reduce_kernel(const float* __restrict__ dw_part, const float* __restrict__ db_part, int nparts, int D,
+                       float* __restrict__ dw_t, float* __restrict__ dw_q, float* __restrict__ db_t,
+                       float* __restrict__ db_q, int accumulate) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int n = 6 * D;
+    const bool bias_block = blockIdx.x == gridDim.x - 1;
+    const int col = bias_block ? lane : blockIdx.x * 32 + lane;
+    const int ncol = bias_block ? 6 : n;
+    const float* part = bias_block ? db_part : dw_part;
+    const long long stride = bias_block ? 6 : n;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (col < ncol) {
+        int b = ph;
+        for (; b + 24 < nparts; b += 32) {
+            s0 += part[(size_t)b * stride + col];
+            s1 += part[(size_t)(b + 8) * stride + col];
+            s2 += part[(size_t)(b + 16) * stride + col];
+            s3 += part[(size_t)(b + 24) * stride + col];
         }
-        float d[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) s = fmaf(dp[j], w[j][q], s);
-            d[q] = s * km[q];
-            if (mask_relu && !(f[q] > 0.f)) d[q] = 0.f;
-            const float fd = f[q] * km[q];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) gw[j][q] = fmaf(dp[j], fd, gw[j][q]);
-        }
-        if (dfeat) *reinterpret_cast<uint4*>(dfeat + row * lddf + c) = pack8(d);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) gb[j] += dp[j];
-        }
+        for (; b < nparts; b += 8) s0 += part[(size_t)b * stride + col];
     }
-    float* o = dw6_part + (size_t)blockIdx.x * 6 * D;
+    red[ph][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ph == 0 && col < ncol) {
+        float s = red[0][lane];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        *reinterpret_cast<float4*>(o + j * D + c) = make_float4(gw[j][0], gw[j][1], gw[j][2], gw[j][3]);
-        *reinterpret_cast<float4*>(o + j * D + c + 4) = make_float4(gw[j][4], gw[j][5], gw[j][6], gw[j][7]);
-    }
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) db6_part[blockIdx.x * 6 + j] = gb[j];
+        for (int k = 1; k < 8; ++k) s += red[k][lane];
+        float* o;
+        if (bias_block) o = col < 3 ? db_t + col : db_q + (col - 3);
+        else o = col < 3 * D ? dw_t + col : dw_q + (col - 3 * D);
+        *o = accumulate ? *o + s : s;
     }
 }
 
@@ -667,6 +833,25 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits,
     }
 }
 
+// Batched form: blockIdx.y picks the descriptor; always accumulating.
+__global__ void __launch_bounds__(256)
+reduce_splits_batch_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
+    const rpg_reduce_desc_t& d = batch.d[blockIdx.y];
+    const long long n = (long long)d.rows * d.cols;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+        float s0 = 0.f, s1 = 0.f;
+        int b = 0;
+        for (; b + 1 < d.splits; b += 2) {
+            s0 += d.part[(size_t)b * d.stride + i];
+            s1 += d.part[(size_t)(b + 1) * d.stride + i];
+        }
+        if (b < d.splits) s0 += d.part[(size_t)b * d.stride + i];
+        float* o = d.out + (size_t)r * d.ldo + c;
+        *o += s0 + s1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // compute_RP (posenet.py:1021-1031) + L1 sums of PoseNetCriterion (criterion.py:51-52) + sign gradient
 // ------------------------------------------------------------------------------------------------
@@ -674,9 +859,14 @@ constexpr int LOSS_THREADS = 256;
 __global__ void __launch_bounds__(LOSS_THREADS)
 pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses, const int* __restrict__ tsrc,
                  const int* __restrict__ tdst, long long Et, int N, int Ep, const float* __restrict__ grad_scale,
+                 const float* __restrict__ sax, const float* __restrict__ saq,
                  float* __restrict__ target, float* __restrict__ dpred, float* __restrict__ partial) {
     float st = 0.f, sq = 0.f;
-    const float gs_t = grad_scale ? grad_scale[0] : 1.f, gs_q = grad_scale ? grad_scale[1] : 1.f;
+    float gs_t = grad_scale ? grad_scale[0] : 1.f, gs_q = grad_scale ? grad_scale[1] : 1.f;
+    if (sax) {   // criterion.py:55-57: d loss / d pred = exp(-s) * sign / (3 Et)
+        gs_t = (float)(exp(-(double)sax[0]) / (3.0 * (double)Et));
+        gs_q = (float)(exp(-(double)saq[0]) / (3.0 * (double)Et));
+    }
     for (long long e = blockIdx.x * (long long)LOSS_THREADS + threadIdx.x; e < Et; e += (long long)gridDim.x * LOSS_THREADS) {
         const long long g = e / Ep;
         const int k = (int)(e - g * Ep);
@@ -706,11 +896,27 @@ pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses
         partial[blockIdx.x * 2 + 1] = b;
     }
 }
-__global__ void pose_loss_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ sums) {
+// sums[0..1] = L1 sums; with sax/saq also the learned-weight combination of criterion.py:55-57:
+// sums[2..6] = loss, t_loss, q_loss, d loss/d sax, d loss/d saq.
+__global__ void pose_loss_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ sums,
+                                       const float* __restrict__ sax, const float* __restrict__ saq, long long Et) {
+    float a = 0.f, b = 0.f;                                  // one warp, fixed order
+    for (int i = threadIdx.x; i < nblocks; i += 32) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        float a = 0.f, b = 0.f;
-        for (int i = 0; i < nblocks; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
         sums[0] = a; sums[1] = b;
+        if (sax) {
+            const float n = 3.f * (float)Et;
+            const float tl = a / n, ql = b / n;
+            const float ex = (float)exp(-(double)sax[0]), eq = (float)exp(-(double)saq[0]);
+            sums[2] = ex * tl + sax[0] + eq * ql + saq[0];
+            sums[3] = tl; sums[4] = ql;
+            sums[5] = 1.f - ex * tl; sums[6] = 1.f - eq * ql;
+        }
     }
 }
 
@@ -936,23 +1142,26 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
     const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
     const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
-    const int grid = grid_for(rows, HEAD_WARPS, 148 * 8);
+    const int grid = grid_for((rows + 1) / 2, HEAD_WARPS, 148 * 8);
     const bf16* f = reinterpret_cast<const bf16*>(feat);
     const bf16* fl = reinterpret_cast<const bf16*>(feat_lo);
     cudaStream_t st = as_stream(stream);
+    const bool plain = !keep && !fl;
     if (D <= 256) {
-        head_fwd_kernel<1><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        if (plain) head_fwd_kernel<1, true><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        else head_fwd_kernel<1, false><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     } else if (D <= 512) {
-        head_fwd_kernel<2><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        if (plain) head_fwd_kernel<2, true><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        else head_fwd_kernel<2, false><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     } else {
         const size_t smem = (size_t)6 * D * sizeof(float);
         if (D > 2048) return set_error(RPG_E_UNSUPPORTED, "head_fwd: D > 2048");
         static size_t configured = 48 * 1024;
         if (smem > configured) {
-            cudaFuncSetAttribute(head_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(head_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
-        head_fwd_kernel<0><<<grid, HEAD_WARPS * 32, smem, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        head_fwd_kernel<0, false><<<grid, HEAD_WARPS * 32, smem, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     }
     return check_launch("head_fwd_kernel");
 }
@@ -973,37 +1182,51 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
     const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
     const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
-    const int threads = ((D / 8 + 31) / 32) * 32;
+    const int ct = D / 8;
+    if (ct > HEADB_THREADS) return set_error(RPG_E_UNSUPPORTED, "head_bwd: D > 2048");
+    const int phases = HEADB_THREADS / ct;
+    const size_t smem = ((size_t)(phases - 1) * 48 * ct + (size_t)phases * 6) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
     cudaStream_t s = as_stream(stream);
-    head_bwd_kernel<<<blocks, threads, 0, s>>>(dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed, thresh,
-                                               use_seed, scale, w6, mask_relu, reinterpret_cast<bf16*>(dfeat), lddf, dw_part,
-                                               db_part);
+    head_bwd_kernel<<<blocks, HEADB_THREADS, smem, s>>>(dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed,
+                                                        thresh, use_seed, scale, w6, mask_relu,
+                                                        reinterpret_cast<bf16*>(dfeat), lddf, dw_part, db_part);
     int rc = check_launch("head_bwd_kernel");
     if (rc) return rc;
     // rows 0..2 -> translation head (fc_xyz*), rows 3..5 -> rotation head (fc_wpqr*)
-    reduce_partials_wide_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(dw_part, blocks, 6 * (long long)D, 3 * D, dw_t, accumulate);
-    if ((rc = check_launch("reduce_partials_wide_kernel"))) return rc;
-    reduce_partials_wide_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(dw_part + 3 * D, blocks, 6 * (long long)D, 3 * D, dw_q, accumulate);
-    if ((rc = check_launch("reduce_partials_wide_kernel"))) return rc;
-    reduce_partials_wide_kernel<<<1, 256, 0, s>>>(db_part, blocks, 6, 3, db_t, accumulate);
-    if ((rc = check_launch("reduce_partials_wide_kernel"))) return rc;
-    reduce_partials_wide_kernel<<<1, 256, 0, s>>>(db_part + 3, blocks, 6, 3, db_q, accumulate);
-    return check_launch("reduce_partials_wide_kernel");
+    head_bwd_reduce_kernel<<<(6 * D + 31) / 32 + 1, 256, 0, s>>>(dw_part, db_part, blocks, D, dw_t, dw_q, db_t, db_q, accumulate);
+    return check_launch("head_bwd_reduce_kernel");
 }
 
 int64_t rpg_pose_loss_ws_floats(int64_t Et) { return 2 * (int64_t)grid_for(Et, LOSS_THREADS, 1024); }
 
-int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* grad_scale,
-                  float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream) {
+static int pose_loss_launch(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* grad_scale,
+                            const float* sax, const float* saq,
+                            float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream) {
     if (!pred || !poses || !graph || !sums || !ws || Et <= 0) return set_error(RPG_E_ARG, "pose_loss: bad arguments");
     const int blocks = grid_for(Et, LOSS_THREADS, 1024);
     cudaStream_t s = as_stream(stream);
     pose_loss_kernel<<<blocks, LOSS_THREADS, 0, s>>>(pred, poses, graph->src, graph->dst, Et, graph->N, graph->Ep, grad_scale,
-                                                     target, dpred, ws);
+                                                     sax, saq, target, dpred, ws);
     int rc = check_launch("pose_loss_kernel");
     if (rc) return rc;
-    pose_loss_final_kernel<<<1, 32, 0, s>>>(ws, blocks, sums);
+    pose_loss_final_kernel<<<1, 32, 0, s>>>(ws, blocks, sums, sax, saq, Et);
     return check_launch("pose_loss_final_kernel");
+}
+
+int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* grad_scale,
+                  float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream) {
+    return pose_loss_launch(pred, poses, graph, Et, grad_scale, nullptr, nullptr, target, sums, dpred, ws, stream);
+}
+
+int rpg_pose_criterion(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* sax,
+                       const float* saq, float* target, float* out7, float* dpred, float* ws, rpg_stream_t stream) {
+    if (!sax || !saq) return set_error(RPG_E_ARG, "pose_criterion: sax/saq must be device pointers");
+    return pose_loss_launch(pred, poses, graph, Et, nullptr, sax, saq, target, out7, dpred, ws, stream);
 }
 
 int64_t rpg_colsum_scratch_floats(int64_t rows, int cols) {
@@ -1030,6 +1253,20 @@ int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, in
     reduce_splits_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, as_stream(stream)>>>(partial, splits, split_stride, rows,
                                                                                               cols, out, ldo, accumulate);
     return check_launch("reduce_splits_kernel");
+}
+
+int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream) {
+    if (!batch || batch->n < 1 || batch->n > RPG_REDUCE_BATCH_MAX) return set_error(RPG_E_ARG, "reduce_splits_batch: bad arguments");
+    long long most = 1;
+    for (int i = 0; i < batch->n; ++i) {
+        const rpg_reduce_desc_t& d = batch->d[i];
+        if (!d.part || !d.out || d.splits < 1 || d.rows <= 0 || d.cols <= 0)
+            return set_error(RPG_E_ARG, "reduce_splits_batch: bad descriptor");
+        most = std::max(most, (long long)d.rows * d.cols);
+    }
+    dim3 grid((unsigned)grid_for(most, 256, 1024), (unsigned)batch->n);
+    reduce_splits_batch_kernel<<<grid, 256, 0, as_stream(stream)>>>(*batch);
+    return check_launch("reduce_splits_batch_kernel");
 }
 
 }  // extern "C"

@@ -58,7 +58,7 @@ static int wgrad_partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, 
     g.block_n = block_n;
     const int tiles = ((M + 127) / 128) * ((N + block_n - 1) / block_n);
     const long long kb = (R + 63) / 64;
-    long long splits = (2LL * sm_count + tiles - 1) / tiles;          // ~2 waves of work items
+    long long splits = sm_count / tiles;                              // one wave of work items: fp32 partials cost HBM traffic
     if (splits > kb) splits = kb;
     if (splits < 1) splits = 1;
     const long long per = (kb + splits - 1) / splits;
@@ -91,6 +91,53 @@ static int sm_count_cached() {
     }
     return n;
 }
+
+// Weight gradients of one layer backward: every TN launch writes its split partials into its own slice of the workspace
+// and queues the fold; all folds run as ONE launch at the end (fixed order per element => deterministic).
+struct WgradQueue {
+    float* ws;
+    size_t off;
+    int sms;
+    cudaStream_t s;
+    rpg_reduce_batch_t batch;
+    WgradQueue(float* ws_, int sms_, cudaStream_t s_) : ws(ws_), off(0), sms(sms_), s(s_) { batch.n = 0; }
+    int add(const float* part, int splits, long long stride, int rows, int cols, float* out, int ldo) {
+        if (batch.n == RPG_REDUCE_BATCH_MAX) {
+            int rc = flush();
+            if (rc) return rc;
+        }
+        rpg_reduce_desc_t& d = batch.d[batch.n++];
+        d.part = part; d.out = out; d.stride = stride; d.splits = splits; d.rows = rows; d.cols = cols; d.ldo = ldo;
+        return 0;
+    }
+    // dW (+)= A^T B over R rows, optionally bias (+)= colsum(A); partials only, fold queued
+    int wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* out, int ldo,
+              float* bias = nullptr) {
+        int splits = 0;
+        float* p = ws + off;
+        int rc = wgrad_partials(A, lda, M, B, ldb, N, R, p, sms, s, &splits, bias != nullptr);
+        if (rc) return rc;
+        off += ((size_t)splits * M * N + (bias ? (size_t)splits * M : 0) + 63) & ~(size_t)63;
+        if ((rc = add(p, splits, (long long)M * N, M, N, out, ldo))) return rc;
+        if (bias) rc = add(p + (size_t)splits * M * N, splits, M, 1, M, bias, M);
+        return rc;
+    }
+    // partials of a stacked product whose row blocks go to different parameters: the caller queues the folds
+    int partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, bool with_colsum,
+                 float** part, int* splits) {
+        *part = ws + off;
+        int rc = wgrad_partials(A, lda, M, B, ldb, N, R, *part, sms, s, splits, with_colsum);
+        if (rc) return rc;
+        off += ((size_t)*splits * M * N + (with_colsum ? (size_t)*splits * M : 0) + 63) & ~(size_t)63;
+        return 0;
+    }
+    int flush() {
+        if (!batch.n) return 0;
+        int rc = rpg_reduce_splits_batch(&batch, (rpg_stream_t)s);
+        batch.n = 0;
+        return rc;
+    }
+};
 
 }  // namespace rpg
 
@@ -308,10 +355,12 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
 
 int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt) {
     (void)Et; (void)Nt;
-    // largest split workspace: (2 * sm_count / tiles + 1) splits of a [D, 3D] partial; bound with 2*148+tiles items
-    // splits * M * N <= 2 * sm_count * (128 * 256) + M * N, with M * N <= 3 D^2; sized for up to 256 SMs;
-    // + [splits, M] column sums (splits <= 2 * sm_count, M <= 3 D)
-    return 2LL * 256 * 128 * 256 + 3LL * D * D + 2LL * 256 * 3 * D;
+    // 11 TN launches per layer backward, each with its own slice: splits * tiles <= sm_count, so the dW partials of one
+    // launch fit sm_count * 128 * 256 floats (+ M * N when a single split is forced, M * N <= 3 D^2), plus [splits, M]
+    // column sums (M <= 3 D) and the 64-float rounding.  Sized for up to 160 SMs.
+    int sms = sm_count_cached();
+    if (sms <= 0 || sms > 160) sms = 160;
+    return 11LL * ((long long)sms * 128 * 256 + 3LL * D * D + (long long)sms * 3 * D + 64);
 }
 
 int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg_layer_acts_t* t,
@@ -400,48 +449,49 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     RPG_TRY(gemm_launch(&g, s));
 
     // ---- weight gradients (fp32, accumulated into the reference's state_dict layout)
-    float* ws = b->split_ws;
+    WgradQueue q(b->split_ws, sms, s);
+    float* part = nullptr;
     int splits = 0;
     // edge_model.edge_mlp.2: dW = de'_tot^T h1 ; db = colsum(de'_tot)
-    RPG_TRY(wgrad(de_tot, D, D, t->h1, D, D, Et, ws, b->g_edge2_w, D, sms, s, b->g_edge2_b));
+    RPG_TRY(q.wgrad(de_tot, D, D, t->h1, D, D, Et, b->g_edge2_w, D, b->g_edge2_b));
     // edge_model.edge_mlp.0, edge columns [2D,3D): dW = dh1^T e ; db = colsum(dh1)
-    RPG_TRY(wgrad(b->dh1, D, D, t->e, D, D, Et, ws, b->g_edge0_w + 2 * D, 3 * D, sms, s, b->g_edge0_b));
+    RPG_TRY(q.wgrad(b->dh1, D, D, t->e, D, D, Et, b->g_edge0_w + 2 * D, 3 * D, b->g_edge0_b));
     // node-side blocks in one launch: dP^T x = [edge_mlp.0[:,0:D]; edge_mlp.0[:,D:2D]; mlp.0[:,0:D]]
     {
         const int Mp = have_out ? 3 * D : 2 * D;
-        RPG_TRY(wgrad_partials(b->dP, 3 * D, Mp, t->x, D, D, Nt, ws, sms, s, &splits));
+        RPG_TRY(q.partials(b->dP, 3 * D, Mp, t->x, D, D, Nt, false, &part, &splits));
         const long long stride = (long long)Mp * D;
-        RPG_TRY(rpg_reduce_splits(ws, splits, stride, D, D, b->g_edge0_w, 3 * D, 1, stream));
-        RPG_TRY(rpg_reduce_splits(ws + (size_t)D * D, splits, stride, D, D, b->g_edge0_w + D, 3 * D, 1, stream));
-        if (have_out)
-            RPG_TRY(rpg_reduce_splits(ws + 2 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w, 2 * D, 1, stream));
+        RPG_TRY(q.add(part, splits, stride, D, D, b->g_edge0_w, 3 * D));
+        RPG_TRY(q.add(part + (size_t)D * D, splits, stride, D, D, b->g_edge0_w + D, 3 * D));
+        if (have_out) RPG_TRY(q.add(part + 2 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w, 2 * D));
     }
     if (have_out) {
         // mlp.2: dW = dm^T h2 ; mlp.0 edge columns [D,2D): dW = dh2^T e'
-        RPG_TRY(wgrad(b->dm, D, D, t->h2, D, D, Et, ws, b->g_mlp2_w, D, sms, s, b->g_mlp2_b));
-        RPG_TRY(wgrad(b->dh2, D, D, t->e_new, D, D, Et, ws, b->g_mlp0_w + D, 2 * D, sms, s, b->g_mlp0_b));
-        // att.g / theta / phi: one launch dgtp^T m [3c, D], three reductions ; biases = colsum(dgtp)
-        RPG_TRY(wgrad_partials(b->dgtp, c3p, c3, t->m, D, D, Et, ws, sms, s, &splits, /*with_colsum=*/true));
+        RPG_TRY(q.wgrad(b->dm, D, D, t->h2, D, D, Et, b->g_mlp2_w, D, b->g_mlp2_b));
+        RPG_TRY(q.wgrad(b->dh2, D, D, t->e_new, D, D, Et, b->g_mlp0_w + D, 2 * D, b->g_mlp0_b));
+        // att.g / theta / phi: one launch dgtp^T m [3c, D], three folds ; biases = colsum(dgtp)
+        RPG_TRY(q.partials(b->dgtp, c3p, c3, t->m, D, D, Et, true, &part, &splits));
         {
             const long long stride = (long long)c3 * D;
-            RPG_TRY(rpg_reduce_splits(ws, splits, stride, c, D, b->g_att_g_w, D, 1, stream));
-            RPG_TRY(rpg_reduce_splits(ws + (size_t)c * D, splits, stride, c, D, b->g_att_theta_w, D, 1, stream));
-            RPG_TRY(rpg_reduce_splits(ws + 2 * (size_t)c * D, splits, stride, c, D, b->g_att_phi_w, D, 1, stream));
-            const float* cs = ws + (size_t)splits * c3 * D;            // [splits, 3c] column sums of dgtp
-            RPG_TRY(rpg_reduce_splits(cs, splits, c3, 1, c, b->g_att_g_b, c, 1, stream));
-            RPG_TRY(rpg_reduce_splits(cs + c, splits, c3, 1, c, b->g_att_theta_b, c, 1, stream));
-            RPG_TRY(rpg_reduce_splits(cs + 2 * c, splits, c3, 1, c, b->g_att_phi_b, c, 1, stream));
+            RPG_TRY(q.add(part, splits, stride, c, D, b->g_att_g_w, D));
+            RPG_TRY(q.add(part + (size_t)c * D, splits, stride, c, D, b->g_att_theta_w, D));
+            RPG_TRY(q.add(part + 2 * (size_t)c * D, splits, stride, c, D, b->g_att_phi_w, D));
+            const float* cs = part + (size_t)splits * c3 * D;            // [splits, 3c] column sums of dgtp
+            RPG_TRY(q.add(cs, splits, c3, 1, c, b->g_att_g_b, c));
+            RPG_TRY(q.add(cs + c, splits, c3, 1, c, b->g_att_theta_b, c));
+            RPG_TRY(q.add(cs + 2 * c, splits, c3, 1, c, b->g_att_phi_b, c));
         }
         // att.W: dW = sum_e dz[e]^T y[e] = dan^T ysum with ysum[n] = sum_{in-edges(n)} y[e];
         //        db = sum_e dz[e] = sum_n indeg(n) * dan[n]
         RPG_TRY(rpg_edge_to_node_sum(t->y, cp, gr, cp, 0, b->ysum, cp, stream));
-        RPG_TRY(wgrad(b->dan, D, D, b->ysum, cp, c, Nt, ws, b->g_att_W_w, c, sms, s));
+        RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
         RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
         // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
-        RPG_TRY(wgrad(b->d_out, D, D, t->h3, D, D, Nt, ws, b->g_upd2_w, D, sms, s, b->g_upd2_b));
-        RPG_TRY(wgrad(b->dh3, D, D, t->x, D, D, Nt, ws, b->g_upd0_w, 2 * D, sms, s, b->g_upd0_b));
-        RPG_TRY(wgrad(b->dh3, D, D, t->a, D, D, Nt, ws, b->g_upd0_w + D, 2 * D, sms, s));
+        RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));
+        RPG_TRY(q.wgrad(b->dh3, D, D, t->x, D, D, Nt, b->g_upd0_w, 2 * D, b->g_upd0_b));
+        RPG_TRY(q.wgrad(b->dh3, D, D, t->a, D, D, Nt, b->g_upd0_w + D, 2 * D));
     }
+    RPG_TRY(q.flush());
     return 0;
 }
 

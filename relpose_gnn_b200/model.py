@@ -263,19 +263,14 @@ class _PoseLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, poses, graph, sax, saq):
         pred = pred.float().contiguous()
-        n = 3.0 * pred.size(0)
-        scale = torch.cat([torch.exp(-sax.detach()), torch.exp(-saq.detach())]).float() / n
-        sums, _, dsign = ops.pose_loss(pred, poses, graph, grad_scale=scale, want_grad=True)
-        t_loss, q_loss = sums[0] / n, sums[1] / n
-        loss = torch.exp(-sax) * t_loss + sax + torch.exp(-saq) * q_loss + saq
-        ctx.save_for_backward(dsign, t_loss, q_loss, sax, saq)
-        return loss.reshape(1), t_loss, q_loss
+        out7, dpred = ops.pose_criterion(pred, poses, graph, sax.detach().float().contiguous(),
+                                         saq.detach().float().contiguous())
+        ctx.save_for_backward(dpred, out7)
+        return out7[2:3], out7[3], out7[4]
 
     @staticmethod
     def backward(ctx, g_loss, g_t, g_q):
-        dsign, t_loss, q_loss, sax, saq = ctx.saved_tensors
+        dpred, out7 = ctx.saved_tensors
         g = g_loss.reshape(())
-        d_pred = dsign * g
-        d_sax = (g * (1.0 - torch.exp(-sax) * t_loss)).reshape(1)
-        d_saq = (g * (1.0 - torch.exp(-saq) * q_loss)).reshape(1)
-        return d_pred, None, None, d_sax, d_saq
+        d_s = out7[5:7] * g
+        return dpred * g, None, None, d_s[0:1], d_s[1:2]

@@ -280,6 +280,19 @@ def pose_loss(pred, poses, graph, grad_scale=None, want_target=False, want_grad=
     return sums, target, dpred
 
 
+def pose_criterion(pred, poses, graph, sax, saq):
+    """criterion.py:42-60 in two launches: returns (out7 = [sum_t, sum_q, loss, t_loss, q_loss, dloss/dsax, dloss/dsaq],
+    dpred = dloss/dpred); sax/saq are 1-element fp32 device tensors."""
+    lib = _lib.load()
+    Et = pred.size(0)
+    ws = torch.empty(lib.rpg_pose_loss_ws_floats(Et), dtype=torch.float32, device=pred.device)
+    out7 = torch.empty(7, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty(Et, 6, dtype=torch.float32, device=pred.device)
+    check(lib.rpg_pose_criterion(pred.data_ptr(), poses.data_ptr(), graph.byref(), Et, sax.data_ptr(), saq.data_ptr(), None,
+                                 out7.data_ptr(), dpred.data_ptr(), ws.data_ptr(), _stream(pred)), "rpg_pose_criterion")
+    return out7, dpred
+
+
 def colsum(v, out, cols=None, row_w=None, accumulate=True):
     lib = _lib.load()
     rows = v.size(0)
