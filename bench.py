@@ -201,10 +201,32 @@ def run_ours(args):
             loss, t_loss, q_loss = crit(pe, poses, ei)
             loss.backward()
             bucket.allreduce()
-            return loss.item() if read_back else loss
+            return loss
         with torch.no_grad():
             pn, pe, _ = model(x, ei)
-        return pe.cpu() if read_back else pe
+        return pe
+
+    # e2e leg: the loop a user writes with the package's own feed (relpose_gnn_b200.feed): every step copies its
+    # inputs host -> device from pinned memory (on a copy stream, overlapping the previous step's kernels) and reads its
+    # result back (training: the loss, through a pinned slot read one step later; inference: the edge poses).
+    feeder = rpg.DeviceFeeder(dev)
+    readback = rpg.ScalarReadback(1 if train else G * N * (N - 1) * 6)
+
+    def e2e_loop(n_steps):
+        results = []
+        feeder.stage(x_host, poses_host)
+        for i in range(n_steps):
+            x, poses = feeder.take()
+            out = step(x, poses, True)
+            feeder.release()
+            if i + 1 < n_steps:          # staged after this step's own small uploads are queued: they go first on the copy engine
+                feeder.stage(x_host, poses_host)
+            if readback.full():
+                results.append(readback.pop())
+            readback.push(out.float())
+        while readback.pending:
+            results.append(readback.pop())
+        assert len(results) == n_steps and all(bool(torch.isfinite(r).all()) for r in results)
 
     def timed(n_steps, e2e):
         if world > 1:
@@ -212,12 +234,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for _ in range(n_steps):
-            if e2e:
-                x = x_host.to(dev, non_blocking=True)
-                poses = poses_host.to(dev, non_blocking=True)
-                step(x, poses, True)
-            else:
+        if e2e:
+            e2e_loop(n_steps)
+        else:
+            for _ in range(n_steps):
                 step(x_dev, poses_dev, False)
         ev1.record()
         torch.cuda.synchronize()
@@ -274,7 +294,9 @@ def run_ours(args):
                        "parallelism": f"dp{world} over graphs", "l2": "activations per step (>1 GB) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + poses_host.numel() * 4,
-                    "d2h_bytes_per_step": 4 if train else G * 2 * int(np.mean([m.sum() for m in masks[:4]])) * 6 * 4},
+                    "d2h_bytes_per_step": 4 if train else G * 2 * int(np.mean([m.sum() for m in masks[:4]])) * 6 * 4,
+                    "pipeline": "relpose_gnn_b200.DeviceFeeder: pinned H2D of step i+1 on a copy stream under step i; "
+                                "result read back through a pinned slot one step later"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<NT|TN> (tcgen05)",

@@ -59,6 +59,10 @@ int rpg_device_sm_count(int device, int* sm_count);
  * Graph structure
  * ---------------------------------------------------------------------------------------- */
 
+/* Writes n int32 words from HOST memory (pageable is fine) to device memory on `stream`; the words travel as kernel
+ * parameters, so the call neither synchronises nor uses a copy engine.  For the per-step graph template tables. */
+int rpg_upload_words(int32_t* dst, const int32_t* src_host, int64_t n, rpg_stream_t stream);
+
 /* Checks that edge_index [2, Et] (int64, device) is G copies of one per-graph template with node
  * offset g*N, i.e. what PyG batching of the reference datasets produces (train.py:24,132), and
  * extracts the template of graph 0 into tmpl_src/tmpl_dst [Ep] (int32, device).

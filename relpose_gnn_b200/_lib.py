@@ -122,6 +122,7 @@ SIGNATURES = {
     "rpg_layer_fwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs), P]),
     "rpg_layer_bwd_ws_floats": (I64, [I, I64, I64]),
     "rpg_reduce_splits_batch": (I, [P, P]),
+    "rpg_upload_words": (I, [P, P, I64, P]),
     "rpg_layer_bwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs),
                           C.POINTER(LayerGrads), P]),
 }

@@ -37,6 +37,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // ------------------------------------------------------------------------------------------------
 __global__ void validate_edge_index_kernel(const long long* __restrict__ ei, long long Et, int G, int N, int Ep,
                                            int* __restrict__ tsrc, int* __restrict__ tdst, int* __restrict__ bad) {
+    pdl_prologue();
     int local_bad = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Et; i += (long long)gridDim.x * blockDim.x) {
         const long long g = i / Ep;
@@ -53,6 +54,7 @@ __global__ void validate_edge_index_kernel(const long long* __restrict__ ei, lon
 // ((p*g+i) / Ep) * N + endpoint[(p*g+i) % Ep].  One thread per (tile row, 8 columns).
 __global__ void selection_patterns_kernel(const int* __restrict__ endpoint, int Ep, int N, int g, int npat,
                                           bf16* __restrict__ sel) {
+    pdl_prologue();
     const int total = npat * 128 * 8;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int row = t >> 3, c8 = (t & 7) << 3;
@@ -73,6 +75,7 @@ __global__ void selection_patterns_kernel(const int* __restrict__ endpoint, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ src, int ld_src, int r0, int c0, int rows, int cols,
                                    bf16* __restrict__ dst, int ld_dst, int transpose) {
+    pdl_prologue();
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // bx: column block, by: row block (source window coords)
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -94,6 +97,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int ld_src, in
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+    pdl_prologue();
     const long long stride = (long long)gridDim.x * blockDim.x * 8;
     for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
         if (i + 8 <= n) {
@@ -107,6 +111,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
     }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+    pdl_prologue();
     const long long stride = (long long)gridDim.x * blockDim.x * 8;
     for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
         if (i + 8 <= n) {
@@ -122,6 +127,7 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 
 // fp32 mode: v -> (hi, lo) = (bf16(v), bf16(v - hi)) and back
 __global__ void cast_f32_split_kernel(const float* __restrict__ src, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n) {
+    pdl_prologue();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = src[i];
         const bf16 h = __float2bfloat16_rn(v);
@@ -130,12 +136,14 @@ __global__ void cast_f32_split_kernel(const float* __restrict__ src, bf16* __res
     }
 }
 __global__ void split_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ dst, long long n) {
+    pdl_prologue();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
 }
 // window of an fp32 weight -> low plane bf16(w - float(bf16(w)))   (the high plane is pack_weight_kernel's output)
 __global__ void pack_weight_lo_kernel(const float* __restrict__ src, int ld_src, int r0, int c0, int rows, int cols,
                                       bf16* __restrict__ dst, int ld_dst) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c < cols && r < rows) {
         const float v = src[(size_t)(r0 + r) * ld_src + c0 + c];
@@ -165,6 +173,7 @@ template <int C_MAX, bool AUX>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy,
                      bf16* __restrict__ y_lo, float* __restrict__ aux) {
+    pdl_prologue();
     __shared__ __align__(16) float s_g[ATT_WARPS][C_MAX];
     __shared__ __align__(16) float s_t[ATT_WARPS][C_MAX];
     __shared__ __align__(16) float s_gt[AUX ? ATT_WARPS : 1][AUX ? C_MAX : 4];
@@ -239,6 +248,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dyn, int ld_dyn,
                      const int* __restrict__ tdst, int Ep, int Nn, long long Et, int c,
                      bf16* __restrict__ dgtp, int ld_dgtp, const float* __restrict__ aux) {
+    pdl_prologue();
     extern __shared__ __align__(16) float att_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* base = att_smem + (size_t)warp * 8 * c;
@@ -355,18 +365,21 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
 // fixed order, one thread per 8 feature columns.
 //   out[g*N+n, c] = scale[n] * sum_{k in csr(n)} v[g*Ep+k, c] * (mask ? mask[g*Ep+k, c] > 0 : 1)
 // ------------------------------------------------------------------------------------------------
+template <typename I>   // index type of the flattened (row, column-group) space: 32-bit whenever it fits (cheap divisions)
 __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf16* __restrict__ mask, int ldm,
                                    const int* __restrict__ ptr, const int* __restrict__ idx,
                                    const float* __restrict__ scale, long long Nt, int N, int Ep, int D,
                                    bf16* __restrict__ out, int ldo, const bf16* __restrict__ v_lo,
                                    bf16* __restrict__ out_lo) {
+    pdl_prologue();
     const int tpr = D >> 3;                                   // threads per row
-    const long long total = Nt * tpr;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t / tpr;
-        const int c = (int)(t - row * tpr) << 3;
-        const long long g = row / N;
-        const int n = (int)(row - g * N);
+    const I total = (I)Nt * (I)tpr;
+    for (I t = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; t < total; t += (I)gridDim.x * (I)blockDim.x) {
+        const I row_i = t / (I)tpr;
+        const int c = (int)(t - row_i * (I)tpr) << 3;
+        const I g_i = row_i / (I)N;
+        const int n = (int)(row_i - g_i * (I)N);
+        const long long row = (long long)row_i, g = (long long)g_i;
         const int k0 = __ldg(ptr + n), k1 = __ldg(ptr + n + 1);
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int kb = k0; kb < k1; kb += 4) {                 // 4 independent row loads in flight per thread
@@ -415,16 +428,19 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
 }
 
 // e0 = relu(pmin[node(min(s,t))] + pmax[node(max(s,t))] + bias)      (posenet.py:1014-1017, 1053-1055)
+template <typename I>
 __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, const float* __restrict__ bias,
                                      const int* __restrict__ tsrc, const int* __restrict__ tdst, long long Et, int N,
                                      int Ep, int D, bf16* __restrict__ e0, int lde, uint8_t* __restrict__ bits) {
+    pdl_prologue();
     const int tpr = D >> 3;
-    const long long total = Et * tpr;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t / tpr;
-        const int c = (int)(t - row * tpr) << 3;
-        const long long g = row / Ep;
-        const int k = (int)(row - g * Ep);
+    const I total = (I)Et * (I)tpr;
+    for (I t = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; t < total; t += (I)gridDim.x * (I)blockDim.x) {
+        const I row_i = t / (I)tpr;
+        const int c = (int)(t - row_i * (I)tpr) << 3;
+        const I g_i = row_i / (I)Ep;
+        const int k = (int)(row_i - g_i * (I)Ep);
+        const long long row = (long long)row_i, g = (long long)g_i;
         const int s = __ldg(tsrc + k), d = __ldg(tdst + k);
         const long long nlo = g * N + min(s, d), nhi = g * N + max(s, d);
         float a[8], b[8];
@@ -449,6 +465,7 @@ __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, cons
 __global__ void edge_init_fwd_f32_kernel(const float* __restrict__ pmm, int ldp, const float* __restrict__ bias,
                                          const int* __restrict__ tsrc, const int* __restrict__ tdst, long long Et, int N,
                                          int Ep, int D, bf16* __restrict__ e_hi, bf16* __restrict__ e_lo, int lde) {
+    pdl_prologue();
     const int tpr = D >> 2;
     const long long total = Et * tpr;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -492,6 +509,7 @@ __device__ __forceinline__ bool keep_from_hash(uint32_t h, int q, uint32_t thres
 
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long rows, int D,
                                     uint8_t* __restrict__ keep) {
+    pdl_prologue();
     const long long total = rows * D;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D;
@@ -537,6 +555,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, PASSES > 0 ? 2 : 1)
 head_fwd_kernel(const bf16* __restrict__ feat, int ldf, long long rows, int D, const uint8_t* __restrict__ keep_,
                 unsigned long long seed, uint32_t thresh, int use_seed, float scale, const float* __restrict__ w6,
                 const float* __restrict__ b6, float* __restrict__ pose, const bf16* __restrict__ feat_lo_) {
+    pdl_prologue();
     const uint8_t* __restrict__ keep = PLAIN ? nullptr : keep_;
     const bf16* __restrict__ feat_lo = PLAIN ? nullptr : feat_lo_;
     extern __shared__ __align__(16) float s_w[];   // [6][D], only used when PASSES == 0
@@ -669,6 +688,7 @@ head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, 
                 int use_seed, float scale, const float* __restrict__ w6, int mask_relu,
                 bf16* __restrict__ dfeat, int lddf, float* __restrict__ dw6_part,
                 float* __restrict__ db6_part) {
+    pdl_prologue();
     extern __shared__ __align__(16) float hb_smem[];   // [phases-1][48][ct] + [phases][6]
     const int ct = D >> 3;                              // column threads
     const int phases = HEADB_THREADS / ct;
@@ -779,6 +799,7 @@ __global__ void __launch_bounds__(256)
 head_bwd_reduce_kernel(const float* __restrict__ dw_part, const float* __restrict__ db_part, int nparts, int D,
                        float* __restrict__ dw_t, float* __restrict__ dw_q, float* __restrict__ db_t,
                        float* __restrict__ db_q, int accumulate) {
+    pdl_prologue();
     __shared__ float red[8][32];
     const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
     const int n = 6 * D;
@@ -814,6 +835,7 @@ head_bwd_reduce_kernel(const float* __restrict__ dw_part, const float* __restric
 // out[i] (+)= sum_b part[b, i]
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, long long stride, long long n,
                                        float* __restrict__ out, int accumulate) {
+    pdl_prologue();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int b = 0; b < nparts; ++b) s += part[(size_t)b * stride + i];
@@ -823,6 +845,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int npart
 // 2-D variant for strided outputs: out[r*ldo + c] (+)= sum_s part[s*stride + r*cols + c]
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits, long long stride, int rows, int cols,
                                      float* __restrict__ out, int ldo, int accumulate) {
+    pdl_prologue();
     const long long n = (long long)rows * cols;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
@@ -833,9 +856,20 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits,
     }
 }
 
+// Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
+// never queue behind a large host->device copy of another stream.
+constexpr int UPLOAD_WORDS = 2032;
+struct UploadWords { int32_t w[UPLOAD_WORDS]; };
+__global__ void __launch_bounds__(256)
+upload_words_kernel(const __grid_constant__ UploadWords p, int32_t* __restrict__ dst, int n) {
+    pdl_prologue();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = p.w[i];
+}
+
 // Batched form: blockIdx.y picks the descriptor; always accumulating.
 __global__ void __launch_bounds__(256)
 reduce_splits_batch_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
+    pdl_prologue();
     const rpg_reduce_desc_t& d = batch.d[blockIdx.y];
     const long long n = (long long)d.rows * d.cols;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -861,6 +895,7 @@ pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses
                  const int* __restrict__ tdst, long long Et, int N, int Ep, const float* __restrict__ grad_scale,
                  const float* __restrict__ sax, const float* __restrict__ saq,
                  float* __restrict__ target, float* __restrict__ dpred, float* __restrict__ partial) {
+    pdl_prologue();
     float st = 0.f, sq = 0.f;
     float gs_t = grad_scale ? grad_scale[0] : 1.f, gs_q = grad_scale ? grad_scale[1] : 1.f;
     if (sax) {   // criterion.py:55-57: d loss / d pred = exp(-s) * sign / (3 Et)
@@ -900,6 +935,7 @@ pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses
 // sums[2..6] = loss, t_loss, q_loss, d loss/d sax, d loss/d saq.
 __global__ void pose_loss_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ sums,
                                        const float* __restrict__ sax, const float* __restrict__ saq, long long Et) {
+    pdl_prologue();
     float a = 0.f, b = 0.f;                                  // one warp, fixed order
     for (int i = threadIdx.x; i < nblocks; i += 32) { a += partial[2 * i]; b += partial[2 * i + 1]; }
 #pragma unroll
@@ -929,6 +965,7 @@ constexpr int COLSUM_THREADS = 256;
 __global__ void __launch_bounds__(COLSUM_THREADS)
 colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int cols,
                      const float* __restrict__ row_w, int row_w_mod, float* __restrict__ part) {
+    pdl_prologue();
     __shared__ float red[8][COLSUM_THREADS];
     const int cg = cols >> 3;                                   // <= COLSUM_THREADS (host-checked)
     const int phases = COLSUM_THREADS / cg;
@@ -962,6 +999,7 @@ colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int co
 __global__ void __launch_bounds__(256)
 reduce_partials_wide_kernel(const float* __restrict__ part, int nparts, long long stride, int n,
                             float* __restrict__ out, int accumulate) {
+    pdl_prologue();
     __shared__ float red[8][32];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), ph = threadIdx.x >> 5;
     float s = 0.f;
@@ -991,14 +1029,14 @@ int rpg_validate_edge_index(const int64_t* edge_index, int64_t Et, int G, int N,
     if (G <= 0 || N <= 0 || Ep <= 0 || Et != (int64_t)G * Ep) return set_error(RPG_E_GRAPH, "validate: Et != G * Ep");
     cudaStream_t s = as_stream(stream);
     cudaMemsetAsync(bad_count, 0, sizeof(int32_t), s);
-    validate_edge_index_kernel<<<grid_for(Et, 256), 256, 0, s>>>(reinterpret_cast<const long long*>(edge_index), Et, G, N,
+    launch_pdl(validate_edge_index_kernel, dim3(grid_for(Et, 256)), dim3(256), 0, s, reinterpret_cast<const long long*>(edge_index), Et, G, N,
                                                                   Ep, tmpl_src, tmpl_dst, bad_count);
     return check_launch("validate_edge_index_kernel");
 }
 
 int rpg_selection_patterns(const int32_t* endpoint, int Ep, int N, int div, int patterns, rpg_bf16* sel, rpg_stream_t stream) {
     if (!endpoint || !sel || Ep <= 0 || N <= 0 || div <= 0 || patterns <= 0) return set_error(RPG_E_ARG, "selection_patterns: bad arguments");
-    selection_patterns_kernel<<<grid_for((long long)patterns * 128 * 8, 256), 256, 0, as_stream(stream)>>>(
+    launch_pdl(selection_patterns_kernel, dim3(grid_for((long long)patterns * 128 * 8, 256)), dim3(256), 0, as_stream(stream), 
         endpoint, Ep, N, div, patterns, reinterpret_cast<bf16*>(sel));
     return check_launch("selection_patterns_kernel");
 }
@@ -1007,7 +1045,7 @@ int rpg_pack_weight(const float* src, int ld_src, int r0, int c0, int rows, int 
                     int transpose, rpg_stream_t stream) {
     if (!src || !dst || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "pack_weight: bad arguments");
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    pack_weight_kernel<<<grid, block, 0, as_stream(stream)>>>(src, ld_src, r0, c0, rows, cols,
+    launch_pdl(pack_weight_kernel, dim3(grid), dim3(block), 0, as_stream(stream), src, ld_src, r0, c0, rows, cols,
                                                               reinterpret_cast<bf16*>(dst), ld_dst, transpose);
     return check_launch("pack_weight_kernel");
 }
@@ -1015,38 +1053,38 @@ int rpg_pack_weight(const float* src, int ld_src, int r0, int c0, int rows, int 
 int rpg_cast_f32_to_bf16(const float* src, rpg_bf16* dst, int64_t n, rpg_stream_t stream) {
     if (!src || !dst || n < 0) return set_error(RPG_E_ARG, "cast: bad arguments");
     if (n == 0) return 0;
-    cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+    launch_pdl(cast_f32_bf16_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), 0, as_stream(stream), src, reinterpret_cast<bf16*>(dst), n);
     return check_launch("cast_f32_bf16_kernel");
 }
 int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_t stream) {
     if (!src || !dst || n < 0) return set_error(RPG_E_ARG, "cast: bad arguments");
     if (n == 0) return 0;
-    cast_bf16_f32_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n);
+    launch_pdl(cast_bf16_f32_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), 0, as_stream(stream), reinterpret_cast<const bf16*>(src), dst, n);
     return check_launch("cast_bf16_f32_kernel");
 }
 
 int rpg_cast_f32_to_split(const float* src, rpg_bf16* hi, rpg_bf16* lo, int64_t n, rpg_stream_t stream) {
     if (!src || !hi || !lo || n <= 0) return set_error(RPG_E_ARG, "cast_f32_to_split: bad arguments");
-    cast_f32_split_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(src, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo), n);
+    launch_pdl(cast_f32_split_kernel, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), src, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo), n);
     return check_launch("cast_f32_split_kernel");
 }
 int rpg_split_to_f32(const rpg_bf16* hi, const rpg_bf16* lo, float* dst, int64_t n, rpg_stream_t stream) {
     if (!dst || !hi || !lo || n <= 0) return set_error(RPG_E_ARG, "split_to_f32: bad arguments");
-    split_to_f32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const bf16*>(hi), reinterpret_cast<const bf16*>(lo), dst, n);
+    launch_pdl(split_to_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, as_stream(stream), reinterpret_cast<const bf16*>(hi), reinterpret_cast<const bf16*>(lo), dst, n);
     return check_launch("split_to_f32_kernel");
 }
 int rpg_pack_weight_lo(const float* src, int ld_src, int r0, int c0, int rows, int cols, rpg_bf16* dst, int ld_dst,
                        rpg_stream_t stream) {
     if (!src || !dst || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "pack_weight_lo: bad arguments");
     dim3 grid((cols + 127) / 128, rows);
-    pack_weight_lo_kernel<<<grid, 128, 0, as_stream(stream)>>>(src, ld_src, r0, c0, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
+    launch_pdl(pack_weight_lo_kernel, dim3(grid), dim3(128), 0, as_stream(stream), src, ld_src, r0, c0, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
     return check_launch("pack_weight_lo_kernel");
 }
 int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e_hi,
                           rpg_bf16* e_lo, int lde, rpg_stream_t stream) {
     if (!pminmax || !bias || !graph || !e_hi || !e_lo || D % 4 || ldp % 4 || lde % 4) return set_error(RPG_E_ARG, "edge_init_fwd_f32: bad arguments");
     const long long Et = (long long)graph->G * graph->Ep;
-    edge_init_fwd_f32_kernel<<<grid_for(Et * (D / 4), 256), 256, 0, as_stream(stream)>>>(
+    launch_pdl(edge_init_fwd_f32_kernel, dim3(grid_for(Et * (D / 4), 256)), dim3(256), 0, as_stream(stream), 
         pminmax, ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D, reinterpret_cast<bf16*>(e_hi),
         reinterpret_cast<bf16*>(e_lo), lde);
     return check_launch("edge_init_fwd_f32_kernel");
@@ -1058,10 +1096,10 @@ int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy,
     if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
     if (aux)
-        attention_fwd_kernel<256, true><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
+        launch_pdl((attention_fwd_kernel<256, true>), dim3(grid), dim3(ATT_WARPS * 32), 0, as_stream(stream), gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
                                                                                       reinterpret_cast<bf16*>(y_lo), aux);
     else
-        attention_fwd_kernel<256, false><<<grid, ATT_WARPS * 32, 0, as_stream(stream)>>>(gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
+        launch_pdl((attention_fwd_kernel<256, false>), dim3(grid), dim3(ATT_WARPS * 32), 0, as_stream(stream), gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
                                                                                        reinterpret_cast<bf16*>(y_lo), nullptr);
     return check_launch("attention_fwd_kernel");
 }
@@ -1077,7 +1115,7 @@ int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_
         configured = smem;
     }
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
-    attention_bwd_kernel<<<grid, ATT_WARPS * 32, smem, as_stream(stream)>>>(gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
+    launch_pdl(attention_bwd_kernel, dim3(grid), dim3(ATT_WARPS * 32), smem, as_stream(stream), gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
                                                                            Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp, aux);
     return check_launch("attention_bwd_kernel");
 }
@@ -1087,10 +1125,11 @@ static int launch_segment(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int 
                           const rpg_bf16* v_lo = nullptr, rpg_bf16* out_lo = nullptr) {
     if (!v || !g || !out || !ptr || !idx || D % 8 || ldv % 8 || ldo % 8) return set_error(RPG_E_ARG, "segment_sum: bad arguments");
     const long long Nt = (long long)g->G * g->N;
-    segment_sum_kernel<<<grid_for(Nt * (D / 8), 256), 256, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv,
-                                                                  reinterpret_cast<const bf16*>(mask), ldm, ptr, idx, scale,
-                                                                  Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out), ldo,
-                                                                  reinterpret_cast<const bf16*>(v_lo), reinterpret_cast<bf16*>(out_lo));
+    const bool small = Nt * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
+    auto kern = small ? segment_sum_kernel<unsigned> : segment_sum_kernel<long long>;
+    launch_pdl(kern, dim3(grid_for(Nt * (D / 8), 256)), dim3(256), 0, s, reinterpret_cast<const bf16*>(v), ldv,
+               reinterpret_cast<const bf16*>(mask), ldm, ptr, idx, scale, Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out), ldo,
+               reinterpret_cast<const bf16*>(v_lo), reinterpret_cast<bf16*>(out_lo));
     return check_launch("segment_sum_kernel");
 }
 
@@ -1123,7 +1162,9 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
                       int lde, uint8_t* e0_bits, rpg_stream_t stream) {
     if (!pminmax || !bias || !graph || !e0 || D % 8 || ldp % 8 || lde % 8) return set_error(RPG_E_ARG, "edge_init_fwd: bad arguments");
     const long long Et = (long long)graph->G * graph->Ep;
-    edge_init_fwd_kernel<<<grid_for(Et * (D / 8), 256), 256, 0, as_stream(stream)>>>(
+    const bool small = Et * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
+    auto kern = small ? edge_init_fwd_kernel<unsigned> : edge_init_fwd_kernel<long long>;
+    launch_pdl(kern, dim3(grid_for(Et * (D / 8), 256)), dim3(256), 0, as_stream(stream),
         reinterpret_cast<const bf16*>(pminmax), ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D,
         reinterpret_cast<bf16*>(e0), lde, e0_bits);
     return check_launch("edge_init_fwd_kernel");
@@ -1132,7 +1173,7 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
 int rpg_dropout_mask(uint64_t seed, float p_drop, int64_t rows, int D, uint8_t* keep, rpg_stream_t stream) {
     if (!keep || rows <= 0 || D <= 0 || p_drop < 0.f || p_drop >= 1.f) return set_error(RPG_E_ARG, "dropout_mask: bad arguments");
     const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
-    dropout_mask_kernel<<<grid_for(rows * D, 256), 256, 0, as_stream(stream)>>>(seed, thresh, rows, D, keep);
+    launch_pdl(dropout_mask_kernel, dim3(grid_for(rows * D, 256)), dim3(256), 0, as_stream(stream), seed, thresh, rows, D, keep);
     return check_launch("dropout_mask_kernel");
 }
 
@@ -1148,11 +1189,11 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
     cudaStream_t st = as_stream(stream);
     const bool plain = !keep && !fl;
     if (D <= 256) {
-        if (plain) head_fwd_kernel<1, true><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
-        else head_fwd_kernel<1, false><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        if (plain) launch_pdl((head_fwd_kernel<1, true>), dim3(grid), dim3(HEAD_WARPS * 32), 0, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        else launch_pdl((head_fwd_kernel<1, false>), dim3(grid), dim3(HEAD_WARPS * 32), 0, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     } else if (D <= 512) {
-        if (plain) head_fwd_kernel<2, true><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
-        else head_fwd_kernel<2, false><<<grid, HEAD_WARPS * 32, 0, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        if (plain) launch_pdl((head_fwd_kernel<2, true>), dim3(grid), dim3(HEAD_WARPS * 32), 0, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        else launch_pdl((head_fwd_kernel<2, false>), dim3(grid), dim3(HEAD_WARPS * 32), 0, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     } else {
         const size_t smem = (size_t)6 * D * sizeof(float);
         if (D > 2048) return set_error(RPG_E_UNSUPPORTED, "head_fwd: D > 2048");
@@ -1161,7 +1202,7 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
             cudaFuncSetAttribute(head_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
-        head_fwd_kernel<0, false><<<grid, HEAD_WARPS * 32, smem, st>>>(f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
+        launch_pdl((head_fwd_kernel<0, false>), dim3(grid), dim3(HEAD_WARPS * 32), smem, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     }
     return check_launch("head_fwd_kernel");
 }
@@ -1192,13 +1233,13 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
         configured = smem;
     }
     cudaStream_t s = as_stream(stream);
-    head_bwd_kernel<<<blocks, HEADB_THREADS, smem, s>>>(dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed,
+    launch_pdl(head_bwd_kernel, dim3(blocks), dim3(HEADB_THREADS), smem, s, dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed,
                                                         thresh, use_seed, scale, w6, mask_relu,
                                                         reinterpret_cast<bf16*>(dfeat), lddf, dw_part, db_part);
     int rc = check_launch("head_bwd_kernel");
     if (rc) return rc;
     // rows 0..2 -> translation head (fc_xyz*), rows 3..5 -> rotation head (fc_wpqr*)
-    head_bwd_reduce_kernel<<<(6 * D + 31) / 32 + 1, 256, 0, s>>>(dw_part, db_part, blocks, D, dw_t, dw_q, db_t, db_q, accumulate);
+    launch_pdl(head_bwd_reduce_kernel, dim3((6 * D + 31) / 32 + 1), dim3(256), 0, s, dw_part, db_part, blocks, D, dw_t, dw_q, db_t, db_q, accumulate);
     return check_launch("head_bwd_reduce_kernel");
 }
 
@@ -1210,11 +1251,11 @@ static int pose_loss_launch(const float* pred, const float* poses, const rpg_gra
     if (!pred || !poses || !graph || !sums || !ws || Et <= 0) return set_error(RPG_E_ARG, "pose_loss: bad arguments");
     const int blocks = grid_for(Et, LOSS_THREADS, 1024);
     cudaStream_t s = as_stream(stream);
-    pose_loss_kernel<<<blocks, LOSS_THREADS, 0, s>>>(pred, poses, graph->src, graph->dst, Et, graph->N, graph->Ep, grad_scale,
+    launch_pdl(pose_loss_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, s, pred, poses, graph->src, graph->dst, Et, graph->N, graph->Ep, grad_scale,
                                                      sax, saq, target, dpred, ws);
     int rc = check_launch("pose_loss_kernel");
     if (rc) return rc;
-    pose_loss_final_kernel<<<1, 32, 0, s>>>(ws, blocks, sums, sax, saq, Et);
+    launch_pdl(pose_loss_final_kernel, dim3(1), dim3(32), 0, s, ws, blocks, sums, sax, saq, Et);
     return check_launch("pose_loss_final_kernel");
 }
 
@@ -1239,20 +1280,34 @@ int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const fl
         return set_error(RPG_E_ARG, "colsum: bad arguments (cols must be a multiple of 8, at most 2048)");
     const int slabs = (int)((rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
     cudaStream_t s = as_stream(stream);
-    colsum_stage1_kernel<<<slabs, COLSUM_THREADS, 0, s>>>(reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
+    launch_pdl(colsum_stage1_kernel, dim3(slabs), dim3(COLSUM_THREADS), 0, s, reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
                                                           row_w_mod > 0 ? row_w_mod : 1, scratch);
     int rc = check_launch("colsum_stage1_kernel");
     if (rc) return rc;
-    reduce_partials_wide_kernel<<<(cols + 31) / 32, 256, 0, s>>>(scratch, slabs, cols, cols, out, accumulate);
+    launch_pdl(reduce_partials_wide_kernel, dim3((cols + 31) / 32), dim3(256), 0, s, scratch, slabs, cols, cols, out, accumulate);
     return check_launch("reduce_partials_wide_kernel");
 }
 
 int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols, float* out, int ldo,
                       int accumulate, rpg_stream_t stream) {
     if (!partial || !out || splits < 1 || rows <= 0 || cols <= 0) return set_error(RPG_E_ARG, "reduce_splits: bad arguments");
-    reduce_splits_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, as_stream(stream)>>>(partial, splits, split_stride, rows,
+    launch_pdl(reduce_splits_kernel, dim3(grid_for((long long)rows * cols, 256)), dim3(256), 0, as_stream(stream), partial, splits, split_stride, rows,
                                                                                               cols, out, ldo, accumulate);
     return check_launch("reduce_splits_kernel");
+}
+
+int rpg_upload_words(int32_t* dst, const int32_t* src_host, int64_t n, rpg_stream_t stream) {
+    if (!dst || !src_host || n <= 0) return set_error(RPG_E_ARG, "upload_words: bad arguments");
+    static_assert(sizeof(UploadWords) <= 8192, "parameter block");
+    for (int64_t off = 0; off < n; off += UPLOAD_WORDS) {
+        UploadWords p;
+        const int cnt = (int)std::min<int64_t>(UPLOAD_WORDS, n - off);
+        memcpy(p.w, src_host + off, (size_t)cnt * sizeof(int32_t));
+        launch_pdl(upload_words_kernel, dim3((cnt + 255) / 256), dim3(256), 0, as_stream(stream), p, dst + off, cnt);
+        int rc = check_launch("upload_words_kernel");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream) {
@@ -1265,7 +1320,7 @@ int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream
         most = std::max(most, (long long)d.rows * d.cols);
     }
     dim3 grid((unsigned)grid_for(most, 256, 1024), (unsigned)batch->n);
-    reduce_splits_batch_kernel<<<grid, 256, 0, as_stream(stream)>>>(*batch);
+    launch_pdl(reduce_splits_batch_kernel, dim3(grid), dim3(256), 0, as_stream(stream), *batch);
     return check_launch("reduce_splits_batch_kernel");
 }
 

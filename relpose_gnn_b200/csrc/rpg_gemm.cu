@@ -149,6 +149,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     if (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // The set-up above overlapped the previous kernel's tail (programmatic dependent launch); its results are visible
+    // only after the wait, and nothing before this line touched global memory.
+    pdl_prologue();
 
     const int cta_rank = CL == 1 ? 0 : (int)cluster_ctarank();
     const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;     // a worker = one cluster
@@ -881,11 +884,13 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cfg.blockDim = dim3(GEMM_THREADS);
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = (pdl_enabled() && !prof) ? 2 : 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmaps, p);
         (void)e;
     }

@@ -22,4 +22,21 @@ int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches
 
 inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: every kernel of the library starts with griddepcontrol.launch_dependents +
+// griddepcontrol.wait (rpg_ptx.cuh: pdl_prologue), so the next kernel's CTAs are scheduled -- and run their prologue --
+// while this one drains; nothing touches global memory before the wait.  RPG_PDL=0 turns the launch attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace rpg

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstddef>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -81,6 +82,17 @@ static int wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, 
     if (rc || !bias) return rc;
     return rpg_reduce_splits(ws + (size_t)splits * M * N, splits, M, 1, M, bias, M, /*accumulate=*/1, s);
 }
+
+}  // namespace rpg
+bool rpg::pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("RPG_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+namespace rpg {
 
 static int sm_count_cached() {
     static int n = 0;

@@ -189,4 +189,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// Programmatic dependent launch (see rpg_internal.h: launch_pdl).  No-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 }  // namespace rpg

@@ -54,36 +54,26 @@ def batched_edge_index(src, dst, n_graphs, n_nodes, device=None):
     return (t.unsqueeze(1) + offs.view(1, -1, 1)).reshape(2, -1).contiguous()
 
 
-class _PinnedUploader:
-    """Asynchronous host->device upload of small int32 tables: a ring of pinned staging buffers, each guarded by a
-    CUDA event, so that building a new template every step (edge dropout) never issues a pageable -- i.e. stream-
-    synchronising -- copy."""
-
-    def __init__(self, slots=32, capacity=8192):
-        self.slots, self.capacity, self.next = slots, capacity, 0
-        self.bufs, self.events = [], []
+class _TableUploader:
+    """Host -> device upload of the small int32 template tables through rpg_upload_words (the words ride along as
+    kernel parameters): asynchronous, no pinned staging, and independent of the copy engines, so a new template every
+    step (edge dropout) never waits behind a large input copy."""
 
     def upload(self, packed_np, device):
-        n = packed_np.size
-        if n > self.capacity or not torch.cuda.is_available() or torch.device(device).type != "cuda":
+        device = torch.device(device)
+        if device.type != "cuda":
             return torch.from_numpy(packed_np).to(device)
-        if not self.bufs:
-            self.bufs = [torch.empty(self.capacity, dtype=torch.int32).pin_memory() for _ in range(self.slots)]
-            self.events = [None] * self.slots
-        i = self.next
-        self.next = (i + 1) % self.slots
-        if self.events[i] is not None:
-            self.events[i].synchronize()                # the previous copy out of this slot has completed
-        self.bufs[i][:n].copy_(torch.from_numpy(packed_np))
-        dev = torch.empty(n, dtype=torch.int32, device=device)
-        dev.copy_(self.bufs[i][:n], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(device))
-        self.events[i] = ev
+        packed_np = np.ascontiguousarray(packed_np, dtype=np.int32)
+        dev = torch.empty(packed_np.size, dtype=torch.int32, device=device)
+        lib = _lib.load()
+        rc = lib.rpg_upload_words(dev.data_ptr(), packed_np.ctypes.data, packed_np.size,
+                                  C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        if rc:
+            raise RuntimeError("rpg_upload_words: " + lib.rpg_last_error_string().decode())
         return dev
 
 
-_uploader = _PinnedUploader()
+_uploader = _TableUploader()
 
 
 def _csr(keys, n):
