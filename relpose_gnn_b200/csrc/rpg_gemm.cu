@@ -109,10 +109,19 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& u) {
 // OPS = the epilogue reads tensor operands (gathered node rows / residual / bf16 mask); compiled separately so that the
 // plain epilogue keeps its smaller register footprint and schedule.
 // EPI = 2 additionally handles the fp32 ("split bf16") mode: fp32 gathered rows, (hi, lo) residuals and outputs.
-template <int MODE, int CL, int EPI>
+// PAIR = the two CTAs of a cluster form ONE cta_group::2 MMA (M = 256): each CTA stages its own 128 rows of A and only
+// HALF of the B tile (no copy of the peer's half), the leader issues the MMAs for both, and each CTA drains its own
+// half of the accumulator.  Shared-memory fill + operand-read traffic per CTA drops by a third (48 -> 32 KB per
+// k-block), which is what bounds the single-CTA form at these shapes, and the ring deepens from 4 to 6 stages.
+// (NT mode without one-hot panels: the panels' node windows differ between the two row blocks.)
+template <int MODE, int CL, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
+    static_assert(!PAIR || (CL == 2 && MODE == 0), "CTA pairs: NT mode, clusters of 2");
     constexpr bool OPS = EPI >= 1;
+    constexpr int NS = PAIR ? 6 : STAGES;                                  // ring depth
+    constexpr int BST = PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;          // B bytes per stage in this CTA
+    static_assert(NS * (A_STAGE_BYTES + BST) == SMEM_RING_BYTES, "ring carve");
     const CUtensorMap& tmA0 = tm.a[0];
     const CUtensorMap& tmB = tm.b;
     const CUtensorMap& tmOut = tm.out;
@@ -121,11 +130,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* smem_b = smem + NS * A_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_RING_BYTES);
-    uint64_t* full_bar = bars;                    // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-    uint64_t* acc_full = bars + 2 * STAGES;       // [ACC_STAGES]
+    uint64_t* full_bar = bars;                    // [NS]
+    uint64_t* empty_bar = bars + NS;              // [NS]
+    uint64_t* acc_full = bars + 2 * NS;           // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES;  // [ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
@@ -136,14 +145,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmB);
         // a stage is free when every CTA's MMAs have drained it (+ the local column-sum warps in TN mode)
-        const uint32_t empty_count = CL + ((MODE == 1 && p.a_colsum) ? EPI_WARPS : 0);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], empty_count); }
-        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+        // (pair mode: one multicast commit per stage; the leader's accumulator barrier hears both CTAs' epilogue warps)
+        const uint32_t empty_count = PAIR ? 1 : CL + ((MODE == 1 && p.a_colsum) ? EPI_WARPS : 0);
+        for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], empty_count); }
+        for (int i = 0; i < ACC_STAGES; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
     if (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers must be initialised before any remote arrive
@@ -177,19 +190,31 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         const CUtensorMap* tmA = &tm.a[s];
                         for (int kb = 0; kb < p.num_kb[s]; ++kb, ++kb_global) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (PAIR) {
+                                // both CTAs' tiles complete on the LEADER's full barrier: it expects the bytes of both
+                                const int half_rows = p.block_n / 2;
+                                const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                                if (cta_rank == 0)
+                                    mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + half_rows * BLOCK_K * 2));
+                                tma_load_2d_pair(tmA, lead_full, smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_blk * BLOCK_M);
+                                tma_load_2d_pair(&tmB, lead_full, smem_b + stage * BST, kb_global * BLOCK_K,
+                                                 n_blk * p.block_n + cta_rank * half_rows);
+                                if (++stage == NS) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
                             tma_load_2d(tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K,
                                         m_blk * BLOCK_M);
                             if (CL == 1) {
-                                tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb_global * BLOCK_K,
+                                tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * BST, kb_global * BLOCK_K,
                                             n_blk * p.block_n);
                             } else {       // my half of the weight rows, delivered to both CTAs
                                 const int half_rows = p.block_n / CL;
                                 tma_load_2d_mc(&tmB, &full_bar[stage],
-                                               smem_b + stage * B_STAGE_BYTES + cta_rank * half_rows * (BLOCK_K * 2),
+                                               smem_b + stage * BST + cta_rank * half_rows * (BLOCK_K * 2),
                                                kb_global * BLOCK_K, n_blk * p.block_n + cta_rank * half_rows, kAllCtas);
                             }
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == NS) { stage = 0; phase ^= 1; }
                         }
                     }
                     // one-hot K panels: selection pattern (A) + the node rows this row block can reference (B, MN-major).
@@ -202,9 +227,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
                         tma_load_2d(&tm.ga[gs], &full_bar[stage], smem_a + stage * A_STAGE_BYTES, 0, pat * BLOCK_M);
                         for (int j = 0; j < p.block_n / 64; ++j)
-                            tma_load_2d(&tm.gb[gs], &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
+                            tma_load_2d(&tm.gb[gs], &full_bar[stage], smem_b + stage * BST + j * 8192,
                                         n_blk * p.block_n + j * 64, win);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
                 } else {
                     const int split = item % p.splits;
@@ -219,21 +244,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                                         m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
                         for (int j = 0; j < p.block_n / 64; ++j) {
                             if (CL == 1)
-                                tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
+                                tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * BST + j * 8192,
                                             n_blk * p.block_n + j * 64, kb * BLOCK_K);
                             else if (j % CL == cta_rank)
-                                tma_load_2d_mc(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + j * 8192,
+                                tma_load_2d_mc(&tmB, &full_bar[stage], smem_b + stage * BST + j * 8192,
                                                n_blk * p.block_n + j * 64, kb * BLOCK_K, kAllCtas);
                         }
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ MMA issuer (single thread)
-            const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.block_n, MODE, MODE);
+        if (lane == 0 && !(PAIR && cta_rank != 0)) {
+            // ------------------------------------------------------------ MMA issuer (single thread; pair: leader only)
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, p.block_n, MODE, MODE);
             // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused.
             // MN-major SW128: 64-element MN slabs 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO).
             const uint32_t lbo = MODE == 0 ? 0u : 8192u, sbo = 1024u;
@@ -260,21 +285,27 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), lbo, sbo);
                     if (MODE == 0 && kb >= n_kb - p.n_gseg) {
                         // one-hot panel: A K-major (selection), B MN-major (node rows): only the B side changes layout
-                        const uint64_t bg_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), 8192u, 1024u);
+                        const uint64_t bg_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * BST), 8192u, 1024u);
                         const uint32_t idesc_g = make_idesc_bf16(BLOCK_M, p.block_n, 0, 1);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16(d_tmem, a_desc + k * k_step, bg_desc + k * ((UMMA_K * 128) >> 4), idesc_g, (kb | k) != 0);
                     } else {
-                        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), lbo, sbo);
+                        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * BST), lbo, sbo);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            if (PAIR) umma_bf16_pair(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
+                            else umma_bf16(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
+                        }
                     }
-                    if (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    if (PAIR) umma_commit_pair(&empty_bar[stage], kAllCtas);   // both CTAs' slots, both producers
+                    else if (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                     else umma_commit_mc(&empty_bar[stage], kAllCtas);   // ... in every CTA that multicasts into it
-                    if (kb == n_kb - 1) umma_commit(&acc_full[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == n_kb - 1) {
+                        if (PAIR) umma_commit_pair(&acc_full[acc], kAllCtas);   // both epilogues
+                        else umma_commit(&acc_full[acc]);
+                    }
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
                 if (n_kb <= 0) umma_commit(&acc_full[acc]);   // empty split: nothing to accumulate (epilogue writes zeros)
             }
@@ -326,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[cs_stage]);
-                    if (++cs_stage == STAGES) { cs_stage = 0; cs_phase ^= 1; }
+                    if (++cs_stage == NS) { cs_stage = 0; cs_phase ^= 1; }
                 }
                 if (n_blk == 0) {
                     // fold the 16 row groups through the (idle) staging area, then one thread per column writes
@@ -425,7 +456,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                 if (c + 2 >= n_chunks) {          // last TMEM read of this tile by this warp: hand the stage back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    if (lane == 0) {
+                        if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acc]), 0));
+                        else mbar_arrive(&acc_empty[acc]);
+                    }
                     released = true;
                 }
                 if (zero_acc) {
@@ -597,7 +631,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             if (!released) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                if (lane == 0) {
+                        if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acc]), 0));
+                        else mbar_arrive(&acc_empty[acc]);
+                    }
             }
         }
         if (lane == 0) bulk_wait_all();            // all results are in global memory before the CTA retires
@@ -608,11 +645,22 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     if (CL == 1) __syncthreads(); else cluster_sync_all();   // no CTA may exit while its peer can still signal it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
 // -------------------------------------------------------------------------------------- host side
+
+// RPG_GEMM_PAIR=0 keeps every GEMM on the single-CTA MMA form (A/B comparisons).
+static bool gemm_pair_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("RPG_GEMM_PAIR");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -848,6 +896,8 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         cudaFuncSetAttribute(gemm_tc_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
@@ -874,6 +924,8 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (cl == 1)
         kern = g->mode == 1 ? gemm_tc_kernel<1, 1, 0>
                             : (split_mode ? gemm_tc_kernel<0, 1, 2> : (ops ? gemm_tc_kernel<0, 1, 1> : gemm_tc_kernel<0, 1, 0>));
+    else if (g->mode == 0 && !split_mode && g->n_gseg == 0 && gemm_pair_enabled())
+        kern = ops ? gemm_tc_kernel<0, 2, 1, true> : gemm_tc_kernel<0, 2, 0, true>;
     else
         kern = g->mode == 1 ? gemm_tc_kernel<1, 2, 0>
                             : (split_mode ? gemm_tc_kernel<0, 2, 2> : (ops ? gemm_tc_kernel<0, 2, 1> : gemm_tc_kernel<0, 2, 0>));
