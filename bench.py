@@ -81,7 +81,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [t.strip() for t in ln.split(",")]
@@ -91,11 +91,15 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": float(np.median(pw)) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------- reference arm (CPU)

@@ -78,6 +78,7 @@ struct GemmKParams {
     int gsel_div;                  // pattern index of row block = ((m_blk * 128) % Ep) / gsel_div
     // TN mode: column sums of A (= bias gradient when A is dY) accumulated by the otherwise idle epilogue warps
     float* a_colsum;               // [splits, M] partial sums, or NULL
+    int resid_tma;                 // pair kernels: the residual tile arrives by TMA in a per-warp operand buffer
 };
 
 struct GemmTmaps {
@@ -86,6 +87,7 @@ struct GemmTmaps {
     CUtensorMap out, out_relu, out_f32, out_lo, out_relu_lo;
     CUtensorMap ga[2];             // one-hot selection patterns [npat * 128, 64] (K-major A tiles)
     CUtensorMap gb[2];             // gathered matrix [rows, N] (MN-major B tiles: 64 rows x 64 columns per box)
+    CUtensorMap resid;             // residual [M, N] in 32-row x 64-column boxes (same geometry as the output maps)
 };
 
 __device__ __forceinline__ void add_bf16x8(float* f, const uint4& u) {
@@ -118,10 +120,16 @@ template <int MODE, int CL, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     static_assert(!PAIR || (CL == 2 && MODE == 0), "CTA pairs: NT mode, clusters of 2");
-    constexpr bool OPS = EPI >= 1;
-    constexpr int NS = PAIR ? 6 : STAGES;                                  // ring depth
+    constexpr bool OPS = EPI == 1 || EPI == 2;
+    constexpr bool RTMA = EPI == 3;        // the only tensor operand is a residual, fetched by TMA (pair kernels)
+    static_assert(!RTMA || PAIR, "TMA-staged residuals are a pair-kernel feature");
+    // EPI = 3 gives one ring stage (32 KB) to per-warp operand buffers: the residual tile of a chunk is fetched by TMA
+    // (coalesced, asynchronous, one chunk ahead) instead of row-per-thread loads, and the operand-register arrays of
+    // the general EPI = 1 epilogue (which spill) are not compiled in.
+    constexpr bool OPBUF = RTMA;
+    constexpr int NS = OPBUF ? 5 : (PAIR ? 6 : STAGES);                    // ring depth
     constexpr int BST = PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;          // B bytes per stage in this CTA
-    static_assert(NS * (A_STAGE_BYTES + BST) == SMEM_RING_BYTES, "ring carve");
+    static_assert(NS * (A_STAGE_BYTES + BST) + (OPBUF ? EPI_WARPS * EPI_STAGE_BYTES : 0) == SMEM_RING_BYTES, "ring carve");
     const CUtensorMap& tmA0 = tm.a[0];
     const CUtensorMap& tmB = tm.b;
     const CUtensorMap& tmOut = tm.out;
@@ -137,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     uint64_t* acc_full = bars + 2 * NS;           // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES;  // [ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    uint64_t* op_bar = bars + 32;                 // [EPI_WARPS] operand-buffer barriers (OPBUF kernels)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -152,6 +161,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
+        if (OPBUF) for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&op_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -325,7 +335,31 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
         const int n_chunks = (p.block_n + 63) / 64;
         uint8_t* stg = smem + SMEM_RING_BYTES + SMEM_BAR_BYTES + ew * EPI_STAGE_BYTES;
         uint8_t* my_row = stg + lane * 128;
+        // operand buffer of this warp (OPBUF kernels): the ring stage that was given up, [32 rows][128 B] swizzled
+        uint8_t* opbuf = smem + NS * (A_STAGE_BYTES + BST) + ew * EPI_STAGE_BYTES;
+        constexpr bool rtma = RTMA;
+        uint32_t op_phase = 0;
         const int my_sw = lane & 7;
+        // The residual tiles are prefetched one chunk ahead, across work items: next valid (item, chunk) of this warp in
+        // processing order, with the coordinates of its 32 x 64 box.
+        auto next_resid = [&](int it_, int c_, int& r0_, int& n0_) -> bool {
+            for (;;) {
+                if (c_ >= n_chunks) { it_ += num_workers; c_ = half; }
+                if (it_ >= num_items) return false;
+                const int mb = (it_ / num_n_blocks) * CL + cta_rank, nb = it_ % num_n_blocks;
+                r0_ = mb * BLOCK_M + quad * 32;
+                n0_ = nb * p.block_n + c_ * 64;
+                if (r0_ < p.M && n0_ < p.N) return true;
+                c_ += 2;
+            }
+        };
+        if (rtma && lane == 0) {
+            int pr0, pn0;
+            if (next_resid(worker, half, pr0, pn0)) {
+                mbar_arrive_expect_tx(&op_bar[ew], EPI_STAGE_BYTES);
+                tma_load_2d(&tm.resid, &op_bar[ew], opbuf, pn0, pr0);
+            }
+        }
         int it = 0;
         int cs_stage = 0;                          // TN column sums: this role walks the smem ring like the MMA warp
         uint32_t cs_phase = 0;
@@ -427,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     const __nv_bfloat16* cand[4] = {
                         (gnode0 >= 0 && p.gadd[0]) ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
                         (gnode1 >= 0 && p.gadd[1]) ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
-                        p.resid ? p.resid + (size_t)row * p.resid_ld : nullptr,
+                        (p.resid && !rtma) ? p.resid + (size_t)row * p.resid_ld : nullptr,
                         p.mask ? p.mask + (size_t)row * p.mask_ld : nullptr};
 #pragma unroll
                     for (int o = 0; o < 4; ++o) {
@@ -466,6 +500,23 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
 #pragma unroll
                     for (int j = 0; j < 64; ++j) f[j] = 0.f;
                 }
+                uint4 rsd[8];
+                if (rtma) {
+                    mbar_wait(&op_bar[ew], op_phase);
+                    op_phase ^= 1;
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq)
+                        rsd[qq] = *reinterpret_cast<const uint4*>(opbuf + lane * 128 + ((qq ^ my_sw) << 4));
+                    __syncwarp();
+                    if (lane == 0) {                         // the next chunk's tile (possibly of the next work item)
+                        int pr0, pn0;                        // overlaps this chunk's math and store
+                        if (next_resid(item, c + 2, pr0, pn0)) {
+                            fence_proxy_async_smem();
+                            mbar_arrive_expect_tx(&op_bar[ew], EPI_STAGE_BYTES);
+                            tma_load_2d(&tm.resid, &op_bar[ew], opbuf, pn0, pr0);
+                        }
+                    }
+                }
                 // the staging tile is free once the previous TMA store of this warp has read it
                 if (lane == 0) bulk_wait_read_all();
                 __syncwarp();
@@ -497,11 +548,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     };
                     if (OPS && src0) { apply(opr0, kind0); ++used; }
                     if (OPS && src1) { apply(opr1, kind1); ++used; }
+                    if (rtma) {                                      // host guarantees: no other tensor operand in this launch
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq) add_bf16x8(f + 8 * qq, rsd[qq]);
+                    }
                     if (OPS && row_ok) {                             // rare: more than two tensor operands
                         const __nv_bfloat16* cand[4] = {
                             (gnode0 >= 0 && p.gadd[0]) ? p.gadd[0] + (size_t)gnode0 * p.gadd_ld[0] : nullptr,
                             (gnode1 >= 0 && p.gadd[1]) ? p.gadd[1] + (size_t)gnode1 * p.gadd_ld[1] : nullptr,
-                            p.resid ? p.resid + (size_t)row * p.resid_ld : nullptr,
+                            (p.resid && !rtma) ? p.resid + (size_t)row * p.resid_ld : nullptr,
                             p.mask ? p.mask + (size_t)row * p.mask_ld : nullptr};
                         int seen = 0;
                         for (int o = 0; o < 4; ++o) {
@@ -898,6 +953,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cudaFuncSetAttribute(gemm_tc_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
@@ -924,8 +980,15 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (cl == 1)
         kern = g->mode == 1 ? gemm_tc_kernel<1, 1, 0>
                             : (split_mode ? gemm_tc_kernel<0, 1, 2> : (ops ? gemm_tc_kernel<0, 1, 1> : gemm_tc_kernel<0, 1, 0>));
-    else if (g->mode == 0 && !split_mode && g->n_gseg == 0 && gemm_pair_enabled())
+    else if (g->mode == 0 && !split_mode && g->n_gseg == 0 && gemm_pair_enabled()) {
         kern = ops ? gemm_tc_kernel<0, 2, 1, true> : gemm_tc_kernel<0, 2, 0, true>;
+        if (ops && p.resid && !p.mask && !p.gadd[0] && !p.gadd[1] && aligned16(p.resid) && p.resid_ld % 8 == 0) {
+            int rc2 = make_tmap(&tmaps.resid, p.resid, p.N, p.M, p.resid_ld, 64, 32);
+            if (rc2) return rc2;
+            p.resid_tma = 1;
+            kern = gemm_tc_kernel<0, 2, 3, true>;
+        }
+    }
     else
         kern = g->mode == 1 ? gemm_tc_kernel<1, 2, 0>
                             : (split_mode ? gemm_tc_kernel<0, 2, 2> : (ops ? gemm_tc_kernel<0, 2, 1> : gemm_tc_kernel<0, 2, 0>));

@@ -66,6 +66,12 @@ def nt_cases():
     out2 = torch.empty(M, N, dtype=BF, device=dev)
     ops.gemm_nt(None, B, segs=[A0, A1, A2], bias=bias, relu=True, out=out2)
     ok &= report("NT relu", out2, (torch.cat([A0, A1, A2], 1).float() @ B.float().t() + bias).clamp(min=0), 1e-2)
+    # residual only (pair kernels fetch it by TMA): ragged M, N below one block, and a multi-block shape
+    for (Mr, Nr, Kr) in [(300, 192, 128), (1000, 512, 256), (36864, 512, 512)]:
+        Ar, Br, Rr = rnd(Mr, Kr), rnd(Nr, Kr, scale=Kr ** -0.5), rnd(Mr, Nr)
+        o_r = torch.empty(Mr, Nr, dtype=BF, device=dev)
+        ops.gemm_nt(Ar, Br, resid=Rr, out=o_r)
+        ok &= report(f"NT resid M={Mr} N={Nr} K={Kr}", o_r, Ar.float() @ Br.float().t() + Rr.float(), 1e-2)
     # gathered adds as one-hot K panels == the epilogue gather path
     for (Gn, Nn, keepmask) in [(5, 9, None), (40, 9, np.array([1, 0, 1, 1, 0, 0, 1, 0, 1, 0] * 3 + [1] * 6, bool)), (3, 17, None)]:
         gg = GraphBatch.fully_connected(Gn, Nn, dev, keepmask)
