@@ -158,6 +158,7 @@ def run_ours(args):
     from relpose_gnn_b200 import _lib, parallel
     from relpose_gnn_b200.graph import GraphBatch, attach, edge_dropout_keep
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
     rank, local_rank, world = parallel.init_distributed("nccl")
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
@@ -192,7 +193,7 @@ def run_ours(args):
     x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
     mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
     masks = [edge_dropout_keep(H, mask_rng) if train else np.ones(H, bool)
-             for _ in range(2 * args.trials * args.steps + max(args.warmup, 3) + 16)]
+             for _ in range(2 * args.trials * args.steps + 2 * max(args.warmup, 3) + 16)]
     mask_iter = iter(masks)
 
     def step(x, poses, read_back):
@@ -265,6 +266,8 @@ def run_ours(args):
     launches = (lib.rpg_launch_count() - launches0) / (args.steps * args.trials)
     clocks = sampler.stop() if (rank == 0 and args.clocks) else None
     ms_step = float(np.median(trials))
+    e2e_loop(max(args.warmup, 3))             # untimed: allocates the feeder's device slots, touches the pinned buffers
+    torch.cuda.synchronize()
     trials_e2e = [timed(args.steps, e2e=True) for _ in range(args.trials)]
     ms_e2e = float(np.median(trials_e2e))
 
