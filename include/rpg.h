@@ -283,6 +283,16 @@ int rpg_pose_criterion(const float* pred, const float* poses, const rpg_graph_t*
                        const float* sax, const float* saq, float* target, float* out7, float* dpred, float* ws,
                        rpg_stream_t stream);
 
+/* pose_utils.qexp (pose_utils.py:340-348): q[i] = [cos|v|, sinc(|v|/pi) v] for n log-quaternions v [n, 3] -> q [n, 4]. */
+int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream);
+/* Evaluation composition (test.py:227-243) for G graphs sharing the template: with k = ref_k the template edge
+ * (src(k) -> node 0) chosen by the caller (the reference takes the ref_node-th edge whose destination is node 0),
+ *   out = poses[g*N + src(k)] - pred_edges[g*Ep + k];  out_pred[g] = [out_t * pose_s + pose_m | qexp(out_q)]   [G, 7]
+ *   out_targ[g] = the same map applied to the ground truth of node 0 (may be NULL).
+ * pose_m / pose_s: HOST float[3] (NULL = 0 / 1), the dataset's translation normalisation. */
+int rpg_eval_compose(const float* pred_edges, const float* poses, const rpg_graph_t* graph, int ref_k,
+                     const float* pose_m, const float* pose_s, float* out_pred, float* out_targ, rpg_stream_t stream);
+
 /* Column sums (bias gradients): out[c] (+)= sum_r w[r % mod] * v[r, c]; deterministic; row_w may be NULL. */
 int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod,
                     float* out, int accumulate, float* scratch, rpg_stream_t stream);

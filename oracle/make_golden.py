@@ -213,6 +213,39 @@ def golden_qexp():
     print("qexp:", q.shape)
 
 
+def golden_eval_compose():
+    """exec test.py:227-243 (reference absolute pose from the first edge into node 0, qexp, un-normalisation) on seeded
+    single-graph cases (the reference evaluates one graph per batch)."""
+    sys.modules.setdefault("transforms3d", types.ModuleType("transforms3d"))
+    for sub in ("euler", "quaternions"):
+        sys.modules.setdefault("transforms3d." + sub, types.ModuleType("transforms3d." + sub))
+        setattr(sys.modules["transforms3d"], sub, sys.modules["transforms3d." + sub])
+    pyg_shim.install()
+    from niantic.utils import pose_utils
+    body = _ref_lines("testing/test.py", 227, 243)
+    fc = np.load(os.path.join(OUT, "fc_enumeration.npz"))
+    out = {}
+    for case, (n, ref_node, seed) in enumerate([(8, 0, 0), (9, 0, 1), (9, 3, 2), (17, 5, 3), (4, 2, 4)]):
+        rs = np.random.RandomState(100 + seed)
+        edges = fc[f"fc_N{n}"]
+        output_R = (rs.randn(edges.shape[1], 6) * 0.3).astype(np.float32)
+        target = (rs.randn(n, 6) * 0.5).astype(np.float32)
+        pose_m = rs.randn(3).astype(np.float32)
+        pose_s = (rs.rand(3) + 0.5).astype(np.float32)
+        env = {"np": np, "qexp": pose_utils.qexp, "edges": edges, "output_R": output_R.copy(), "target": target.copy(),
+               "ref_node": ref_node, "self": types.SimpleNamespace(pose_m=pose_m, pose_s=pose_s)}
+        exec(body, env)
+        out[f"case{case}_meta"] = np.array([n, ref_node, seed])
+        out[f"case{case}_output_R"] = output_R
+        out[f"case{case}_target"] = target
+        out[f"case{case}_pose_m"] = pose_m
+        out[f"case{case}_pose_s"] = pose_s
+        out[f"case{case}_pred7"] = np.asarray(env["output"][0], dtype=np.float64)
+        out[f"case{case}_targ7"] = np.asarray(env["target"], dtype=np.float64)      # all nodes; the reference keeps row 0
+    np.savez(os.path.join(OUT, "eval_compose.npz"), **out)
+    print("eval_compose: cases", len(out) // 7)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)

@@ -211,6 +211,26 @@ def compose_query_pose(pose_edges, poses_abs, edge_index, ref_node=0):
     return np.concatenate([out[:3].numpy(), qexp(out[3:].numpy())])
 
 
+def compose_eval_batch(pose_edges, poses_abs, template, n_graphs, n_nodes, ref_node=0, pose_m=None, pose_s=None):
+    """test.py:227-243 for a batch of graphs sharing one edge template (the reference evaluates one graph at a time):
+    per graph, the `ref_node`-th template edge into node 0 gives  abs(query) = target[src] - RP_pred;  translations are
+    un-normalised with (pose_s, pose_m), log-quaternions go through qexp.  Returns (pred [G, 7], target [G, 7]) fp64."""
+    pose_edges = np.asarray(pose_edges, dtype=np.float64)
+    poses_abs = np.asarray(poses_abs, dtype=np.float64)
+    template = np.asarray(template)
+    Ep = template.shape[1]
+    k = np.argwhere(template[1] == 0)[ref_node, 0]
+    m = np.zeros(3) if pose_m is None else np.asarray(pose_m, dtype=np.float64)
+    sc = np.ones(3) if pose_s is None else np.asarray(pose_s, dtype=np.float64)
+    pred, targ = np.zeros((n_graphs, 7)), np.zeros((n_graphs, 7))
+    for g in range(n_graphs):
+        out = poses_abs[g * n_nodes + template[0, k]] - pose_edges[g * Ep + k]
+        pred[g] = np.concatenate([out[:3] * sc + m, qexp(out[3:])])
+        t = poses_abs[g * n_nodes]
+        targ[g] = np.concatenate([t[:3] * sc + m, qexp(t[3:])])
+    return pred, targ
+
+
 # --------------------------------------------------------------------------------------
 # Deterministic synthetic parameters / inputs shared by fixtures, tests and the bench
 # --------------------------------------------------------------------------------------

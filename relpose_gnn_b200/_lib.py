@@ -123,6 +123,8 @@ SIGNATURES = {
     "rpg_layer_bwd_ws_floats": (I64, [I, I64, I64]),
     "rpg_reduce_splits_batch": (I, [P, P]),
     "rpg_upload_words": (I, [P, P, I64, P]),
+    "rpg_qexp": (I, [P, I64, P, P]),
+    "rpg_eval_compose": (I, [P, P, C.POINTER(Graph), I, P, P, P, P, P]),
     "rpg_layer_bwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs),
                           C.POINTER(LayerGrads), P]),
 }

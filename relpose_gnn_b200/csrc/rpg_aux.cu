@@ -856,6 +856,48 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int splits,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation composition (test.py:227-243) and qexp (pose_utils.py:340-348): one thread per graph / per vector.
+// Double arithmetic: G threads of work, and the reference's own numbers are numpy on the host.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void qexp_d(const double* v, float* q) {
+    const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double sc = n > 0.0 ? sin(n) / n : 1.0;          // np.sinc(n / pi)
+    q[0] = (float)cos(n); q[1] = (float)(sc * v[0]); q[2] = (float)(sc * v[1]); q[3] = (float)(sc * v[2]);
+}
+__global__ void qexp_kernel(const float* __restrict__ v, long long n, float* __restrict__ q) {
+    pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double d[3] = {v[i * 3], v[i * 3 + 1], v[i * 3 + 2]};
+        qexp_d(d, q + i * 4);
+    }
+}
+struct EvalNorm { float m[3], s[3]; };
+__global__ void eval_compose_kernel(const float* __restrict__ pred_edges, const float* __restrict__ poses,
+                                    const int* __restrict__ tsrc, int G, int N, int Ep, int ref_k, EvalNorm nm,
+                                    float* __restrict__ out_pred, float* __restrict__ out_targ) {
+    pdl_prologue();
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+        const float* ap = poses + ((long long)g * N + __ldg(tsrc + ref_k)) * 6;      // absolute pose of the reference image
+        const float* rp = pred_edges + ((long long)g * Ep + ref_k) * 6;              // predicted RP = p[src] - p[query]
+        const float* tq = poses + (long long)g * N * 6;                              // ground truth of the query (node 0)
+        double o[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o[j] = (double)ap[j] - (double)rp[j];
+        float* op = out_pred + (long long)g * 7;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) op[j] = (float)(o[j] * nm.s[j] + nm.m[j]);
+        qexp_d(o + 3, op + 3);
+        if (out_targ) {
+            float* ot = out_targ + (long long)g * 7;
+            const double t[3] = {tq[3], tq[4], tq[5]};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ot[j] = (float)((double)tq[j] * nm.s[j] + nm.m[j]);
+            qexp_d(t, ot + 3);
+        }
+    }
+}
+
 // Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
 // never queue behind a large host->device copy of another stream.
 constexpr int UPLOAD_WORDS = 2032;
@@ -1294,6 +1336,23 @@ int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, in
     launch_pdl(reduce_splits_kernel, dim3(grid_for((long long)rows * cols, 256)), dim3(256), 0, as_stream(stream), partial, splits, split_stride, rows,
                                                                                               cols, out, ldo, accumulate);
     return check_launch("reduce_splits_kernel");
+}
+
+int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream) {
+    if (!v || !q || n <= 0) return set_error(RPG_E_ARG, "qexp: bad arguments");
+    launch_pdl(qexp_kernel, dim3(grid_for(n, 128)), dim3(128), 0, as_stream(stream), v, n, q);
+    return check_launch("qexp_kernel");
+}
+
+int rpg_eval_compose(const float* pred_edges, const float* poses, const rpg_graph_t* graph, int ref_k, const float* pose_m,
+                     const float* pose_s, float* out_pred, float* out_targ, rpg_stream_t stream) {
+    if (!pred_edges || !poses || !graph || !out_pred || ref_k < 0 || ref_k >= graph->Ep)
+        return set_error(RPG_E_ARG, "eval_compose: bad arguments");
+    EvalNorm nm;
+    for (int j = 0; j < 3; ++j) { nm.m[j] = pose_m ? pose_m[j] : 0.f; nm.s[j] = pose_s ? pose_s[j] : 1.f; }
+    launch_pdl(eval_compose_kernel, dim3(grid_for(graph->G, 128)), dim3(128), 0, as_stream(stream), pred_edges, poses,
+               graph->src, graph->G, graph->N, graph->Ep, ref_k, nm, out_pred, out_targ);
+    return check_launch("eval_compose_kernel");
 }
 
 int rpg_upload_words(int32_t* dst, const int32_t* src_host, int64_t n, rpg_stream_t stream) {

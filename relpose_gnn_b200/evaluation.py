@@ -1,0 +1,43 @@
+"""Evaluation composition of the reference (test.py:222-243): from the predicted relative poses of the edges into the
+query image (node 0 of every graph) and the known absolute pose of a reference image to the absolute pose of the query,
+with the log-quaternion mapped to a unit quaternion (pose_utils.qexp, pose_utils.py:340-348).  The reference does this
+in numpy, one graph per batch; here it is one small kernel over all graphs of the batch."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, graph as graph_mod
+from .ops import _stream, check
+
+
+def qexp(v):
+    """[n, 3] log-quaternions (CUDA tensor) -> [n, 4] unit quaternions [cos|v|, sinc(|v|/pi) v]."""
+    if not v.is_cuda:
+        raise ValueError("relpose_gnn_b200.qexp needs a CUDA tensor")
+    v = v.float().contiguous().reshape(-1, 3)
+    q = torch.empty(v.size(0), 4, dtype=torch.float32, device=v.device)
+    check(_lib.load().rpg_qexp(v.data_ptr(), v.size(0), q.data_ptr(), _stream(v)), "rpg_qexp")
+    return q
+
+
+def compose_query_pose(pred_edges, poses_abs, edge_index, ref_node=0, pose_m=None, pose_s=None):
+    """pred_edges [Et, 6] (output_R of the model), poses_abs [Nt, 6] (data.y), edge_index of the batch.
+    Returns (pred [G, 7], target [G, 7]) = (t, unit quaternion) of every graph's query image (node 0), translations
+    un-normalised with (pose_s, pose_m) as in test.py:241-243.  `ref_node` picks the ref_node-th edge into node 0."""
+    if not pred_edges.is_cuda:
+        raise ValueError("relpose_gnn_b200.compose_query_pose needs CUDA tensors")
+    g = graph_mod.from_edge_index(edge_index, poses_abs.size(0))
+    into0 = np.flatnonzero(g.dst_np == 0)
+    if ref_node >= into0.size:
+        raise ValueError(f"ref_node {ref_node}: only {into0.size} edges end in node 0")
+    ref_k = int(into0[ref_node])
+    pred_edges = pred_edges.float().contiguous()
+    poses_abs = poses_abs.float().contiguous()
+    out_p = torch.empty(g.G, 7, dtype=torch.float32, device=pred_edges.device)
+    out_t = torch.empty(g.G, 7, dtype=torch.float32, device=pred_edges.device)
+    m = (C.c_float * 3)(*[float(x) for x in pose_m]) if pose_m is not None else None
+    s = (C.c_float * 3)(*[float(x) for x in pose_s]) if pose_s is not None else None
+    check(_lib.load().rpg_eval_compose(pred_edges.data_ptr(), poses_abs.data_ptr(), g.byref(), ref_k, m, s,
+                                       out_p.data_ptr(), out_t.data_ptr(), _stream(pred_edges)), "rpg_eval_compose")
+    return out_p, out_t

@@ -81,7 +81,8 @@ def test_layer_against_reference_fixture(tag):
 
 
 @pytest.mark.parametrize("D,N,Gn,drop_edges", [(512, 9, 5, False), (512, 17, 3, False), (512, 8, 16, True),
-                                               (256, 9, 33, True), (128, 3, 50, False), (1024, 8, 2, False)])
+                                               (256, 9, 33, True), (128, 3, 50, False), (1024, 8, 2, False),
+                                               (2048, 8, 2, True)])
 def test_layer_against_oracle(D, N, Gn, drop_edges):
     """Forward against the plain oracle; backward against the oracle with the kernel's activation pattern imposed.
     Inputs, weights and cotangents are bf16-representable so that only the kernel arithmetic is measured."""
@@ -272,8 +273,9 @@ def test_stack_backward_against_mask_matched_oracle():
         assert rel(model.get_parameter(k).grad, p[k].grad) < 2e-2, k
 
 
-def test_stack_against_oracle_full_width_with_dropout():
-    D, N, Gn = 512, 9, 6
+@pytest.mark.parametrize("D,N,Gn", [(512, 9, 6), (1024, 8, 3), (2048, 8, 2)])
+def test_stack_against_oracle_full_width_with_dropout(D, N, Gn):
+    """D = 1024 / 2048 are the widths of the released R2 / R3 checkpoints (the tested set)."""
     case = R.synth_stack_case(D, N, Gn, 4242, droprate=0.5, edge_dropout=True)
     model = rpg.RelPoseGNN(D, D, D, droprate=0.5).to(dev())
     model.load_state_dict({k: v.float() for k, v in case["params"].items()}, strict=False)
@@ -395,3 +397,35 @@ def test_fp32_mode_stack_against_oracle(droprate):
         pn, pe, _ = model(case["x"].float().to(dev()), case["edge_index"].to(dev()), keep_x=kx, keep_e=ke)
     pn_o, pe_o, _, _ = R.stack_forward(case["params"], case["x"], case["edge_index"], 2, droprate, case["keep_x"], case["keep_e"])
     assert rel(pn, pn_o) < TOL_FP32 and rel(pe, pe_o) < TOL_FP32, (rel(pn, pn_o), rel(pe, pe_o))
+
+
+def test_qexp_and_eval_composition_against_reference_fixtures():
+    """pose_utils.qexp and the evaluation composition of test.py:227-243."""
+    fx = np.load(os.path.join(GOLD, "qexp.npz"))
+    q = rpg.qexp(torch.from_numpy(fx["v"]).float().to(dev()))
+    assert np.allclose(q.cpu().numpy(), fx["q"], rtol=0, atol=1e-6)
+    ec = np.load(os.path.join(GOLD, "eval_compose.npz"))
+    fc = np.load(os.path.join(GOLD, "fc_enumeration.npz"))
+    for case in range(5):
+        n, ref_node, _ = [int(v) for v in ec[f"case{case}_meta"]]
+        ei = torch.from_numpy(fc[f"fc_N{n}"]).to(dev())
+        pred, targ = rpg.compose_query_pose(torch.from_numpy(ec[f"case{case}_output_R"]).to(dev()),
+                                            torch.from_numpy(ec[f"case{case}_target"]).to(dev()), ei, ref_node,
+                                            ec[f"case{case}_pose_m"], ec[f"case{case}_pose_s"])
+        assert np.allclose(pred.cpu().numpy()[0], ec[f"case{case}_pred7"], rtol=0, atol=2e-6)
+        assert np.allclose(targ.cpu().numpy()[0], ec[f"case{case}_targ7"][0], rtol=0, atol=2e-6)
+    # a batch of graphs with an edge-dropout template against the oracle
+    Gn, N = 37, 9
+    keep = R.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(3).random_sample(N * (N - 1) // 2))
+    tmpl = R.apply_edge_dropout(R.fc_edge_index(N), keep)
+    ei = R.batched_edge_index(tmpl, Gn, N)
+    gen = torch.Generator().manual_seed(5)
+    pe = torch.randn(ei.size(1), 6, generator=gen) * 0.3
+    pa = torch.randn(Gn * N, 6, generator=gen) * 0.5
+    into0 = int((tmpl[1] == 0).sum())
+    for ref_node in range(min(into0, 3)):
+        pred, targ = rpg.compose_query_pose(pe.to(dev()), pa.to(dev()), ei.to(dev()), ref_node, [0.1, -0.2, 0.3], [2.0, 1.5, 0.5])
+        po, to = R.compose_eval_batch(pe.numpy(), pa.numpy(), tmpl.numpy(), Gn, N, ref_node, [0.1, -0.2, 0.3], [2.0, 1.5, 0.5])
+        assert np.allclose(pred.cpu().numpy(), po, rtol=0, atol=2e-6) and np.allclose(targ.cpu().numpy(), to, rtol=0, atol=2e-6)
+    with pytest.raises(ValueError):
+        rpg.compose_query_pose(pe.to(dev()), pa.to(dev()), ei.to(dev()), into0)

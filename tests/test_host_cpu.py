@@ -131,3 +131,12 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_evaluation_api_refuses_cpu_tensors():
+    """No CPU fallback: the evaluation helpers raise on host tensors."""
+    import relpose_gnn_b200 as rpg
+    with pytest.raises(ValueError):
+        rpg.qexp(torch.zeros(4, 3))
+    with pytest.raises(ValueError):
+        rpg.compose_query_pose(torch.zeros(72, 6), torch.zeros(9, 6), torch.zeros(2, 72, dtype=torch.long))

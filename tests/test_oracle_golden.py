@@ -48,6 +48,18 @@ def test_edge_dropout_mask_matches_reference():
     assert keep.all() and fx["none_survive_tiled"].all()
 
 
+def test_eval_composition_matches_reference():
+    """test.py:227-243 executed on seeded single graphs (oracle/make_golden.py: golden_eval_compose)."""
+    fx = np.load(os.path.join(G, "eval_compose.npz"))
+    fc = np.load(os.path.join(G, "fc_enumeration.npz"))
+    for case in range(5):
+        n, ref_node, _ = [int(v) for v in fx[f"case{case}_meta"]]
+        pred, targ = R.compose_eval_batch(fx[f"case{case}_output_R"], fx[f"case{case}_target"], fc[f"fc_N{n}"], 1, n,
+                                          ref_node, fx[f"case{case}_pose_m"], fx[f"case{case}_pose_s"])
+        assert np.allclose(pred[0], fx[f"case{case}_pred7"], rtol=0, atol=2e-6)     # the reference computes in fp32
+        assert np.allclose(targ[0], fx[f"case{case}_targ7"][0], rtol=0, atol=2e-6)
+
+
 def test_qexp_matches_reference():
     fx = np.load(os.path.join(G, "qexp.npz"))
     assert np.allclose(R.qexp(fx["v"]), fx["q"], atol=1e-14)
