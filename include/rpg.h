@@ -293,6 +293,18 @@ int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream);
 int rpg_eval_compose(const float* pred_edges, const float* poses, const rpg_graph_t* graph, int ref_k,
                      const float* pose_m, const float* pose_s, float* out_pred, float* out_targ, rpg_stream_t stream);
 
+/* Per-edge gather of node rows through the template (simpleConv, my_gnn_layer.py:394-412: its first Linear acts on
+ * cat[x_i, x_j] only, so it factors into two per-node products and this gather):
+ *   out[e] = act(pa[node_a(e)] + pb[node_b(e)] + bias) * bit(e),   which_x: 0 = source, 1 = destination of edge e;
+ * pb, bias, mask_bits ([Et, D/8] bit pattern), out_bits (pattern of the result) may be NULL; relu: 0 / 1. */
+int rpg_edge_gather(const rpg_bf16* pa, int lda, int which_a, const rpg_bf16* pb, int ldb, int which_b, const float* bias,
+                    const rpg_graph_t* graph, int D, int relu, const uint8_t* mask_bits, rpg_bf16* out, int ldo,
+                    uint8_t* out_bits, rpg_stream_t stream);
+
+/* out[r, :] = v[r, :] * scale[r % mod]   (bf16 rows; the 1/deg of a mean's backward). */
+int rpg_scale_rows(const rpg_bf16* v, int ldv, int64_t rows, int D, const float* scale, int mod, rpg_bf16* out, int ldo,
+                   rpg_stream_t stream);
+
 /* Column sums (bias gradients): out[c] (+)= sum_r w[r % mod] * v[r, c]; deterministic; row_w may be NULL. */
 int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod,
                     float* out, int accumulate, float* scratch, rpg_stream_t stream);
@@ -323,6 +335,12 @@ typedef struct {
   const rpg_bf16* W1uT;           /* [2D, D] */
   /* fp32 biases */
   const float* b1e, *b2e, *b1m, *b2m, *bgtp, *bW, *b1u, *b2u;
+  /* 0 = simpleConvEdge_upt (above).
+   * 1 = simpleConvEdge (my_gnn_layer.py:242-274): message = att(mlp(cat[x_i, x_j, e'])) and NO update MLP, the layer
+   *     output is the mean itself (acts.a).  Then Wn is [4D, D] with rows edge_mlp.0[:,0:D] | edge_mlp.0[:,D:2D] |
+   *     mlp.0[:,D:2D] (x_j = source) | mlp.0[:,0:D] (x_i = destination), WnT is [D, 4D], W1m_e = mlp.0[:,2D:3D],
+   *     acts.P / grads.dP are [Nt, 4D], g_mlp0_w is [D, 3D]; W1u, W2u, h3, out, dh3, dxu and the g_upd* are unused. */
+  int variant;
 } rpg_layer_weights_t;
 
 typedef struct {                  /* activations of one layer call; all bf16 unless noted               */

@@ -122,6 +122,33 @@ def golden_layer(tag, D, N, G, seed, store_params):
     print(f"layer_{tag}: out {out['out_f64'].shape} e_new {out['e_new_f64'].shape}")
 
 
+def golden_sibling(kind, tag, D, N, G, seed):
+    """simpleConvEdge / simpleConv (my_gnn_layer.py:242-274, 394-412) forward + backward, float64 reference run."""
+    gnn, _, _ = pyg_shim.import_reference()
+    case = R.synth_sibling_case(kind, D, N, G, seed)
+    params, x, e, ei = case["params"], case["x"], case["e"], case["edge_index"]
+    layer = (gnn.simpleConvEdge(D, D, D) if kind == "convedge" else gnn.simpleConv(D, D)).double()
+    _load_into(layer, params)
+    xd = x.clone().requires_grad_(True)
+    out = {}
+    if kind == "convedge":
+        ed = e.clone().requires_grad_(True)
+        o, en = layer(xd, ei, ed)
+        ((o * case["ct_out"]).sum() + (en * case["ct_e"]).sum()).backward()
+        out["e_new_f64"] = en.detach().numpy()
+        out["de"] = ed.grad.numpy()
+    else:
+        o = layer(xd, ei)
+        (o * case["ct_out"]).sum().backward()
+    out["out_f64"] = o.detach().numpy()
+    out["dx"] = xd.grad.numpy()
+    for k, p in layer.named_parameters():
+        out["grad." + k] = p.grad.numpy()
+    out["meta"] = np.array([D, N, G, seed])
+    np.savez_compressed(os.path.join(OUT, f"{kind}_{tag}.npz"), **out)
+    print(f"{kind}_{tag}: out {out['out_f64'].shape}")
+
+
 class _StubFE(torch.nn.Module):
     """Stands in for torchvision resnet34 (train.py:173): identity features, NOT the target path."""
 
@@ -252,6 +279,11 @@ def main():
     golden_fc_enumeration()
     golden_edge_dropout()
     golden_qexp()
+    golden_eval_compose()
+    golden_sibling("convedge", "D128_N9_G2", 128, 9, 2, 200)
+    golden_sibling("convedge", "D128_N5_G3", 128, 5, 3, 201)
+    golden_sibling("conv", "D128_N9_G2", 128, 9, 2, 210)
+    golden_sibling("conv", "D128_N4_G3", 128, 4, 3, 211)
     golden_layer("D128_N9_G2", 128, 9, 2, 100, store_params=True)
     golden_layer("D128_N4_G3", 128, 4, 3, 101, store_params=True)
     golden_layer("D512_N8_G2", 512, 8, 2, 102, store_params=False)

@@ -135,6 +135,43 @@ def layer_forward(p, x, edge_index, e, return_intermediates=False, relu_masks=No
     return out, e_new
 
 
+def conv_edge_forward(p, x, edge_index, e, relu_masks=None):
+    """simpleConvEdge.forward, my_gnn_layer.py:253-274: edge model, message = att(mlp(cat[x_i, x_j, e'])) with
+    x_i = x[edge_index[1]] (destination), x_j = x[edge_index[0]] (source) [3p PyG], mean over destinations; no update."""
+    rm = relu_masks or {}
+    row, col = edge_index[0], edge_index[1]
+    e_new = edge_model_forward(p, x[row], x[col], e, mask=rm.get("h1"))     # :255-257
+    h = torch.cat([x[col], x[row], e_new], dim=1)                           # message, :269
+    h = _relu(_linear(h, p["mlp.0.weight"], p["mlp.0.bias"]), rm.get("h2"))
+    m = _linear(h, p["mlp.2.weight"], p["mlp.2.bias"])
+    z = attention_block(p, m)                                               # :271
+    return scatter_mean(z, col, x.size(0)), e_new                           # :262-264
+
+
+def conv_forward(p, x, edge_index, relu_mask=None):
+    """simpleConv.forward, my_gnn_layer.py:394-412: mean over destinations of mlp(cat[x_i, x_j])."""
+    row, col = edge_index[0], edge_index[1]
+    h = _relu(_linear(torch.cat([x[col], x[row]], dim=1), p["mlp.0.weight"], p["mlp.0.bias"]), relu_mask)
+    return scatter_mean(_linear(h, p["mlp.2.weight"], p["mlp.2.bias"]), col, x.size(0))
+
+
+def CONV_EDGE_SHAPES(D):
+    s = {k: v for k, v in LAYER_SHAPES(D).items() if not k.startswith("mlp_updating.")}
+    s["mlp.0.weight"] = (D, 3 * D)
+    return s
+
+
+def CONV_SHAPES(D):
+    return {"mlp.0.weight": (D, 2 * D), "mlp.0.bias": (D,), "mlp.2.weight": (D, D), "mlp.2.bias": (D,)}
+
+
+def synth_sibling_case(kind, D, N, G, seed, dtype=torch.float64):
+    """Inputs of the `convedge_*` / `conv_*` golden fixtures (oracle/make_golden.py:golden_sibling)."""
+    case = synth_layer_case(D, N, G, seed, dtype)
+    case["params"] = synth_params(CONV_EDGE_SHAPES(D) if kind == "convedge" else CONV_SHAPES(D), seed, dtype)
+    return case
+
+
 # --------------------------------------------------------------------------------------
 # Caller side: the GNN part of PoseNetX_R2.forward
 # --------------------------------------------------------------------------------------

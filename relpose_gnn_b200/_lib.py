@@ -47,7 +47,7 @@ class LayerWeights(C.Structure):
     _fields_ = [("D", I)] + [(n, P) for n in (
         "Wn", "W1e_e", "W2e", "W1m_e", "W2m", "Wgtp", "WW", "WWI", "W1u", "W2u",
         "WnT", "W1e_eT", "W2eT", "W1m_eT", "W2mT", "W2uT", "WgtpT", "WWT", "W1uT",
-        "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")]
+        "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")] + [("variant", I)]
 
 
 class LayerActs(C.Structure):
@@ -124,6 +124,8 @@ SIGNATURES = {
     "rpg_reduce_splits_batch": (I, [P, P]),
     "rpg_upload_words": (I, [P, P, I64, P]),
     "rpg_qexp": (I, [P, I64, P, P]),
+    "rpg_scale_rows": (I, [P, I, I64, I, P, I, P, I, P]),
+    "rpg_edge_gather": (I, [P, I, I, P, I, I, P, C.POINTER(Graph), I, I, P, P, I, P, P]),
     "rpg_eval_compose": (I, [P, P, C.POINTER(Graph), I, P, P, P, P, P]),
     "rpg_layer_bwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs),
                           C.POINTER(LayerGrads), P]),

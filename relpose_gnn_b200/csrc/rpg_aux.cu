@@ -427,6 +427,23 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
     }
 }
 
+__global__ void scale_rows_kernel(const bf16* __restrict__ v, int ldv, long long rows, int D, const float* __restrict__ scale,
+                                  int mod, bf16* __restrict__ out, int ldo) {
+    pdl_prologue();
+    const int tpr = D >> 3;
+    const long long total = rows * tpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / tpr;
+        const int c = (int)(t - row * tpr) << 3;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(v + row * ldv + c)), f);
+        const float s = __ldg(scale + (int)(row % mod));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] *= s;
+        *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(f);
+    }
+}
+
 // e0 = relu(pmin[node(min(s,t))] + pmax[node(max(s,t))] + bias)      (posenet.py:1014-1017, 1053-1055)
 template <typename I>
 __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, const float* __restrict__ bias,
@@ -457,6 +474,55 @@ __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, cons
 #pragma unroll
             for (int q = 0; q < 8; ++q) m |= (uint32_t)(a[q] > 0.f) << q;
             bits[row * (D >> 3) + (c >> 3)] = (uint8_t)m;
+        }
+    }
+}
+
+// General per-edge gather of node rows through the template (sibling layers without an edge-feature GEMM):
+//   out[e] = act( pa[node_a(e)] + pb[node_b(e)] + bias ) * bit(e)      node_x = source (0) or destination (1)
+// pb, bias, mask_bits optional; act = ReLU or identity; optional pattern output.
+__global__ void edge_gather_kernel(const bf16* __restrict__ pa, int lda, int which_a, const bf16* __restrict__ pb, int ldb,
+                                   int which_b, const float* __restrict__ bias, const int* __restrict__ tsrc,
+                                   const int* __restrict__ tdst, long long Et, int N, int Ep, int D, int relu,
+                                   const uint8_t* __restrict__ mask_bits, bf16* __restrict__ out, int ldo,
+                                   uint8_t* __restrict__ out_bits) {
+    pdl_prologue();
+    const int tpr = D >> 3;
+    const long long total = Et * tpr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / tpr;
+        const int c = (int)(t - row * tpr) << 3;
+        const long long g = row / Ep;
+        const int k = (int)(row - g * Ep);
+        const int s = __ldg(tsrc + k), d = __ldg(tdst + k);
+        float a[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pa + (g * N + (which_a ? d : s)) * lda + c)), a);
+        if (pb) {
+            float b[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(pb + (g * N + (which_b ? d : s)) * ldb + c)), b);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] += b[q];
+        }
+        if (bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+            a[0] += b0.x; a[1] += b0.y; a[2] += b0.z; a[3] += b0.w; a[4] += b1.x; a[5] += b1.y; a[6] += b1.z; a[7] += b1.w;
+        }
+        if (relu) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = fmaxf(a[q], 0.f);
+        }
+        if (mask_bits) {
+            const uint32_t m = mask_bits[row * (D >> 3) + (c >> 3)];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (!((m >> q) & 1u)) a[q] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(a);
+        if (out_bits) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m |= (uint32_t)(a[q] > 0.f) << q;
+            out_bits[row * (D >> 3) + (c >> 3)] = (uint8_t)m;
         }
     }
 }
@@ -1336,6 +1402,28 @@ int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, in
     launch_pdl(reduce_splits_kernel, dim3(grid_for((long long)rows * cols, 256)), dim3(256), 0, as_stream(stream), partial, splits, split_stride, rows,
                                                                                               cols, out, ldo, accumulate);
     return check_launch("reduce_splits_kernel");
+}
+
+int rpg_edge_gather(const rpg_bf16* pa, int lda, int which_a, const rpg_bf16* pb, int ldb, int which_b, const float* bias,
+                    const rpg_graph_t* graph, int D, int relu, const uint8_t* mask_bits, rpg_bf16* out, int ldo,
+                    uint8_t* out_bits, rpg_stream_t stream) {
+    if (!pa || !graph || !out || D % 8 || lda % 8 || ldo % 8 || (pb && ldb % 8) || (which_a & ~1) || (which_b & ~1))
+        return set_error(RPG_E_ARG, "edge_gather: bad arguments");
+    const long long Et = (long long)graph->G * graph->Ep;
+    launch_pdl(edge_gather_kernel, dim3(grid_for(Et * (D / 8), 256)), dim3(256), 0, as_stream(stream),
+               reinterpret_cast<const bf16*>(pa), lda, which_a, reinterpret_cast<const bf16*>(pb), ldb, which_b, bias,
+               graph->src, graph->dst, Et, graph->N, graph->Ep, D, relu, mask_bits, reinterpret_cast<bf16*>(out), ldo,
+               out_bits);
+    return check_launch("edge_gather_kernel");
+}
+
+int rpg_scale_rows(const rpg_bf16* v, int ldv, int64_t rows, int D, const float* scale, int mod, rpg_bf16* out, int ldo,
+                   rpg_stream_t stream) {
+    if (!v || !scale || !out || rows <= 0 || D % 8 || ldv % 8 || ldo % 8 || mod <= 0)
+        return set_error(RPG_E_ARG, "scale_rows: bad arguments");
+    launch_pdl(scale_rows_kernel, dim3(grid_for(rows * (D / 8), 256)), dim3(256), 0, as_stream(stream),
+               reinterpret_cast<const bf16*>(v), ldv, rows, D, scale, mod, reinterpret_cast<bf16*>(out), ldo);
+    return check_launch("scale_rows_kernel");
 }
 
 int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream) {

@@ -219,9 +219,10 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     const int cp = pad64(c);
     rpg_gemm_t g;
 
-    // (1) per-node projections  P = x [W1e_src; W1e_dst; W1m_src]^T                      [Nt, 3D]
-    g = nt((int)Nt, 3 * D, t->x, D, D, w->Wn, D);
-    g.out = t->P; g.ldo = 3 * D;
+    // (1) per-node projections  P = x [W1e_src; W1e_dst; W1m_src (; W1m_dst)]^T          [Nt, 3D] ([Nt, 4D] for variant 1)
+    const int np = w->variant == 1 ? 4 : 3, ldP = np * D;
+    g = nt((int)Nt, ldP, t->x, D, D, w->Wn, D);
+    g.out = t->P; g.ldo = ldP;
     RPG_TRY(gemm_launch(&g, s));
 
     // (2) edge MLP layer 1 (my_gnn_layer.py:232,237-238): h1 = relu(e W1e_e^T + P_s[src] + P_d[dst] + b)
@@ -229,11 +230,11 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g.bias = w->b1e;
     if (gr->sel_src && gr->sel_dst) {            // gathers as one-hot K panels (plain epilogue)
         g.n_gseg = 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
-        g.gsel[0] = gr->sel_src; g.gsrc[0] = t->P;     g.gsrc_ld[0] = 3 * D;
-        g.gsel[1] = gr->sel_dst; g.gsrc[1] = t->P + D; g.gsrc_ld[1] = 3 * D;
+        g.gsel[0] = gr->sel_src; g.gsrc[0] = t->P;     g.gsrc_ld[0] = ldP;
+        g.gsel[1] = gr->sel_dst; g.gsrc[1] = t->P + D; g.gsrc_ld[1] = ldP;
     } else {
-        g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
-        g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = 3 * D;
+        g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = ldP;
+        g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = ldP;
     }
     g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
     g.out = t->h1; g.ldo = D; g.out_bits = t->h1_bits; g.out_bits_ld = D / 8;
@@ -248,11 +249,14 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // (4) message MLP layer 1 (my_gnn_layer.py:280,305): h2 = relu(e' W1m_e^T + P_m[src] + b)   (x_j = source)
     g = nt((int)Et, D, t->e_new, D, D, w->W1m_e, D);
     g.bias = w->b1m;
-    if (gr->sel_src) {
-        g.n_gseg = 1; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
-        g.gsel[0] = gr->sel_src; g.gsrc[0] = t->P + 2 * D; g.gsrc_ld[0] = 3 * D;
+    //     variant 1 (my_gnn_layer.py:269-270): + P_mi[dst]   (x_i = destination)
+    if (gr->sel_src && (np == 3 || gr->sel_dst)) {
+        g.n_gseg = np - 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
+        g.gsel[0] = gr->sel_src; g.gsrc[0] = t->P + 2 * D; g.gsrc_ld[0] = ldP;
+        if (np == 4) { g.gsel[1] = gr->sel_dst; g.gsrc[1] = t->P + 3 * D; g.gsrc_ld[1] = ldP; }
     } else {
-        g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = 3 * D;
+        g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = ldP;
+        if (np == 4) { g.gadd[1] = t->P + 3 * D; g.gmap[1] = gr->dst; g.gadd_ld[1] = ldP; }
     }
     g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
     g.out = t->h2; g.ldo = D; g.out_bits = t->h2_bits; g.out_bits_ld = D / 8;
@@ -280,6 +284,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
 
     // (9) mean over incoming edges (PyG aggregate [3p], my_gnn_layer.py:301)
     RPG_TRY(rpg_aggregate_mean(t->z, D, gr, D, t->a, D, stream));
+    if (w->variant == 1) return 0;               // simpleConvEdge: the mean is the layer output (no update step)
 
     // (10) update MLP (my_gnn_layer.py:284-286,309-311): out = relu([x | a] W1u^T + b) W2u^T + b
     g = nt((int)Nt, D, t->x, D, D, w->W1u, 2 * D);
@@ -372,7 +377,7 @@ int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt) {
     // column sums (M <= 3 D) and the 64-float rounding.  Sized for up to 160 SMs.
     int sms = sm_count_cached();
     if (sms <= 0 || sms > 160) sms = 160;
-    return 11LL * ((long long)sms * 128 * 256 + 3LL * D * D + (long long)sms * 3 * D + 64);
+    return 11LL * ((long long)sms * 128 * 256 + 4LL * D * D + (long long)sms * 4 * D + 64);
 }
 
 int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg_layer_acts_t* t,
@@ -385,9 +390,15 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     const int sms = sm_count_cached();
     rpg_gemm_t g;
     const bool have_out = b->d_out != nullptr;
+    const bool v1 = w->variant == 1;
+    const int np = v1 ? 4 : 3, ldP = np * D;
 
+    if (have_out && v1) {
+        // simpleConvEdge: out IS the mean, so dan = d_out / deg directly
+        RPG_TRY(rpg_scale_rows(b->d_out, D, Nt, D, gr->inv_deg, gr->N, b->dan, D, stream));
+    }
     // ---- update MLP backward (only when a gradient reaches `out`)
-    if (have_out) {
+    if (have_out && !v1) {
         // dh3 = (d_out W2u) * [h3 > 0]
         g = nt((int)Nt, D, b->d_out, D, D, w->W2uT, D);
         if (t->h3_bits) { g.mask_bits = t->h3_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->h3; g.mask_ld = D; }
@@ -400,6 +411,8 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         g = nt((int)Nt, D, b->dh3, D, D, w->W1uT + (size_t)D * D, D);
         g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; g.out = b->dan; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
+    }
+    if (have_out) {
         // dy per destination node: dyn = dan WW   fp32 [Nt, c]
         g = nt((int)Nt, c, b->dan, D, D, w->WWT, D);
         g.out_f32 = b->dyn; g.ldo_f32 = c;
@@ -445,14 +458,15 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     RPG_TRY(gemm_launch(&g, s));
 
     // ---- node side: dP = [sum_src dh1 | sum_dst dh1 | sum_src dh2], dx = dP Wn + dx_u
-    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 1, b->dP, 3 * D, stream));
-    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 0, b->dP + D, 3 * D, stream));
+    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 1, b->dP, ldP, stream));
+    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 0, b->dP + D, ldP, stream));
     if (have_out) {
-        RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 1, b->dP + 2 * D, 3 * D, stream));
-        g = nt((int)Nt, D, b->dP, 3 * D, 3 * D, w->WnT, 3 * D);
-        g.resid = b->dxu; g.resid_ld = D;
+        RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 1, b->dP + 2 * D, ldP, stream));
+        if (v1) RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 0, b->dP + 3 * D, ldP, stream));
+        g = nt((int)Nt, D, b->dP, ldP, ldP, w->WnT, ldP);
+        if (!v1) { g.resid = b->dxu; g.resid_ld = D; }
     } else {
-        g = nt((int)Nt, D, b->dP, 2 * D, 3 * D, w->WnT, 3 * D);
+        g = nt((int)Nt, D, b->dP, 2 * D, ldP, w->WnT, ldP);
     }
     if (b->mask_dx) {
         if (t->x_bits) { g.mask_bits = t->x_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->x; g.mask_ld = D; }
@@ -470,17 +484,21 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     RPG_TRY(q.wgrad(b->dh1, D, D, t->e, D, D, Et, b->g_edge0_w + 2 * D, 3 * D, b->g_edge0_b));
     // node-side blocks in one launch: dP^T x = [edge_mlp.0[:,0:D]; edge_mlp.0[:,D:2D]; mlp.0[:,0:D]]
     {
-        const int Mp = have_out ? 3 * D : 2 * D;
-        RPG_TRY(q.partials(b->dP, 3 * D, Mp, t->x, D, D, Nt, false, &part, &splits));
+        const int Mp = have_out ? ldP : 2 * D;
+        RPG_TRY(q.partials(b->dP, ldP, Mp, t->x, D, D, Nt, false, &part, &splits));
         const long long stride = (long long)Mp * D;
         RPG_TRY(q.add(part, splits, stride, D, D, b->g_edge0_w, 3 * D));
         RPG_TRY(q.add(part + (size_t)D * D, splits, stride, D, D, b->g_edge0_w + D, 3 * D));
-        if (have_out) RPG_TRY(q.add(part + 2 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w, 2 * D));
+        if (have_out && !v1) RPG_TRY(q.add(part + 2 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w, 2 * D));
+        if (have_out && v1) {                     // mlp.0 = [x_i (dst) | x_j (src) | e']: block 2 is x_j, block 3 is x_i
+            RPG_TRY(q.add(part + 2 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w + D, 3 * D));
+            RPG_TRY(q.add(part + 3 * (size_t)D * D, splits, stride, D, D, b->g_mlp0_w, 3 * D));
+        }
     }
     if (have_out) {
         // mlp.2: dW = dm^T h2 ; mlp.0 edge columns [D,2D): dW = dh2^T e'
         RPG_TRY(q.wgrad(b->dm, D, D, t->h2, D, D, Et, b->g_mlp2_w, D, b->g_mlp2_b));
-        RPG_TRY(q.wgrad(b->dh2, D, D, t->e_new, D, D, Et, b->g_mlp0_w + D, 2 * D, b->g_mlp0_b));
+        RPG_TRY(q.wgrad(b->dh2, D, D, t->e_new, D, D, Et, b->g_mlp0_w + (v1 ? 2 * D : D), v1 ? 3 * D : 2 * D, b->g_mlp0_b));
         // att.g / theta / phi: one launch dgtp^T m [3c, D], three folds ; biases = colsum(dgtp)
         RPG_TRY(q.partials(b->dgtp, c3p, c3, t->m, D, D, Et, true, &part, &splits));
         {
@@ -498,10 +516,12 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         RPG_TRY(rpg_edge_to_node_sum(t->y, cp, gr, cp, 0, b->ysum, cp, stream));
         RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
         RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
-        // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
-        RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));
-        RPG_TRY(q.wgrad(b->dh3, D, D, t->x, D, D, Nt, b->g_upd0_w, 2 * D, b->g_upd0_b));
-        RPG_TRY(q.wgrad(b->dh3, D, D, t->a, D, D, Nt, b->g_upd0_w + D, 2 * D));
+        if (!v1) {
+            // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
+            RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));
+            RPG_TRY(q.wgrad(b->dh3, D, D, t->x, D, D, Nt, b->g_upd0_w, 2 * D, b->g_upd0_b));
+            RPG_TRY(q.wgrad(b->dh3, D, D, t->a, D, D, Nt, b->g_upd0_w + D, 2 * D));
+        }
     }
     RPG_TRY(q.flush());
     return 0;

@@ -31,6 +31,11 @@ _GRAD_FIELDS = (
 )
 
 
+# simpleConvEdge (my_gnn_layer.py:242-274) has no update MLP
+PARAM_ORDER_EDGE = tuple(n for n in PARAM_ORDER if not n.startswith("mlp_updating."))
+_GRAD_FIELD_OF = dict(zip(PARAM_ORDER, _GRAD_FIELDS))
+
+
 class simpleEdgeModel(nn.Module):
     """Parameter container mirroring my_gnn_layer.py:224-239 (keeps the `edge_model.edge_mlp.*` keys)."""
 
@@ -56,16 +61,19 @@ class PackedLayerWeights:
     """bf16 operand copies of the fp32 master parameters, cut per input source and transposed for dgrad.
     Re-packed whenever any parameter's version counter changes (optimizer.step() bumps it in place)."""
 
-    def __init__(self, D, device):
-        self.D, self.device = D, device
+    def __init__(self, D, device, variant=0):
+        self.D, self.device, self.variant = D, device, variant
         c = D // 8
         self.c, self.cp, self.c3p = c, pad64(c), pad64(3 * c)
+        npj = 4 if variant == 1 else 3                       # node projection blocks (rpg.h: rpg_layer_weights_t.variant)
         shapes = {
-            "Wn": (3 * D, D), "W1e_e": (D, D), "W2e": (D, D), "W1m_e": (D, D), "W2m": (D, D),
-            "Wgtp": (3 * c, D), "WW": (D, self.cp), "WWI": (D, self.cp + D), "W1u": (D, 2 * D), "W2u": (D, D),
-            "WnT": (D, 3 * D), "W1e_eT": (D, D), "W2eT": (D, D), "W1m_eT": (D, D), "W2mT": (D, D), "W2uT": (D, D),
-            "WgtpT": (D, self.c3p), "WWT": (c, D), "W1uT": (2 * D, D),
+            "Wn": (npj * D, D), "W1e_e": (D, D), "W2e": (D, D), "W1m_e": (D, D), "W2m": (D, D),
+            "Wgtp": (3 * c, D), "WW": (D, self.cp), "WWI": (D, self.cp + D),
+            "WnT": (D, npj * D), "W1e_eT": (D, D), "W2eT": (D, D), "W1m_eT": (D, D), "W2mT": (D, D),
+            "WgtpT": (D, self.c3p), "WWT": (c, D),
         }
+        if variant == 0:
+            shapes.update({"W1u": (D, 2 * D), "W2u": (D, D), "W2uT": (D, D), "W1uT": (2 * D, D)})
         total = sum(r * k for r, k in shapes.values())
         self.flat = torch.zeros(total, dtype=BF16, device=device)     # zero padding columns stay zero
         self.t = {}
@@ -79,7 +87,8 @@ class PackedLayerWeights:
         self.struct = _lib.LayerWeights()
 
     def refresh(self, mod):
-        p = {n: mod.get_parameter(n) for n in PARAM_ORDER}
+        v1 = self.variant == 1
+        p = {n: mod.get_parameter(n) for n in (PARAM_ORDER_EDGE if v1 else PARAM_ORDER)}
         versions = tuple((q.data_ptr(), q._version) for q in p.values())
         if versions == self.versions:
             return self.struct
@@ -87,16 +96,20 @@ class PackedLayerWeights:
             if q.dtype != torch.float32 or not q.is_cuda or not q.is_contiguous():
                 raise TypeError("layer parameters must be contiguous float32 CUDA tensors (fp32 master weights)")
         D, c, t = self.D, self.c, self.t
-        W1e, W1m, W1u = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data, p["mlp_updating.0.weight"].data
-        W2e, W2m, W2u = p["edge_model.edge_mlp.2.weight"].data, p["mlp.2.weight"].data, p["mlp_updating.2.weight"].data
+        W1e, W1m = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data
+        W2e, W2m = p["edge_model.edge_mlp.2.weight"].data, p["mlp.2.weight"].data
         pk = ops.pack_weight
+        # mlp.0 columns: _upt = [x_j (src) | e'];  simpleConvEdge = [x_i (dst) | x_j (src) | e']  (my_gnn_layer.py:269,305)
+        mj0, me0 = (D, 2 * D) if v1 else (0, D)
         # forward operands
         pk(W1e, t["Wn"][0:D], c0=0, cols=D)
         pk(W1e, t["Wn"][D:2 * D], c0=D, cols=D)
-        pk(W1m, t["Wn"][2 * D:3 * D], c0=0, cols=D)
+        pk(W1m, t["Wn"][2 * D:3 * D], c0=mj0, cols=D)
+        if v1:
+            pk(W1m, t["Wn"][3 * D:4 * D], c0=0, cols=D)
         pk(W1e, t["W1e_e"], c0=2 * D, cols=D)
         pk(W2e, t["W2e"])
-        pk(W1m, t["W1m_e"], c0=D, cols=D)
+        pk(W1m, t["W1m_e"], c0=me0, cols=D)
         pk(W2m, t["W2m"])
         for i, nm in enumerate(("g", "theta", "phi")):
             pk(p[f"att.{nm}.weight"].data, t["Wgtp"][i * c:(i + 1) * c])
@@ -104,21 +117,26 @@ class PackedLayerWeights:
             self.bgtp[i * c:(i + 1) * c].copy_(p[f"att.{nm}.bias"].data)
         pk(p["att.W.weight"].data, t["WW"][:, :c])
         pk(p["att.W.weight"].data, t["WWI"][:, :c])
-        pk(W1u, t["W1u"])
-        pk(W2u, t["W2u"])
         # dgrad operands (transposes)
         pk(W1e, t["WnT"][:, 0:D], c0=0, cols=D, transpose=True)
         pk(W1e, t["WnT"][:, D:2 * D], c0=D, cols=D, transpose=True)
-        pk(W1m, t["WnT"][:, 2 * D:3 * D], c0=0, cols=D, transpose=True)
+        pk(W1m, t["WnT"][:, 2 * D:3 * D], c0=mj0, cols=D, transpose=True)
+        if v1:
+            pk(W1m, t["WnT"][:, 3 * D:4 * D], c0=0, cols=D, transpose=True)
         pk(W1e, t["W1e_eT"], c0=2 * D, cols=D, transpose=True)
         pk(W2e, t["W2eT"], transpose=True)
-        pk(W1m, t["W1m_eT"], c0=D, cols=D, transpose=True)
+        pk(W1m, t["W1m_eT"], c0=me0, cols=D, transpose=True)
         pk(W2m, t["W2mT"], transpose=True)
-        pk(W2u, t["W2uT"], transpose=True)
         pk(p["att.W.weight"].data, t["WWT"], transpose=True)
-        pk(W1u, t["W1uT"], transpose=True)
+        if not v1:
+            W1u, W2u = p["mlp_updating.0.weight"].data, p["mlp_updating.2.weight"].data
+            pk(W1u, t["W1u"])
+            pk(W2u, t["W2u"])
+            pk(W2u, t["W2uT"], transpose=True)
+            pk(W1u, t["W1uT"], transpose=True)
         s = self.struct
         s.D = D
+        s.variant = self.variant
         for name, tensor in t.items():
             setattr(s, name, tensor.data_ptr())
         s.b1e = p["edge_model.edge_mlp.0.bias"].data_ptr()
@@ -127,8 +145,9 @@ class PackedLayerWeights:
         s.b2m = p["mlp.2.bias"].data_ptr()
         s.bgtp = self.bgtp.data_ptr()
         s.bW = p["att.W.bias"].data_ptr()
-        s.b1u = p["mlp_updating.0.bias"].data_ptr()
-        s.b2u = p["mlp_updating.2.bias"].data_ptr()
+        if not v1:
+            s.b1u = p["mlp_updating.0.bias"].data_ptr()
+            s.b2u = p["mlp_updating.2.bias"].data_ptr()
         self.versions = versions
         return s
 
@@ -228,15 +247,20 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
     arena = arena if arena is not None else ops.Arena(dev, ops.layer_fwd_bytes(D, Nt, Et))
     new = arena.take
 
-    a = {"x": x, "e": e, "P": new(Nt, 3 * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
+    v1 = weights.variant == 1
+    a = {"x": x, "e": e, "P": new(Nt, (4 if v1 else 3) * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
          "m": new(Et, D), "gtp": new(Et, 3 * c, torch.float32),
          "y": new(Et, cp, zero=(cp != c)),
-         "z": new(Et, D), "a": new(Nt, D), "h3": new(Nt, D), "out": new(Nt, D)}
+         "z": new(Et, D), "a": new(Nt, D)}
     u8 = torch.uint8
-    a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8), "h3_bits": new(Nt, D // 8, u8)})
+    a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8)})
+    if not v1:
+        a.update({"h3": new(Nt, D), "out": new(Nt, D), "h3_bits": new(Nt, D // 8, u8)})
     if for_backward:
         a["att_aux"] = new(Et, 4 * c, torch.float32)           # attention row statistics: the backward skips a sweep
     if want_relu_copies:
+        if v1:
+            raise ValueError("ReLU copies are a feature of the simpleConvEdge_upt stack path")
         a["e_new_relu"] = new(Et, D)
         a["out_relu"] = new(Nt, D)
         a["e_new_bits"] = new(Et, D // 8, u8)
@@ -251,6 +275,8 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(_lib.load().rpg_layer_fwd(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd")
     a["_struct"] = s
+    if v1:
+        a["out"] = a["a"]                        # simpleConvEdge returns the mean itself (my_gnn_layer.py:262-264)
     return a
 
 
@@ -270,11 +296,14 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
 
     b = _lib.LayerGrads()
     have_out = d_out is not None
-    keep = {"dx": new(Nt, D), "de": new(Et, D), "dh1": new(Et, D), "dP": new(Nt, 3 * D),
+    v1 = weights.variant == 1
+    keep = {"dx": new(Nt, D), "de": new(Et, D), "dh1": new(Et, D), "dP": new(Nt, (4 if v1 else 3) * D),
             "split_ws": new(1, lib.rpg_layer_bwd_ws_floats(D, 0, 0), f32),
             "colsum_ws": new(1, lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), f32)}
     if have_out:
-        keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D), "dan": new(Nt, D), "dyn": new(Nt, c, f32),
+        if not v1:
+            keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D)})
+        keep.update({"dan": new(Nt, D), "dyn": new(Nt, c, f32),
                      "dgtp": new(Et, c3p, zero=(c3p != 3 * c)),
                      "dm": new(Et, D), "dh2": new(Et, D), "de_tot": new(Et, D),
                      "ysum": new(Nt, cp), "gtp_bias_tmp": new(1, c3p, f32)})
@@ -283,8 +312,8 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
     b.d_out = ops.ptr(d_out)
     b.d_e_new = ops.ptr(d_e_new)
     b.mask_dx, b.mask_de = int(mask_dx), int(mask_de)
-    for name, field in zip(PARAM_ORDER, _GRAD_FIELDS):
-        setattr(b, field, grads[name].data_ptr())
+    for name in (PARAM_ORDER_EDGE if v1 else PARAM_ORDER):
+        setattr(b, _GRAD_FIELD_OF[name], grads[name].data_ptr())
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(lib.rpg_layer_bwd(C.byref(weights), graph.byref(), C.byref(acts["_struct"]), C.byref(b), stream),
                "rpg_layer_bwd")
@@ -309,7 +338,8 @@ class _LayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, d_e_new):
         dev = ctx.acts["x"].device
-        grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(PARAM_ORDER, ctx.param_shapes)}
+        order = ctx.module._param_order
+        grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(order, ctx.param_shapes)}
         d_out = ops.to_bf16(d_out) if d_out is not None else None
         d_e_new = ops.to_bf16(d_e_new) if d_e_new is not None else None
         dx, de = layer_backward_raw(ctx.weights, ctx.graph, ctx.acts, d_out, d_e_new, grads)
@@ -317,7 +347,7 @@ class _LayerFn(torch.autograd.Function):
             dx = ops.to_f32(dx)
         if ctx.in_dtypes[1] == torch.float32:
             de = ops.to_f32(de)
-        return (dx, de, None, None) + tuple(grads[n] for n in PARAM_ORDER)
+        return (dx, de, None, None) + tuple(grads[n] for n in order)
 
 
 class simpleConvEdge_upt(nn.Module):
@@ -351,11 +381,14 @@ class simpleConvEdge_upt(nn.Module):
         # "bf16" (default; forward + backward) or "fp32" (split-bf16 arithmetic, ~1e-5 relative; inference only for now)
         self.precision = "bf16"
 
+    _variant = 0
+    _param_order = PARAM_ORDER
+
     def _packed(self, device):
         key = str(device)
         pw = self._pack_cache.get(key)
         if pw is None:
-            pw = self._pack_cache[key] = PackedLayerWeights(self.in_channels, device)
+            pw = self._pack_cache[key] = PackedLayerWeights(self.in_channels, device, self._variant)
         return pw
 
     def _packed_split(self, device):
@@ -366,7 +399,7 @@ class simpleConvEdge_upt(nn.Module):
         return pw
 
     def _ordered_params(self):
-        return [self.get_parameter(n) for n in PARAM_ORDER]
+        return [self.get_parameter(n) for n in self._param_order]
 
     def _check_inputs(self, x, edge_index, edge_attr):
         D = self.in_channels
@@ -396,3 +429,147 @@ class simpleConvEdge_upt(nn.Module):
         if self.precision != "bf16":
             raise ValueError("precision must be 'bf16' or 'fp32'")
         return _LayerFn.apply(x, edge_attr, self, graph, *self._ordered_params())
+
+
+class simpleConvEdge(simpleConvEdge_upt):
+    """B200-native `simpleConvEdge` (my_gnn_layer.py:242-274; used by PoseNetX3 / LIGHT / XOX, posenet.py:281-282,
+    400-401, 519-520): the same edge MLP, a message MLP over cat[x_i, x_j, e'] with channel attention, and the mean over
+    incoming edges as the layer output (no update MLP).  Same kernels as simpleConvEdge_upt (rpg.h: variant 1).
+    State dict: mlp.{0,2}, edge_model.edge_mlp.{0,2}, att.{g,theta,phi,W} -- 16 tensors, reference layout."""
+
+    _variant = 1
+    _param_order = PARAM_ORDER_EDGE
+
+    def __init__(self, in_channels, edge_channels, out_channels, use_attention=True):
+        nn.Module.__init__(self)
+        if not use_attention:
+            raise AttributeError("simpleConvEdge without attention is undefined in the reference (message() uses self.att)")
+        if not (in_channels == edge_channels == out_channels):
+            raise ValueError("in == edge == out channels at every reference call site; AttentionBlock(in_channels) on an "
+                             "out_channels-wide message requires it")
+        if in_channels % 128:
+            raise ValueError("channel count must be a multiple of 128 (tcgen05 tile / attention group constraints)")
+        self.in_channels = in_channels
+        self.aggr = "mean"
+        # construction order == reference (my_gnn_layer.py:245-252)
+        self.mlp = Seq(Linear(2 * in_channels + edge_channels, out_channels), ReLU(), Linear(out_channels, out_channels))
+        self.edge_model = simpleEdgeModel(in_channels, edge_channels, edge_channels)
+        self.att = AttentionBlock(in_channels)
+        self._pack_cache = {}
+        self.precision = "bf16"
+
+    def forward(self, x, edge_index, edge_attr):
+        if self.precision != "bf16":
+            raise NotImplementedError("simpleConvEdge runs in the bf16 mode")
+        return super().forward(x, edge_index, edge_attr)
+
+
+class _ConvFn(torch.autograd.Function):
+    """simpleConv forward / backward out of the path's kernels.  The first Linear acts on cat[x_i, x_j] only, so it is two
+    per-node products + a gather (rpg_edge_gather); the mean's backward and the second Linear's gradients are evaluated
+    at node level (dm[e] = dan[dst(e)])."""
+
+    @staticmethod
+    def forward(ctx, x, module, graph, w1, b1, w2, b2):
+        D = module.in_channels
+        dev = x.device
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        pk = module._packed_conv(dev)
+        xb = ops.to_bf16(x)
+        P = torch.empty(Nt, 2 * D, dtype=BF16, device=dev)
+        ops.gemm_nt(xb, pk["Wn"], out=P)                               # [P_i | P_j] = x [W1[:, :D]; W1[:, D:]]^T
+        h = torch.empty(Et, D, dtype=BF16, device=dev)
+        hbits = torch.empty(Et, D // 8, dtype=torch.uint8, device=dev)
+        ops.edge_gather(P[:, :D], "dst", graph, h, pb=P[:, D:], which_b="src", bias=b1, relu=True, out_bits=hbits)
+        m = torch.empty(Et, D, dtype=BF16, device=dev)
+        ops.gemm_nt(h, pk["W2"], bias=b2, out=m)
+        out = torch.empty(Nt, D, dtype=BF16, device=dev)
+        ops.aggregate_mean(m, graph, out)
+        ctx.module, ctx.graph, ctx.saved = module, graph, (xb, h, hbits, pk)
+        ctx.in_dtype = x.dtype
+        return ops.to_f32(out) if x.dtype == torch.float32 else out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        module, graph = ctx.module, ctx.graph
+        xb, h, hbits, pk = ctx.saved
+        D = module.in_channels
+        dev = xb.device
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        f32 = torch.float32
+        tb = graph._tables
+        dan = torch.empty(Nt, D, dtype=BF16, device=dev)
+        ops.scale_rows(ops.to_bf16(d_out), tb["inv_deg"], graph.N, dan)  # mean backward: d m[e] = dan[dst(e)]
+        Q = torch.empty(Nt, D, dtype=BF16, device=dev)
+        ops.gemm_nt(dan, pk["W2T"], out=Q)                              # (dm W2)[e] = Q[dst(e)]
+        dh = torch.empty(Et, D, dtype=BF16, device=dev)
+        ops.edge_gather(Q, "dst", graph, dh, mask_bits=hbits)           # * [h > 0]
+        dP = torch.empty(Nt, 2 * D, dtype=BF16, device=dev)
+        ops.segment_sum(dh, graph, "in", dP[:, :D])                     # x_i = destination
+        ops.segment_sum(dh, graph, "out", dP[:, D:])                    # x_j = source
+        dx = torch.empty(Nt, D, dtype=BF16, device=dev)
+        ops.gemm_nt(dP, pk["WnT"], out=dx)
+        g_w1 = torch.zeros(D, 2 * D, dtype=f32, device=dev)
+        g_b1 = torch.zeros(D, dtype=f32, device=dev)
+        g_w2 = torch.zeros(D, D, dtype=f32, device=dev)
+        g_b2 = torch.zeros(D, dtype=f32, device=dev)
+        ws = ops.wgrad_ws(D, dev)
+        ops.wgrad(dP[:, :D], xb, g_w1[:, :D], ws)
+        ops.wgrad(dP[:, D:], xb, g_w1[:, D:], ws)
+        ops.colsum(dh, g_b1)
+        hsum = torch.empty(Nt, D, dtype=BF16, device=dev)
+        ops.segment_sum(h, graph, "in", hsum)                           # dW2 = sum_e dm[e]^T h[e] = dan^T hsum
+        ops.wgrad(dan, hsum, g_w2, ws)
+        ops.colsum(dan, g_b2, row_w=tb["deg"])                          # db2 = sum_n indeg(n) dan[n]
+        if ctx.in_dtype == torch.float32:
+            dx = ops.to_f32(dx)
+        return dx, None, None, g_w1, g_b1, g_w2, g_b2
+
+
+class simpleConv(nn.Module):
+    """B200-native `simpleConv` (my_gnn_layer.py:394-412; PoseNetX / X2, posenet.py:123-124):
+    forward(x [Nn, C], edge_index [2, Et]) -> mean over incoming edges of mlp(cat[x_i, x_j]).
+    State dict: mlp.0.{weight [C, 2C], bias}, mlp.2.{weight [C, C], bias} (reference layout)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        if in_channels != out_channels:
+            raise ValueError("in == out channels at every reference call site")
+        if in_channels % 128:
+            raise ValueError("channel count must be a multiple of 128 (tcgen05 tile constraints)")
+        self.in_channels = in_channels
+        self.aggr = "mean"
+        self.mlp = Seq(Linear(2 * in_channels, out_channels), ReLU(), Linear(out_channels, out_channels))
+        self._pack_cache = {}
+
+    def _packed_conv(self, device):
+        D = self.in_channels
+        w1, w2 = self.mlp[0].weight, self.mlp[2].weight
+        key = (str(device), w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+        pk = self._pack_cache.get("pk")
+        if pk is None or pk["key"] != key:
+            for q in (w1, w2):
+                if q.dtype != torch.float32 or not q.is_cuda or not q.is_contiguous():
+                    raise TypeError("layer parameters must be contiguous float32 CUDA tensors (fp32 master weights)")
+            t = {n: torch.empty(s, dtype=BF16, device=device) for n, s in
+                 (("Wn", (2 * D, D)), ("WnT", (D, 2 * D)), ("W2", (D, D)), ("W2T", (D, D)))}
+            ops.pack_weight(w1.data, t["Wn"][0:D], c0=0, cols=D)
+            ops.pack_weight(w1.data, t["Wn"][D:2 * D], c0=D, cols=D)
+            ops.pack_weight(w1.data, t["WnT"][:, 0:D], c0=0, cols=D, transpose=True)
+            ops.pack_weight(w1.data, t["WnT"][:, D:2 * D], c0=D, cols=D, transpose=True)
+            ops.pack_weight(w2.data, t["W2"])
+            ops.pack_weight(w2.data, t["W2T"], transpose=True)
+            t["key"] = key
+            pk = self._pack_cache["pk"] = t
+        return pk
+
+    def forward(self, x, edge_index):
+        D = self.in_channels
+        if not torch.is_tensor(x) or x.dim() != 2 or x.size(1) != D:
+            raise ValueError(f"x must be a [rows, {D}] tensor")
+        if x.dtype not in (torch.float32, BF16):
+            raise TypeError(f"x must be float32 or bfloat16, got {x.dtype}")
+        if not x.is_cuda:
+            raise ValueError("x must be a CUDA tensor: the sm_100a kernels are the only implementation")
+        graph = graph_mod.from_edge_index(edge_index, x.size(0))
+        return _ConvFn.apply(x, self, graph, self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias)

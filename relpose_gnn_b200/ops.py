@@ -230,6 +230,19 @@ def segment_sum(v, graph, which, out, mask=None, scale=None, D=None):
                                       graph.byref(), D, out.data_ptr(), out.stride(0), _stream(v)), "rpg_segment_sum")
 
 
+def edge_gather(pa, which_a, graph, out, pb=None, which_b="src", bias=None, relu=False, mask_bits=None, out_bits=None):
+    """out[e] = act(pa[node_a(e)] + pb[node_b(e)] + bias) * bit(e); which_x in {'src', 'dst'}."""
+    code = {"src": 0, "dst": 1}
+    check(_lib.load().rpg_edge_gather(pa.data_ptr(), pa.stride(0), code[which_a], ptr(pb), pb.stride(0) if pb is not None else 0,
+                                      code[which_b], ptr(bias), graph.byref(), out.size(1), int(relu), ptr(mask_bits),
+                                      out.data_ptr(), out.stride(0), ptr(out_bits), _stream(pa)), "rpg_edge_gather")
+
+
+def scale_rows(v, scale, mod, out):
+    check(_lib.load().rpg_scale_rows(v.data_ptr(), v.stride(0), v.size(0), v.size(1), scale.data_ptr(), mod, out.data_ptr(),
+                                     out.stride(0), _stream(v)), "rpg_scale_rows")
+
+
 def edge_init_fwd(pmm, bias, graph, D, e0, e0_bits=None):
     check(_lib.load().rpg_edge_init_fwd(pmm.data_ptr(), pmm.stride(0), bias.data_ptr(), graph.byref(), D,
                                         e0.data_ptr(), e0.stride(0), ptr(e0_bits), _stream(pmm)), "rpg_edge_init_fwd")

@@ -429,3 +429,96 @@ def test_qexp_and_eval_composition_against_reference_fixtures():
         assert np.allclose(pred.cpu().numpy(), po, rtol=0, atol=2e-6) and np.allclose(targ.cpu().numpy(), to, rtol=0, atol=2e-6)
     with pytest.raises(ValueError):
         rpg.compose_query_pose(pe.to(dev()), pa.to(dev()), ei.to(dev()), into0)
+
+
+# ------------------------------------------------------------------ sibling layers
+def _sibling_modules(kind, D, params):
+    m = rpg.simpleConvEdge(D, D, D) if kind == "convedge" else rpg.simpleConv(D, D)
+    m.load_state_dict({k: v.float() for k, v in params.items()})
+    return m.to(dev())
+
+
+@pytest.mark.parametrize("kind,tag", [("convedge", "D128_N9_G2"), ("convedge", "D128_N5_G3"),
+                                      ("conv", "D128_N9_G2"), ("conv", "D128_N4_G3")])
+def test_sibling_layers_against_reference_fixture(kind, tag):
+    """simpleConvEdge / simpleConv (my_gnn_layer.py:242-274, 394-412) drop-ins against the real reference's output."""
+    fx = np.load(os.path.join(GOLD, f"{kind}_{tag}.npz"))
+    D, N, Gn, seed = [int(v) for v in fx["meta"]]
+    case = R.synth_sibling_case(kind, D, N, Gn, seed)
+    m = _sibling_modules(kind, D, case["params"])
+    assert set(m.state_dict().keys()) == set(case["params"].keys())
+    x = case["x"].float().to(dev()).requires_grad_(True)
+    ei = case["edge_index"].to(dev())
+    if kind == "convedge":
+        e = case["e"].float().to(dev()).requires_grad_(True)
+        out, e_new = m(x, ei, e)
+        assert rel(e_new, fx["e_new_f64"]) < TOL_BF16
+        ((out * case["ct_out"].float().to(dev())).sum() + (e_new * case["ct_e"].float().to(dev())).sum()).backward()
+        assert rel(e.grad, fx["de"]) < TOL_GRAD_FLIP
+    else:
+        out = m(x, ei)
+        (out * case["ct_out"].float().to(dev())).sum().backward()
+    assert out.dtype == torch.float32 and out.shape == (Gn * N, D)
+    assert rel(out, fx["out_f64"]) < TOL_BF16
+    assert rel(x.grad, fx["dx"]) < TOL_GRAD_FLIP
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(fx["grad." + k])
+        num += (p.grad.double().cpu() - ref).norm().item() ** 2
+        den += ref.norm().item() ** 2
+    assert (num / den) ** 0.5 < TOL_GRAD_FLIP
+
+
+@pytest.mark.parametrize("kind,D,N,Gn,drop_edges", [("convedge", 512, 9, 5, False), ("convedge", 256, 8, 21, True),
+                                                    ("conv", 512, 9, 5, False), ("conv", 128, 17, 3, True)])
+def test_sibling_layers_against_mask_matched_oracle(kind, D, N, Gn, drop_edges):
+    """Tight gradient check: bf16-representable inputs, the kernel's own ReLU patterns imposed on the fp64 oracle."""
+    seed = 3000 + D + N + Gn
+    q = lambda t: t.bfloat16().double()                                         # noqa: E731
+    shapes = R.CONV_EDGE_SHAPES(D) if kind == "convedge" else R.CONV_SHAPES(D)
+    params = {k: (q(v) if k.endswith("weight") else v.float().double())
+              for k, v in R.synth_params(shapes, seed, torch.float64).items()}
+    x = q(R.synth_inputs(Gn, N, D, seed + 1, torch.float64)[0])
+    tmpl = R.fc_edge_index(N)
+    if drop_edges:
+        keep = R.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(seed).random_sample(N * (N - 1) // 2))
+        tmpl = R.apply_edge_dropout(tmpl, keep)
+    ei = R.batched_edge_index(tmpl, Gn, N)
+    gen = torch.Generator().manual_seed(seed + 2)
+    e = q(torch.relu(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64)))
+    ct_o = q(torch.randn(Gn * N, D, generator=gen, dtype=torch.float64))
+    ct_e = q(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64))
+    m = _sibling_modules(kind, D, params)
+    xg = x.float().to(dev()).requires_grad_(True)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xo = x.clone().requires_grad_(True)
+    if kind == "convedge":
+        from relpose_gnn_b200.layers import PARAM_ORDER_EDGE, layer_backward_raw, layer_forward_raw
+        graph = G.from_edge_index(ei.to(dev()), Gn * N)
+        lw = m._packed(dev()).refresh(m)
+        acts = layer_forward_raw(lw, graph, x.to(dev()).bfloat16(), e.to(dev()).bfloat16())
+        grads = {k: torch.zeros_like(m.get_parameter(k)) for k in PARAM_ORDER_EDGE}
+        dx, de = layer_backward_raw(lw, graph, acts, ct_o.to(dev()).bfloat16(), ct_e.to(dev()).bfloat16(), grads)
+        out_o, en_o = R.conv_edge_forward(params, x, ei, e)
+        assert rel(acts["out"].float(), out_o) < TOL_BF16 and rel(acts["e_new"].float(), en_o) < TOL_BF16
+        masks = {k: (acts[k] > 0).cpu() for k in ("h1", "h2")}
+        eo = e.clone().requires_grad_(True)
+        out_m, en_m = R.conv_edge_forward(p, xo, ei, eo, relu_masks=masks)
+        ((out_m * ct_o).sum() + (en_m * ct_e).sum()).backward()
+        assert rel(de.float(), eo.grad) < TOL_GRAD
+        errs = {k: rel(grads[k], p[k].grad) for k in PARAM_ORDER_EDGE}
+    else:
+        out = m(xg, ei.to(dev()))
+        (out * ct_o.float().to(dev())).sum().backward()
+        dx = xg.grad
+        assert rel(out, R.conv_forward(params, x, ei)) < TOL_BF16
+        # the kernel's activation pattern: recompute h in fp64 from the bf16 node projections' sign is not observable
+        # from outside, so impose the oracle's own pattern where |pre-activation| is not tiny and compare loosely below
+        out_m = R.conv_forward(p, xo, ei)
+        (out_m * ct_o).sum().backward()
+        errs = {k: rel(v.grad, p[k].grad) for k, v in m.named_parameters()}
+    tol_dx = TOL_GRAD if kind == "convedge" else TOL_GRAD_FLIP
+    assert rel(dx.float(), xo.grad) < tol_dx
+    lim = TOL_GRAD if kind == "convedge" else TOL_GRAD_FLIP
+    bad = {k: v for k, v in errs.items() if v > (4 * lim if k.startswith("att.") and k.endswith("bias") else lim)}
+    assert not bad, bad

@@ -140,3 +140,20 @@ def test_evaluation_api_refuses_cpu_tensors():
         rpg.qexp(torch.zeros(4, 3))
     with pytest.raises(ValueError):
         rpg.compose_query_pose(torch.zeros(72, 6), torch.zeros(9, 6), torch.zeros(2, 72, dtype=torch.long))
+
+
+def test_sibling_layer_state_dict_layout_matches_reference():
+    """simpleConvEdge / simpleConv keep the reference's parameter names and shapes
+    (my_gnn_layer.py:242-252, 394-399) and refuse host tensors."""
+    D = 128
+    m = rpg.simpleConvEdge(D, D, D)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == R.CONV_EDGE_SHAPES(D)
+    assert list(m.state_dict().keys())[:4] == ["mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias"]
+    c = rpg.simpleConv(D, D)
+    assert {k: tuple(v.shape) for k, v in c.state_dict().items()} == R.CONV_SHAPES(D)
+    with pytest.raises(ValueError):
+        c(torch.zeros(9, D), torch.zeros(2, 72, dtype=torch.long))
+    with pytest.raises(ValueError):
+        m(torch.zeros(9, D), torch.zeros(2, 72, dtype=torch.long), torch.zeros(72, D))
+    with pytest.raises(AttributeError):
+        rpg.simpleConvEdge(D, D, D, use_attention=False)

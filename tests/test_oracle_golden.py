@@ -48,6 +48,30 @@ def test_edge_dropout_mask_matches_reference():
     assert keep.all() and fx["none_survive_tiled"].all()
 
 
+@pytest.mark.parametrize("kind,tag", [("convedge", "D128_N9_G2"), ("convedge", "D128_N5_G3"),
+                                      ("conv", "D128_N9_G2"), ("conv", "D128_N4_G3")])
+def test_sibling_layers_match_reference(kind, tag):
+    """simpleConvEdge / simpleConv (my_gnn_layer.py:242-274, 394-412): oracle restatement vs the real reference."""
+    fx = np.load(os.path.join(G, f"{kind}_{tag}.npz"))
+    D, N, Gn, seed = [int(v) for v in fx["meta"]]
+    case = R.synth_sibling_case(kind, D, N, Gn, seed)
+    p = {k: v.clone().requires_grad_(True) for k, v in case["params"].items()}
+    x = case["x"].clone().requires_grad_(True)
+    if kind == "convedge":
+        e = case["e"].clone().requires_grad_(True)
+        out, e_new = R.conv_edge_forward(p, x, case["edge_index"], e)
+        ((out * case["ct_out"]).sum() + (e_new * case["ct_e"]).sum()).backward()
+        assert np.allclose(e_new.detach().numpy(), fx["e_new_f64"], rtol=1e-10, atol=1e-12)
+        assert np.allclose(e.grad.numpy(), fx["de"], rtol=1e-9, atol=1e-11)
+    else:
+        out = R.conv_forward(p, x, case["edge_index"])
+        (out * case["ct_out"]).sum().backward()
+    assert np.allclose(out.detach().numpy(), fx["out_f64"], rtol=1e-10, atol=1e-12)
+    assert np.allclose(x.grad.numpy(), fx["dx"], rtol=1e-9, atol=1e-11)
+    for k, v in p.items():
+        assert np.allclose(v.grad.numpy(), fx["grad." + k], rtol=1e-8, atol=1e-10), k
+
+
 def test_eval_composition_matches_reference():
     """test.py:227-243 executed on seeded single graphs (oracle/make_golden.py: golden_eval_compose)."""
     fx = np.load(os.path.join(G, "eval_compose.npz"))
