@@ -92,6 +92,7 @@ typedef struct {
   const rpg_bf16* sel_src;
   const rpg_bf16* sel_dst;
   int sel_patterns, sel_div;
+  const float* has_in;        /* [N] 1 if the node has incoming edges, else 0 (a mean over nothing is 0 [3p])   */
 } rpg_graph_t;
 
 /* Builds the one-hot selection tiles of rpg_graph_t.sel_src / sel_dst on the device from a template endpoint table
@@ -354,8 +355,8 @@ typedef struct {                  /* activations of one layer call; all bf16 unl
   rpg_bf16* m;                    /* [Et, D]                                                            */
   float* gtp;                     /* [Et, 3c] fp32                                                      */
   rpg_bf16* y;                    /* [Et, max(c,64)]                                                    */
-  rpg_bf16* z;                    /* [Et, D] scratch                                                    */
-  rpg_bf16* a;                    /* [Nt, D]                                                            */
+  rpg_bf16* z;                    /* unused (kept for layout stability): z = W(y) + m is never materialised   */
+  rpg_bf16* a;                    /* [Nt, D]  mean over in-edges of z = mean(y) WW^T + bW + mean(m)           */
   rpg_bf16* h3;                   /* [Nt, D]                                                            */
   rpg_bf16* out;                  /* [Nt, D] out (pre-ReLU)                                             */
   rpg_bf16* out_relu;             /* [Nt, D] optional relu(out) (posenet.py:1064)                       */
@@ -368,6 +369,8 @@ typedef struct {                  /* activations of one layer call; all bf16 unl
   uint8_t* out_bits;              /* [Nt, D/8] optional: (out > 0) for the next round's mask_dx          */
   const uint8_t* x_bits;          /* [Nt, D/8] optional pattern of the input x (used when mask_dx)       */
   const uint8_t* e_bits;          /* [Et, D/8] optional pattern of the input e (used when mask_de)       */
+  rpg_bf16* ybar;                 /* [Nt, max(c,64)] scratch: mean over in-edges of y                    */
+  rpg_bf16* mbar;                 /* [Nt, D]         scratch: mean over in-edges of m                    */
 } rpg_layer_acts_t;
 
 int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,

@@ -26,7 +26,7 @@ class Graph(C.Structure):
     _fields_ = [("G", I), ("N", I), ("Ep", I),
                 ("src", P), ("dst", P), ("in_ptr", P), ("in_idx", P), ("out_ptr", P), ("out_idx", P),
                 ("inv_deg", P), ("deg", P), ("min_ptr", P), ("min_idx", P), ("max_ptr", P), ("max_idx", P),
-                ("sel_src", P), ("sel_dst", P), ("sel_patterns", I), ("sel_div", I)]
+                ("sel_src", P), ("sel_dst", P), ("sel_patterns", I), ("sel_div", I), ("has_in", P)]
 
 
 class Gemm(C.Structure):
@@ -53,7 +53,7 @@ class LayerWeights(C.Structure):
 class LayerActs(C.Structure):
     _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
                                  "h3", "out", "out_relu", "att_aux", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
-                                 "x_bits", "e_bits")]
+                                 "x_bits", "e_bits", "ybar", "mbar")]
 
 
 class LayerWeightsSplit(C.Structure):

@@ -275,15 +275,17 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     // (7) rank-1 softmax attention (att.py:25-30)
     RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, t->att_aux, stream));
 
-    // (8) z = y WW^T + bW + m (att.py:32-33) as [y | m] [WW | I]^T: the residual is a second K segment (exact in the
-    //     fp32 accumulator) so it streams through TMA with the operands instead of being fetched by the epilogue
-    g = nt((int)Et, D, t->y, cp, cp, w->WWI, cp + D);
-    g.n_seg = 2; g.A[1] = t->m; g.K[1] = D; g.lda[1] = D;
-    g.bias = w->bW; g.out = t->z; g.ldo = D;
+    // (8)+(9) z = y WW^T + bW + m (att.py:32-33) is only ever averaged over the incoming edges (PyG aggregate [3p],
+    //     my_gnn_layer.py:301), and the mean is linear: a = mean(y) WW^T + bW + mean(m).  So the edge-level GEMM and
+    //     the [Et, D] tensor z disappear: two segment means (y is only c wide) and ONE node-level GEMM
+    //     [ybar | mbar] [WW | I]^T + bW, zeroed for nodes without incoming edges (their mean is 0, not bW).
+    if (!t->ybar || !t->mbar || !gr->has_in) return set_error(RPG_E_ARG, "layer_fwd: ybar / mbar / has_in missing");
+    RPG_TRY(rpg_aggregate_mean(t->y, cp, gr, cp, t->ybar, cp, stream));
+    RPG_TRY(rpg_aggregate_mean(t->m, D, gr, D, t->mbar, D, stream));
+    g = nt((int)Nt, D, t->ybar, cp, cp, w->WWI, cp + D);
+    g.n_seg = 2; g.A[1] = t->mbar; g.K[1] = D; g.lda[1] = D;
+    g.bias = w->bW; g.row_scale = gr->has_in; g.row_scale_mod = gr->N; g.out = t->a; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
-
-    // (9) mean over incoming edges (PyG aggregate [3p], my_gnn_layer.py:301)
-    RPG_TRY(rpg_aggregate_mean(t->z, D, gr, D, t->a, D, stream));
     if (w->variant == 1) return 0;               // simpleConvEdge: the mean is the layer output (no update step)
 
     // (10) update MLP (my_gnn_layer.py:284-286,309-311): out = relu([x | a] W1u^T + b) W2u^T + b

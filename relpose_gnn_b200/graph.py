@@ -129,6 +129,7 @@ class GraphBatch:
         deg = np.bincount(dst, minlength=n).astype(np.float32)
         host = {"src": src, "dst": dst, "in_ptr": in_ptr, "in_idx": in_idx, "out_ptr": out_ptr,
                 "out_idx": out_idx, "inv_deg": (1.0 / np.maximum(deg, 1.0)).astype(np.float32), "deg": deg,
+                "has_in": (deg > 0).astype(np.float32),
                 "min_ptr": min_ptr, "min_idx": min_idx, "max_ptr": max_ptr, "max_idx": max_idx}
         offs, total = {}, 0
         for k, v in host.items():

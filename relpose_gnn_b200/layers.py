@@ -251,7 +251,7 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
     a = {"x": x, "e": e, "P": new(Nt, (4 if v1 else 3) * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
          "m": new(Et, D), "gtp": new(Et, 3 * c, torch.float32),
          "y": new(Et, cp, zero=(cp != c)),
-         "z": new(Et, D), "a": new(Nt, D)}
+         "ybar": new(Nt, cp), "mbar": new(Nt, D), "a": new(Nt, D)}
     u8 = torch.uint8
     a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8)})
     if not v1:

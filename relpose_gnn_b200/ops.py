@@ -32,8 +32,8 @@ class Arena:
 
 def layer_fwd_bytes(D, Nt, Et):
     c = D // 8
-    return (Et * (6 * D * 2 + 3 * c * 4 + 4 * c * 4 + pad64(c) * 2 + 3 * (D // 8)) +
-            Nt * (3 * D * 2 + 4 * D * 2 + 2 * (D // 8)) + 64 * 256)
+    return (Et * (5 * D * 2 + 3 * c * 4 + 4 * c * 4 + pad64(c) * 2 + 3 * (D // 8)) +
+            Nt * (4 * D * 2 + 5 * D * 2 + pad64(c) * 2 + 2 * (D // 8)) + 64 * 256)
 
 
 def layer_bwd_bytes(D, Nt, Et):
