@@ -284,6 +284,12 @@ int rpg_pose_criterion(const float* pred, const float* poses, const rpg_graph_t*
                        const float* sax, const float* saq, float* target, float* out7, float* dpred, float* ws,
                        rpg_stream_t stream);
 
+/* Dynamic kNN rewiring: torch_cluster.knn_graph(x, k, batch, loop=False) [3p, torch-cluster 1.5.9] as called at
+ * posenet.py:1043-1050 for G graphs of N nodes each (2 <= N <= 64, k < N): edge_index [2, G*N*k] int64 with
+ * column (g*N + i)*k + r = (r-th nearest other node of i in graph g  ->  i); squared Euclidean distances in fp32 on
+ * x [G*N, D] (pitch ldx), ties to the lower node index. */
+int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* edge_index, rpg_stream_t stream);
+
 /* pose_utils.qexp (pose_utils.py:340-348): q[i] = [cos|v|, sinc(|v|/pi) v] for n log-quaternions v [n, 3] -> q [n, 4]. */
 int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream);
 /* Evaluation composition (test.py:227-243) for G graphs sharing the template: with k = ref_k the template edge

@@ -135,6 +135,22 @@ def layer_forward(p, x, edge_index, e, return_intermediates=False, relu_masks=No
     return out, e_new
 
 
+def knn_graph(x, k, n_graphs, n_nodes):
+    """torch_cluster.knn_graph(x, k, batch, loop=False) [3p: torch-cluster 1.5.9, requirements-cu111.txt:6; absent from
+    /root/reference -- PARITY UNPINNED for this function: restated from its documented behaviour] as called at
+    posenet.py:1043-1050: per graph, edges (neighbour -> centre) to the k nearest other nodes (Euclidean), grouped by
+    centre, nearest first (stable: ties to the lower index)."""
+    cols = []
+    for g in range(n_graphs):
+        xg = x[g * n_nodes:(g + 1) * n_nodes].double()
+        d = ((xg.unsqueeze(1) - xg.unsqueeze(0)) ** 2).sum(-1)
+        d = d + torch.diag(torch.full((n_nodes,), float("inf"), dtype=torch.float64))
+        nbr = torch.sort(d, dim=1, stable=True).indices[:, :k]
+        centre = torch.arange(n_nodes).view(-1, 1).expand_as(nbr)
+        cols.append(torch.stack([nbr.reshape(-1), centre.reshape(-1)], 0) + g * n_nodes)
+    return torch.cat(cols, dim=1)
+
+
 def conv_edge_forward(p, x, edge_index, e, relu_masks=None):
     """simpleConvEdge.forward, my_gnn_layer.py:253-274: edge model, message = att(mlp(cat[x_i, x_j, e'])) with
     x_i = x[edge_index[1]] (destination), x_j = x[edge_index[0]] (source) [3p PyG], mean over destinations; no update."""

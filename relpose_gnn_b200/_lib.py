@@ -124,6 +124,7 @@ SIGNATURES = {
     "rpg_reduce_splits_batch": (I, [P, P]),
     "rpg_upload_words": (I, [P, P, I64, P]),
     "rpg_qexp": (I, [P, I64, P, P]),
+    "rpg_knn_graph": (I, [P, I, I, I, I, I, P, P]),
     "rpg_scale_rows": (I, [P, I, I64, I, P, I, P, I, P]),
     "rpg_edge_gather": (I, [P, I, I, P, I, I, P, C.POINTER(Graph), I, I, P, P, I, P, P]),
     "rpg_eval_compose": (I, [P, P, C.POINTER(Graph), I, P, P, P, P, P]),

@@ -964,6 +964,58 @@ __global__ void eval_compose_kernel(const float* __restrict__ pred_edges, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dynamic kNN rewiring (posenet.py:1043-1050 -> torch_cluster.knn_graph [3p, 1.5.9], loop=False, source_to_target):
+// per graph, every node i gets edges (j -> i) from its k nearest other nodes j in embedding space (squared Euclidean
+// distance, fp32), grouped by centre, nearest first; ties go to the lower index.  One block per graph: warps compute
+// the N(N-1)/2 distances, then one thread per centre selects k times.
+// ------------------------------------------------------------------------------------------------
+constexpr int KNN_MAX_N = 64;
+__global__ void __launch_bounds__(256)
+knn_graph_kernel(const float* __restrict__ x, int ldx, int N, int D, int k, long long* __restrict__ ei, long long Et) {
+    pdl_prologue();
+    __shared__ float dist[KNN_MAX_N][KNN_MAX_N + 1];
+    const int g = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float* xg = x + (size_t)g * N * ldx;
+    const int npairs = N * (N - 1) / 2;
+    for (int p = warp; p < npairs; p += nwarps) {
+        // unrank p -> (i, j), i < j
+        int i = 0, rem = p;
+        while (rem >= N - 1 - i) { rem -= N - 1 - i; ++i; }
+        const int j = i + 1 + rem;
+        const float* a = xg + (size_t)i * ldx;
+        const float* b = xg + (size_t)j * ldx;
+        float acc = 0.f;
+        for (int c = lane * 4; c < D; c += 128) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(a + c));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(b + c));
+            const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
+            acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { dist[i][j] = acc; dist[j][i] = acc; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        unsigned long long taken = 1ull << i;                 // self excluded (loop=False)
+        for (int r = 0; r < k; ++r) {
+            int best = -1;
+            float bd = INFINITY;
+            for (int j = 0; j < N; ++j) {
+                if ((taken >> j) & 1ull) continue;
+                const float d = dist[i][j];
+                if (best < 0 || d < bd) { best = j; bd = d; }
+            }
+            taken |= 1ull << best;
+            const long long e = ((long long)g * N + i) * k + r;
+            ei[e] = (long long)g * N + best;                  // row 0: source = neighbour
+            ei[Et + e] = (long long)g * N + i;                // row 1: destination = centre
+        }
+    }
+}
+
 // Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
 // never queue behind a large host->device copy of another stream.
 constexpr int UPLOAD_WORDS = 2032;
@@ -1424,6 +1476,15 @@ int rpg_scale_rows(const rpg_bf16* v, int ldv, int64_t rows, int D, const float*
     launch_pdl(scale_rows_kernel, dim3(grid_for(rows * (D / 8), 256)), dim3(256), 0, as_stream(stream),
                reinterpret_cast<const bf16*>(v), ldv, rows, D, scale, mod, reinterpret_cast<bf16*>(out), ldo);
     return check_launch("scale_rows_kernel");
+}
+
+int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* edge_index, rpg_stream_t stream) {
+    if (!x || !edge_index || G <= 0 || N < 2 || N > KNN_MAX_N || k < 1 || k >= N || D % 4 || ldx % 4)
+        return set_error(RPG_E_ARG, "knn_graph: need 2 <= N <= 64, 1 <= k < N, D and pitch multiples of 4");
+    const long long Et = (long long)G * N * k;
+    launch_pdl(knn_graph_kernel, dim3(G), dim3(256), 0, as_stream(stream), x, ldx, N, D, k,
+               reinterpret_cast<long long*>(edge_index), Et);
+    return check_launch("knn_graph_kernel");
 }
 
 int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream) {

@@ -61,7 +61,7 @@ class _TableUploader:
 
     def upload(self, packed_np, device):
         device = torch.device(device)
-        if device.type != "cuda":
+        if device.type != "cuda" or packed_np.size > 64 * 1024:      # big tables (one-graph fallback): a plain copy
             return torch.from_numpy(packed_np).to(device)
         packed_np = np.ascontiguousarray(packed_np, dtype=np.int32)
         dev = torch.empty(packed_np.size, dtype=torch.int32, device=device)
@@ -197,6 +197,30 @@ def attach(edge_index, graph):
     edge_index.rpg_graph = graph
     edge_index.rpg_graph_version = edge_index._version
     return edge_index
+
+
+def knn_graph(x, k, batch=None, loop=False, num_nodes_per_graph=None):
+    """torch_cluster.knn_graph as the reference calls it (posenet.py:1043-1050: `knn_graph(x, k, batch=data.batch,
+    loop=False)`) for batches of equally sized graphs: int64 edge_index [2, G*N*k], edges (neighbour -> centre) grouped
+    by centre, nearest first.  x: float32 CUDA [G*N, D]; graph size from `num_nodes_per_graph` or the `batch` vector."""
+    if loop:
+        raise NotImplementedError("loop=True is never used by the reference")
+    if not x.is_cuda:
+        raise ValueError("knn_graph needs a CUDA tensor: the sm_100a kernels are the only implementation")
+    if num_nodes_per_graph is None:
+        if batch is None:
+            num_nodes_per_graph = x.size(0)
+        else:
+            num_nodes_per_graph = int((batch == batch[0]).sum().item())
+    N = int(num_nodes_per_graph)
+    if x.size(0) % N:
+        raise ValueError("knn_graph: the batch must consist of equally sized graphs")
+    xf = x.float().contiguous()
+    G = xf.size(0) // N
+    ei = torch.empty(2, G * N * k, dtype=torch.int64, device=x.device)
+    _lib.check(_lib.load().rpg_knn_graph(xf.data_ptr(), xf.stride(0), G, N, xf.size(1), k, ei.data_ptr(),
+                                         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "rpg_knn_graph")
+    return ei
 
 
 def from_edge_index(edge_index, n_node_rows):

@@ -121,8 +121,9 @@ class _StackFn(torch.autograd.Function):
 class RelPoseGNN(nn.Module):
     """GNN stack of PoseNetX_R2 (constructor arguments as posenet.py:923-930 where they concern this path)."""
 
-    def __init__(self, feat_dim=1024, edge_feat_dim=1024, node_dim=1024, droprate=0.5, gnn_recursion=2, L=1):
+    def __init__(self, feat_dim=1024, edge_feat_dim=1024, node_dim=1024, droprate=0.5, gnn_recursion=2, L=1, knn=-1):
         super().__init__()
+        self.knn = knn                           # > 0: rewire every graph to its k-NN graph in embedding space (posenet.py:1046-1048)
         if not (feat_dim == edge_feat_dim == node_dim):
             raise ValueError("the reference instantiates feat_dim == edge_feat_dim == node_dim (train.py:174-189)")
         self.node_dim, self.droprate, self.gnn_recursion, self.n_layers = node_dim, droprate, gnn_recursion, L
@@ -196,14 +197,20 @@ class RelPoseGNN(nn.Module):
         self.dropout_seed += 2
         return (float(self.droprate), None, None, self.dropout_seed)
 
-    def forward(self, x, edge_index, keep_x=None, keep_e=None):
+    def forward(self, x, edge_index, keep_x=None, keep_e=None, k=None):
         """x: node embeddings [G*N, D] (what feature_extractor returns, posenet.py:1037).  keep_x / keep_e: optional
-        explicit Bernoulli keep masks for the feature dropout (parity tests); otherwise a counter-based in-kernel RNG."""
+        explicit Bernoulli keep masks for the feature dropout (parity tests); otherwise a counter-based in-kernel RNG.
+        With `self.knn > 0` (or `k`) the given edge_index only tells the graph size: every graph is rewired to its k-NN
+        graph in embedding space (posenet.py:1043-1050) and that edge_index is returned, as in the reference."""
         if not x.is_cuda:
             raise ValueError("RelPoseGNN needs CUDA tensors: the sm_100a kernels are the only implementation")
         if x.dim() != 2 or x.size(1) != self.node_dim:
             raise ValueError(f"x must be [rows, {self.node_dim}]")
         graph = graph_mod.from_edge_index(edge_index, x.size(0))
+        kk = self.knn if self.knn > 0 else k
+        if kk is not None and kk > 0:
+            edge_index = graph_mod.knn_graph(x, kk, num_nodes_per_graph=graph.N)
+            graph = graph_mod.from_edge_index(edge_index, x.size(0))
         drop = self._drop_args(keep_x, keep_e)
         if self.precision == "fp32":
             pose_n, pose_e = self._forward_fp32(x, graph, drop)

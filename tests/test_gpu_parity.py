@@ -522,3 +522,52 @@ def test_sibling_layers_against_mask_matched_oracle(kind, D, N, Gn, drop_edges):
     lim = TOL_GRAD if kind == "convedge" else TOL_GRAD_FLIP
     bad = {k: v for k, v in errs.items() if v > (4 * lim if k.startswith("att.") and k.endswith("bias") else lim)}
     assert not bad, bad
+
+
+# ------------------------------------------------------------------ dynamic kNN rewiring
+@pytest.mark.parametrize("N,k,D,Gn", [(8, 4, 512, 40), (9, 4, 1024, 7), (17, 6, 128, 5), (4, 3, 64, 3)])
+def test_knn_graph_matches_restated_torch_cluster(N, k, D, Gn):
+    gen = torch.Generator().manual_seed(N * 100 + k)
+    x = torch.randn(Gn * N, D, generator=gen)
+    ei = rpg.knn_graph(x.to(dev()), k, num_nodes_per_graph=N)
+    ref = R.knn_graph(x, k, Gn, N)
+    assert ei.dtype == torch.int64 and tuple(ei.shape) == (2, Gn * N * k)
+    assert torch.equal(ei.cpu(), ref)
+    batch = torch.arange(Gn).repeat_interleave(N).to(dev())
+    assert torch.equal(rpg.knn_graph(x.to(dev()), k, batch=batch), ei)
+
+
+def test_stack_with_knn_rewiring_against_oracle():
+    """PoseNetX_R2.forward with knn=4 (the CLI default, train.py:377): rewired graph + the same stack, forward and
+    backward (gradients against the oracle with the kernel's own activation patterns imposed)."""
+    D, N, Gn, k = 256, 8, 6, 4
+    q = lambda t: t.bfloat16().double()                                         # noqa: E731
+    case = R.synth_stack_case(D, N, Gn, 777, droprate=0.0)
+    params = {kk: (q(v) if kk.endswith("weight") and not kk.startswith("fc_") else v.float().double())
+              for kk, v in case["params"].items()}
+    x = q(case["x"])
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.0, knn=k).to(dev())
+    model.load_state_dict({kk: v.float() for kk, v in params.items()}, strict=False)
+    model.keep_debug_activations = True
+    xg = x.float().to(dev()).requires_grad_(True)
+    pn, pe, ei_out = model(xg, case["edge_index"].to(dev()))
+    ei_ref = R.knn_graph(x.float(), k, Gn, N)
+    assert torch.equal(ei_out.cpu(), ei_ref)
+    assert tuple(pe.shape) == (Gn * N * k, 6)
+    pn_o, pe_o, _, _ = R.stack_forward(params, x, ei_ref, 2, 0.0)
+    assert rel(pn, pn_o) < TOL_BF16 and rel(pe, pe_o) < TOL_BF16
+    gen = torch.Generator().manual_seed(9)
+    ct_n = torch.randn(pn.shape, generator=gen).double()
+    ct_e = torch.randn(pe.shape, generator=gen).double()
+    ((pn * ct_n.float().to(dev())).sum() + (pe * ct_e.float().to(dev())).sum()).backward()
+    dbg = model.debug_activations
+    masks = {"e0": (dbg["e0"] > 0).cpu(),
+             "rounds": [{"h1": (a["h1"] > 0).cpu(), "h2": (a["h2"] > 0).cpu(), "h3": (a["h3"] > 0).cpu(),
+                         "x": (a["out_relu"] > 0).cpu(), "e": (a["e_new_relu"] > 0).cpu()} for a in dbg["rounds"]]}
+    p = {kk: v.clone().requires_grad_(True) for kk, v in params.items()}
+    xo = x.clone().requires_grad_(True)
+    pn_m, pe_m, _, _ = R.stack_forward(p, xo, ei_ref, 2, 0.0, relu_masks=masks)
+    ((pn_m * ct_n).sum() + (pe_m * ct_e).sum()).backward()
+    assert rel(xg.grad.float(), xo.grad) < 2e-2
+    for kk in params:
+        assert rel(model.get_parameter(kk).grad, p[kk].grad) < 2e-2, kk

@@ -157,3 +157,13 @@ def test_sibling_layer_state_dict_layout_matches_reference():
         m(torch.zeros(9, D), torch.zeros(2, 72, dtype=torch.long), torch.zeros(72, D))
     with pytest.raises(AttributeError):
         rpg.simpleConvEdge(D, D, D, use_attention=False)
+
+
+def test_knn_graph_api():
+    """the restated torch_cluster semantics (edges neighbour -> centre, grouped by centre, nearest
+    first, no self loops) and the no-CPU-fallback rule."""
+    x = torch.tensor([[0.0, 0.0], [1.0, 0.0], [3.0, 0.0], [7.0, 0.0]])
+    ei = R.knn_graph(x, 2, 1, 4)
+    assert ei.tolist() == [[1, 2, 0, 2, 1, 0, 2, 1], [0, 0, 1, 1, 2, 2, 3, 3]]
+    with pytest.raises(ValueError):
+        rpg.knn_graph(torch.zeros(8, 64), 2, num_nodes_per_graph=4)
