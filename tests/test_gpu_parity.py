@@ -571,3 +571,47 @@ def test_stack_with_knn_rewiring_against_oracle():
     assert rel(xg.grad.float(), xo.grad) < 2e-2
     for kk in params:
         assert rel(model.get_parameter(kk).grad, p[kk].grad) < 2e-2, kk
+
+
+@pytest.mark.parametrize("kept", [[0], [0, 9], [3, 17, 30]])
+def test_layer_with_isolated_nodes_and_tiny_templates(kept):
+    """Edge dropout can leave nodes without incoming edges (their mean is 0, not the attention bias) and templates so
+    small that a 128-row block spans more than 64 nodes (gathers fall back from one-hot panels to the epilogue)."""
+    from relpose_gnn_b200.layers import layer_backward_raw, layer_forward_raw
+    D, N, Gn = 128, 9, 41
+    seed = 5000 + len(kept)
+    q = lambda t: t.bfloat16().double()                                         # noqa: E731
+    params = {k: (q(v) if k.endswith("weight") else v.float().double())
+              for k, v in R.synth_params(R.LAYER_SHAPES(D), seed, torch.float64).items()}
+    x = q(R.synth_inputs(Gn, N, D, seed + 1, torch.float64)[0])
+    keep = np.zeros(N * (N - 1) // 2, bool)
+    keep[kept] = True
+    tmpl = R.apply_edge_dropout(R.fc_edge_index(N), keep)
+    ei = R.batched_edge_index(tmpl, Gn, N)
+    indeg = torch.bincount(tmpl[1], minlength=N)
+    assert (indeg == 0).any()                                                    # the case under test
+    gen = torch.Generator().manual_seed(seed + 2)
+    e = q(torch.relu(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64)))
+    ct_o = q(torch.randn(Gn * N, D, generator=gen, dtype=torch.float64))
+    ct_e = q(torch.randn(ei.size(1), D, generator=gen, dtype=torch.float64))
+    m = make_layer(D, params)
+    graph = G.from_edge_index(ei.to(dev()), Gn * N)
+    assert graph.Ep == 2 * len(kept)
+    lw = m._packed(dev()).refresh(m)
+    acts = layer_forward_raw(lw, graph, x.to(dev()).bfloat16(), e.to(dev()).bfloat16())
+    grads = {k: torch.zeros_like(m.get_parameter(k)) for k in PARAM_ORDER}
+    dx, de = layer_backward_raw(lw, graph, acts, ct_o.to(dev()).bfloat16(), ct_e.to(dev()).bfloat16(), grads)
+    out_o, en_o, mid = R.layer_forward(params, x, ei, e, return_intermediates=True)
+    iso = (indeg == 0).repeat(Gn)
+    assert float(acts["a"].float().cpu()[iso].abs().max()) == 0.0               # mean over nothing
+    assert rel(acts["a"].float(), mid["a"]) < TOL_BF16
+    assert rel(acts["out"].float(), out_o) < TOL_BF16 and rel(acts["e_new"].float(), en_o) < TOL_BF16
+    masks = {k: (acts[k] > 0).cpu() for k in ("h1", "h2", "h3")}
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xo, eo = x.clone().requires_grad_(True), e.clone().requires_grad_(True)
+    out_m, en_m = R.layer_forward(p, xo, ei, eo, relu_masks=masks)
+    ((out_m * ct_o).sum() + (en_m * ct_e).sum()).backward()
+    assert rel(dx.float(), xo.grad) < TOL_GRAD and rel(de.float(), eo.grad) < TOL_GRAD
+    errs = {k: rel(grads[k], p[k].grad) for k in PARAM_ORDER}
+    bad = {k: v for k, v in errs.items() if v > (4 * TOL_GRAD if k.startswith("att.") and k.endswith("bias") else TOL_GRAD)}
+    assert not bad, bad
