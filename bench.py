@@ -28,7 +28,11 @@ WORKLOADS = {
     "train_2048x17": (2048, 17, 512, "train"),
     "infer_4096x9": (4096, 9, 512, "infer"),
     "infer_fp32_4096x9": (4096, 9, 512, "infer_fp32"),     # BASELINE configs[1]: fp32 mode (split-bf16 arithmetic)
+    "infer_8192x9": (8192, 9, 512, "infer"),               # BASELINE configs[4], weak: 65 536 graphs over 8 GPUs
+    "infer_65536x9_strong": (65536, 9, 512, "infer"),      # BASELINE configs[4], strong: 65 536 graphs in total
+    "train_2048x17_strong": (2048, 17, 512, "train"),      # BASELINE configs[3], strong: 2048 graphs in total
 }
+STRONG = {"infer_65536x9_strong", "train_2048x17_strong"}
 METRIC = "GNN graphs/sec fwd+bwd"
 R_ROUNDS = 2
 
@@ -167,6 +171,11 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     lib = _lib.load()
     G, N, D, mode = WORKLOADS[args.workload]
+    strong = args.workload in STRONG
+    if strong:
+        if G % world:
+            raise SystemExit("strong-scaling workloads need a GPU count that divides the graph count")
+        G //= world                               # contiguous block of graphs per rank
     train = mode == "train"
     fp32_mode = mode == "infer_fp32"
     H = N * (N - 1) // 2
@@ -290,7 +299,7 @@ def run_ours(args):
         e2e_value = world * G / (ms_e2e * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32 (split-bf16 x3 on the bf16 tensor pipe)" if fp32_mode else "bf16",
             "data": "synthetic",
             "trials_ms_per_step": trials, "trials_e2e_ms_per_step": trials_e2e,

@@ -3,6 +3,7 @@
 // dropout + pose heads, pose loss, column sums.  All accesses are 16-byte vectorised and coalesced along the
 // feature dimension; no atomics on floating-point data (fixed summation order => bitwise reproducible).
 #include <algorithm>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -14,6 +15,18 @@
 namespace rpg {
 
 typedef __nv_bfloat16 bf16;
+
+// Raises a kernel's dynamic shared-memory limit once per size class.  Called from the forward thread and from autograd's
+// backward thread: the cached limit is guarded by a mutex.
+static std::mutex g_smem_mu;
+template <typename K>
+static void ensure_dyn_smem(K kern, size_t bytes, size_t* configured) {
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    if (bytes > *configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        *configured = bytes;
+    }
+}
 
 static inline int grid_for(long long work, int block, int cap = 148 * 16) {
     long long g = (work + block - 1) / block;
@@ -365,13 +378,18 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
 // fixed order, one thread per 8 feature columns.
 //   out[g*N+n, c] = scale[n] * sum_{k in csr(n)} v[g*Ep+k, c] * (mask ? mask[g*Ep+k, c] > 0 : 1)
 // ------------------------------------------------------------------------------------------------
-template <typename I>   // index type of the flattened (row, column-group) space: 32-bit whenever it fits (cheap divisions)
-__global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf16* __restrict__ mask, int ldm,
+// PLAIN: no ReLU mask and no fp32-mode lo plane (every launch of the bf16 path) -- a third of the registers, so more
+// rows are in flight per SM.
+template <typename I, bool PLAIN>   // I: index type of the flattened (row, column-group) space: 32-bit whenever it fits
+__global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf16* __restrict__ mask_, int ldm,
                                    const int* __restrict__ ptr, const int* __restrict__ idx,
                                    const float* __restrict__ scale, long long Nt, int N, int Ep, int D,
-                                   bf16* __restrict__ out, int ldo, const bf16* __restrict__ v_lo,
-                                   bf16* __restrict__ out_lo) {
+                                   bf16* __restrict__ out, int ldo, const bf16* __restrict__ v_lo_,
+                                   bf16* __restrict__ out_lo_) {
     pdl_prologue();
+    const bf16* __restrict__ mask = PLAIN ? nullptr : mask_;
+    const bf16* __restrict__ v_lo = PLAIN ? nullptr : v_lo_;
+    bf16* __restrict__ out_lo = PLAIN ? nullptr : out_lo_;
     const int tpr = D >> 3;                                   // threads per row
     const I total = (I)Nt * (I)tpr;
     for (I t = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; t < total; t += (I)gridDim.x * (I)blockDim.x) {
@@ -1270,10 +1288,7 @@ int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_
     if (c % 4 || c < 4 || c > 512) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c must be a multiple of 4 in [4,512]");
     const size_t smem = (size_t)ATT_WARPS * 8 * c * sizeof(float);
     static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    ensure_dyn_smem(attention_bwd_kernel, smem, &configured);
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
     launch_pdl(attention_bwd_kernel, dim3(grid), dim3(ATT_WARPS * 32), smem, as_stream(stream), gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
                                                                            Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp, aux);
@@ -1286,7 +1301,9 @@ static int launch_segment(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int 
     if (!v || !g || !out || !ptr || !idx || D % 8 || ldv % 8 || ldo % 8) return set_error(RPG_E_ARG, "segment_sum: bad arguments");
     const long long Nt = (long long)g->G * g->N;
     const bool small = Nt * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
-    auto kern = small ? segment_sum_kernel<unsigned> : segment_sum_kernel<long long>;
+    const bool plain = !mask && !v_lo && !out_lo;
+    auto kern = small ? (plain ? segment_sum_kernel<unsigned, true> : segment_sum_kernel<unsigned, false>)
+                      : (plain ? segment_sum_kernel<long long, true> : segment_sum_kernel<long long, false>);
     launch_pdl(kern, dim3(grid_for(Nt * (D / 8), 256)), dim3(256), 0, s, reinterpret_cast<const bf16*>(v), ldv,
                reinterpret_cast<const bf16*>(mask), ldm, ptr, idx, scale, Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out), ldo,
                reinterpret_cast<const bf16*>(v_lo), reinterpret_cast<bf16*>(out_lo));
@@ -1358,10 +1375,7 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
         const size_t smem = (size_t)6 * D * sizeof(float);
         if (D > 2048) return set_error(RPG_E_UNSUPPORTED, "head_fwd: D > 2048");
         static size_t configured = 48 * 1024;
-        if (smem > configured) {
-            cudaFuncSetAttribute(head_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
+        ensure_dyn_smem(head_fwd_kernel<0, false>, smem, &configured);
         launch_pdl((head_fwd_kernel<0, false>), dim3(grid), dim3(HEAD_WARPS * 32), smem, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     }
     return check_launch("head_fwd_kernel");
@@ -1388,10 +1402,7 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     const int phases = HEADB_THREADS / ct;
     const size_t smem = ((size_t)(phases - 1) * 48 * ct + (size_t)phases * 6) * sizeof(float);
     static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    ensure_dyn_smem(head_bwd_kernel, smem, &configured);
     cudaStream_t s = as_stream(stream);
     launch_pdl(head_bwd_kernel, dim3(blocks), dim3(HEADB_THREADS), smem, s, dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed,
                                                         thresh, use_seed, scale, w6, mask_relu,

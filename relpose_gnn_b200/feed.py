@@ -94,13 +94,24 @@ class ScalarReadback:
         self.depth = depth
         self.head = self.tail = self.pending = 0
         self.d2h_bytes = 0
+        self.copy_stream = None                      # created on first use (per device)
 
     def push(self, t):
+        """The copy runs on a side stream behind everything queued on the current stream so far: large results
+        (inference poses) leave the device while the next step computes."""
         if self.pending == self.depth:
             raise RuntimeError("ScalarReadback: pop() before pushing more")
         k = self.head
-        self.host[k].copy_(t.detach().reshape(-1), non_blocking=True)
-        self.done[k].record(torch.cuda.current_stream(t.device))
+        src = t.detach().reshape(-1)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(t.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(t.device))
+        src.record_stream(self.copy_stream)          # the caching allocator must not recycle it under the copy
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            self.host[k].copy_(src, non_blocking=True)
+            self.done[k].record(self.copy_stream)
         self.d2h_bytes += self.host[k].numel() * self.host[k].element_size()
         self.head = (k + 1) % self.depth
         self.pending += 1
