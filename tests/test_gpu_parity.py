@@ -615,3 +615,37 @@ def test_layer_with_isolated_nodes_and_tiny_templates(kept):
     errs = {k: rel(grads[k], p[k].grad) for k in PARAM_ORDER}
     bad = {k: v for k, v in errs.items() if v > (4 * TOL_GRAD if k.startswith("att.") and k.endswith("bias") else TOL_GRAD)}
     assert not bad, bad
+
+
+def test_seeded_dropout_equals_explicit_masks_forward_and_backward():
+    """The in-kernel counter-based feature dropout (production path) against the same masks passed explicitly (the
+    path every oracle comparison uses): identical poses and gradients."""
+    from relpose_gnn_b200 import ops
+    D, N, Gn = 256, 9, 11
+    case = R.synth_stack_case(D, N, Gn, 2024, droprate=0.5, edge_dropout=True)
+    ei = case["edge_index"].to(dev())
+
+    def run(explicit_seed=None):
+        model = rpg.RelPoseGNN(D, D, D, droprate=0.5).to(dev())
+        model.load_state_dict({k: v.float() for k, v in case["params"].items()}, strict=False)
+        model.dropout_seed = 4711
+        x = case["x"].float().to(dev()).requires_grad_(True)
+        if explicit_seed is None:
+            pn, pe, _ = model(x, ei)
+        else:
+            kx = ops.dropout_mask(explicit_seed, 0.5, Gn * N, D, dev())
+            ke = ops.dropout_mask(explicit_seed + 1, 0.5, ei.size(1), D, dev())
+            pn, pe, _ = model(x, ei, keep_x=kx, keep_e=ke)
+        gen = torch.Generator().manual_seed(3)
+        ct_n = torch.randn(pn.shape, generator=gen).to(dev())
+        ct_e = torch.randn(pe.shape, generator=gen).to(dev())
+        ((pn * ct_n).sum() + (pe * ct_e).sum()).backward()
+        return model.dropout_seed, pn.detach(), pe.detach(), x.grad.detach(), {k: v.grad.detach().clone()
+                                                                              for k, v in model.named_parameters()}
+
+    seed_used, pn0, pe0, gx0, g0 = run()
+    _, pn1, pe1, gx1, g1 = run(explicit_seed=seed_used)
+    assert rel(pn0, pn1.double().cpu()) < 1e-6 and rel(pe0, pe1.double().cpu()) < 1e-6
+    assert rel(gx0, gx1.double().cpu()) < 1e-6
+    for k in g0:
+        assert rel(g0[k], g1[k].double().cpu()) < 1e-5, k
