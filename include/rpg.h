@@ -164,6 +164,12 @@ typedef struct {
    * a_colsum [splits, M]; accumulated from the shared-memory operand tiles by the warps that are idle during the
    * main loop, so the gradient tensor is not read a second time.  NULL = off.                          */
   float* a_colsum;
+  /* NT mode, plain epilogue: counter-based feature dropout fused into the `out_relu` output (posenet.py:1073-1075 applied
+   * by the kernel that produces the last layer's outputs): out_relu = keep ? max(v, 0) / (1 - drop_p) : 0 and out_bits =
+   * pattern of THAT tensor; `out` stays undropped.  The keep decision is the one of rpg_dropout_mask(drop_seed, drop_p).
+   * drop_p = 0: off.                                                                                      */
+  uint64_t drop_seed;
+  float drop_p;
 } rpg_gemm_t;
 
 int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream);
@@ -268,6 +274,18 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
                  uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf,
                  float* dw_t, float* dw_q, float* db_t, float* db_q, int accumulate, float* ws,
                  rpg_stream_t stream);
+
+/* Pose heads on tensor cores, for features that the producing GEMM already dropped and rescaled (rpg_gemm_t.drop_*):
+ * forward is a plain rpg_gemm (pose = feat_d W6^T + b6 with W6 padded to 8 rows); this is its backward:
+ *   dfeat = scale * (dpose W6) * [feat_d > 0]  (bits = pattern of feat_d = keep & relu; dfeat may be NULL)
+ *   dw_t / dw_q (+)= (dpose^T feat_d) rows 0..2 / 3..5 ;  db_t / db_q (+)= column sums of dpose.
+ * dpose fp32 [rows, 6] travels as a bf16 K panel [hi | lo] (dp16: scratch [rows, 64]); w6T_ext bf16 [D, 64] holds
+ * W6[j, :] in columns j and 8 + j (j < 6), zeros elsewhere; ws: rpg_head_bwd_tc_ws_floats(D) floats. */
+int64_t rpg_head_bwd_tc_ws_floats(int D);
+int rpg_pack_dpose(const float* dpose, int64_t rows, rpg_bf16* dp16, float scale, float* scale_out, rpg_stream_t stream);
+int rpg_head_bwd_tc(const float* dpose, const rpg_bf16* feat_d, int ldf, const uint8_t* bits, int64_t rows, int D,
+                    float scale, const rpg_bf16* w6T_ext, rpg_bf16* dp16, rpg_bf16* dfeat, int lddf, float* dw_t,
+                    float* dw_q, float* db_t, float* db_q, float* ws, rpg_stream_t stream);
 
 /* compute_RP (posenet.py:1021-1031) + the L1 sums of PoseNetCriterion (criterion.py:51-52) fused:
  * target[e] = poses[src(e)] - poses[dst(e)];  sums[0] = sum|pred_t - targ_t|, sums[1] = sum|pred_q - targ_q|
@@ -377,6 +395,10 @@ typedef struct {                  /* activations of one layer call; all bf16 unl
   const uint8_t* e_bits;          /* [Et, D/8] optional pattern of the input e (used when mask_de)       */
   rpg_bf16* ybar;                 /* [Nt, max(c,64)] scratch: mean over in-edges of y                    */
   rpg_bf16* mbar;                 /* [Nt, D]         scratch: mean over in-edges of m                    */
+  /* feature dropout of the stack's last round fused into the producing GEMMs (rpg_gemm_t.drop_*): out_relu and
+   * e_new_relu are then the DROPPED, rescaled features the pose heads consume, out_bits / e_new_bits their patterns. */
+  uint64_t drop_seed_x, drop_seed_e;
+  float drop_p;                   /* 0 = off */
 } rpg_layer_acts_t;
 
 int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,

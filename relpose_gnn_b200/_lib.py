@@ -40,7 +40,7 @@ class Gemm(C.Structure):
                 ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I),
                 ("gadd_f32", P * 2), ("gadd_f32_ld", I * 2), ("resid_lo", P), ("out_lo", P), ("out_relu_lo", P),
                 ("n_gseg", I), ("gsel", P * 2), ("gsel_patterns", I), ("gsel_div", I), ("gsrc", P * 2), ("gsrc_ld", I * 2),
-                ("gsrc_rows", I), ("a_colsum", P)]
+                ("gsrc_rows", I), ("a_colsum", P), ("drop_seed", C.c_uint64), ("drop_p", C.c_float)]
 
 
 class LayerWeights(C.Structure):
@@ -53,7 +53,8 @@ class LayerWeights(C.Structure):
 class LayerActs(C.Structure):
     _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
                                  "h3", "out", "out_relu", "att_aux", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
-                                 "x_bits", "e_bits", "ybar", "mbar")]
+                                 "x_bits", "e_bits", "ybar", "mbar")] + [
+        ("drop_seed_x", C.c_uint64), ("drop_seed_e", C.c_uint64), ("drop_p", C.c_float)]
 
 
 class LayerWeightsSplit(C.Structure):
@@ -125,6 +126,9 @@ SIGNATURES = {
     "rpg_upload_words": (I, [P, P, I64, P]),
     "rpg_qexp": (I, [P, I64, P, P]),
     "rpg_knn_graph": (I, [P, I, I, I, I, I, P, P]),
+    "rpg_head_bwd_tc_ws_floats": (I64, [I]),
+    "rpg_pack_dpose": (I, [P, I64, P, C.c_float, P, P]),
+    "rpg_head_bwd_tc": (I, [P, P, I, P, I64, I, C.c_float, P, P, P, I, P, P, P, P, P, P]),
     "rpg_scale_rows": (I, [P, I, I64, I, P, I, P, I, P]),
     "rpg_edge_gather": (I, [P, I, I, P, I, I, P, C.POINTER(Graph), I, I, P, P, I, P, P]),
     "rpg_eval_compose": (I, [P, P, C.POINTER(Graph), I, P, P, P, P, P]),

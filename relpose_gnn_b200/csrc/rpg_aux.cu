@@ -578,19 +578,6 @@ __global__ void edge_init_fwd_f32_kernel(const float* __restrict__ pmm, int ldp,
 // ------------------------------------------------------------------------------------------------
 // Dropout keep decision: explicit uint8 mask (parity tests) or a counter-based hash of (seed,row,col)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {   // lowbias32 finaliser
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return x;
-}
-// One 32-bit hash serves 4 consecutive columns (8 bits each): keep iff byte >= thresh8, P(drop) = thresh8 / 256.
-__device__ __forceinline__ uint32_t keep_hash4(unsigned long long seed, long long row, int col4) {
-    return mix32(mix32((uint32_t)seed ^ (uint32_t)(row * 0x9E3779B1ull)) ^ (uint32_t)(seed >> 32) ^
-                 (uint32_t)col4 * 0x85EBCA77u ^ (uint32_t)(row >> 32));
-}
-__device__ __forceinline__ bool keep_from_hash(uint32_t h, int q, uint32_t thresh8) {
-    return ((h >> (8 * (q & 3))) & 0xFFu) >= thresh8;
-}
-
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long rows, int D,
                                     uint8_t* __restrict__ keep) {
     pdl_prologue();
@@ -1034,6 +1021,29 @@ knn_graph_kernel(const float* __restrict__ x, int ldx, int N, int D, int k, long
     }
 }
 
+// dpose fp32 [rows, 6] -> bf16 [rows, 64] K-panel for the tensor-core head backward: columns j = hi, 8 + j = lo
+// (dpose = hi + lo to ~2^-17), everything else zero.  Also drops `scale` into scale_out[0] (a 1-entry row-scale table).
+__global__ void pack_dpose_kernel(const float* __restrict__ dpose, long long rows, bf16* __restrict__ dp16, float scale,
+                                  float* __restrict__ scale_out) {
+    pdl_prologue();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out) scale_out[0] = scale;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        float hi[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float v = dpose[r * 6 + j];
+            hi[j] = __bfloat162float(__float2bfloat16_rn(v));
+            lo[j] = v - hi[j];
+        }
+        uint4* o = reinterpret_cast<uint4*>(dp16 + r * 64);
+        o[0] = pack8(hi);
+        o[1] = pack8(lo);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 2; q < 8; ++q) o[q] = z;
+    }
+}
+
 // Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
 // never queue behind a large host->device copy of another stream.
 constexpr int UPLOAD_WORDS = 2032;
@@ -1044,23 +1054,38 @@ upload_words_kernel(const __grid_constant__ UploadWords p, int32_t* __restrict__
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = p.w[i];
 }
 
-// Batched form: blockIdx.y picks the descriptor; always accumulating.
+// Batched form: blockIdx.y picks the descriptor; always accumulating.  A block covers 32 consecutive elements with 8
+// split phases (phase q sums splits q, q + 8, ...; the phases are folded through shared memory in a fixed order), so
+// small outputs with many splits do not serialise on one thread.  Deterministic.
 __global__ void __launch_bounds__(256)
 reduce_splits_batch_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
     pdl_prologue();
+    __shared__ float red[8][32];
     const rpg_reduce_desc_t& d = batch.d[blockIdx.y];
     const long long n = (long long)d.rows * d.cols;
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+    const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    for (long long base = blockIdx.x * 32LL; base < n; base += (long long)gridDim.x * 32) {
+        const long long i = base + lane;
         float s0 = 0.f, s1 = 0.f;
-        int b = 0;
-        for (; b + 1 < d.splits; b += 2) {
-            s0 += d.part[(size_t)b * d.stride + i];
-            s1 += d.part[(size_t)(b + 1) * d.stride + i];
+        if (i < n) {
+            int b = ph;
+            for (; b + 8 < d.splits; b += 16) {
+                s0 += d.part[(size_t)b * d.stride + i];
+                s1 += d.part[(size_t)(b + 8) * d.stride + i];
+            }
+            if (b < d.splits) s0 += d.part[(size_t)b * d.stride + i];
         }
-        if (b < d.splits) s0 += d.part[(size_t)b * d.stride + i];
-        float* o = d.out + (size_t)r * d.ldo + c;
-        *o += s0 + s1;
+        red[ph][lane] = s0 + s1;
+        __syncthreads();
+        if (ph == 0 && i < n) {
+            float s = red[0][lane];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) s += red[k][lane];
+            const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+            float* o = d.out + (size_t)r * d.ldo + c;
+            *o += s;
+        }
+        __syncthreads();
     }
 }
 
@@ -1489,6 +1514,13 @@ int rpg_scale_rows(const rpg_bf16* v, int ldv, int64_t rows, int D, const float*
     return check_launch("scale_rows_kernel");
 }
 
+int rpg_pack_dpose(const float* dpose, int64_t rows, rpg_bf16* dp16, float scale, float* scale_out, rpg_stream_t stream) {
+    if (!dpose || !dp16 || rows <= 0) return set_error(RPG_E_ARG, "pack_dpose: bad arguments");
+    launch_pdl(pack_dpose_kernel, dim3(grid_for(rows, 256)), dim3(256), 0, as_stream(stream), dpose, rows,
+               reinterpret_cast<bf16*>(dp16), scale, scale_out);
+    return check_launch("pack_dpose_kernel");
+}
+
 int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* edge_index, rpg_stream_t stream) {
     if (!x || !edge_index || G <= 0 || N < 2 || N > KNN_MAX_N || k < 1 || k >= N || D % 4 || ldx % 4)
         return set_error(RPG_E_ARG, "knn_graph: need 2 <= N <= 64, 1 <= k < N, D and pitch multiples of 4");
@@ -1538,7 +1570,7 @@ int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream
             return set_error(RPG_E_ARG, "reduce_splits_batch: bad descriptor");
         most = std::max(most, (long long)d.rows * d.cols);
     }
-    dim3 grid((unsigned)grid_for(most, 256, 1024), (unsigned)batch->n);
+    dim3 grid((unsigned)grid_for(most, 32, 8192), (unsigned)batch->n);
     launch_pdl(reduce_splits_batch_kernel, dim3(grid), dim3(256), 0, as_stream(stream), *batch);
     return check_launch("reduce_splits_batch_kernel");
 }

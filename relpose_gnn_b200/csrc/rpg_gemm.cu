@@ -79,6 +79,9 @@ struct GemmKParams {
     // TN mode: column sums of A (= bias gradient when A is dY) accumulated by the otherwise idle epilogue warps
     float* a_colsum;               // [splits, M] partial sums, or NULL
     int resid_tma;                 // pair kernels: the residual tile arrives by TMA in a per-warp operand buffer
+    unsigned long long drop_seed;  // fused feature dropout of the out_relu output (plain epilogue)
+    uint32_t drop_thresh;          // keep iff hash byte >= thresh; 0 = off
+    float drop_scale;              // 1 / (1 - p)
 };
 
 struct GemmTmaps {
@@ -127,9 +130,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     // (coalesced, asynchronous, one chunk ahead) instead of row-per-thread loads, and the operand-register arrays of
     // the general EPI = 1 epilogue (which spill) are not compiled in.
     constexpr bool OPBUF = RTMA;
-    constexpr int NS = OPBUF ? 5 : (PAIR ? 6 : STAGES);                    // ring depth
+    // STG_BUFS = 2 would give one ring stage of the plain pair kernel to a SECOND staging tile per epilogue warp, so
+    // that a chunk's TMA store need not finish reading shared memory before the next chunk is written.  Measured on
+    // B200: no gain (plain 155648 x 512 x 512 in the training step 87 -> 91 us with the 5-stage ring it costs) -- the
+    // wait is not what paces an item -- so the single tile and the 6-stage ring stay.
+    constexpr int STG_BUFS = 1;
+    constexpr int NS = (OPBUF || STG_BUFS == 2) ? 5 : (PAIR ? 6 : STAGES);  // ring depth
     constexpr int BST = PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;          // B bytes per stage in this CTA
-    static_assert(NS * (A_STAGE_BYTES + BST) + (OPBUF ? EPI_WARPS * EPI_STAGE_BYTES : 0) == SMEM_RING_BYTES, "ring carve");
+    static_assert(NS * (A_STAGE_BYTES + BST) + ((OPBUF || STG_BUFS == 2) ? EPI_WARPS * EPI_STAGE_BYTES : 0) == SMEM_RING_BYTES,
+                  "ring carve");
     const CUtensorMap& tmA0 = tm.a[0];
     const CUtensorMap& tmB = tm.b;
     const CUtensorMap& tmOut = tm.out;
@@ -333,8 +342,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int half = ew >> 2;                  // the two warps of a quadrant alternate 64-column chunks
         const int n_chunks = (p.block_n + 63) / 64;
-        uint8_t* stg = smem + SMEM_RING_BYTES + SMEM_BAR_BYTES + ew * EPI_STAGE_BYTES;
+        uint8_t* const stg0 = smem + SMEM_RING_BYTES + SMEM_BAR_BYTES + ew * EPI_STAGE_BYTES;
+        uint8_t* const stg1 = smem + NS * (A_STAGE_BYTES + BST) + ew * EPI_STAGE_BYTES;   // only with STG_BUFS == 2
+        uint8_t* stg = stg0;
         uint8_t* my_row = stg + lane * 128;
+        int sbuf = 0;
+        // a staging tile that no earlier TMA store of this warp still reads (stores alternate between the tiles)
+        auto acquire_stage = [&]() {
+            if (lane == 0) { if (STG_BUFS == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }
+            __syncwarp();
+            if (STG_BUFS == 2) {
+                sbuf ^= 1;
+                stg = sbuf ? stg1 : stg0;
+                my_row = stg + lane * 128;
+            }
+        };
         // operand buffer of this warp (OPBUF kernels): the ring stage that was given up, [32 rows][128 B] swizzled
         uint8_t* opbuf = smem + NS * (A_STAGE_BYTES + BST) + ew * EPI_STAGE_BYTES;
         constexpr bool rtma = RTMA;
@@ -517,9 +539,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         }
                     }
                 }
-                // the staging tile is free once the previous TMA store of this warp has read it
-                if (lane == 0) bulk_wait_read_all();
-                __syncwarp();
+                acquire_stage();
 
                 if (MODE == 0) {
                     if (p.bias) {
@@ -603,10 +623,24 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
 #pragma unroll
                         for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
+                    // fused feature dropout (last layer of the stack): keep pattern of this row's 64 columns, the same
+                    // counter-based decision the head kernels and rpg_dropout_mask make
+                    unsigned long long keepm = ~0ull;
+                    if (EPI == 0 && p.drop_thresh) {
+                        keepm = 0ull;
+#pragma unroll
+                        for (int q4 = 0; q4 < 16; ++q4) {
+                            const uint32_t h = keep_hash4(p.drop_seed, row, (n0 >> 2) + q4);
+#pragma unroll
+                            for (int b4 = 0; b4 < 4; ++b4)
+                                keepm |= (unsigned long long)(((h >> (8 * b4)) & 0xFFu) >= p.drop_thresh) << (4 * q4 + b4);
+                        }
+                    }
                     if (p.out_bits && row_ok) {
                         unsigned long long ob = 0ull;
 #pragma unroll
                         for (int j = 0; j < 64; ++j) ob |= (unsigned long long)(f[j] > 0.f) << j;
+                        ob &= keepm;
                         *reinterpret_cast<unsigned long long*>(p.out_bits + (size_t)row * p.out_bits_ld + (n0 >> 3)) = ob;
                     }
                     if (p.out) {
@@ -622,9 +656,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         if (lane == 0) { tma_store_2d(&tmOut, stg, n0, row0); bulk_commit(); }
                     }
                     if (p.out_relu) {
-                        if (p.out) {
-                            if (lane == 0) bulk_wait_read_all();
-                            __syncwarp();
+                        if (p.out) acquire_stage();
+                        if (EPI == 0 && p.drop_thresh) {
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) f[j] = ((keepm >> j) & 1ull) ? fmaxf(f[j], 0.f) * p.drop_scale : 0.f;
                         }
 #pragma unroll
                         for (int qq = 0; qq < 8; ++qq) {
@@ -643,8 +678,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
 #pragma unroll
                         for (int pass = 0; pass < 2; ++pass) {
                             if (pass == 0 ? p.out_lo == nullptr : p.out_relu_lo == nullptr) continue;
-                            if (lane == 0) bulk_wait_read_all();
-                            __syncwarp();
+                            acquire_stage();
 #pragma unroll
                             for (int qq = 0; qq < 8; ++qq) {
                                 float r[8];
@@ -669,10 +703,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {               // 32 fp32 columns = 128 B per row per pass
                         if (h * 32 >= ncols) break;
-                        if (h == 1 || (MODE == 0 && (p.out || p.out_relu))) {
-                            if (lane == 0) bulk_wait_read_all();
-                            __syncwarp();
-                        }
+                        if (h == 1 || (MODE == 0 && (p.out || p.out_relu))) acquire_stage();
 #pragma unroll
                         for (int qq = 0; qq < 8; ++qq)
                             *reinterpret_cast<float4*>(my_row + ((qq ^ my_sw) << 4)) =
@@ -898,6 +929,13 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     p.ldo = g->ldo;
     p.out_f32 = g->out_f32; p.ldo_f32 = g->ldo_f32;
     p.a_colsum = g->mode == 1 ? g->a_colsum : nullptr;
+    if (g->drop_p > 0.f) {
+        if (g->mode != 0 || !g->out_relu || g->out_f32 || g->gadd[0] || g->gadd[1] || g->resid || g->mask || g->drop_p >= 1.f)
+            return set_error(RPG_E_ARG, "rpg_gemm: fused dropout needs NT mode, an out_relu output, the plain epilogue, 0 < p < 1");
+        p.drop_seed = g->drop_seed;
+        p.drop_thresh = (uint32_t)(g->drop_p * 256.0f + 0.5f);
+        p.drop_scale = 1.f / (1.f - g->drop_p);
+    }
     p.mask_bits = g->mask_bits; p.mask_bits_ld = g->mask_bits_ld;
     p.out_bits = g->out_bits; p.out_bits_ld = g->out_bits_ld;
     if ((p.mask_bits || p.out_bits) && (g->mode != 0 || p.N % 64 || block_n % 64))

@@ -244,6 +244,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g = nt((int)Et, D, t->h1, D, D, w->W2e, D);
     g.bias = w->b2e; g.out = t->e_new; g.out_relu = t->e_new_relu; g.ldo = D;
     g.out_bits = t->e_new_bits; g.out_bits_ld = D / 8;
+    if (t->drop_p > 0.f && t->e_new_relu) { g.drop_p = t->drop_p; g.drop_seed = t->drop_seed_e; }
     RPG_TRY(gemm_launch(&g, s));
 
     // (4) message MLP layer 1 (my_gnn_layer.py:280,305): h2 = relu(e' W1m_e^T + P_m[src] + b)   (x_j = source)
@@ -296,6 +297,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g = nt((int)Nt, D, t->h3, D, D, w->W2u, D);
     g.bias = w->b2u; g.out = t->out; g.out_relu = t->out_relu; g.ldo = D;
     g.out_bits = t->out_bits; g.out_bits_ld = D / 8;
+    if (t->drop_p > 0.f && t->out_relu) { g.drop_p = t->drop_p; g.drop_seed = t->drop_seed_x; }
     RPG_TRY(gemm_launch(&g, s));
     return 0;
 }
@@ -369,6 +371,50 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     g.bias = w->b2u; g.out = t->out_hi; g.out_lo = t->out_lo; g.ldo = D;
     g.out_relu = t->out_relu_hi; g.out_relu_lo = t->out_relu_lo;
     RPG_TRY(gemm_launch(&g, s));
+    return 0;
+}
+
+int64_t rpg_head_bwd_tc_ws_floats(int D) {
+    int sms = sm_count_cached();
+    if (sms <= 0 || sms > 160) sms = 160;
+    return 64 + (int64_t)sms * 16 * D + (int64_t)sms * 16 + 64;
+}
+
+int rpg_head_bwd_tc(const float* dpose, const rpg_bf16* feat_d, int ldf, const uint8_t* bits, int64_t rows, int D,
+                    float scale, const rpg_bf16* w6T_ext, rpg_bf16* dp16, rpg_bf16* dfeat, int lddf, float* dw_t,
+                    float* dw_q, float* db_t, float* db_q, float* ws, rpg_stream_t stream) {
+    if (!dpose || !feat_d || !w6T_ext || !dp16 || !dw_t || !dw_q || !db_t || !db_q || !ws || rows <= 0 || D % 64 || ldf % 8)
+        return set_error(RPG_E_ARG, "head_bwd_tc: bad arguments");
+    if (rows > 0x7fffffff) return set_error(RPG_E_UNSUPPORTED, "head_bwd_tc: more than 2^31 rows");
+    cudaStream_t s = as_stream(stream);
+    const int sms = sm_count_cached();
+    // K panel [hi | lo] of dpose; ws[0] = scale (1-entry row-scale table)
+    RPG_TRY(rpg_pack_dpose(dpose, rows, dp16, scale, ws, stream));
+    if (dfeat) {
+        // dfeat = scale * (dpose W6) * [feat_d > 0]      (K = 64: slots j and 8 + j both multiply W6[j, :])
+        if (!bits) return set_error(RPG_E_ARG, "head_bwd_tc: dfeat needs the bit pattern of the dropped features");
+        rpg_gemm_t g = nt((int)rows, D, dp16, 64, 64, w6T_ext, 64);
+        g.row_scale = ws; g.row_scale_mod = 1;
+        g.mask_bits = bits; g.mask_bits_ld = D / 8;
+        g.out = dfeat; g.ldo = lddf;
+        RPG_TRY(gemm_launch(&g, s));
+    }
+    // dW6 = dpose^T feat_d: rows j (hi) and 8 + j (lo) of a [16, D] TN product; db6 = column sums of the panel
+    float* part = ws + 64;
+    int splits = 0;
+    RPG_TRY(wgrad_partials(dp16, 64, 16, feat_d, ldf, D, rows, part, sms, s, &splits, /*with_colsum=*/true));
+    const float* cs = part + (size_t)splits * 16 * D;
+    const long long stride = 16LL * D;
+    for (int half = 0; half < 2; ++half) {           // hi rows, then lo rows: two folds into the same outputs
+        rpg_reduce_batch_t b;
+        b.n = 4;
+        const int r0 = half * 8;
+        b.d[0] = {part + (size_t)(r0 + 0) * D, dw_t, stride, splits, 3, D, D};
+        b.d[1] = {part + (size_t)(r0 + 3) * D, dw_q, stride, splits, 3, D, D};
+        b.d[2] = {cs + r0 + 0, db_t, 16, splits, 1, 3, 3};
+        b.d[3] = {cs + r0 + 3, db_q, 16, splits, 1, 3, 3};
+        RPG_TRY(rpg_reduce_splits_batch(&b, stream));
+    }
     return 0;
 }
 

@@ -103,6 +103,7 @@ __device__ __forceinline__ void tma_store_3d(const void* desc, const void* src, 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Wait until the bulk stores committed by this thread have finished READING their shared-memory source.
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------ clusters
@@ -235,6 +236,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ------------------------------------------------------------------ counter-based feature-dropout decision
+// Shared by the pose-head kernels, rpg_dropout_mask and the GEMM epilogue (fused dropout of the last layer outputs).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {   // lowbias32 finaliser
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// One 32-bit hash serves 4 consecutive columns (8 bits each): keep iff byte >= thresh8, P(drop) = thresh8 / 256.
+__device__ __forceinline__ uint32_t keep_hash4(unsigned long long seed, long long row, int col4) {
+    return mix32(mix32((uint32_t)seed ^ (uint32_t)(row * 0x9E3779B1ull)) ^ (uint32_t)(seed >> 32) ^
+                 (uint32_t)col4 * 0x85EBCA77u ^ (uint32_t)(row >> 32));
+}
+__device__ __forceinline__ bool keep_from_hash(uint32_t h, int q, uint32_t thresh8) {
+    return ((h >> (8 * (q & 3))) & 0xFFu) >= thresh8;
+}
 
 // Programmatic dependent launch (see rpg_internal.h: launch_pdl).  No-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_prologue() {

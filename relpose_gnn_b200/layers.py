@@ -235,7 +235,7 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
 
 
 def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None, e_bits=None, arena=None,
-                      for_backward=True):
+                      for_backward=True, drop=None):
     """Runs rpg_layer_fwd on bf16 inputs; returns the dict of activation tensors (kept for backward).
     x_bits / e_bits: optional ReLU bit patterns of the inputs (when they are ReLU outputs of a previous op)."""
     D = weights.D
@@ -272,6 +272,10 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
     s = _lib.LayerActs()
     for k, v in a.items():
         setattr(s, k, v.data_ptr())
+    if drop is not None:            # (p, seed_x, seed_e): the last round's ReLU copies leave the GEMMs dropped + rescaled
+        if not want_relu_copies:
+            raise ValueError("fused feature dropout acts on the ReLU copies")
+        s.drop_p, s.drop_seed_x, s.drop_seed_e = float(drop[0]), int(drop[1]), int(drop[2])
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(_lib.load().rpg_layer_fwd(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd")
     a["_struct"] = s

@@ -47,15 +47,29 @@ class _StackFn(torch.autograd.Function):
         ops.edge_init_fwd(pmm, model.proj_edge.bias.data, graph, D, e, e_bits)
         acts = []
         xin, x_bits = xb, None
-        for _ in range(R):                                       # same gnn1 weights each round (posenet.py:1060-1069)
+        p_drop, keep_x, keep_e, seed = drop
+        # Seeded feature dropout (the production path) is applied by the GEMMs that produce the last round's outputs,
+        # and the heads then are plain tensor-core GEMMs.  Explicit keep masks (parity tests) and droprate 0 keep the
+        # stand-alone head kernels.
+        fused = p_drop > 0 and keep_x is None and model.tensor_core_heads
+        for r in range(R):                                       # same gnn1 weights each round (posenet.py:1060-1069)
             a = layer_forward_raw(lw, graph, xin, e, want_relu_copies=True, x_bits=x_bits, e_bits=e_bits, arena=arena,
-                                  for_backward=any(ctx.needs_input_grad))
+                                  for_backward=any(ctx.needs_input_grad),
+                                  drop=(p_drop, seed, seed + 1) if (fused and r == R - 1) else None)
             acts.append(a)
             xin, e, x_bits, e_bits = a["out_relu"], a["e_new_relu"], a["out_bits"], a["e_new_bits"]
-        p_drop, keep_x, keep_e, seed = drop
-        pose_n = ops.head_fwd(xin, sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop)
-        pose_e = ops.head_fwd(e, sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop)
+        if fused:
+            pose8_n = torch.empty(Nt, 8, dtype=torch.float32, device=dev)
+            pose8_e = torch.empty(Et, 8, dtype=torch.float32, device=dev)
+            ops.gemm_nt(xin, sw["w6n_p"], bias=sw["b6n_p"], out_f32=pose8_n)
+            ops.gemm_nt(e, sw["w6e_p"], bias=sw["b6e_p"], out_f32=pose8_e)
+            pose_n, pose_e = pose8_n[:, :6].contiguous(), pose8_e[:, :6].contiguous()
+        else:
+            pose_n = ops.head_fwd(xin, sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop)
+            pose_e = ops.head_fwd(e, sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop)
         ctx.model, ctx.graph, ctx.drop = model, graph, drop
+        ctx.fused_heads = fused
+        ctx.head_bits = (x_bits, e_bits)
         ctx.saved = (xb, pmm, acts, xin, e, lw, sw)
         ctx.x_dtype = x.dtype
         if model.keep_debug_activations:
@@ -88,6 +102,18 @@ class _StackFn(torch.autograd.Function):
 
         # heads (posenet.py:1077-1086): gradient w.r.t. the pre-ReLU layer outputs (mask_relu)
         d_e = d_x = None
+        if ctx.fused_heads:
+            scale = 1.0 / (1.0 - p_drop)
+            xb_bits, eb_bits = ctx.head_bits
+            if d_pose_e is not None:
+                d_e = ops.head_bwd_tc(d_pose_e.contiguous().float(), e_last, eb_bits, sw["w6eT"], scale,
+                                      grads["fc_xyz_R.weight"], grads["fc_wpqr_R.weight"], grads["fc_xyz_R.bias"],
+                                      grads["fc_wpqr_R.bias"])
+            if d_pose_n is not None:
+                d_x = ops.head_bwd_tc(d_pose_n.contiguous().float(), x_last, xb_bits, sw["w6nT"], scale,
+                                      grads["fc_xyz.weight"], grads["fc_wpqr.weight"], grads["fc_xyz.bias"],
+                                      grads["fc_wpqr.bias"])
+            d_pose_e = d_pose_n = None
         if d_pose_e is not None:
             d_e = ops.head_bwd(d_pose_e.contiguous().float(), e_last, sw["w6e"], grads["fc_xyz_R.weight"],
                                grads["fc_wpqr_R.weight"], grads["fc_xyz_R.bias"], grads["fc_wpqr_R.bias"],
@@ -140,6 +166,7 @@ class RelPoseGNN(nn.Module):
         self.dropout_seed = 0x5EED
         self.keep_debug_activations = False      # tests: keep the saved activations of the last forward
         self.fused_grad_accumulation = False     # see attach_grad_bucket
+        self.tensor_core_heads = True            # seeded dropout fused into the last GEMMs + heads as GEMMs (see _StackFn)
         self.precision = "bf16"                  # or "fp32": split-bf16 arithmetic, inference only for now
 
     def attach_grad_bucket(self, bucket):
@@ -181,6 +208,18 @@ class RelPoseGNN(nn.Module):
         ent["b6n"] = torch.cat([self.fc_xyz.bias.data, self.fc_wpqr.bias.data]).contiguous()
         ent["w6e"] = torch.cat([self.fc_xyz_R.weight.data, self.fc_wpqr_R.weight.data]).contiguous()
         ent["b6e"] = torch.cat([self.fc_xyz_R.bias.data, self.fc_wpqr_R.bias.data]).contiguous()
+        # tensor-core heads (features dropped by the producing GEMM): W6 padded to 8 output rows, bias to 8, and the
+        # dgrad operand [D, 64] with W6[j, :] in columns j and 8 + j (hi / lo halves of dpose)
+        for tag in ("n", "e"):
+            if "w6%s_p" % tag not in ent:
+                ent["w6%s_p" % tag] = torch.zeros(8, D, dtype=BF16, device=device)
+                ent["b6%s_p" % tag] = torch.zeros(8, dtype=torch.float32, device=device)
+                ent["w6%sT" % tag] = torch.zeros(D, 64, dtype=BF16, device=device)
+            w6 = ent["w6" + tag]
+            ops.pack_weight(w6, ent["w6%s_p" % tag][:6])
+            ops.pack_weight(w6, ent["w6%sT" % tag][:, 0:6], transpose=True)
+            ops.pack_weight(w6, ent["w6%sT" % tag][:, 8:14], transpose=True)
+            ent["b6%s_p" % tag][:6].copy_(ent["b6" + tag])
         ent["versions"] = versions
         return ent
 

@@ -267,6 +267,20 @@ def head_fwd(feat, w6, b6, keep=None, seed=0, p_drop=0.0, feat_lo=None):
     return pose
 
 
+def head_bwd_tc(dpose, feat_d, bits, w6T_ext, scale, dw_t, dw_q, db_t, db_q, want_dfeat=True):
+    """Backward of the tensor-core pose heads (features dropped + rescaled by the producing GEMM); see rpg.h."""
+    lib = _lib.load()
+    rows, D = feat_d.shape
+    dev = feat_d.device
+    ws = torch.empty(lib.rpg_head_bwd_tc_ws_floats(D), dtype=torch.float32, device=dev)
+    dp16 = torch.empty(rows, 64, dtype=BF16, device=dev)
+    dfeat = torch.empty(rows, D, dtype=BF16, device=dev) if want_dfeat else None
+    check(lib.rpg_head_bwd_tc(dpose.data_ptr(), feat_d.data_ptr(), feat_d.stride(0), ptr(bits), rows, D, float(scale),
+                              w6T_ext.data_ptr(), dp16.data_ptr(), ptr(dfeat), D, dw_t.data_ptr(), dw_q.data_ptr(),
+                              db_t.data_ptr(), db_q.data_ptr(), ws.data_ptr(), _stream(feat_d)), "rpg_head_bwd_tc")
+    return dfeat
+
+
 def head_bwd(dpose, feat, w6, dw_t, dw_q, db_t, db_q, keep=None, seed=0, p_drop=0.0, mask_relu=True, want_dfeat=True,
              accumulate=True):
     """Backward of head_fwd; dw_t/db_t (translation head) and dw_q/db_q (rotation head) are accumulated in place."""

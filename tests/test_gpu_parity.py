@@ -645,7 +645,27 @@ def test_seeded_dropout_equals_explicit_masks_forward_and_backward():
 
     seed_used, pn0, pe0, gx0, g0 = run()
     _, pn1, pe1, gx1, g1 = run(explicit_seed=seed_used)
-    assert rel(pn0, pn1.double().cpu()) < 1e-6 and rel(pe0, pe1.double().cpu()) < 1e-6
-    assert rel(gx0, gx1.double().cpu()) < 1e-6
+    # The seeded path drops inside the producing GEMMs and runs the heads as bf16-weight tensor-core GEMMs, the explicit
+    # path uses the stand-alone fp32-weight head kernels: same masks, bf16-level differences in the head arithmetic.
+    assert rel(pn0, pn1.double().cpu()) < 5e-3 and rel(pe0, pe1.double().cpu()) < 5e-3
+    assert rel(gx0, gx1.double().cpu()) < 1e-2
     for k in g0:
-        assert rel(g0[k], g1[k].double().cpu()) < 1e-5, k
+        assert rel(g0[k], g1[k].double().cpu()) < 1e-2, k
+    # and with the tensor-core heads switched off the two paths agree to fp32 rounding
+    def run_plain(explicit_seed=None):
+        import relpose_gnn_b200.model as M
+        orig = M.RelPoseGNN.__init__
+        def patched(self, *a, **kw):
+            orig(self, *a, **kw)
+            self.tensor_core_heads = False
+        M.RelPoseGNN.__init__ = patched
+        try:
+            return run(explicit_seed)
+        finally:
+            M.RelPoseGNN.__init__ = orig
+    seed_used, pn2, pe2, gx2, g2 = run_plain()
+    _, pn3, pe3, gx3, g3 = run_plain(explicit_seed=seed_used)
+    assert rel(pn2, pn3.double().cpu()) < 1e-6 and rel(pe2, pe3.double().cpu()) < 1e-6
+    assert rel(gx2, gx3.double().cpu()) < 1e-6
+    for k in g2:
+        assert rel(g2[k], g3[k].double().cpu()) < 1e-5, k
