@@ -34,6 +34,7 @@ WORKLOADS = {
 }
 STRONG = {"infer_65536x9_strong", "train_2048x17_strong"}
 METRIC = "GNN graphs/sec fwd+bwd"
+_emit = print
 R_ROUNDS = 2
 
 
@@ -151,7 +152,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} graphs x {N} nodes per step, {mode}, fp32, torch CPU"},
             "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- our arm (B200)
@@ -334,7 +335,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_sample} graphs x {N} nodes, {mode}, fp32 torch CPU, median of 3 "
                                               f"({med * 1e3:.0f} ms per sample)"}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -351,10 +352,26 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-clocks", dest="clocks", action="store_false", help="(experiments) skip the nvidia-smi sampler")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON): native libraries that write to file descriptor 1 on their own (NCCL
+    # prints its version banner there) are pointed at stderr for the duration of the run.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(text):
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
 
 
 if __name__ == "__main__":
