@@ -330,6 +330,10 @@ int rpg_edge_gather(const rpg_bf16* pa, int lda, int which_a, const rpg_bf16* pb
 int rpg_scale_rows(const rpg_bf16* v, int ldv, int64_t rows, int D, const float* scale, int mod, rpg_bf16* out, int ldo,
                    rpg_stream_t stream);
 
+/* Evaluation error metrics (test.py:202-203, 262-265) over n pose pairs [n, 7] = (t, unit quaternion):
+ * t_err[i] = ||t_pred - t_gt||, q_err[i] = 2 acos(min(1, |<q_pred, q_gt>|)) in degrees (pose_utils.py:420-431). */
+int rpg_pose_errors(const float* pred7, const float* targ7, int64_t n, float* t_err, float* q_err, rpg_stream_t stream);
+
 /* Column sums (bias gradients): out[c] (+)= sum_r w[r % mod] * v[r, c]; deterministic; row_w may be NULL. */
 int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod,
                     float* out, int accumulate, float* scratch, rpg_stream_t stream);

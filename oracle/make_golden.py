@@ -269,8 +269,20 @@ def golden_eval_compose():
         out[f"case{case}_pose_s"] = pose_s
         out[f"case{case}_pred7"] = np.asarray(env["output"][0], dtype=np.float64)
         out[f"case{case}_targ7"] = np.asarray(env["target"], dtype=np.float64)      # all nodes; the reference keeps row 0
+    # error metrics of test.py:202-203, 262-265: ||t_pred - t_gt|| and pose_utils.quaternion_angular_error
+    rs = np.random.RandomState(77)
+    pred = rs.randn(24, 7)
+    targ = rs.randn(24, 7)
+    pred[:, 3:] /= np.linalg.norm(pred[:, 3:], axis=1, keepdims=True)
+    targ[:, 3:] /= np.linalg.norm(targ[:, 3:], axis=1, keepdims=True)
+    targ[0, 3:] = pred[0, 3:]                       # identical rotation -> 0 degrees (|d| clamps to 1)
+    targ[1, 3:] = -pred[1, 3:]                      # antipodal quaternion = same rotation
+    out["err_pred"] = pred
+    out["err_targ"] = targ
+    out["err_t"] = np.asarray([np.linalg.norm(p - t) for p, t in zip(pred[:, :3], targ[:, :3])])
+    out["err_q"] = np.asarray([pose_utils.quaternion_angular_error(p, t) for p, t in zip(pred[:, 3:], targ[:, 3:])])
     np.savez(os.path.join(OUT, "eval_compose.npz"), **out)
-    print("eval_compose: cases", len(out) // 7)
+    print("eval_compose: cases", sum(k.endswith("_meta") for k in out))
 
 
 def main():

@@ -264,6 +264,15 @@ def compose_query_pose(pose_edges, poses_abs, edge_index, ref_node=0):
     return np.concatenate([out[:3].numpy(), qexp(out[3:].numpy())])
 
 
+def pose_errors(pred7, targ7):
+    """test.py:202-203, 262-265: translation error ||t_pred - t_gt|| and pose_utils.quaternion_angular_error
+    (pose_utils.py:420-431: 2 acos(min(1, |<q1, q2>|)) in degrees) per row of [*, 7] (t, q) poses."""
+    pred7, targ7 = np.asarray(pred7, dtype=np.float64), np.asarray(targ7, dtype=np.float64)
+    t_err = np.linalg.norm(pred7[:, :3] - targ7[:, :3], axis=1)
+    d = np.minimum(1.0, np.abs((pred7[:, 3:] * targ7[:, 3:]).sum(1)))
+    return t_err, 2.0 * np.arccos(d) * 180.0 / np.pi
+
+
 def compose_eval_batch(pose_edges, poses_abs, template, n_graphs, n_nodes, ref_node=0, pose_m=None, pose_s=None):
     """test.py:227-243 for a batch of graphs sharing one edge template (the reference evaluates one graph at a time):
     per graph, the `ref_node`-th template edge into node 0 gives  abs(query) = target[src] - RP_pred;  translations are

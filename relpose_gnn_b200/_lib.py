@@ -125,6 +125,7 @@ SIGNATURES = {
     "rpg_reduce_splits_batch": (I, [P, P]),
     "rpg_upload_words": (I, [P, P, I64, P]),
     "rpg_qexp": (I, [P, I64, P, P]),
+    "rpg_pose_errors": (I, [P, P, I64, P, P, P]),
     "rpg_knn_graph": (I, [P, I, I, I, I, I, P, P]),
     "rpg_head_bwd_tc_ws_floats": (I64, [I]),
     "rpg_pack_dpose": (I, [P, I64, P, C.c_float, P, P]),

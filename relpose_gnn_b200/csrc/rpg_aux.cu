@@ -1044,6 +1044,25 @@ __global__ void pack_dpose_kernel(const float* __restrict__ dpose, long long row
     }
 }
 
+// Evaluation error metrics (test.py:202-203, 262-265): translation error ||t_pred - t_gt|| and the quaternion angular
+// error 2 acos(min(1, |<q1, q2>|)) in degrees (pose_utils.py:420-431), one thread per pose pair, double arithmetic.
+__global__ void pose_errors_kernel(const float* __restrict__ pred7, const float* __restrict__ targ7, long long n,
+                                   float* __restrict__ t_err, float* __restrict__ q_err) {
+    pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float* p = pred7 + i * 7;
+        const float* t = targ7 + i * 7;
+        double st = 0.0, d = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const double v = (double)p[j] - (double)t[j]; st += v * v; }
+#pragma unroll
+        for (int j = 3; j < 7; ++j) d += (double)p[j] * (double)t[j];
+        d = fmin(1.0, fabs(d));
+        t_err[i] = (float)sqrt(st);
+        q_err[i] = (float)(2.0 * acos(d) * 180.0 / 3.14159265358979323846);
+    }
+}
+
 // Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
 // never queue behind a large host->device copy of another stream.
 constexpr int UPLOAD_WORDS = 2032;
@@ -1528,6 +1547,12 @@ int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* 
     launch_pdl(knn_graph_kernel, dim3(G), dim3(256), 0, as_stream(stream), x, ldx, N, D, k,
                reinterpret_cast<long long*>(edge_index), Et);
     return check_launch("knn_graph_kernel");
+}
+
+int rpg_pose_errors(const float* pred7, const float* targ7, int64_t n, float* t_err, float* q_err, rpg_stream_t stream) {
+    if (!pred7 || !targ7 || !t_err || !q_err || n <= 0) return set_error(RPG_E_ARG, "pose_errors: bad arguments");
+    launch_pdl(pose_errors_kernel, dim3(grid_for(n, 128)), dim3(128), 0, as_stream(stream), pred7, targ7, n, t_err, q_err);
+    return check_launch("pose_errors_kernel");
 }
 
 int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream) {

@@ -41,3 +41,29 @@ def compose_query_pose(pred_edges, poses_abs, edge_index, ref_node=0, pose_m=Non
     check(_lib.load().rpg_eval_compose(pred_edges.data_ptr(), poses_abs.data_ptr(), g.byref(), ref_k, m, s,
                                        out_p.data_ptr(), out_t.data_ptr(), _stream(pred_edges)), "rpg_eval_compose")
     return out_p, out_t
+
+
+def pose_errors(pred7, targ7):
+    """Per-pose translation error (same unit as t) and rotation error in degrees of [n, 7] = (t, unit quaternion) poses:
+    the reference's `t_criterion` / `quaternion_angular_error` (test.py:202-203; pose_utils.py:420-431).  CUDA tensors."""
+    if not pred7.is_cuda or not targ7.is_cuda:
+        raise ValueError("relpose_gnn_b200.pose_errors needs CUDA tensors")
+    pred7, targ7 = pred7.float().contiguous(), targ7.float().contiguous()
+    if pred7.shape != targ7.shape or pred7.dim() != 2 or pred7.size(1) != 7:
+        raise ValueError("pose_errors expects two [n, 7] tensors")
+    t_err = torch.empty(pred7.size(0), dtype=torch.float32, device=pred7.device)
+    q_err = torch.empty_like(t_err)
+    check(_lib.load().rpg_pose_errors(pred7.data_ptr(), targ7.data_ptr(), pred7.size(0), t_err.data_ptr(), q_err.data_ptr(),
+                                      _stream(pred7)), "rpg_pose_errors")
+    return t_err, q_err
+
+
+def save_poses(pred_poses, rel_paths, p_output, target_poses):
+    """The reference's result file (test.py:38-42): an .npz with rel_path, abs_t, abs_q, targ_t, targ_q.
+    pred_poses / target_poses: [n, 7] tensors or arrays."""
+    pred = pred_poses.detach().cpu().numpy() if torch.is_tensor(pred_poses) else np.asarray(pred_poses)
+    targ = target_poses.detach().cpu().numpy() if torch.is_tensor(target_poses) else np.asarray(target_poses)
+    if len(rel_paths) != len(pred):
+        raise ValueError(f"len(rel_paths): {len(rel_paths)} != {len(pred)} len(pred_poses)")
+    np.savez(p_output, rel_path=[str(p) for p in rel_paths], abs_t=pred[:, :3], abs_q=pred[:, 3:], targ_t=targ[:, :3],
+             targ_q=targ[:, 3:])

@@ -429,6 +429,10 @@ def test_qexp_and_eval_composition_against_reference_fixtures():
         assert np.allclose(pred.cpu().numpy(), po, rtol=0, atol=2e-6) and np.allclose(targ.cpu().numpy(), to, rtol=0, atol=2e-6)
     with pytest.raises(ValueError):
         rpg.compose_query_pose(pe.to(dev()), pa.to(dev()), ei.to(dev()), into0)
+    # error metrics of the evaluation loop (test.py:202-203, 262-265) against the reference functions' own numbers
+    t_err, q_err = rpg.pose_errors(torch.from_numpy(ec["err_pred"]).to(dev()), torch.from_numpy(ec["err_targ"]).to(dev()))
+    assert np.allclose(t_err.cpu().numpy(), ec["err_t"], rtol=1e-6, atol=1e-6)
+    assert np.allclose(q_err.cpu().numpy(), ec["err_q"], rtol=1e-5, atol=0.1)       # acos near 1: fp32 inputs => ~0.05 deg floor
 
 
 # ------------------------------------------------------------------ sibling layers

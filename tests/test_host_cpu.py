@@ -167,3 +167,15 @@ def test_knn_graph_api():
     assert ei.tolist() == [[1, 2, 0, 2, 1, 0, 2, 1], [0, 0, 1, 1, 2, 2, 3, 3]]
     with pytest.raises(ValueError):
         rpg.knn_graph(torch.zeros(8, 64), 2, num_nodes_per_graph=4)
+
+
+def test_save_poses_writes_the_reference_npz_layout(tmp_path):
+    """test.py:38-42: keys rel_path, abs_t, abs_q, targ_t, targ_q."""
+    pred, targ = np.arange(14.0).reshape(2, 7), np.arange(14.0, 28.0).reshape(2, 7)
+    out = tmp_path / "res.npz"
+    rpg.save_poses(torch.from_numpy(pred), ["a/0.png", "a/1.png"], out, targ)
+    z = np.load(out)
+    assert sorted(z.files) == ["abs_q", "abs_t", "rel_path", "targ_q", "targ_t"]
+    assert np.array_equal(z["abs_t"], pred[:, :3]) and np.array_equal(z["targ_q"], targ[:, 3:])
+    with pytest.raises(ValueError):
+        rpg.save_poses(pred, ["only one"], out, targ)

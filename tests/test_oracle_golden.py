@@ -84,6 +84,13 @@ def test_eval_composition_matches_reference():
         assert np.allclose(targ[0], fx[f"case{case}_targ7"][0], rtol=0, atol=2e-6)
 
 
+def test_pose_errors_match_reference():
+    fx = np.load(os.path.join(G, "eval_compose.npz"))
+    t_err, q_err = R.pose_errors(fx["err_pred"], fx["err_targ"])
+    assert np.allclose(t_err, fx["err_t"], atol=1e-12) and np.allclose(q_err, fx["err_q"], atol=1e-9)
+    assert q_err[0] < 1e-5 and q_err[1] < 1e-5
+
+
 def test_qexp_matches_reference():
     fx = np.load(os.path.join(G, "qexp.npz"))
     assert np.allclose(R.qexp(fx["v"]), fx["q"], atol=1e-14)
