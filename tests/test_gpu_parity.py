@@ -673,3 +673,54 @@ def test_seeded_dropout_equals_explicit_masks_forward_and_backward():
     assert rel(gx2, gx3.double().cpu()) < 1e-6
     for k in g2:
         assert rel(g2[k], g3[k].double().cpu()) < 1e-5, k
+
+
+def _full_step(model, crit, x, ei, poses):
+    for p in list(model.parameters()) + list(crit.parameters()):
+        p.grad = None
+    pn, pe, _ = model(x, ei)
+    loss, _, _ = crit(pe, poses, ei)
+    loss.backward()
+    return loss.detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+
+
+def test_training_step_is_bitwise_deterministic_at_full_size():
+    """No atomics anywhere (fixed-order segment sums, split-R folds, head reductions): two runs of the BASELINE-size
+    training step (4096 graphs x 9 nodes, D = 512, edge dropout, seeded feature dropout) give identical bits."""
+    D, N, Gn = 512, 9, 4096
+    torch.manual_seed(0)
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.5).to(dev())
+    crit = rpg.PoseNetCriterion(0.0, -2.0).to(dev())
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(Gn * N, D, generator=gen).to(dev()).bfloat16()
+    poses = (0.1 * torch.randn(Gn * N, 6, generator=gen)).to(dev())
+    keep = G.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(3))
+    ei = G.GraphBatch.fully_connected(Gn, N, dev(), keep).edge_index()
+    model.dropout_seed = 99
+    l0, g0 = _full_step(model, crit, x, ei, poses)
+    model.dropout_seed = 99
+    l1, g1 = _full_step(model, crit, x, ei, poses)
+    assert torch.equal(l0, l1) and torch.equal(g0, g1)
+    assert torch.isfinite(g0).all() and g0.abs().sum() > 0
+
+
+def test_full_size_batch_equals_mean_of_its_halves():
+    """Graphs are independent and the loss is a mean over edges: loss and every gradient of the 4096-graph batch equal
+    the average over its two 2048-graph halves (size-independent property at the BASELINE size; droprate 0 because the
+    seeded dropout pattern is indexed by the global row)."""
+    D, N, Gn = 512, 9, 4096
+    torch.manual_seed(0)
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.0).to(dev())
+    crit = rpg.PoseNetCriterion(0.0, -2.0).to(dev())
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(Gn * N, D, generator=gen).to(dev()).bfloat16()
+    poses = (0.1 * torch.randn(Gn * N, 6, generator=gen)).to(dev())
+    keep = G.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(5))
+    ei = G.GraphBatch.fully_connected(Gn, N, dev(), keep).edge_index()
+    ei_h = G.GraphBatch.fully_connected(Gn // 2, N, dev(), keep).edge_index()
+    l, g = _full_step(model, crit, x, ei, poses)
+    h = Gn // 2 * N
+    la, ga = _full_step(model, crit, x[:h].contiguous(), ei_h, poses[:h].contiguous())
+    lb, gb = _full_step(model, crit, x[h:].contiguous(), ei_h, poses[h:].contiguous())
+    assert abs(l.item() - 0.5 * (la.item() + lb.item())) < 1e-5 * max(1.0, abs(l.item()))
+    assert rel(g, (0.5 * (ga + gb)).double().cpu()) < 2e-3          # fp32 accumulation order differs between the splits
