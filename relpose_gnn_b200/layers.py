@@ -253,9 +253,12 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
          "y": new(Et, cp, zero=(cp != c)),
          "ybar": new(Nt, cp), "mbar": new(Nt, D), "a": new(Nt, D)}
     u8 = torch.uint8
-    a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8)})
+    if for_backward:                     # ReLU patterns are only consumed by the backward epilogues
+        a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8)})
     if not v1:
-        a.update({"h3": new(Nt, D), "out": new(Nt, D), "h3_bits": new(Nt, D // 8, u8)})
+        a.update({"h3": new(Nt, D), "out": new(Nt, D)})
+        if for_backward:
+            a["h3_bits"] = new(Nt, D // 8, u8)
     if for_backward:
         a["att_aux"] = new(Et, 4 * c, torch.float32)           # attention row statistics: the backward skips a sweep
     if want_relu_copies:
@@ -263,8 +266,9 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
             raise ValueError("ReLU copies are a feature of the simpleConvEdge_upt stack path")
         a["e_new_relu"] = new(Et, D)
         a["out_relu"] = new(Nt, D)
-        a["e_new_bits"] = new(Et, D // 8, u8)
-        a["out_bits"] = new(Nt, D // 8, u8)
+        if for_backward:
+            a["e_new_bits"] = new(Et, D // 8, u8)
+            a["out_bits"] = new(Nt, D // 8, u8)
     if x_bits is not None:
         a["x_bits"] = x_bits
     if e_bits is not None:

@@ -43,7 +43,7 @@ class _StackFn(torch.autograd.Function):
         pmm = arena.take(Nt, 2 * D)
         ops.gemm_nt(xb, sw["Wmm"], out=pmm)
         e = arena.take(Et, D)
-        e_bits = arena.take(Et, D // 8, torch.uint8)
+        e_bits = arena.take(Et, D // 8, torch.uint8) if any(ctx.needs_input_grad) else None   # patterns: backward only
         ops.edge_init_fwd(pmm, model.proj_edge.bias.data, graph, D, e, e_bits)
         acts = []
         xin, x_bits = xb, None
@@ -57,7 +57,7 @@ class _StackFn(torch.autograd.Function):
                                   for_backward=any(ctx.needs_input_grad),
                                   drop=(p_drop, seed, seed + 1) if (fused and r == R - 1) else None)
             acts.append(a)
-            xin, e, x_bits, e_bits = a["out_relu"], a["e_new_relu"], a["out_bits"], a["e_new_bits"]
+            xin, e, x_bits, e_bits = a["out_relu"], a["e_new_relu"], a.get("out_bits"), a.get("e_new_bits")
         if fused:
             pose8_n = torch.empty(Nt, 8, dtype=torch.float32, device=dev)
             pose8_e = torch.empty(Et, 8, dtype=torch.float32, device=dev)
