@@ -1076,8 +1076,9 @@ upload_words_kernel(const __grid_constant__ UploadWords p, int32_t* __restrict__
 // Batched form: blockIdx.y picks the descriptor; always accumulating.  A block covers 32 consecutive elements with 8
 // split phases (phase q sums splits q, q + 8, ...; the phases are folded through shared memory in a fixed order), so
 // small outputs with many splits do not serialise on one thread.  Deterministic.
+// (small outputs; large ones use reduce_splits_batch_kernel below: one thread per element, splits in sequence)
 __global__ void __launch_bounds__(256)
-reduce_splits_batch_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
+reduce_splits_batch_phased_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
     pdl_prologue();
     __shared__ float red[8][32];
     const rpg_reduce_desc_t& d = batch.d[blockIdx.y];
@@ -1105,6 +1106,25 @@ reduce_splits_batch_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
             *o += s;
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_splits_batch_kernel(const __grid_constant__ rpg_reduce_batch_t batch) {
+    pdl_prologue();
+    const rpg_reduce_desc_t& d = batch.d[blockIdx.y];
+    const long long n = (long long)d.rows * d.cols;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const int r = (int)(i / d.cols), c = (int)(i - (long long)r * d.cols);
+        float s0 = 0.f, s1 = 0.f;
+        int b = 0;
+        for (; b + 1 < d.splits; b += 2) {
+            s0 += d.part[(size_t)b * d.stride + i];
+            s1 += d.part[(size_t)(b + 1) * d.stride + i];
+        }
+        if (b < d.splits) s0 += d.part[(size_t)b * d.stride + i];
+        float* o = d.out + (size_t)r * d.ldo + c;
+        *o += s0 + s1;
     }
 }
 
@@ -1595,7 +1615,12 @@ int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream
             return set_error(RPG_E_ARG, "reduce_splits_batch: bad descriptor");
         most = std::max(most, (long long)d.rows * d.cols);
     }
-    dim3 grid((unsigned)grid_for(most, 32, 8192), (unsigned)batch->n);
+    if (most <= 16384) {      // few elements, many splits (head gradients): spread the splits over 8 phases per element
+        dim3 grid((unsigned)grid_for(most, 32, 8192), (unsigned)batch->n);
+        launch_pdl(reduce_splits_batch_phased_kernel, dim3(grid), dim3(256), 0, as_stream(stream), *batch);
+        return check_launch("reduce_splits_batch_phased_kernel");
+    }
+    dim3 grid((unsigned)grid_for(most, 256, 1024), (unsigned)batch->n);
     launch_pdl(reduce_splits_batch_kernel, dim3(grid), dim3(256), 0, as_stream(stream), *batch);
     return check_launch("reduce_splits_batch_kernel");
 }
