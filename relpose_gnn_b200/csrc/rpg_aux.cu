@@ -1201,7 +1201,7 @@ __global__ void pose_loss_final_kernel(const float* __restrict__ partial, int nb
 // ------------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix (bias gradients): stage 1 per row-slab, stage 2 over slabs.
 // ------------------------------------------------------------------------------------------------
-constexpr int COLSUM_ROWS = 256;
+constexpr int COLSUM_ROWS = 64;      // short slabs: enough blocks to fill the machine at node-level row counts
 constexpr int COLSUM_THREADS = 256;
 // A block owns COLSUM_ROWS rows and all columns: thread = (column group of 8, row phase); phases are folded in smem.
 __global__ void __launch_bounds__(COLSUM_THREADS)
@@ -1219,7 +1219,7 @@ colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int co
         for (long long r = r0 + my_ph; r < r1; r += phases) {
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(v + r * ldv + my_cg * 8)), f);
-            const float wgt = row_w ? __ldg(row_w + (r % row_w_mod)) : 1.f;
+            const float wgt = row_w ? __ldg(row_w + (int)((unsigned long long)r % (unsigned)row_w_mod)) : 1.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] = fmaf(wgt, f[q], acc[q]);
         }
@@ -1478,13 +1478,13 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     return check_launch("head_bwd_reduce_kernel");
 }
 
-int64_t rpg_pose_loss_ws_floats(int64_t Et) { return 2 * (int64_t)grid_for(Et, LOSS_THREADS, 1024); }
+int64_t rpg_pose_loss_ws_floats(int64_t Et) { return 2 * (int64_t)grid_for(Et, LOSS_THREADS, 296); }
 
 static int pose_loss_launch(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* grad_scale,
                             const float* sax, const float* saq,
                             float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream) {
     if (!pred || !poses || !graph || !sums || !ws || Et <= 0) return set_error(RPG_E_ARG, "pose_loss: bad arguments");
-    const int blocks = grid_for(Et, LOSS_THREADS, 1024);
+    const int blocks = grid_for(Et, LOSS_THREADS, 296);
     cudaStream_t s = as_stream(stream);
     launch_pdl(pose_loss_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, s, pred, poses, graph->src, graph->dst, Et, graph->N, graph->Ep, grad_scale,
                                                      sax, saq, target, dpred, ws);
