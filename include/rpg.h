@@ -318,6 +318,13 @@ int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream);
 int rpg_eval_compose(const float* pred_edges, const float* poses, const rpg_graph_t* graph, int ref_k,
                      const float* pose_m, const float* pose_s, float* out_pred, float* out_targ, rpg_stream_t stream);
 
+/* Train-time edge dropout applied to a per-edge tensor (train.py:238-247: the tiled mask indexes data.edge_attr, and
+ * -- documented intent -- data.edge_index): keeps the rows of the surviving template slots of every graph,
+ *   out[g * Ep_kept + j, :] = in[g * Ep_full + kept_idx[j], :]     rows of row_bytes bytes (multiple of 4).
+ * kept_idx: device int32 [Ep_kept], ascending slot indices of the kept directed edges. */
+int rpg_edge_mask_apply(const void* in, int64_t G, int Ep_full, int Ep_kept, const int32_t* kept_idx, int row_bytes,
+                        void* out, rpg_stream_t stream);
+
 /* Per-edge gather of node rows through the template (simpleConv, my_gnn_layer.py:394-412: its first Linear acts on
  * cat[x_i, x_j] only, so it factors into two per-node products and this gather):
  *   out[e] = act(pa[node_a(e)] + pb[node_b(e)] + bias) * bit(e),   which_x: 0 = source, 1 = destination of edge e;

@@ -131,6 +131,7 @@ SIGNATURES = {
     "rpg_pack_dpose": (I, [P, I64, P, C.c_float, P, P]),
     "rpg_head_bwd_tc": (I, [P, P, I, P, I64, I, C.c_float, P, P, P, I, P, P, P, P, P, P]),
     "rpg_scale_rows": (I, [P, I, I64, I, P, I, P, I, P]),
+    "rpg_edge_mask_apply": (I, [P, I64, I, I, P, I, P, P]),
     "rpg_edge_gather": (I, [P, I, I, P, I, I, P, C.POINTER(Graph), I, I, P, P, I, P, P]),
     "rpg_eval_compose": (I, [P, P, C.POINTER(Graph), I, P, P, P, P, P]),
     "rpg_layer_bwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs),

@@ -496,6 +496,21 @@ __global__ void edge_init_fwd_kernel(const bf16* __restrict__ pmm, int ldp, cons
     }
 }
 
+// Edge-dropout mask applied to a per-edge tensor (train.py:242-247 masks data.edge_attr with the tiled mask): rows of
+// the kept template slots, graph by graph:  out[g * Ep_kept + j, :] = in[g * Ep_full + kept_idx[j], :]   (any 4-byte type)
+__global__ void edge_rows_select_kernel(const uint32_t* __restrict__ in, long long G, int Ep_full, int Ep_kept,
+                                        const int* __restrict__ kept_idx, int words, uint32_t* __restrict__ out) {
+    pdl_prologue();
+    const long long total = G * Ep_kept * (long long)words;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / words;
+        const int w = (int)(t - row * words);
+        const long long g = row / Ep_kept;
+        const int j = (int)(row - g * Ep_kept);
+        out[t] = in[(g * Ep_full + __ldg(kept_idx + j)) * words + w];
+    }
+}
+
 // General per-edge gather of node rows through the template (sibling layers without an edge-feature GEMM):
 //   out[e] = act( pa[node_a(e)] + pb[node_b(e)] + bias ) * bit(e)      node_x = source (0) or destination (1)
 // pb, bias, mask_bits optional; act = ReLU or identity; optional pattern output.
@@ -1542,6 +1557,17 @@ int rpg_edge_gather(const rpg_bf16* pa, int lda, int which_a, const rpg_bf16* pb
                graph->src, graph->dst, Et, graph->N, graph->Ep, D, relu, mask_bits, reinterpret_cast<bf16*>(out), ldo,
                out_bits);
     return check_launch("edge_gather_kernel");
+}
+
+int rpg_edge_mask_apply(const void* in, int64_t G, int Ep_full, int Ep_kept, const int32_t* kept_idx, int row_bytes, void* out,
+                        rpg_stream_t stream) {
+    if (!in || !out || !kept_idx || G <= 0 || Ep_full <= 0 || Ep_kept <= 0 || Ep_kept > Ep_full || row_bytes <= 0 || row_bytes % 4)
+        return set_error(RPG_E_ARG, "edge_mask_apply: bad arguments (rows must be a multiple of 4 bytes)");
+    const int words = row_bytes / 4;
+    launch_pdl(edge_rows_select_kernel, dim3(grid_for(G * Ep_kept * (long long)words, 256)), dim3(256), 0, as_stream(stream),
+               reinterpret_cast<const uint32_t*>(in), (long long)G, Ep_full, Ep_kept, kept_idx, words,
+               reinterpret_cast<uint32_t*>(out));
+    return check_launch("edge_rows_select_kernel");
 }
 
 int rpg_scale_rows(const rpg_bf16* v, int ldv, int64_t rows, int D, const float* scale, int mod, rpg_bf16* out, int ldo,

@@ -199,6 +199,28 @@ def attach(edge_index, graph):
     return edge_index
 
 
+def apply_edge_mask(t, keep_undirected, n_graphs):
+    """train.py:242-247: `t[surviving_edges]` for a per-edge tensor t [G*E, ...] (edge labels, edge features) with the
+    batch-shared undirected keep mask (edge_dropout_keep); both directions of an edge follow the same bit.  CUDA tensor,
+    element size 4 bytes or rows that are a multiple of 4 bytes."""
+    if not t.is_cuda:
+        raise ValueError("apply_edge_mask needs a CUDA tensor: the sm_100a kernels are the only implementation")
+    keep = np.asarray(keep_undirected, dtype=bool)
+    keep2 = np.concatenate([keep, keep])
+    Ep_full = keep2.size
+    if t.size(0) != n_graphs * Ep_full:
+        raise ValueError("apply_edge_mask: tensor rows must equal graphs x directed edges of the full template")
+    idx = np.flatnonzero(keep2).astype(np.int32)
+    tc = t.contiguous()
+    row_bytes = tc[0].numel() * tc.element_size()
+    out = torch.empty((n_graphs * idx.size,) + tuple(tc.shape[1:]), dtype=tc.dtype, device=tc.device)
+    idx_dev = _uploader.upload(idx, tc.device)
+    _lib.check(_lib.load().rpg_edge_mask_apply(tc.data_ptr(), n_graphs, Ep_full, int(idx.size), idx_dev.data_ptr(), row_bytes,
+                                               out.data_ptr(), C.c_void_p(torch.cuda.current_stream(tc.device).cuda_stream)),
+               "rpg_edge_mask_apply")
+    return out
+
+
 def knn_graph(x, k, batch=None, loop=False, num_nodes_per_graph=None):
     """torch_cluster.knn_graph as the reference calls it (posenet.py:1043-1050: `knn_graph(x, k, batch=data.batch,
     loop=False)`) for batches of equally sized graphs: int64 edge_index [2, G*N*k], edges (neighbour -> centre) grouped

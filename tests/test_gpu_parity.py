@@ -724,3 +724,29 @@ def test_full_size_batch_equals_mean_of_its_halves():
     lb, gb = _full_step(model, crit, x[h:].contiguous(), ei_h, poses[h:].contiguous())
     assert abs(l.item() - 0.5 * (la.item() + lb.item())) < 1e-5 * max(1.0, abs(l.item()))
     assert rel(g, (0.5 * (ga + gb)).double().cpu()) < 2e-3          # fp32 accumulation order differs between the splits
+
+
+def test_edge_mask_apply_matches_reference_indexing_and_config_A():
+    """(1) train.py:242-247: per-edge tensors indexed by the tiled keep mask; (2) BASELINE config A (one graph, 9 nodes,
+    72 edges, D = 512) through the whole stack against the oracle."""
+    N, Gn = 9, 13
+    keep = R.edge_dropout_keep(N * (N - 1) // 2, np.random.RandomState(11).random_sample(N * (N - 1) // 2))
+    tiled = torch.from_numpy(np.tile(np.concatenate([keep, keep]), Gn))
+    gen = torch.Generator().manual_seed(4)
+    for t in (torch.randn(Gn * N * (N - 1), 6, generator=gen), torch.randn(Gn * N * (N - 1), 64, generator=gen).bfloat16(),
+              torch.randint(0, 1000, (Gn * N * (N - 1), 2), generator=gen, dtype=torch.int64)):
+        got = rpg.apply_edge_mask(t.to(dev()), keep, Gn)
+        assert torch.equal(got.cpu(), t[tiled])
+    # the compacted edge_index is what GraphBatch builds from the same mask
+    ei_full = R.batched_edge_index(R.fc_edge_index(N), Gn, N)
+    ei_kept = rpg.apply_edge_mask(ei_full.t().contiguous().to(dev()), keep, Gn).t().contiguous()
+    assert torch.equal(ei_kept.cpu(), R.batched_edge_index(R.apply_edge_dropout(R.fc_edge_index(N), keep), Gn, N))
+    # config A
+    D = 512
+    case = R.synth_stack_case(D, 9, 1, 4711, droprate=0.0)
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.0).to(dev())
+    model.load_state_dict({k: v.float() for k, v in case["params"].items()}, strict=False)
+    with torch.no_grad():
+        pn, pe, _ = model(case["x"].float().to(dev()), case["edge_index"].to(dev()))
+    pn_o, pe_o, _, _ = R.stack_forward(case["params"], case["x"], case["edge_index"], 2, 0.0)
+    assert tuple(pe.shape) == (72, 6) and rel(pn, pn_o) < TOL_BF16 and rel(pe, pe_o) < TOL_BF16
