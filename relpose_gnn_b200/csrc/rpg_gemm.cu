@@ -177,6 +177,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
         if (PAIR) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
         else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     }
+    if (warp == 2 && lane == 0) {          // the store-side descriptors too: the first TMA store of a tile must not miss
+        if (p.out) tma_prefetch_desc(&tmOut);
+        if (p.out_relu) tma_prefetch_desc(&tmOutRelu);
+        if (p.out_f32) tma_prefetch_desc(&tmOutF32);
+        if (RTMA) tma_prefetch_desc(&tm.resid);
+        if (MODE == 0 && p.n_gseg) { tma_prefetch_desc(&tm.ga[0]); tma_prefetch_desc(&tm.gb[0]); }
+    }
     tc_fence_before();
     if (CL == 1) __syncthreads(); else cluster_sync_all();   // peer barriers must be initialised before any remote arrive
     tc_fence_after();
