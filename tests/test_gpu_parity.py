@@ -82,7 +82,7 @@ def test_layer_against_reference_fixture(tag):
 
 @pytest.mark.parametrize("D,N,Gn,drop_edges", [(512, 9, 5, False), (512, 17, 3, False), (512, 8, 16, True),
                                                (256, 9, 33, True), (128, 3, 50, False), (1024, 8, 2, False),
-                                               (2048, 8, 2, True)])
+                                               (2048, 8, 2, True), (384, 9, 4, True), (640, 5, 6, False)])
 def test_layer_against_oracle(D, N, Gn, drop_edges):
     """Forward against the plain oracle; backward against the oracle with the kernel's activation pattern imposed.
     Inputs, weights and cotangents are bf16-representable so that only the kernel arithmetic is measured."""
