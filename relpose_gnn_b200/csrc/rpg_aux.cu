@@ -175,8 +175,10 @@ constexpr float LOG2E = 1.4426950408889634f;
 // is packed fp32x2 math (FFMA2/FADD2, sm_100+): a lane owns two rows (forward) or two columns (backward sweep 2) of the
 // c x c score matrix as one 64-bit register pair and the broadcast operand is a scalar, so a pair of exps costs
 // 5-7 issue slots and 3-5 FMA-pipe instructions against 16 MUFU cycles.  (Scalar FFMA issues every other cycle on this
-// part, which made the scalar form FMA-pipe bound.)  Tried and measured neutral: an FMA-pipe polynomial exp2 and the
-// packed ex2.approx.f16x2 form (ptxas lowers it to two scalar MUFU.EX2.F16).
+// part, which made the scalar form FMA-pipe bound.)  Tried and measured neutral or worse: moving a quarter of the exps
+// to an FMA-pipe polynomial (scalar form: neutral; packed Cody-Waite form with FFMA2: forward 205 -> 228 us, the clamp /
+// exponent-splice ALU work and issue slots cost more than the MUFU cycles they free) and the packed ex2.approx.f16x2 /
+// bf16x2 forms (ptxas lowers them to two scalar MUFU.EX2).
 // AUX: also store the per-row statistics [1/den | y | sum_j S_ij theta_j | sum_j S_ij g_j theta_j] (fp32 [Et, 4c]) that
 // let the backward skip its first sweep.
 __device__ __forceinline__ float2 ex2_pair(float2 a) { return make_float2(exp2f(a.x), exp2f(a.y)); }
