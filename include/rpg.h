@@ -95,6 +95,10 @@ typedef struct {
   const float* has_in;        /* [N] 1 if the node has incoming edges, else 0 (a mean over nothing is 0 [3p])   */
 } rpg_graph_t;
 
+/* The batched edge_index of the template (what PyG's Batch hands the model, train.py:24,132), on the device:
+ * edge_index [2, G*Ep] int64 with column g*Ep + k = (g*N + src[k], g*N + dst[k]). */
+int rpg_build_edge_index(const rpg_graph_t* graph, int64_t* edge_index, rpg_stream_t stream);
+
 /* Builds the one-hot selection tiles of rpg_graph_t.sel_src / sel_dst on the device from a template endpoint table
  * (src or dst): sel [patterns * 128, 64] bf16, div = gcd(128, Ep), patterns = Ep / div.  The caller checks first
  * that no 128-row block references more than 64 node rows.                                             */

@@ -1080,6 +1080,20 @@ __global__ void pose_errors_kernel(const float* __restrict__ pred7, const float*
     }
 }
 
+// PyG-style batched edge_index of G template copies (what torch_geometric's Batch produces, train.py:24,132):
+// ei[0, g*Ep + k] = g*N + src[k], ei[1, g*Ep + k] = g*N + dst[k].
+__global__ void build_edge_index_kernel(const int* __restrict__ tsrc, const int* __restrict__ tdst, long long G, int N, int Ep,
+                                        long long* __restrict__ ei) {
+    pdl_prologue();
+    const long long Et = G * Ep;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < Et; e += (long long)gridDim.x * blockDim.x) {
+        const long long g = e / Ep;
+        const int k = (int)(e - g * Ep);
+        ei[e] = g * N + __ldg(tsrc + k);
+        ei[Et + e] = g * N + __ldg(tdst + k);
+    }
+}
+
 // Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
 // never queue behind a large host->device copy of another stream.
 constexpr int UPLOAD_WORDS = 2032;
@@ -1586,6 +1600,14 @@ int rpg_pack_dpose(const float* dpose, int64_t rows, rpg_bf16* dp16, float scale
     launch_pdl(pack_dpose_kernel, dim3(grid_for(rows, 256)), dim3(256), 0, as_stream(stream), dpose, rows,
                reinterpret_cast<bf16*>(dp16), scale, scale_out);
     return check_launch("pack_dpose_kernel");
+}
+
+int rpg_build_edge_index(const rpg_graph_t* graph, int64_t* edge_index, rpg_stream_t stream) {
+    if (!graph || !edge_index || graph->G <= 0 || graph->Ep <= 0) return set_error(RPG_E_ARG, "build_edge_index: bad arguments");
+    const long long Et = (long long)graph->G * graph->Ep;
+    launch_pdl(build_edge_index_kernel, dim3(grid_for(Et, 256)), dim3(256), 0, as_stream(stream), graph->src, graph->dst,
+               (long long)graph->G, graph->N, graph->Ep, reinterpret_cast<long long*>(edge_index));
+    return check_launch("build_edge_index_kernel");
 }
 
 int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* edge_index, rpg_stream_t stream) {

@@ -176,9 +176,11 @@ class GraphBatch:
         """int64 [2, G*Ep] PyG-style batched edge_index, built on the device from the template tables."""
         if self.device.type != "cuda":
             return batched_edge_index(self.src_np, self.dst_np, self.G, self.N, self.device)
-        t = torch.stack([self._tables["src"], self._tables["dst"]]).long()
-        offs = torch.arange(self.G, dtype=torch.long, device=self.device) * self.N
-        return (t.unsqueeze(1) + offs.view(1, -1, 1)).reshape(2, -1)
+        ei = torch.empty(2, self.G * self.Ep, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.load().rpg_build_edge_index(self.byref(), ei.data_ptr(),
+                                                    C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                   "rpg_build_edge_index")
+        return ei
 
     def with_graphs(self, n_graphs):
         return GraphBatch(self.src_np, self.dst_np, n_graphs, self.N, self.device)

@@ -741,6 +741,8 @@ def test_edge_mask_apply_matches_reference_indexing_and_config_A():
     ei_full = R.batched_edge_index(R.fc_edge_index(N), Gn, N)
     ei_kept = rpg.apply_edge_mask(ei_full.t().contiguous().to(dev()), keep, Gn).t().contiguous()
     assert torch.equal(ei_kept.cpu(), R.batched_edge_index(R.apply_edge_dropout(R.fc_edge_index(N), keep), Gn, N))
+    # ... and what the device-side builder (rpg_build_edge_index) emits
+    assert torch.equal(G.GraphBatch.fully_connected(Gn, N, dev(), keep).edge_index(), ei_kept)
     # config A
     D = 512
     case = R.synth_stack_case(D, 9, 1, 4711, droprate=0.0)
