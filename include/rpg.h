@@ -302,9 +302,9 @@ int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* grap
 /* The same with the learned loss weights of PoseNetCriterion folded in (criterion.py:55-57; sax, saq: device
  * scalars): out7 = [sum_t, sum_q, loss, t_loss, q_loss, dloss/dsax, dloss/dsaq] with t_loss = sum_t / (3 Et),
  * loss = exp(-sax) t_loss + sax + exp(-saq) q_loss + saq; dpred = dloss/dpred.  No host round trip. */
-int rpg_pose_criterion(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et,
+int rpg_pose_criterion(const float* pred, int ld_pred, const float* poses, const rpg_graph_t* graph, int64_t Et,
                        const float* sax, const float* saq, float* target, float* out7, float* dpred, float* ws,
-                       rpg_stream_t stream);
+                       rpg_stream_t stream);   /* ld_pred: row pitch of pred in floats (>= 6; the tensor-core heads emit 8) */
 
 /* Dynamic kNN rewiring: torch_cluster.knn_graph(x, k, batch, loop=False) [3p, torch-cluster 1.5.9] as called at
  * posenet.py:1043-1050 for G graphs of N nodes each (2 <= N <= 64, k < N): edge_index [2, G*N*k] int64 with

@@ -117,7 +117,7 @@ SIGNATURES = {
     "rpg_head_bwd": (I, [P, P, I, I64, I, P, U64, F, P, I, P, I, P, P, P, P, I, P, P]),
     "rpg_pose_loss_ws_floats": (I64, [I64]),
     "rpg_pose_loss": (I, [P, P, C.POINTER(Graph), I64, P, P, P, P, P, P]),
-    "rpg_pose_criterion": (I, [P, P, C.POINTER(Graph), I64, P, P, P, P, P, P, P]),
+    "rpg_pose_criterion": (I, [P, I, P, C.POINTER(Graph), I64, P, P, P, P, P, P, P]),
     "rpg_colsum_bf16": (I, [P, I, I64, I, P, I, P, I, P, P]),
     "rpg_colsum_scratch_floats": (I64, [I64, I]),
     "rpg_layer_fwd": (I, [C.POINTER(LayerWeights), C.POINTER(Graph), C.POINTER(LayerActs), P]),

@@ -1167,7 +1167,7 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses, const int* __restrict__ tsrc,
                  const int* __restrict__ tdst, long long Et, int N, int Ep, const float* __restrict__ grad_scale,
                  const float* __restrict__ sax, const float* __restrict__ saq,
-                 float* __restrict__ target, float* __restrict__ dpred, float* __restrict__ partial) {
+                 float* __restrict__ target, float* __restrict__ dpred, float* __restrict__ partial, int ld_pred) {
     pdl_prologue();
     float st = 0.f, sq = 0.f;
     float gs_t = grad_scale ? grad_scale[0] : 1.f, gs_q = grad_scale ? grad_scale[1] : 1.f;
@@ -1183,7 +1183,7 @@ pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ poses
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             const float t = ps[j] - pd[j];
-            const float diff = pred[e * 6 + j] - t;
+            const float diff = pred[e * ld_pred + j] - t;
             if (target) target[e * 6 + j] = t;
             if (j < 3) st += fabsf(diff); else sq += fabsf(diff);
             if (dpred) dpred[e * 6 + j] = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * (j < 3 ? gs_t : gs_q);
@@ -1513,12 +1513,12 @@ int64_t rpg_pose_loss_ws_floats(int64_t Et) { return 2 * (int64_t)grid_for(Et, L
 
 static int pose_loss_launch(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* grad_scale,
                             const float* sax, const float* saq,
-                            float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream) {
-    if (!pred || !poses || !graph || !sums || !ws || Et <= 0) return set_error(RPG_E_ARG, "pose_loss: bad arguments");
+                            float* target, float* sums, float* dpred, float* ws, rpg_stream_t stream, int ld_pred = 6) {
+    if (!pred || !poses || !graph || !sums || !ws || Et <= 0 || ld_pred < 6) return set_error(RPG_E_ARG, "pose_loss: bad arguments");
     const int blocks = grid_for(Et, LOSS_THREADS, 296);
     cudaStream_t s = as_stream(stream);
     launch_pdl(pose_loss_kernel, dim3(blocks), dim3(LOSS_THREADS), 0, s, pred, poses, graph->src, graph->dst, Et, graph->N, graph->Ep, grad_scale,
-                                                     sax, saq, target, dpred, ws);
+                                                     sax, saq, target, dpred, ws, ld_pred);
     int rc = check_launch("pose_loss_kernel");
     if (rc) return rc;
     launch_pdl(pose_loss_final_kernel, dim3(1), dim3(32), 0, s, ws, blocks, sums, sax, saq, Et);
@@ -1530,10 +1530,10 @@ int rpg_pose_loss(const float* pred, const float* poses, const rpg_graph_t* grap
     return pose_loss_launch(pred, poses, graph, Et, grad_scale, nullptr, nullptr, target, sums, dpred, ws, stream);
 }
 
-int rpg_pose_criterion(const float* pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* sax,
+int rpg_pose_criterion(const float* pred, int ld_pred, const float* poses, const rpg_graph_t* graph, int64_t Et, const float* sax,
                        const float* saq, float* target, float* out7, float* dpred, float* ws, rpg_stream_t stream) {
     if (!sax || !saq) return set_error(RPG_E_ARG, "pose_criterion: sax/saq must be device pointers");
-    return pose_loss_launch(pred, poses, graph, Et, nullptr, sax, saq, target, out7, dpred, ws, stream);
+    return pose_loss_launch(pred, poses, graph, Et, nullptr, sax, saq, target, out7, dpred, ws, stream, ld_pred);
 }
 
 int64_t rpg_colsum_scratch_floats(int64_t rows, int cols) {

@@ -63,7 +63,7 @@ class _StackFn(torch.autograd.Function):
             pose8_e = torch.empty(Et, 8, dtype=torch.float32, device=dev)
             ops.gemm_nt(xin, sw["w6n_p"], bias=sw["b6n_p"], out_f32=pose8_n)
             ops.gemm_nt(e, sw["w6e_p"], bias=sw["b6e_p"], out_f32=pose8_e)
-            pose_n, pose_e = pose8_n[:, :6].contiguous(), pose8_e[:, :6].contiguous()
+            pose_n, pose_e = pose8_n[:, :6], pose8_e[:, :6]      # row pitch 8: rpg_pose_criterion takes the pitch
         else:
             pose_n = ops.head_fwd(xin, sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop)
             pose_e = ops.head_fwd(e, sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop)
@@ -308,7 +308,9 @@ class PoseNetCriterion(nn.Module):
 class _PoseLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, poses, graph, sax, saq):
-        pred = pred.float().contiguous()
+        if pred.dtype != torch.float32 or pred.stride(1) != 1:      # row-pitched fp32 views (tensor-core heads) pass through
+            pred = pred.float().contiguous()
+        ctx.set_materialize_grads(False)
         out7, dpred = ops.pose_criterion(pred, poses, graph, sax.detach().float().contiguous(),
                                          saq.detach().float().contiguous())
         ctx.save_for_backward(dpred, out7)
@@ -317,6 +319,8 @@ class _PoseLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_t, g_q):
         dpred, out7 = ctx.saved_tensors
+        if g_loss is None:                       # only the logged t_loss / q_loss were used
+            return None, None, None, None, None
         g = g_loss.reshape(())
         d_s = out7[5:7] * g
         return dpred * g, None, None, d_s[0:1], d_s[1:2]

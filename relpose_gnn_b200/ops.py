@@ -315,7 +315,7 @@ def pose_criterion(pred, poses, graph, sax, saq):
     ws = torch.empty(lib.rpg_pose_loss_ws_floats(Et), dtype=torch.float32, device=pred.device)
     out7 = torch.empty(7, dtype=torch.float32, device=pred.device)
     dpred = torch.empty(Et, 6, dtype=torch.float32, device=pred.device)
-    check(lib.rpg_pose_criterion(pred.data_ptr(), poses.data_ptr(), graph.byref(), Et, sax.data_ptr(), saq.data_ptr(), None,
+    check(lib.rpg_pose_criterion(pred.data_ptr(), pred.stride(0), poses.data_ptr(), graph.byref(), Et, sax.data_ptr(), saq.data_ptr(), None,
                                  out7.data_ptr(), dpred.data_ptr(), ws.data_ptr(), _stream(pred)), "rpg_pose_criterion")
     return out7, dpred
 
