@@ -95,6 +95,16 @@ typedef struct {
   const float* has_in;        /* [N] 1 if the node has incoming edges, else 0 (a mean over nothing is 0 [3p])   */
 } rpg_graph_t;
 
+/* Tables for a batch whose graphs have different edge sets of equal size Ep (dynamic kNN rewiring, posenet.py:1043-1050):
+ * graph g owns edge columns [g*Ep, (g+1)*Ep) of edge_index [2, G*Ep] and nodes [g*N, (g+1)*N).  Built on the device, no
+ * host round trip.  `tables`: rpg_per_graph_tables_words(G, N, Ep) int32 words laid out as
+ *   src | dst | in_ptr | in_idx | out_ptr | out_idx | min_ptr | min_idx | max_ptr | max_idx | inv_deg | deg | has_in
+ * (edge tables G*Ep words, ptr tables G*N + 1, node tables G*N; each rounded up to a multiple of 4 words), to be used as
+ * an rpg_graph_t with G = 1, N = G*N, Ep = G*Ep (global rows).  bad[0] (device int32) counts edges that leave their
+ * graph's node range. */
+int64_t rpg_per_graph_tables_words(int G, int N, int Ep);
+int rpg_per_graph_tables(const int64_t* edge_index, int G, int N, int Ep, int32_t* tables, int32_t* bad, rpg_stream_t stream);
+
 /* The batched edge_index of the template (what PyG's Batch hands the model, train.py:24,132), on the device:
  * edge_index [2, G*Ep] int64 with column g*Ep + k = (g*N + src[k], g*N + dst[k]). */
 int rpg_build_edge_index(const rpg_graph_t* graph, int64_t* edge_index, rpg_stream_t stream);

@@ -128,6 +128,8 @@ SIGNATURES = {
     "rpg_pose_errors": (I, [P, P, I64, P, P, P]),
     "rpg_knn_graph": (I, [P, I, I, I, I, I, P, P]),
     "rpg_build_edge_index": (I, [C.POINTER(Graph), P, P]),
+    "rpg_per_graph_tables_words": (I64, [I, I, I]),
+    "rpg_per_graph_tables": (I, [P, I, I, I, P, P, P]),
     "rpg_head_bwd_tc_ws_floats": (I64, [I]),
     "rpg_pack_dpose": (I, [P, I64, P, C.c_float, P, P]),
     "rpg_head_bwd_tc": (I, [P, P, I, P, I64, I, C.c_float, P, P, P, I, P, P, P, P, P, P]),

@@ -1094,6 +1094,54 @@ __global__ void build_edge_index_kernel(const int* __restrict__ tsrc, const int*
     }
 }
 
+// Tables of a batch whose graphs have DIFFERENT edge sets of equal size (kNN rewiring: every graph its own 4-NN graph):
+// graph g owns edge rows [g*Ep, (g+1)*Ep) and node rows [g*N, (g+1)*N).  The compute kernels see it as ONE graph of
+// G*N nodes and G*Ep edges (rpg_graph_t with G = 1), so the tables hold global rows; they are built here, one thread
+// per graph (counting sorts over <= a few hundred edges), without any host round trip.  bad[0] counts edges that leave
+// their graph's node range.
+__global__ void per_graph_tables_kernel(const long long* __restrict__ ei, int G, int N, int Ep, int* __restrict__ src,
+                                        int* __restrict__ dst, int* __restrict__ in_ptr, int* __restrict__ in_idx,
+                                        int* __restrict__ out_ptr, int* __restrict__ out_idx, int* __restrict__ min_ptr,
+                                        int* __restrict__ min_idx, int* __restrict__ max_ptr, int* __restrict__ max_idx,
+                                        float* __restrict__ inv_deg, float* __restrict__ deg, float* __restrict__ has_in,
+                                        int* __restrict__ bad) {
+    pdl_prologue();
+    const long long Et = (long long)G * Ep;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+        const long long e0 = (long long)g * Ep;
+        const int n0 = g * N;
+        int nbad = 0;
+        for (int k = 0; k < Ep; ++k) {
+            const long long s = ei[e0 + k], d = ei[Et + e0 + k];
+            if (s < n0 || s >= n0 + N || d < n0 || d >= n0 + N) ++nbad;
+            src[e0 + k] = (int)s;
+            dst[e0 + k] = (int)d;
+        }
+        if (nbad) { atomicAdd(bad, nbad); continue; }
+        // four CSRs keyed by destination / source / lower / upper endpoint (stable: edge order within a node)
+        for (int t = 0; t < 4; ++t) {
+            int* ptr = t == 0 ? in_ptr : t == 1 ? out_ptr : t == 2 ? min_ptr : max_ptr;
+            int* idx = t == 0 ? in_idx : t == 1 ? out_idx : t == 2 ? min_idx : max_idx;
+            int fill = (int)e0;
+            for (int n = 0; n < N; ++n) {
+                ptr[n0 + n] = fill;
+                for (int k = 0; k < Ep; ++k) {
+                    const int s = src[e0 + k], d = dst[e0 + k];
+                    const int key = t == 0 ? d : t == 1 ? s : t == 2 ? min(s, d) : max(s, d);
+                    if (key == n0 + n) idx[fill++] = (int)(e0 + k);
+                }
+                if (t == 0) {
+                    const int dg = fill - ptr[n0 + n];
+                    deg[n0 + n] = (float)dg;
+                    inv_deg[n0 + n] = 1.f / (float)max(dg, 1);
+                    has_in[n0 + n] = dg > 0 ? 1.f : 0.f;
+                }
+            }
+            if (g == G - 1) ptr[(long long)G * N] = (int)Et;
+        }
+    }
+}
+
 // Small host tables (graph templates) travel as KERNEL PARAMETERS: no staging buffer, no copy engine -- an upload can
 // never queue behind a large host->device copy of another stream.
 constexpr int UPLOAD_WORDS = 2032;
@@ -1600,6 +1648,39 @@ int rpg_pack_dpose(const float* dpose, int64_t rows, rpg_bf16* dp16, float scale
     launch_pdl(pack_dpose_kernel, dim3(grid_for(rows, 256)), dim3(256), 0, as_stream(stream), dpose, rows,
                reinterpret_cast<bf16*>(dp16), scale, scale_out);
     return check_launch("pack_dpose_kernel");
+}
+
+int rpg_per_graph_tables(const int64_t* edge_index, int G, int N, int Ep, int32_t* tables, int32_t* bad, rpg_stream_t stream) {
+    if (!edge_index || !tables || !bad || G <= 0 || N <= 0 || Ep <= 0 || (long long)G * Ep > 0x7fffffffLL || (long long)G * N > 0x7ffffff0LL)
+        return set_error(RPG_E_ARG, "per_graph_tables: bad arguments");
+    const long long Et = (long long)G * Ep, Nt = (long long)G * N;
+    // layout of `tables` (int32 words, every table 4-word aligned): see rpg_per_graph_tables_words()
+    auto al = [](long long v) { return (v + 3) / 4 * 4; };
+    int32_t* p = tables;
+    int32_t* src = p; p += al(Et);
+    int32_t* dst = p; p += al(Et);
+    int32_t* in_ptr = p; p += al(Nt + 1);
+    int32_t* in_idx = p; p += al(Et);
+    int32_t* out_ptr = p; p += al(Nt + 1);
+    int32_t* out_idx = p; p += al(Et);
+    int32_t* min_ptr = p; p += al(Nt + 1);
+    int32_t* min_idx = p; p += al(Et);
+    int32_t* max_ptr = p; p += al(Nt + 1);
+    int32_t* max_idx = p; p += al(Et);
+    float* inv_deg = reinterpret_cast<float*>(p); p += al(Nt);
+    float* deg = reinterpret_cast<float*>(p); p += al(Nt);
+    float* has_in = reinterpret_cast<float*>(p);
+    cudaMemsetAsync(bad, 0, sizeof(int32_t), as_stream(stream));
+    launch_pdl(per_graph_tables_kernel, dim3(grid_for(G, 64)), dim3(64), 0, as_stream(stream),
+               reinterpret_cast<const long long*>(edge_index), G, N, Ep, src, dst, in_ptr, in_idx, out_ptr, out_idx, min_ptr,
+               min_idx, max_ptr, max_idx, inv_deg, deg, has_in, bad);
+    return check_launch("per_graph_tables_kernel");
+}
+
+int64_t rpg_per_graph_tables_words(int G, int N, int Ep) {
+    const long long Et = (long long)G * Ep, Nt = (long long)G * N;
+    auto al = [](long long v) { return (v + 3) / 4 * 4; };
+    return 6 * al(Et) + 4 * al(Nt + 1) + 3 * al(Nt);
 }
 
 int rpg_build_edge_index(const rpg_graph_t* graph, int64_t* edge_index, rpg_stream_t stream) {

@@ -161,6 +161,50 @@ class GraphBatch:
                 out[name] = sel
         return out
 
+    @classmethod
+    def per_graph(cls, edge_index, n_graphs, n_nodes, check=False):
+        """Batch whose graphs have different edge sets of equal size (dynamic kNN rewiring, posenet.py:1043-1050): graph g
+        owns edge columns [g*Ep, (g+1)*Ep) and nodes [g*N, (g+1)*N).  The kernels see ONE graph of G*N nodes; its tables
+        are built on the device (rpg_per_graph_tables), so nothing synchronises unless `check` asks for the validation
+        result (edge endpoints inside their graph)."""
+        if not edge_index.is_cuda or edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise TypeError("edge_index must be a CUDA int64 tensor of shape [2, E]")
+        Et = edge_index.size(1)
+        if Et == 0 or Et % n_graphs:
+            raise ValueError("per-graph batches need the same number of edges in every graph")
+        Ep, dev = Et // n_graphs, edge_index.device
+        lib = _lib.load()
+        ei = edge_index.contiguous()
+        words = lib.rpg_per_graph_tables_words(n_graphs, n_nodes, Ep)
+        buf = torch.empty(words + 4, dtype=torch.int32, device=dev)
+        bad = buf[words:words + 1]
+        _lib.check(lib.rpg_per_graph_tables(ei.data_ptr(), n_graphs, n_nodes, Ep, buf.data_ptr(), bad.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "rpg_per_graph_tables")
+        if check and int(bad.item()):
+            raise ValueError(f"{int(bad.item())} edges connect nodes of different graphs")
+        self = cls.__new__(cls)
+        Nt = n_graphs * n_nodes
+        self.G, self.N, self.Ep, self.device = 1, Nt, Et, dev
+        self.src_np = self.dst_np = None
+        self._edge_index = ei
+        al = lambda v: (v + 3) // 4 * 4                                     # noqa: E731
+        tables, off = {"_buf": buf}, 0
+        for name, size, is_f in (("src", Et, 0), ("dst", Et, 0), ("in_ptr", Nt + 1, 0), ("in_idx", Et, 0),
+                                 ("out_ptr", Nt + 1, 0), ("out_idx", Et, 0), ("min_ptr", Nt + 1, 0), ("min_idx", Et, 0),
+                                 ("max_ptr", Nt + 1, 0), ("max_idx", Et, 0), ("inv_deg", Nt, 1), ("deg", Nt, 1),
+                                 ("has_in", Nt, 1)):
+            t = buf[off:off + size]
+            tables[name] = t.view(torch.float32) if is_f else t
+            off += al(size)
+        self._tables = tables
+        s = _lib.Graph()
+        s.G, s.N, s.Ep = 1, Nt, Et
+        for name, t in tables.items():
+            if name != "_buf":
+                setattr(s, name, t.data_ptr())
+        self.struct = s
+        return self
+
     @property
     def n_node_rows(self):
         return self.G * self.N
@@ -174,6 +218,8 @@ class GraphBatch:
 
     def edge_index(self):
         """int64 [2, G*Ep] PyG-style batched edge_index, built on the device from the template tables."""
+        if getattr(self, "_edge_index", None) is not None:
+            return self._edge_index
         if self.device.type != "cuda":
             return batched_edge_index(self.src_np, self.dst_np, self.G, self.N, self.device)
         ei = torch.empty(2, self.G * self.Ep, dtype=torch.int64, device=self.device)

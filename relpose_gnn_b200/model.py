@@ -248,8 +248,10 @@ class RelPoseGNN(nn.Module):
         graph = graph_mod.from_edge_index(edge_index, x.size(0))
         kk = self.knn if self.knn > 0 else k
         if kk is not None and kk > 0:
-            edge_index = graph_mod.knn_graph(x, kk, num_nodes_per_graph=graph.N)
-            graph = graph_mod.from_edge_index(edge_index, x.size(0))
+            n_graphs, n_nodes = graph.G, graph.N
+            edge_index = graph_mod.knn_graph(x, kk, num_nodes_per_graph=n_nodes)
+            graph = graph_mod.GraphBatch.per_graph(edge_index, n_graphs, n_nodes)    # tables built on the device
+            graph_mod.attach(edge_index, graph)
         drop = self._drop_args(keep_x, keep_e)
         if self.precision == "fp32":
             pose_n, pose_e = self._forward_fp32(x, graph, drop)

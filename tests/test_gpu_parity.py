@@ -752,3 +752,23 @@ def test_edge_mask_apply_matches_reference_indexing_and_config_A():
         pn, pe, _ = model(case["x"].float().to(dev()), case["edge_index"].to(dev()))
     pn_o, pe_o, _, _ = R.stack_forward(case["params"], case["x"], case["edge_index"], 2, 0.0)
     assert tuple(pe.shape) == (72, 6) and rel(pn, pn_o) < TOL_BF16 and rel(pe, pe_o) < TOL_BF16
+
+
+@pytest.mark.parametrize("N,k,Gn", [(8, 4, 33), (9, 4, 5), (17, 6, 3)])
+def test_per_graph_tables_built_on_device_equal_host_tables(N, k, Gn):
+    """GraphBatch.per_graph (kNN fast path: tables by rpg_per_graph_tables, no host round trip) against the general
+    host-built one-graph tables, table by table; and the validation counter."""
+    gen = torch.Generator().manual_seed(N + k)
+    x = torch.randn(Gn * N, 64, generator=gen).to(dev())
+    ei = rpg.knn_graph(x, k, num_nodes_per_graph=N)
+    fast = G.GraphBatch.per_graph(ei, Gn, N, check=True)
+    host = G.GraphBatch(ei[0].cpu().numpy(), ei[1].cpu().numpy(), 1, Gn * N, dev())
+    assert (fast.G, fast.N, fast.Ep) == (host.G, host.N, host.Ep)
+    for name in ("src", "dst", "in_ptr", "in_idx", "out_ptr", "out_idx", "min_ptr", "min_idx", "max_ptr", "max_idx",
+                 "inv_deg", "deg", "has_in"):
+        assert torch.equal(fast._tables[name].cpu(), host._tables[name].cpu()), name
+    assert torch.equal(fast.edge_index(), ei)
+    bad = ei.clone()
+    bad[0, 3] = (bad[0, 3] + N) % (Gn * N)           # an edge into another graph
+    with pytest.raises(ValueError):
+        G.GraphBatch.per_graph(bad, Gn, N, check=True)
