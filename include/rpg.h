@@ -93,6 +93,9 @@ typedef struct {
   const rpg_bf16* sel_dst;
   int sel_patterns, sel_div;
   const float* has_in;        /* [N] 1 if the node has incoming edges, else 0 (a mean over nothing is 0 [3p])   */
+  /* per-graph edge sets (rpg_per_graph_tables: G = 1 above): edges / nodes of ONE member graph, 0 otherwise.  With
+   * them set, sel_src / sel_dst hold one pattern tile per 128-row block (rpg_selection_patterns_rows, sel_div = 0).   */
+  int pg_Ep, pg_N;
 } rpg_graph_t;
 
 /* Tables for a batch whose graphs have different edge sets of equal size Ep (dynamic kNN rewiring, posenet.py:1043-1050):
@@ -114,6 +117,11 @@ int rpg_build_edge_index(const rpg_graph_t* graph, int64_t* edge_index, rpg_stre
  * that no 128-row block references more than 64 node rows.                                             */
 int rpg_selection_patterns(const int32_t* endpoint, int Ep, int N, int div, int patterns, rpg_bf16* sel,
                            rpg_stream_t stream);
+/* The same for per-graph edge sets (no period): one tile per 128-row block b of the edge rows, column =
+ * endpoint[row] - ((b * 128) / pg_Ep) * pg_N with `endpoint` the GLOBAL node row of every edge ([Et]); sel
+ * [ceil(Et / 128) * 128, 64].  bad[0] (device int32, pre-zeroed by the caller) counts columns outside [0, 64). */
+int rpg_selection_patterns_rows(const int32_t* endpoint, int64_t Et, int pg_Ep, int pg_N, rpg_bf16* sel, int32_t* bad,
+                                rpg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Generic tcgen05 GEMM with fused epilogue (the workhorse; exposed for unit tests)
@@ -166,7 +174,7 @@ typedef struct {
   /* Gathered node adds as one-hot K panels (preferred over gadd): for each of n_gseg (0..2) operands one extra
    * 64-wide k-block is multiplied, A = the 128 x 64 one-hot selection tile of the row block -- which for a batch of
    * identical graph templates depends only on (row0 mod Ep), so gsel holds gsel_patterns tiles, pattern index
-   * ((row0 % Ep) / gsel_div) -- and B = rows [(row0 / Ep) * Nn, +64) of gsrc [gsrc_rows, >= N] (pitch gsrc_ld),
+   * ((row0 % Ep) / gsel_div), or row block index row0 / 128 when gsel_div = 0 -- and B = rows [(row0 / Ep) * Nn, +64) of gsrc [gsrc_rows, >= N] (pitch gsrc_ld),
    * loaded MN-major.  Exact: 1.0 * bf16 accumulates in fp32.  The epilogue stays the plain one.        */
   int n_gseg;
   const rpg_bf16* gsel[2];

@@ -26,7 +26,7 @@ class Graph(C.Structure):
     _fields_ = [("G", I), ("N", I), ("Ep", I),
                 ("src", P), ("dst", P), ("in_ptr", P), ("in_idx", P), ("out_ptr", P), ("out_idx", P),
                 ("inv_deg", P), ("deg", P), ("min_ptr", P), ("min_idx", P), ("max_ptr", P), ("max_idx", P),
-                ("sel_src", P), ("sel_dst", P), ("sel_patterns", I), ("sel_div", I), ("has_in", P)]
+                ("sel_src", P), ("sel_dst", P), ("sel_patterns", I), ("sel_div", I), ("has_in", P), ("pg_Ep", I), ("pg_N", I)]
 
 
 class Gemm(C.Structure):
@@ -130,6 +130,7 @@ SIGNATURES = {
     "rpg_build_edge_index": (I, [C.POINTER(Graph), P, P]),
     "rpg_per_graph_tables_words": (I64, [I, I, I]),
     "rpg_per_graph_tables": (I, [P, I, I, I, P, P, P]),
+    "rpg_selection_patterns_rows": (I, [P, I64, I, I, P, P, P]),
     "rpg_head_bwd_tc_ws_floats": (I64, [I]),
     "rpg_pack_dpose": (I, [P, I64, P, C.c_float, P, P]),
     "rpg_head_bwd_tc": (I, [P, P, I, P, I64, I, C.c_float, P, P, P, I, P, P, P, P, P, P]),

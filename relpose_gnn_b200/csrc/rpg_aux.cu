@@ -86,6 +86,27 @@ __global__ void selection_patterns_kernel(const int* __restrict__ endpoint, int 
 // ------------------------------------------------------------------------------------------------
 // weights / casts
 // ------------------------------------------------------------------------------------------------
+// Per-row-block variant for per-graph edge sets: no period, one tile per 128 edge rows.
+__global__ void selection_patterns_rows_kernel(const int* __restrict__ endpoint, long long Et, int pg_Ep, int pg_N,
+                                               bf16* __restrict__ sel, int* __restrict__ bad) {
+    pdl_prologue();
+    const long long rows = (Et + 127) / 128 * 128;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < rows * 8; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t >> 3;
+        const int cg = (int)(t & 7);
+        int col = -1;
+        if (r < Et) {
+            const long long win = ((r / 128 * 128) / pg_Ep) * pg_N;
+            col = (int)(__ldg(endpoint + r) - win);
+            if ((col < 0 || col >= 64) && cg == 0) atomicAdd(bad, 1);
+        }
+        float f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = (cg * 8 + q == col) ? 1.f : 0.f;
+        *reinterpret_cast<uint4*>(sel + r * 64 + cg * 8) = pack8(f);
+    }
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ src, int ld_src, int r0, int c0, int rows, int cols,
                                    bf16* __restrict__ dst, int ld_dst, int transpose) {
     pdl_prologue();
@@ -1681,6 +1702,15 @@ int64_t rpg_per_graph_tables_words(int G, int N, int Ep) {
     const long long Et = (long long)G * Ep, Nt = (long long)G * N;
     auto al = [](long long v) { return (v + 3) / 4 * 4; };
     return 6 * al(Et) + 4 * al(Nt + 1) + 3 * al(Nt);
+}
+
+int rpg_selection_patterns_rows(const int32_t* endpoint, int64_t Et, int pg_Ep, int pg_N, rpg_bf16* sel, int32_t* bad,
+                                rpg_stream_t stream) {
+    if (!endpoint || !sel || !bad || Et <= 0 || pg_Ep <= 0 || pg_N <= 0) return set_error(RPG_E_ARG, "selection_patterns_rows: bad arguments");
+    const long long rows = (Et + 127) / 128 * 128;
+    launch_pdl(selection_patterns_rows_kernel, dim3(grid_for(rows * 8, 256)), dim3(256), 0, as_stream(stream), endpoint,
+               (long long)Et, pg_Ep, pg_N, reinterpret_cast<bf16*>(sel), bad);
+    return check_launch("selection_patterns_rows_kernel");
 }
 
 int rpg_build_edge_index(const rpg_graph_t* graph, int64_t* edge_index, rpg_stream_t stream) {

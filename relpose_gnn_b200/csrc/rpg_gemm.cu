@@ -247,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     // The two CTAs of a cluster own different row blocks => different node windows: no multicast here.
                     for (int gs = 0; gs < p.n_gseg; ++gs) {
                         const int r0 = m_blk * BLOCK_M;
-                        const int pat = (r0 % p.Ep) / p.gsel_div;
+                        const int pat = p.gsel_div ? (r0 % p.Ep) / p.gsel_div : m_blk;   // periodic template | per-block tiles
                         const int win = (r0 / p.Ep) * p.Nn;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
@@ -956,7 +956,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         return set_error(RPG_E_ARG, "rpg_gemm: output pointers must be 16-byte aligned");
     // result tiles leave through TMA stores: 32 rows x 64 bf16 (or 32 fp32) columns per box, clipped at the tensor edge
     if (g->n_gseg) {
-        if (g->mode != 0 || g->n_gseg < 0 || g->n_gseg > 2 || block_n % 64 || g->Ep <= 0 || g->Nn <= 0 || g->gsel_div <= 0 ||
+        if (g->mode != 0 || g->n_gseg < 0 || g->n_gseg > 2 || block_n % 64 || g->Ep <= 0 || g->Nn <= 0 || g->gsel_div < 0 ||
             g->gsel_patterns <= 0 || g->gsrc_rows <= 0)
             return set_error(RPG_E_ARG, "rpg_gemm: one-hot gather panels need NT mode, block_n % 64 == 0, Ep, Nn, gsel_div, patterns");
         for (int i = 0; i < g->n_gseg; ++i) {

@@ -236,7 +236,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         g.gadd[0] = t->P;     g.gmap[0] = gr->src; g.gadd_ld[0] = ldP;
         g.gadd[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_ld[1] = ldP;
     }
-    g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
+    g.Ep = gr->Ep; g.Nn = gr->N; if (g.n_gseg && gr->pg_Ep) { g.Ep = gr->pg_Ep; g.Nn = gr->pg_N; } g.relu = 1;
     g.out = t->h1; g.ldo = D; g.out_bits = t->h1_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
 
@@ -259,7 +259,7 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         g.gadd[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_ld[0] = ldP;
         if (np == 4) { g.gadd[1] = t->P + 3 * D; g.gmap[1] = gr->dst; g.gadd_ld[1] = ldP; }
     }
-    g.Ep = gr->Ep; g.Nn = gr->N; g.relu = 1;
+    g.Ep = gr->Ep; g.Nn = gr->N; if (g.n_gseg && gr->pg_Ep) { g.Ep = gr->pg_Ep; g.Nn = gr->pg_N; } g.relu = 1;
     g.out = t->h2; g.ldo = D; g.out_bits = t->h2_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
 
@@ -473,6 +473,7 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         if (gr->sel_dst) {
             g.n_gseg = 1; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
             g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->dan; g.gsrc_ld[0] = D;
+            if (gr->pg_Ep) { g.Ep = gr->pg_Ep; g.Nn = gr->pg_N; }       // per-graph edge sets: window of a member graph
         } else {
             g.gadd[0] = b->dan; g.gmap[0] = gr->dst; g.gadd_ld[0] = D;
         }

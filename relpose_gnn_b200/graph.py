@@ -177,6 +177,7 @@ class GraphBatch:
         ei = edge_index.contiguous()
         words = lib.rpg_per_graph_tables_words(n_graphs, n_nodes, Ep)
         buf = torch.empty(words + 4, dtype=torch.int32, device=dev)
+        buf[words:].zero_()
         bad = buf[words:words + 1]
         _lib.check(lib.rpg_per_graph_tables(ei.data_ptr(), n_graphs, n_nodes, Ep, buf.data_ptr(), bad.data_ptr(),
                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "rpg_per_graph_tables")
@@ -202,6 +203,20 @@ class GraphBatch:
         for name, t in tables.items():
             if name != "_buf":
                 setattr(s, name, t.data_ptr())
+        # One-hot selection tiles, one per 128-row block: a block touches at most ceil(127 / Ep) + 1 member graphs, whose
+        # nodes must fit the 64-row panel.  (Edges were validated to stay inside their graph, so no column can leave it.)
+        if ((127 + Ep - 1) // Ep + 1) * n_nodes <= 64:
+            nblk = (Et + 127) // 128
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for name, tab in (("sel_src", "src"), ("sel_dst", "dst")):
+                sel = torch.empty(nblk * 128, 64, dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.rpg_selection_patterns_rows(tables[tab].data_ptr(), Et, Ep, n_nodes, sel.data_ptr(),
+                                                           buf[words + 1:words + 2].data_ptr(), stream),
+                           "rpg_selection_patterns_rows")
+                tables[name] = sel
+            s.sel_src, s.sel_dst = tables["sel_src"].data_ptr(), tables["sel_dst"].data_ptr()
+            s.sel_patterns, s.sel_div = nblk, 0
+            s.pg_Ep, s.pg_N = Ep, n_nodes
         self.struct = s
         return self
 
