@@ -31,6 +31,7 @@ WORKLOADS = {
     "infer_8192x9": (8192, 9, 512, "infer"),               # BASELINE configs[4], weak: 65 536 graphs over 8 GPUs
     "infer_65536x9_strong": (65536, 9, 512, "infer"),      # BASELINE configs[4], strong: 65 536 graphs in total
     "train_2048x17_strong": (2048, 17, 512, "train"),      # BASELINE configs[3], strong: 2048 graphs in total
+    "train_knn4_4096x9": (4096, 9, 512, "train_knn"),      # the reference CLI default: dynamic 4-NN rewiring (train.py:377)
 }
 STRONG = {"infer_65536x9_strong", "train_2048x17_strong"}
 METRIC = "GNN graphs/sec fwd+bwd"
@@ -177,13 +178,16 @@ def run_ours(args):
         if G % world:
             raise SystemExit("strong-scaling workloads need a GPU count that divides the graph count")
         G //= world                               # contiguous block of graphs per rank
+    knn = 4 if mode == "train_knn" else -1
+    if knn > 0:
+        mode = "train"
     train = mode == "train"
     fp32_mode = mode == "infer_fp32"
     H = N * (N - 1) // 2
     peaks = load_peaks()
 
     torch.manual_seed(0)
-    model = rpg.RelPoseGNN(D, D, D, droprate=0.5, gnn_recursion=R_ROUNDS).to(dev)
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.5, gnn_recursion=R_ROUNDS, knn=knn).to(dev)
     if fp32_mode:
         model.precision = "fp32"
     crit = rpg.PoseNetCriterion(sax=0.0, saq=-2.0).to(dev)
@@ -202,7 +206,7 @@ def run_ours(args):
     poses_host = (0.1 * torch.randn(G * N, 6, generator=gen)).pin_memory()
     x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
     mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
-    masks = [edge_dropout_keep(H, mask_rng) if train else np.ones(H, bool)
+    masks = [edge_dropout_keep(H, mask_rng) if (train and knn <= 0) else np.ones(H, bool)
              for _ in range(2 * args.trials * args.steps + 2 * max(args.warmup, 3) + 16)]
     mask_iter = iter(masks)
 
@@ -212,8 +216,8 @@ def run_ours(args):
         ei = attach(graph.edge_index(), graph)                   # what the PyG loader + train.py:238-245 hand the model
         if train:
             bucket.zero()
-            pn, pe, _ = model(x, ei)
-            loss, t_loss, q_loss = crit(pe, poses, ei)
+            pn, pe, ei_used = model(x, ei)                        # ei_used: the rewired graph when knn > 0
+            loss, t_loss, q_loss = crit(pe, poses, ei_used)
             loss.backward()
             bucket.allreduce()
             return loss
@@ -284,7 +288,7 @@ def run_ours(args):
     # roofline leg: per-launch CUDA events on the tcgen05 GEMM kernel during one more step (same stream)
     keep_prof = masks[0]
     mask_iter = iter([keep_prof] + masks)
-    Ep_prof = 2 * int(keep_prof.sum())
+    Ep_prof = N * knn if knn > 0 else 2 * int(keep_prof.sum())
     lib.rpg_profile_begin()
     step(x_dev, poses_dev, False)
     torch.cuda.synchronize()
@@ -293,7 +297,7 @@ def run_ours(args):
     lib.rpg_profile_end(C.byref(nt_ms), C.byref(tn_ms), C.byref(nt_n), C.byref(tn_n), C.byref(nt_fl), C.byref(tn_fl))
     gemm_ms = nt_ms.value + tn_ms.value
     alg_flops = algorithmic_flops_per_graph(D, N, Ep_prof, train=train) * G
-    mean_Ep = float(np.mean([2 * m.sum() for m in masks[:args.steps]]))
+    mean_Ep = float(N * knn) if knn > 0 else float(np.mean([2 * m.sum() for m in masks[:args.steps]]))
 
     if rank == 0:
         value = world * G / (ms_step * 1e-3)
@@ -305,7 +309,7 @@ def run_ours(args):
             "data": "synthetic",
             "trials_ms_per_step": trials, "trials_e2e_ms_per_step": trials_e2e,
             "config": {"workload": args.workload, "graphs_per_gpu": G, "nodes_per_graph": N, "D": D, "mode": mode,
-                       "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if train else 1.0,
+                       "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if (train and knn <= 0) else 1.0, "knn": knn,
                        "mean_edges_per_graph": mean_Ep, "feature_dropout": 0.5,
                        "step": "forward + compute_RP/L1 criterion + backward" + (" + 1 NCCL all-reduce" if world > 1 else "") if train else "forward",
                        "parallelism": f"dp{world} over graphs", "l2": "activations per step (>1 GB) exceed the 126 MB L2; no flush needed"},
