@@ -502,6 +502,8 @@ typedef struct {
   float* gtp;                                      /* [Et, 3c] fp32                                     */
   rpg_bf16 *y_hi, *y_lo;                           /* [Et, pad64(c)]                                    */
   rpg_bf16 *z_hi, *z_lo, *a_hi, *a_lo, *h3_hi, *h3_lo, *out_hi, *out_lo, *out_relu_hi, *out_relu_lo;
+  rpg_bf16* ybar_hi, *ybar_lo;    /* [Nt, max(c,64)] scratch: mean over in-edges of y                  */
+  rpg_bf16* mbar_hi, *mbar_lo;    /* [Nt, D]         scratch: mean over in-edges of m   (z is never materialised) */
 } rpg_layer_acts_split_t;
 
 int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* graph,

@@ -66,7 +66,7 @@ class LayerActsSplit(C.Structure):
     _fields_ = [(n, P) for n in ("x_hi", "x_lo", "e_hi", "e_lo", "P", "h1_hi", "h1_lo", "e_new_hi", "e_new_lo",
                                  "e_new_relu_hi", "e_new_relu_lo", "h2_hi", "h2_lo", "m_hi", "m_lo", "gtp", "y_hi", "y_lo",
                                  "z_hi", "z_lo", "a_hi", "a_lo", "h3_hi", "h3_lo", "out_hi", "out_lo", "out_relu_hi",
-                                 "out_relu_lo")]
+                                 "out_relu_lo", "ybar_hi", "ybar_lo", "mbar_hi", "mbar_lo")]
 
 
 class LayerGrads(C.Structure):

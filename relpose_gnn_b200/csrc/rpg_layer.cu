@@ -356,13 +356,17 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     RPG_TRY(gemm_launch(&g, s));
     // (7) attention -> y (hi, lo)
     RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y_hi, cp, t->y_lo, nullptr, stream));
-    // (8) z = y WW^T + bW + m
-    base((int)Et, D, w->WW3, 3 * cp); g.n_seg = 3; set3(g, 0, t->y_hi, t->y_lo, cp, cp);
-    g.bias = w->bW; g.resid = t->m_hi; g.resid_lo = t->m_lo; g.resid_ld = D;
-    g.out = t->z_hi; g.out_lo = t->z_lo; g.ldo = D;
+    // (8)+(9) mean over incoming edges of z = y WW^T + bW + m, evaluated at node level (the mean is linear; see
+    //     rpg_layer_fwd): a = mean(y) WW^T + bW + mean(m), zero for nodes without incoming edges
+    if (!t->ybar_hi || !t->ybar_lo || !t->mbar_hi || !t->mbar_lo || !gr->has_in)
+        return set_error(RPG_E_ARG, "layer_fwd_split: ybar / mbar planes or has_in missing");
+    RPG_TRY(rpg_aggregate_mean_split(t->y_hi, t->y_lo, cp, gr, cp, t->ybar_hi, t->ybar_lo, cp, stream));
+    RPG_TRY(rpg_aggregate_mean_split(t->m_hi, t->m_lo, D, gr, D, t->mbar_hi, t->mbar_lo, D, stream));
+    base((int)Nt, D, w->WW3, 3 * cp); g.n_seg = 3; set3(g, 0, t->ybar_hi, t->ybar_lo, cp, cp);
+    g.bias = w->bW; g.resid = t->mbar_hi; g.resid_lo = t->mbar_lo; g.resid_ld = D;
+    g.row_scale = gr->has_in; g.row_scale_mod = gr->N;
+    g.out = t->a_hi; g.out_lo = t->a_lo; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
-    // (9) mean over incoming edges
-    RPG_TRY(rpg_aggregate_mean_split(t->z_hi, t->z_lo, D, gr, D, t->a_hi, t->a_lo, D, stream));
     // (10) out = relu([x | a] W1u^T + b) W2u^T + b
     base((int)Nt, D, w->W1u3, 6 * D); g.n_seg = 6; set3(g, 0, t->x_hi, t->x_lo, D, D); set3(g, 3, t->a_hi, t->a_lo, D, D);
     g.bias = w->b1u; g.relu = 1; g.out = t->h3_hi; g.out_lo = t->h3_lo; g.ldo = D;

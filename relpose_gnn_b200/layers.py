@@ -217,7 +217,8 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
         return f(rows, cols, dtype=BF16, device=dev), f(rows, cols, dtype=BF16, device=dev)
 
     a = {"x": x, "e": e, "h1": pair(Et, D), "e_new": pair(Et, D), "h2": pair(Et, D), "m": pair(Et, D),
-         "y": pair(Et, cp, zero=(cp != c)), "z": pair(Et, D), "a": pair(Nt, D), "h3": pair(Nt, D), "out": pair(Nt, D)}
+         "y": pair(Et, cp, zero=(cp != c)), "ybar": pair(Nt, cp), "mbar": pair(Nt, D), "a": pair(Nt, D),
+         "h3": pair(Nt, D), "out": pair(Nt, D)}
     if want_relu_copies:
         a["e_new_relu"] = pair(Et, D)
         a["out_relu"] = pair(Nt, D)
