@@ -171,16 +171,16 @@ typedef struct {
   const rpg_bf16* resid_lo;   /* low plane of resid (pitch resid_ld) or NULL                          */
   rpg_bf16* out_lo;           /* low plane of out: bf16(v - float(bf16(v))) (pitch ldo) or NULL        */
   rpg_bf16* out_relu_lo;      /* low plane of out_relu or NULL                                        */
-  /* Gathered node adds as one-hot K panels (preferred over gadd): for each of n_gseg (0..2) operands one extra
+  /* Gathered node adds as one-hot K panels (preferred over gadd): for each of n_gseg (0..4) operands one extra
    * 64-wide k-block is multiplied, A = the 128 x 64 one-hot selection tile of the row block -- which for a batch of
    * identical graph templates depends only on (row0 mod Ep), so gsel holds gsel_patterns tiles, pattern index
    * ((row0 % Ep) / gsel_div), or row block index row0 / 128 when gsel_div = 0 -- and B = rows [(row0 / Ep) * Nn, +64) of gsrc [gsrc_rows, >= N] (pitch gsrc_ld),
    * loaded MN-major.  Exact: 1.0 * bf16 accumulates in fp32.  The epilogue stays the plain one.        */
   int n_gseg;
-  const rpg_bf16* gsel[2];
+  const rpg_bf16* gsel[4];
   int gsel_patterns, gsel_div;
-  const rpg_bf16* gsrc[2];
-  int gsrc_ld[2];
+  const rpg_bf16* gsrc[4];
+  int gsrc_ld[4];
   int gsrc_rows;
   /* TN mode: per-split column sums of A, i.e. sum_r A[r, m] (the bias gradient when A is dY), written to
    * a_colsum [splits, M]; accumulated from the shared-memory operand tiles by the warps that are idle during the
@@ -497,13 +497,15 @@ typedef struct {
 
 typedef struct {
   const rpg_bf16 *x_hi, *x_lo, *e_hi, *e_lo;        /* inputs  [Nt, D], [Et, D]                          */
-  float* P;                                        /* [Nt, 3D] fp32 node projections                    */
+  float* P;                                        /* [Nt, 3D] fp32 node projections (epilogue-gather path) */
   rpg_bf16 *h1_hi, *h1_lo, *e_new_hi, *e_new_lo, *e_new_relu_hi, *e_new_relu_lo, *h2_hi, *h2_lo, *m_hi, *m_lo;
   float* gtp;                                      /* [Et, 3c] fp32                                     */
   rpg_bf16 *y_hi, *y_lo;                           /* [Et, pad64(c)]                                    */
   rpg_bf16 *z_hi, *z_lo, *a_hi, *a_lo, *h3_hi, *h3_lo, *out_hi, *out_lo, *out_relu_hi, *out_relu_lo;
   rpg_bf16* ybar_hi, *ybar_lo;    /* [Nt, max(c,64)] scratch: mean over in-edges of y                  */
   rpg_bf16* mbar_hi, *mbar_lo;    /* [Nt, D]         scratch: mean over in-edges of m   (z is never materialised) */
+  rpg_bf16* P_hi, *P_lo;          /* [Nt, 3D] node projections as (hi, lo) planes: with selection patterns in the graph
+                                     the gathered terms are one-hot K panels over both planes (P may then be NULL)  */
 } rpg_layer_acts_split_t;
 
 int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* graph,

@@ -39,7 +39,7 @@ class Gemm(C.Structure):
                 ("out", P), ("out_relu", P), ("ldo", I), ("out_f32", P), ("ldo_f32", I),
                 ("mask_bits", P), ("mask_bits_ld", I), ("out_bits", P), ("out_bits_ld", I),
                 ("gadd_f32", P * 2), ("gadd_f32_ld", I * 2), ("resid_lo", P), ("out_lo", P), ("out_relu_lo", P),
-                ("n_gseg", I), ("gsel", P * 2), ("gsel_patterns", I), ("gsel_div", I), ("gsrc", P * 2), ("gsrc_ld", I * 2),
+                ("n_gseg", I), ("gsel", P * 4), ("gsel_patterns", I), ("gsel_div", I), ("gsrc", P * 4), ("gsrc_ld", I * 4),
                 ("gsrc_rows", I), ("a_colsum", P), ("drop_seed", C.c_uint64), ("drop_p", C.c_float)]
 
 
@@ -66,7 +66,7 @@ class LayerActsSplit(C.Structure):
     _fields_ = [(n, P) for n in ("x_hi", "x_lo", "e_hi", "e_lo", "P", "h1_hi", "h1_lo", "e_new_hi", "e_new_lo",
                                  "e_new_relu_hi", "e_new_relu_lo", "h2_hi", "h2_lo", "m_hi", "m_lo", "gtp", "y_hi", "y_lo",
                                  "z_hi", "z_lo", "a_hi", "a_lo", "h3_hi", "h3_lo", "out_hi", "out_lo", "out_relu_hi",
-                                 "out_relu_lo", "ybar_hi", "ybar_lo", "mbar_hi", "mbar_lo")]
+                                 "out_relu_lo", "ybar_hi", "ybar_lo", "mbar_hi", "mbar_lo", "P_hi", "P_lo")]
 
 
 class LayerGrads(C.Structure):

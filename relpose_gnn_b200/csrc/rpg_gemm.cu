@@ -88,8 +88,8 @@ struct GemmTmaps {
     CUtensorMap a[6];              // A segments (NT) / a[0] = A (TN)
     CUtensorMap b;
     CUtensorMap out, out_relu, out_f32, out_lo, out_relu_lo;
-    CUtensorMap ga[2];             // one-hot selection patterns [npat * 128, 64] (K-major A tiles)
-    CUtensorMap gb[2];             // gathered matrix [rows, N] (MN-major B tiles: 64 rows x 64 columns per box)
+    CUtensorMap ga[4];             // one-hot selection patterns [npat * 128, 64] (K-major A tiles)
+    CUtensorMap gb[4];             // gathered matrix [rows, N] (MN-major B tiles: 64 rows x 64 columns per box)
     CUtensorMap resid;             // residual [M, N] in 32-row x 64-column boxes (same geometry as the output maps)
 };
 
@@ -956,7 +956,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         return set_error(RPG_E_ARG, "rpg_gemm: output pointers must be 16-byte aligned");
     // result tiles leave through TMA stores: 32 rows x 64 bf16 (or 32 fp32) columns per box, clipped at the tensor edge
     if (g->n_gseg) {
-        if (g->mode != 0 || g->n_gseg < 0 || g->n_gseg > 2 || block_n % 64 || g->Ep <= 0 || g->Nn <= 0 || g->gsel_div < 0 ||
+        if (g->mode != 0 || g->n_gseg < 0 || g->n_gseg > 4 || block_n % 64 || g->Ep <= 0 || g->Nn <= 0 || g->gsel_div < 0 ||
             g->gsel_patterns <= 0 || g->gsrc_rows <= 0)
             return set_error(RPG_E_ARG, "rpg_gemm: one-hot gather panels need NT mode, block_n % 64 == 0, Ep, Nn, gsel_div, patterns");
         for (int i = 0; i < g->n_gseg; ++i) {

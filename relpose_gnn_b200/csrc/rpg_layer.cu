@@ -324,15 +324,30 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
         memset(&g, 0, sizeof g);
         g.mode = 0; g.M = M; g.N = N; g.B = B; g.ldb = ldb;
     };
-    // (1) P = x Wn^T  -> fp32 [Nt, 3D]
+    // (1) P = x Wn^T  [Nt, 3D]: (hi, lo) planes when the gathers below can be one-hot K panels (a one-hot row times a
+    //     bf16 plane is exact, so two panels per gather add P_hi + P_lo = P to 2^-17), else fp32 for the epilogue gathers
+    const bool panels = gr->sel_src && gr->sel_dst && t->P_hi && t->P_lo;
+    if (!panels && !t->P) return set_error(RPG_E_ARG, "layer_fwd_split: P (fp32) or P_hi / P_lo with selection patterns needed");
+    const int pEp = gr->pg_Ep ? gr->pg_Ep : gr->Ep, pNn = gr->pg_Ep ? gr->pg_N : gr->N;
     base((int)Nt, 3 * D, w->Wn3, 3 * D); g.n_seg = 3; set3(g, 0, t->x_hi, t->x_lo, D, D);
-    g.out_f32 = t->P; g.ldo_f32 = 3 * D;
+    if (panels) { g.out = t->P_hi; g.out_lo = t->P_lo; g.ldo = 3 * D; }
+    else { g.out_f32 = t->P; g.ldo_f32 = 3 * D; }
     RPG_TRY(gemm_launch(&g, s));
+    auto panel = [&](int i, const rpg_bf16* sel, const rpg_bf16* plane, int col0) {
+        g.gsel[i] = sel; g.gsrc[i] = plane + col0; g.gsrc_ld[i] = 3 * D;
+    };
     // (2) h1 = relu(e W1e_e^T + P_s[src] + P_d[dst] + b)
     base((int)Et, D, w->W1e_e3, 3 * D); g.n_seg = 3; set3(g, 0, t->e_hi, t->e_lo, D, D);
-    g.bias = w->b1e; g.relu = 1; g.Ep = gr->Ep; g.Nn = gr->N;
-    g.gadd_f32[0] = t->P;     g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
-    g.gadd_f32[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_f32_ld[1] = 3 * D;
+    g.bias = w->b1e; g.relu = 1;
+    if (panels) {
+        g.n_gseg = 4; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt; g.Ep = pEp; g.Nn = pNn;
+        panel(0, gr->sel_src, t->P_hi, 0); panel(1, gr->sel_src, t->P_lo, 0);
+        panel(2, gr->sel_dst, t->P_hi, D); panel(3, gr->sel_dst, t->P_lo, D);
+    } else {
+        g.Ep = gr->Ep; g.Nn = gr->N;
+        g.gadd_f32[0] = t->P;     g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
+        g.gadd_f32[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_f32_ld[1] = 3 * D;
+    }
     g.out = t->h1_hi; g.out_lo = t->h1_lo; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
     // (3) e' = h1 W2e^T + b  (+ relu'd copy)
@@ -342,8 +357,14 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     RPG_TRY(gemm_launch(&g, s));
     // (4) h2 = relu(e' W1m_e^T + P_m[src] + b)
     base((int)Et, D, w->W1m_e3, 3 * D); g.n_seg = 3; set3(g, 0, t->e_new_hi, t->e_new_lo, D, D);
-    g.bias = w->b1m; g.relu = 1; g.Ep = gr->Ep; g.Nn = gr->N;
-    g.gadd_f32[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
+    g.bias = w->b1m; g.relu = 1;
+    if (panels) {
+        g.n_gseg = 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt; g.Ep = pEp; g.Nn = pNn;
+        panel(0, gr->sel_src, t->P_hi, 2 * D); panel(1, gr->sel_src, t->P_lo, 2 * D);
+    } else {
+        g.Ep = gr->Ep; g.Nn = gr->N;
+        g.gadd_f32[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
+    }
     g.out = t->h2_hi; g.out_lo = t->h2_lo; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
     // (5) m = h2 W2m^T + b

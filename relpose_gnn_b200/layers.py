@@ -222,13 +222,19 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
     if want_relu_copies:
         a["e_new_relu"] = pair(Et, D)
         a["out_relu"] = pair(Nt, D)
-    P = torch.empty(Nt, 3 * D, dtype=torch.float32, device=dev)
+    # node projections: (hi, lo) planes for the one-hot-panel gathers when the graph has selection patterns, else fp32
+    use_panels = bool(graph.struct.sel_src and graph.struct.sel_dst)
+    if use_panels:
+        a["P"] = pair(Nt, 3 * D)
+        P = None
+    else:
+        P = torch.empty(Nt, 3 * D, dtype=torch.float32, device=dev)
     gtp = torch.empty(Et, 3 * c, dtype=torch.float32, device=dev)
     s = _lib.LayerActsSplit()
     for k, (hi, lo) in a.items():
         setattr(s, k + "_hi", hi.data_ptr())
         setattr(s, k + "_lo", lo.data_ptr())
-    s.P, s.gtp = P.data_ptr(), gtp.data_ptr()
+    s.P, s.gtp = (P.data_ptr() if P is not None else None), gtp.data_ptr()
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(_lib.load().rpg_layer_fwd_split(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd_split")
     a["_keep"] = (P, gtp, s)
