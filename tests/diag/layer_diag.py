@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import relpose_gnn_b200 as rpg  # noqa: E402
 from oracle import restatement as R  # noqa: E402
 from relpose_gnn_b200 import ops  # noqa: E402

@@ -19,7 +19,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL_BF16 = 2e-2
 # Gradients against the plain fp64 reference: a bf16 forward flips the sign of ~0.3 % of the near-zero ReLU
 # pre-activations, and each flip changes d(relu) by O(1) => relative Frobenius error ~ sqrt(flip fraction) = 3-6 %
-# (measured, tools/layer_diag.py; drops to the 3e-3 arithmetic floor before the first ReLU).  This is a property
+# (measured, tests/diag/layer_diag.py; drops to the 3e-3 arithmetic floor before the first ReLU).  This is a property
 # of bf16 arithmetic, not of the kernels, so the fixture comparison is loose ...
 TOL_GRAD_FLIP = 1e-1
 TOL_GRAD_SMALL = 2.5e-1        # per-tensor bound for tiny gradients (attention biases) dominated by flip noise
