@@ -999,6 +999,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
@@ -1025,6 +1026,8 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (cl == 1)
         kern = g->mode == 1 ? gemm_tc_kernel<1, 1, 0>
                             : (split_mode ? gemm_tc_kernel<0, 1, 2> : (ops ? gemm_tc_kernel<0, 1, 1> : gemm_tc_kernel<0, 1, 0>));
+    else if (g->mode == 0 && split_mode && g->n_gseg == 0 && gemm_pair_enabled())
+        kern = gemm_tc_kernel<0, 2, 2, true>;           // fp32 mode on CTA pairs
     else if (g->mode == 0 && !split_mode && g->n_gseg == 0 && gemm_pair_enabled()) {
         kern = ops ? gemm_tc_kernel<0, 2, 1, true> : gemm_tc_kernel<0, 2, 0, true>;
         if (ops && p.resid && !p.mask && !p.gadd[0] && !p.gadd[1] && aligned16(p.resid) && p.resid_ld % 8 == 0) {
