@@ -32,6 +32,7 @@ WORKLOADS = {
     "infer_65536x9_strong": (65536, 9, 512, "infer"),      # BASELINE configs[4], strong: 65 536 graphs in total
     "train_2048x17_strong": (2048, 17, 512, "train"),      # BASELINE configs[3], strong: 2048 graphs in total
     "train_knn4_4096x9": (4096, 9, 512, "train_knn"),      # the reference CLI default: dynamic 4-NN rewiring (train.py:377)
+    "train_fp32_4096x9": (4096, 9, 512, "train_fp32"),     # the reference's native precision (train.py:266-274) in fp32 mode
 }
 STRONG = {"infer_65536x9_strong", "train_2048x17_strong"}
 METRIC = "GNN graphs/sec fwd+bwd"
@@ -110,11 +111,17 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference_throughput(G_sample, N, D, train, steps, warmup, threads=None):
-    """The reference algorithm (oracle/restatement.py, pinned to the real reference by tests/golden) on the host
-    CPU in fp32 with all threads, on `G_sample` graphs per step; graphs/s = G_sample / median step time."""
-    from oracle import restatement as R
+    """The reference's own modules (oracle/reference_arm.py: PoseNetX_R2 + compute_RP + PoseNetCriterion + Adam through
+    the PyG shim, staged under baseline/_ref for the GPU box) on the host CPU, fp32, all threads, `G_sample` graphs per
+    step; if they are not available, the oracle port (oracle/restatement.py).  Returns (graphs/s, s/step, threads, kind)."""
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
+    from oracle import reference_arm
+    if reference_arm.available():
+        v, med = reference_arm.time_reference(D, N, G_sample, train, edge_dropout=train, steps=steps, warmup=warmup,
+                                              threads=threads)
+        return v, med, threads, "reference"
+    from oracle import restatement as R
     case = R.synth_stack_case(D, N, G_sample, 4242, droprate=0.5, edge_dropout=train, dtype=torch.float32)
     params = {k: v.clone().requires_grad_(train) for k, v in case["params"].items()}
     sax = torch.zeros(1, requires_grad=train)
@@ -135,7 +142,14 @@ def cpu_reference_throughput(G_sample, N, D, train, steps, warmup, threads=None)
         if it >= warmup:
             times.append(dt)
     med = float(np.median(times))
-    return G_sample / med, med, threads
+    return G_sample / med, med, threads, "port"
+
+
+def cpu_sample_note(kind, sample, N, mode, threads, med):
+    what = ("the reference's own PoseNetX_R2 / simpleConvEdge_upt / compute_RP / PoseNetCriterion / Adam, imported unmodified "
+            "through oracle/pyg_shim.py") if kind == "reference" else "oracle port (oracle/restatement.py)"
+    return (f"{sample} graphs x {N} nodes per step, {mode}, fp32 torch CPU, {threads} threads, {what}; "
+            f"{med * 1e3:.0f} ms per sample")
 
 
 def run_reference(args):
@@ -143,20 +157,48 @@ def run_reference(args):
     if rank != 0:
         return
     G, N, D, mode = WORKLOADS[args.workload]
+    train = mode in ("train", "train_knn")
     sample = args.cpu_sample
-    value, med, threads = cpu_reference_throughput(sample, N, D, mode == "train", args.steps, args.warmup)
+    value, med, threads, kind = cpu_reference_throughput(sample, N, D, train, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "graphs_per_step": sample, "nodes": N, "D": D, "mode": mode,
-                       "note": "reference algorithm (oracle port) on host CPU; bounded sample of the workload per step"},
-            "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} graphs x {N} nodes per step, {mode}, fp32, torch CPU"},
+                       "note": "the reference's CPU implementation of the path on the host cores; each step is a bounded "
+                               "sample of the workload (the reference materialises [Et, D/8, D/8] attention tensors)"},
+            "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": threads, "kind": kind,
+                             "sample": cpu_sample_note(kind, sample, N, mode, threads, med)},
             "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- our arm (B200)
+def hbm_roofline(records, peaks, D):
+    """Per kernel class of the bandwidth-bound part of the path: algorithmic bytes / CUDA-event time vs the measured HBM peak."""
+    from relpose_gnn_b200 import _lib
+    out = {}
+    groups = {}
+    for r in records:
+        name = _lib.PROF_CLASSES[r.cls]
+        if name == "gemm_nt" and r.N <= 8:
+            name = "pose_heads(gemm N=8)"
+        elif name.startswith("gemm"):
+            continue
+        groups.setdefault(name, []).append(r)
+    for name, rs in groups.items():
+        ms = sum(r.ms for r in rs)
+        by = sum(r.bytes for r in rs)
+        ent = {"launches": len(rs), "ms_per_step": ms, "algorithmic_bytes_per_launch": by / len(rs),
+               "achieved": by / (ms * 1e-3) / 1e9 if ms > 0 else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "frac": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if ms > 0 else None, "bound": "hbm"}
+        if name.startswith("attention"):
+            ex = sum(r.flops for r in rs)             # exp evaluations
+            ent["bound"] = "mufu (exp2: 16/clk/SM)"
+            ent["gexp_per_s"] = ex / (ms * 1e-3) / 1e9 if ms > 0 else None
+        out[name] = ent
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -182,7 +224,9 @@ def run_ours(args):
     if knn > 0:
         mode = "train"
     train = mode == "train"
-    fp32_mode = mode == "infer_fp32"
+    fp32_mode = mode in ("infer_fp32", "train_fp32")
+    if mode == "train_fp32":
+        train = True
     H = N * (N - 1) // 2
     peaks = load_peaks()
 
@@ -196,55 +240,80 @@ def run_ours(args):
         for p in params:
             dist.broadcast(p.data, 0)
     bucket = parallel.FlatGradBucket(params) if train else None
+    opt = None
     if train:
         model.attach_grad_bucket(bucket)
+        if args.optimizer:
+            # train.py:211: Adam over the parameters of the path; one fused kernel over the flat buckets.  Its 1/world
+            # folds the gradient average of the data-parallel sum, and every step re-packs the bf16 operands.
+            opt = rpg.FusedAdam(params, lr=1e-5, grad_bucket=bucket, modules=[model])
+    rpg.set_validation("async" if args.validation == "async" else "sync")
 
-    # synthetic inputs of the named shape: ResNet34 embeddings ~ N(0,1) in bf16, poses ~ N(0, 0.1)
+    # synthetic inputs of the named shape: ResNet34 embeddings ~ N(0,1) in bf16, poses ~ N(0, 0.1), and the
+    # PyG-batched int64 edge_index of the FULL templates as the loader produces it (train.py:24,132)
     gen = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(G * N, D, generator=gen)
     x_host = (x_host if fp32_mode else x_host.bfloat16()).pin_memory()
     poses_host = (0.1 * torch.randn(G * N, 6, generator=gen)).pin_memory()
-    x_dev, poses_dev = x_host.to(dev), poses_host.to(dev)
+    src_t, dst_t = rpg.fc_template(N)
+    ei_host = rpg.batched_edge_index(src_t, dst_t, G, N).pin_memory()
+    x_dev, poses_dev, ei_dev = x_host.to(dev), poses_host.to(dev), ei_host.to(dev)
     mask_rng = np.random.RandomState(7)           # same mask sequence on every rank (one mask per global batch)
-    masks = [edge_dropout_keep(H, mask_rng) if (train and knn <= 0) else np.ones(H, bool)
+    use_mask = train and knn <= 0
+    masks = [edge_dropout_keep(H, mask_rng) if use_mask else np.ones(H, bool)
              for _ in range(2 * args.trials * args.steps + 2 * max(args.warmup, 3) + 16)]
     mask_iter = iter(masks)
 
-    def step(x, poses, read_back):
+    def step(x, poses, ei_full):
         keep = next(mask_iter)
-        graph = GraphBatch.fully_connected(G, N, dev, keep)
-        ei = attach(graph.edge_index(), graph)                   # what the PyG loader + train.py:238-245 hand the model
+        if args.boundary == "attached":           # round-1 shortcut: the caller builds the GraphBatch itself
+            graph = GraphBatch.fully_connected(G, N, dev, keep)
+            ei = attach(graph.edge_index(), graph)
+        elif use_mask:                            # train.py:238-245 on the device, then a FRESH un-annotated edge_index
+            ei = rpg.mask_edge_index(ei_full, keep, G)
+        else:
+            ei = ei_full
         if train:
-            bucket.zero()
+            if opt is not None:
+                opt.zero_grad()
+            else:
+                bucket.zero()
             pn, pe, ei_used = model(x, ei)                        # ei_used: the rewired graph when knn > 0
             loss, t_loss, q_loss = crit(pe, poses, ei_used)
             loss.backward()
-            bucket.allreduce()
+            if opt is not None:
+                bucket.allreduce(average=False)
+                opt.step(grad_scale=1.0 / world)
+            else:
+                bucket.allreduce()
             return loss
         with torch.no_grad():
             pn, pe, _ = model(x, ei)
         return pe
 
     # e2e leg: the loop a user writes with the package's own feed (relpose_gnn_b200.feed): every step copies its
-    # inputs host -> device from pinned memory (on a copy stream, overlapping the previous step's kernels) and reads its
-    # result back (training: the loss, through a pinned slot read one step later; inference: the edge poses).
+    # inputs -- node embeddings, poses AND the int64 edge_index -- host -> device from pinned memory (on a copy stream,
+    # overlapping the previous step's kernels), the model receives that edge_index un-annotated (validated on the
+    # device, rpg.graph.from_edge_index) and the step's result is read back (training: the loss, through a pinned slot
+    # read one step later; inference: the edge poses).
     feeder = rpg.DeviceFeeder(dev)
     readback = rpg.ScalarReadback(1 if train else G * N * (N - 1) * 6)
 
     def e2e_loop(n_steps):
         results = []
-        feeder.stage(x_host, poses_host)
+        feeder.stage(x_host, poses_host, ei_host)
         for i in range(n_steps):
-            x, poses = feeder.take()
-            out = step(x, poses, True)
+            x, poses, ei_full = feeder.take()
+            out = step(x, poses, ei_full)
             feeder.release()
             if i + 1 < n_steps:          # staged after this step's own small uploads are queued: they go first on the copy engine
-                feeder.stage(x_host, poses_host)
+                feeder.stage(x_host, poses_host, ei_host)
             if readback.full():
                 results.append(readback.pop())
             readback.push(out.float())
         while readback.pending:
             results.append(readback.pop())
+        rpg.check_pending(block=True)
         assert len(results) == n_steps and all(bool(torch.isfinite(r).all()) for r in results)
 
     def timed(n_steps, e2e):
@@ -257,7 +326,7 @@ def run_ours(args):
             e2e_loop(n_steps)
         else:
             for _ in range(n_steps):
-                step(x_dev, poses_dev, False)
+                step(x_dev, poses_dev, ei_dev)
         ev1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -270,8 +339,9 @@ def run_ours(args):
     # holds blocks big enough for every later edge-dropout mask), then W steps of the real mask sequence
     mask_iter = iter([np.ones(H, bool)] * 2 + masks)
     for _ in range(2 + max(args.warmup, 3)):
-        step(x_dev, poses_dev, False)
+        step(x_dev, poses_dev, ei_dev)
     torch.cuda.synchronize()
+    rpg.check_pending(block=True)
     sampler = ClockSampler(local_rank)
     if rank == 0 and args.clocks:
         sampler.start()
@@ -285,23 +355,28 @@ def run_ours(args):
     trials_e2e = [timed(args.steps, e2e=True) for _ in range(args.trials)]
     ms_e2e = float(np.median(trials_e2e))
 
-    # roofline leg: per-launch CUDA events on the tcgen05 GEMM kernel during one more step (same stream)
+    # roofline leg: per-launch CUDA events on EVERY kernel class during one more step (same stream, no PDL overlap)
     keep_prof = masks[0]
     mask_iter = iter([keep_prof] + masks)
     Ep_prof = N * knn if knn > 0 else 2 * int(keep_prof.sum())
     lib.rpg_profile_begin()
-    step(x_dev, poses_dev, False)
+    step(x_dev, poses_dev, ei_dev)
     torch.cuda.synchronize()
-    nt_ms, tn_ms, nt_fl, tn_fl = C.c_double(), C.c_double(), C.c_double(), C.c_double()
-    nt_n, tn_n = C.c_int(), C.c_int()
-    lib.rpg_profile_end(C.byref(nt_ms), C.byref(tn_ms), C.byref(nt_n), C.byref(tn_n), C.byref(nt_fl), C.byref(tn_fl))
-    gemm_ms = nt_ms.value + tn_ms.value
+    recs = (_lib.ProfRec * 1024)()
+    n_rec = C.c_int()
+    lib.rpg_profile_records(recs, 1024, C.byref(n_rec))
+    recs = [recs[i] for i in range(min(n_rec.value, 1024))]
+    gemms = [r for r in recs if r.cls <= 1]
+    gemm_ms = sum(r.ms for r in gemms)
+    gemm_fl = sum(r.flops for r in gemms)
+    edge_gemms = [r for r in gemms if r.N > 8 and r.M >= G * Ep_prof]          # the edge-level (MLP) GEMMs of the path
     alg_flops = algorithmic_flops_per_graph(D, N, Ep_prof, train=train) * G
     mean_Ep = float(N * knn) if knn > 0 else float(np.mean([2 * m.sum() for m in masks[:args.steps]]))
 
     if rank == 0:
         value = world * G / (ms_step * 1e-3)
         e2e_value = world * G / (ms_e2e * 1e-3)
+        ei_bytes = ei_host.numel() * 8
         line = {
             "metric": METRIC, "value": value, "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
@@ -309,15 +384,20 @@ def run_ours(args):
             "data": "synthetic",
             "trials_ms_per_step": trials, "trials_e2e_ms_per_step": trials_e2e,
             "config": {"workload": args.workload, "graphs_per_gpu": G, "nodes_per_graph": N, "D": D, "mode": mode,
-                       "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if (train and knn <= 0) else 1.0, "knn": knn,
+                       "gnn_recursion": R_ROUNDS, "edge_dropout_keep": 0.5 if use_mask else 1.0, "knn": knn,
                        "mean_edges_per_graph": mean_Ep, "feature_dropout": 0.5,
-                       "step": "forward + compute_RP/L1 criterion + backward" + (" + 1 NCCL all-reduce" if world > 1 else "") if train else "forward",
+                       "step": ("edge mask (train.py:238-245) + forward + compute_RP/L1 criterion + backward"
+                                + (" + 1 NCCL all-reduce" if world > 1 else "")
+                                + (" + Adam step + re-pack of the bf16 operands" if opt is not None else "")) if train else "forward",
+                       "boundary": ("fresh int64 edge_index every step -> rpg.graph.from_edge_index (device-side validation + "
+                                    f"template tables, validation={args.validation})") if args.boundary == "fresh"
+                                   else "GraphBatch attached by the caller (no validation)",
                        "parallelism": f"dp{world} over graphs", "l2": "activations per step (>1 GB) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + poses_host.numel() * 4,
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + poses_host.numel() * 4 + ei_bytes,
                     "d2h_bytes_per_step": 4 if train else G * 2 * int(np.mean([m.sum() for m in masks[:4]])) * 6 * 4,
-                    "pipeline": "relpose_gnn_b200.DeviceFeeder: pinned H2D of step i+1 on a copy stream under step i; "
-                                "result read back through a pinned slot one step later"},
+                    "pipeline": "relpose_gnn_b200.DeviceFeeder: pinned H2D of step i+1 (embeddings, poses, int64 edge_index) on a "
+                                "copy stream under step i; result read back through a pinned slot one step later"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<NT|TN> (tcgen05)",
@@ -326,19 +406,35 @@ def run_ours(args):
                          "traffic": (load_traffic() or {}).get("dram_bytes_per_launch") if args.workload == "train_4096x9" else None,
                          "traffic_source": "profiles/r1_gemm_traffic.json (ncu dram__bytes_read+write per launch, train_4096x9)",
                          "peak_source": peaks["source"] + ", sustained bf16",
-                         "algorithmic_flops_per_launch": alg_flops / max(nt_n.value + tn_n.value, 1),
-                         "avg_launch_ms": gemm_ms / max(nt_n.value + tn_n.value, 1),
-                         "launches_per_step": nt_n.value + tn_n.value,
-                         "executed_tflops": (nt_fl.value + tn_fl.value) / (gemm_ms * 1e-3) / 1e12,
-                         "executed_frac": (nt_fl.value + tn_fl.value) / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                         "algorithmic_flops_per_launch": alg_flops / max(len(gemms), 1),
+                         "avg_launch_ms": gemm_ms / max(len(gemms), 1),
+                         "launches_per_step": len(gemms),
+                         "executed_tflops": gemm_fl / (gemm_ms * 1e-3) / 1e12,
+                         "executed_frac": gemm_fl / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                         "edge_mlp_gemms": {"launches": len(edge_gemms), "ms": sum(r.ms for r in edge_gemms),
+                                            "executed_tflops": sum(r.flops for r in edge_gemms) / max(sum(r.ms for r in edge_gemms), 1e-9) / 1e9,
+                                            "executed_frac": sum(r.flops for r in edge_gemms) / max(sum(r.ms for r in edge_gemms), 1e-9) / 1e9 / peaks["bf16_sustained"]},
                          "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_step,
+                         "note": "per-launch events with programmatic dependent launch OFF (kernels serialised); in-step the GEMMs overlap their neighbours' prologues",
                          "edges_per_graph_profiled_step": Ep_prof},
+            "roofline_hbm": hbm_roofline(recs, peaks, D),
         }
         if args.cpu_baseline and world == 1:
-            v, med, threads = cpu_reference_throughput(args.cpu_sample, N, D, train, steps=3, warmup=1)
-            line["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_sample} graphs x {N} nodes, {mode}, fp32 torch CPU, median of 3 "
-                                              f"({med * 1e3:.0f} ms per sample)"}
+            v, med, threads, kind = cpu_reference_throughput(args.cpu_sample, N, D, train, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": threads, "kind": kind,
+                                    "sample": cpu_sample_note(kind, args.cpu_sample, N, mode, threads, med) + ", median of 3"}
+            if args.ref_eager:
+                try:
+                    from oracle import reference_arm
+                    if reference_arm.available():
+                        ve, mede = reference_arm.time_reference(D, N, 256, train, edge_dropout=train, steps=3, warmup=2,
+                                                                device=str(dev), vector_rp=True)
+                        line["reference_eager_b200"] = {
+                            "value": ve, "unit": "graphs/s", "ms_per_sample": mede * 1e3,
+                            "sample": "the reference modules in torch eager (cuBLAS) on the same B200, fp32, 256 graphs per step "
+                                      "(the [Et, D/8, D/8] attention tensors bound the chunk), compute_RP vectorised; informative"}
+                except Exception as exc:                     # informative column only
+                    line["reference_eager_b200"] = {"unavailable": repr(exc)[:200]}
         _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -355,6 +451,15 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128, help="graphs per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-clocks", dest="clocks", action="store_false", help="(experiments) skip the nvidia-smi sampler")
+    ap.add_argument("--no-optimizer", dest="optimizer", action="store_false",
+                    help="(A/B) leave the Adam step + operand re-pack out of the training step")
+    ap.add_argument("--boundary", default="fresh", choices=["fresh", "attached"],
+                    help="fresh: the model receives an un-annotated int64 edge_index every step (the drop-in boundary); "
+                         "attached: the caller builds the GraphBatch and annotates the tensor (A/B)")
+    ap.add_argument("--validation", default="async", choices=["async", "sync"],
+                    help="edge_index validation read-back: async (checked one step late) or sync (one event wait per step)")
+    ap.add_argument("--no-ref-eager", dest="ref_eager", action="store_false",
+                    help="skip the informative reference-in-torch-eager-on-the-GPU column")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON): native libraries that write to file descriptor 1 on their own (NCCL
     # prints its version banner there) are pointed at stderr for the duration of the run.

@@ -52,6 +52,20 @@ int64_t rpg_launch_count(void);
 int rpg_profile_begin(void);
 int rpg_profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches,
                     double* nt_flops, double* tn_flops);
+/* Per-launch records of the same profiling window, for EVERY kernel class of the path (rpg_profile_records drains what
+ * rpg_profile_begin .. the last launch collected and ends the window; it synchronises on the recorded events).
+ * cls: RPG_PROF_*; ms: CUDA-event duration on the launch stream; flops / bytes: executed FLOPs and ALGORITHMIC bytes
+ * of the launch (DESIGN.md section 5 gives the per-unit figures); M, N, K: GEMM shape (0 otherwise).
+ * While a window is open every kernel is launched WITHOUT programmatic dependent launch, so that consecutive kernels do
+ * not overlap and an event pair brackets exactly one kernel.                                           */
+enum { RPG_PROF_GEMM_NT = 0, RPG_PROF_GEMM_TN = 1, RPG_PROF_SEGMENT_SUM = 2, RPG_PROF_ATTENTION_FWD = 3,
+       RPG_PROF_ATTENTION_BWD = 4, RPG_PROF_EDGE_INIT = 5, RPG_PROF_REDUCE = 6, RPG_PROF_OTHER = 7, RPG_PROF_CLASSES = 8 };
+typedef struct {
+  int32_t cls, M, N, K;
+  float ms;
+  double flops, bytes;
+} rpg_prof_rec_t;
+int rpg_profile_records(rpg_prof_rec_t* out, int max_records, int* n_records);
 /* Device properties the host side sizes grids with (SM count etc.); also proves the .so loads. */
 int rpg_device_sm_count(int device, int* sm_count);
 
@@ -107,6 +121,15 @@ typedef struct {
  * graph's node range. */
 int64_t rpg_per_graph_tables_words(int G, int N, int Ep);
 int rpg_per_graph_tables(const int64_t* edge_index, int G, int N, int Ep, int32_t* tables, int32_t* bad, rpg_stream_t stream);
+
+/* Template tables of a batch of G IDENTICAL graphs built on the device in one launch from the template endpoints
+ * tmpl_src / tmpl_dst (device int32 [Ep], as rpg_validate_edge_index extracts them): no host round trip between
+ * receiving a fresh edge_index and launching the layer.  `tables`: rpg_template_tables_words(N, Ep) int32 words,
+ *   src | dst | in_ptr | in_idx | out_ptr | out_idx | min_ptr | min_idx | max_ptr | max_idx | inv_deg | deg | has_in
+ * (edge tables Ep words, ptr tables N + 1, node tables N; each rounded up to a multiple of 4 words; CSR order = edge
+ * order within a node, i.e. a stable counting sort -- identical to the host-built tables).  N <= 1024, Ep <= 65536. */
+int64_t rpg_template_tables_words(int N, int Ep);
+int rpg_template_tables(const int32_t* tmpl_src, const int32_t* tmpl_dst, int N, int Ep, int32_t* tables, rpg_stream_t stream);
 
 /* The batched edge_index of the template (what PyG's Batch hands the model, train.py:24,132), on the device:
  * edge_index [2, G*Ep] int64 with column g*Ep + k = (g*N + src[k], g*N + dst[k]). */
@@ -207,7 +230,7 @@ int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int
 int rpg_wgrad_bias(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R,
                    float* ws, float* out, int ldo, float* bias, rpg_stream_t stream);
 /* sizeof / offsetof probes so a foreign-language mirror of the structs can verify its layout.      */
-void rpg_struct_sizes(int32_t* out10);
+void rpg_struct_sizes(int32_t* out16);   /* 13 values used, 16 slots */
 
 /* out[r, c] (+)= sum_s partial[s, r, c]  -- deterministic second stage of the TN split.            */
 int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols,
@@ -237,6 +260,31 @@ int rpg_reduce_splits_batch(const rpg_reduce_batch_t* batch, rpg_stream_t stream
  * my_gnn_layer.py:232,280,284 into per-source blocks and to build the dgrad (transposed) copies. */
 int rpg_pack_weight(const float* src, int ld_src, int r0, int c0, int rows, int cols,
                     rpg_bf16* dst, int ld_dst, int transpose, rpg_stream_t stream);
+
+/* Many rpg_pack_weight windows in ONE launch (a training step re-packs every operand after optimizer.step()):
+ * descriptor i converts the rows x cols window at (r0, c0) of the fp32 matrix src (pitch ld_src) into dst (pitch ld_dst),
+ * transposed if `transpose`; dst is bf16, or fp32 when dst_f32 != 0 (plain strided copy: head matrices, bias vectors),
+ * or the bf16 LOW plane bf16(w - float(bf16(w))) when lo_plane != 0 (fp32 mode).                          */
+#define RPG_PACK_BATCH_MAX 64
+typedef struct {
+  const float* src;
+  void* dst;
+  int32_t ld_src, r0, c0, rows, cols, ld_dst;
+  int16_t transpose, dst_f32, lo_plane, pad_;
+} rpg_pack_desc_t;
+typedef struct {
+  rpg_pack_desc_t d[RPG_PACK_BATCH_MAX];
+  int32_t n;
+} rpg_pack_batch_t;
+int rpg_pack_weights_batch(const rpg_pack_batch_t* batch, rpg_stream_t stream);
+
+/* Adam step (torch.optim.Adam semantics as used by train.py:211: L2 weight decay added to the gradient, bias
+ * correction, no amsgrad) over flat fp32 buffers of n elements, one launch:
+ *   g = grad * grad_scale + wd * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+ *   p -= lr / (1 - b1^t) * m / (sqrt(v / (1 - b2^t)) + eps)
+ * grad_scale folds the 1/world of a summed data-parallel gradient into the step.  step = t >= 1.          */
+int rpg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, int64_t step, rpg_stream_t stream);
 
 int rpg_cast_f32_to_bf16(const float* src, rpg_bf16* dst, int64_t n, rpg_stream_t stream);
 int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_t stream);

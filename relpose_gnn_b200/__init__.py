@@ -9,12 +9,14 @@ Everything executes in librpg_b200.so (C ABI: include/rpg.h).  Importing this pa
 calling any op without the built library or without CUDA tensors raises.
 """
 from . import graph  # noqa: F401
-from .graph import (GraphBatch, apply_edge_mask, attach, batched_edge_index, edge_dropout_keep, fc_template,  # noqa: F401
-                    knn_graph)
+from . import parallel  # noqa: F401
+from .graph import (GraphBatch, apply_edge_mask, attach, batched_edge_index, check_pending, edge_dropout_keep,  # noqa: F401
+                    fc_template, knn_graph, mask_edge_index, set_validation)
 from .layers import simpleConv, simpleConvEdge, simpleConvEdge_upt  # noqa: F401
 from .evaluation import compose_query_pose, pose_errors, qexp, save_poses  # noqa: F401
 from .feed import DeviceFeeder, ScalarReadback  # noqa: F401
 from .model import PoseNetCriterion, RelPoseGNN  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["DeviceFeeder", "ScalarReadback", "apply_edge_mask", "compose_query_pose", "pose_errors", "save_poses", "qexp", "knn_graph", "simpleConv", "simpleConvEdge", "simpleConvEdge_upt", "RelPoseGNN", "PoseNetCriterion", "GraphBatch", "attach", "batched_edge_index",
+__all__ = ["FusedAdam", "mask_edge_index", "set_validation", "check_pending", "DeviceFeeder", "ScalarReadback", "apply_edge_mask", "compose_query_pose", "pose_errors", "save_poses", "qexp", "knn_graph", "simpleConv", "simpleConvEdge", "simpleConvEdge_upt", "RelPoseGNN", "PoseNetCriterion", "GraphBatch", "attach", "batched_edge_index",
            "edge_dropout_keep", "fc_template", "graph"]

@@ -79,6 +79,26 @@ class LayerGrads(C.Structure):
         "g_att_W_w", "g_att_W_b")]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [("src", P), ("dst", P), ("ld_src", C.c_int32), ("r0", C.c_int32), ("c0", C.c_int32), ("rows", C.c_int32),
+                ("cols", C.c_int32), ("ld_dst", C.c_int32), ("transpose", C.c_int16), ("dst_f32", C.c_int16),
+                ("lo_plane", C.c_int16), ("pad_", C.c_int16)]
+
+
+PACK_BATCH_MAX = 64
+
+
+class PackBatch(C.Structure):
+    _fields_ = [("d", PackDesc * PACK_BATCH_MAX), ("n", C.c_int32)]
+
+
+class ProfRec(C.Structure):
+    _fields_ = [("cls", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ms", C.c_float),
+                ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+PROF_CLASSES = ("gemm_nt", "gemm_tn", "segment_sum", "attention_fwd", "attention_bwd", "edge_init", "reduce", "other")
+
 # name -> (restype, argtypes); every symbol include/rpg.h declares
 SIGNATURES = {
     "rpg_last_error_string": (C.c_char_p, []),
@@ -88,6 +108,11 @@ SIGNATURES = {
     "rpg_profile_begin": (I, []),
     "rpg_profile_end": (I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I), C.POINTER(I),
                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rpg_profile_records": (I, [C.POINTER(ProfRec), I, C.POINTER(I)]),
+    "rpg_template_tables_words": (I64, [I, I]),
+    "rpg_template_tables": (I, [P, P, I, I, P, P]),
+    "rpg_pack_weights_batch": (I, [C.POINTER(PackBatch), P]),
+    "rpg_adam_step": (I, [P, P, P, P, I64, F, F, F, F, F, F, I64, P]),
     "rpg_validate_edge_index": (I, [P, I64, I, I, I, P, P, P, P]),
     "rpg_selection_patterns": (I, [P, I, I, I, I, P, P]),
     "rpg_gemm": (I, [C.POINTER(Gemm), P]),
@@ -147,11 +172,12 @@ _lock = threading.Lock()
 
 
 def _check_layout(lib):
-    probe = (C.c_int32 * 10)()
+    probe = (C.c_int32 * 16)()
     lib.rpg_struct_sizes(probe)
     want = [C.sizeof(Graph), C.sizeof(Gemm), C.sizeof(LayerWeights), C.sizeof(LayerActs), C.sizeof(LayerGrads),
             Gemm.out_f32.offset, LayerGrads.g_mlp0_w.offset, LayerWeights.b1e.offset,
-            C.sizeof(LayerWeightsSplit), C.sizeof(LayerActsSplit)]
+            C.sizeof(LayerWeightsSplit), C.sizeof(LayerActsSplit), C.sizeof(PackDesc), C.sizeof(PackBatch),
+            C.sizeof(ProfRec), 0, 0, 0]
     if list(probe) != want:
         raise RpgError(f"ctypes mirrors out of sync with include/rpg.h: library {list(probe)} vs python {want}")
 

@@ -19,12 +19,16 @@ typedef __nv_bfloat16 bf16;
 // Raises a kernel's dynamic shared-memory limit once per size class.  Called from the forward thread and from autograd's
 // backward thread: the cached limit is guarded by a mutex.
 static std::mutex g_smem_mu;
+struct SmemLimit { size_t bytes[64]; SmemLimit() { for (auto& b : bytes) b = 48 * 1024; } };
 template <typename K>
-static void ensure_dyn_smem(K kern, size_t bytes, size_t* configured) {
+static void ensure_dyn_smem(K kern, size_t bytes, SmemLimit* configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);                          // the opt-in is a per-device attribute of the function
+    if (dev < 0 || dev >= 64) dev = 0;
     std::lock_guard<std::mutex> lk(g_smem_mu);
-    if (bytes > *configured) {
+    if (bytes > configured->bytes[dev]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        *configured = bytes;
+        configured->bytes[dev] = bytes;
     }
 }
 
@@ -1437,6 +1441,8 @@ int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy,
     if (!gtp || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd: bad arguments");
     if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
+    ProfScope prof(RPG_PROF_ATTENTION_FWD, (double)Et * c * (12.0 + 2.0 + (y_lo ? 2.0 : 0.0) + (aux ? 16.0 : 0.0)), as_stream(stream),
+                   (double)Et * c * c);          // "flops" field = exp evaluations (the kernel is MUFU-bound)
     if (aux)
         launch_pdl((attention_fwd_kernel<256, true>), dim3(grid), dim3(ATT_WARPS * 32), 0, as_stream(stream), gtp, Et, c, reinterpret_cast<bf16*>(y), ldy,
                                                                                       reinterpret_cast<bf16*>(y_lo), aux);
@@ -1451,9 +1457,11 @@ int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_
     if (!gtp || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd: bad arguments");
     if (c % 4 || c < 4 || c > 512) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c must be a multiple of 4 in [4,512]");
     const size_t smem = (size_t)ATT_WARPS * 8 * c * sizeof(float);
-    static size_t configured = 48 * 1024;
+    static SmemLimit configured;
     ensure_dyn_smem(attention_bwd_kernel, smem, &configured);
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
+    ProfScope prof(RPG_PROF_ATTENTION_BWD, (double)Et * c * (12.0 + 6.0 + (aux ? 16.0 : 0.0)) + (double)graph->G * graph->N * c * 4.0,
+                   as_stream(stream), (double)Et * c * c * (aux ? 1.0 : 2.0));
     launch_pdl(attention_bwd_kernel, dim3(grid), dim3(ATT_WARPS * 32), smem, as_stream(stream), gtp, dyn, ld_dyn, graph->dst, graph->Ep, graph->N,
                                                                            Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp, aux);
     return check_launch("attention_bwd_kernel");
@@ -1466,6 +1474,8 @@ static int launch_segment(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int 
     const long long Nt = (long long)g->G * g->N;
     const bool small = Nt * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
     const bool plain = !mask && !v_lo && !out_lo;
+    // algorithmic bytes: every edge row of the CSR read once, every node row written once
+    ProfScope prof(RPG_PROF_SEGMENT_SUM, ((double)g->G * g->Ep * (mask ? 2 : 1) * (v_lo ? 2 : 1) + (double)Nt * (out_lo ? 2 : 1)) * D * 2.0, s);
     auto kern = small ? (plain ? segment_sum_kernel<unsigned, true> : segment_sum_kernel<unsigned, false>)
                       : (plain ? segment_sum_kernel<long long, true> : segment_sum_kernel<long long, false>);
     launch_pdl(kern, dim3(grid_for(Nt * (D / 8), 256)), dim3(256), 0, s, reinterpret_cast<const bf16*>(v), ldv,
@@ -1504,6 +1514,8 @@ int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const
     if (!pminmax || !bias || !graph || !e0 || D % 8 || ldp % 8 || lde % 8) return set_error(RPG_E_ARG, "edge_init_fwd: bad arguments");
     const long long Et = (long long)graph->G * graph->Ep;
     const bool small = Et * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
+    ProfScope prof(RPG_PROF_EDGE_INIT, (double)Et * D * 2.0 + (e0_bits ? (double)Et * D / 8 : 0.0) + (double)graph->G * graph->N * 2 * D * 2.0,
+                   as_stream(stream));
     auto kern = small ? edge_init_fwd_kernel<unsigned> : edge_init_fwd_kernel<long long>;
     launch_pdl(kern, dim3(grid_for(Et * (D / 8), 256)), dim3(256), 0, as_stream(stream),
         reinterpret_cast<const bf16*>(pminmax), ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D,
@@ -1522,8 +1534,9 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
                  uint64_t seed, float p_drop, const float* w6, const float* b6, float* pose, rpg_stream_t stream) {
     if (!feat || !w6 || !b6 || !pose || rows <= 0 || D % 8 || ldf % 8) return set_error(RPG_E_ARG, "head_fwd: bad arguments");
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
-    const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
     const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
+    // explicit masks: F.dropout's 1 / (1 - p); seeded: the rate actually applied (p quantised to 1/256), so E[out] = in
+    const float scale = keep ? 1.f / (1.f - p_drop) : (use_seed ? 256.f / (256.f - (float)thresh) : 1.f);
     const int grid = grid_for((rows + 1) / 2, HEAD_WARPS, 148 * 8);
     const bf16* f = reinterpret_cast<const bf16*>(feat);
     const bf16* fl = reinterpret_cast<const bf16*>(feat_lo);
@@ -1538,7 +1551,7 @@ int rpg_head_fwd(const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t
     } else {
         const size_t smem = (size_t)6 * D * sizeof(float);
         if (D > 2048) return set_error(RPG_E_UNSUPPORTED, "head_fwd: D > 2048");
-        static size_t configured = 48 * 1024;
+        static SmemLimit configured;
         ensure_dyn_smem(head_fwd_kernel<0, false>, smem, &configured);
         launch_pdl((head_fwd_kernel<0, false>), dim3(grid), dim3(HEAD_WARPS * 32), smem, st, f, ldf, rows, D, keep, seed, thresh, use_seed, scale, w6, b6, pose, fl);
     }
@@ -1559,13 +1572,14 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     float* dw_part = ws;
     float* db_part = ws + (size_t)blocks * 6 * D;
     const int use_seed = (!keep && p_drop > 0.f) ? 1 : 0;
-    const float scale = (keep || use_seed) ? 1.f / (1.f - p_drop) : 1.f;
     const uint32_t thresh = (uint32_t)(p_drop * 256.0f + 0.5f);
+    // explicit masks: F.dropout's 1 / (1 - p); seeded: the rate actually applied (p quantised to 1/256), so E[out] = in
+    const float scale = keep ? 1.f / (1.f - p_drop) : (use_seed ? 256.f / (256.f - (float)thresh) : 1.f);
     const int ct = D / 8;
     if (ct > HEADB_THREADS) return set_error(RPG_E_UNSUPPORTED, "head_bwd: D > 2048");
     const int phases = HEADB_THREADS / ct;
     const size_t smem = ((size_t)(phases - 1) * 48 * ct + (size_t)phases * 6) * sizeof(float);
-    static size_t configured = 48 * 1024;
+    static SmemLimit configured;
     ensure_dyn_smem(head_bwd_kernel, smem, &configured);
     cudaStream_t s = as_stream(stream);
     launch_pdl(head_bwd_kernel, dim3(blocks), dim3(HEADB_THREADS), smem, s, dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed,

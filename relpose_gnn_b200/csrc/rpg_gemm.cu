@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -814,48 +815,89 @@ static int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t cols, ui
     return 0;
 }
 
-// ---- per-launch event timing (enabled only between rpg_profile_begin / rpg_profile_end)
-struct ProfRec { cudaEvent_t e0, e1; int mode; double flops; int M, N, K, flags; };
+// ---- per-launch event timing (enabled only between rpg_profile_begin and rpg_profile_end / rpg_profile_records)
+struct ProfRec { cudaEvent_t e0, e1; int cls; double flops, bytes; int M, N, K, flags; };
 static std::mutex g_prof_mu;
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfRec> g_prof;
+
+bool prof_active() { return g_prof_on.load(std::memory_order_relaxed); }
 
 int profile_begin() {
     std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.clear();
     g_prof_on = true;
     return 0;
 }
 
-int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops) {
+int prof_open(int cls, double flops, double bytes, int M, int N, int K, cudaStream_t s) {
+    if (!prof_active()) return -1;
+    ProfRec rec;
+    cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
+    rec.cls = cls; rec.flops = flops; rec.bytes = bytes; rec.M = M; rec.N = N; rec.K = K; rec.flags = 0;
+    cudaEventRecord(rec.e0, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+    return (int)g_prof.size() - 1;
+}
+
+void prof_close(int slot, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot >= 0 && slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, s);
+}
+
+// Drains the window: every record with its measured duration.
+int profile_records(rpg_prof_rec_t* out, int max_records, int* n_records) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = false;
-    double ms[2] = {0, 0}, fl[2] = {0, 0};
-    int n[2] = {0, 0};
+    int n = 0;
     for (auto& r : g_prof) {
         cudaEventSynchronize(r.e1);
         float t = 0.f;
         cudaEventElapsedTime(&t, r.e0, r.e1);
-        ms[r.mode] += t; fl[r.mode] += r.flops; n[r.mode]++;
+        if (out && n < max_records) {
+            out[n].cls = r.cls; out[n].M = r.M; out[n].N = r.N; out[n].K = r.K;
+            out[n].ms = t; out[n].flops = r.flops; out[n].bytes = r.bytes;
+        }
+        ++n;
         if (getenv("RPG_PROFILE_VERBOSE"))
-            fprintf(stderr, "[rpg gemm] %s M=%d N=%d K=%d flags=%s%s%s%s%s%s%s%s%s  %.1f us  %.0f TFLOP/s\n", r.mode ? "TN" : "NT", r.M, r.N,
-                    r.K, (r.flags >> 8) ? "onehot-gather " : "", r.flags & 1 ? "bias " : "", r.flags & 2 ? "gadd0 " : "", r.flags & 4 ? "gadd1 " : "",
-                    r.flags & 8 ? "resid " : "", r.flags & 16 ? "mask " : "", r.flags & 32 ? "out " : "",
-                    r.flags & 64 ? "out_relu " : "", r.flags & 128 ? "out_f32 " : "", t * 1e3, r.flops / (t * 1e-3) / 1e12);
+            fprintf(stderr, "[rpg prof] cls=%d M=%d N=%d K=%d  %.1f us  %.0f TFLOP/s  %.0f GB/s\n", r.cls, r.M, r.N, r.K, t * 1e3,
+                    r.flops / (t * 1e-3) / 1e12, r.bytes / (t * 1e-3) / 1e9);
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
     g_prof.clear();
+    if (n_records) *n_records = n;
+    return 0;
+}
+
+int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops) {
+    std::vector<rpg_prof_rec_t> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        recs.resize(g_prof.size());
+    }
+    int n = 0;
+    profile_records(recs.data(), (int)recs.size(), &n);
+    double ms[2] = {0, 0}, fl[2] = {0, 0};
+    int cnt[2] = {0, 0};
+    for (int i = 0; i < n && i < (int)recs.size(); ++i) {
+        if (recs[i].cls > RPG_PROF_GEMM_TN) continue;
+        ms[recs[i].cls] += recs[i].ms; fl[recs[i].cls] += recs[i].flops; cnt[recs[i].cls]++;
+    }
     if (nt_ms) *nt_ms = ms[0];
     if (tn_ms) *tn_ms = ms[1];
-    if (nt_launches) *nt_launches = n[0];
-    if (tn_launches) *tn_launches = n[1];
+    if (nt_launches) *nt_launches = cnt[0];
+    if (tn_launches) *tn_launches = cnt[1];
     if (nt_flops) *nt_flops = fl[0];
     if (tn_flops) *tn_flops = fl[1];
     return 0;
 }
 
-static int g_sm_count = 0;
-static std::once_flag g_attr_once;
+static thread_local int g_sm_count = 0;
+static std::mutex g_attr_mu;
+static bool g_attr_done[64] = {false};
+static int g_sm_counts[64] = {0};
 static int g_cluster = 2;       // CTAs per cluster (1 or 2); see rpg_set_gemm_cluster
 
 int set_gemm_cluster(int cl) {
@@ -865,6 +907,21 @@ int set_gemm_cluster(int cl) {
 }
 
 static int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static void set_smem_attrs() {
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
 
 int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (!g) return set_error(RPG_E_ARG, "rpg_gemm: null descriptor");
@@ -941,7 +998,8 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
             return set_error(RPG_E_ARG, "rpg_gemm: fused dropout needs NT mode, an out_relu output, the plain epilogue, 0 < p < 1");
         p.drop_seed = g->drop_seed;
         p.drop_thresh = (uint32_t)(g->drop_p * 256.0f + 0.5f);
-        p.drop_scale = 1.f / (1.f - g->drop_p);
+        if (p.drop_thresh > 255u) p.drop_thresh = 255u;
+        p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);      // the rate actually applied (p quantised to 1/256): E[out] = in
     }
     p.mask_bits = g->mask_bits; p.mask_bits_ld = g->mask_bits_ld;
     p.out_bits = g->out_bits; p.out_bits_ld = g->out_bits_ld;
@@ -984,42 +1042,42 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     if (p.out_relu_lo && (rc = make_tmap(&tmaps.out_relu_lo, p.out_relu_lo, p.N, p.M, p.ldo, 64, 32))) return rc;
     if (p.out_f32 && (rc = make_tmap_f32_3d(&tmaps.out_f32, p.out_f32, p.N, p.M, p.splits, p.ldo_f32, p.split_stride))) return rc;
 
-    std::call_once(g_attr_once, [] {
+    // the shared-memory opt-in is a per-device function attribute: set it once on every device the library is used on
+    {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    });
+        std::lock_guard<std::mutex> lk(g_attr_mu);
+        if (dev >= 0 && dev < 64 && !g_attr_done[dev]) {
+            cudaDeviceGetAttribute(&g_sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
+            set_smem_attrs();
+            g_attr_done[dev] = true;
+        }
+        g_sm_count = g_sm_counts[dev < 64 && dev >= 0 ? dev : 0];
+    }
     const int num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
     const int items = ((num_m_blocks + cl - 1) / cl) * num_n_blocks * p.splits;      // one item per cluster
     const int max_workers = g_sm_count / cl;
     const int grid = (items < max_workers ? items : max_workers) * cl;
-    ProfRec rec;
-    bool prof = false;
-    {
-        std::lock_guard<std::mutex> lk(g_prof_mu);
-        prof = g_prof_on;
-    }
+    const bool prof = prof_active();
+    int prof_slot = -1;
     if (prof) {
-        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1);
-        rec.mode = g->mode;
-        rec.flops = 2.0 * p.M * p.N * (g->mode == 0 ? (double)(p.total_kb + p.n_gseg) * BLOCK_K : (double)g->R);
-        rec.M = p.M; rec.N = p.N; rec.K = g->mode == 0 ? (p.total_kb + p.n_gseg) * BLOCK_K : g->R;
-        rec.flags = (p.bias ? 1 : 0) | (p.gadd[0] ? 2 : 0) | (p.gadd[1] ? 4 : 0) | (p.resid ? 8 : 0) | (p.mask ? 16 : 0) |
-                    (p.out ? 32 : 0) | (p.out_relu ? 64 : 0) | (p.out_f32 ? 128 : 0) | (p.n_gseg << 8);
-        cudaEventRecord(rec.e0, stream);
+        const double kdim = g->mode == 0 ? (double)(p.total_kb + p.n_gseg) * BLOCK_K : (double)g->R;
+        // algorithmic bytes of the launch: operands read once, results written once
+        double bytes = 0.0;
+        if (g->mode == 0) {
+            bytes = (double)p.M * p.total_kb * BLOCK_K * 2 + (double)p.N * kdim * 2;
+            if (p.out) bytes += (double)p.M * p.N * 2;
+            if (p.out_relu) bytes += (double)p.M * p.N * 2;
+            if (p.out_f32) bytes += (double)p.M * p.N * 4;
+            if (p.resid) bytes += (double)p.M * p.N * 2;
+            if (p.mask_bits) bytes += (double)p.M * p.N / 8;
+            if (p.out_bits) bytes += (double)p.M * p.N / 8;
+        } else {
+            bytes = (double)g->R * (p.M + p.N) * 2 + (double)p.splits * p.M * p.N * 4;
+        }
+        prof_slot = prof_open(g->mode == 0 ? RPG_PROF_GEMM_NT : RPG_PROF_GEMM_TN, 2.0 * p.M * p.N * kdim, bytes, p.M, p.N,
+                              (int)kdim, stream);
     }
     const bool ops = g->mode == 0 && (p.gadd[0] || p.gadd[1] || p.resid || p.mask);
     void (*kern)(GemmTmaps, GemmKParams);
@@ -1057,11 +1115,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmaps, p);
         (void)e;
     }
-    if (prof) {
-        cudaEventRecord(rec.e1, stream);
-        std::lock_guard<std::mutex> lk(g_prof_mu);
-        g_prof.push_back(rec);
-    }
+    if (prof_slot >= 0) prof_close(prof_slot, stream);
     return check_launch("gemm_tc_kernel");
 }
 

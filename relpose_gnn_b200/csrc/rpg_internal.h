@@ -20,6 +20,19 @@ int set_gemm_cluster(int cl);
 int profile_begin();
 int profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_launches, double* nt_flops, double* tn_flops);
 
+// Per-launch records for every kernel class (rpg_profile_records).  prof_open records the start event and returns a
+// slot (or -1 when no window is open); prof_close records the end event.  ProfScope brackets one launch.
+bool prof_active();
+int prof_open(int cls, double flops, double bytes, int M, int N, int K, cudaStream_t s);
+void prof_close(int slot, cudaStream_t s);
+int profile_records(rpg_prof_rec_t* out, int max_records, int* n_records);
+struct ProfScope {
+    int slot;
+    cudaStream_t s;
+    ProfScope(int cls, double bytes, cudaStream_t s_, double flops = 0.0) : slot(prof_open(cls, flops, bytes, 0, 0, 0, s_)), s(s_) {}
+    ~ProfScope() { if (slot >= 0) prof_close(slot, s); }
+};
+
 inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Programmatic dependent launch: every kernel of the library starts with griddepcontrol.launch_dependents +
@@ -35,7 +48,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && !prof_active()) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -201,6 +201,10 @@ void rpg_struct_sizes(int32_t* out) {
     out[7] = (int32_t)offsetof(rpg_layer_weights_t, b1e);
     out[8] = (int32_t)sizeof(rpg_layer_weights_split_t);
     out[9] = (int32_t)sizeof(rpg_layer_acts_split_t);
+    out[10] = (int32_t)sizeof(rpg_pack_desc_t);
+    out[11] = (int32_t)sizeof(rpg_pack_batch_t);
+    out[12] = (int32_t)sizeof(rpg_prof_rec_t);
+    out[13] = out[14] = out[15] = 0;
 }
 
 #define RPG_TRY(expr)            \

@@ -28,7 +28,7 @@ def compose_query_pose(pred_edges, poses_abs, edge_index, ref_node=0, pose_m=Non
     if not pred_edges.is_cuda:
         raise ValueError("relpose_gnn_b200.compose_query_pose needs CUDA tensors")
     g = graph_mod.from_edge_index(edge_index, poses_abs.size(0))
-    into0 = np.flatnonzero(g.dst_np == 0)
+    into0 = np.flatnonzero(g.host_template()[1] == 0)
     if ref_node >= into0.size:
         raise ValueError(f"ref_node {ref_node}: only {into0.size} edges end in node 0")
     ref_k = int(into0[ref_node])

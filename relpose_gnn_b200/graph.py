@@ -231,6 +231,13 @@ class GraphBatch:
     def byref(self):
         return C.byref(self.struct)
 
+    def host_template(self):
+        """(src, dst) int32 numpy arrays of the template; device-built batches read them back once (synchronises)."""
+        if self.src_np is None:
+            self.src_np = self._tables["src"].cpu().numpy().copy()
+            self.dst_np = self._tables["dst"].cpu().numpy().copy()
+        return self.src_np, self.dst_np
+
     def edge_index(self):
         """int64 [2, G*Ep] PyG-style batched edge_index, built on the device from the template tables."""
         if getattr(self, "_edge_index", None) is not None:
@@ -244,7 +251,8 @@ class GraphBatch:
         return ei
 
     def with_graphs(self, n_graphs):
-        return GraphBatch(self.src_np, self.dst_np, n_graphs, self.N, self.device)
+        src, dst = self.host_template()
+        return GraphBatch(src, dst, n_graphs, self.N, self.device)
 
     @classmethod
     def fully_connected(cls, n_graphs, n_nodes, device, keep_undirected=None):
@@ -284,6 +292,29 @@ def apply_edge_mask(t, keep_undirected, n_graphs):
     return out
 
 
+def mask_edge_index(edge_index, keep_undirected, n_graphs):
+    """train.py:238-245 (documented intent: `data.edge_index[:, surviving_edges]`) on the device: the batched
+    edge_index [2, G*E] of full templates thinned by the batch-shared undirected keep mask -> [2, G*E_kept].
+    Two row-selection launches; the mask travels as kernel parameters (no copy engine, no synchronisation)."""
+    if not edge_index.is_cuda or edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("edge_index must be a CUDA int64 tensor of shape [2, E]")
+    keep = np.asarray(keep_undirected, dtype=bool)
+    keep2 = np.concatenate([keep, keep])
+    Ep_full = keep2.size
+    if edge_index.size(1) != n_graphs * Ep_full:
+        raise ValueError("mask_edge_index: columns must equal graphs x directed edges of the full template")
+    idx = np.flatnonzero(keep2).astype(np.int32)
+    ei = edge_index.contiguous()
+    out = torch.empty(2, n_graphs * idx.size, dtype=torch.int64, device=ei.device)
+    idx_dev = _uploader.upload(idx, ei.device)
+    lib = _lib.load()
+    stream = C.c_void_p(torch.cuda.current_stream(ei.device).cuda_stream)
+    for r in range(2):
+        _lib.check(lib.rpg_edge_mask_apply(ei[r].data_ptr(), n_graphs, Ep_full, int(idx.size), idx_dev.data_ptr(), 8,
+                                           out[r].data_ptr(), stream), "rpg_edge_mask_apply")
+    return out
+
+
 def knn_graph(x, k, batch=None, loop=False, num_nodes_per_graph=None):
     """torch_cluster.knn_graph as the reference calls it (posenet.py:1043-1050: `knn_graph(x, k, batch=data.batch,
     loop=False)`) for batches of equally sized graphs: int64 edge_index [2, G*N*k], edges (neighbour -> centre) grouped
@@ -308,10 +339,109 @@ def knn_graph(x, k, batch=None, loop=False, num_nodes_per_graph=None):
     return ei
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# edge_index -> GraphBatch.  A fresh edge_index (what the PyG loader + train.py:238-245 hand the model every step) takes
+# the DEVICE path: the batch shape (G, N) of the previous batch with the same number of node rows is the guess, one
+# kernel validates every column against it and extracts the template, a second builds the template tables, two more the
+# one-hot selection tiles -- no eager torch ops and no host round trip.  The only thing the host needs back is the
+# 4-byte count of violating columns:
+#   validation "sync"  (default): read at once through a pinned slot (ONE small event wait); a failed guess falls back to
+#                                 the full inference below, so the semantics are those of a cold call.
+#   validation "async" (training loops): the count is read when its copy has completed -- at the next call or at
+#                                 check_pending() -- and a violation raises ValueError THEN (one step late).
+# The first call for a shape infers (G, N) from the tensor itself (eager ops + read-backs; once per shape).
+_validation_mode = "sync"
+_shape_cache = {}            # (node rows, device) -> (G, N)
+_pending = []                # async validation: (event, pinned count, description, keep-alive)
+_pinned_counts = []          # recycled pinned 4-byte slots
+
+
+def set_validation(mode):
+    """'sync' or 'async' (see above).  Returns the previous mode."""
+    global _validation_mode
+    if mode not in ("sync", "async"):
+        raise ValueError("validation mode must be 'sync' or 'async'")
+    prev, _validation_mode = _validation_mode, mode
+    return prev
+
+
+def check_pending(block=False):
+    """Raises ValueError if an asynchronously validated edge_index turned out not to be a batched uniform template.
+    block=True waits for every outstanding check (call it before trusting the results of the last steps)."""
+    keep = []
+    err = None
+    for ev, host, what, alive in _pending:
+        if block:
+            ev.synchronize()
+        if ev.query():
+            if int(host[0]) and err is None:
+                err = f"{what}: {int(host[0])} edge_index columns violate the batched-template property (detected asynchronously)"
+            _pinned_counts.append(host)
+        else:
+            keep.append((ev, host, what, alive))
+    _pending[:] = keep
+    if err:
+        raise ValueError(err)
+
+
+def _device_graph(ei, G, N, Ep):
+    """GraphBatch of G copies of the template found in columns [0, Ep) of `ei`, tables built on the device.
+    Returns (graph, bad) with bad = device int32 [1] count of violating columns (not yet read)."""
+    lib = _lib.load()
+    dev = ei.device
+    Et = ei.size(1)
+    words = lib.rpg_template_tables_words(N, Ep)
+    al = lambda v: (v + 3) // 4 * 4                                       # noqa: E731
+    buf = torch.empty(words + 2 * al(Ep) + 4, dtype=torch.int32, device=dev)
+    tsrc, tdst = buf[words:words + Ep], buf[words + al(Ep):words + al(Ep) + Ep]
+    bad = buf[words + 2 * al(Ep):words + 2 * al(Ep) + 1]
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib.rpg_validate_edge_index(ei.data_ptr(), Et, G, N, Ep, tsrc.data_ptr(), tdst.data_ptr(), bad.data_ptr(),
+                                           stream), "rpg_validate_edge_index")
+    _lib.check(lib.rpg_template_tables(tsrc.data_ptr(), tdst.data_ptr(), N, Ep, buf.data_ptr(), stream), "rpg_template_tables")
+    self = GraphBatch.__new__(GraphBatch)
+    self.G, self.N, self.Ep, self.device = G, N, Ep, dev
+    self.src_np = self.dst_np = None
+    self._edge_index = ei
+    tables, off = {"_buf": buf}, 0
+    for name, size, is_f in (("src", Ep, 0), ("dst", Ep, 0), ("in_ptr", N + 1, 0), ("in_idx", Ep, 0),
+                             ("out_ptr", N + 1, 0), ("out_idx", Ep, 0), ("min_ptr", N + 1, 0), ("min_idx", Ep, 0),
+                             ("max_ptr", N + 1, 0), ("max_idx", Ep, 0), ("inv_deg", N, 1), ("deg", N, 1), ("has_in", N, 1)):
+        t = buf[off:off + size]
+        tables[name] = t.view(torch.float32) if is_f else t
+        off += al(size)
+    s = _lib.Graph()
+    s.G, s.N, s.Ep = G, N, Ep
+    for name, t in tables.items():
+        if name != "_buf":
+            setattr(s, name, t.data_ptr())
+    g = int(np.gcd(128, Ep))
+    npat = Ep // g
+    if ((Ep - g + 127) // Ep) * N + N <= 64:                  # same feasibility rule as GraphBatch._build_tables
+        for name, tab in (("sel_src", "src"), ("sel_dst", "dst")):
+            sel = torch.empty(npat * 128, 64, dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.rpg_selection_patterns(tables[tab].data_ptr(), Ep, N, g, npat, sel.data_ptr(), stream),
+                       "rpg_selection_patterns")
+            tables[name] = sel
+        s.sel_src, s.sel_dst = tables["sel_src"].data_ptr(), tables["sel_dst"].data_ptr()
+        s.sel_patterns, s.sel_div = npat, g
+    self._tables = tables
+    self.struct = s
+    return self, bad
+
+
+def _read_count_async(bad):
+    host = _pinned_counts.pop() if _pinned_counts else torch.empty(1, dtype=torch.int32).pin_memory()
+    host.copy_(bad, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(bad.device))
+    return ev, host
+
+
 def from_edge_index(edge_index, n_node_rows):
-    """Infers (G, N, Ep), validates on the device that edge_index is a batched uniform template and returns
-    the GraphBatch.  Raises ValueError otherwise (no PyG-scatter fallback).  One small
-    device->host read per distinct edge_index tensor; the result is cached as an attribute of the tensor."""
+    """Returns the GraphBatch of a batched edge_index (see the block comment above); raises ValueError if it is not a
+    batch of G copies of one per-graph template (no PyG-scatter fallback).  The result is cached as an
+    attribute of the tensor."""
     g = getattr(edge_index, "rpg_graph", None)
     if g is not None and getattr(edge_index, "rpg_graph_version", edge_index._version) == edge_index._version:
         if g.n_node_rows != n_node_rows or g.n_edge_rows != edge_index.size(1):
@@ -324,6 +454,35 @@ def from_edge_index(edge_index, n_node_rows):
     if edge_index.size(1) == 0:
         raise ValueError("empty edge_index: the layer needs at least one edge per graph")
     ei = edge_index.contiguous()
+    Et = ei.size(1)
+    if _pending:
+        check_pending()
+    key = (int(n_node_rows), str(ei.device))
+    guess = _shape_cache.get(key)
+    g = None
+    if guess is not None and Et % guess[0] == 0 and guess[1] <= 1024 and Et // guess[0] <= 65536:
+        G_, N_ = guess
+        g, bad = _device_graph(ei, G_, N_, Et // G_)
+        ev, host = _read_count_async(bad)
+        if _validation_mode == "async":
+            _pending.append((ev, host, f"edge_index [2, {Et}] as {G_} graphs x {N_} nodes", g))
+        else:
+            ev.synchronize()
+            nbad = int(host[0])
+            _pinned_counts.append(host)
+            if nbad:
+                g = None                              # not that shape: infer from scratch
+    if g is None:
+        g = _infer_graph(ei, n_node_rows)
+        if g.G > 1:
+            _shape_cache[key] = (g.G, g.N)
+    edge_index.rpg_graph = g                      # cached on the tensor object itself
+    edge_index.rpg_graph_version = edge_index._version
+    return g
+
+
+def _infer_graph(ei, n_node_rows):
+    """Cold path: infers (G, N, Ep) from the tensor and validates on the device (read-backs; once per batch shape)."""
     Et = ei.size(1)
     # Column Ep of a batched template equals column 0 shifted by N on both rows.  Candidates are the columns
     # with an equal, positive shift on both rows; the first one consistent with (Et, n_node_rows) is validated
@@ -355,6 +514,4 @@ def from_edge_index(edge_index, n_node_rows):
         raise ValueError("edge_index is not a batch of G copies of one per-graph edge template with node offset "
                          f"g*N ({bad} violating columns for the last candidate); per-graph edge sets are not "
                          "supported (no PyG-scatter fallback exists)")
-    edge_index.rpg_graph = g                      # cached on the tensor object itself
-    edge_index.rpg_graph_version = edge_index._version
     return g

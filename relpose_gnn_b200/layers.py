@@ -36,6 +36,11 @@ PARAM_ORDER_EDGE = tuple(n for n in PARAM_ORDER if not n.startswith("mlp_updatin
 _GRAD_FIELD_OF = dict(zip(PARAM_ORDER, _GRAD_FIELDS))
 
 
+def _invalidate_hook(module, _incompatible_keys):
+    """load_state_dict post-hook: checkpoints loaded through `.data` copies must not leave stale packed operands."""
+    module.invalidate_packed()
+
+
 class simpleEdgeModel(nn.Module):
     """Parameter container mirroring my_gnn_layer.py:224-239 (keeps the `edge_model.edge_mlp.*` keys)."""
 
@@ -89,7 +94,7 @@ class PackedLayerWeights:
     def refresh(self, mod):
         v1 = self.variant == 1
         p = {n: mod.get_parameter(n) for n in (PARAM_ORDER_EDGE if v1 else PARAM_ORDER)}
-        versions = tuple((q.data_ptr(), q._version) for q in p.values())
+        versions = (getattr(mod, "_pack_epoch", 0),) + tuple((q.data_ptr(), q._version) for q in p.values())
         if versions == self.versions:
             return self.struct
         for q in p.values():
@@ -98,7 +103,8 @@ class PackedLayerWeights:
         D, c, t = self.D, self.c, self.t
         W1e, W1m = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data
         W2e, W2m = p["edge_model.edge_mlp.2.weight"].data, p["mlp.2.weight"].data
-        pk = ops.pack_weight
+        q = ops.PackQueue()                                    # every window below converts in ONE launch
+        pk = q.add
         # mlp.0 columns: _upt = [x_j (src) | e'];  simpleConvEdge = [x_i (dst) | x_j (src) | e']  (my_gnn_layer.py:269,305)
         mj0, me0 = (D, 2 * D) if v1 else (0, D)
         # forward operands
@@ -114,7 +120,7 @@ class PackedLayerWeights:
         for i, nm in enumerate(("g", "theta", "phi")):
             pk(p[f"att.{nm}.weight"].data, t["Wgtp"][i * c:(i + 1) * c])
             pk(p[f"att.{nm}.weight"].data, t["WgtpT"][:, i * c:(i + 1) * c], transpose=True)
-            self.bgtp[i * c:(i + 1) * c].copy_(p[f"att.{nm}.bias"].data)
+            pk(p[f"att.{nm}.bias"].data.view(1, c), self.bgtp[i * c:(i + 1) * c].view(1, c))
         pk(p["att.W.weight"].data, t["WW"][:, :c])
         pk(p["att.W.weight"].data, t["WWI"][:, :c])
         # dgrad operands (transposes)
@@ -134,6 +140,7 @@ class PackedLayerWeights:
             pk(W2u, t["W2u"])
             pk(W2u, t["W2uT"], transpose=True)
             pk(W1u, t["W1uT"], transpose=True)
+        q.flush()
         s = self.struct
         s.D = D
         s.variant = self.variant
@@ -168,12 +175,13 @@ class PackedLayerWeightsSplit:
 
     def refresh(self, mod):
         p = {n: mod.get_parameter(n) for n in PARAM_ORDER}
-        versions = tuple((q.data_ptr(), q._version) for q in p.values())
+        versions = (getattr(mod, "_pack_epoch", 0),) + tuple((q.data_ptr(), q._version) for q in p.values())
         if versions == self.versions:
             return self.struct
         D, c, t = self.D, self.c, self.t
         W1e, W1m, W1u = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data, p["mlp_updating.0.weight"].data
-        pk3 = ops.pack_weight3
+        q = ops.PackQueue()
+        pk3 = q.add3
         pk3(W1e, t["Wn3"][0:D], c0=0, cols=D)
         pk3(W1e, t["Wn3"][D:2 * D], c0=D, cols=D)
         pk3(W1m, t["Wn3"][2 * D:3 * D], c0=0, cols=D)
@@ -183,11 +191,12 @@ class PackedLayerWeightsSplit:
         pk3(p["mlp.2.weight"].data, t["W2m3"])
         for i, nm in enumerate(("g", "theta", "phi")):
             pk3(p[f"att.{nm}.weight"].data, t["Wgtp3"][i * c:(i + 1) * c])
-            self.bgtp[i * c:(i + 1) * c].copy_(p[f"att.{nm}.bias"].data)
+            q.add(p[f"att.{nm}.bias"].data.view(1, c), self.bgtp[i * c:(i + 1) * c].view(1, c))
         pk3(p["att.W.weight"].data, t["WW3"], cols=c)        # K padded to pad64(c): the padding columns stay zero
         pk3(W1u, t["W1u3"][:, :3 * D], c0=0, cols=D)
         pk3(W1u, t["W1u3"][:, 3 * D:], c0=D, cols=D)
         pk3(p["mlp_updating.2.weight"].data, t["W2u3"])
+        q.flush()
         s = self.struct
         s.D = D
         for name, tensor in t.items():
@@ -393,11 +402,25 @@ class simpleConvEdge_upt(nn.Module):
         self.edge_model = simpleEdgeModel(in_channels, edge_channels, edge_channels)
         self.att = AttentionBlock(in_channels)
         self._pack_cache = {}
-        # "bf16" (default; forward + backward) or "fp32" (split-bf16 arithmetic, ~1e-5 relative; inference only for now)
+        self.register_load_state_dict_post_hook(_invalidate_hook)
+        # "bf16" (default; forward + backward) or "fp32" (split-bf16 arithmetic on the same kernels, ~1e-5 relative)
         self.precision = "bf16"
 
     _variant = 0
     _param_order = PARAM_ORDER
+    _pack_epoch = 0
+
+    def invalidate_packed(self):
+        """Forces the bf16 operand copies to be rebuilt at the next forward.  They follow `optimizer.step()`,
+        `load_state_dict` and every in-place op on a parameter automatically (version counters); writes that bypass
+        the counter -- `p.data.copy_()`, `nn.init.*(p.data)`, a custom optimizer kernel -- need this call."""
+        self._pack_epoch = self._pack_epoch + 1
+
+    def __getstate__(self):
+        # the packed operands and their ctypes structs are a cache: never pickled / deep-copied with the module
+        state = dict(self.__dict__)
+        state["_pack_cache"] = {}
+        return state
 
     def _packed(self, device):
         key = str(device)
@@ -471,6 +494,7 @@ class simpleConvEdge(simpleConvEdge_upt):
         self.edge_model = simpleEdgeModel(in_channels, edge_channels, edge_channels)
         self.att = AttentionBlock(in_channels)
         self._pack_cache = {}
+        self.register_load_state_dict_post_hook(_invalidate_hook)
         self.precision = "bf16"
 
     def forward(self, x, edge_index, edge_attr):
@@ -556,11 +580,23 @@ class simpleConv(nn.Module):
         self.aggr = "mean"
         self.mlp = Seq(Linear(2 * in_channels, out_channels), ReLU(), Linear(out_channels, out_channels))
         self._pack_cache = {}
+        self.register_load_state_dict_post_hook(_invalidate_hook)
+
+    _pack_epoch = 0
+
+    def invalidate_packed(self):
+        """See simpleConvEdge_upt.invalidate_packed."""
+        self._pack_epoch = self._pack_epoch + 1
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_pack_cache"] = {}
+        return state
 
     def _packed_conv(self, device):
         D = self.in_channels
         w1, w2 = self.mlp[0].weight, self.mlp[2].weight
-        key = (str(device), w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+        key = (str(device), self._pack_epoch, w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
         pk = self._pack_cache.get("pk")
         if pk is None or pk["key"] != key:
             for q in (w1, w2):

@@ -14,7 +14,8 @@ import torch
 from torch import nn
 
 from . import graph as graph_mod, ops
-from .layers import PARAM_ORDER, layer_backward_raw, layer_forward_raw, layer_forward_split_raw, simpleConvEdge_upt
+from .layers import (PARAM_ORDER, _invalidate_hook, layer_backward_raw, layer_forward_raw, layer_forward_split_raw,
+                     simpleConvEdge_upt)
 from .ops import BF16
 
 _HEADS = ("fc_xyz", "fc_wpqr", "fc_xyz_R", "fc_wpqr_R")
@@ -103,7 +104,8 @@ class _StackFn(torch.autograd.Function):
         # heads (posenet.py:1077-1086): gradient w.r.t. the pre-ReLU layer outputs (mask_relu)
         d_e = d_x = None
         if ctx.fused_heads:
-            scale = 1.0 / (1.0 - p_drop)
+            thresh = min(int(p_drop * 256.0 + 0.5), 255)
+            scale = 256.0 / (256.0 - thresh)       # the rate the seeded dropout actually applies (rpg_gemm_t.drop_p)
             xb_bits, eb_bits = ctx.head_bits
             if d_pose_e is not None:
                 d_e = ops.head_bwd_tc(d_pose_e.contiguous().float(), e_last, eb_bits, sw["w6eT"], scale,
@@ -163,7 +165,11 @@ class RelPoseGNN(nn.Module):
             nn.init.kaiming_normal_(m.weight.data)
             nn.init.constant_(m.bias.data, 0)
         self._stack_cache = {}
+        self.register_load_state_dict_post_hook(_invalidate_hook)
+        # Seed of the in-kernel feature dropout: a counter hashed together with the data-parallel rank, so that replicas
+        # draw different masks and consecutive steps draw unrelated ones (set `dropout_seed` for reproducible runs).
         self.dropout_seed = 0x5EED
+        self.dropout_rank = None                 # None: torch.distributed rank if initialised, else 0
         self.keep_debug_activations = False      # tests: keep the saved activations of the last forward
         self.fused_grad_accumulation = False     # see attach_grad_bucket
         self.tensor_core_heads = True            # seeded dropout fused into the last GEMMs + heads as GEMMs (see _StackFn)
@@ -187,39 +193,57 @@ class RelPoseGNN(nn.Module):
     def _ordered_params(self):
         return [self.get_parameter(n) for n in self._param_names()]
 
+    _pack_epoch = 0
+
+    def invalidate_packed(self):
+        """Forces every packed operand of the stack (and of gnn1..gnnL) to be rebuilt at the next forward; see
+        simpleConvEdge_upt.invalidate_packed."""
+        self._pack_epoch = self._pack_epoch + 1
+        for layer in range(self.n_layers):
+            getattr(self, f"gnn{layer + 1}").invalidate_packed()
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_stack_cache"] = {}                   # packed operands are a cache: not pickled / deep-copied
+        return state
+
     def _packed_stack(self, device):
-        """bf16 proj_edge operands and the [6, D] fp32 head matrices; refreshed when parameters change."""
+        """bf16 proj_edge operands and the [6, D] fp32 head matrices; refreshed (ONE launch) when parameters change."""
         D = self.node_dim
         ps = [self.proj_edge.weight] + [getattr(self, h).weight for h in _HEADS] + [getattr(self, h).bias for h in _HEADS]
-        versions = tuple((p.data_ptr(), p._version) for p in ps)
+        versions = (self._pack_epoch,) + tuple((p.data_ptr(), p._version) for p in ps)
         ent = self._stack_cache.get(str(device))
         if ent is not None and ent["versions"] == versions:
             return ent
         if ent is None:
+            f32 = torch.float32
             ent = {"Wmm": torch.empty(2 * D, D, dtype=BF16, device=device),
                    "WmmT": torch.empty(D, 2 * D, dtype=BF16, device=device)}
-            self._stack_cache[str(device)] = ent
-        W = self.proj_edge.weight.data                                     # [D, 2D]: columns (min node | max node)
-        ops.pack_weight(W, ent["Wmm"][:D], c0=0, cols=D)
-        ops.pack_weight(W, ent["Wmm"][D:], c0=D, cols=D)
-        ops.pack_weight(W, ent["WmmT"][:, :D], c0=0, cols=D, transpose=True)
-        ops.pack_weight(W, ent["WmmT"][:, D:], c0=D, cols=D, transpose=True)
-        ent["w6n"] = torch.cat([self.fc_xyz.weight.data, self.fc_wpqr.weight.data]).contiguous()
-        ent["b6n"] = torch.cat([self.fc_xyz.bias.data, self.fc_wpqr.bias.data]).contiguous()
-        ent["w6e"] = torch.cat([self.fc_xyz_R.weight.data, self.fc_wpqr_R.weight.data]).contiguous()
-        ent["b6e"] = torch.cat([self.fc_xyz_R.bias.data, self.fc_wpqr_R.bias.data]).contiguous()
-        # tensor-core heads (features dropped by the producing GEMM): W6 padded to 8 output rows, bias to 8, and the
-        # dgrad operand [D, 64] with W6[j, :] in columns j and 8 + j (hi / lo halves of dpose)
-        for tag in ("n", "e"):
-            if "w6%s_p" % tag not in ent:
+            # tensor-core heads (features dropped by the producing GEMM): W6 padded to 8 output rows, bias to 8, and the
+            # dgrad operand [D, 64] with W6[j, :] in columns j and 8 + j (hi / lo halves of dpose)
+            for tag in ("n", "e"):
+                ent["w6" + tag] = torch.empty(6, D, dtype=f32, device=device)
+                ent["b6" + tag] = torch.empty(6, dtype=f32, device=device)
                 ent["w6%s_p" % tag] = torch.zeros(8, D, dtype=BF16, device=device)
-                ent["b6%s_p" % tag] = torch.zeros(8, dtype=torch.float32, device=device)
+                ent["b6%s_p" % tag] = torch.zeros(8, dtype=f32, device=device)
                 ent["w6%sT" % tag] = torch.zeros(D, 64, dtype=BF16, device=device)
-            w6 = ent["w6" + tag]
-            ops.pack_weight(w6, ent["w6%s_p" % tag][:6])
-            ops.pack_weight(w6, ent["w6%sT" % tag][:, 0:6], transpose=True)
-            ops.pack_weight(w6, ent["w6%sT" % tag][:, 8:14], transpose=True)
-            ent["b6%s_p" % tag][:6].copy_(ent["b6" + tag])
+            self._stack_cache[str(device)] = ent
+        q = ops.PackQueue()
+        W = self.proj_edge.weight.data                                     # [D, 2D]: columns (min node | max node)
+        q.add(W, ent["Wmm"][:D], c0=0, cols=D)
+        q.add(W, ent["Wmm"][D:], c0=D, cols=D)
+        q.add(W, ent["WmmT"][:, :D], c0=0, cols=D, transpose=True)
+        q.add(W, ent["WmmT"][:, D:], c0=D, cols=D, transpose=True)
+        for tag, (ht, hq) in (("n", (self.fc_xyz, self.fc_wpqr)), ("e", (self.fc_xyz_R, self.fc_wpqr_R))):
+            for r0, head in ((0, ht), (3, hq)):
+                w, b = head.weight.data, head.bias.data.view(1, 3)
+                q.add(w, ent["w6" + tag][r0:r0 + 3])
+                q.add(b, ent["b6" + tag][r0:r0 + 3].view(1, 3))
+                q.add(w, ent["w6%s_p" % tag][r0:r0 + 3])
+                q.add(b, ent["b6%s_p" % tag][r0:r0 + 3].view(1, 3))
+                q.add(w, ent["w6%sT" % tag][:, r0:r0 + 3], transpose=True)
+                q.add(w, ent["w6%sT" % tag][:, 8 + r0:8 + r0 + 3], transpose=True)
+        q.flush()
         ent["versions"] = versions
         return ent
 
@@ -234,7 +258,19 @@ class RelPoseGNN(nn.Module):
             keep_e = keep_e.to(torch.uint8).contiguous()
             return (float(self.droprate), keep_x, keep_e, 0)
         self.dropout_seed += 2
-        return (float(self.droprate), None, None, self.dropout_seed)
+        self.last_seed = self._mixed_seed()      # what the kernels received (tests rebuild the masks from it)
+        return (float(self.droprate), None, None, self.last_seed)
+
+    def _mixed_seed(self):
+        """splitmix64 of (step counter, rank): the seed the kernels see (an even number; the edge stream uses seed + 1)."""
+        rank = self.dropout_rank
+        if rank is None:
+            import torch.distributed as dist
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        z = (int(self.dropout_seed) * 0x9E3779B97F4A7C15 + (int(rank) + 1) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return ((z ^ (z >> 31)) & 0x7FFFFFFFFFFFFFFE)
 
     def forward(self, x, edge_index, keep_x=None, keep_e=None, k=None):
         """x: node embeddings [G*N, D] (what feature_extractor returns, posenet.py:1037).  keep_x / keep_e: optional
@@ -269,10 +305,13 @@ class RelPoseGNN(nn.Module):
         lw = self.gnn1._packed_split(dev).refresh(self.gnn1)
         sw = self._packed_stack(dev)
         if "Wmm3" not in sw or sw.get("Wmm3_versions") != sw["versions"]:
-            sw["Wmm3"] = torch.zeros(2 * D, 3 * D, dtype=BF16, device=dev)
+            if "Wmm3" not in sw:
+                sw["Wmm3"] = torch.zeros(2 * D, 3 * D, dtype=BF16, device=dev)
             W = self.proj_edge.weight.data
-            ops.pack_weight3(W, sw["Wmm3"][:D], c0=0, cols=D)
-            ops.pack_weight3(W, sw["Wmm3"][D:], c0=D, cols=D)
+            q = ops.PackQueue()
+            q.add3(W, sw["Wmm3"][:D], c0=0, cols=D)
+            q.add3(W, sw["Wmm3"][D:], c0=D, cols=D)
+            q.flush()
             sw["Wmm3_versions"] = sw["versions"]
         xs = ops.to_split(x.float())
         pmm = torch.empty(Nt, 2 * D, dtype=torch.float32, device=dev)

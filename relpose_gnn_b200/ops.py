@@ -156,6 +156,51 @@ def pack_weight(src, dst, r0=0, c0=0, rows=None, cols=None, transpose=False):
                               int(transpose), _stream(src)), "rpg_pack_weight")
 
 
+class PackQueue:
+    """Collects rpg_pack_weight windows and converts them in ONE launch (rpg_pack_weights_batch): a training step
+    re-packs ~35 operand windows of the layer after every optimizer step.  dst dtype bf16 (operands) or fp32 (plain
+    strided copies: head matrices, concatenated biases); lo=True writes the low bf16 plane of the fp32 mode."""
+
+    def __init__(self):
+        self.batch = _lib.PackBatch()
+        self.batch.n = 0
+        self.stream = None
+        self.keep = []
+
+    def add(self, src, dst, r0=0, c0=0, rows=None, cols=None, transpose=False, lo=False):
+        _require_cuda(src, dst)
+        if src.dtype != torch.float32 or src.dim() != 2 or src.stride(1) != 1:
+            raise TypeError("pack source must be a float32 matrix with unit column stride")
+        if dst.dtype not in (BF16, torch.float32) or dst.dim() != 2 or dst.stride(1) != 1:
+            raise TypeError("pack destination must be a bf16 / float32 matrix with unit column stride")
+        if self.batch.n == _lib.PACK_BATCH_MAX:
+            self.flush()
+        d = self.batch.d[self.batch.n]
+        d.src, d.dst = src.data_ptr(), dst.data_ptr()
+        d.ld_src, d.r0, d.c0 = src.stride(0), r0, c0
+        d.rows = rows if rows is not None else src.size(0) - r0
+        d.cols = cols if cols is not None else src.size(1) - c0
+        d.ld_dst = dst.stride(0)
+        d.transpose, d.dst_f32, d.lo_plane, d.pad_ = int(transpose), int(dst.dtype == torch.float32), int(lo), 0
+        self.batch.n += 1
+        self.stream = _stream(src)
+        self.keep.append((src, dst))
+
+    def add3(self, src, dst, c0=0, cols=None):
+        """dst[:, 0:3*kp] = [W_hi | W_hi | W_lo] of the column window [c0, c0+cols) of `src` (fp32 mode operands)."""
+        cols = cols if cols is not None else src.size(1) - c0
+        kp = dst.size(1) // 3
+        self.add(src, dst[:, 0:kp], c0=c0, cols=cols)
+        self.add(src, dst[:, kp:2 * kp], c0=c0, cols=cols)
+        self.add(src, dst[:, 2 * kp:], c0=c0, cols=cols, lo=True)
+
+    def flush(self):
+        if self.batch.n:
+            check(_lib.load().rpg_pack_weights_batch(C.byref(self.batch), self.stream), "rpg_pack_weights_batch")
+            self.batch.n = 0
+            self.keep = []
+
+
 def to_bf16(t):
     if t.dtype == BF16:
         return t.contiguous()

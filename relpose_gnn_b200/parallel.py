@@ -40,9 +40,15 @@ def init_distributed(backend=None):
 class FlatGradBucket:
     """All gradients of `params` as views of one flat fp32 buffer, so a training step issues a single collective.
 
-    `param.grad` is pointed at its slice once; autograd then accumulates in place, `zero()` is one memset and
-    `allreduce()` one `all_reduce(SUM)` followed by the 1/world scaling (equal shards + mean-reduced loss =>
-    the single-GPU gradient up to summation order)."""
+    `param.grad` is pointed at its slice; autograd (and the fused weight-gradient kernels, RelPoseGNN.attach_grad_bucket)
+    then accumulate in place, `zero()` is one memset and `allreduce()` one `all_reduce(SUM)` (+ the 1/world scaling:
+    equal shards + mean-reduced loss => the single-GPU gradient up to summation order).
+
+    `optimizer.zero_grad()` / `model.zero_grad()` with the torch >= 2 default `set_to_none=True` (the reference loop
+    calls it, train.py:252) detach `param.grad` from the bucket; autograd then allocates fresh gradient tensors.  Both
+    `zero()` and `allreduce()` therefore re-attach: a gradient that no longer aliases its slice is copied into it
+    (allreduce) or discarded (zero) and `param.grad` is pointed back, so the collective never reduces a stale buffer.
+    """
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -51,20 +57,46 @@ class FlatGradBucket:
         dev = self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise TypeError("FlatGradBucket expects float32 parameters on one device")
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.reattach(keep=False)
+
+    def reattach(self, keep):
+        """Points every `param.grad` at its slice again.  keep=True first copies gradients that live elsewhere (fresh
+        tensors autograd allocated after a `zero_grad(set_to_none=True)`) into the slice; keep=False drops them.
+        Returns the number of parameters that had to be re-pointed."""
+        moved = 0
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is not None and g.data_ptr() == v.data_ptr() and g.shape == v.shape:
+                continue
+            if keep:
+                if g is not None:
+                    v.copy_(g)
+                else:
+                    v.zero_()                     # no gradient reached this parameter in this step
+            p.grad = v
+            moved += 1
+        return moved
 
     def zero(self):
+        self.reattach(keep=False)
         self.flat.zero_()
 
-    def allreduce(self, group=None, average=True):
+    def allreduce(self, group=None, average=True, async_op=False):
+        """SUM over the ranks of `group` (then / world if `average`).  async_op=True returns the work handle of the
+        collective (the caller waits, and folds the 1/world into its optimizer step: no extra kernel)."""
+        self.reattach(keep=True)
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
-            return self.flat
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return None if async_op else self.flat
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if async_op:
+            return work
         if average:
             self.flat.div_(dist.get_world_size(group))
         return self.flat

@@ -290,7 +290,7 @@ def test_stack_against_oracle_full_width_with_dropout(D, N, Gn):
     model.dropout_seed = 100
     with torch.no_grad():
         pn2, pe2, _ = model(x, ei)
-    seed = model.dropout_seed
+    seed = model.last_seed                     # the (counter, rank)-hashed seed the kernels received
     kx = ops.dropout_mask(seed, 0.5, Gn * N, D, dev()).cpu().bool()
     ke = ops.dropout_mask(seed + 1, 0.5, ei.size(1), D, dev()).cpu().bool()
     assert 0.45 < kx.float().mean().item() < 0.55 and 0.45 < ke.float().mean().item() < 0.55
@@ -644,7 +644,7 @@ def test_seeded_dropout_equals_explicit_masks_forward_and_backward():
         ct_n = torch.randn(pn.shape, generator=gen).to(dev())
         ct_e = torch.randn(pe.shape, generator=gen).to(dev())
         ((pn * ct_n).sum() + (pe * ct_e).sum()).backward()
-        return model.dropout_seed, pn.detach(), pe.detach(), x.grad.detach(), {k: v.grad.detach().clone()
+        return getattr(model, "last_seed", 0), pn.detach(), pe.detach(), x.grad.detach(), {k: v.grad.detach().clone()
                                                                               for k, v in model.named_parameters()}
 
     seed_used, pn0, pe0, gx0, g0 = run()

@@ -179,3 +179,42 @@ def test_save_poses_writes_the_reference_npz_layout(tmp_path):
     assert np.array_equal(z["abs_t"], pred[:, :3]) and np.array_equal(z["targ_q"], targ[:, 3:])
     with pytest.raises(ValueError):
         rpg.save_poses(pred, ["only one"], out, targ)
+
+
+def test_reference_arm_runs_the_unmodified_reference_modules():
+    """bench.py --impl reference / cpu_baseline: the reference's own PoseNetX_R2 + compute_RP + criterion (+ Adam) through
+    the shim, from /root/reference here or from the staged baseline/_ref on the GPU box."""
+    from oracle import reference_arm, stage_reference
+    if not reference_arm.available():
+        pytest.skip("no reference tree and nothing staged under baseline/_ref")
+    step = reference_arm.ReferenceStep(128, 4, 2, train=True, edge_dropout=True)
+    assert type(step.model).__name__ == "PoseNetX_R2" and type(step.model.gnn1).__name__ == "simpleConvEdge_upt"
+    assert step.model.__class__.__module__ == "niantic.modules.posenet"
+    l0 = step()
+    assert torch.isfinite(l0).all()
+    infer = reference_arm.ReferenceStep(128, 4, 2, train=False, edge_dropout=False)
+    pe = infer()
+    assert pe.shape == (2 * 12, 6)
+    if os.path.isdir("/root/reference/python"):
+        assert stage_reference.stage() is not None and stage_reference.staged()
+        for f in stage_reference.FILES:
+            src = os.path.join("/root/reference/python", f)
+            if os.path.isfile(src):
+                assert open(src, "rb").read() == open(os.path.join(stage_reference.DST, f), "rb").read()   # unmodified
+
+
+def test_packed_weight_caches_are_not_pickled_and_can_be_invalidated():
+    import copy
+    m = rpg.RelPoseGNN(128, 128, 128)
+    m._stack_cache["x"] = object()
+    m.gnn1._pack_cache["x"] = object()
+    m2 = copy.deepcopy(m)
+    assert m2._stack_cache == {} and m2.gnn1._pack_cache == {}
+    e0, l0 = m._pack_epoch, m.gnn1._pack_epoch
+    m.invalidate_packed()
+    assert m._pack_epoch == e0 + 1 and m.gnn1._pack_epoch == l0 + 1
+    m.load_state_dict(m2.state_dict())
+    assert m._pack_epoch == e0 + 2 and m.gnn1._pack_epoch > l0 + 1
+    s1 = m._mixed_seed()
+    m.dropout_rank = 1
+    assert m._mixed_seed() != s1 and m._mixed_seed() % 2 == 0      # replicas draw different dropout masks

@@ -60,3 +60,24 @@ def test_flat_gradient_allreduce_matches_single_process(tmp_path):
     lin(data).pow(2).mean().backward()                     # equal shards + mean loss => averaged grads == full-batch grads
     want = torch.cat([p.grad.flatten() for p in lin.parameters()])
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)
+
+
+def test_bucket_reattaches_after_zero_grad_set_to_none():
+    """optimizer.zero_grad() (set_to_none=True, train.py:252) detaches p.grad from the flat buffer; the
+    bucket must copy the fresh gradients back before the collective instead of reducing a stale buffer."""
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    params = list(lin.parameters())
+    bucket = parallel.FlatGradBucket(params)
+    x = torch.randn(5, 4)
+    lin(x).sum().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in params]).clone()
+    assert torch.equal(bucket.allreduce(), want)
+    torch.optim.SGD(params, lr=0.1).zero_grad()                    # every p.grad is None now
+    assert all(p.grad is None for p in params)
+    lin(x).sum().backward()                                        # autograd allocates fresh gradient tensors
+    assert all(p.grad.data_ptr() != v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    assert torch.equal(bucket.allreduce(), want)                   # copied back and re-pointed
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    bucket.zero()
+    assert float(bucket.flat.abs().sum()) == 0.0 and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
