@@ -278,6 +278,23 @@ typedef struct {
 } rpg_pack_batch_t;
 int rpg_pack_weights_batch(const rpg_pack_batch_t* batch, rpg_stream_t stream);
 
+/* Small fp32 products with the master weights (weight composition and its backward), several in ONE launch:
+ *   C[m, n] (+)= sum_k opA(m, k) opB(k, n)     opA = A[m, k] or A[k, m] (transA), opB = B[k, n] or B[n, k] (transB)
+ * plus an optional rank-1 term u[m] v[n]; optional bf16 copies of the result, plain (Cb) and transposed (CbT).     */
+#define RPG_SGEMM_BATCH_MAX 8
+typedef struct {
+  const float* A; const float* B; float* C;
+  const float* u; const float* v;
+  rpg_bf16* Cb; rpg_bf16* CbT;
+  int32_t M, N, K, lda, ldb, ldc, ldcb, ldcbT;
+  int32_t transA, transB, accumulate, pad_;
+} rpg_sgemm_desc_t;
+typedef struct {
+  rpg_sgemm_desc_t d[RPG_SGEMM_BATCH_MAX];
+  int32_t n;
+} rpg_sgemm_batch_t;
+int rpg_sgemm_batch(const rpg_sgemm_batch_t* batch, rpg_stream_t stream);
+
 /* Adam step (torch.optim.Adam semantics as used by train.py:211: L2 weight decay added to the gradient, bias
  * correction, no amsgrad) over flat fp32 buffers of n elements, one launch:
  *   g = grad * grad_scale + wd * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
@@ -295,6 +312,11 @@ int rpg_cast_bf16_to_f32(const rpg_bf16* src, float* dst, int64_t n, rpg_stream_
 
 /* AttentionBlock core, att.py:25-30: y[e,i] = sum_j softmax_j(phi[e,i]*theta[e,j]) * g[e,j].
  * gtp [Et, 3c] fp32 holds (g | theta | phi) rows; y [Et, ldy] bf16 (only the first c columns written). */
+/* Two implementations with the same result to fp32 rounding: the SERIES form (default when aux == NULL and c % 16 == 0;
+ * csrc/rpg_attention.cu: the rank-1 logits make exp(phi_i theta_j) separable, O(c K) multiply-adds per row with the order
+ * K chosen from the row's range and an exact exp2 path for rows beyond the series bound) and the exp2 form (aux != NULL,
+ * or RPG_ATT_SERIES=0).  rpg_attention_series_enabled() tells the caller whether `aux` is still worth allocating. */
+int rpg_attention_series_enabled(void);
 int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo /* NULL in bf16 mode */,
                       float* aux /* optional [Et, 4c] fp32 row statistics for the backward, or NULL */,
                       rpg_stream_t stream);
@@ -441,6 +463,19 @@ typedef struct {
   const rpg_bf16* W1uT;           /* [2D, D] */
   /* fp32 biases */
   const float* b1e, *b2e, *b1m, *b2m, *bgtp, *bW, *b1u, *b2u;
+  /* The message m = h2 W2m^T + b2m (my_gnn_layer.py:282) only ever enters LINEAR maps -- the attention projections
+   * (att.py:20-24) and, through z = W(y) + m, the mean over incoming edges -- so it is never materialised:
+   *   (g | theta | phi) = h2 Wgc^T + bgc      with Wgc = Wgtp W2m, bgc = Wgtp b2m + bgtp   (composed in fp32, rpg_compose)
+   *   mean(z) = [mean(y) | mean(h2)] [WW | W2m]^T + (bW + b2m)
+   * and the backward follows the same factorisation (dh2 = (dgtp Wgc + (dan W2m)[dst]) * [h2 > 0]; the weight gradients of
+   * mlp.2 / att.{g,theta,phi} from T = dgtp^T h2 and small fp32 products with the master weights).                */
+  const rpg_bf16* Wgc;            /* [3c, D]            composed attention projection                            */
+  const rpg_bf16* WgcT;           /* [D, pad64(3c)]     its transpose (dgrad)                                    */
+  const rpg_bf16* WWM;            /* [D, pad64(c) + D]  [att.W | mlp.2]                                          */
+  const float* bgc;               /* [3c]                                                                        */
+  const float* bWm;               /* [D]                bW + b2m                                                 */
+  const float* Wgtp_f32;          /* [3c, D] fp32       att.g | att.theta | att.phi master weights, concatenated */
+  const float* W2m_f32;           /* [D, D]  fp32       mlp.2.weight (master)                                    */
   /* 0 = simpleConvEdge_upt (above).
    * 1 = simpleConvEdge (my_gnn_layer.py:242-274): message = att(mlp(cat[x_i, x_j, e'])) and NO update MLP, the layer
    *     output is the mean itself (acts.a).  Then Wn is [4D, D] with rows edge_mlp.0[:,0:D] | edge_mlp.0[:,D:2D] |
@@ -506,7 +541,10 @@ typedef struct {
   rpg_bf16* ysum;                 /* [Nt, max(c,64)] */
   float* split_ws;                /* fp32 split-R workspace, rpg_layer_bwd_ws_floats() elements         */
   float* colsum_ws;               /* rpg_colsum_scratch_floats(Et, D) floats                            */
-  float* gtp_bias_tmp;            /* [pad64(3c)] fp32                                                   */
+  float* gtp_bias_tmp;            /* [pad64(3c)] fp32: column sums of dgtp                              */
+  rpg_bf16* Q;                    /* [Nt, D]    dan W2m (node level)                                    */
+  rpg_bf16* h2sum;                /* [Nt, D]    deg * mean(h2) = sum over in-edges of h2                */
+  float* T_tmp;                   /* [3c, D] fp32: dgtp^T h2                                            */
   /* fp32 weight gradients in the reference's state_dict layout, accumulated (+=) */
   float* g_mlp0_w;  float* g_mlp0_b;      /* [D, 2D], [D]   mlp.0            */
   float* g_mlp2_w;  float* g_mlp2_b;      /* [D, D]         mlp.2            */

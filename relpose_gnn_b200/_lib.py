@@ -47,7 +47,8 @@ class LayerWeights(C.Structure):
     _fields_ = [("D", I)] + [(n, P) for n in (
         "Wn", "W1e_e", "W2e", "W1m_e", "W2m", "Wgtp", "WW", "WWI", "W1u", "W2u",
         "WnT", "W1e_eT", "W2eT", "W1m_eT", "W2mT", "W2uT", "WgtpT", "WWT", "W1uT",
-        "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")] + [("variant", I)]
+        "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u",
+        "Wgc", "WgcT", "WWM", "bgc", "bWm", "Wgtp_f32", "W2m_f32")] + [("variant", I)]
 
 
 class LayerActs(C.Structure):
@@ -72,7 +73,7 @@ class LayerActsSplit(C.Structure):
 class LayerGrads(C.Structure):
     _fields_ = [("d_out", P), ("d_e_new", P), ("mask_dx", I), ("mask_de", I)] + [(n, P) for n in (
         "dx", "de", "dh3", "dxu", "dan", "dyn", "dgtp", "dm", "dh2", "de_tot", "dh1", "dP", "ysum",
-        "split_ws", "colsum_ws", "gtp_bias_tmp",
+        "split_ws", "colsum_ws", "gtp_bias_tmp", "Q", "h2sum", "T_tmp",
         "g_mlp0_w", "g_mlp0_b", "g_mlp2_w", "g_mlp2_b", "g_upd0_w", "g_upd0_b", "g_upd2_w", "g_upd2_b",
         "g_edge0_w", "g_edge0_b", "g_edge2_w", "g_edge2_b",
         "g_att_g_w", "g_att_g_b", "g_att_theta_w", "g_att_theta_b", "g_att_phi_w", "g_att_phi_b",
@@ -90,6 +91,18 @@ PACK_BATCH_MAX = 64
 
 class PackBatch(C.Structure):
     _fields_ = [("d", PackDesc * PACK_BATCH_MAX), ("n", C.c_int32)]
+
+
+class SgemmDesc(C.Structure):
+    _fields_ = [("A", P), ("B", P), ("C", P), ("u", P), ("v", P), ("Cb", P), ("CbT", P)] + [
+        (n, C.c_int32) for n in ("M", "N", "K", "lda", "ldb", "ldc", "ldcb", "ldcbT", "transA", "transB", "accumulate", "pad_")]
+
+
+SGEMM_BATCH_MAX = 8
+
+
+class SgemmBatch(C.Structure):
+    _fields_ = [("d", SgemmDesc * SGEMM_BATCH_MAX), ("n", C.c_int32)]
 
 
 class ProfRec(C.Structure):
@@ -113,6 +126,7 @@ SIGNATURES = {
     "rpg_template_tables": (I, [P, P, I, I, P, P]),
     "rpg_pack_weights_batch": (I, [C.POINTER(PackBatch), P]),
     "rpg_adam_step": (I, [P, P, P, P, I64, F, F, F, F, F, F, I64, P]),
+    "rpg_sgemm_batch": (I, [C.POINTER(SgemmBatch), P]),
     "rpg_validate_edge_index": (I, [P, I64, I, I, I, P, P, P, P]),
     "rpg_selection_patterns": (I, [P, I, I, I, I, P, P]),
     "rpg_gemm": (I, [C.POINTER(Gemm), P]),
@@ -124,6 +138,7 @@ SIGNATURES = {
     "rpg_pack_weight": (I, [P, I, I, I, I, I, P, I, I, P]),
     "rpg_cast_f32_to_bf16": (I, [P, P, I64, P]),
     "rpg_cast_bf16_to_f32": (I, [P, P, I64, P]),
+    "rpg_attention_series_enabled": (I, []),
     "rpg_attention_fwd": (I, [P, I64, I, P, I, P, P, P]),
     "rpg_cast_f32_to_split": (I, [P, P, P, I64, P]),
     "rpg_split_to_f32": (I, [P, P, P, I64, P]),
@@ -177,7 +192,7 @@ def _check_layout(lib):
     want = [C.sizeof(Graph), C.sizeof(Gemm), C.sizeof(LayerWeights), C.sizeof(LayerActs), C.sizeof(LayerGrads),
             Gemm.out_f32.offset, LayerGrads.g_mlp0_w.offset, LayerWeights.b1e.offset,
             C.sizeof(LayerWeightsSplit), C.sizeof(LayerActsSplit), C.sizeof(PackDesc), C.sizeof(PackBatch),
-            C.sizeof(ProfRec), 0, 0, 0]
+            C.sizeof(ProfRec), C.sizeof(SgemmBatch), 0, 0]
     if list(probe) != want:
         raise RpgError(f"ctypes mirrors out of sync with include/rpg.h: library {list(probe)} vs python {want}")
 

@@ -1439,6 +1439,8 @@ int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, cons
 int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, float* aux,
                       rpg_stream_t stream) {
     if (!gtp || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd: bad arguments");
+    if (!aux && attention_series_enabled() && c % 16 == 0 && c >= 16 && c <= 256 && ldy % 8 == 0)
+        return attention_series_fwd(gtp, Et, c, y, ldy, y_lo, as_stream(stream));
     if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
     ProfScope prof(RPG_PROF_ATTENTION_FWD, (double)Et * c * (12.0 + 2.0 + (y_lo ? 2.0 : 0.0) + (aux ? 16.0 : 0.0)), as_stream(stream),
@@ -1455,6 +1457,8 @@ int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy,
 int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
                       rpg_bf16* dgtp, int ld_dgtp, const float* aux, rpg_stream_t stream) {
     if (!gtp || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd: bad arguments");
+    if (!aux && attention_series_enabled() && c % 16 == 0 && c >= 16 && c <= 256 && ld_dgtp % 8 == 0 && ld_dyn % 4 == 0)
+        return attention_series_bwd(gtp, dyn, ld_dyn, graph, Et, c, dgtp, ld_dgtp, nullptr, as_stream(stream));
     if (c % 4 || c < 4 || c > 512) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c must be a multiple of 4 in [4,512]");
     const size_t smem = (size_t)ATT_WARPS * 8 * c * sizeof(float);
     static SmemLimit configured;

@@ -171,6 +171,8 @@ int rpg_gemm(const rpg_gemm_t* g, rpg_stream_t stream) { return gemm_launch(g, a
 
 int rpg_set_gemm_cluster(int cl) { return set_gemm_cluster(cl); }
 
+int rpg_attention_series_enabled(void) { return attention_series_enabled() ? 1 : 0; }
+
 int64_t rpg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int rpg_profile_begin(void) { return profile_begin(); }
@@ -204,7 +206,8 @@ void rpg_struct_sizes(int32_t* out) {
     out[10] = (int32_t)sizeof(rpg_pack_desc_t);
     out[11] = (int32_t)sizeof(rpg_pack_batch_t);
     out[12] = (int32_t)sizeof(rpg_prof_rec_t);
-    out[13] = out[14] = out[15] = 0;
+    out[13] = (int32_t)sizeof(rpg_sgemm_batch_t);
+    out[14] = out[15] = 0;
 }
 
 #define RPG_TRY(expr)            \
@@ -267,29 +270,28 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     g.out = t->h2; g.ldo = D; g.out_bits = t->h2_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
 
-    // (5) message MLP layer 2 (my_gnn_layer.py:282): m = h2 W2m^T + b
-    g = nt((int)Et, D, t->h2, D, D, w->W2m, D);
-    g.bias = w->b2m; g.out = t->m; g.ldo = D;
-    RPG_TRY(gemm_launch(&g, s));
-
-    // (6) attention projections (att.py:20-24): (g | theta | phi) = m [Wg; Wtheta; Wphi]^T + b   fp32 [Et, 3c]
-    g = nt((int)Et, c3, t->m, D, D, w->Wgtp, D);
-    g.bias = w->bgtp; g.out_f32 = t->gtp; g.ldo_f32 = c3;
+    // (5) message MLP layer 2 (my_gnn_layer.py:282): m = h2 W2m^T + b2m is NEVER materialised -- it only enters linear
+    //     maps (the attention projections and, through z = W(y) + m, the mean over incoming edges), so both are taken
+    //     straight from h2 with composed weights (rpg.h: rpg_layer_weights_t.Wgc / WWM).
+    // (6) attention projections (att.py:20-24): (g | theta | phi) = m Wgtp^T + b = h2 (Wgtp W2m)^T + (Wgtp b2m + bgtp)
+    if (!w->Wgc || !w->bgc || !w->WWM || !w->bWm) return set_error(RPG_E_ARG, "layer_fwd: composed operands (Wgc / WWM) missing");
+    g = nt((int)Et, c3, t->h2, D, D, w->Wgc, D);
+    g.bias = w->bgc; g.out_f32 = t->gtp; g.ldo_f32 = c3;
     RPG_TRY(gemm_launch(&g, s));
 
     // (7) rank-1 softmax attention (att.py:25-30)
-    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, t->att_aux, stream));
+    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, attention_series_enabled() ? nullptr : t->att_aux, stream));
 
     // (8)+(9) z = y WW^T + bW + m (att.py:32-33) is only ever averaged over the incoming edges (PyG aggregate [3p],
-    //     my_gnn_layer.py:301), and the mean is linear: a = mean(y) WW^T + bW + mean(m).  So the edge-level GEMM and
-    //     the [Et, D] tensor z disappear: two segment means (y is only c wide) and ONE node-level GEMM
-    //     [ybar | mbar] [WW | I]^T + bW, zeroed for nodes without incoming edges (their mean is 0, not bW).
+    //     my_gnn_layer.py:301), and the mean is linear: a = mean(y) WW^T + bW + mean(h2) W2m^T + b2m.  So neither the
+    //     edge-level GEMMs nor the [Et, D] tensors m, z exist: two segment means (y is only c wide) and ONE node-level
+    //     GEMM [ybar | h2bar] [WW | W2m]^T + (bW + b2m), zeroed for nodes without incoming edges (their mean is 0).
     if (!t->ybar || !t->mbar || !gr->has_in) return set_error(RPG_E_ARG, "layer_fwd: ybar / mbar / has_in missing");
     RPG_TRY(rpg_aggregate_mean(t->y, cp, gr, cp, t->ybar, cp, stream));
-    RPG_TRY(rpg_aggregate_mean(t->m, D, gr, D, t->mbar, D, stream));
-    g = nt((int)Nt, D, t->ybar, cp, cp, w->WWI, cp + D);
+    RPG_TRY(rpg_aggregate_mean(t->h2, D, gr, D, t->mbar, D, stream));      // mbar holds mean(h2)
+    g = nt((int)Nt, D, t->ybar, cp, cp, w->WWM, cp + D);
     g.n_seg = 2; g.A[1] = t->mbar; g.K[1] = D; g.lda[1] = D;
-    g.bias = w->bW; g.row_scale = gr->has_in; g.row_scale_mod = gr->N; g.out = t->a; g.ldo = D;
+    g.bias = w->bWm; g.row_scale = gr->has_in; g.row_scale_mod = gr->N; g.out = t->a; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
     if (w->variant == 1) return 0;               // simpleConvEdge: the mean is the layer output (no update step)
 
@@ -495,21 +497,22 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         g.out_f32 = b->dyn; g.ldo_f32 = c;
         RPG_TRY(gemm_launch(&g, s));
         // attention backward -> dgtp [Et, 3c]
-        RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, t->att_aux, stream));
-        // dm = dgtp Wgtp + dan[dst]
-        g = nt((int)Et, D, b->dgtp, c3p, c3p, w->WgtpT, c3p);
+        RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, attention_series_enabled() ? nullptr : t->att_aux, stream));
+        // dh2 = (dm W2m) * [h2 > 0] with dm = dgtp Wgtp + dan[dst] (never materialised):
+        //     dh2 = (dgtp (Wgtp W2m) + Q[dst]) * [h2 > 0],  Q = dan W2m at node level
+        if (!b->Q || !w->WgcT) return set_error(RPG_E_ARG, "layer_bwd: Q / WgcT missing");
+        g = nt((int)Nt, D, b->dan, D, D, w->W2mT, D);
+        g.out = b->Q; g.ldo = D;
+        RPG_TRY(gemm_launch(&g, s));
+        g = nt((int)Et, D, b->dgtp, c3p, c3p, w->WgcT, c3p);
         g.Ep = gr->Ep; g.Nn = gr->N;
         if (gr->sel_dst) {
             g.n_gseg = 1; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt;
-            g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->dan; g.gsrc_ld[0] = D;
+            g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->Q; g.gsrc_ld[0] = D;
             if (gr->pg_Ep) { g.Ep = gr->pg_Ep; g.Nn = gr->pg_N; }       // per-graph edge sets: window of a member graph
         } else {
-            g.gadd[0] = b->dan; g.gmap[0] = gr->dst; g.gadd_ld[0] = D;
+            g.gadd[0] = b->Q; g.gmap[0] = gr->dst; g.gadd_ld[0] = D;
         }
-        g.out = b->dm; g.ldo = D;
-        RPG_TRY(gemm_launch(&g, s));
-        // dh2 = (dm W2m) * [h2 > 0]
-        g = nt((int)Et, D, b->dm, D, D, w->W2mT, D);
         if (t->h2_bits) { g.mask_bits = t->h2_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->h2; g.mask_ld = D; }
         g.out = b->dh2; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
@@ -574,26 +577,56 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         }
     }
     if (have_out) {
-        // mlp.2: dW = dm^T h2 ; mlp.0 edge columns [D,2D): dW = dh2^T e'
-        RPG_TRY(q.wgrad(b->dm, D, D, t->h2, D, D, Et, b->g_mlp2_w, D, b->g_mlp2_b));
+        // mlp.0 edge columns [D,2D): dW = dh2^T e'
         RPG_TRY(q.wgrad(b->dh2, D, D, t->e_new, D, D, Et, b->g_mlp0_w + (v1 ? 2 * D : D), v1 ? 3 * D : 2 * D, b->g_mlp0_b));
-        // att.g / theta / phi: one launch dgtp^T m [3c, D], three folds ; biases = colsum(dgtp)
-        RPG_TRY(q.partials(b->dgtp, c3p, c3, t->m, D, D, Et, true, &part, &splits));
+        // mlp.2 and att.g / theta / phi through the factorisation dm = dgtp Wgtp + dan[dst], m = h2 W2m^T + b2m:
+        //   T = dgtp^T h2 [3c, D], csg = colsum(dgtp)                      (one TN launch over the edge rows)
+        //   d att.{g,theta,phi}.weight = T W2m^T + csg b2m^T ;  bias = csg
+        //   d mlp.2.weight = Wgtp^T T + dan^T h2sum ;  bias = Wgtp^T csg + sum_n deg(n) dan[n]
+        // with h2sum[n] = sum over in-edges of h2 = deg(n) * mean(h2)[n] (the forward's node-level mean).
+        if (!b->T_tmp || !b->h2sum || !w->Wgtp_f32 || !w->W2m_f32) return set_error(RPG_E_ARG, "layer_bwd: T_tmp / h2sum / master weights missing");
+        RPG_TRY(q.partials(b->dgtp, c3p, c3, t->h2, D, D, Et, true, &part, &splits));
         {
-            const long long stride = (long long)c3 * D;
-            RPG_TRY(q.add(part, splits, stride, c, D, b->g_att_g_w, D));
-            RPG_TRY(q.add(part + (size_t)c * D, splits, stride, c, D, b->g_att_theta_w, D));
-            RPG_TRY(q.add(part + 2 * (size_t)c * D, splits, stride, c, D, b->g_att_phi_w, D));
             const float* cs = part + (size_t)splits * c3 * D;            // [splits, 3c] column sums of dgtp
             RPG_TRY(q.add(cs, splits, c3, 1, c, b->g_att_g_b, c));
             RPG_TRY(q.add(cs + c, splits, c3, 1, c, b->g_att_theta_b, c));
             RPG_TRY(q.add(cs + 2 * c, splits, c3, 1, c, b->g_att_phi_b, c));
+            // T and csg are needed NOW by the small fp32 products: their own fold launch into zeroed scratch
+            cudaMemsetAsync(b->T_tmp, 0, (size_t)c3 * D * sizeof(float), s);
+            cudaMemsetAsync(b->gtp_bias_tmp, 0, (size_t)c3 * sizeof(float), s);
+            rpg_reduce_batch_t fold;
+            fold.n = 2;
+            fold.d[0] = {part, b->T_tmp, (long long)c3 * D, splits, c3, D, D};
+            fold.d[1] = {cs, b->gtp_bias_tmp, c3, splits, 1, c3, c3};
+            RPG_TRY(rpg_reduce_splits_batch(&fold, stream));
+            rpg_sgemm_batch_t sg;
+            memset(&sg, 0, sizeof sg);
+            float* dW[3] = {b->g_att_g_w, b->g_att_theta_w, b->g_att_phi_w};
+            for (int i = 0; i < 3; ++i) {                                   // [c, D] += T_i W2m^T + csg_i b2m^T
+                rpg_sgemm_desc_t& d = sg.d[sg.n++];
+                d.A = b->T_tmp + (size_t)i * c * D; d.lda = D; d.B = w->W2m_f32; d.ldb = D; d.transB = 1;
+                d.C = dW[i]; d.ldc = D; d.M = c; d.N = D; d.K = D; d.accumulate = 1;
+                d.u = b->gtp_bias_tmp + i * c; d.v = w->b2m;
+            }
+            {                                                               // mlp.2.weight [D, D] += Wgtp^T T
+                rpg_sgemm_desc_t& d = sg.d[sg.n++];
+                d.A = w->Wgtp_f32; d.lda = D; d.transA = 1; d.B = b->T_tmp; d.ldb = D;
+                d.C = b->g_mlp2_w; d.ldc = D; d.M = D; d.N = D; d.K = c3; d.accumulate = 1;
+            }
+            {                                                               // mlp.2.bias [D] += Wgtp^T csg
+                rpg_sgemm_desc_t& d = sg.d[sg.n++];
+                d.A = w->Wgtp_f32; d.lda = D; d.transA = 1; d.B = b->gtp_bias_tmp; d.ldb = 1;
+                d.C = b->g_mlp2_b; d.ldc = 1; d.M = D; d.N = 1; d.K = c3; d.accumulate = 1;
+            }
+            RPG_TRY(rpg_sgemm_batch(&sg, stream));
         }
-        // att.W: dW = sum_e dz[e]^T y[e] = dan^T ysum with ysum[n] = sum_{in-edges(n)} y[e];
-        //        db = sum_e dz[e] = sum_n indeg(n) * dan[n]
-        RPG_TRY(rpg_edge_to_node_sum(t->y, cp, gr, cp, 0, b->ysum, cp, stream));
+        // node-level parts: dan^T h2sum -> mlp.2.weight, dan^T ysum -> att.W.weight, sum_n deg(n) dan[n] -> both biases
+        RPG_TRY(rpg_scale_rows(t->mbar, D, Nt, D, gr->deg, gr->N, b->h2sum, D, stream));
+        RPG_TRY(q.wgrad(b->dan, D, D, b->h2sum, D, D, Nt, b->g_mlp2_w, D));
+        RPG_TRY(rpg_scale_rows(t->ybar, cp, Nt, cp, gr->deg, gr->N, b->ysum, cp, stream));
         RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
         RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
+        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
         if (!v1) {
             // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
             RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));

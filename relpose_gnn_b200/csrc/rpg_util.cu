@@ -195,3 +195,67 @@ int rpg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int rpg_profile_records(rpg_prof_rec_t* out, int max_records, int* n_records) { return profile_records(out, max_records, n_records); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Small fp32 products (weight composition Wgc = Wgtp W2m and the matching backward): 32 x 32 output tile per block,
+// 32-wide k chunks through shared memory, 4 outputs per thread.  ~50 MFLOP per product: a few microseconds.
+// ------------------------------------------------------------------------------------------------
+namespace rpg {
+__global__ void __launch_bounds__(256)
+sgemm_batch_kernel(const __grid_constant__ rpg_sgemm_batch_t batch) {
+    pdl_prologue();
+    const rpg_sgemm_desc_t& d = batch.d[blockIdx.z];
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    if (m0 >= d.M || n0 >= d.N) return;
+    __shared__ float sa[32][33], sb[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8; thread owns rows ty + 8 r, column tx
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < d.K; k0 += 32) {
+        for (int r = ty; r < 32; r += 8) {
+            // sa[m][k], sb[k][n]
+            const int m = m0 + r, ka = k0 + tx;
+            sa[r][tx] = (m < d.M && ka < d.K) ? (d.transA ? d.A[(size_t)ka * d.lda + m] : d.A[(size_t)m * d.lda + ka]) : 0.f;
+            const int kb = k0 + r, n = n0 + tx;
+            sb[r][tx] = (kb < d.K && n < d.N) ? (d.transB ? d.B[(size_t)n * d.ldb + kb] : d.B[(size_t)kb * d.ldb + n]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float bv = sb[k][tx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[ty + 8 * r][k], bv, acc[r]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx;
+    if (n >= d.N) return;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + ty + 8 * r;
+        if (m >= d.M) continue;
+        float v = acc[r];
+        if (d.u && d.v) v = fmaf(d.u[m], d.v[n], v);
+        if (d.C) {
+            float* o = d.C + (size_t)m * d.ldc + n;
+            v = d.accumulate ? *o + v : v;
+            *o = v;
+        }
+        if (d.Cb) reinterpret_cast<bf16*>(d.Cb)[(size_t)m * d.ldcb + n] = __float2bfloat16_rn(v);
+        if (d.CbT) reinterpret_cast<bf16*>(d.CbT)[(size_t)n * d.ldcbT + m] = __float2bfloat16_rn(v);
+    }
+}
+}  // namespace rpg
+
+extern "C" int rpg_sgemm_batch(const rpg_sgemm_batch_t* batch, rpg_stream_t stream) {
+    if (!batch || batch->n < 1 || batch->n > RPG_SGEMM_BATCH_MAX) return set_error(RPG_E_ARG, "sgemm_batch: bad arguments");
+    int mx = 1, nx = 1;
+    for (int i = 0; i < batch->n; ++i) {
+        const rpg_sgemm_desc_t& d = batch->d[i];
+        if (!d.A || !d.B || (!d.C && !d.Cb && !d.CbT) || d.M <= 0 || d.N <= 0 || d.K <= 0)
+            return set_error(RPG_E_ARG, "sgemm_batch: bad descriptor");
+        mx = d.M > mx ? d.M : mx;
+        nx = d.N > nx ? d.N : nx;
+    }
+    launch_pdl(sgemm_batch_kernel, dim3((nx + 31) / 32, (mx + 31) / 32, batch->n), dim3(256), 0, as_stream(stream), *batch);
+    return check_launch("sgemm_batch_kernel");
+}

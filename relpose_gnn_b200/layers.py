@@ -72,10 +72,10 @@ class PackedLayerWeights:
         self.c, self.cp, self.c3p = c, pad64(c), pad64(3 * c)
         npj = 4 if variant == 1 else 3                       # node projection blocks (rpg.h: rpg_layer_weights_t.variant)
         shapes = {
-            "Wn": (npj * D, D), "W1e_e": (D, D), "W2e": (D, D), "W1m_e": (D, D), "W2m": (D, D),
-            "Wgtp": (3 * c, D), "WW": (D, self.cp), "WWI": (D, self.cp + D),
+            "Wn": (npj * D, D), "W1e_e": (D, D), "W2e": (D, D), "W1m_e": (D, D),
+            "Wgc": (3 * c, D), "WWM": (D, self.cp + D),
             "WnT": (D, npj * D), "W1e_eT": (D, D), "W2eT": (D, D), "W1m_eT": (D, D), "W2mT": (D, D),
-            "WgtpT": (D, self.c3p), "WWT": (c, D),
+            "WgcT": (D, self.c3p), "WWT": (c, D),
         }
         if variant == 0:
             shapes.update({"W1u": (D, 2 * D), "W2u": (D, D), "W2uT": (D, D), "W1uT": (2 * D, D)})
@@ -86,8 +86,13 @@ class PackedLayerWeights:
         for name, (r, k) in shapes.items():
             self.t[name] = self.flat[off:off + r * k].view(r, k)
             off += r * k
-        self.t["WWI"][:, self.cp:].copy_(torch.eye(D, dtype=BF16, device=device))   # identity panel (residual)
-        self.bgtp = torch.zeros(3 * c, dtype=torch.float32, device=device)
+        f32 = torch.float32
+        self.bgtp = torch.zeros(3 * c, dtype=f32, device=device)
+        # the message m = h2 W2m^T + b2m is never materialised (rpg.h: rpg_layer_weights_t.Wgc): composed operands
+        self.bgc = torch.zeros(3 * c, dtype=f32, device=device)           # Wgtp b2m + bgtp
+        self.bWm = torch.zeros(D, dtype=f32, device=device)               # bW + b2m
+        self.Wgtp_f32 = torch.zeros(3 * c, D, dtype=f32, device=device)   # att.g | att.theta | att.phi master weights
+        self.one = torch.ones(1, dtype=f32, device=device)
         self.versions = None
         self.struct = _lib.LayerWeights()
 
@@ -116,13 +121,13 @@ class PackedLayerWeights:
         pk(W1e, t["W1e_e"], c0=2 * D, cols=D)
         pk(W2e, t["W2e"])
         pk(W1m, t["W1m_e"], c0=me0, cols=D)
-        pk(W2m, t["W2m"])
         for i, nm in enumerate(("g", "theta", "phi")):
-            pk(p[f"att.{nm}.weight"].data, t["Wgtp"][i * c:(i + 1) * c])
-            pk(p[f"att.{nm}.weight"].data, t["WgtpT"][:, i * c:(i + 1) * c], transpose=True)
+            pk(p[f"att.{nm}.weight"].data, self.Wgtp_f32[i * c:(i + 1) * c])
             pk(p[f"att.{nm}.bias"].data.view(1, c), self.bgtp[i * c:(i + 1) * c].view(1, c))
-        pk(p["att.W.weight"].data, t["WW"][:, :c])
-        pk(p["att.W.weight"].data, t["WWI"][:, :c])
+            pk(p[f"att.{nm}.bias"].data.view(1, c), self.bgc[i * c:(i + 1) * c].view(1, c))
+        pk(p["att.W.weight"].data, t["WWM"][:, :c])
+        pk(W2m, t["WWM"][:, self.cp:])
+        pk(p["att.W.bias"].data.view(1, D), self.bWm.view(1, D))
         # dgrad operands (transposes)
         pk(W1e, t["WnT"][:, 0:D], c0=0, cols=D, transpose=True)
         pk(W1e, t["WnT"][:, D:2 * D], c0=D, cols=D, transpose=True)
@@ -141,11 +146,27 @@ class PackedLayerWeights:
             pk(W2u, t["W2uT"], transpose=True)
             pk(W1u, t["W1uT"], transpose=True)
         q.flush()
+        # composed operands in fp32 (one launch): Wgc = Wgtp W2m (+ its transpose), bgc += Wgtp b2m, bWm += b2m
+        b2m = p["mlp.2.bias"].data
+        sg = _lib.SgemmBatch()
+        d = sg.d[0]
+        d.A, d.lda, d.B, d.ldb = self.Wgtp_f32.data_ptr(), D, W2m.data_ptr(), W2m.stride(0)
+        d.Cb, d.ldcb, d.CbT, d.ldcbT = t["Wgc"].data_ptr(), D, t["WgcT"].data_ptr(), self.c3p
+        d.M, d.N, d.K = 3 * c, D, D
+        d = sg.d[1]
+        d.A, d.lda, d.B, d.ldb, d.C, d.ldc = self.Wgtp_f32.data_ptr(), D, b2m.data_ptr(), 1, self.bgc.data_ptr(), 1
+        d.M, d.N, d.K, d.accumulate = 3 * c, 1, D, 1
+        d = sg.d[2]
+        d.A, d.lda, d.B, d.ldb, d.C, d.ldc = b2m.data_ptr(), 1, self.one.data_ptr(), 1, self.bWm.data_ptr(), 1
+        d.M, d.N, d.K, d.accumulate = D, 1, 1, 1
+        sg.n = 3
+        _lib.check(_lib.load().rpg_sgemm_batch(C.byref(sg), ops._stream(W2m)), "rpg_sgemm_batch")
         s = self.struct
         s.D = D
         s.variant = self.variant
         for name, tensor in t.items():
             setattr(s, name, tensor.data_ptr())
+        s.bgc, s.bWm, s.Wgtp_f32, s.W2m_f32 = self.bgc.data_ptr(), self.bWm.data_ptr(), self.Wgtp_f32.data_ptr(), W2m.data_ptr()
         s.b1e = p["edge_model.edge_mlp.0.bias"].data_ptr()
         s.b2e = p["edge_model.edge_mlp.2.bias"].data_ptr()
         s.b1m = p["mlp.0.bias"].data_ptr()
@@ -265,7 +286,7 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
 
     v1 = weights.variant == 1
     a = {"x": x, "e": e, "P": new(Nt, (4 if v1 else 3) * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
-         "m": new(Et, D), "gtp": new(Et, 3 * c, torch.float32),
+         "gtp": new(Et, 3 * c, torch.float32),                      # m is never materialised (rpg.h: Wgc / WWM)
          "y": new(Et, cp, zero=(cp != c)),
          "ybar": new(Nt, cp), "mbar": new(Nt, D), "a": new(Nt, D)}
     u8 = torch.uint8
@@ -275,8 +296,8 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
         a.update({"h3": new(Nt, D), "out": new(Nt, D)})
         if for_backward:
             a["h3_bits"] = new(Nt, D // 8, u8)
-    if for_backward:
-        a["att_aux"] = new(Et, 4 * c, torch.float32)           # attention row statistics: the backward skips a sweep
+    if for_backward and not _lib.load().rpg_attention_series_enabled():
+        a["att_aux"] = new(Et, 4 * c, torch.float32)           # exp2 attention only: row statistics, the backward skips a sweep
     if want_relu_copies:
         if v1:
             raise ValueError("ReLU copies are a feature of the simpleConvEdge_upt stack path")
@@ -329,8 +350,8 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
             keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D)})
         keep.update({"dan": new(Nt, D), "dyn": new(Nt, c, f32),
                      "dgtp": new(Et, c3p, zero=(c3p != 3 * c)),
-                     "dm": new(Et, D), "dh2": new(Et, D), "de_tot": new(Et, D),
-                     "ysum": new(Nt, cp), "gtp_bias_tmp": new(1, c3p, f32)})
+                     "dh2": new(Et, D), "de_tot": new(Et, D), "Q": new(Nt, D), "h2sum": new(Nt, D),
+                     "ysum": new(Nt, cp), "gtp_bias_tmp": new(1, c3p, f32), "T_tmp": new(3 * c, D, f32)})
     for k, v in keep.items():
         setattr(b, k, v.data_ptr())
     b.d_out = ops.ptr(d_out)
