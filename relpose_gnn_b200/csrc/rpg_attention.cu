@@ -7,9 +7,12 @@
 // exponentials (c = 64: 4096 MUFU.EX2 forward and again backward, which made the former kernels MUFU-bound at 200 us per
 // launch); the backward is separable in the same way (moments over i).  The order K follows from the row's own range
 // R = max_i |phi_i| * (max_j theta_j - min_j theta_j) / 2: the truncation error relative to the softmax denominator is
-// <= R^(K+1) / (K+1)!, kept below 1e-7 (fp32 rounding level) with two extra orders for the derivative polynomials.  Rows
-// with R > 3.4 (K would exceed 20) take the EXACT path -- the former warp-per-row exp2 code -- inside the same kernel, so
-// the result is the reference's softmax to fp32 accuracy for every input.
+// <= R^(K+1) / (K+1)!; K is taken one order higher than a 2e-8 bound needs (fp32 mode) or a 2e-6 bound (bf16 mode, where
+// the result is rounded to 8 bits right after), the extra order covering the derivative polynomials of the backward.
+// Rows beyond the K = 20 bound (R > 3.4 / 4.3) take the EXACT path -- warp-per-row exp2 with the rank-1 row maximum --
+// inside the same kernel, so the result is the reference's softmax to fp32 accuracy for every input.  Measured on B200
+// (294 912 rows, c = 64, K = 10): forward 115 us, backward 194 us against 323 / 701 us for the exp2 kernels; rows on the
+// exact path cost about twice the exp2 kernels (8 warps per SM hide the MUFU latency less well).
 //
 // Mapping: one THREAD per edge row (the moments are private sums: no shuffles), rows staged through shared memory with
 // 16-byte cp.async (coalesced; row pitch 3c + 4 floats keeps the per-thread float4 reads bank-conflict free), results
@@ -43,36 +46,45 @@ __device__ __forceinline__ float inv_fact(int k) {
     return t[k];
 }
 
-// Series class of a row from its range R (see the header): 0..3 -> K = 6 / 10 / 14 / 20, 4 -> exact path.
-// Bounds: R^K / K! <= 2e-8 (the order K - 1 bound: margin for the derivative polynomials of the backward); measured
-// against an fp64 softmax at the class limits: truncation < 1e-9, fp32 evaluation 1e-7 (tests/test_gpu_attention.py).
-__device__ __forceinline__ int series_class(float R) {
-    return R <= 0.15f ? 0 : (R <= 0.75f ? 1 : (R <= 1.7f ? 2 : (R <= 3.4f ? 3 : 4)));
+// Series class of a row from its range R (see the header): 0..4 -> K = 4 / 6 / 10 / 14 / 20, 5 -> exact path.
+// strict (fp32 mode, results kept as (hi, lo) planes): R^K / K! <= 2e-8 -- the order K - 1 bound, one order of margin for
+// the derivative polynomials of the backward; measured against an fp64 softmax at the class limits: truncation < 1e-9,
+// fp32 evaluation 1e-7 (tests/test_gpu_attention.py).  Otherwise (bf16 mode: the result is rounded to 8 bits right
+// after): R^K / K! <= 2e-6.
+__device__ __forceinline__ int series_class(float R, bool strict) {
+    if (strict) return R <= 0.026f ? 0 : (R <= 0.15f ? 1 : (R <= 0.75f ? 2 : (R <= 1.7f ? 3 : (R <= 3.4f ? 4 : 5))));
+    return R <= 0.083f ? 0 : (R <= 0.33f ? 1 : (R <= 1.2f ? 2 : (R <= 2.4f ? 3 : (R <= 4.3f ? 4 : 5))));
 }
 
-// (U_k, T_k) = (sum_j beta_j^k, sum_j beta_j^k g_j) / k!  for k = 0..KM over the staged row r = (g | theta | phi)
+// (U_k, T_k) = (sum_j beta_j^k, sum_j beta_j^k g_j) / k!  for k = 0..KM over the staged row r = (g | theta | phi).
+// Two columns j share every instruction: P = (beta_a^k, beta_b^k), U2_k += P, T2_k += P * (g_a, g_b), P *= (beta_a, beta_b).
 template <int KM>
 __device__ __forceinline__ void series_moments(const float* r, int c, float b0, float2 (&UT)[KM + 1]) {
+    float2 U2[KM + 1], T2[KM + 1];
 #pragma unroll
-    for (int k = 0; k <= KM; ++k) UT[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k <= KM; ++k) { U2[k] = make_float2(0.f, 0.f); T2[k] = make_float2(0.f, 0.f); }
+    const float2 nb0 = b2(-b0);
     for (int j = 0; j < c; j += 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(r + c + j);
         const float4 g4 = *reinterpret_cast<const float4*>(r + j);
-        const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float beta = tt[q] - b0;
-            const float2 og = make_float2(1.f, gg[q]);
-            float p = 1.f;
+        for (int h = 0; h < 2; ++h) {
+            const float2 beta = __fadd2_rn(h ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y), nb0);
+            const float2 gg = h ? make_float2(g4.z, g4.w) : make_float2(g4.x, g4.y);
+            // k = 0: P = 1
+            T2[0] = __fadd2_rn(T2[0], gg);
+            float2 P = beta;
 #pragma unroll
-            for (int k = 0; k <= KM; ++k) {
-                UT[k] = __ffma2_rn(b2(p), og, UT[k]);
-                p *= beta;
+            for (int k = 1; k <= KM; ++k) {
+                U2[k] = __fadd2_rn(U2[k], P);
+                T2[k] = __ffma2_rn(P, gg, T2[k]);
+                if (k < KM) P = __fmul2_rn(P, beta);
             }
         }
     }
+    UT[0] = make_float2((float)c, T2[0].x + T2[0].y);
 #pragma unroll
-    for (int k = 2; k <= KM; ++k) UT[k] = __fmul2_rn(UT[k], b2(inv_fact(k)));
+    for (int k = 1; k <= KM; ++k) UT[k] = make_float2((U2[k].x + U2[k].y) * inv_fact(k), (T2[k].x + T2[k].y) * inv_fact(k));
 }
 
 // forward of one row: y_i = N_i / D_i written over g (r[i]); the row's g values are consumed before
@@ -100,14 +112,15 @@ template <int KM>
 __device__ __forceinline__ void series_bwd_row(float* r, int c, float b0, const float* __restrict__ dy) {
     float2 UT[KM + 1];
     series_moments<KM>(r, c, b0, UT);
-    float2 AB[KM + 2];                                   // (sum_i w_i phi_i^k, sum_i w_i y_i phi_i^k), k = 0..KM+1
+    // (A_k, B_k) = (sum_i w_i phi_i^k, sum_i w_i y_i phi_i^k), k = 0..KM+1, two rows i per instruction
+    float2 A2[KM + 2], B2[KM + 2];
 #pragma unroll
-    for (int k = 0; k <= KM + 1; ++k) AB[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k <= KM + 1; ++k) { A2[k] = make_float2(0.f, 0.f); B2[k] = make_float2(0.f, 0.f); }
     for (int i = 0; i < c; i += 4) {
         const float4 p4 = *reinterpret_cast<const float4*>(r + 2 * c + i);
         const float4 d4 = __ldg(reinterpret_cast<const float4*>(dy + i));
         const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-        float dphi[4];
+        float dphi[4], yv[4], wv[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float2 ph = b2(pp[q]);
@@ -118,45 +131,52 @@ __device__ __forceinline__ void series_bwd_row(float* r, int c, float b0, const 
                 DN = __ffma2_rn(DN, ph, UT[k]);
             }
             const float invD = __fdividef(1.f, DN.x);
-            const float y = DN.y * invD, w = dd[q] * invD;
-            dphi[q] = w * (dDN.y - y * dDN.x);               // sum_j dl_ij theta_j (the b0 part sums to zero)
-            const float2 oy = make_float2(1.f, y);
-            float qv = w;
-#pragma unroll
-            for (int k = 0; k <= KM + 1; ++k) {
-                AB[k] = __ffma2_rn(b2(qv), oy, AB[k]);
-                qv *= pp[q];
-            }
+            yv[q] = DN.y * invD;
+            wv[q] = dd[q] * invD;
+            dphi[q] = wv[q] * (dDN.y - yv[q] * dDN.x);           // sum_j dl_ij theta_j (the b0 part sums to zero)
         }
         *reinterpret_cast<float4*>(r + 2 * c + i) = make_float4(dphi[0], dphi[1], dphi[2], dphi[3]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 ph = make_float2(pp[2 * h], pp[2 * h + 1]), y2 = make_float2(yv[2 * h], yv[2 * h + 1]);
+            float2 Q = make_float2(wv[2 * h], wv[2 * h + 1]);
+#pragma unroll
+            for (int k = 0; k <= KM + 1; ++k) {
+                A2[k] = __fadd2_rn(A2[k], Q);
+                B2[k] = __ffma2_rn(Q, y2, B2[k]);
+                if (k <= KM) Q = __fmul2_rn(Q, ph);
+            }
+        }
     }
     // dg_j = sum_k A_k beta^k / k!;  dtheta_j = g_j sum_k A_{k+1} beta^k / k! - sum_k B_{k+1} beta^k / k!
-    float C[KM + 1];
+    float C[KM + 1], SA[KM + 1], SB[KM + 1];
 #pragma unroll
     for (int k = 0; k <= KM; ++k) {
-        C[k] = AB[k].x * inv_fact(k);
-        AB[k] = __fmul2_rn(AB[k + 1], b2(inv_fact(k)));      // AB[k] now holds (A_{k+1}, B_{k+1}) / k!
+        C[k] = (A2[k].x + A2[k].y) * inv_fact(k);
+        SA[k] = (A2[k + 1].x + A2[k + 1].y) * inv_fact(k);
+        SB[k] = (B2[k + 1].x + B2[k + 1].y) * inv_fact(k);
     }
+    const float2 nb0 = b2(-b0);
     for (int j = 0; j < c; j += 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(r + c + j);
         const float4 g4 = *reinterpret_cast<const float4*>(r + j);
-        const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
-        float dg[4], dt[4];
+        float2 dgo[2], dto[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float beta = tt[q] - b0;
-            float a0 = C[KM];
-            float2 s = AB[KM];
+        for (int h = 0; h < 2; ++h) {
+            const float2 beta = __fadd2_rn(h ? make_float2(t4.z, t4.w) : make_float2(t4.x, t4.y), nb0);
+            const float2 gg = h ? make_float2(g4.z, g4.w) : make_float2(g4.x, g4.y);
+            float2 a0 = b2(C[KM]), sa = b2(SA[KM]), sb = b2(SB[KM]);
 #pragma unroll
             for (int k = KM - 1; k >= 0; --k) {
-                a0 = fmaf(a0, beta, C[k]);
-                s = __ffma2_rn(s, b2(beta), AB[k]);
+                a0 = __ffma2_rn(a0, beta, b2(C[k]));
+                sa = __ffma2_rn(sa, beta, b2(SA[k]));
+                sb = __ffma2_rn(sb, beta, b2(SB[k]));
             }
-            dg[q] = a0;
-            dt[q] = gg[q] * s.x - s.y;
+            dgo[h] = a0;
+            dto[h] = make_float2(gg.x * sa.x - sb.x, gg.y * sa.y - sb.y);
         }
-        *reinterpret_cast<float4*>(r + j) = make_float4(dg[0], dg[1], dg[2], dg[3]);
-        *reinterpret_cast<float4*>(r + c + j) = make_float4(dt[0], dt[1], dt[2], dt[3]);
+        *reinterpret_cast<float4*>(r + j) = make_float4(dgo[0].x, dgo[0].y, dgo[1].x, dgo[1].y);
+        *reinterpret_cast<float4*>(r + c + j) = make_float4(dto[0].x, dto[0].y, dto[1].x, dto[1].y);
     }
 }
 
@@ -222,27 +242,36 @@ __device__ void exact_bwd_row(const float* r, int c, float tmax, float tmin, con
     __syncwarp();
 }
 
+// Row tiles are staged with 16-byte cp.async (consecutive lanes -> consecutive 16 bytes of the dense [Et, 3c] tensor);
+// rows beyond Et are zero-filled.  (A double-buffered bulk-copy variant with one warp per scheduler was measured slower:
+// the kernel is issue-bound, so the second tile costs more in lost warps than the overlap buys.)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Stages 32 rows of gtp [Et, 3c] (row0 ..) into the warp's tile (pitch `pitch` floats); rows beyond Et are zero-filled.
-__device__ __forceinline__ void stage_rows(const float* __restrict__ gtp, long long row0, long long Et, int c, float* tile,
-                                           int pitch, int lane) {
+__device__ __forceinline__ void stage_issue(const float* __restrict__ gtp, long long row0, long long Et, int c, float* tile,
+                                            int pitch, int lane) {
     const int per_row = 3 * c / 4;                       // 16-byte chunks per row
-    for (int idx = lane; idx < 32 * per_row; idx += 32) {
-        const int rr = idx / per_row, q = idx - rr * per_row;
+    const float* src = gtp + row0 * 3 * c;
+    int rr = 0, q = lane;
+    while (q >= per_row) { q -= per_row; ++rr; }
+    while (rr < 32) {
         float* dst = tile + rr * pitch + 4 * q;
-        if (row0 + rr < Et) cp_async16(dst, gtp + (row0 + rr) * 3 * c + 4 * q);
+        if (row0 + rr < Et) cp_async16(dst, src + (size_t)rr * 3 * c + 4 * q);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        q += 32;
+        while (q >= per_row) { q -= per_row; ++rr; }
     }
-    cp_async_wait_all();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
     __syncwarp();
 }
 
 // per-thread row statistics: theta extremes and the series class
-__device__ __forceinline__ int row_stats(const float* r, int c, float& tmax, float& tmin, float& b0) {
+__device__ __forceinline__ int row_stats(const float* r, int c, float& tmax, float& tmin, float& b0, bool strict) {
     tmax = -INFINITY; tmin = INFINITY;
     float amax = 0.f;
     for (int j = 0; j < c; j += 4) {
@@ -254,9 +283,43 @@ __device__ __forceinline__ int row_stats(const float* r, int c, float& tmax, flo
     }
     b0 = 0.5f * (tmax + tmin);
     const float R = amax * 0.5f * (tmax - tmin);
-    return (R == R) ? series_class(R) : 4;               // NaN / inf inputs propagate through the exact path
+    return (R == R) ? series_class(R, strict) : 5;       // NaN / inf inputs propagate through the exact path
 }
 
+// fp32 rows of the tile -> bf16 (and optionally the low plane) rows in global memory, 16 bytes per lane and store
+__device__ __forceinline__ void store_rows_bf16(const float* tile, int pitch, int cols, long long row0, long long Et,
+                                                unsigned skip_rows, bf16* __restrict__ out, int ld, bf16* __restrict__ out_lo,
+                                                int lane) {
+    const int per_row = cols / 8;
+    int rr = 0, q = lane;
+    while (q >= per_row) { q -= per_row; ++rr; }
+    while (rr < 32) {
+        if (row0 + rr < Et && !((skip_rows >> rr) & 1u)) {
+            const float* src = tile + rr * pitch + 8 * q;
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            uint4 u;
+            u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+            *reinterpret_cast<uint4*>(out + (row0 + rr) * ld + 8 * q) = u;
+            if (out_lo) {
+                const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                float l[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) l[t] = f[t] - __bfloat162float(__float2bfloat16_rn(f[t]));
+                uint4 v;
+                v.x = pack_bf16x2(l[0], l[1]); v.y = pack_bf16x2(l[2], l[3]); v.z = pack_bf16x2(l[4], l[5]); v.w = pack_bf16x2(l[6], l[7]);
+                *reinterpret_cast<uint4*>(out_lo + (row0 + rr) * ld + 8 * q) = v;
+            }
+        }
+        q += 32;
+        while (q >= per_row) { q -= per_row; ++rr; }
+    }
+}
+
+constexpr int EXACT_CLASS = 5;
+
+// PIPE: two tiles per warp -- the next 32 rows are in flight (cp.async) while the current ones are worked on; the CTA is
+// persistent (one per SM).  !PIPE: one tile per warp, twice the warps per SM.
+template <bool PIPE>
 __global__ void __launch_bounds__(128)
 attention_series_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, bf16* __restrict__ y, int ldy,
                             bf16* __restrict__ y_lo, int force_exact) {
@@ -264,28 +327,39 @@ attention_series_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, 
     extern __shared__ __align__(16) float ats_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int pitch = 3 * c + 4;
-    float* tile = ats_smem + (size_t)warp * 32 * pitch;
-    float* r = tile + lane * pitch;
+    float* tiles = ats_smem + (size_t)warp * (PIPE ? 2 : 1) * 32 * pitch;
+    const bool strict = y_lo != nullptr;
     const long long nblk = (Et + 31) / 32;
-    for (long long blk = (long long)blockIdx.x * nwarps + warp; blk < nblk; blk += (long long)gridDim.x * nwarps) {
+    const long long gw = (long long)blockIdx.x * nwarps + warp, tw = (long long)gridDim.x * nwarps;
+    if (PIPE && gw < nblk) stage_issue(gtp, gw * 32, Et, c, tiles, pitch, lane);
+    int it = 0;
+    for (long long blk = gw; blk < nblk; blk += tw, ++it) {
         const long long row0 = blk * 32;
-        stage_rows(gtp, row0, Et, c, tile, pitch, lane);
+        float* tile = tiles + (PIPE ? (it & 1) * 32 * pitch : 0);
+        if (PIPE) {
+            if (blk + tw < nblk) { stage_issue(gtp, (blk + tw) * 32, Et, c, tiles + ((it & 1) ^ 1) * 32 * pitch, pitch, lane); stage_wait<1>(); }
+            else stage_wait<0>();
+        } else {
+            stage_issue(gtp, row0, Et, c, tile, pitch, lane);
+            stage_wait<0>();
+        }
+        float* r = tile + lane * pitch;
         float tmax, tmin, b0;
-        int cls = row_stats(r, c, tmax, tmin, b0);
-        if (force_exact) cls = 4;
-        const bool row_ok = row0 + lane < Et;
-        if (!row_ok) cls = 0;
-        const int top = __reduce_max_sync(0xffffffffu, cls < 4 ? cls : 0);   // one order for all series rows of the warp
-        if (cls < 4) {
+        int cls = row_stats(r, c, tmax, tmin, b0, strict);
+        if (force_exact) cls = EXACT_CLASS;
+        if (row0 + lane >= Et) cls = 0;
+        const int top = __reduce_max_sync(0xffffffffu, cls < EXACT_CLASS ? cls : 0);   // one order for the warp's series rows
+        if (cls < EXACT_CLASS) {
             switch (top) {
-                case 0: series_fwd_row<6>(r, c, b0); break;
-                case 1: series_fwd_row<10>(r, c, b0); break;
-                case 2: series_fwd_row<14>(r, c, b0); break;
+                case 0: series_fwd_row<4>(r, c, b0); break;
+                case 1: series_fwd_row<6>(r, c, b0); break;
+                case 2: series_fwd_row<10>(r, c, b0); break;
+                case 3: series_fwd_row<14>(r, c, b0); break;
                 default: series_fwd_row<20>(r, c, b0); break;
             }
         }
         __syncwarp();
-        unsigned exact = __ballot_sync(0xffffffffu, cls == 4);
+        unsigned exact = __ballot_sync(0xffffffffu, cls == EXACT_CLASS);
         const unsigned exact_rows = exact;
         while (exact) {                                   // whole warp on one row at a time
             const int rr = __ffs(exact) - 1;
@@ -294,25 +368,7 @@ attention_series_fwd_kernel(const float* __restrict__ gtp, long long Et, int c, 
             exact_fwd_row(tile + rr * pitch, c, xmax, xmin, y + (row0 + rr) * ldy, y_lo ? y_lo + (row0 + rr) * ldy : nullptr, lane);
         }
         // coalesced write-back of the series rows: y_i sits in the first c floats of every staged row
-        const int per_row = c / 8;
-        for (int idx = lane; idx < 32 * per_row; idx += 32) {
-            const int rr = idx / per_row, q = idx - rr * per_row;
-            if (row0 + rr >= Et || ((exact_rows >> rr) & 1u)) continue;
-            const float* src = tile + rr * pitch + 8 * q;
-            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-            uint4 u;
-            u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
-            *reinterpret_cast<uint4*>(y + (row0 + rr) * ldy + 8 * q) = u;
-            if (y_lo) {
-                const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                float l[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) l[t] = f[t] - __bfloat162float(__float2bfloat16_rn(f[t]));
-                uint4 v;
-                v.x = pack_bf16x2(l[0], l[1]); v.y = pack_bf16x2(l[2], l[3]); v.z = pack_bf16x2(l[4], l[5]); v.w = pack_bf16x2(l[6], l[7]);
-                *reinterpret_cast<uint4*>(y_lo + (row0 + rr) * ldy + 8 * q) = v;
-            }
-        }
+        store_rows_bf16(tile, pitch, c, row0, Et, exact_rows, y, ldy, y_lo, lane);
         __syncwarp();
     }
 }
@@ -328,29 +384,32 @@ attention_series_bwd_kernel(const float* __restrict__ gtp, const float* __restri
     float* tile = ats_smem + (size_t)warp * (32 * pitch + 5 * c);
     float* scratch = tile + 32 * pitch;
     float* r = tile + lane * pitch;
+    const bool strict = dgtp_lo != nullptr;
     const long long nblk = (Et + 31) / 32;
     for (long long blk = (long long)blockIdx.x * nwarps + warp; blk < nblk; blk += (long long)gridDim.x * nwarps) {
         const long long row0 = blk * 32;
-        stage_rows(gtp, row0, Et, c, tile, pitch, lane);
+        stage_issue(gtp, row0, Et, c, tile, pitch, lane);
+        stage_wait<0>();
         const bool row_ok = row0 + lane < Et;
         const long long row = row_ok ? row0 + lane : Et - 1;
         const long long gi = row / Ep;
         const float* dy = dyn + (gi * Nn + __ldg(tdst + (int)(row - gi * Ep))) * ld_dyn;
         float tmax, tmin, b0;
-        int cls = row_stats(r, c, tmax, tmin, b0);
-        if (force_exact) cls = 4;
+        int cls = row_stats(r, c, tmax, tmin, b0, strict);
+        if (force_exact) cls = EXACT_CLASS;
         if (!row_ok) cls = 0;
-        const int top = __reduce_max_sync(0xffffffffu, cls < 4 ? cls : 0);
-        if (cls < 4) {
+        const int top = __reduce_max_sync(0xffffffffu, cls < EXACT_CLASS ? cls : 0);
+        if (cls < EXACT_CLASS) {
             switch (top) {
-                case 0: series_bwd_row<6>(r, c, b0, dy); break;
-                case 1: series_bwd_row<10>(r, c, b0, dy); break;
-                case 2: series_bwd_row<14>(r, c, b0, dy); break;
+                case 0: series_bwd_row<4>(r, c, b0, dy); break;
+                case 1: series_bwd_row<6>(r, c, b0, dy); break;
+                case 2: series_bwd_row<10>(r, c, b0, dy); break;
+                case 3: series_bwd_row<14>(r, c, b0, dy); break;
                 default: series_bwd_row<20>(r, c, b0, dy); break;
             }
         }
         __syncwarp();
-        unsigned exact = __ballot_sync(0xffffffffu, cls == 4);
+        unsigned exact = __ballot_sync(0xffffffffu, cls == EXACT_CLASS);
         const unsigned exact_rows = exact;
         while (exact) {
             const int rr = __ffs(exact) - 1;
@@ -364,32 +423,14 @@ attention_series_bwd_kernel(const float* __restrict__ gtp, const float* __restri
             }
         }
         // coalesced write-back: (dg | dtheta | dphi) fp32 in the staged rows -> bf16 [Et, ld_dgtp]
-        const int per_row = 3 * c / 8;
-        for (int idx = lane; idx < 32 * per_row; idx += 32) {
-            const int rr = idx / per_row, q = idx - rr * per_row;
-            if (row0 + rr >= Et || ((exact_rows >> rr) & 1u)) continue;
-            const float* src = tile + rr * pitch + 8 * q;
-            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-            uint4 u;
-            u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
-            *reinterpret_cast<uint4*>(dgtp + (row0 + rr) * ld_dgtp + 8 * q) = u;
-            if (dgtp_lo) {
-                const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                float l[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) l[t] = f[t] - __bfloat162float(__float2bfloat16_rn(f[t]));
-                uint4 v;
-                v.x = pack_bf16x2(l[0], l[1]); v.y = pack_bf16x2(l[2], l[3]); v.z = pack_bf16x2(l[4], l[5]); v.w = pack_bf16x2(l[6], l[7]);
-                *reinterpret_cast<uint4*>(dgtp_lo + (row0 + rr) * ld_dgtp + 8 * q) = v;
-            }
-        }
+        store_rows_bf16(tile, pitch, 3 * c, row0, Et, exact_rows, dgtp, ld_dgtp, dgtp_lo, lane);
         __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 static std::mutex g_ats_mu;
-static size_t g_ats_limit[2][64];
+static size_t g_ats_limit[3][64];
 
 template <typename K>
 static void ats_smem_limit(K kern, int which, size_t bytes) {
@@ -421,25 +462,49 @@ static int force_exact() {
     return v;
 }
 
-static int ats_warps(int c, size_t per_warp_bytes) {
+static int ats_warps(size_t per_warp_bytes) {
     int w = 4;
-    while (w > 1 && (size_t)w * per_warp_bytes > 200 * 1024) w >>= 1;
+    while (w > 1 && (size_t)w * per_warp_bytes > 110 * 1024) w >>= 1;      // two CTAs per SM where the row width allows
     return w;
+}
+
+// RPG_ATT_PIPE=1: double-buffered persistent forward (two tiles per warp, 4 warps per SM).  Measured on B200 at
+// 294 912 rows, c = 64: 183 us against 115 us for the single-tile form with 8 warps per SM -- the kernel is issue-bound
+// (O(c K) FMAs per row with short dependent chains), warps matter more than overlap.  Kept for A/B runs; default off.
+static int att_pipe() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RPG_ATT_PIPE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
 }
 
 int attention_series_fwd(const float* gtp, long long Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, cudaStream_t s) {
     if (c % 16 || c < 16 || c > 256 || ldy % 8) return set_error(RPG_E_UNSUPPORTED, "attention_fwd (series): c must be a multiple of 16 in [16,256], ldy of 8");
-    const size_t per_warp = (size_t)32 * (3 * c + 4) * sizeof(float);
-    const int warps = ats_warps(c, per_warp);
+    const size_t tile = (size_t)32 * (3 * c + 4) * sizeof(float);
+    const bool pipe = att_pipe() && 2 * tile <= 225 * 1024;
+    const size_t per_warp = pipe ? 2 * tile : tile;
+    int warps = 4;
+    while (warps > 1 && (size_t)warps * per_warp > (pipe ? 225 : 110) * 1024) warps >>= 1;
     const size_t smem = warps * per_warp;
     if (smem > 227 * 1024) return set_error(RPG_E_UNSUPPORTED, "attention_fwd (series): row too wide for shared memory");
-    ats_smem_limit(attention_series_fwd_kernel, 0, smem);
+    if (pipe) ats_smem_limit(attention_series_fwd_kernel<true>, 0, smem);
+    else ats_smem_limit(attention_series_fwd_kernel<false>, 2, smem);
     const long long nblk = (Et + 31) / 32;
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int per_sm = (int)((227 * 1024) / smem) > 0 ? (int)((227 * 1024) / smem) : 1;
     long long grid = (nblk + warps - 1) / warps;
-    if (grid > 148 * 8) grid = 148 * 8;
+    const long long cap = pipe ? (long long)sms * per_sm : (long long)sms * per_sm * 4;
+    if (grid > cap) grid = cap;
     ProfScope prof(RPG_PROF_ATTENTION_FWD, (double)Et * c * (12.0 + 2.0 + (y_lo ? 2.0 : 0.0)), s, 0.0);
-    launch_pdl(attention_series_fwd_kernel, dim3((unsigned)grid), dim3(warps * 32), smem, s, gtp, Et, c,
-               reinterpret_cast<bf16*>(y), ldy, reinterpret_cast<bf16*>(y_lo), force_exact());
+    if (pipe)
+        launch_pdl(attention_series_fwd_kernel<true>, dim3((unsigned)grid), dim3(warps * 32), smem, s, gtp, Et, c,
+                   reinterpret_cast<bf16*>(y), ldy, reinterpret_cast<bf16*>(y_lo), force_exact());
+    else
+        launch_pdl(attention_series_fwd_kernel<false>, dim3((unsigned)grid), dim3(warps * 32), smem, s, gtp, Et, c,
+                   reinterpret_cast<bf16*>(y), ldy, reinterpret_cast<bf16*>(y_lo), force_exact());
     return check_launch("attention_series_fwd_kernel");
 }
 
@@ -448,13 +513,16 @@ int attention_series_bwd(const float* gtp, const float* dyn, int ld_dyn, const r
     if (c % 16 || c < 16 || c > 256 || ld_dgtp % 8 || ld_dyn % 4)
         return set_error(RPG_E_UNSUPPORTED, "attention_bwd (series): c must be a multiple of 16 in [16,256]");
     const size_t per_warp = ((size_t)32 * (3 * c + 4) + 5 * c) * sizeof(float);
-    const int warps = ats_warps(c, per_warp);
+    const int warps = ats_warps(per_warp);
     const size_t smem = warps * per_warp;
     if (smem > 227 * 1024) return set_error(RPG_E_UNSUPPORTED, "attention_bwd (series): row too wide for shared memory");
     ats_smem_limit(attention_series_bwd_kernel, 1, smem);
     const long long nblk = (Et + 31) / 32;
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int per_sm = (int)((227 * 1024) / smem) > 0 ? (int)((227 * 1024) / smem) : 1;
     long long grid = (nblk + warps - 1) / warps;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > (long long)sms * per_sm * 4) grid = (long long)sms * per_sm * 4;
     ProfScope prof(RPG_PROF_ATTENTION_BWD, (double)Et * c * (12.0 + 6.0 + (dgtp_lo ? 6.0 : 0.0)) + (double)graph->G * graph->N * c * 4.0, s, 0.0);
     launch_pdl(attention_series_bwd_kernel, dim3((unsigned)grid), dim3(warps * 32), smem, s, gtp, dyn, ld_dyn, graph->dst,
                graph->Ep, graph->N, Et, c, reinterpret_cast<bf16*>(dgtp), ld_dgtp, reinterpret_cast<bf16*>(dgtp_lo), force_exact());
