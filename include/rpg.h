@@ -341,6 +341,12 @@ int rpg_segment_sum(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, c
                     const int32_t* csr_idx, const float* scale, const rpg_graph_t* graph, int D,
                     rpg_bf16* out, int ldo, rpg_stream_t stream);
 
+/* Two segment sums of the same edge tensor in one pass over HBM (the backward's scatters come in pairs: by source and by
+ * destination, by lower and by upper endpoint): which_* selects the CSR, 0 = in (destination), 1 = out (source),
+ * 2 = min endpoint, 3 = max endpoint.  out_x[g*N+n, :] = sum_{k in csr_x(n)} v[g*Ep+k, :].                     */
+int rpg_segment_sum2(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, int which_a, int which_b, int D, rpg_bf16* out_a,
+                     int ldo_a, rpg_bf16* out_b, int ldo_b, rpg_stream_t stream);
+
 /* Edge-feature initialiser, posenet.py:1014-1017 + :1053-1055 in factorised form:
  * e0[g*Ep+k, :] = relu(pmin[node(min(s,t)), :] + pmax[node(max(s,t)), :] + bias), where
  * pminmax [Nt, 2D] = x * [W_min; W_max]^T (proj_edge.weight[:, 0:D] and [:, D:2D]).

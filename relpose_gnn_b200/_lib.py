@@ -150,6 +150,7 @@ SIGNATURES = {
     "rpg_aggregate_mean": (I, [P, I, C.POINTER(Graph), I, P, I, P]),
     "rpg_edge_to_node_sum": (I, [P, I, C.POINTER(Graph), I, I, P, I, P]),
     "rpg_segment_sum": (I, [P, I, P, I, P, P, P, C.POINTER(Graph), I, P, I, P]),
+    "rpg_segment_sum2": (I, [P, I, C.POINTER(Graph), I, I, I, P, I, P, I, P]),
     "rpg_edge_init_fwd": (I, [P, I, P, C.POINTER(Graph), I, P, I, P, P]),
     "rpg_dropout_mask": (I, [U64, F, I64, I, P, P]),
     "rpg_head_fwd": (I, [P, P, I, I64, I, P, U64, F, P, P, P, P]),

@@ -472,6 +472,52 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
     }
 }
 
+// Two segment sums of the SAME edge tensor in one pass (by source and by destination of dh1; by lower and by upper endpoint
+// of the edge-initialiser gradient): a thread owns 8 columns of one node row and walks both CSRs.  Every edge row is
+// read by two threads of the same graph a few hundred cycles apart, so the second read is an L1 / L2 hit and DRAM
+// sees the tensor once.  Fixed order: deterministic.
+template <typename I>
+__global__ void segment_sum2_kernel(const bf16* __restrict__ v, int ldv, const int* __restrict__ ptr_a,
+                                    const int* __restrict__ idx_a, const int* __restrict__ ptr_b,
+                                    const int* __restrict__ idx_b, long long Nt, int N, int Ep, int D,
+                                    bf16* __restrict__ out_a, int ldo_a, bf16* __restrict__ out_b, int ldo_b) {
+    pdl_prologue();
+    const int tpr = D >> 3;
+    const I total = (I)Nt * (I)tpr;
+    for (I t = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; t < total; t += (I)gridDim.x * (I)blockDim.x) {
+        const I row_i = t / (I)tpr;
+        const int c = (int)(t - row_i * (I)tpr) << 3;
+        const I g_i = row_i / (I)N;
+        const int n = (int)(row_i - g_i * (I)N);
+        const long long row = (long long)row_i, g = (long long)g_i;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int* __restrict__ ptr = pass ? ptr_b : ptr_a;
+            const int* __restrict__ idx = pass ? idx_b : idx_a;
+            const int k0 = __ldg(ptr + n), k1 = __ldg(ptr + n + 1);
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int kb = k0; kb < k1; kb += 4) {
+                uint4 u[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = kb + j < k1;
+                    const long long er = g * Ep + (ok ? __ldg(idx + kb + j) : 0);
+                    u[j] = ok ? __ldg(reinterpret_cast<const uint4*>(v + er * ldv + c)) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float f[8];
+                    unpack8(u[j], f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] += f[q];
+                }
+            }
+            bf16* o = pass ? out_b + row * ldo_b : out_a + row * ldo_a;
+            *reinterpret_cast<uint4*>(o + c) = pack8(acc);
+        }
+    }
+}
+
 __global__ void scale_rows_kernel(const bf16* __restrict__ v, int ldv, long long rows, int D, const float* __restrict__ scale,
                                   int mod, bf16* __restrict__ out, int ldo) {
     pdl_prologue();
@@ -1511,6 +1557,24 @@ int rpg_edge_to_node_sum(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, i
 int rpg_segment_sum(const rpg_bf16* v, int ldv, const rpg_bf16* mask, int ldm, const int32_t* csr_ptr, const int32_t* csr_idx,
                     const float* scale, const rpg_graph_t* graph, int D, rpg_bf16* out, int ldo, rpg_stream_t stream) {
     return launch_segment(v, ldv, mask, ldm, csr_ptr, csr_idx, scale, graph, D, out, ldo, as_stream(stream));
+}
+
+int rpg_segment_sum2(const rpg_bf16* v, int ldv, const rpg_graph_t* g, int which_a, int which_b, int D, rpg_bf16* out_a,
+                     int ldo_a, rpg_bf16* out_b, int ldo_b, rpg_stream_t stream) {
+    if (!v || !g || !out_a || !out_b || D % 8 || ldv % 8 || ldo_a % 8 || ldo_b % 8 || (which_a & ~3) || (which_b & ~3))
+        return set_error(RPG_E_ARG, "segment_sum2: bad arguments");
+    const int32_t* ptrs[4] = {g->in_ptr, g->out_ptr, g->min_ptr, g->max_ptr};
+    const int32_t* idxs[4] = {g->in_idx, g->out_idx, g->min_idx, g->max_idx};
+    const long long Nt = (long long)g->G * g->N;
+    cudaStream_t s = as_stream(stream);
+    // algorithmic bytes: the edge tensor once, two node tensors
+    ProfScope prof(RPG_PROF_SEGMENT_SUM, ((double)g->G * g->Ep + 2.0 * (double)Nt) * D * 2.0, s);
+    const bool small = Nt * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
+    auto kern = small ? segment_sum2_kernel<unsigned> : segment_sum2_kernel<long long>;
+    launch_pdl(kern, dim3(grid_for(Nt * (D / 8), 256)), dim3(256), 0, s, reinterpret_cast<const bf16*>(v), ldv, ptrs[which_a],
+               idxs[which_a], ptrs[which_b], idxs[which_b], Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out_a), ldo_a,
+               reinterpret_cast<bf16*>(out_b), ldo_b);
+    return check_launch("segment_sum2_kernel");
 }
 
 int rpg_edge_init_fwd(const rpg_bf16* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e0,

@@ -539,8 +539,7 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     RPG_TRY(gemm_launch(&g, s));
 
     // ---- node side: dP = [sum_src dh1 | sum_dst dh1 | sum_src dh2], dx = dP Wn + dx_u
-    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 1, b->dP, ldP, stream));
-    RPG_TRY(rpg_edge_to_node_sum(b->dh1, D, gr, D, 0, b->dP + D, ldP, stream));
+    RPG_TRY(rpg_segment_sum2(b->dh1, D, gr, /*by source*/ 1, /*by destination*/ 0, D, b->dP, ldP, b->dP + D, ldP, stream));
     if (have_out) {
         RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 1, b->dP + 2 * D, ldP, stream));
         if (v1) RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 0, b->dP + 3 * D, ldP, stream));

@@ -48,6 +48,9 @@ class DeviceFeeder:
                 b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, host_tensors)):
             bufs = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors]
             self.slots[k] = bufs
+            # A fresh block of the caching allocator may be a recycled one whose previous user (a kernel still queued on
+            # the compute stream) has not run yet: the copy stream must not write into it before that work is done.
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             if self.free[k] is not None:
                 self.copy_stream.wait_event(self.free[k])

@@ -133,8 +133,7 @@ class _StackFn(torch.autograd.Function):
 
         # edge-feature initialiser backward: d_e is already masked by (e0 > 0)
         dpmm = arena.take(Nt, 2 * D)
-        ops.segment_sum(d_e, graph, "min", dpmm[:, :D])
-        ops.segment_sum(d_e, graph, "max", dpmm[:, D:])
+        ops.segment_sum2(d_e, graph, "min", dpmm[:, :D], "max", dpmm[:, D:])
         dx = arena.take(Nt, D)
         ops.gemm_nt(dpmm, sw["WmmT"], resid=d_x, out=dx)
         gw = grads["proj_edge.weight"]

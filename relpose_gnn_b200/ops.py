@@ -275,6 +275,15 @@ def segment_sum(v, graph, which, out, mask=None, scale=None, D=None):
                                       graph.byref(), D, out.data_ptr(), out.stride(0), _stream(v)), "rpg_segment_sum")
 
 
+def segment_sum2(v, graph, which_a, out_a, which_b, out_b, D=None):
+    """Two segment sums of the same edge tensor in one pass: which_* in {'in','out','min','max'}."""
+    code = {"in": 0, "out": 1, "min": 2, "max": 3}
+    D = D if D is not None else v.size(1)
+    check(_lib.load().rpg_segment_sum2(v.data_ptr(), v.stride(0), graph.byref(), code[which_a], code[which_b], D,
+                                       out_a.data_ptr(), out_a.stride(0), out_b.data_ptr(), out_b.stride(0), _stream(v)),
+          "rpg_segment_sum2")
+
+
 def edge_gather(pa, which_a, graph, out, pb=None, which_b="src", bias=None, relu=False, mask_bits=None, out_bits=None):
     """out[e] = act(pa[node_a(e)] + pb[node_b(e)] + bias) * bit(e); which_x in {'src', 'dst'}."""
     code = {"src": 0, "dst": 1}
