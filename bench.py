@@ -242,7 +242,7 @@ def run_ours(args):
     bucket = parallel.FlatGradBucket(params) if train else None
     opt = None
     if train:
-        model.attach_grad_bucket(bucket)
+        model.attach_grad_bucket(bucket, overlap=args.overlap_allreduce and world > 1)
         if args.optimizer:
             # train.py:211: Adam over the parameters of the path; one fused kernel over the flat buckets.  Its 1/world
             # folds the gradient average of the data-parallel sum, and every step re-packs the bf16 operands.
@@ -282,7 +282,10 @@ def run_ours(args):
             loss, t_loss, q_loss = crit(pe, poses, ei_used)
             loss.backward()
             if opt is not None:
-                bucket.allreduce(average=False)
+                if args.overlap_allreduce and world > 1:
+                    bucket.finish_allreduce(average=False)
+                else:
+                    bucket.allreduce(average=False)
                 opt.step(grad_scale=1.0 / world)
             else:
                 bucket.allreduce()
@@ -458,6 +461,8 @@ def main():
                          "attached: the caller builds the GraphBatch and annotates the tensor (A/B)")
     ap.add_argument("--validation", default="async", choices=["async", "sync"],
                     help="edge_index validation read-back: async (checked one step late) or sync (one event wait per step)")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="start the all-reduce of every gradient but proj_edge's from inside the backward (A/B)")
     ap.add_argument("--no-ref-eager", dest="ref_eager", action="store_false",
                     help="skip the informative reference-in-torch-eager-on-the-GPU column")
     args = ap.parse_args()

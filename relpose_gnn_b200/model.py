@@ -130,6 +130,11 @@ class _StackFn(torch.autograd.Function):
         for r in range(R - 1, -1, -1):
             d_x, d_e = layer_backward_raw(lw, graph, acts[r], d_x, d_e, lgrads, mask_dx=(r > 0), mask_de=True, arena=arena)
             acts[r] = None                                      # free this round's activations
+        # Every gradient except proj_edge's is final here (the criterion's and the heads' came first): with an attached
+        # bucket in overlap mode their all-reduce starts now and runs under the edge-initialiser backward below.
+        if direct and model._early_reduce is not None:
+            bucket, ranges = model._early_reduce
+            bucket.begin_allreduce(ranges)
 
         # edge-feature initialiser backward: d_e is already masked by (e0 > 0)
         dpmm = arena.take(Nt, 2 * D)
@@ -174,7 +179,9 @@ class RelPoseGNN(nn.Module):
         self.tensor_core_heads = True            # seeded dropout fused into the last GEMMs + heads as GEMMs (see _StackFn)
         self.precision = "bf16"                  # or "fp32": split-bf16 arithmetic, inference only for now
 
-    def attach_grad_bucket(self, bucket):
+    _early_reduce = None
+
+    def attach_grad_bucket(self, bucket, overlap=False):
         """Makes backward accumulate every gradient of this module directly into `param.grad` (which a
         parallel.FlatGradBucket has pointed at one flat buffer) instead of returning fresh tensors to autograd:
         the weight-gradient kernels already accumulate (+=), so a step needs no per-parameter add kernels."""
@@ -183,6 +190,9 @@ class RelPoseGNN(nn.Module):
         if not mine <= have:
             raise ValueError("the bucket must cover every parameter of this module")
         self.fused_grad_accumulation = True
+        # overlap: the all-reduce of everything but proj_edge's gradients is launched from inside the backward (see
+        # _StackFn.backward); finish with bucket.finish_allreduce() instead of bucket.allreduce()
+        self._early_reduce = (bucket, bucket.ranges_excluding(list(self.proj_edge.parameters()))) if overlap else None
         return self
 
     def _param_names(self):

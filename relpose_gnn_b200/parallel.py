@@ -101,5 +101,50 @@ class FlatGradBucket:
             self.flat.div_(dist.get_world_size(group))
         return self.flat
 
+    # ---- overlapped reduction: the part of the bucket that is final before the backward has finished goes first
+    def ranges_excluding(self, late_params):
+        """Contiguous [lo, hi) ranges of the flat buffer that do NOT hold gradients of `late_params`."""
+        late = {id(p) for p in late_params}
+        ranges, off, lo = [], 0, None
+        for p in self.params:
+            if id(p) in late:
+                if lo is not None:
+                    ranges.append((lo, off))
+                    lo = None
+            elif lo is None:
+                lo = off
+            off += p.numel()
+        if lo is not None:
+            ranges.append((lo, off))
+        return ranges
+
+    def begin_allreduce(self, ranges, group=None):
+        """Starts asynchronous all-reduces (SUM) of flat[lo:hi] for the given ranges: the collectives run on NCCL's own
+        stream behind everything queued so far, while the caller keeps enqueueing the rest of the backward.  The
+        remaining ranges are reduced by the next `allreduce()` call, which also waits for these."""
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        self._pending = [(lo, hi, dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+                         for lo, hi in ranges]
+
+    def finish_allreduce(self, group=None, average=True):
+        """Reduces whatever `begin_allreduce` left out, waits for everything, scales by 1 / world if `average`."""
+        self.reattach(keep=True)
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            self._pending = []
+            return self.flat
+        done = sorted((lo, hi) for lo, hi, _ in getattr(self, "_pending", []))
+        pos = 0
+        for lo, hi in done + [(self.numel, self.numel)]:
+            if lo > pos:
+                dist.all_reduce(self.flat[pos:lo], op=dist.ReduceOp.SUM, group=group)
+            pos = max(pos, hi)
+        for _, _, work in getattr(self, "_pending", []):
+            work.wait()
+        self._pending = []
+        if average:
+            self.flat.div_(dist.get_world_size(group))
+        return self.flat
+
     def nbytes(self):
         return self.numel * 4

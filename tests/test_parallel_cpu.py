@@ -42,7 +42,11 @@ def _worker(rank, world, port, out):
         bucket.zero()
         lin(data[lo:hi]).pow(2).mean().backward()
         assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())   # still views
-        bucket.allreduce()
+        if _ == 0:
+            bucket.allreduce()
+        else:       # overlapped form: everything but the first layer's weight goes first, the rest at the end
+            bucket.begin_allreduce(bucket.ranges_excluding([lin[0].weight]))
+            bucket.finish_allreduce()
     if rank == 0:
         torch.save(bucket.flat.clone(), out)
     dist.barrier()
@@ -81,3 +85,14 @@ def test_bucket_reattaches_after_zero_grad_set_to_none():
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
     bucket.zero()
     assert float(bucket.flat.abs().sum()) == 0.0 and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+
+
+def test_ranges_excluding_late_parameters():
+    a, b, c = (torch.nn.Parameter(torch.zeros(n)) for n in (3, 5, 2))
+    bucket = parallel.FlatGradBucket([a, b, c])
+    assert bucket.ranges_excluding([a]) == [(3, 10)]
+    assert bucket.ranges_excluding([b]) == [(0, 3), (8, 10)]
+    assert bucket.ranges_excluding([c]) == [(0, 8)]
+    assert bucket.ranges_excluding([]) == [(0, 10)]
+    bucket.begin_allreduce([(3, 10)])                 # no process group: nothing to do
+    assert bucket.finish_allreduce() is bucket.flat
