@@ -577,6 +577,14 @@ int rpg_pack_weight_lo(const float* src, int ld_src, int r0, int c0, int rows, i
                        int ld_dst, rpg_stream_t stream);
 int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D,
                           rpg_bf16* e_hi, rpg_bf16* e_lo, int lde, rpg_stream_t stream);
+/* the same with the ReLU bit pattern of e0 [Et, D/8] for the backward (e_bits may be NULL) */
+int rpg_edge_init_fwd_split(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D,
+                            rpg_bf16* e_hi, rpg_bf16* e_lo, int lde, uint8_t* e_bits, rpg_stream_t stream);
+/* rpg_head_bwd for (hi, lo) features; dfeat as (hi, lo) planes */
+int rpg_head_bwd_split(const float* dpose, const rpg_bf16* feat_hi, const rpg_bf16* feat_lo, int ldf, int64_t rows, int D,
+                       const uint8_t* keep, uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat_hi,
+                       rpg_bf16* dfeat_lo, int lddf, float* dw_t, float* dw_q, float* db_t, float* db_q, int accumulate,
+                       float* ws, rpg_stream_t stream);
 int rpg_aggregate_mean_split(const rpg_bf16* z_hi, const rpg_bf16* z_lo, int ldz, const rpg_graph_t* graph, int D,
                              rpg_bf16* a_hi, rpg_bf16* a_lo, int lda, rpg_stream_t stream);
 
@@ -585,6 +593,15 @@ typedef struct {
   /* every operand is [N, 3K] = [W_hi | W_hi | W_lo] along K (W1u3: [D, 6D] = x part then a part)      */
   const rpg_bf16 *Wn3, *W1e_e3, *W2e3, *W1m_e3, *W2m3, *Wgtp3, *WW3, *W1u3, *W2u3;
   const float *b1e, *b2e, *b1m, *b2m, *bgtp, *bW, *b1u, *b2u;
+  /* composed operands (the message m is never materialised, see rpg_layer_weights_t): Wgc3 [3c, 3D] of Wgtp W2m,
+   * WWM3 [D, 3 pad64(c) + 3D] = [WW3 | W2m3], bgc [3c] = Wgtp b2m + bgtp, bWm [D] = bW + b2m                     */
+  const rpg_bf16 *Wgc3, *WWM3;
+  const float *bgc, *bWm;
+  /* backward (dgrad) operands, [N, 3K] = [W^T_hi | W^T_hi | W^T_lo]: WnT3 [D, 9D], W1uT3 [2D, 3D] (x rows, then a rows),
+   * WgcT3 [D, 3 pad64(3c)], WWT3 [c, 3D], the others [D, 3D]; NULL for inference                                  */
+  const rpg_bf16 *WnT3, *W1e_eT3, *W2eT3, *W1m_eT3, *W2mT3, *WgcT3, *WWT3, *W1uT3, *W2uT3;
+  const rpg_bf16 *WnT3_sd;                  /* [D, 6D]: WnT3 restricted to the two edge-MLP blocks (rounds without d_out) */
+  const float *Wgtp_f32, *W2m_f32;          /* master weights for the small fp32 products of the backward          */
 } rpg_layer_weights_split_t;
 
 typedef struct {
@@ -598,10 +615,47 @@ typedef struct {
   rpg_bf16* mbar_hi, *mbar_lo;    /* [Nt, D]         scratch: mean over in-edges of m   (z is never materialised) */
   rpg_bf16* P_hi, *P_lo;          /* [Nt, 3D] node projections as (hi, lo) planes: with selection patterns in the graph
                                      the gathered terms are one-hot K panels over both planes (P may then be NULL)  */
+  /* ReLU bit patterns for the backward (optional, as in rpg_layer_acts_t)                                          */
+  uint8_t *h1_bits, *h2_bits, *h3_bits, *e_new_bits, *out_bits;
+  const uint8_t *x_bits, *e_bits;
 } rpg_layer_acts_split_t;
 
 int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* graph,
                         const rpg_layer_acts_split_t* t, rpg_stream_t stream);
+
+/* Backward of rpg_layer_fwd_split: the sequence of rpg_layer_bwd with every value a (hi, lo) pair, every dgrad GEMM the
+ * 3-segment form [dY_hi | dY_lo | dY_hi] [W^T_hi | W^T_hi | W^T_lo]^T and every weight gradient three TN launches
+ * (hi^T hi + lo^T hi + hi^T lo, fp32 partials folded in a fixed order).  split_ws: 3 * rpg_layer_bwd_ws_floats().      */
+typedef struct {
+  const rpg_bf16 *d_out_hi, *d_out_lo;        /* [Nt, D] grad wrt out (pre-ReLU) or NULL                            */
+  const rpg_bf16 *d_e_new_hi, *d_e_new_lo;    /* [Et, D] grad wrt e_new (pre-ReLU) or NULL                          */
+  int mask_dx, mask_de;
+  rpg_bf16 *dx_hi, *dx_lo, *de_hi, *de_lo;    /* outputs                                                            */
+  /* scratch (shapes as rpg_layer_grads_t) */
+  rpg_bf16 *dh3_hi, *dh3_lo, *dxu_hi, *dxu_lo, *dan_hi, *dan_lo;
+  float* dyn;
+  rpg_bf16 *dgtp_hi, *dgtp_lo, *Q_hi, *Q_lo, *dh2_hi, *dh2_lo, *de_tot_hi, *de_tot_lo, *dh1_hi, *dh1_lo, *dP_hi, *dP_lo;
+  rpg_bf16 *ysum_hi, *ysum_lo, *h2sum_hi, *h2sum_lo;
+  float *split_ws, *colsum_ws, *gtp_bias_tmp, *T_tmp;
+  /* fp32 weight gradients in the reference's state_dict layout, accumulated (+=) */
+  float* g_mlp0_w;  float* g_mlp0_b;  float* g_mlp2_w;  float* g_mlp2_b;
+  float* g_upd0_w;  float* g_upd0_b;  float* g_upd2_w;  float* g_upd2_b;
+  float* g_edge0_w; float* g_edge0_b; float* g_edge2_w; float* g_edge2_b;
+  float* g_att_g_w; float* g_att_g_b; float* g_att_theta_w; float* g_att_theta_b; float* g_att_phi_w; float* g_att_phi_b;
+  float* g_att_W_w; float* g_att_W_b;
+} rpg_layer_grads_split_t;
+int rpg_layer_bwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* graph, const rpg_layer_acts_split_t* t,
+                        const rpg_layer_grads_split_t* g, rpg_stream_t stream);
+/* split-plane forms of the bandwidth kernels the fp32-mode training step needs */
+int rpg_segment_sum_split(const rpg_bf16* v_hi, const rpg_bf16* v_lo, int ldv, const int32_t* csr_ptr, const int32_t* csr_idx,
+                          const float* scale, const rpg_graph_t* graph, int D, rpg_bf16* out_hi, rpg_bf16* out_lo, int ldo,
+                          rpg_stream_t stream);
+int rpg_attention_bwd_split(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
+                            rpg_bf16* dgtp_hi, rpg_bf16* dgtp_lo, int ld_dgtp, rpg_stream_t stream);
+/* dW[M, N] += (A_hi + A_lo)^T (B_hi + B_lo) to first order (the lo^T lo term, 2^-18 relative, is dropped), and
+ * bias[m] += column sums of A_hi + A_lo (bias may be NULL); ws: 3 * rpg_layer_bwd_ws_floats() floats.               */
+int rpg_wgrad_split(const rpg_bf16* A_hi, const rpg_bf16* A_lo, int lda, int M, const rpg_bf16* B_hi, const rpg_bf16* B_lo,
+                    int ldb, int N, int64_t R, float* ws, float* out, int ldo, float* bias, rpg_stream_t stream);
 
 int64_t rpg_layer_bwd_ws_floats(int D, int64_t Et, int64_t Nt);
 int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,

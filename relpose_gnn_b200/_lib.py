@@ -60,14 +60,32 @@ class LayerActs(C.Structure):
 
 class LayerWeightsSplit(C.Structure):
     _fields_ = [("D", I)] + [(n, P) for n in ("Wn3", "W1e_e3", "W2e3", "W1m_e3", "W2m3", "Wgtp3", "WW3", "W1u3", "W2u3",
-                                              "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u")]
+                                              "b1e", "b2e", "b1m", "b2m", "bgtp", "bW", "b1u", "b2u",
+                                              "Wgc3", "WWM3", "bgc", "bWm",
+                                              "WnT3", "W1e_eT3", "W2eT3", "W1m_eT3", "W2mT3", "WgcT3", "WWT3", "W1uT3", "W2uT3",
+                                              "WnT3_sd", "Wgtp_f32", "W2m_f32")]
 
 
 class LayerActsSplit(C.Structure):
     _fields_ = [(n, P) for n in ("x_hi", "x_lo", "e_hi", "e_lo", "P", "h1_hi", "h1_lo", "e_new_hi", "e_new_lo",
                                  "e_new_relu_hi", "e_new_relu_lo", "h2_hi", "h2_lo", "m_hi", "m_lo", "gtp", "y_hi", "y_lo",
                                  "z_hi", "z_lo", "a_hi", "a_lo", "h3_hi", "h3_lo", "out_hi", "out_lo", "out_relu_hi",
-                                 "out_relu_lo", "ybar_hi", "ybar_lo", "mbar_hi", "mbar_lo", "P_hi", "P_lo")]
+                                 "out_relu_lo", "ybar_hi", "ybar_lo", "mbar_hi", "mbar_lo", "P_hi", "P_lo",
+                                 "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits", "x_bits", "e_bits")]
+
+
+_GRAD_NAMES = ("g_mlp0_w", "g_mlp0_b", "g_mlp2_w", "g_mlp2_b", "g_upd0_w", "g_upd0_b", "g_upd2_w", "g_upd2_b",
+               "g_edge0_w", "g_edge0_b", "g_edge2_w", "g_edge2_b",
+               "g_att_g_w", "g_att_g_b", "g_att_theta_w", "g_att_theta_b", "g_att_phi_w", "g_att_phi_b",
+               "g_att_W_w", "g_att_W_b")
+
+
+class LayerGradsSplit(C.Structure):
+    _fields_ = ([(n, P) for n in ("d_out_hi", "d_out_lo", "d_e_new_hi", "d_e_new_lo")] + [("mask_dx", I), ("mask_de", I)] +
+                [(n, P) for n in ("dx_hi", "dx_lo", "de_hi", "de_lo", "dh3_hi", "dh3_lo", "dxu_hi", "dxu_lo", "dan_hi", "dan_lo",
+                                  "dyn", "dgtp_hi", "dgtp_lo", "Q_hi", "Q_lo", "dh2_hi", "dh2_lo", "de_tot_hi", "de_tot_lo",
+                                  "dh1_hi", "dh1_lo", "dP_hi", "dP_lo", "ysum_hi", "ysum_lo", "h2sum_hi", "h2sum_lo",
+                                  "split_ws", "colsum_ws", "gtp_bias_tmp", "T_tmp") + _GRAD_NAMES])
 
 
 class LayerGrads(C.Structure):
@@ -146,6 +164,13 @@ SIGNATURES = {
     "rpg_edge_init_fwd_f32": (I, [P, I, P, C.POINTER(Graph), I, P, P, I, P]),
     "rpg_aggregate_mean_split": (I, [P, P, I, C.POINTER(Graph), I, P, P, I, P]),
     "rpg_layer_fwd_split": (I, [C.POINTER(LayerWeightsSplit), C.POINTER(Graph), C.POINTER(LayerActsSplit), P]),
+    "rpg_layer_bwd_split": (I, [C.POINTER(LayerWeightsSplit), C.POINTER(Graph), C.POINTER(LayerActsSplit),
+                                C.POINTER(LayerGradsSplit), P]),
+    "rpg_segment_sum_split": (I, [P, P, I, P, P, P, C.POINTER(Graph), I, P, P, I, P]),
+    "rpg_attention_bwd_split": (I, [P, P, I, C.POINTER(Graph), I64, I, P, P, I, P]),
+    "rpg_wgrad_split": (I, [P, P, I, I, P, P, I, I, I64, P, P, I, P, P]),
+    "rpg_edge_init_fwd_split": (I, [P, I, P, C.POINTER(Graph), I, P, P, I, P, P]),
+    "rpg_head_bwd_split": (I, [P, P, P, I, I64, I, P, U64, F, P, I, P, P, I, P, P, P, P, I, P, P]),
     "rpg_attention_bwd": (I, [P, P, I, C.POINTER(Graph), I64, I, P, I, P, P]),
     "rpg_aggregate_mean": (I, [P, I, C.POINTER(Graph), I, P, I, P]),
     "rpg_edge_to_node_sum": (I, [P, I, C.POINTER(Graph), I, I, P, I, P]),
@@ -193,7 +218,7 @@ def _check_layout(lib):
     want = [C.sizeof(Graph), C.sizeof(Gemm), C.sizeof(LayerWeights), C.sizeof(LayerActs), C.sizeof(LayerGrads),
             Gemm.out_f32.offset, LayerGrads.g_mlp0_w.offset, LayerWeights.b1e.offset,
             C.sizeof(LayerWeightsSplit), C.sizeof(LayerActsSplit), C.sizeof(PackDesc), C.sizeof(PackBatch),
-            C.sizeof(ProfRec), C.sizeof(SgemmBatch), 0, 0]
+            C.sizeof(ProfRec), C.sizeof(SgemmBatch), C.sizeof(LayerGradsSplit), 0]
     if list(probe) != want:
         raise RpgError(f"ctypes mirrors out of sync with include/rpg.h: library {list(probe)} vs python {want}")
 

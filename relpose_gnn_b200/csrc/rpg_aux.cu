@@ -636,7 +636,8 @@ __global__ void edge_gather_kernel(const bf16* __restrict__ pa, int lda, int whi
 // fp32 mode: pmm fp32 [Nt, 2D] -> e0 (hi, lo)
 __global__ void edge_init_fwd_f32_kernel(const float* __restrict__ pmm, int ldp, const float* __restrict__ bias,
                                          const int* __restrict__ tsrc, const int* __restrict__ tdst, long long Et, int N,
-                                         int Ep, int D, bf16* __restrict__ e_hi, bf16* __restrict__ e_lo, int lde) {
+                                         int Ep, int D, bf16* __restrict__ e_hi, bf16* __restrict__ e_lo, int lde,
+                                         uint8_t* __restrict__ bits) {
     pdl_prologue();
     const int tpr = D >> 2;
     const long long total = Et * tpr;
@@ -660,6 +661,13 @@ __global__ void edge_init_fwd_f32_kernel(const float* __restrict__ pmm, int ldp,
         l.x = pack_bf16x2(r[0], r[1]); l.y = pack_bf16x2(r[2], r[3]);
         *reinterpret_cast<uint2*>(e_hi + row * lde + c) = h;
         *reinterpret_cast<uint2*>(e_lo + row * lde + c) = l;
+        if (bits) {                                        // 4 pattern bits per thread; the two threads of a byte merge by shuffle
+            unsigned m = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m |= (unsigned)(v[q] > 0.f) << q;
+            const unsigned other = __shfl_xor_sync(__activemask(), m, 1);
+            if (!(t & 1)) bits[row * (D >> 3) + (c >> 3)] = (uint8_t)(m | (other << 4));
+        }
     }
 }
 
@@ -846,7 +854,7 @@ head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, 
                 int D, const uint8_t* __restrict__ keep, unsigned long long seed, uint32_t thresh,
                 int use_seed, float scale, const float* __restrict__ w6, int mask_relu,
                 bf16* __restrict__ dfeat, int lddf, float* __restrict__ dw6_part,
-                float* __restrict__ db6_part) {
+                float* __restrict__ db6_part, const bf16* __restrict__ feat_lo, bf16* __restrict__ dfeat_lo) {
     pdl_prologue();
     extern __shared__ __align__(16) float hb_smem[];   // [phases-1][48][ct] + [phases][6]
     const int ct = D >> 3;                              // column threads
@@ -874,6 +882,12 @@ head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, 
             for (int j = 0; j < 6; ++j) dp[j] = __ldg(dpose + row * 6 + j);
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(feat + row * ldf + c)), f);
+            if (feat_lo) {                                    // fp32 mode: value = hi + lo
+                float fl[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(feat_lo + row * ldf + c)), fl);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] += fl[q];
+            }
             float km[8];
             if (keep) {
                 const uint2 k8 = __ldg(reinterpret_cast<const uint2*>(keep + row * D + c));
@@ -903,6 +917,12 @@ head_bwd_kernel(const float* __restrict__ dpose, const bf16* __restrict__ feat, 
                 for (int j = 0; j < 6; ++j) gw[j][q] = __ffma2_rn(fd, make_float2(dp[j], dp[j]), gw[j][q]);
             }
             if (dfeat) *reinterpret_cast<uint4*>(dfeat + row * lddf + c) = pack8(d);
+            if (dfeat_lo) {
+                float dl[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dl[q] = d[q] - __bfloat162float(__float2bfloat16_rn(d[q]));
+                *reinterpret_cast<uint4*>(dfeat_lo + row * lddf + c) = pack8(dl);
+            }
             if (tx == 0) {
 #pragma unroll
                 for (int j = 0; j < 6; ++j) gb[j] += dp[j];
@@ -1472,14 +1492,23 @@ int rpg_pack_weight_lo(const float* src, int ld_src, int r0, int c0, int rows, i
     launch_pdl(pack_weight_lo_kernel, dim3(grid), dim3(128), 0, as_stream(stream), src, ld_src, r0, c0, rows, cols, reinterpret_cast<bf16*>(dst), ld_dst);
     return check_launch("pack_weight_lo_kernel");
 }
+static int edge_init_f32_impl(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e_hi,
+                              rpg_bf16* e_lo, int lde, uint8_t* bits, rpg_stream_t stream) {
+    if (!pminmax || !bias || !graph || !e_hi || !e_lo || D % 8 || ldp % 4 || lde % 4) return set_error(RPG_E_ARG, "edge_init_fwd_f32: bad arguments");
+    const long long Et = (long long)graph->G * graph->Ep;
+    // total threads is even (D / 4 is even) and a block is a multiple of 32: shuffle partners always exist
+    launch_pdl(edge_init_fwd_f32_kernel, dim3(grid_for(Et * (D / 4), 256)), dim3(256), 0, as_stream(stream),
+        pminmax, ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D, reinterpret_cast<bf16*>(e_hi),
+        reinterpret_cast<bf16*>(e_lo), lde, bits);
+    return check_launch("edge_init_fwd_f32_kernel");
+}
 int rpg_edge_init_fwd_f32(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e_hi,
                           rpg_bf16* e_lo, int lde, rpg_stream_t stream) {
-    if (!pminmax || !bias || !graph || !e_hi || !e_lo || D % 4 || ldp % 4 || lde % 4) return set_error(RPG_E_ARG, "edge_init_fwd_f32: bad arguments");
-    const long long Et = (long long)graph->G * graph->Ep;
-    launch_pdl(edge_init_fwd_f32_kernel, dim3(grid_for(Et * (D / 4), 256)), dim3(256), 0, as_stream(stream), 
-        pminmax, ldp, bias, graph->src, graph->dst, Et, graph->N, graph->Ep, D, reinterpret_cast<bf16*>(e_hi),
-        reinterpret_cast<bf16*>(e_lo), lde);
-    return check_launch("edge_init_fwd_f32_kernel");
+    return edge_init_f32_impl(pminmax, ldp, bias, graph, D, e_hi, e_lo, lde, nullptr, stream);
+}
+int rpg_edge_init_fwd_split(const float* pminmax, int ldp, const float* bias, const rpg_graph_t* graph, int D, rpg_bf16* e_hi,
+                            rpg_bf16* e_lo, int lde, uint8_t* e_bits, rpg_stream_t stream) {
+    return edge_init_f32_impl(pminmax, ldp, bias, graph, D, e_hi, e_lo, lde, e_bits, stream);
 }
 
 int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, float* aux,
@@ -1545,6 +1574,19 @@ int rpg_aggregate_mean_split(const rpg_bf16* z_hi, const rpg_bf16* z_lo, int ldz
     if (!graph || !z_lo || !a_lo) return set_error(RPG_E_ARG, "aggregate_mean_split: null argument");
     return launch_segment(z_hi, ldz, nullptr, 0, graph->in_ptr, graph->in_idx, graph->inv_deg, graph, D, a_hi, lda,
                           as_stream(stream), z_lo, a_lo);
+}
+
+int rpg_segment_sum_split(const rpg_bf16* v_hi, const rpg_bf16* v_lo, int ldv, const int32_t* csr_ptr, const int32_t* csr_idx,
+                          const float* scale, const rpg_graph_t* graph, int D, rpg_bf16* out_hi, rpg_bf16* out_lo, int ldo,
+                          rpg_stream_t stream) {
+    if (!graph || !v_lo || !out_lo) return set_error(RPG_E_ARG, "segment_sum_split: null argument");
+    return launch_segment(v_hi, ldv, nullptr, 0, csr_ptr, csr_idx, scale, graph, D, out_hi, ldo, as_stream(stream), v_lo, out_lo);
+}
+
+int rpg_attention_bwd_split(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
+                            rpg_bf16* dgtp_hi, rpg_bf16* dgtp_lo, int ld_dgtp, rpg_stream_t stream) {
+    if (!gtp || !dyn || !graph || !dgtp_hi || !dgtp_lo || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd_split: bad arguments");
+    return attention_series_bwd(gtp, dyn, ld_dyn, graph, Et, c, dgtp_hi, ld_dgtp, dgtp_lo, as_stream(stream));
 }
 
 int rpg_edge_to_node_sum(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, int D, int by_src, rpg_bf16* out, int ldo,
@@ -1631,9 +1673,31 @@ int64_t rpg_head_bwd_ws_floats(int64_t rows, int D) {
     return blocks * (6 * (int64_t)D + 6);
 }
 
+static int head_bwd_impl(const float* dpose, const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t rows, int D,
+                         const uint8_t* keep, uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat,
+                         rpg_bf16* dfeat_lo, int lddf, float* dw_t, float* dw_q, float* db_t, float* db_q, int accumulate,
+                         float* ws, rpg_stream_t stream);
+
 int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows, int D, const uint8_t* keep, uint64_t seed,
                  float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat, int lddf, float* dw_t, float* dw_q,
                  float* db_t, float* db_q, int accumulate, float* ws, rpg_stream_t stream) {
+    return head_bwd_impl(dpose, feat, nullptr, ldf, rows, D, keep, seed, p_drop, w6, mask_relu, dfeat, nullptr, lddf, dw_t, dw_q,
+                         db_t, db_q, accumulate, ws, stream);
+}
+
+int rpg_head_bwd_split(const float* dpose, const rpg_bf16* feat_hi, const rpg_bf16* feat_lo, int ldf, int64_t rows, int D,
+                       const uint8_t* keep, uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat_hi,
+                       rpg_bf16* dfeat_lo, int lddf, float* dw_t, float* dw_q, float* db_t, float* db_q, int accumulate,
+                       float* ws, rpg_stream_t stream) {
+    if (!feat_lo || (dfeat_hi && !dfeat_lo)) return set_error(RPG_E_ARG, "head_bwd_split: low planes missing");
+    return head_bwd_impl(dpose, feat_hi, feat_lo, ldf, rows, D, keep, seed, p_drop, w6, mask_relu, dfeat_hi, dfeat_lo, lddf,
+                         dw_t, dw_q, db_t, db_q, accumulate, ws, stream);
+}
+
+static int head_bwd_impl(const float* dpose, const rpg_bf16* feat, const rpg_bf16* feat_lo, int ldf, int64_t rows, int D,
+                         const uint8_t* keep, uint64_t seed, float p_drop, const float* w6, int mask_relu, rpg_bf16* dfeat,
+                         rpg_bf16* dfeat_lo, int lddf, float* dw_t, float* dw_q, float* db_t, float* db_q, int accumulate,
+                         float* ws, rpg_stream_t stream) {
     if (!dpose || !feat || !w6 || !dw_t || !dw_q || !db_t || !db_q || !ws || rows <= 0 || D % 8 || ldf % 8 || D > 8 * 1024)
         return set_error(RPG_E_ARG, "head_bwd: bad arguments");
     const int blocks = (int)((rows + HEADB_ROWS_PER_BLOCK - 1) / HEADB_ROWS_PER_BLOCK);
@@ -1652,7 +1716,8 @@ int rpg_head_bwd(const float* dpose, const rpg_bf16* feat, int ldf, int64_t rows
     cudaStream_t s = as_stream(stream);
     launch_pdl(head_bwd_kernel, dim3(blocks), dim3(HEADB_THREADS), smem, s, dpose, reinterpret_cast<const bf16*>(feat), ldf, rows, D, keep, seed,
                                                         thresh, use_seed, scale, w6, mask_relu,
-                                                        reinterpret_cast<bf16*>(dfeat), lddf, dw_part, db_part);
+                                                        reinterpret_cast<bf16*>(dfeat), lddf, dw_part, db_part,
+                                                        reinterpret_cast<const bf16*>(feat_lo), reinterpret_cast<bf16*>(dfeat_lo));
     int rc = check_launch("head_bwd_kernel");
     if (rc) return rc;
     // rows 0..2 -> translation head (fc_xyz*), rows 3..5 -> rotation head (fc_wpqr*)

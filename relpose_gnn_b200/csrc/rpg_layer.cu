@@ -207,7 +207,8 @@ void rpg_struct_sizes(int32_t* out) {
     out[11] = (int32_t)sizeof(rpg_pack_batch_t);
     out[12] = (int32_t)sizeof(rpg_prof_rec_t);
     out[13] = (int32_t)sizeof(rpg_sgemm_batch_t);
-    out[14] = out[15] = 0;
+    out[14] = (int32_t)sizeof(rpg_layer_grads_split_t);
+    out[15] = 0;
 }
 
 #define RPG_TRY(expr)            \
@@ -354,12 +355,12 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
         g.gadd_f32[0] = t->P;     g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
         g.gadd_f32[1] = t->P + D; g.gmap[1] = gr->dst; g.gadd_f32_ld[1] = 3 * D;
     }
-    g.out = t->h1_hi; g.out_lo = t->h1_lo; g.ldo = D;
+    g.out = t->h1_hi; g.out_lo = t->h1_lo; g.ldo = D; g.out_bits = t->h1_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
     // (3) e' = h1 W2e^T + b  (+ relu'd copy)
     base((int)Et, D, w->W2e3, 3 * D); g.n_seg = 3; set3(g, 0, t->h1_hi, t->h1_lo, D, D);
     g.bias = w->b2e; g.out = t->e_new_hi; g.out_lo = t->e_new_lo; g.ldo = D;
-    g.out_relu = t->e_new_relu_hi; g.out_relu_lo = t->e_new_relu_lo;
+    g.out_relu = t->e_new_relu_hi; g.out_relu_lo = t->e_new_relu_lo; g.out_bits = t->e_new_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
     // (4) h2 = relu(e' W1m_e^T + P_m[src] + b)
     base((int)Et, D, w->W1m_e3, 3 * D); g.n_seg = 3; set3(g, 0, t->e_new_hi, t->e_new_lo, D, D);
@@ -371,37 +372,240 @@ int rpg_layer_fwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
         g.Ep = gr->Ep; g.Nn = gr->N;
         g.gadd_f32[0] = t->P + 2 * D; g.gmap[0] = gr->src; g.gadd_f32_ld[0] = 3 * D;
     }
-    g.out = t->h2_hi; g.out_lo = t->h2_lo; g.ldo = D;
+    g.out = t->h2_hi; g.out_lo = t->h2_lo; g.ldo = D; g.out_bits = t->h2_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
-    // (5) m = h2 W2m^T + b
-    base((int)Et, D, w->W2m3, 3 * D); g.n_seg = 3; set3(g, 0, t->h2_hi, t->h2_lo, D, D);
-    g.bias = w->b2m; g.out = t->m_hi; g.out_lo = t->m_lo; g.ldo = D;
-    RPG_TRY(gemm_launch(&g, s));
-    // (6) (g | theta | phi) fp32
-    base((int)Et, c3, w->Wgtp3, 3 * D); g.n_seg = 3; set3(g, 0, t->m_hi, t->m_lo, D, D);
-    g.bias = w->bgtp; g.out_f32 = t->gtp; g.ldo_f32 = c3;
+    // (5)+(6) the message m = h2 W2m^T + b2m is never materialised (see rpg_layer_fwd): (g | theta | phi) = h2 Wgc^T + bgc
+    if (!w->Wgc3 || !w->WWM3 || !w->bgc || !w->bWm) return set_error(RPG_E_ARG, "layer_fwd_split: composed operands missing");
+    base((int)Et, c3, w->Wgc3, 3 * D); g.n_seg = 3; set3(g, 0, t->h2_hi, t->h2_lo, D, D);
+    g.bias = w->bgc; g.out_f32 = t->gtp; g.ldo_f32 = c3;
     RPG_TRY(gemm_launch(&g, s));
     // (7) attention -> y (hi, lo)
     RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y_hi, cp, t->y_lo, nullptr, stream));
-    // (8)+(9) mean over incoming edges of z = y WW^T + bW + m, evaluated at node level (the mean is linear; see
-    //     rpg_layer_fwd): a = mean(y) WW^T + bW + mean(m), zero for nodes without incoming edges
+    // (8)+(9) a = mean(y) WW^T + mean(h2) W2m^T + (bW + b2m), zero for nodes without incoming edges
     if (!t->ybar_hi || !t->ybar_lo || !t->mbar_hi || !t->mbar_lo || !gr->has_in)
         return set_error(RPG_E_ARG, "layer_fwd_split: ybar / mbar planes or has_in missing");
     RPG_TRY(rpg_aggregate_mean_split(t->y_hi, t->y_lo, cp, gr, cp, t->ybar_hi, t->ybar_lo, cp, stream));
-    RPG_TRY(rpg_aggregate_mean_split(t->m_hi, t->m_lo, D, gr, D, t->mbar_hi, t->mbar_lo, D, stream));
-    base((int)Nt, D, w->WW3, 3 * cp); g.n_seg = 3; set3(g, 0, t->ybar_hi, t->ybar_lo, cp, cp);
-    g.bias = w->bW; g.resid = t->mbar_hi; g.resid_lo = t->mbar_lo; g.resid_ld = D;
-    g.row_scale = gr->has_in; g.row_scale_mod = gr->N;
+    RPG_TRY(rpg_aggregate_mean_split(t->h2_hi, t->h2_lo, D, gr, D, t->mbar_hi, t->mbar_lo, D, stream));   // mean(h2)
+    base((int)Nt, D, w->WWM3, 3 * cp + 3 * D); g.n_seg = 6;
+    set3(g, 0, t->ybar_hi, t->ybar_lo, cp, cp); set3(g, 3, t->mbar_hi, t->mbar_lo, D, D);
+    g.bias = w->bWm; g.row_scale = gr->has_in; g.row_scale_mod = gr->N;
     g.out = t->a_hi; g.out_lo = t->a_lo; g.ldo = D;
     RPG_TRY(gemm_launch(&g, s));
     // (10) out = relu([x | a] W1u^T + b) W2u^T + b
     base((int)Nt, D, w->W1u3, 6 * D); g.n_seg = 6; set3(g, 0, t->x_hi, t->x_lo, D, D); set3(g, 3, t->a_hi, t->a_lo, D, D);
-    g.bias = w->b1u; g.relu = 1; g.out = t->h3_hi; g.out_lo = t->h3_lo; g.ldo = D;
+    g.bias = w->b1u; g.relu = 1; g.out = t->h3_hi; g.out_lo = t->h3_lo; g.ldo = D; g.out_bits = t->h3_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
     base((int)Nt, D, w->W2u3, 3 * D); g.n_seg = 3; set3(g, 0, t->h3_hi, t->h3_lo, D, D);
     g.bias = w->b2u; g.out = t->out_hi; g.out_lo = t->out_lo; g.ldo = D;
-    g.out_relu = t->out_relu_hi; g.out_relu_lo = t->out_relu_lo;
+    g.out_relu = t->out_relu_hi; g.out_relu_lo = t->out_relu_lo; g.out_bits = t->out_bits; g.out_bits_ld = D / 8;
     RPG_TRY(gemm_launch(&g, s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32-mode backward.  Same sequence as rpg_layer_bwd below; every value is a (hi, lo) bf16 pair.
+namespace {
+struct Pl { const rpg_bf16* hi; const rpg_bf16* lo; };
+struct PlW { rpg_bf16* hi; rpg_bf16* lo; };
+
+// out = epi([A_hi | A_lo | A_hi] B3^T) with B3 = [W_hi | W_hi | W_lo] ([N, 3K], pitch ldb)
+rpg_gemm_t nt3(int M, int N, Pl A, int K, int lda, const rpg_bf16* B3, int ldb) {
+    rpg_gemm_t g;
+    memset(&g, 0, sizeof g);
+    g.mode = 0; g.M = M; g.N = N; g.n_seg = 3; g.B = B3; g.ldb = ldb;
+    g.A[0] = A.hi; g.A[1] = A.lo; g.A[2] = A.hi;
+    for (int i = 0; i < 3; ++i) { g.K[i] = K; g.lda[i] = lda; }
+    return g;
+}
+
+// Three TN launches per weight gradient (hi^T hi, lo^T hi, hi^T lo), each queue with its own workspace third and its own
+// fold launch (descriptors of one launch must not share outputs).
+struct WgradQueue3 {
+    WgradQueue q0, q1, q2;
+    WgradQueue3(float* ws, size_t third, int sms, cudaStream_t s) : q0(ws, sms, s), q1(ws + third, sms, s), q2(ws + 2 * third, sms, s) {}
+    int wgrad(Pl A, int lda, int M, Pl B, int ldb, int N, long long R, float* out, int ldo, float* bias = nullptr) {
+        int rc = q0.wgrad(A.hi, lda, M, B.hi, ldb, N, R, out, ldo, bias);
+        if (!rc) rc = q1.wgrad(A.lo, lda, M, B.hi, ldb, N, R, out, ldo, bias);
+        if (!rc) rc = q2.wgrad(A.hi, lda, M, B.lo, ldb, N, R, out, ldo, nullptr);
+        return rc;
+    }
+    int partials(Pl A, int lda, int M, Pl B, int ldb, int N, long long R, bool with_colsum, float* part[3], int splits[3]) {
+        int rc = q0.partials(A.hi, lda, M, B.hi, ldb, N, R, with_colsum, &part[0], &splits[0]);
+        if (!rc) rc = q1.partials(A.lo, lda, M, B.hi, ldb, N, R, with_colsum, &part[1], &splits[1]);
+        if (!rc) rc = q2.partials(A.hi, lda, M, B.lo, ldb, N, R, false, &part[2], &splits[2]);
+        return rc;
+    }
+    // folds of a stacked product: the same (row block -> parameter) mapping for the three launches
+    int add(float* const part[3], const int splits[3], size_t block_off, long long stride, int rows, int cols, float* out, int ldo) {
+        int rc = q0.add(part[0] + block_off, splits[0], stride, rows, cols, out, ldo);
+        if (!rc) rc = q1.add(part[1] + block_off, splits[1], stride, rows, cols, out, ldo);
+        if (!rc) rc = q2.add(part[2] + block_off, splits[2], stride, rows, cols, out, ldo);
+        return rc;
+    }
+    int flush() {
+        int rc = q0.flush();
+        if (!rc) rc = q1.flush();
+        if (!rc) rc = q2.flush();
+        return rc;
+    }
+};
+}  // namespace
+
+int rpg_wgrad_split(const rpg_bf16* A_hi, const rpg_bf16* A_lo, int lda, int M, const rpg_bf16* B_hi, const rpg_bf16* B_lo,
+                    int ldb, int N, int64_t R, float* ws, float* out, int ldo, float* bias, rpg_stream_t stream) {
+    if (!A_hi || !A_lo || !B_hi || !B_lo || !ws || !out) return set_error(RPG_E_ARG, "wgrad_split: null pointer");
+    WgradQueue3 q(ws, (size_t)rpg_layer_bwd_ws_floats(M > N ? M : N, 0, 0), sm_count_cached(), as_stream(stream));
+    RPG_TRY(q.wgrad({A_hi, A_lo}, lda, M, {B_hi, B_lo}, ldb, N, R, out, ldo, bias));
+    return q.flush();
+}
+
+int rpg_layer_bwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* gr, const rpg_layer_acts_split_t* t,
+                        const rpg_layer_grads_split_t* b, rpg_stream_t stream) {
+    if (!w || !gr || !t || !b) return set_error(RPG_E_ARG, "layer_bwd_split: null argument");
+    if (!w->WnT3 || !w->W2eT3 || !w->WgcT3) return set_error(RPG_E_ARG, "layer_bwd_split: backward operands missing");
+    const int D = w->D, c = D / 8, c3 = 3 * c, cp = pad64(c), c3p = pad64(c3);
+    if (D % 128) return set_error(RPG_E_UNSUPPORTED, "layer_bwd_split: channel count must be a multiple of 128");
+    const long long Nt = (long long)gr->G * gr->N, Et = (long long)gr->G * gr->Ep;
+    cudaStream_t s = as_stream(stream);
+    const int sms = sm_count_cached();
+    rpg_gemm_t g;
+    const bool have_out = b->d_out_hi != nullptr;
+    const int ldP = 3 * D;
+    const bool panels = gr->sel_src && gr->sel_dst;
+    const int pEp = gr->pg_Ep ? gr->pg_Ep : gr->Ep, pNn = gr->pg_Ep ? gr->pg_N : gr->N;
+    if (!panels) return set_error(RPG_E_UNSUPPORTED, "layer_bwd_split: needs a graph template with selection patterns");
+    auto outp = [&](PlW o) { g.out = o.hi; g.out_lo = o.lo; g.ldo = D; };
+
+    if (have_out) {
+        // dh3 = (d_out W2u) * [h3 > 0]
+        g = nt3((int)Nt, D, {b->d_out_hi, b->d_out_lo}, D, D, w->W2uT3, 3 * D);
+        g.mask_bits = t->h3_bits; g.mask_bits_ld = D / 8; outp({b->dh3_hi, b->dh3_lo});
+        RPG_TRY(gemm_launch(&g, s));
+        // [dx_u | da] = dh3 W1u ; da / deg -> dan
+        g = nt3((int)Nt, D, {b->dh3_hi, b->dh3_lo}, D, D, w->W1uT3, 3 * D);
+        outp({b->dxu_hi, b->dxu_lo});
+        RPG_TRY(gemm_launch(&g, s));
+        g = nt3((int)Nt, D, {b->dh3_hi, b->dh3_lo}, D, D, w->W1uT3 + (size_t)D * 3 * D, 3 * D);
+        g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; outp({b->dan_hi, b->dan_lo});
+        RPG_TRY(gemm_launch(&g, s));
+        // dyn = dan WW   fp32 [Nt, c]
+        g = nt3((int)Nt, c, {b->dan_hi, b->dan_lo}, D, D, w->WWT3, 3 * D);
+        g.out_f32 = b->dyn; g.ldo_f32 = c;
+        RPG_TRY(gemm_launch(&g, s));
+        // attention backward -> dgtp (hi, lo) [Et, pad64(3c)]
+        RPG_TRY(rpg_attention_bwd_split(t->gtp, b->dyn, c, gr, Et, c, b->dgtp_hi, b->dgtp_lo, c3p, stream));
+        // Q = dan W2m ; dh2 = (dgtp Wgc + Q[dst]) * [h2 > 0]
+        g = nt3((int)Nt, D, {b->dan_hi, b->dan_lo}, D, D, w->W2mT3, 3 * D);
+        outp({b->Q_hi, b->Q_lo});
+        RPG_TRY(gemm_launch(&g, s));
+        g = nt3((int)Et, D, {b->dgtp_hi, b->dgtp_lo}, c3p, c3p, w->WgcT3, 3 * c3p);
+        g.n_gseg = 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt; g.Ep = pEp; g.Nn = pNn;
+        g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->Q_hi; g.gsrc_ld[0] = D;
+        g.gsel[1] = gr->sel_dst; g.gsrc[1] = b->Q_lo; g.gsrc_ld[1] = D;
+        g.mask_bits = t->h2_bits; g.mask_bits_ld = D / 8; outp({b->dh2_hi, b->dh2_lo});
+        RPG_TRY(gemm_launch(&g, s));
+        // de'_tot = dh2 W1m_e + d_e_new
+        g = nt3((int)Et, D, {b->dh2_hi, b->dh2_lo}, D, D, w->W1m_eT3, 3 * D);
+        if (b->d_e_new_hi) { g.resid = b->d_e_new_hi; g.resid_lo = b->d_e_new_lo; g.resid_ld = D; }
+        outp({b->de_tot_hi, b->de_tot_lo});
+        RPG_TRY(gemm_launch(&g, s));
+    }
+    const Pl de_tot = have_out ? Pl{b->de_tot_hi, b->de_tot_lo} : Pl{b->d_e_new_hi, b->d_e_new_lo};
+    if (!de_tot.hi || !de_tot.lo) return set_error(RPG_E_ARG, "layer_bwd_split: neither d_out nor d_e_new given");
+
+    // dh1 = (de'_tot W2e) * [h1 > 0] ; de = dh1 W1e_e (* [e > 0])
+    g = nt3((int)Et, D, de_tot, D, D, w->W2eT3, 3 * D);
+    g.mask_bits = t->h1_bits; g.mask_bits_ld = D / 8; outp({b->dh1_hi, b->dh1_lo});
+    RPG_TRY(gemm_launch(&g, s));
+    g = nt3((int)Et, D, {b->dh1_hi, b->dh1_lo}, D, D, w->W1e_eT3, 3 * D);
+    if (b->mask_de) { g.mask_bits = t->e_bits; g.mask_bits_ld = D / 8; }
+    outp({b->de_hi, b->de_lo});
+    RPG_TRY(gemm_launch(&g, s));
+
+    // node side: dP = [sum_src dh1 | sum_dst dh1 | sum_src dh2], dx = dP Wn + dx_u
+    RPG_TRY(rpg_segment_sum_split(b->dh1_hi, b->dh1_lo, D, gr->out_ptr, gr->out_idx, nullptr, gr, D, b->dP_hi, b->dP_lo, ldP, stream));
+    RPG_TRY(rpg_segment_sum_split(b->dh1_hi, b->dh1_lo, D, gr->in_ptr, gr->in_idx, nullptr, gr, D, b->dP_hi + D, b->dP_lo + D, ldP, stream));
+    if (have_out) {
+        RPG_TRY(rpg_segment_sum_split(b->dh2_hi, b->dh2_lo, D, gr->out_ptr, gr->out_idx, nullptr, gr, D, b->dP_hi + 2 * D, b->dP_lo + 2 * D, ldP, stream));
+        g = nt3((int)Nt, D, {b->dP_hi, b->dP_lo}, ldP, ldP, w->WnT3, 3 * ldP);
+        g.resid = b->dxu_hi; g.resid_lo = b->dxu_lo; g.resid_ld = D;
+    } else {
+        // only the two edge-MLP blocks carry a gradient: K = 2D with the operand cut to those columns
+        if (!w->WnT3_sd) return set_error(RPG_E_ARG, "layer_bwd_split: WnT3_sd missing");
+        g = nt3((int)Nt, D, {b->dP_hi, b->dP_lo}, 2 * D, ldP, w->WnT3_sd, 6 * D);
+    }
+    if (b->mask_dx) { g.mask_bits = t->x_bits; g.mask_bits_ld = D / 8; }
+    outp({b->dx_hi, b->dx_lo});
+    RPG_TRY(gemm_launch(&g, s));
+
+    // ---- weight gradients
+    const size_t third = (size_t)rpg_layer_bwd_ws_floats(D, 0, 0);
+    WgradQueue3 q(b->split_ws, third, sms, s);
+    float* part[3];
+    int splits[3];
+    RPG_TRY(q.wgrad(de_tot, D, D, {t->h1_hi, t->h1_lo}, D, D, Et, b->g_edge2_w, D, b->g_edge2_b));
+    RPG_TRY(q.wgrad({b->dh1_hi, b->dh1_lo}, D, D, {t->e_hi, t->e_lo}, D, D, Et, b->g_edge0_w + 2 * D, 3 * D, b->g_edge0_b));
+    {
+        RPG_TRY(q.partials({b->dP_hi, b->dP_lo}, ldP, ldP, {t->x_hi, t->x_lo}, D, D, Nt, false, part, splits));
+        const long long stride = (long long)ldP * D;
+        RPG_TRY(q.add(part, splits, 0, stride, D, D, b->g_edge0_w, 3 * D));
+        RPG_TRY(q.add(part, splits, (size_t)D * D, stride, D, D, b->g_edge0_w + D, 3 * D));
+        RPG_TRY(q.add(part, splits, 2 * (size_t)D * D, stride, D, D, b->g_mlp0_w, 2 * D));
+    }
+    RPG_TRY(q.wgrad({b->dh2_hi, b->dh2_lo}, D, D, {t->e_new_hi, t->e_new_lo}, D, D, Et, b->g_mlp0_w + D, 2 * D, b->g_mlp0_b));
+    {
+        // T = dgtp^T h2, csg = colsum(dgtp): three partial sets folded NOW into zeroed scratch (three small launches)
+        RPG_TRY(q.partials({b->dgtp_hi, b->dgtp_lo}, c3p, c3, {t->h2_hi, t->h2_lo}, D, D, Et, true, part, splits));
+        cudaMemsetAsync(b->T_tmp, 0, (size_t)c3 * D * sizeof(float), s);
+        cudaMemsetAsync(b->gtp_bias_tmp, 0, (size_t)c3 * sizeof(float), s);
+        for (int i = 0; i < 3; ++i) {
+            rpg_reduce_batch_t fold;
+            fold.n = i < 2 ? 2 : 1;
+            fold.d[0] = {part[i], b->T_tmp, (long long)c3 * D, splits[i], c3, D, D};
+            if (i < 2) fold.d[1] = {part[i] + (size_t)splits[i] * c3 * D, b->gtp_bias_tmp, c3, splits[i], 1, c3, c3};
+            RPG_TRY(rpg_reduce_splits_batch(&fold, stream));
+        }
+        rpg_sgemm_batch_t sg;
+        memset(&sg, 0, sizeof sg);
+        float* dW[3] = {b->g_att_g_w, b->g_att_theta_w, b->g_att_phi_w};
+        float* dB[3] = {b->g_att_g_b, b->g_att_theta_b, b->g_att_phi_b};
+        for (int i = 0; i < 3; ++i) {
+            rpg_sgemm_desc_t& d = sg.d[sg.n++];
+            d.A = b->T_tmp + (size_t)i * c * D; d.lda = D; d.B = w->W2m_f32; d.ldb = D; d.transB = 1;
+            d.C = dW[i]; d.ldc = D; d.M = c; d.N = D; d.K = D; d.accumulate = 1;
+            d.u = b->gtp_bias_tmp + i * c; d.v = w->b2m;
+        }
+        {
+            rpg_sgemm_desc_t& d = sg.d[sg.n++];
+            d.A = w->Wgtp_f32; d.lda = D; d.transA = 1; d.B = b->T_tmp; d.ldb = D;
+            d.C = b->g_mlp2_w; d.ldc = D; d.M = D; d.N = D; d.K = c3; d.accumulate = 1;
+        }
+        {
+            rpg_sgemm_desc_t& d = sg.d[sg.n++];
+            d.A = w->Wgtp_f32; d.lda = D; d.transA = 1; d.B = b->gtp_bias_tmp; d.ldb = 1;
+            d.C = b->g_mlp2_b; d.ldc = 1; d.M = D; d.N = 1; d.K = c3; d.accumulate = 1;
+        }
+        RPG_TRY(rpg_sgemm_batch(&sg, stream));
+        // att.{g,theta,phi}.bias += csg  (fp32 copy-add: a 1 x c fold of one "split")
+        rpg_reduce_batch_t bb;
+        bb.n = 3;
+        for (int i = 0; i < 3; ++i) bb.d[i] = {b->gtp_bias_tmp + i * c, dB[i], c, 1, 1, c, c};
+        RPG_TRY(rpg_reduce_splits_batch(&bb, stream));
+    }
+    // node-level parts
+    RPG_TRY(rpg_segment_sum_split(t->h2_hi, t->h2_lo, D, gr->in_ptr, gr->in_idx, nullptr, gr, D, b->h2sum_hi, b->h2sum_lo, D, stream));
+    RPG_TRY(q.wgrad({b->dan_hi, b->dan_lo}, D, D, {b->h2sum_hi, b->h2sum_lo}, D, D, Nt, b->g_mlp2_w, D));
+    RPG_TRY(rpg_segment_sum_split(t->y_hi, t->y_lo, cp, gr->in_ptr, gr->in_idx, nullptr, gr, cp, b->ysum_hi, b->ysum_lo, cp, stream));
+    RPG_TRY(q.wgrad({b->dan_hi, b->dan_lo}, D, D, {b->ysum_hi, b->ysum_lo}, cp, c, Nt, b->g_att_W_w, c));
+    for (int pass = 0; pass < 2; ++pass) {                  // sum_n deg(n) dan[n] -> att.W.bias and mlp.2.bias (hi + lo planes)
+        float* dst = pass ? b->g_mlp2_b : b->g_att_W_b;
+        RPG_TRY(rpg_colsum_bf16(b->dan_hi, D, Nt, D, gr->deg, gr->N, dst, 1, b->colsum_ws, stream));
+        RPG_TRY(rpg_colsum_bf16(b->dan_lo, D, Nt, D, gr->deg, gr->N, dst, 1, b->colsum_ws, stream));
+    }
+    RPG_TRY(q.wgrad({b->d_out_hi, b->d_out_lo}, D, D, {t->h3_hi, t->h3_lo}, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));
+    RPG_TRY(q.wgrad({b->dh3_hi, b->dh3_lo}, D, D, {t->x_hi, t->x_lo}, D, D, Nt, b->g_upd0_w, 2 * D, b->g_upd0_b));
+    RPG_TRY(q.wgrad({b->dh3_hi, b->dh3_lo}, D, D, {t->a_hi, t->a_lo}, D, D, Nt, b->g_upd0_w + D, 2 * D));
+    RPG_TRY(q.flush());
     return 0;
 }
 

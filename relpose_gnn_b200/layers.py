@@ -181,42 +181,92 @@ class PackedLayerWeights:
 
 
 class PackedLayerWeightsSplit:
-    """fp32 mode: every forward operand as [W_hi | W_hi | W_lo] along K (see include/rpg.h, rpg_layer_fwd_split)."""
+    """fp32 mode: every operand as [W_hi | W_hi | W_lo] along K (see include/rpg.h, rpg_layer_fwd_split / _bwd_split);
+    the backward (transposed) operands are packed only once a backward is requested (`training=True`)."""
 
     def __init__(self, D, device):
         self.D, self.device = D, device
         c = D // 8
-        self.c, self.cp = c, pad64(c)
-        shapes = {"Wn3": (3 * D, 3 * D), "W1e_e3": (D, 3 * D), "W2e3": (D, 3 * D), "W1m_e3": (D, 3 * D), "W2m3": (D, 3 * D),
-                  "Wgtp3": (3 * c, 3 * D), "WW3": (D, 3 * self.cp), "W1u3": (D, 6 * D), "W2u3": (D, 3 * D)}
-        self.t = {n: torch.zeros(r, k, dtype=BF16, device=device) for n, (r, k) in shapes.items()}
-        self.bgtp = torch.zeros(3 * c, dtype=torch.float32, device=device)
+        self.c, self.cp, self.c3p = c, pad64(c), pad64(3 * c)
+        cp, c3p = self.cp, self.c3p
+        self.shapes_fwd = {"Wn3": (3 * D, 3 * D), "W1e_e3": (D, 3 * D), "W2e3": (D, 3 * D), "W1m_e3": (D, 3 * D),
+                           "Wgc3": (3 * c, 3 * D), "WWM3": (D, 3 * cp + 3 * D), "W1u3": (D, 6 * D), "W2u3": (D, 3 * D)}
+        self.shapes_bwd = {"WnT3": (D, 9 * D), "WnT3_sd": (D, 6 * D), "W1e_eT3": (D, 3 * D), "W2eT3": (D, 3 * D),
+                           "W1m_eT3": (D, 3 * D), "W2mT3": (D, 3 * D), "WgcT3": (D, 3 * c3p), "WWT3": (c, 3 * D),
+                           "W1uT3": (2 * D, 3 * D), "W2uT3": (D, 3 * D)}
+        self.t = {n: torch.zeros(r, k, dtype=BF16, device=device) for n, (r, k) in self.shapes_fwd.items()}
+        f32 = torch.float32
+        self.bgtp = torch.zeros(3 * c, dtype=f32, device=device)
+        self.bgc = torch.zeros(3 * c, dtype=f32, device=device)
+        self.bWm = torch.zeros(D, dtype=f32, device=device)
+        self.Wgtp_f32 = torch.zeros(3 * c, D, dtype=f32, device=device)
+        self.Wgc_f32 = torch.zeros(3 * c, D, dtype=f32, device=device)
+        self.one = torch.ones(1, dtype=f32, device=device)
         self.versions = None
         self.struct = _lib.LayerWeightsSplit()
 
-    def refresh(self, mod):
+    def refresh(self, mod, training=False):
         p = {n: mod.get_parameter(n) for n in PARAM_ORDER}
-        versions = (getattr(mod, "_pack_epoch", 0),) + tuple((q.data_ptr(), q._version) for q in p.values())
+        versions = (getattr(mod, "_pack_epoch", 0), bool(training)) + tuple((q.data_ptr(), q._version) for q in p.values())
         if versions == self.versions:
             return self.struct
-        D, c, t = self.D, self.c, self.t
+        D, c, cp, c3p, t = self.D, self.c, self.cp, self.c3p, self.t
+        if training and "WnT3" not in t:
+            t.update({n: torch.zeros(r, k, dtype=BF16, device=self.device) for n, (r, k) in self.shapes_bwd.items()})
         W1e, W1m, W1u = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data, p["mlp_updating.0.weight"].data
+        W2e, W2m, W2u = p["edge_model.edge_mlp.2.weight"].data, p["mlp.2.weight"].data, p["mlp_updating.2.weight"].data
+        WW = p["att.W.weight"].data
+        b2m = p["mlp.2.bias"].data
         q = ops.PackQueue()
         pk3 = q.add3
         pk3(W1e, t["Wn3"][0:D], c0=0, cols=D)
         pk3(W1e, t["Wn3"][D:2 * D], c0=D, cols=D)
         pk3(W1m, t["Wn3"][2 * D:3 * D], c0=0, cols=D)
         pk3(W1e, t["W1e_e3"], c0=2 * D, cols=D)
-        pk3(p["edge_model.edge_mlp.2.weight"].data, t["W2e3"])
+        pk3(W2e, t["W2e3"])
         pk3(W1m, t["W1m_e3"], c0=D, cols=D)
-        pk3(p["mlp.2.weight"].data, t["W2m3"])
         for i, nm in enumerate(("g", "theta", "phi")):
-            pk3(p[f"att.{nm}.weight"].data, t["Wgtp3"][i * c:(i + 1) * c])
+            q.add(p[f"att.{nm}.weight"].data, self.Wgtp_f32[i * c:(i + 1) * c])
             q.add(p[f"att.{nm}.bias"].data.view(1, c), self.bgtp[i * c:(i + 1) * c].view(1, c))
-        pk3(p["att.W.weight"].data, t["WW3"], cols=c)        # K padded to pad64(c): the padding columns stay zero
+            q.add(p[f"att.{nm}.bias"].data.view(1, c), self.bgc[i * c:(i + 1) * c].view(1, c))
+        pk3(WW, t["WWM3"][:, :3 * cp], cols=c)                # K padded to pad64(c): the padding columns stay zero
+        pk3(W2m, t["WWM3"][:, 3 * cp:])
+        q.add(p["att.W.bias"].data.view(1, D), self.bWm.view(1, D))
         pk3(W1u, t["W1u3"][:, :3 * D], c0=0, cols=D)
         pk3(W1u, t["W1u3"][:, 3 * D:], c0=D, cols=D)
-        pk3(p["mlp_updating.2.weight"].data, t["W2u3"])
+        pk3(W2u, t["W2u3"])
+        if training:
+            tr = dict(transpose=True)
+            for blk, (src, c0) in enumerate(((W1e, 0), (W1e, D), (W1m, 0))):     # WnT = [W1e_s^T | W1e_d^T | W1m_s^T]  [D, 3D]
+                for i, lo in enumerate((False, False, True)):
+                    q.add(src, t["WnT3"][:, i * 3 * D + blk * D:i * 3 * D + (blk + 1) * D], c0=c0, cols=D, lo=lo, **tr)
+                    if blk < 2:
+                        q.add(src, t["WnT3_sd"][:, i * 2 * D + blk * D:i * 2 * D + (blk + 1) * D], c0=c0, cols=D, lo=lo, **tr)
+            pk3(W1e, t["W1e_eT3"], c0=2 * D, cols=D, **tr)
+            pk3(W2e, t["W2eT3"], **tr)
+            pk3(W1m, t["W1m_eT3"], c0=D, cols=D, **tr)
+            pk3(W2m, t["W2mT3"], **tr)
+            pk3(WW, t["WWT3"], **tr)
+            pk3(W1u, t["W1uT3"][:D], c0=0, cols=D, **tr)          # x rows
+            pk3(W1u, t["W1uT3"][D:], c0=D, cols=D, **tr)          # a rows
+            pk3(W2u, t["W2uT3"], **tr)
+        q.flush()
+        # composed operands in fp32: Wgc = Wgtp W2m, bgc += Wgtp b2m, bWm += b2m -- then split into planes
+        sg = _lib.SgemmBatch()
+        d = sg.d[0]
+        d.A, d.lda, d.B, d.ldb, d.C, d.ldc = self.Wgtp_f32.data_ptr(), D, W2m.data_ptr(), W2m.stride(0), self.Wgc_f32.data_ptr(), D
+        d.M, d.N, d.K = 3 * c, D, D
+        d = sg.d[1]
+        d.A, d.lda, d.B, d.ldb, d.C, d.ldc = self.Wgtp_f32.data_ptr(), D, b2m.data_ptr(), 1, self.bgc.data_ptr(), 1
+        d.M, d.N, d.K, d.accumulate = 3 * c, 1, D, 1
+        d = sg.d[2]
+        d.A, d.lda, d.B, d.ldb, d.C, d.ldc = b2m.data_ptr(), 1, self.one.data_ptr(), 1, self.bWm.data_ptr(), 1
+        d.M, d.N, d.K, d.accumulate = D, 1, 1, 1
+        sg.n = 3
+        _lib.check(_lib.load().rpg_sgemm_batch(C.byref(sg), ops._stream(W2m)), "rpg_sgemm_batch")
+        q.add3(self.Wgc_f32, t["Wgc3"])
+        if training:
+            q.add3(self.Wgc_f32, t["WgcT3"], transpose=True)      # K padded to pad64(3c) per plane
         q.flush()
         s = self.struct
         s.D = D
@@ -225,16 +275,18 @@ class PackedLayerWeightsSplit:
         s.b1e = p["edge_model.edge_mlp.0.bias"].data_ptr()
         s.b2e = p["edge_model.edge_mlp.2.bias"].data_ptr()
         s.b1m = p["mlp.0.bias"].data_ptr()
-        s.b2m = p["mlp.2.bias"].data_ptr()
+        s.b2m = b2m.data_ptr()
         s.bgtp = self.bgtp.data_ptr()
         s.bW = p["att.W.bias"].data_ptr()
         s.b1u = p["mlp_updating.0.bias"].data_ptr()
         s.b2u = p["mlp_updating.2.bias"].data_ptr()
+        s.bgc, s.bWm = self.bgc.data_ptr(), self.bWm.data_ptr()
+        s.Wgtp_f32, s.W2m_f32 = self.Wgtp_f32.data_ptr(), W2m.data_ptr()
         self.versions = versions
         return s
 
 
-def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
+def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False, for_backward=False, x_bits=None, e_bits=None):
     """fp32 mode forward.  x, e: (hi, lo) bf16 plane pairs.  Returns the dict of activation planes."""
     D = weights.D
     dev = x[0].device
@@ -246,7 +298,7 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
         f = torch.zeros if zero else torch.empty
         return f(rows, cols, dtype=BF16, device=dev), f(rows, cols, dtype=BF16, device=dev)
 
-    a = {"x": x, "e": e, "h1": pair(Et, D), "e_new": pair(Et, D), "h2": pair(Et, D), "m": pair(Et, D),
+    a = {"x": x, "e": e, "h1": pair(Et, D), "e_new": pair(Et, D), "h2": pair(Et, D),
          "y": pair(Et, cp, zero=(cp != c)), "ybar": pair(Nt, cp), "mbar": pair(Nt, D), "a": pair(Nt, D),
          "h3": pair(Nt, D), "out": pair(Nt, D)}
     if want_relu_copies:
@@ -265,10 +317,92 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False):
         setattr(s, k + "_hi", hi.data_ptr())
         setattr(s, k + "_lo", lo.data_ptr())
     s.P, s.gtp = (P.data_ptr() if P is not None else None), gtp.data_ptr()
+    bits = {}
+    if for_backward:
+        u8 = torch.uint8
+        bits = {"h1_bits": torch.empty(Et, D // 8, dtype=u8, device=dev), "h2_bits": torch.empty(Et, D // 8, dtype=u8, device=dev),
+                "h3_bits": torch.empty(Nt, D // 8, dtype=u8, device=dev)}
+        if want_relu_copies:
+            bits["e_new_bits"] = torch.empty(Et, D // 8, dtype=u8, device=dev)
+            bits["out_bits"] = torch.empty(Nt, D // 8, dtype=u8, device=dev)
+        if x_bits is not None:
+            bits["x_bits"] = x_bits
+        if e_bits is not None:
+            bits["e_bits"] = e_bits
+        for k, v in bits.items():
+            setattr(s, k, v.data_ptr())
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(_lib.load().rpg_layer_fwd_split(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd_split")
-    a["_keep"] = (P, gtp, s)
+    a.update(bits)
+    a["gtp"] = gtp
+    a["_keep"] = (P, s)
+    a["_struct"] = s
     return a
+
+
+def layer_backward_split_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=False, mask_de=False):
+    """fp32 mode backward (rpg_layer_bwd_split).  d_out / d_e_new: (hi, lo) pairs or None; returns (dx, de) pairs."""
+    D = weights.D
+    dev = acts["x"][0].device
+    Nt, Et = graph.n_node_rows, graph.n_edge_rows
+    c = D // 8
+    cp, c3p = pad64(c), pad64(3 * c)
+    lib = _lib.load()
+    f32 = torch.float32
+
+    def pair(rows, cols, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(rows, cols, dtype=BF16, device=dev), f(rows, cols, dtype=BF16, device=dev)
+
+    b = _lib.LayerGradsSplit()
+    keep = {"dx": pair(Nt, D), "de": pair(Et, D), "dh1": pair(Et, D), "dP": pair(Nt, 3 * D)}
+    if d_out is not None:
+        keep.update({"dh3": pair(Nt, D), "dxu": pair(Nt, D), "dan": pair(Nt, D), "dgtp": pair(Et, c3p, zero=(c3p != 3 * c)),
+                     "Q": pair(Nt, D), "dh2": pair(Et, D), "de_tot": pair(Et, D), "ysum": pair(Nt, cp), "h2sum": pair(Nt, D)})
+    for k, (hi, lo) in keep.items():
+        setattr(b, k + "_hi", hi.data_ptr())
+        setattr(b, k + "_lo", lo.data_ptr())
+    scratch = {"dyn": torch.empty(Nt, c, dtype=f32, device=dev),
+               "split_ws": torch.empty(3 * lib.rpg_layer_bwd_ws_floats(D, 0, 0), dtype=f32, device=dev),
+               "colsum_ws": torch.empty(lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), dtype=f32, device=dev),
+               "gtp_bias_tmp": torch.empty(c3p, dtype=f32, device=dev), "T_tmp": torch.empty(3 * c, D, dtype=f32, device=dev)}
+    for k, v in scratch.items():
+        setattr(b, k, v.data_ptr())
+    if d_out is not None:
+        b.d_out_hi, b.d_out_lo = d_out[0].data_ptr(), d_out[1].data_ptr()
+    if d_e_new is not None:
+        b.d_e_new_hi, b.d_e_new_lo = d_e_new[0].data_ptr(), d_e_new[1].data_ptr()
+    b.mask_dx, b.mask_de = int(mask_dx), int(mask_de)
+    for name in PARAM_ORDER:
+        setattr(b, _GRAD_FIELD_OF[name], grads[name].data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(lib.rpg_layer_bwd_split(C.byref(weights), graph.byref(), C.byref(acts["_struct"]), C.byref(b), stream),
+               "rpg_layer_bwd_split")
+    return keep["dx"], keep["de"]
+
+
+class _LayerFnSplit(torch.autograd.Function):
+    """simpleConvEdge_upt in fp32 mode (split-bf16 arithmetic) with its hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, x, e, module, graph, *params):
+        need_bwd = any(ctx.needs_input_grad)
+        w = module._packed_split(x.device).refresh(module, training=need_bwd)
+        acts = layer_forward_split_raw(w, graph, ops.to_split(x.float()), ops.to_split(e.float()), for_backward=need_bwd)
+        ctx.module, ctx.graph, ctx.acts, ctx.weights = module, graph, acts, w
+        ctx.param_shapes = [p.shape for p in params]
+        return ops.from_split(*acts["out"]), ops.from_split(*acts["e_new"])
+
+    @staticmethod
+    def backward(ctx, d_out, d_e_new):
+        dev = ctx.acts["x"][0].device
+        grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(PARAM_ORDER, ctx.param_shapes)}
+        if d_out is None:                    # the kernels cut the node-update part; an all-zero gradient is simplest here
+            d_out = torch.zeros_like(ctx.acts["out"][0], dtype=torch.float32)
+        d_out = ops.to_split(d_out.float().contiguous())
+        d_e_new = ops.to_split(d_e_new.float().contiguous()) if d_e_new is not None else None
+        dx, de = layer_backward_split_raw(ctx.weights, ctx.graph, ctx.acts, d_out, d_e_new, grads)
+        return (ops.from_split(*dx), ops.from_split(*de), None, None) + tuple(grads[n] for n in PARAM_ORDER)
 
 
 def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None, e_bits=None, arena=None,
@@ -478,13 +612,9 @@ class simpleConvEdge_upt(nn.Module):
         self._check_inputs(x, edge_index, edge_attr)
         graph = graph_mod.from_edge_index(edge_index, x.size(0))
         if self.precision == "fp32":
-            if torch.is_grad_enabled() and (x.requires_grad or edge_attr.requires_grad or
-                                            any(p.requires_grad for p in self.parameters())):
-                raise NotImplementedError("precision='fp32' is inference-only in this version: call under torch.no_grad() "
-                                          "(training runs in the bf16 mode)")
-            w = self._packed_split(x.device).refresh(self)
-            acts = layer_forward_split_raw(w, graph, ops.to_split(x.float()), ops.to_split(edge_attr.float()))
-            return ops.from_split(*acts["out"]), ops.from_split(*acts["e_new"])
+            if self._variant != 0:
+                raise NotImplementedError("the fp32 mode covers simpleConvEdge_upt")
+            return _LayerFnSplit.apply(x, edge_attr, self, graph, *self._ordered_params())
         if self.precision != "bf16":
             raise ValueError("precision must be 'bf16' or 'fp32'")
         return _LayerFn.apply(x, edge_attr, self, graph, *self._ordered_params())

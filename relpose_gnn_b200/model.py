@@ -14,8 +14,8 @@ import torch
 from torch import nn
 
 from . import graph as graph_mod, ops
-from .layers import (PARAM_ORDER, _invalidate_hook, layer_backward_raw, layer_forward_raw, layer_forward_split_raw,
-                     simpleConvEdge_upt)
+from .layers import (PARAM_ORDER, _invalidate_hook, layer_backward_raw, layer_backward_split_raw, layer_forward_raw,
+                     layer_forward_split_raw, simpleConvEdge_upt)
 from .ops import BF16
 
 _HEADS = ("fc_xyz", "fc_wpqr", "fc_xyz_R", "fc_wpqr_R")
@@ -145,6 +145,98 @@ class _StackFn(torch.autograd.Function):
         ops.wgrad(dpmm[:, :D], xb, gw[:, :D], ws, bias=grads["proj_edge.bias"])   # every edge has exactly one lower endpoint
         ops.wgrad(dpmm[:, D:], xb, gw[:, D:], ws)
         dx = ops.to_f32(dx) if ctx.x_dtype == torch.float32 else dx
+        if direct:
+            return (dx, None, None, None) + (None,) * len(names)
+        return (dx, None, None, None) + tuple(grads[n] for n in names)
+
+
+class _StackFnSplit(torch.autograd.Function):
+    """The stack in fp32 mode (split-bf16 arithmetic on the same tcgen05 kernels; the reference trains in fp32,
+    train.py:266-274): every value a (hi, lo) bf16 pair, Linear = [A_hi | A_lo | A_hi] [W_hi | W_hi | W_lo]^T, weight
+    gradients hi^T hi + lo^T hi + hi^T lo.  Feature dropout + heads run in the stand-alone head kernels (fp32 weights)."""
+
+    @staticmethod
+    def forward(ctx, x, model, graph, drop, *params):
+        D, R = model.node_dim, model.gnn_recursion
+        dev = x.device
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        need_bwd = any(ctx.needs_input_grad)
+        lw = model.gnn1._packed_split(dev).refresh(model.gnn1, training=need_bwd)
+        sw = model._packed_stack_split(dev, training=need_bwd)
+        xs = ops.to_split(x.float())
+        pmm = torch.empty(Nt, 2 * D, dtype=torch.float32, device=dev)
+        ops.gemm_nt(None, sw["Wmm3"], segs=[xs[0], xs[1], xs[0]], out_f32=pmm)
+        e = (torch.empty(Et, D, dtype=BF16, device=dev), torch.empty(Et, D, dtype=BF16, device=dev))
+        e_bits = torch.empty(Et, D // 8, dtype=torch.uint8, device=dev) if need_bwd else None
+        ops.edge_init_fwd_split(pmm, model.proj_edge.bias.data, graph, D, e[0], e[1], e_bits)
+        acts = []
+        xin, x_bits = xs, None
+        for r in range(R):
+            a = layer_forward_split_raw(lw, graph, xin, e, want_relu_copies=True, for_backward=need_bwd, x_bits=x_bits,
+                                        e_bits=e_bits)
+            acts.append(a)
+            xin, e, x_bits, e_bits = a["out_relu"], a["e_new_relu"], a.get("out_bits"), a.get("e_new_bits")
+        p_drop, keep_x, keep_e, seed = drop
+        pose_n = ops.head_fwd(xin[0], sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop, feat_lo=xin[1])
+        pose_e = ops.head_fwd(e[0], sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop, feat_lo=e[1])
+        ctx.model, ctx.graph, ctx.drop = model, graph, drop
+        ctx.saved = (xs, acts, xin, e, lw, sw)
+        ctx.x_dtype = x.dtype
+        if model.keep_debug_activations:
+            model.debug_activations = {"e0": acts[0]["e"], "rounds": acts[:]}
+        ctx.set_materialize_grads(False)
+        return pose_n, pose_e
+
+    @staticmethod
+    def backward(ctx, d_pose_n, d_pose_e):
+        model, graph = ctx.model, ctx.graph
+        xs, acts, x_last, e_last, lw, sw = ctx.saved
+        p_drop, keep_x, keep_e, seed = ctx.drop
+        D, R = model.node_dim, model.gnn_recursion
+        dev = xs[0].device
+        names = model._param_names()
+        params = model._ordered_params()
+        direct = model.fused_grad_accumulation and all(p.grad is not None for p in params)
+        if direct:
+            grads = {n: p.grad for n, p in zip(names, params)}
+        else:
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+            grads, off = {}, 0
+            for n, p in zip(names, params):
+                grads[n] = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        lgrads = {n: grads["gnn1." + n] for n in PARAM_ORDER}
+        Nt, Et = graph.n_node_rows, graph.n_edge_rows
+        d_e = d_x = None
+        if d_pose_e is not None:
+            d_e = ops.head_bwd_split(d_pose_e.contiguous().float(), e_last, sw["w6e"], grads["fc_xyz_R.weight"],
+                                     grads["fc_wpqr_R.weight"], grads["fc_xyz_R.bias"], grads["fc_wpqr_R.bias"],
+                                     keep=keep_e, seed=seed + 1, p_drop=p_drop, mask_relu=True)
+        if d_pose_n is not None:
+            d_x = ops.head_bwd_split(d_pose_n.contiguous().float(), x_last, sw["w6n"], grads["fc_xyz.weight"],
+                                     grads["fc_wpqr.weight"], grads["fc_xyz.bias"], grads["fc_wpqr.bias"],
+                                     keep=keep_x, seed=seed, p_drop=p_drop, mask_relu=True)
+        if d_e is None and d_x is None:
+            return (None,) * (4 + len(names))
+        for r in range(R - 1, -1, -1):
+            d_x, d_e = layer_backward_split_raw(lw, graph, acts[r], d_x, d_e, lgrads, mask_dx=(r > 0), mask_de=True)
+            acts[r] = None
+        if direct and model._early_reduce is not None:
+            bucket, ranges = model._early_reduce
+            bucket.begin_allreduce(ranges)
+        # edge-feature initialiser backward: d_e is already masked by (e0 > 0)
+        def pair(rows, cols):
+            return torch.empty(rows, cols, dtype=BF16, device=dev), torch.empty(rows, cols, dtype=BF16, device=dev)
+        dpmm = pair(Nt, 2 * D)
+        ops.segment_sum_split(d_e, graph, "min", (dpmm[0][:, :D], dpmm[1][:, :D]))
+        ops.segment_sum_split(d_e, graph, "max", (dpmm[0][:, D:], dpmm[1][:, D:]))
+        dx = pair(Nt, D)
+        ops.gemm_nt(None, sw["WmmT3"], segs=[dpmm[0], dpmm[1], dpmm[0]], resid=d_x[0], resid_lo=d_x[1], out=dx[0], out_lo=dx[1])
+        ws = torch.empty(3 * _lib_ws_floats(D), dtype=torch.float32, device=dev)
+        gw = grads["proj_edge.weight"]
+        ops.wgrad_split((dpmm[0][:, :D], dpmm[1][:, :D]), xs, gw[:, :D], ws, bias=grads["proj_edge.bias"])
+        ops.wgrad_split((dpmm[0][:, D:], dpmm[1][:, D:]), xs, gw[:, D:], ws)
+        dx = ops.from_split(*dx)
         if direct:
             return (dx, None, None, None) + (None,) * len(names)
         return (dx, None, None, None) + tuple(grads[n] for n in names)
@@ -304,36 +396,32 @@ class RelPoseGNN(nn.Module):
         pose_n, pose_e = _StackFn.apply(x, self, graph, drop, *self._ordered_params())
         return pose_n, pose_e, edge_index
 
-    def _forward_fp32(self, x, graph, drop):
-        """fp32 mode (BASELINE config B): split-bf16 arithmetic end to end; inference only in this version."""
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("precision='fp32' is inference-only in this version: call under torch.no_grad()")
-        D, R = self.node_dim, self.gnn_recursion
-        dev = x.device
-        Nt, Et = graph.n_node_rows, graph.n_edge_rows
-        lw = self.gnn1._packed_split(dev).refresh(self.gnn1)
-        sw = self._packed_stack(dev)
-        if "Wmm3" not in sw or sw.get("Wmm3_versions") != sw["versions"]:
+    def _packed_stack_split(self, device, training=False):
+        """fp32-mode operands of the stack: proj_edge as [W_hi | W_hi | W_lo] (and its transpose for the backward)."""
+        sw = self._packed_stack(device)
+        D = self.node_dim
+        key = (sw["versions"], bool(training))
+        if sw.get("split_key") != key:
             if "Wmm3" not in sw:
-                sw["Wmm3"] = torch.zeros(2 * D, 3 * D, dtype=BF16, device=dev)
+                sw["Wmm3"] = torch.zeros(2 * D, 3 * D, dtype=BF16, device=device)
+            if training and "WmmT3" not in sw:
+                sw["WmmT3"] = torch.zeros(D, 6 * D, dtype=BF16, device=device)
             W = self.proj_edge.weight.data
             q = ops.PackQueue()
             q.add3(W, sw["Wmm3"][:D], c0=0, cols=D)
             q.add3(W, sw["Wmm3"][D:], c0=D, cols=D)
+            if training:                                   # WmmT = [W_min^T | W_max^T]  [D, 2D], thirds of 2D columns
+                for i, lo in enumerate((False, False, True)):
+                    for blk in range(2):
+                        q.add(W, sw["WmmT3"][:, i * 2 * D + blk * D:i * 2 * D + (blk + 1) * D], c0=blk * D, cols=D,
+                              transpose=True, lo=lo)
             q.flush()
-            sw["Wmm3_versions"] = sw["versions"]
-        xs = ops.to_split(x.float())
-        pmm = torch.empty(Nt, 2 * D, dtype=torch.float32, device=dev)
-        ops.gemm_nt(None, sw["Wmm3"], segs=[xs[0], xs[1], xs[0]], out_f32=pmm)
-        e = (torch.empty(Et, D, dtype=BF16, device=dev), torch.empty(Et, D, dtype=BF16, device=dev))
-        ops.edge_init_fwd_f32(pmm, self.proj_edge.bias.data, graph, D, e[0], e[1])
-        for _ in range(R):
-            a = layer_forward_split_raw(lw, graph, xs, e, want_relu_copies=True)
-            xs, e = a["out_relu"], a["e_new_relu"]
-        p_drop, keep_x, keep_e, seed = drop
-        pose_n = ops.head_fwd(xs[0], sw["w6n"], sw["b6n"], keep=keep_x, seed=seed, p_drop=p_drop, feat_lo=xs[1])
-        pose_e = ops.head_fwd(e[0], sw["w6e"], sw["b6e"], keep=keep_e, seed=seed + 1, p_drop=p_drop, feat_lo=e[1])
-        return pose_n, pose_e
+            sw["split_key"] = key
+        return sw
+
+    def _forward_fp32(self, x, graph, drop):
+        """fp32 mode (BASELINE config B; the reference's native training precision): split-bf16 arithmetic end to end."""
+        return _StackFnSplit.apply(x, self, graph, drop, *self._ordered_params())
 
     @staticmethod
     def compute_RP(p, edge_index):

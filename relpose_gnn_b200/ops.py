@@ -60,7 +60,7 @@ def _require_cuda(*ts):
 
 def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, row_scale=None, mask=None,
             relu=False, out=None, out_relu=None, out_f32=None, graph=None, block_n=0, mask_bits=None, out_bits=None,
-            gpanel=()):
+            gpanel=(), resid_lo=None, out_lo=None):
     """C = epilogue(sum_s A_s @ B^T).  A: bf16 [M, K] (or `segs`: list of up to 3 such tensors concatenated along
     K); B: bf16 [N, sum K].  Row pitches are taken from stride(0), so column-sliced views are fine.
     gadd: up to two (tensor [rows, >=N] bf16, 'src'|'dst') pairs added through the graph template."""
@@ -111,6 +111,10 @@ def gemm_nt(A, B, *, M=None, N=None, segs=None, bias=None, gadd=(), resid=None, 
         g.n_gseg = len(gpanel)
         g.gsel_patterns, g.gsel_div = graph.struct.sel_patterns, graph.struct.sel_div
         g.gsrc_rows, g.Ep, g.Nn = graph.n_node_rows, graph.Ep, graph.N
+    if resid_lo is not None:
+        g.resid_lo = resid_lo.data_ptr()
+    if out_lo is not None:
+        g.out_lo = out_lo.data_ptr()
     if mask_bits is not None:
         g.mask_bits, g.mask_bits_ld = mask_bits.data_ptr(), mask_bits.stride(0)
     if out_bits is not None:
@@ -186,13 +190,14 @@ class PackQueue:
         self.stream = _stream(src)
         self.keep.append((src, dst))
 
-    def add3(self, src, dst, c0=0, cols=None):
-        """dst[:, 0:3*kp] = [W_hi | W_hi | W_lo] of the column window [c0, c0+cols) of `src` (fp32 mode operands)."""
+    def add3(self, src, dst, c0=0, cols=None, r0=0, rows=None, transpose=False):
+        """dst[:, 0:3*kp] = [W_hi | W_hi | W_lo] of the window (r0, c0, rows, cols) of `src`, or of its transpose (fp32 mode
+        operands); kp = dst.size(1) // 3 >= the window's K extent (extra columns stay zero)."""
         cols = cols if cols is not None else src.size(1) - c0
+        rows = rows if rows is not None else src.size(0) - r0
         kp = dst.size(1) // 3
-        self.add(src, dst[:, 0:kp], c0=c0, cols=cols)
-        self.add(src, dst[:, kp:2 * kp], c0=c0, cols=cols)
-        self.add(src, dst[:, 2 * kp:], c0=c0, cols=cols, lo=True)
+        for i, lo in enumerate((False, False, True)):
+            self.add(src, dst[:, i * kp:(i + 1) * kp], r0=r0, c0=c0, rows=rows, cols=cols, transpose=transpose, lo=lo)
 
     def flush(self):
         if self.batch.n:
@@ -254,6 +259,43 @@ def pack_weight3(src, dst, c0=0, cols=None):
     pack_weight(src, dst[:, kp:2 * kp], c0=c0, cols=cols)
     check(lib.rpg_pack_weight_lo(src.data_ptr(), src.stride(0), 0, c0, rows, cols, dst[:, 2 * kp:].data_ptr(), dst.stride(0),
                                  _stream(src)), "rpg_pack_weight_lo")
+
+
+def wgrad_split(A, B, out, ws, bias=None):
+    """out[M, N] += (A_hi + A_lo)^T (B_hi + B_lo) for plane pairs A = (hi, lo) [R, M], B = (hi, lo) [R, N] (fp32 mode)."""
+    lib = _lib.load()
+    check(lib.rpg_wgrad_split(A[0].data_ptr(), A[1].data_ptr(), A[0].stride(0), A[0].size(1), B[0].data_ptr(), B[1].data_ptr(),
+                              B[0].stride(0), B[0].size(1), A[0].size(0), ws.data_ptr(), out.data_ptr(), out.stride(0), ptr(bias),
+                              _stream(out)), "rpg_wgrad_split")
+
+
+def segment_sum_split(v, graph, which, out):
+    """(hi, lo) plane form of segment_sum."""
+    s = graph.struct
+    check(_lib.load().rpg_segment_sum_split(v[0].data_ptr(), v[1].data_ptr(), v[0].stride(0), getattr(s, which + "_ptr"),
+                                            getattr(s, which + "_idx"), None, graph.byref(), v[0].size(1), out[0].data_ptr(),
+                                            out[1].data_ptr(), out[0].stride(0), _stream(v[0])), "rpg_segment_sum_split")
+
+
+def head_bwd_split(dpose, feat, w6, dw_t, dw_q, db_t, db_q, keep=None, seed=0, p_drop=0.0, mask_relu=True):
+    """Backward of head_fwd on (hi, lo) features; returns dfeat as a (hi, lo) pair."""
+    lib = _lib.load()
+    rows, D = feat[0].shape
+    dev = feat[0].device
+    ws = torch.empty(lib.rpg_head_bwd_ws_floats(rows, D), dtype=torch.float32, device=dev)
+    dh = torch.empty(rows, D, dtype=BF16, device=dev)
+    dl = torch.empty(rows, D, dtype=BF16, device=dev)
+    check(lib.rpg_head_bwd_split(dpose.data_ptr(), feat[0].data_ptr(), feat[1].data_ptr(), feat[0].stride(0), rows, D, ptr(keep),
+                                 seed, p_drop, w6.data_ptr(), int(mask_relu), dh.data_ptr(), dl.data_ptr(), D, dw_t.data_ptr(),
+                                 dw_q.data_ptr(), db_t.data_ptr(), db_q.data_ptr(), 1, ws.data_ptr(), _stream(dh)),
+          "rpg_head_bwd_split")
+    return dh, dl
+
+
+def edge_init_fwd_split(pmm, bias, graph, D, e_hi, e_lo, e_bits=None):
+    check(_lib.load().rpg_edge_init_fwd_split(pmm.data_ptr(), pmm.stride(0), bias.data_ptr(), graph.byref(), D, e_hi.data_ptr(),
+                                              e_lo.data_ptr(), e_hi.stride(0), ptr(e_bits), _stream(pmm)),
+          "rpg_edge_init_fwd_split")
 
 
 def attention_bwd(gtp, dyn, graph, c, dgtp, aux=None):
