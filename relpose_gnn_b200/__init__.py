@@ -15,8 +15,9 @@ from .graph import (GraphBatch, apply_edge_mask, attach, batched_edge_index, che
 from .layers import simpleConv, simpleConvEdge, simpleConvEdge_upt  # noqa: F401
 from .evaluation import compose_query_pose, pose_errors, qexp, save_poses  # noqa: F401
 from .feed import DeviceFeeder, ScalarReadback  # noqa: F401
+from .graph_io import collate, load_graph  # noqa: F401
 from .model import PoseNetCriterion, RelPoseGNN  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["FusedAdam", "mask_edge_index", "set_validation", "check_pending", "DeviceFeeder", "ScalarReadback", "apply_edge_mask", "compose_query_pose", "pose_errors", "save_poses", "qexp", "knn_graph", "simpleConv", "simpleConvEdge", "simpleConvEdge_upt", "RelPoseGNN", "PoseNetCriterion", "GraphBatch", "attach", "batched_edge_index",
+__all__ = ["FusedAdam", "load_graph", "collate", "mask_edge_index", "set_validation", "check_pending", "DeviceFeeder", "ScalarReadback", "apply_edge_mask", "compose_query_pose", "pose_errors", "save_poses", "qexp", "knn_graph", "simpleConv", "simpleConvEdge", "simpleConvEdge_upt", "RelPoseGNN", "PoseNetCriterion", "GraphBatch", "attach", "batched_edge_index",
            "edge_dropout_keep", "fc_template", "graph"]

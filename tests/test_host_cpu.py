@@ -218,3 +218,82 @@ def test_packed_weight_caches_are_not_pickled_and_can_be_invalidated():
     s1 = m._mixed_seed()
     m.dropout_rank = 1
     assert m._mixed_seed() != s1 and m._mixed_seed() % 2 == 0      # replicas draw different dropout masks
+
+
+def _fake_pyg_classes():
+    """Stand-ins carrying torch_geometric 2.0.1's module / class names, so that torch.save writes the pickle a real
+    `Data` object would produce (class references + state dicts)."""
+    import sys
+    import types
+    import weakref
+
+    mods = {}
+    for name in ("torch_geometric", "torch_geometric.data", "torch_geometric.data.data", "torch_geometric.data.storage"):
+        mods[name] = types.ModuleType(name)
+
+    class BaseStorage:                                       # storage.py: state = __dict__ with _parent dereferenced
+        def __init__(self, mapping, parent):
+            self.__dict__["_mapping"] = dict(mapping)
+            self.__dict__["_parent"] = weakref.ref(parent)
+
+        def __getstate__(self):
+            out = self.__dict__.copy()
+            out["_parent"] = out["_parent"]()
+            return out
+
+        def __setstate__(self, mapping):
+            self.__dict__.update(mapping)
+
+    GlobalStorage = type("GlobalStorage", (BaseStorage,), {"__module__": "torch_geometric.data.storage"})
+    BaseStorage.__module__ = "torch_geometric.data.storage"
+
+    class Data:
+        def __init__(self, **kw):
+            self.__dict__["_store"] = GlobalStorage(kw, self)
+    Data.__module__ = "torch_geometric.data.data"
+
+    class DataV1:                                            # PyG 1.x: plain attributes
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+    DataV1.__module__ = "torch_geometric.data.data"
+    DataV1.__name__ = DataV1.__qualname__ = "Data"
+    for cls, nm in ((BaseStorage, "BaseStorage"), (GlobalStorage, "GlobalStorage"), (Data, "Data"), (DataV1, "Data")):
+        cls.__name__ = cls.__qualname__ = nm                 # pickle looks classes up by (module, qualified name)
+    mods["torch_geometric.data.storage"].GlobalStorage = GlobalStorage
+    mods["torch_geometric.data.storage"].BaseStorage = BaseStorage
+    return mods, Data, DataV1
+
+
+def test_reference_graph_files_load_and_batch(tmp_path):
+    """dataset_7Scenes_multi.py:437-446 writes Data(x, edge_index, y, edge_attr) pickles; both PyG layouts read back
+    without torch_geometric installed, and collate() reproduces PyG batching (train.py:24,132)."""
+    import sys
+    from relpose_gnn_b200 import graph_io
+    mods, Data, DataV1 = _fake_pyg_classes()
+    n = 4
+    src, dst = G.fc_template(n)
+    ei = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+    graphs = []
+    for i, cls in enumerate((Data, DataV1, Data)):
+        x = torch.randn(n, 12)
+        y = torch.randn(n, 6)
+        ea = y[ei[1]] - y[ei[0]]                              # dataset_7Scenes_multi.py:425-429
+        path = str(tmp_path / f"data_{i:06d}.pt")
+        sys.modules.update(mods)
+        mods["torch_geometric.data.data"].Data = cls
+        try:
+            torch.save(cls(x=x, edge_index=ei, y=y, edge_attr=ea), path)
+        finally:
+            for k in mods:
+                sys.modules.pop(k, None)
+        assert "torch_geometric" not in sys.modules
+        g = graph_io.load_graph(path)
+        assert torch.equal(g.x, x) and torch.equal(g.edge_index, ei) and torch.equal(g.y, y) and torch.equal(g.edge_attr, ea)
+        graphs.append(g)
+    b = graph_io.collate(graphs)
+    assert b.x.shape == (3 * n, 12) and b.num_graphs == 3
+    assert torch.equal(b.edge_index, G.batched_edge_index(src, dst, 3, n))      # == the template batch the kernels expect
+    assert torch.equal(b.batch, torch.arange(3).repeat_interleave(n))
+    with pytest.raises(ValueError):
+        torch.save({"foo": 1}, str(tmp_path / "bad.pt"))
+        graph_io.load_graph(str(tmp_path / "bad.pt"))
