@@ -320,6 +320,11 @@ int rpg_attention_series_enabled(void);
 int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo /* NULL in bf16 mode */,
                       float* aux /* optional [Et, 4c] fp32 row statistics for the backward, or NULL */,
                       rpg_stream_t stream);
+/* The series form on bf16 projections [Et, 3c] (dense rows; the bf16 mode of the layer: half the HBM traffic of the
+ * fp32 tensor and twice the resident warps).  Same results up to the bf16 rounding of (g | theta | phi).          */
+int rpg_attention_fwd_bf16(const rpg_bf16* gtp16, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_stream_t stream);
+int rpg_attention_bwd_bf16(const rpg_bf16* gtp16, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
+                           rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream);
 /* Backward of the above with dy[e,:] = dyn[node(dst(e)), :] gathered through the template:
  * dgtp [Et, ld_dgtp] bf16 = (dg | dtheta | dphi) in the first 3c columns.                          */
 int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph,
@@ -521,6 +526,8 @@ typedef struct {                  /* activations of one layer call; all bf16 unl
    * e_new_relu are then the DROPPED, rescaled features the pose heads consume, out_bits / e_new_bits their patterns. */
   uint64_t drop_seed_x, drop_seed_e;
   float drop_p;                   /* 0 = off */
+  rpg_bf16* gtp16;                /* [Et, 3c] bf16 optional: the attention projections in bf16 instead of `gtp` (series
+                                     attention only; then `gtp` may be NULL)                                       */
 } rpg_layer_acts_t;
 
 int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* graph, const rpg_layer_acts_t* t,

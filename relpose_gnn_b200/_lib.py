@@ -55,7 +55,7 @@ class LayerActs(C.Structure):
     _fields_ = [(n, P) for n in ("x", "e", "P", "h1", "e_new", "e_new_relu", "h2", "m", "gtp", "y", "z", "a",
                                  "h3", "out", "out_relu", "att_aux", "h1_bits", "h2_bits", "h3_bits", "e_new_bits", "out_bits",
                                  "x_bits", "e_bits", "ybar", "mbar")] + [
-        ("drop_seed_x", C.c_uint64), ("drop_seed_e", C.c_uint64), ("drop_p", C.c_float)]
+        ("drop_seed_x", C.c_uint64), ("drop_seed_e", C.c_uint64), ("drop_p", C.c_float), ("gtp16", P)]
 
 
 class LayerWeightsSplit(C.Structure):
@@ -157,6 +157,8 @@ SIGNATURES = {
     "rpg_cast_f32_to_bf16": (I, [P, P, I64, P]),
     "rpg_cast_bf16_to_f32": (I, [P, P, I64, P]),
     "rpg_attention_series_enabled": (I, []),
+    "rpg_attention_fwd_bf16": (I, [P, I64, I, P, I, P]),
+    "rpg_attention_bwd_bf16": (I, [P, P, I, C.POINTER(Graph), I64, I, P, I, P]),
     "rpg_attention_fwd": (I, [P, I64, I, P, I, P, P, P]),
     "rpg_cast_f32_to_split": (I, [P, P, P, I64, P]),
     "rpg_split_to_f32": (I, [P, P, P, I64, P]),

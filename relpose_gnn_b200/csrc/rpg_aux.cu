@@ -1515,7 +1515,7 @@ int rpg_attention_fwd(const float* gtp, int64_t Et, int c, rpg_bf16* y, int ldy,
                       rpg_stream_t stream) {
     if (!gtp || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd: bad arguments");
     if (!aux && attention_series_enabled() && c % 16 == 0 && c >= 16 && c <= 256 && ldy % 8 == 0)
-        return attention_series_fwd(gtp, Et, c, y, ldy, y_lo, as_stream(stream));
+        return attention_series_fwd(gtp, 0, Et, c, y, ldy, y_lo, as_stream(stream));
     if (c % 4 || c < 4 || c > 256 || ldy % 2) return set_error(RPG_E_UNSUPPORTED, "attention_fwd: c must be a multiple of 4 in [4,256]");
     const int grid = grid_for(Et, ATT_WARPS, 148 * 8);
     ProfScope prof(RPG_PROF_ATTENTION_FWD, (double)Et * c * (12.0 + 2.0 + (y_lo ? 2.0 : 0.0) + (aux ? 16.0 : 0.0)), as_stream(stream),
@@ -1533,7 +1533,7 @@ int rpg_attention_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_
                       rpg_bf16* dgtp, int ld_dgtp, const float* aux, rpg_stream_t stream) {
     if (!gtp || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd: bad arguments");
     if (!aux && attention_series_enabled() && c % 16 == 0 && c >= 16 && c <= 256 && ld_dgtp % 8 == 0 && ld_dyn % 4 == 0)
-        return attention_series_bwd(gtp, dyn, ld_dyn, graph, Et, c, dgtp, ld_dgtp, nullptr, as_stream(stream));
+        return attention_series_bwd(gtp, 0, dyn, ld_dyn, graph, Et, c, dgtp, ld_dgtp, nullptr, as_stream(stream));
     if (c % 4 || c < 4 || c > 512) return set_error(RPG_E_UNSUPPORTED, "attention_bwd: c must be a multiple of 4 in [4,512]");
     const size_t smem = (size_t)ATT_WARPS * 8 * c * sizeof(float);
     static SmemLimit configured;
@@ -1576,6 +1576,16 @@ int rpg_aggregate_mean_split(const rpg_bf16* z_hi, const rpg_bf16* z_lo, int ldz
                           as_stream(stream), z_lo, a_lo);
 }
 
+int rpg_attention_fwd_bf16(const rpg_bf16* gtp16, int64_t Et, int c, rpg_bf16* y, int ldy, rpg_stream_t stream) {
+    if (!gtp16 || !y || Et <= 0) return set_error(RPG_E_ARG, "attention_fwd_bf16: bad arguments");
+    return attention_series_fwd(gtp16, 1, Et, c, y, ldy, nullptr, as_stream(stream));
+}
+int rpg_attention_bwd_bf16(const rpg_bf16* gtp16, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
+                           rpg_bf16* dgtp, int ld_dgtp, rpg_stream_t stream) {
+    if (!gtp16 || !dyn || !graph || !dgtp || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd_bf16: bad arguments");
+    return attention_series_bwd(gtp16, 1, dyn, ld_dyn, graph, Et, c, dgtp, ld_dgtp, nullptr, as_stream(stream));
+}
+
 int rpg_segment_sum_split(const rpg_bf16* v_hi, const rpg_bf16* v_lo, int ldv, const int32_t* csr_ptr, const int32_t* csr_idx,
                           const float* scale, const rpg_graph_t* graph, int D, rpg_bf16* out_hi, rpg_bf16* out_lo, int ldo,
                           rpg_stream_t stream) {
@@ -1586,7 +1596,7 @@ int rpg_segment_sum_split(const rpg_bf16* v_hi, const rpg_bf16* v_lo, int ldv, c
 int rpg_attention_bwd_split(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, int64_t Et, int c,
                             rpg_bf16* dgtp_hi, rpg_bf16* dgtp_lo, int ld_dgtp, rpg_stream_t stream) {
     if (!gtp || !dyn || !graph || !dgtp_hi || !dgtp_lo || Et <= 0) return set_error(RPG_E_ARG, "attention_bwd_split: bad arguments");
-    return attention_series_bwd(gtp, dyn, ld_dyn, graph, Et, c, dgtp_hi, ld_dgtp, dgtp_lo, as_stream(stream));
+    return attention_series_bwd(gtp, 0, dyn, ld_dyn, graph, Et, c, dgtp_hi, ld_dgtp, dgtp_lo, as_stream(stream));
 }
 
 int rpg_edge_to_node_sum(const rpg_bf16* v, int ldv, const rpg_graph_t* graph, int D, int by_src, rpg_bf16* out, int ldo,

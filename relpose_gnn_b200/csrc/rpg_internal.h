@@ -36,9 +36,10 @@ struct ProfScope {
 // Series form of the channel attention (rpg_attention.cu); the exp2 kernels of rpg_aux.cu remain for RPG_ATT_SERIES=0,
 // for callers that want the row statistics (`aux`) and for c that is not a multiple of 16.
 bool attention_series_enabled();
-int attention_series_fwd(const float* gtp, long long Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, cudaStream_t s);
-int attention_series_bwd(const float* gtp, const float* dyn, int ld_dyn, const rpg_graph_t* graph, long long Et, int c,
-                         rpg_bf16* dgtp, int ld_dgtp, rpg_bf16* dgtp_lo, cudaStream_t s);
+// gtp: the projections [Et, 3c], fp32 or (gtp_bf16 != 0) bf16
+int attention_series_fwd(const void* gtp, int gtp_bf16, long long Et, int c, rpg_bf16* y, int ldy, rpg_bf16* y_lo, cudaStream_t s);
+int attention_series_bwd(const void* gtp, int gtp_bf16, const float* dyn, int ld_dyn, const rpg_graph_t* graph, long long Et,
+                         int c, rpg_bf16* dgtp, int ld_dgtp, rpg_bf16* dgtp_lo, cudaStream_t s);
 
 inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

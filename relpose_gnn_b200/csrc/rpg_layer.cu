@@ -276,12 +276,17 @@ int rpg_layer_fwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
     //     straight from h2 with composed weights (rpg.h: rpg_layer_weights_t.Wgc / WWM).
     // (6) attention projections (att.py:20-24): (g | theta | phi) = m Wgtp^T + b = h2 (Wgtp W2m)^T + (Wgtp b2m + bgtp)
     if (!w->Wgc || !w->bgc || !w->WWM || !w->bWm) return set_error(RPG_E_ARG, "layer_fwd: composed operands (Wgc / WWM) missing");
+    const bool gtp_bf16 = t->gtp16 != nullptr && attention_series_enabled() && c % 16 == 0 && c <= 256;
+    if (!gtp_bf16 && !t->gtp) return set_error(RPG_E_ARG, "layer_fwd: gtp (fp32) or gtp16 needed");
     g = nt((int)Et, c3, t->h2, D, D, w->Wgc, D);
-    g.bias = w->bgc; g.out_f32 = t->gtp; g.ldo_f32 = c3;
+    g.bias = w->bgc;
+    if (gtp_bf16) { g.out = t->gtp16; g.ldo = c3; }
+    else { g.out_f32 = t->gtp; g.ldo_f32 = c3; }
     RPG_TRY(gemm_launch(&g, s));
 
     // (7) rank-1 softmax attention (att.py:25-30)
-    RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, attention_series_enabled() ? nullptr : t->att_aux, stream));
+    if (gtp_bf16) RPG_TRY(rpg_attention_fwd_bf16(t->gtp16, Et, c, t->y, cp, stream));
+    else RPG_TRY(rpg_attention_fwd(t->gtp, Et, c, t->y, cp, nullptr, attention_series_enabled() ? nullptr : t->att_aux, stream));
 
     // (8)+(9) z = y WW^T + bW + m (att.py:32-33) is only ever averaged over the incoming edges (PyG aggregate [3p],
     //     my_gnn_layer.py:301), and the mean is linear: a = mean(y) WW^T + bW + mean(h2) W2m^T + b2m.  So neither the
@@ -701,7 +706,10 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         g.out_f32 = b->dyn; g.ldo_f32 = c;
         RPG_TRY(gemm_launch(&g, s));
         // attention backward -> dgtp [Et, 3c]
-        RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, attention_series_enabled() ? nullptr : t->att_aux, stream));
+        if (t->gtp16 != nullptr && attention_series_enabled() && c % 16 == 0 && c <= 256)
+            RPG_TRY(rpg_attention_bwd_bf16(t->gtp16, b->dyn, c, gr, Et, c, b->dgtp, c3p, stream));
+        else
+            RPG_TRY(rpg_attention_bwd(t->gtp, b->dyn, c, gr, Et, c, b->dgtp, c3p, attention_series_enabled() ? nullptr : t->att_aux, stream));
         // dh2 = (dm W2m) * [h2 > 0] with dm = dgtp Wgtp + dan[dst] (never materialised):
         //     dh2 = (dgtp (Wgtp W2m) + Q[dst]) * [h2 > 0],  Q = dan W2m at node level
         if (!b->Q || !w->WgcT) return set_error(RPG_E_ARG, "layer_bwd: Q / WgcT missing");

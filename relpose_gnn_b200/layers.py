@@ -419,10 +419,14 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
     new = arena.take
 
     v1 = weights.variant == 1
-    a = {"x": x, "e": e, "P": new(Nt, (4 if v1 else 3) * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D),
-         "gtp": new(Et, 3 * c, torch.float32),                      # m is never materialised (rpg.h: Wgc / WWM)
+    series = bool(_lib.load().rpg_attention_series_enabled()) and c % 16 == 0 and c <= 256
+    a = {"x": x, "e": e, "P": new(Nt, (4 if v1 else 3) * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D)}
+    # the attention projections (g | theta | phi): bf16 for the series attention, fp32 for the exp2 kernels;
+    # the message m itself is never materialised (rpg.h: Wgc / WWM)
+    a["gtp16" if series else "gtp"] = new(Et, 3 * c, BF16 if series else torch.float32)
+    a.update({
          "y": new(Et, cp, zero=(cp != c)),
-         "ybar": new(Nt, cp), "mbar": new(Nt, D), "a": new(Nt, D)}
+         "ybar": new(Nt, cp), "mbar": new(Nt, D), "a": new(Nt, D)})
     u8 = torch.uint8
     if for_backward:                     # ReLU patterns are only consumed by the backward epilogues
         a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8)})

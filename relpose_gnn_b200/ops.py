@@ -232,6 +232,17 @@ def attention_fwd(gtp, c, y, y_lo=None, aux=None):
                                         _stream(gtp)), "rpg_attention_fwd")
 
 
+def attention_fwd_bf16(gtp16, c, y):
+    """Series attention on bf16 projections [Et, 3c] (dense rows)."""
+    check(_lib.load().rpg_attention_fwd_bf16(gtp16.data_ptr(), gtp16.size(0), c, y.data_ptr(), y.stride(0), _stream(gtp16)),
+          "rpg_attention_fwd_bf16")
+
+
+def attention_bwd_bf16(gtp16, dyn, graph, c, dgtp):
+    check(_lib.load().rpg_attention_bwd_bf16(gtp16.data_ptr(), dyn.data_ptr(), dyn.stride(0), graph.byref(), gtp16.size(0), c,
+                                             dgtp.data_ptr(), dgtp.stride(0), _stream(gtp16)), "rpg_attention_bwd_bf16")
+
+
 def to_split(t):
     """fp32 [rows, C] -> (hi, lo) bf16 planes with t = hi + lo to ~2^-17 relative."""
     t = t.contiguous()

@@ -64,6 +64,16 @@ def test_series_attention_matches_fp64_softmax_in_every_class(c):
     ops.attention_bwd(gtp.to(dev()), dyn.to(dev()), graph, c, dgtp)
     gerr = rel_rows(dgtp.float()[:, :3 * c].cpu(), d_ref)
     assert gerr.max().item() < 8e-3, gerr.max().item()                      # bf16 output of an fp32 computation
+    # bf16 projections (the layer's bf16 mode): same kernels on rows rounded to bf16 -- compare with the fp64 softmax OF
+    # THOSE rounded rows, so that only the kernel arithmetic is measured
+    g16 = gtp.bfloat16()
+    y_ref16, d_ref16 = reference(g16.float(), dy, c)
+    yb = torch.zeros_like(y)
+    ops.attention_fwd_bf16(g16.to(dev()), c, yb)
+    assert rel_rows(yb.float()[:, :c].cpu(), y_ref16).max().item() < 6e-3
+    db = torch.zeros_like(dgtp)
+    ops.attention_bwd_bf16(g16.to(dev()), dyn.to(dev()), graph, c, db)
+    assert rel_rows(db.float()[:, :3 * c].cpu(), d_ref16).max().item() < 8e-3
     # the former exp2 kernels (selected by passing the statistics buffer) agree with the series form
     aux = torch.empty(Et, 4 * c, dtype=torch.float32, device=dev())
     if c <= 256:
