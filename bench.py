@@ -461,8 +461,8 @@ def main():
                          "attached: the caller builds the GraphBatch and annotates the tensor (A/B)")
     ap.add_argument("--validation", default="async", choices=["async", "sync"],
                     help="edge_index validation read-back: async (checked one step late) or sync (one event wait per step)")
-    ap.add_argument("--overlap-allreduce", action="store_true",
-                    help="start the all-reduce of every gradient but proj_edge's from inside the backward (A/B)")
+    ap.add_argument("--no-overlap-allreduce", dest="overlap_allreduce", action="store_false",
+                    help="(A/B) one all-reduce after the backward instead of starting it from inside the backward")
     ap.add_argument("--no-ref-eager", dest="ref_eager", action="store_false",
                     help="skip the informative reference-in-torch-eager-on-the-GPU column")
     args = ap.parse_args()

@@ -551,12 +551,14 @@ int rpg_layer_bwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     RPG_TRY(q.wgrad(de_tot, D, D, {t->h1_hi, t->h1_lo}, D, D, Et, b->g_edge2_w, D, b->g_edge2_b));
     RPG_TRY(q.wgrad({b->dh1_hi, b->dh1_lo}, D, D, {t->e_hi, t->e_lo}, D, D, Et, b->g_edge0_w + 2 * D, 3 * D, b->g_edge0_b));
     {
-        RPG_TRY(q.partials({b->dP_hi, b->dP_lo}, ldP, ldP, {t->x_hi, t->x_lo}, D, D, Nt, false, part, splits));
-        const long long stride = (long long)ldP * D;
+        const int Mp = have_out ? ldP : 2 * D;
+        RPG_TRY(q.partials({b->dP_hi, b->dP_lo}, ldP, Mp, {t->x_hi, t->x_lo}, D, D, Nt, false, part, splits));
+        const long long stride = (long long)Mp * D;
         RPG_TRY(q.add(part, splits, 0, stride, D, D, b->g_edge0_w, 3 * D));
         RPG_TRY(q.add(part, splits, (size_t)D * D, stride, D, D, b->g_edge0_w + D, 3 * D));
-        RPG_TRY(q.add(part, splits, 2 * (size_t)D * D, stride, D, D, b->g_mlp0_w, 2 * D));
+        if (have_out) RPG_TRY(q.add(part, splits, 2 * (size_t)D * D, stride, D, D, b->g_mlp0_w, 2 * D));
     }
+    if (!have_out) return q.flush();
     RPG_TRY(q.wgrad({b->dh2_hi, b->dh2_lo}, D, D, {t->e_new_hi, t->e_new_lo}, D, D, Et, b->g_mlp0_w + D, 2 * D, b->g_mlp0_b));
     {
         // T = dgtp^T h2, csg = colsum(dgtp): three partial sets folded NOW into zeroed scratch (three small launches)

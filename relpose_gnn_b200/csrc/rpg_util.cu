@@ -197,51 +197,86 @@ int rpg_profile_records(rpg_prof_rec_t* out, int max_records, int* n_records) { 
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
-// Small fp32 products (weight composition Wgc = Wgtp W2m and the matching backward): 32 x 32 output tile per block,
-// 32-wide k chunks through shared memory, 4 outputs per thread.  ~50 MFLOP per product: a few microseconds.
+// Small fp32 products (weight composition Wgc = Wgtp W2m and the matching backward), ~50 MFLOP each.
 // ------------------------------------------------------------------------------------------------
 namespace rpg {
+// 64 x 64 output tile per block, 16-deep k chunks, 4 x 4 outputs per thread; the next chunk's global loads are issued
+// before the current chunk's FMAs (register prefetch), and the thread -> element mapping of the loads follows the
+// operand's storage order so that they coalesce for every transpose flag.
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
 __global__ void __launch_bounds__(256)
 sgemm_batch_kernel(const __grid_constant__ rpg_sgemm_batch_t batch) {
     pdl_prologue();
     const rpg_sgemm_desc_t& d = batch.d[blockIdx.z];
-    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
     if (m0 >= d.M || n0 >= d.N) return;
-    __shared__ float sa[32][33], sb[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8; thread owns rows ty + 8 r, column tx
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < d.K; k0 += 32) {
-        for (int r = ty; r < 32; r += 8) {
-            // sa[m][k], sb[k][n]
-            const int m = m0 + r, ka = k0 + tx;
-            sa[r][tx] = (m < d.M && ka < d.K) ? (d.transA ? d.A[(size_t)ka * d.lda + m] : d.A[(size_t)m * d.lda + ka]) : 0.f;
-            const int kb = k0 + r, n = n0 + tx;
-            sb[r][tx] = (kb < d.K && n < d.N) ? (d.transB ? d.B[(size_t)n * d.ldb + kb] : d.B[(size_t)kb * d.ldb + n]) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const float bv = sb[k][tx];
+    __shared__ __align__(16) float As[SG_BK][SG_BM + 4], Bs[SG_BK][SG_BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;                         // outputs: rows m0 + 4 ty + i, columns n0 + 4 tx + j
+    // load mapping: 1024 elements per operand tile, 4 per thread; `fast` runs along the operand's contiguous dimension
+    // A tile element (m, k): stored A[m, k] (k contiguous) or, transA, A[k, m] (m contiguous)
+    int am[4], ak[4], bk[4], bn[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[ty + 8 * r][k], bv, acc[r]);
+    for (int i = 0; i < 4; ++i) {
+        const int e = tid + 256 * i;
+        if (d.transA) { am[i] = e & 63; ak[i] = e >> 6; } else { ak[i] = e & 15; am[i] = e >> 4; }
+        if (d.transB) { bk[i] = e & 15; bn[i] = e >> 4; } else { bn[i] = e & 63; bk[i] = e >> 6; }
+    }
+    auto ldA = [&](int k0, int i) -> float {
+        const int m = m0 + am[i], k = k0 + ak[i];
+        if (m >= d.M || k >= d.K) return 0.f;
+        return d.transA ? d.A[(size_t)k * d.lda + m] : d.A[(size_t)m * d.lda + k];
+    };
+    auto ldB = [&](int k0, int i) -> float {
+        const int n = n0 + bn[i], k = k0 + bk[i];
+        if (n >= d.N || k >= d.K) return 0.f;
+        return d.transB ? d.B[(size_t)n * d.ldb + k] : d.B[(size_t)k * d.ldb + n];
+    };
+    float ra[4], rb[4], acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ra[i] = ldA(0, i); rb[i] = ldB(0, i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    for (int k0 = 0; k0 < d.K; k0 += SG_BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { As[ak[i]][am[i]] = ra[i]; Bs[bk[i]][bn[i]] = rb[i]; }
+        __syncthreads();
+        if (k0 + SG_BK < d.K) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ra[i] = ldA(k0 + SG_BK, i); rb[i] = ldB(k0 + SG_BK, i); }
+        }
+#pragma unroll
+        for (int k = 0; k < SG_BK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
-    const int n = n0 + tx;
-    if (n >= d.N) return;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int m = m0 + ty + 8 * r;
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 4 * ty + i;
         if (m >= d.M) continue;
-        float v = acc[r];
-        if (d.u && d.v) v = fmaf(d.u[m], d.v[n], v);
-        if (d.C) {
-            float* o = d.C + (size_t)m * d.ldc + n;
-            v = d.accumulate ? *o + v : v;
-            *o = v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 4 * tx + j;
+            if (n >= d.N) continue;
+            float v = acc[i][j];
+            if (d.u && d.v) v = fmaf(d.u[m], d.v[n], v);
+            if (d.C) {
+                float* o = d.C + (size_t)m * d.ldc + n;
+                v = d.accumulate ? *o + v : v;
+                *o = v;
+            }
+            if (d.Cb) reinterpret_cast<bf16*>(d.Cb)[(size_t)m * d.ldcb + n] = __float2bfloat16_rn(v);
+            if (d.CbT) reinterpret_cast<bf16*>(d.CbT)[(size_t)n * d.ldcbT + m] = __float2bfloat16_rn(v);
         }
-        if (d.Cb) reinterpret_cast<bf16*>(d.Cb)[(size_t)m * d.ldcb + n] = __float2bfloat16_rn(v);
-        if (d.CbT) reinterpret_cast<bf16*>(d.CbT)[(size_t)n * d.ldcbT + m] = __float2bfloat16_rn(v);
     }
 }
 }  // namespace rpg
@@ -256,6 +291,6 @@ extern "C" int rpg_sgemm_batch(const rpg_sgemm_batch_t* batch, rpg_stream_t stre
         mx = d.M > mx ? d.M : mx;
         nx = d.N > nx ? d.N : nx;
     }
-    launch_pdl(sgemm_batch_kernel, dim3((nx + 31) / 32, (mx + 31) / 32, batch->n), dim3(256), 0, as_stream(stream), *batch);
+    launch_pdl(sgemm_batch_kernel, dim3((nx + 63) / 64, (mx + 63) / 64, batch->n), dim3(256), 0, as_stream(stream), *batch);
     return check_launch("sgemm_batch_kernel");
 }

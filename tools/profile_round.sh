@@ -3,7 +3,7 @@
 tag=${1:-r2}
 mkdir -p gpurun_out
 # (1) every launch of a training step: duration + DRAM bytes
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/${tag}_launches_train_4096x9.csv python bench.py --steps 2 --warmup 1 --trials 1 --no-cpu-baseline --no-ref-eager > /dev/null 2> gpurun_out/${tag}_launches.err
 # (2) which tensor-pipe counters exist on this part
 ncu --query-metrics 2>/dev/null | grep -i -E "tensor|tmem|utc" > gpurun_out/${tag}_tensor_metric_names.txt
