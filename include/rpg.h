@@ -644,6 +644,7 @@ typedef struct {
   rpg_bf16 *dgtp_hi, *dgtp_lo, *Q_hi, *Q_lo, *dh2_hi, *dh2_lo, *de_tot_hi, *de_tot_lo, *dh1_hi, *dh1_lo, *dP_hi, *dP_lo;
   rpg_bf16 *ysum_hi, *ysum_lo, *h2sum_hi, *h2sum_lo;
   float *split_ws, *colsum_ws, *gtp_bias_tmp, *T_tmp;
+  float* Q_f32;                               /* [Nt, D] fp32: dan W2m for templates without selection patterns     */
   /* fp32 weight gradients in the reference's state_dict layout, accumulated (+=) */
   float* g_mlp0_w;  float* g_mlp0_b;  float* g_mlp2_w;  float* g_mlp2_b;
   float* g_upd0_w;  float* g_upd0_b;  float* g_upd2_w;  float* g_upd2_b;

@@ -85,7 +85,7 @@ class LayerGradsSplit(C.Structure):
                 [(n, P) for n in ("dx_hi", "dx_lo", "de_hi", "de_lo", "dh3_hi", "dh3_lo", "dxu_hi", "dxu_lo", "dan_hi", "dan_lo",
                                   "dyn", "dgtp_hi", "dgtp_lo", "Q_hi", "Q_lo", "dh2_hi", "dh2_lo", "de_tot_hi", "de_tot_lo",
                                   "dh1_hi", "dh1_lo", "dP_hi", "dP_lo", "ysum_hi", "ysum_lo", "h2sum_hi", "h2sum_lo",
-                                  "split_ws", "colsum_ws", "gtp_bias_tmp", "T_tmp") + _GRAD_NAMES])
+                                  "split_ws", "colsum_ws", "gtp_bias_tmp", "T_tmp", "Q_f32") + _GRAD_NAMES])
 
 
 class LayerGrads(C.Structure):

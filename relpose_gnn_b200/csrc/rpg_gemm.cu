@@ -120,10 +120,17 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& u) {
 // half of the accumulator.  Shared-memory fill + operand-read traffic per CTA drops by a third (48 -> 32 KB per
 // k-block), which is what bounds the single-CTA form at these shapes, and the ring deepens from 4 to 6 stages.
 // (NT mode without one-hot panels: the panels' node windows differ between the two row blocks.)
-template <int MODE, int CL, int EPI, bool PAIR = false>
+// WS = weight-stationary pair kernel (plain epilogue, K <= 512, no one-hot panels): the cluster's half-tiles of B for ALL
+// k-blocks stay resident in shared memory (8 x 16 KB per CTA) and only A streams through a 4-stage ring.  The operand
+// fill from L2 is what bounds the streaming form at these shapes (32 KB per k-block and CTA, ~8.4 TB/s chip-wide at
+// the measured item time -- the L2 -> SM limit); with B resident it halves.  The work items of a cluster all share one
+// column block (the host sizes the grid so that the cluster count is a multiple of the number of column blocks, and the
+// item stride then keeps item % num_n_blocks constant).
+template <int MODE, int CL, int EPI, bool PAIR = false, bool WS = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     static_assert(!PAIR || (CL == 2 && MODE == 0), "CTA pairs: NT mode, clusters of 2");
+    static_assert(!WS || (PAIR && EPI == 0), "weight-stationary: plain pair kernels");
     constexpr bool OPS = EPI == 1 || EPI == 2;
     constexpr bool RTMA = EPI == 3;        // the only tensor operand is a residual, fetched by TMA (pair kernels)
     static_assert(!RTMA || PAIR, "TMA-staged residuals are a pair-kernel feature");
@@ -136,9 +143,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     // B200: no gain (plain 155648 x 512 x 512 in the training step 87 -> 91 us with the 5-stage ring it costs) -- the
     // wait is not what paces an item -- so the single tile and the 6-stage ring stay.
     constexpr int STG_BUFS = 1;
-    constexpr int NS = (OPBUF || STG_BUFS == 2) ? 5 : (PAIR ? 6 : STAGES);  // ring depth
+    constexpr int NS = WS ? 4 : ((OPBUF || STG_BUFS == 2) ? 5 : (PAIR ? 6 : STAGES));  // ring depth
     constexpr int BST = PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;          // B bytes per stage in this CTA
-    static_assert(NS * (A_STAGE_BYTES + BST) + ((OPBUF || STG_BUFS == 2) ? EPI_WARPS * EPI_STAGE_BYTES : 0) == SMEM_RING_BYTES,
+    constexpr int WS_KB = 8;                                               // resident k-blocks (K <= 512)
+    static_assert(WS ? (NS * A_STAGE_BYTES + WS_KB * BST == SMEM_RING_BYTES)
+                     : (NS * (A_STAGE_BYTES + BST) + ((OPBUF || STG_BUFS == 2) ? EPI_WARPS * EPI_STAGE_BYTES : 0) == SMEM_RING_BYTES),
                   "ring carve");
     const CUtensorMap& tmA0 = tm.a[0];
     const CUtensorMap& tmB = tm.b;
@@ -156,6 +165,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
     uint64_t* acc_empty = acc_full + ACC_STAGES;  // [ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
     uint64_t* op_bar = bars + 32;                 // [EPI_WARPS] operand-buffer barriers (OPBUF kernels)
+    uint64_t* b_full = bars + 24;                 // WS: the resident B tiles have landed (leader's barrier)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -172,6 +182,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             mbar_init(&acc_empty[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
         if (OPBUF) for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&op_bar[i], 1);
+        if (WS) mbar_init(b_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -208,6 +219,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             // ------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
+            if (WS && worker < num_items) {
+                // every item of this cluster has the same column block: its B half-tiles for all k-blocks, once
+                const int n_blk = worker % num_n_blocks;
+                const int half_rows = p.block_n / 2;
+                const uint32_t lead_bfull = mapa_u32(smem_u32(b_full), 0);
+                if (cta_rank == 0) mbar_arrive_expect_tx(b_full, 2u * (uint32_t)p.total_kb * (uint32_t)half_rows * BLOCK_K * 2);
+                for (int kb = 0; kb < p.total_kb; ++kb)
+                    tma_load_2d_pair(&tmB, lead_bfull, smem_b + kb * BST, kb * BLOCK_K, n_blk * p.block_n + cta_rank * half_rows);
+            }
             for (int item = worker; item < num_items; item += num_workers) {
                 const int tile = MODE == 0 ? item : item / p.splits;
                 const int m_blk = (tile / num_n_blocks) * CL + cta_rank, n_blk = tile % num_n_blocks;
@@ -217,6 +237,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         const CUtensorMap* tmA = &tm.a[s];
                         for (int kb = 0; kb < p.num_kb[s]; ++kb, ++kb_global) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (WS) {
+                                const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
+                                tma_load_2d_pair(tmA, lead_full, smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_blk * BLOCK_M);
+                                if (++stage == NS) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             if (PAIR) {
                                 // both CTAs' tiles complete on the LEADER's full barrier: it expects the bytes of both
                                 const int half_rows = p.block_n / 2;
@@ -293,6 +320,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            if (WS && worker < num_items) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (int item = worker; item < num_items; item += num_workers, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -318,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                             umma_bf16(d_tmem, a_desc + k * k_step, bg_desc + k * ((UMMA_K * 128) >> 4), idesc_g, (kb | k) != 0);
                     } else {
-                        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * BST), lbo, sbo);
+                        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + (WS ? kb : stage) * BST), lbo, sbo);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             if (PAIR) umma_bf16_pair(d_tmem, a_desc + k * k_step, b_desc + k * k_step, idesc, (kb | k) != 0);
@@ -746,6 +774,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
 
 // -------------------------------------------------------------------------------------- host side
 
+// RPG_GEMM_WS=0 keeps the plain pair GEMMs on the streaming-B form (A/B comparisons).
+static bool gemm_ws_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("RPG_GEMM_WS");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
 // RPG_GEMM_PAIR=0 keeps every GEMM on the single-CTA MMA form (A/B comparisons).
 static bool gemm_pair_enabled() {
     static int on = -1;
@@ -918,6 +955,7 @@ static void set_smem_attrs() {
     cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_tc_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(gemm_tc_kernel<0, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -1058,7 +1096,8 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     const int num_n_blocks = (p.N + block_n - 1) / block_n;
     const int items = ((num_m_blocks + cl - 1) / cl) * num_n_blocks * p.splits;      // one item per cluster
     const int max_workers = g_sm_count / cl;
-    const int grid = (items < max_workers ? items : max_workers) * cl;
+    int grid = (items < max_workers ? items : max_workers) * cl;
+
     const bool prof = prof_active();
     int prof_slot = -1;
     if (prof) {
@@ -1080,6 +1119,14 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
                               (int)kdim, stream);
     }
     const bool ops = g->mode == 0 && (p.gadd[0] || p.gadd[1] || p.resid || p.mask);
+    // weight-stationary form: plain pair kernel, K <= 512, every cluster bound to one column block (cluster count a
+    // multiple of the column-block count), enough items per cluster to amortise the resident B load
+    bool ws = false;
+    if (cl == 2 && g->mode == 0 && !split_mode && !ops && gemm_pair_enabled() && gemm_ws_enabled() && p.total_kb <= 8 &&
+        g->n_gseg == 0 && num_n_blocks <= max_workers) {
+        const int workers = (max_workers / num_n_blocks) * num_n_blocks;
+        if (workers > 0 && items >= 3 * workers) { ws = true; grid = workers * cl; }
+    }
     void (*kern)(GemmTmaps, GemmKParams);
     if (cl == 1)
         kern = g->mode == 1 ? gemm_tc_kernel<1, 1, 0>
@@ -1087,7 +1134,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     else if (g->mode == 0 && split_mode && g->n_gseg == 0 && gemm_pair_enabled())
         kern = gemm_tc_kernel<0, 2, 2, true>;           // fp32 mode on CTA pairs
     else if (g->mode == 0 && !split_mode && g->n_gseg == 0 && gemm_pair_enabled()) {
-        kern = ops ? gemm_tc_kernel<0, 2, 1, true> : gemm_tc_kernel<0, 2, 0, true>;
+        kern = ops ? gemm_tc_kernel<0, 2, 1, true> : (ws ? gemm_tc_kernel<0, 2, 0, true, true> : gemm_tc_kernel<0, 2, 0, true>);
         if (ops && p.resid && !p.mask && !p.gadd[0] && !p.gadd[1] && aligned16(p.resid) && p.resid_ld % 8 == 0) {
             int rc2 = make_tmap(&tmaps.resid, p.resid, p.N, p.M, p.resid_ld, 64, 32);
             if (rc2) return rc2;

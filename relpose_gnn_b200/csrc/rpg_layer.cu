@@ -478,7 +478,7 @@ int rpg_layer_bwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     const int ldP = 3 * D;
     const bool panels = gr->sel_src && gr->sel_dst;
     const int pEp = gr->pg_Ep ? gr->pg_Ep : gr->Ep, pNn = gr->pg_Ep ? gr->pg_N : gr->N;
-    if (!panels) return set_error(RPG_E_UNSUPPORTED, "layer_bwd_split: needs a graph template with selection patterns");
+    if (!panels && have_out && !b->Q_f32) return set_error(RPG_E_ARG, "layer_bwd_split: Q_f32 needed for templates without selection patterns");
     auto outp = [&](PlW o) { g.out = o.hi; g.out_lo = o.lo; g.ldo = D; };
 
     if (have_out) {
@@ -501,12 +501,18 @@ int rpg_layer_bwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
         RPG_TRY(rpg_attention_bwd_split(t->gtp, b->dyn, c, gr, Et, c, b->dgtp_hi, b->dgtp_lo, c3p, stream));
         // Q = dan W2m ; dh2 = (dgtp Wgc + Q[dst]) * [h2 > 0]
         g = nt3((int)Nt, D, {b->dan_hi, b->dan_lo}, D, D, w->W2mT3, 3 * D);
-        outp({b->Q_hi, b->Q_lo});
+        if (panels) outp({b->Q_hi, b->Q_lo});
+        else { g.out_f32 = b->Q_f32; g.ldo_f32 = D; }          // epilogue gather of fp32 rows (tiny / irregular templates)
         RPG_TRY(gemm_launch(&g, s));
         g = nt3((int)Et, D, {b->dgtp_hi, b->dgtp_lo}, c3p, c3p, w->WgcT3, 3 * c3p);
-        g.n_gseg = 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt; g.Ep = pEp; g.Nn = pNn;
-        g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->Q_hi; g.gsrc_ld[0] = D;
-        g.gsel[1] = gr->sel_dst; g.gsrc[1] = b->Q_lo; g.gsrc_ld[1] = D;
+        if (panels) {
+            g.n_gseg = 2; g.gsel_patterns = gr->sel_patterns; g.gsel_div = gr->sel_div; g.gsrc_rows = (int)Nt; g.Ep = pEp; g.Nn = pNn;
+            g.gsel[0] = gr->sel_dst; g.gsrc[0] = b->Q_hi; g.gsrc_ld[0] = D;
+            g.gsel[1] = gr->sel_dst; g.gsrc[1] = b->Q_lo; g.gsrc_ld[1] = D;
+        } else {
+            g.Ep = gr->Ep; g.Nn = gr->N;
+            g.gadd_f32[0] = b->Q_f32; g.gmap[0] = gr->dst; g.gadd_f32_ld[0] = D;
+        }
         g.mask_bits = t->h2_bits; g.mask_bits_ld = D / 8; outp({b->dh2_hi, b->dh2_lo});
         RPG_TRY(gemm_launch(&g, s));
         // de'_tot = dh2 W1m_e + d_e_new

@@ -17,11 +17,15 @@ typedef __nv_bfloat16 bf16;
 // Template tables: four CSRs (by destination / source / lower / upper endpoint) + degrees of ONE graph template.
 // One block; thread n owns node n (strided): count pass, block-wide exclusive scan, stable fill pass.
 // ------------------------------------------------------------------------------------------------
-constexpr int TT_THREADS = 256;
+constexpr int TT_THREADS = 128;          // one warp per CSR (destination / source / lower / upper endpoint)
 constexpr int TT_MAX_N = 1024;
 
 __device__ __forceinline__ int tt_key(int t, int s, int d) { return t == 0 ? d : t == 1 ? s : t == 2 ? min(s, d) : max(s, d); }
 
+// Warp t builds CSR t: for every node n in turn the lanes scan the template 32 edges at a time, a ballot marks the edges
+// keyed by n and each marked lane writes its edge at (running offset + number of marked lanes below it) -- a stable
+// counting sort (edge order within a node), identical to the host tables.  ~N * Ep / 32 ballots: microseconds for the
+// templates of the path (N <= 17, Ep <= 272).
 __global__ void __launch_bounds__(TT_THREADS)
 template_tables_kernel(const int* __restrict__ tsrc, const int* __restrict__ tdst, int N, int Ep, int* __restrict__ src,
                        int* __restrict__ dst, int* __restrict__ in_ptr, int* __restrict__ in_idx, int* __restrict__ out_ptr,
@@ -29,36 +33,31 @@ template_tables_kernel(const int* __restrict__ tsrc, const int* __restrict__ tds
                        int* __restrict__ max_ptr, int* __restrict__ max_idx, float* __restrict__ inv_deg,
                        float* __restrict__ deg, float* __restrict__ has_in) {
     pdl_prologue();
-    __shared__ int cnt[TT_MAX_N + 1];
     for (int k = threadIdx.x; k < Ep; k += TT_THREADS) { src[k] = tsrc[k]; dst[k] = tdst[k]; }
-    for (int t = 0; t < 4; ++t) {
-        int* ptr = t == 0 ? in_ptr : t == 1 ? out_ptr : t == 2 ? min_ptr : max_ptr;
-        int* idx = t == 0 ? in_idx : t == 1 ? out_idx : t == 2 ? min_idx : max_idx;
-        for (int n = threadIdx.x; n < N; n += TT_THREADS) {
-            int c = 0;
-            for (int k = 0; k < Ep; ++k) c += tt_key(t, __ldg(tsrc + k), __ldg(tdst + k)) == n;
-            cnt[n] = c;
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* ptr = t == 0 ? in_ptr : t == 1 ? out_ptr : t == 2 ? min_ptr : max_ptr;
+    int* idx = t == 0 ? in_idx : t == 1 ? out_idx : t == 2 ? min_idx : max_idx;
+    int base = 0;
+    for (int n = 0; n < N; ++n) {
+        const int start = base;
+        for (int k0 = 0; k0 < Ep; k0 += 32) {
+            const int k = k0 + lane;
+            const bool hit = k < Ep && tt_key(t, __ldg(tsrc + k), __ldg(tdst + k)) == n;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) idx[base + __popc(m & ((1u << lane) - 1u))] = k;
+            base += __popc(m);
+        }
+        if (lane == 0) {
+            ptr[n] = start;
             if (t == 0) {
+                const int c = base - start;
                 deg[n] = (float)c;
                 inv_deg[n] = 1.f / (float)max(c, 1);
                 has_in[n] = c > 0 ? 1.f : 0.f;
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {                       // exclusive scan (N <= 1024: a few hundred cycles)
-            int run = 0;
-            for (int n = 0; n < N; ++n) { const int c = cnt[n]; cnt[n] = run; run += c; }
-            cnt[N] = run;
-        }
-        __syncthreads();
-        for (int n = threadIdx.x; n <= N; n += TT_THREADS) ptr[n] = cnt[n];
-        for (int n = threadIdx.x; n < N; n += TT_THREADS) {
-            int fill = cnt[n];
-            for (int k = 0; k < Ep; ++k)
-                if (tt_key(t, __ldg(tsrc + k), __ldg(tdst + k)) == n) idx[fill++] = k;
-        }
-        __syncthreads();
     }
+    if (lane == 0) ptr[N] = base;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -142,7 +141,8 @@ int64_t rpg_template_tables_words(int N, int Ep) { return 6 * al4(Ep) + 4 * al4(
 
 int rpg_template_tables(const int32_t* tsrc, const int32_t* tdst, int N, int Ep, int32_t* tables, rpg_stream_t stream) {
     if (!tsrc || !tdst || !tables || N <= 0 || Ep <= 0) return set_error(RPG_E_ARG, "template_tables: bad arguments");
-    if (N > TT_MAX_N || Ep > 65536) return set_error(RPG_E_UNSUPPORTED, "template_tables: N <= 1024 and Ep <= 65536 (larger templates: host tables)");
+    if (N > TT_MAX_N || Ep > 65536 || (long long)N * Ep > (1LL << 22))
+        return set_error(RPG_E_UNSUPPORTED, "template_tables: N <= 1024, Ep <= 65536, N * Ep <= 2^22 (larger templates: host tables)");
     int32_t* p = tables;
     int32_t* src = p; p += al4(Ep);
     int32_t* dst = p; p += al4(Ep);

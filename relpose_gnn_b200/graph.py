@@ -460,7 +460,7 @@ def from_edge_index(edge_index, n_node_rows):
     key = (int(n_node_rows), str(ei.device))
     guess = _shape_cache.get(key)
     g = None
-    if guess is not None and Et % guess[0] == 0 and guess[1] <= 1024 and Et // guess[0] <= 65536:
+    if guess is not None and Et % guess[0] == 0 and guess[1] <= 1024 and guess[1] * (Et // guess[0]) <= (1 << 22):
         G_, N_ = guess
         g, bad = _device_graph(ei, G_, N_, Et // G_)
         ev, host = _read_count_async(bad)

@@ -366,6 +366,8 @@ def layer_backward_split_raw(weights, graph, acts, d_out, d_e_new, grads, mask_d
                "split_ws": torch.empty(3 * lib.rpg_layer_bwd_ws_floats(D, 0, 0), dtype=f32, device=dev),
                "colsum_ws": torch.empty(lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), dtype=f32, device=dev),
                "gtp_bias_tmp": torch.empty(c3p, dtype=f32, device=dev), "T_tmp": torch.empty(3 * c, D, dtype=f32, device=dev)}
+    if d_out is not None and not (graph.struct.sel_src and graph.struct.sel_dst):
+        scratch["Q_f32"] = torch.empty(Nt, D, dtype=f32, device=dev)
     for k, v in scratch.items():
         setattr(b, k, v.data_ptr())
     if d_out is not None:
