@@ -11,7 +11,8 @@ hdr, units, vals = r[0], r[1], r[2]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum", "sm__inst_executed_pipe_tensor.sum",
         "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
         "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
         "launch__registers_per_thread", "sm__cycles_elapsed.max", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -22,9 +23,10 @@ for h, u, v in zip(hdr, units, vals):
         out.append(f"{h:92s} {v:>18s} {u}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h2 = rows[1]
+hi = next(i for i, x in enumerate(rows) if "# Samples" in x)
+h2 = rows[hi]
 ix = {h: i for i, h in enumerate(h2)}
-data = [x for x in rows[2:] if len(x) == len(h2)]
+data = [x for x in rows[hi + 1:] if len(x) == len(h2) and x[ix["# Samples"]].strip().isdigit()]
 tot = sum(int(x[ix["# Samples"]]) for x in data) or 1
 out.append(f"# top stall-sample locations ({tot} samples)")
 for x in sorted(data, key=lambda x: -int(x[ix["# Samples"]]))[:14]:
