@@ -242,6 +242,11 @@ def run_ours(args):
     bucket = parallel.FlatGradBucket(params) if train else None
     opt = None
     if train:
+        # diagnostic only (the printed line says so): replicas step without exchanging gradients, to separate the
+        # cost of the collective from what a multi-GPU box costs by itself (clocks, host contention)
+        skip_reduce = os.environ.get("RPG_BENCH_SKIP_ALLREDUCE") == "1"
+        if skip_reduce:
+            args.overlap_allreduce = False
         model.attach_grad_bucket(bucket, overlap=args.overlap_allreduce and world > 1)
         if args.optimizer:
             # train.py:211: Adam over the parameters of the path; one fused kernel over the flat buckets.  Its 1/world
@@ -282,7 +287,9 @@ def run_ours(args):
             loss, t_loss, q_loss = crit(pe, poses, ei_used)
             loss.backward()
             if opt is not None:
-                if args.overlap_allreduce and world > 1:
+                if skip_reduce:
+                    pass
+                elif args.overlap_allreduce and world > 1:
                     bucket.finish_allreduce(average=False)
                 else:
                     bucket.allreduce(average=False)
@@ -422,6 +429,8 @@ def run_ours(args):
                          "edges_per_graph_profiled_step": Ep_prof},
             "roofline_hbm": hbm_roofline(recs, peaks, D),
         }
+        if train and skip_reduce:
+            line["diagnostic"] = "RPG_BENCH_SKIP_ALLREDUCE=1: replicas did not exchange gradients; not a benchmark value"
         if args.cpu_baseline and world == 1:
             v, med, threads, kind = cpu_reference_throughput(args.cpu_sample, N, D, train, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": "graphs/s", "cores": threads, "kind": kind,

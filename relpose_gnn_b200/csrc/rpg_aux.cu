@@ -402,7 +402,9 @@ attention_bwd_kernel(const float* __restrict__ gtp, const float* __restrict__ dy
 
 // ------------------------------------------------------------------------------------------------
 // Segment reductions over the per-graph template (mean aggregation, dgrad scatters): gather formulation,
-// fixed order, one thread per 8 feature columns.
+// fixed order, one thread per 8 feature columns.  (Round 2 measured the alternative -- whole graph blocks bulk-copied
+// into shared memory, several in flight per SM, sums gathered from there: same DRAM bytes, same 38-40 us / 56-58 us
+// per launch under ncu on the 155 648 x 512 tensor, so the extra kernel was dropped)
 //   out[g*N+n, c] = scale[n] * sum_{k in csr(n)} v[g*Ep+k, c] * (mask ? mask[g*Ep+k, c] > 0 : 1)
 // ------------------------------------------------------------------------------------------------
 // PLAIN: no ReLU mask and no fp32-mode lo plane (every launch of the bf16 path) -- a third of the registers, so more
@@ -472,10 +474,10 @@ __global__ void segment_sum_kernel(const bf16* __restrict__ v, int ldv, const bf
     }
 }
 
-// Two segment sums of the SAME edge tensor in one pass (by source and by destination of dh1; by lower and by upper endpoint
-// of the edge-initialiser gradient): a thread owns 8 columns of one node row and walks both CSRs.  Every edge row is
-// read by two threads of the same graph a few hundred cycles apart, so the second read is an L1 / L2 hit and DRAM
-// sees the tensor once.  Fixed order: deterministic.
+// Two segment sums of the SAME edge tensor in one launch (by source and by destination of dh1; by lower and by upper
+// endpoint of the edge-initialiser gradient): a thread owns 8 columns of one node row of ONE of the two CSRs; the two
+// CSR passes of a node row sit next to each other in the flattened index space, so a graph's edge rows are read by
+// both passes within a few hundred cycles: the second read is an L2 hit and DRAM sees the tensor once.  Fixed order.
 template <typename I>
 __global__ void segment_sum2_kernel(const bf16* __restrict__ v, int ldv, const int* __restrict__ ptr_a,
                                     const int* __restrict__ idx_a, const int* __restrict__ ptr_b,
@@ -483,38 +485,37 @@ __global__ void segment_sum2_kernel(const bf16* __restrict__ v, int ldv, const i
                                     bf16* __restrict__ out_a, int ldo_a, bf16* __restrict__ out_b, int ldo_b) {
     pdl_prologue();
     const int tpr = D >> 3;
-    const I total = (I)Nt * (I)tpr;
+    const I total = (I)Nt * (I)tpr * (I)2;
     for (I t = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; t < total; t += (I)gridDim.x * (I)blockDim.x) {
-        const I row_i = t / (I)tpr;
-        const int c = (int)(t - row_i * (I)tpr) << 3;
+        const I unit = t / (I)tpr;                             // (node row, pass)
+        const int c = (int)(t - unit * (I)tpr) << 3;
+        const I row_i = unit >> 1;
+        const int pass = (int)(unit & 1);
         const I g_i = row_i / (I)N;
         const int n = (int)(row_i - g_i * (I)N);
         const long long row = (long long)row_i, g = (long long)g_i;
+        const int* __restrict__ ptr = pass ? ptr_b : ptr_a;
+        const int* __restrict__ idx = pass ? idx_b : idx_a;
+        const int k0 = __ldg(ptr + n), k1 = __ldg(ptr + n + 1);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int kb = k0; kb < k1; kb += 4) {
+            uint4 u[4];
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int* __restrict__ ptr = pass ? ptr_b : ptr_a;
-            const int* __restrict__ idx = pass ? idx_b : idx_a;
-            const int k0 = __ldg(ptr + n), k1 = __ldg(ptr + n + 1);
-            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int kb = k0; kb < k1; kb += 4) {
-                uint4 u[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool ok = kb + j < k1;
-                    const long long er = g * Ep + (ok ? __ldg(idx + kb + j) : 0);
-                    u[j] = ok ? __ldg(reinterpret_cast<const uint4*>(v + er * ldv + c)) : make_uint4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float f[8];
-                    unpack8(u[j], f);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[q] += f[q];
-                }
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = kb + j < k1;
+                const long long er = g * Ep + (ok ? __ldg(idx + kb + j) : 0);
+                u[j] = ok ? __ldg(reinterpret_cast<const uint4*>(v + er * ldv + c)) : make_uint4(0, 0, 0, 0);
             }
-            bf16* o = pass ? out_b + row * ldo_b : out_a + row * ldo_a;
-            *reinterpret_cast<uint4*>(o + c) = pack8(acc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f[8];
+                unpack8(u[j], f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            }
         }
+        bf16* o = pass ? out_b + row * ldo_b : out_a + row * ldo_a;
+        *reinterpret_cast<uint4*>(o + c) = pack8(acc);
     }
 }
 
@@ -1645,9 +1646,9 @@ int rpg_segment_sum2(const rpg_bf16* v, int ldv, const rpg_graph_t* g, int which
     cudaStream_t s = as_stream(stream);
     // algorithmic bytes: the edge tensor once, two node tensors
     ProfScope prof(RPG_PROF_SEGMENT_SUM, ((double)g->G * g->Ep + 2.0 * (double)Nt) * D * 2.0, s);
-    const bool small = Nt * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
+    const bool small = 2 * Nt * (D / 8) + 148LL * 16 * 256 < (1LL << 31);
     auto kern = small ? segment_sum2_kernel<unsigned> : segment_sum2_kernel<long long>;
-    launch_pdl(kern, dim3(grid_for(Nt * (D / 8), 256)), dim3(256), 0, s, reinterpret_cast<const bf16*>(v), ldv, ptrs[which_a],
+    launch_pdl(kern, dim3(grid_for(2 * Nt * (D / 8), 256)), dim3(256), 0, s, reinterpret_cast<const bf16*>(v), ldv, ptrs[which_a],
                idxs[which_a], ptrs[which_b], idxs[which_b], Nt, g->N, g->Ep, D, reinterpret_cast<bf16*>(out_a), ldo_a,
                reinterpret_cast<bf16*>(out_b), ldo_b);
     return check_launch("segment_sum2_kernel");

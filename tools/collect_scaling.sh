@@ -7,5 +7,5 @@ for w in train_4096x9 train_2048x17 train_2048x17_strong infer_8192x9 infer_6553
   run --workload $w --trials 3 --no-ref-eager > gpurun_out/${tag}_n${N}_${w}.json 2> gpurun_out/${tag}_n${N}_${w}.err || echo "FAILED $w"
 done
 for w in train_4096x9 train_2048x17_strong; do
-  run --workload $w --trials 3 --no-ref-eager --overlap-allreduce > gpurun_out/${tag}_n${N}_${w}_overlap.json 2> gpurun_out/${tag}_n${N}_${w}_overlap.err || echo "FAILED overlap $w"
+  run --workload $w --trials 3 --no-ref-eager --no-overlap-allreduce > gpurun_out/${tag}_n${N}_${w}_nooverlap.json 2> gpurun_out/${tag}_n${N}_${w}_nooverlap.err || echo "FAILED no-overlap $w"
 done
