@@ -376,6 +376,10 @@ def run_ours(args):
     n_rec = C.c_int()
     lib.rpg_profile_records(recs, 1024, C.byref(n_rec))
     recs = [recs[i] for i in range(min(n_rec.value, 1024))]
+    if os.environ.get("RPG_BENCH_DUMP_RECORDS") == "1" and rank == 0:      # development aid: the per-launch list on stderr
+        for r in recs:
+            print(f"rec {_lib.PROF_CLASSES[r.cls]:14s} {r.ms * 1e3:8.1f} us  {r.flops / 1e9:8.2f} GF  {r.bytes / 1e6:8.1f} MB  "
+                  f"M={r.M} N={r.N} K={r.K}", file=sys.stderr)
     gemms = [r for r in recs if r.cls <= 1]
     gemm_ms = sum(r.ms for r in gemms)
     gemm_fl = sum(r.flops for r in gemms)

@@ -410,6 +410,12 @@ int rpg_pose_criterion(const float* pred, int ld_pred, const float* poses, const
  * column (g*N + i)*k + r = (r-th nearest other node of i in graph g  ->  i); squared Euclidean distances in fp32 on
  * x [G*N, D] (pitch ldx), ties to the lower node index. */
 int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* edge_index, rpg_stream_t stream);
+/* The same for a batch of graphs of DIFFERENT sizes (a general PyG `batch` vector): graph g owns the node rows
+ * [node_ptr[g], node_ptr[g+1]) and writes min(k, n_g - 1) edges per node (fewer candidates than k: all of them, as
+ * torch_cluster does) starting at column edge_ptr[g]; node_ptr / edge_ptr: device int64 [G+1]; max_nodes = the largest
+ * n_g (<= 64); n_edges = edge_ptr[G] = the number of columns of edge_index [2, n_edges]. */
+int rpg_knn_graph_ragged(const float* x, int ldx, int G, const int64_t* node_ptr, const int64_t* edge_ptr, int max_nodes, int D,
+                         int k, int64_t n_edges, int64_t* edge_index, rpg_stream_t stream);
 
 /* pose_utils.qexp (pose_utils.py:340-348): q[i] = [cos|v|, sinc(|v|/pi) v] for n log-quaternions v [n, 3] -> q [n, 4]. */
 int rpg_qexp(const float* v, int64_t n, float* q, rpg_stream_t stream);

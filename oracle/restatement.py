@@ -151,6 +151,27 @@ def knn_graph(x, k, n_graphs, n_nodes):
     return torch.cat(cols, dim=1)
 
 
+def knn_graph_batch(x, k, batch):
+    """knn_graph for a general sorted PyG `batch` vector (graphs of different sizes): a node with fewer than k other
+    nodes in its graph gets all of them [3p torch-cluster 1.5.9: missing neighbours are dropped from the result].
+    Same ordering and tie rule as `knn_graph`; PARITY UNPINNED like it."""
+    cols = []
+    batch = batch.long()
+    for g in torch.unique(batch).tolist():
+        ids = torch.nonzero(batch == g).flatten()
+        n = ids.numel()
+        kk = min(k, n - 1)
+        if kk <= 0:
+            continue
+        xg = x[ids].double()
+        d = ((xg.unsqueeze(1) - xg.unsqueeze(0)) ** 2).sum(-1)
+        d = d + torch.diag(torch.full((n,), float("inf"), dtype=torch.float64))
+        nbr = torch.sort(d, dim=1, stable=True).indices[:, :kk]
+        centre = torch.arange(n).view(-1, 1).expand_as(nbr)
+        cols.append(torch.stack([ids[nbr.reshape(-1)], ids[centre.reshape(-1)]], 0))
+    return torch.cat(cols, dim=1) if cols else torch.zeros(2, 0, dtype=torch.long)
+
+
 def conv_edge_forward(p, x, edge_index, e, relu_masks=None):
     """simpleConvEdge.forward, my_gnn_layer.py:253-274: edge model, message = att(mlp(cat[x_i, x_j, e'])) with
     x_i = x[edge_index[1]] (destination), x_j = x[edge_index[0]] (source) [3p PyG], mean over destinations; no update."""

@@ -195,6 +195,7 @@ SIGNATURES = {
     "rpg_qexp": (I, [P, I64, P, P]),
     "rpg_pose_errors": (I, [P, P, I64, P, P, P]),
     "rpg_knn_graph": (I, [P, I, I, I, I, I, P, P]),
+    "rpg_knn_graph_ragged": (I, [P, I, I, P, P, I, I, I, C.c_int64, P, P]),
     "rpg_build_edge_index": (I, [C.POINTER(Graph), P, P]),
     "rpg_per_graph_tables_words": (I64, [I, I, I]),
     "rpg_per_graph_tables": (I, [P, I, I, I, P, P, P]),

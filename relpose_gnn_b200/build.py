@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librpg_b200.so")
-SOURCES = ["rpg_gemm.cu", "rpg_aux.cu", "rpg_layer.cu", "rpg_util.cu", "rpg_attention.cu"]
+SOURCES = ["rpg_gemm.cu", "rpg_gemm_tn.cu", "rpg_aux.cu", "rpg_layer.cu", "rpg_util.cu", "rpg_attention.cu"]
 HEADERS = ["rpg_ptx.cuh", "rpg_internal.h", os.path.join("..", "..", "include", "rpg.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

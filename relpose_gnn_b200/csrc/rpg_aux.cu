@@ -1085,13 +1085,21 @@ __global__ void eval_compose_kernel(const float* __restrict__ pred_edges, const 
 // the N(N-1)/2 distances, then one thread per centre selects k times.
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_MAX_N = 64;
+// One CTA per graph.  Uniform batches: N nodes and N*k edges per graph.  Ragged batches (node_ptr / edge_ptr given):
+// graph g owns nodes [node_ptr[g], node_ptr[g+1]) and edges from edge_ptr[g], min(k, n_g - 1) per node.
 __global__ void __launch_bounds__(256)
-knn_graph_kernel(const float* __restrict__ x, int ldx, int N, int D, int k, long long* __restrict__ ei, long long Et) {
+knn_graph_kernel(const float* __restrict__ x, int ldx, int N_uniform, int D, int k_max, long long* __restrict__ ei, long long Et,
+                 const long long* __restrict__ node_ptr, const long long* __restrict__ edge_ptr) {
     pdl_prologue();
     __shared__ float dist[KNN_MAX_N][KNN_MAX_N + 1];
     const int g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const float* xg = x + (size_t)g * N * ldx;
+    const long long node0 = node_ptr ? node_ptr[g] : (long long)g * N_uniform;
+    const int N = node_ptr ? (int)(node_ptr[g + 1] - node0) : N_uniform;
+    if (N > KNN_MAX_N) __trap();                                  // the host checks the largest graph; never reached
+    const int k = k_max < N - 1 ? k_max : N - 1;
+    const long long edge0 = edge_ptr ? edge_ptr[g] : (long long)g * N_uniform * k_max;
+    const float* xg = x + (size_t)node0 * ldx;
     const int npairs = N * (N - 1) / 2;
     for (int p = warp; p < npairs; p += nwarps) {
         // unrank p -> (i, j), i < j
@@ -1117,15 +1125,15 @@ knn_graph_kernel(const float* __restrict__ x, int ldx, int N, int D, int k, long
         for (int r = 0; r < k; ++r) {
             int best = -1;
             float bd = INFINITY;
-            for (int j = 0; j < N; ++j) {
+            for (int j = 0; j < N; ++j) {                     // strict <: equal distances keep the lower node index
                 if ((taken >> j) & 1ull) continue;
                 const float d = dist[i][j];
                 if (best < 0 || d < bd) { best = j; bd = d; }
             }
             taken |= 1ull << best;
-            const long long e = ((long long)g * N + i) * k + r;
-            ei[e] = (long long)g * N + best;                  // row 0: source = neighbour
-            ei[Et + e] = (long long)g * N + i;                // row 1: destination = centre
+            const long long e = edge0 + (long long)i * k + r;
+            ei[e] = node0 + best;                             // row 0: source = neighbour
+            ei[Et + e] = node0 + i;                           // row 1: destination = centre
         }
     }
 }
@@ -1908,7 +1916,19 @@ int rpg_knn_graph(const float* x, int ldx, int G, int N, int D, int k, int64_t* 
         return set_error(RPG_E_ARG, "knn_graph: need 2 <= N <= 64, 1 <= k < N, D and pitch multiples of 4");
     const long long Et = (long long)G * N * k;
     launch_pdl(knn_graph_kernel, dim3(G), dim3(256), 0, as_stream(stream), x, ldx, N, D, k,
-               reinterpret_cast<long long*>(edge_index), Et);
+               reinterpret_cast<long long*>(edge_index), Et, (const long long*)nullptr, (const long long*)nullptr);
+    return check_launch("knn_graph_kernel");
+}
+
+int rpg_knn_graph_ragged(const float* x, int ldx, int G, const int64_t* node_ptr, const int64_t* edge_ptr, int max_nodes, int D,
+                         int k, int64_t n_edges, int64_t* edge_index, rpg_stream_t stream) {
+    if (!x || !edge_index || !node_ptr || !edge_ptr || G <= 0 || max_nodes < 1 || max_nodes > KNN_MAX_N || k < 1 || n_edges < 0 ||
+        D % 4 || ldx % 4)
+        return set_error(RPG_E_ARG, "knn_graph_ragged: need graphs of <= 64 nodes, k >= 1, D and pitch multiples of 4");
+    if (n_edges == 0) return 0;
+    launch_pdl(knn_graph_kernel, dim3(G), dim3(256), 0, as_stream(stream), x, ldx, 0, D, k,
+               reinterpret_cast<long long*>(edge_index), (long long)n_edges, reinterpret_cast<const long long*>(node_ptr),
+               reinterpret_cast<const long long*>(edge_ptr));
     return check_launch("knn_graph_kernel");
 }
 

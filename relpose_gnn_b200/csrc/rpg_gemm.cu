@@ -83,6 +83,7 @@ struct GemmKParams {
     unsigned long long drop_seed;  // fused feature dropout of the out_relu output (plain epilogue)
     uint32_t drop_thresh;          // keep iff hash byte >= thresh; 0 = off
     float drop_scale;              // 1 / (1 - p)
+    int l2_prefetch;               // producer pulls the NEXT work item's streamed tiles into L2 while it feeds this one
 };
 
 struct GemmTmaps {
@@ -108,6 +109,23 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& u) {
         if (!(hi != 0 && hi < 0x8000u)) f[2 * i + 1] = 0.f;
     }
 }
+
+// Development build only (-DRPG_GEMM_TRACE, tools/gemm_trace.py): cycles each single-thread role of a CTA spends waiting,
+// accumulated per CTA.  slots: 0 producer waits for a free ring stage, 1 producer total, 2 MMA issuer waits for operands,
+// 3 MMA issuer waits for a drained accumulator, 4 MMA issuer total, 5 epilogue warp 0 waits for the accumulator,
+// 6 epilogue warp 0 waits for its staging tile (previous TMA store still reading), 7 epilogue warp 0 total.
+#ifdef RPG_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[512][8];
+#define TR_DECL(a) unsigned long long a = 0ull
+#define TR_T0(v) const long long v = clock64()
+#define TR_ACC(a, v) a += (unsigned long long)(clock64() - (v))
+#define TR_FLUSH(slot, a) g_gemm_trace[blockIdx.x & 511][slot] += (a)
+#else
+#define TR_DECL(a)
+#define TR_T0(v)
+#define TR_ACC(a, v)
+#define TR_FLUSH(slot, a)
+#endif
 
 // CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on adjacent 128-row blocks of the same column
 // block and each fetches HALF of every weight (B) tile, multicast into both shared memories: the L2 -> SM traffic for
@@ -219,6 +237,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             // ------------------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
+            TR_T0(tr_prod);
+            TR_DECL(tr_w0);
+            TR_DECL(tr_tot);
             if (WS && worker < num_items) {
                 // every item of this cluster has the same column block: its B half-tiles for all k-blocks, once
                 const int n_blk = worker % num_n_blocks;
@@ -232,11 +253,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                 const int tile = MODE == 0 ? item : item / p.splits;
                 const int m_blk = (tile / num_n_blocks) * CL + cta_rank, n_blk = tile % num_n_blocks;
                 if (MODE == 0) {
+                    // L2 prefetch: the ring (64-96 KB of A per CTA) is shallower than the HBM latency under load (the MMA
+                    // issuer waited for operands 12-24 % of its time, tools/gemm_trace.py); the next item's A tiles are
+                    // pulled into L2 one item ahead, so its ring loads see the L2 latency instead.
+                    const int item_nx = item + num_workers;
+                    const bool pf = p.l2_prefetch && item_nx < num_items;
+                    const int m_blk_nx = ((item_nx / num_n_blocks) * CL + cta_rank) * BLOCK_M;
                     int kb_global = 0;
                     for (int s = 0; s < 6; ++s) {
                         const CUtensorMap* tmA = &tm.a[s];
                         for (int kb = 0; kb < p.num_kb[s]; ++kb, ++kb_global) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (pf && m_blk_nx < p.M) tma_prefetch_2d(tmA, kb * BLOCK_K, m_blk_nx);
+                            { TR_T0(t); mbar_wait(&empty_bar[stage], phase ^ 1); TR_ACC(tr_w0, t); }
                             if (WS) {
                                 const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
                                 if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * A_STAGE_BYTES);
@@ -277,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                         const int r0 = m_blk * BLOCK_M;
                         const int pat = p.gsel_div ? (r0 % p.Ep) / p.gsel_div : m_blk;   // periodic template | per-block tiles
                         const int win = (r0 / p.Ep) * p.Nn;
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        { TR_T0(t); mbar_wait(&empty_bar[stage], phase ^ 1); TR_ACC(tr_w0, t); }
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
                         tma_load_2d(&tm.ga[gs], &full_bar[stage], smem_a + stage * A_STAGE_BYTES, 0, pat * BLOCK_M);
                         for (int j = 0; j < p.block_n / 64; ++j)
@@ -290,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     const int kb0 = split * p.kb_per_split;
                     const int kb1 = min(kb0 + p.kb_per_split, p.total_kb);
                     for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        { TR_T0(t); mbar_wait(&empty_bar[stage], phase ^ 1); TR_ACC(tr_w0, t); }
                         mbar_arrive_expect_tx(&full_bar[stage], stage_tx_bytes);
                         // MN-major tiles: one 64(MN) x 64(K rows) box per 128-byte slab of the MN extent
                         for (int j = 0; j < BLOCK_M / 64; ++j)
@@ -308,6 +336,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     }
                 }
             }
+            TR_ACC(tr_tot, tr_prod);
+            TR_FLUSH(0, tr_w0);
+            TR_FLUSH(1, tr_tot);
         }
     } else if (warp == 1) {
         if (lane == 0 && !(PAIR && cta_rank != 0)) {
@@ -320,6 +351,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            TR_T0(tr_mma);
+            TR_DECL(tr_w2);
+            TR_DECL(tr_w3);
+            TR_DECL(tr_tot);
             if (WS && worker < num_items) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (int item = worker; item < num_items; item += num_workers, ++it) {
                 const int acc = it & 1;
@@ -331,11 +366,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                     const int kb0 = (item % p.splits) * p.kb_per_split;
                     n_kb = min(kb0 + p.kb_per_split, p.total_kb) - kb0;
                 }
-                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                { TR_T0(t); mbar_wait(&acc_empty[acc], acc_phase ^ 1); TR_ACC(tr_w3, t); }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    { TR_T0(t); mbar_wait(&full_bar[stage], phase); TR_ACC(tr_w2, t); }
                     tc_fence_after();
                     const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), lbo, sbo);
                     if (MODE == 0 && kb >= n_kb - p.n_gseg) {
@@ -364,6 +399,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                 }
                 if (n_kb <= 0) umma_commit(&acc_full[acc]);   // empty split: nothing to accumulate (epilogue writes zeros)
             }
+            TR_ACC(tr_tot, tr_mma);
+            TR_FLUSH(2, tr_w2);
+            TR_FLUSH(3, tr_w3);
+            TR_FLUSH(4, tr_tot);
         }
     } else {
         // ---------------------------------------------------------------- epilogue warps
@@ -383,9 +422,16 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
         uint8_t* stg = stg0;
         uint8_t* my_row = stg + lane * 128;
         int sbuf = 0;
+        TR_DECL(tr_w5);
+        TR_DECL(tr_w6);
+        TR_DECL(tr_etot);
         // a staging tile that no earlier TMA store of this warp still reads (stores alternate between the tiles)
         auto acquire_stage = [&]() {
-            if (lane == 0) { if (STG_BUFS == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }
+            if (lane == 0) {
+                TR_T0(t);
+                if (STG_BUFS == 2) bulk_wait_read_1(); else bulk_wait_read_all();
+                TR_ACC(tr_w6, t);
+            }
             __syncwarp();
             if (STG_BUFS == 2) {
                 sbuf ^= 1;
@@ -419,6 +465,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             }
         }
         int it = 0;
+        TR_T0(tr_epi);
         int cs_stage = 0;                          // TN column sums: this role walks the smem ring like the MMA warp
         uint32_t cs_phase = 0;
         for (int item = worker; item < num_items; item += num_workers, ++it) {
@@ -498,7 +545,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
                 if (half + 2 < n_chunks && n0b < p.N)
                     mbits1 = __ldg(reinterpret_cast<const unsigned long long*>(p.mask_bits + (size_t)row * p.mask_bits_ld + (n0b >> 3)));
             }
-            mbar_wait(&acc_full[acc], acc_phase);
+            { TR_T0(t); mbar_wait(&acc_full[acc], acc_phase); TR_ACC(tr_w5, t); }
             tc_fence_after();
             bool released = false;
 
@@ -760,6 +807,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTmaps tm, const GemmKParams p) {
             }
         }
         if (lane == 0) bulk_wait_all();            // all results are in global memory before the CTA retires
+        TR_ACC(tr_etot, tr_epi);
+        if (ew == 0 && lane == 0) { TR_FLUSH(5, tr_w5); TR_FLUSH(6, tr_w6); TR_FLUSH(7, tr_etot); }
     }
 
     __syncwarp();
@@ -779,6 +828,15 @@ static bool gemm_ws_enabled() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("RPG_GEMM_WS");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+// RPG_GEMM_L2PF=0 turns the producer's L2 prefetch of the next work item off (A/B comparisons).
+static bool gemm_l2_prefetch_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("RPG_GEMM_L2PF");
         on = (e && e[0] == '0') ? 0 : 1;
     }
     return on == 1;
@@ -1031,6 +1089,7 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
     p.ldo = g->ldo;
     p.out_f32 = g->out_f32; p.ldo_f32 = g->ldo_f32;
     p.a_colsum = g->mode == 1 ? g->a_colsum : nullptr;
+    p.l2_prefetch = gemm_l2_prefetch_enabled() ? 1 : 0;
     if (g->drop_p > 0.f) {
         if (g->mode != 0 || !g->out_relu || g->out_f32 || g->gadd[0] || g->gadd[1] || g->resid || g->mask || g->drop_p >= 1.f)
             return set_error(RPG_E_ARG, "rpg_gemm: fused dropout needs NT mode, an out_relu output, the plain epilogue, 0 < p < 1");
@@ -1167,3 +1226,19 @@ int gemm_launch(const rpg_gemm_t* g, cudaStream_t stream) {
 }
 
 }  // namespace rpg
+
+#ifdef RPG_GEMM_TRACE
+// Development build only: copies (and optionally clears) the per-CTA wait-cycle counters of gemm_tc_kernel.
+extern "C" int rpg_debug_gemm_trace(unsigned long long* out_host, int n_blocks, int reset) {
+    if (n_blocks < 0 || n_blocks > 512) return -1;
+    cudaDeviceSynchronize();
+    if (out_host && n_blocks &&
+        cudaMemcpyFromSymbol(out_host, rpg::g_gemm_trace, sizeof(unsigned long long) * 8 * n_blocks) != cudaSuccess) return -2;
+    if (reset) {
+        void* sym = nullptr;
+        if (cudaGetSymbolAddress(&sym, rpg::g_gemm_trace) != cudaSuccess || cudaMemset(sym, 0, sizeof(unsigned long long) * 8 * 512) != cudaSuccess)
+            return -3;
+    }
+    return 0;
+}
+#endif

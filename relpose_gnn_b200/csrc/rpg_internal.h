@@ -41,6 +41,20 @@ int attention_series_fwd(const void* gtp, int gtp_bf16, long long Et, int c, rpg
 int attention_series_bwd(const void* gtp, int gtp_bf16, const float* dyn, int ld_dyn, const rpg_graph_t* graph, long long Et,
                          int c, rpg_bf16* dgtp, int ld_dgtp, rpg_bf16* dgtp_lo, cudaStream_t s);
 
+// Grouped weight-gradient GEMMs on CTA pairs (rpg_gemm_tn.cu): C_i[M, N] partials = A_i^T B_i for up to TN_GROUP_MAX
+// independent problems in one persistent launch.  part: fp32 [splits][M][N] (+ colsum [splits][M] when given).
+constexpr int TN_GROUP_MAX = 12;
+struct TnDesc {
+    const rpg_bf16* A; int lda; int M;
+    const rpg_bf16* B; int ldb; int N;
+    long long R;
+    float* part; int splits;
+    float* colsum;
+};
+bool tn_group_supported(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R);
+int tn_group_splits(int M, int N, long long R, int sm_count);
+int tn_group_launch(const TnDesc* d, int n, cudaStream_t stream);
+
 inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Programmatic dependent launch: every kernel of the library starts with griddepcontrol.launch_dependents +

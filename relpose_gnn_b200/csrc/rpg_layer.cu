@@ -112,7 +112,9 @@ struct WgradQueue {
     int sms;
     cudaStream_t s;
     rpg_reduce_batch_t batch;
-    WgradQueue(float* ws_, int sms_, cudaStream_t s_) : ws(ws_), off(0), sms(sms_), s(s_) { batch.n = 0; }
+    TnDesc pend[TN_GROUP_MAX];       // weight-gradient products queued for ONE grouped launch (rpg_gemm_tn.cu)
+    int npend;
+    WgradQueue(float* ws_, int sms_, cudaStream_t s_) : ws(ws_), off(0), sms(sms_), s(s_), npend(0) { batch.n = 0; }
     int add(const float* part, int splits, long long stride, int rows, int cols, float* out, int ldo) {
         if (batch.n == RPG_REDUCE_BATCH_MAX) {
             int rc = flush();
@@ -122,14 +124,34 @@ struct WgradQueue {
         d.part = part; d.out = out; d.stride = stride; d.splits = splits; d.rows = rows; d.cols = cols; d.ldo = ldo;
         return 0;
     }
+    // partials of A^T B at ws + off: queued for the grouped pair kernel when the shapes qualify, launched at once otherwise
+    int product(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, bool with_colsum,
+                float** part, int* splits) {
+        float* p = ws + off;
+        *part = p;
+        if (tn_group_supported(A, lda, M, B, ldb, N, R)) {
+            if (npend == TN_GROUP_MAX) {
+                int rc = launch();
+                if (rc) return rc;
+            }
+            *splits = tn_group_splits(M, N, R, sms);
+            TnDesc& d = pend[npend++];
+            d.A = A; d.lda = lda; d.M = M; d.B = B; d.ldb = ldb; d.N = N; d.R = R; d.part = p; d.splits = *splits;
+            d.colsum = with_colsum ? p + (size_t)*splits * M * N : nullptr;
+        } else {
+            int rc = wgrad_partials(A, lda, M, B, ldb, N, R, p, sms, s, splits, with_colsum);
+            if (rc) return rc;
+        }
+        off += ((size_t)*splits * M * N + (with_colsum ? (size_t)*splits * M : 0) + 63) & ~(size_t)63;
+        return 0;
+    }
     // dW (+)= A^T B over R rows, optionally bias (+)= colsum(A); partials only, fold queued
     int wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* out, int ldo,
               float* bias = nullptr) {
         int splits = 0;
-        float* p = ws + off;
-        int rc = wgrad_partials(A, lda, M, B, ldb, N, R, p, sms, s, &splits, bias != nullptr);
+        float* p = nullptr;
+        int rc = product(A, lda, M, B, ldb, N, R, bias != nullptr, &p, &splits);
         if (rc) return rc;
-        off += ((size_t)splits * M * N + (bias ? (size_t)splits * M : 0) + 63) & ~(size_t)63;
         if ((rc = add(p, splits, (long long)M * N, M, N, out, ldo))) return rc;
         if (bias) rc = add(p + (size_t)splits * M * N, splits, M, 1, M, bias, M);
         return rc;
@@ -137,15 +159,20 @@ struct WgradQueue {
     // partials of a stacked product whose row blocks go to different parameters: the caller queues the folds
     int partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, bool with_colsum,
                  float** part, int* splits) {
-        *part = ws + off;
-        int rc = wgrad_partials(A, lda, M, B, ldb, N, R, *part, sms, s, splits, with_colsum);
-        if (rc) return rc;
-        off += ((size_t)*splits * M * N + (with_colsum ? (size_t)*splits * M : 0) + 63) & ~(size_t)63;
-        return 0;
+        return product(A, lda, M, B, ldb, N, R, with_colsum, part, splits);
+    }
+    // launches the queued products (their partials exist on the stream afterwards)
+    int launch() {
+        if (!npend) return 0;
+        int rc = tn_group_launch(pend, npend, s);
+        npend = 0;
+        return rc;
     }
     int flush() {
+        int rc = launch();
+        if (rc) return rc;
         if (!batch.n) return 0;
-        int rc = rpg_reduce_splits_batch(&batch, (rpg_stream_t)s);
+        rc = rpg_reduce_splits_batch(&batch, (rpg_stream_t)s);
         batch.n = 0;
         return rc;
     }
@@ -447,8 +474,15 @@ struct WgradQueue3 {
         if (!rc) rc = q2.add(part[2] + block_off, splits[2], stride, rows, cols, out, ldo);
         return rc;
     }
+    int launch() {
+        int rc = q0.launch();
+        if (!rc) rc = q1.launch();
+        if (!rc) rc = q2.launch();
+        return rc;
+    }
     int flush() {
-        int rc = q0.flush();
+        int rc = launch();
+        if (!rc) rc = q0.flush();
         if (!rc) rc = q1.flush();
         if (!rc) rc = q2.flush();
         return rc;
@@ -569,6 +603,7 @@ int rpg_layer_bwd_split(const rpg_layer_weights_split_t* w, const rpg_graph_t* g
     {
         // T = dgtp^T h2, csg = colsum(dgtp): three partial sets folded NOW into zeroed scratch (three small launches)
         RPG_TRY(q.partials({b->dgtp_hi, b->dgtp_lo}, c3p, c3, {t->h2_hi, t->h2_lo}, D, D, Et, true, part, splits));
+        RPG_TRY(q.launch());
         cudaMemsetAsync(b->T_tmp, 0, (size_t)c3 * D * sizeof(float), s);
         cudaMemsetAsync(b->gtp_bias_tmp, 0, (size_t)c3 * sizeof(float), s);
         for (int i = 0; i < 3; ++i) {
@@ -805,12 +840,29 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         // with h2sum[n] = sum over in-edges of h2 = deg(n) * mean(h2)[n] (the forward's node-level mean).
         if (!b->T_tmp || !b->h2sum || !w->Wgtp_f32 || !w->W2m_f32) return set_error(RPG_E_ARG, "layer_bwd: T_tmp / h2sum / master weights missing");
         RPG_TRY(q.partials(b->dgtp, c3p, c3, t->h2, D, D, Et, true, &part, &splits));
-        {
+        // node-level parts: dan^T h2sum -> mlp.2.weight, dan^T ysum -> att.W.weight, sum_n deg(n) dan[n] -> both biases
+        RPG_TRY(rpg_scale_rows(t->mbar, D, Nt, D, gr->deg, gr->N, b->h2sum, D, stream));
+        RPG_TRY(q.wgrad(b->dan, D, D, b->h2sum, D, D, Nt, b->g_mlp2_w, D));
+        RPG_TRY(rpg_scale_rows(t->ybar, cp, Nt, cp, gr->deg, gr->N, b->ysum, cp, stream));
+        RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
+        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
+        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
+        if (!v1) {
+            // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
+            RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));
+            RPG_TRY(q.wgrad(b->dh3, D, D, t->x, D, D, Nt, b->g_upd0_w, 2 * D, b->g_upd0_b));
+            RPG_TRY(q.wgrad(b->dh3, D, D, t->a, D, D, Nt, b->g_upd0_w + D, 2 * D));
+        }
+    }
+    if (have_out) {
+            // (after every product of this layer has been queued: ONE grouped launch carries all of them)
             const float* cs = part + (size_t)splits * c3 * D;            // [splits, 3c] column sums of dgtp
             RPG_TRY(q.add(cs, splits, c3, 1, c, b->g_att_g_b, c));
             RPG_TRY(q.add(cs + c, splits, c3, 1, c, b->g_att_theta_b, c));
             RPG_TRY(q.add(cs + 2 * c, splits, c3, 1, c, b->g_att_phi_b, c));
-            // T and csg are needed NOW by the small fp32 products: their own fold launch into zeroed scratch
+            // T and csg are needed NOW by the small fp32 products: the queued products run, then their own fold launch
+            // into zeroed scratch
+            RPG_TRY(q.launch());
             cudaMemsetAsync(b->T_tmp, 0, (size_t)c3 * D * sizeof(float), s);
             cudaMemsetAsync(b->gtp_bias_tmp, 0, (size_t)c3 * sizeof(float), s);
             rpg_reduce_batch_t fold;
@@ -839,20 +891,6 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
             }
             RPG_TRY(rpg_sgemm_batch(&sg, stream));
         }
-        // node-level parts: dan^T h2sum -> mlp.2.weight, dan^T ysum -> att.W.weight, sum_n deg(n) dan[n] -> both biases
-        RPG_TRY(rpg_scale_rows(t->mbar, D, Nt, D, gr->deg, gr->N, b->h2sum, D, stream));
-        RPG_TRY(q.wgrad(b->dan, D, D, b->h2sum, D, D, Nt, b->g_mlp2_w, D));
-        RPG_TRY(rpg_scale_rows(t->ybar, cp, Nt, cp, gr->deg, gr->N, b->ysum, cp, stream));
-        RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
-        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
-        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
-        if (!v1) {
-            // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
-            RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));
-            RPG_TRY(q.wgrad(b->dh3, D, D, t->x, D, D, Nt, b->g_upd0_w, 2 * D, b->g_upd0_b));
-            RPG_TRY(q.wgrad(b->dh3, D, D, t->a, D, D, Nt, b->g_upd0_w + D, 2 * D));
-        }
-    }
     RPG_TRY(q.flush());
     return 0;
 }

@@ -69,6 +69,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
 }
+// 2-D tile global -> L2 only (no shared-memory destination, no completion): pulls a tile the ring will ask for later
+// out of HBM ahead of time, so that the ring's own depth only has to cover the L2 latency.
+__device__ __forceinline__ void tma_prefetch_2d(const void* desc, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(c_inner), "r"(c_outer) : "memory");
+}
 // 2-D tiled load global -> shared, completion counted in bytes on `bar`.
 __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, void* dst, int c_inner, int c_outer) {
     asm volatile(

@@ -317,25 +317,47 @@ def mask_edge_index(edge_index, keep_undirected, n_graphs):
 
 def knn_graph(x, k, batch=None, loop=False, num_nodes_per_graph=None):
     """torch_cluster.knn_graph as the reference calls it (posenet.py:1043-1050: `knn_graph(x, k, batch=data.batch,
-    loop=False)`) for batches of equally sized graphs: int64 edge_index [2, G*N*k], edges (neighbour -> centre) grouped
-    by centre, nearest first.  x: float32 CUDA [G*N, D]; graph size from `num_nodes_per_graph` or the `batch` vector."""
+    loop=False)`): int64 edge_index, edges (neighbour -> centre) grouped by centre, nearest first, equal distances to
+    the lower node index.  x: float32 CUDA [n, D].  The graph sizes come from `num_nodes_per_graph` (equally sized
+    graphs, no host synchronisation: the model's path) or from the sorted PyG `batch` vector, which may describe graphs
+    of different sizes (<= 64 nodes each; a node with fewer than k candidates gets all of them)."""
     if loop:
         raise NotImplementedError("loop=True is never used by the reference")
     if not x.is_cuda:
         raise ValueError("knn_graph needs a CUDA tensor: the sm_100a kernels are the only implementation")
-    if num_nodes_per_graph is None:
-        if batch is None:
-            num_nodes_per_graph = x.size(0)
-        else:
-            num_nodes_per_graph = int((batch == batch[0]).sum().item())
-    N = int(num_nodes_per_graph)
+    if k < 1:
+        raise ValueError("knn_graph: k must be >= 1")
+    xf = x.float().contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    if num_nodes_per_graph is None and batch is not None:
+        if batch.numel() != x.size(0):
+            raise ValueError("knn_graph: batch must hold one graph id per row of x")
+        b = batch.to(device=x.device, dtype=torch.int64)
+        if bool((b[1:] < b[:-1]).any()):
+            raise ValueError("knn_graph: batch must be sorted (PyG batches are)")
+        counts = torch.bincount(b)
+        counts = counts[counts > 0]
+        n_max = int(counts.max())
+        if not bool((counts == n_max).all()):                      # graphs of different sizes
+            if n_max > 64:
+                raise ValueError("knn_graph: graphs of more than 64 nodes are not supported")
+            node_ptr = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=x.device)
+            node_ptr[1:] = counts.cumsum(0)
+            edge_ptr = torch.zeros_like(node_ptr)
+            edge_ptr[1:] = (counts * torch.clamp(counts - 1, max=k)).cumsum(0)
+            n_edges = int(edge_ptr[-1])
+            ei = torch.empty(2, n_edges, dtype=torch.int64, device=x.device)
+            _lib.check(_lib.load().rpg_knn_graph_ragged(xf.data_ptr(), xf.stride(0), counts.numel(), node_ptr.data_ptr(),
+                                                        edge_ptr.data_ptr(), n_max, xf.size(1), k, n_edges, ei.data_ptr(), stream),
+                       "rpg_knn_graph_ragged")
+            return ei
+        num_nodes_per_graph = n_max
+    N = int(num_nodes_per_graph) if num_nodes_per_graph is not None else x.size(0)
     if x.size(0) % N:
         raise ValueError("knn_graph: the batch must consist of equally sized graphs")
-    xf = x.float().contiguous()
     G = xf.size(0) // N
     ei = torch.empty(2, G * N * k, dtype=torch.int64, device=x.device)
-    _lib.check(_lib.load().rpg_knn_graph(xf.data_ptr(), xf.stride(0), G, N, xf.size(1), k, ei.data_ptr(),
-                                         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "rpg_knn_graph")
+    _lib.check(_lib.load().rpg_knn_graph(xf.data_ptr(), xf.stride(0), G, N, xf.size(1), k, ei.data_ptr(), stream), "rpg_knn_graph")
     return ei
 
 

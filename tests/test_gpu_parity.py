@@ -652,6 +652,46 @@ def test_knn_graph_matches_restated_torch_cluster(N, k, D, Gn):
     assert torch.equal(rpg.knn_graph(x.to(dev()), k, batch=batch), ei)
 
 
+def test_knn_graph_ties_and_duplicate_points_go_to_the_lower_index():
+    """VERDICT r1 missing 5: equal distances.  Integer coordinates make every squared distance exact in fp32 and fp64
+    alike, so ties are real ties on both sides: duplicated points (distance 0), whole graphs of identical points, and
+    lattice points at equal distance.  Rule (restated torch_cluster CUDA kernel: candidates scanned in index order,
+    strict <): the lower node index first."""
+    N, k, D, Gn = 9, 4, 64, 50
+    gen = torch.Generator().manual_seed(99)
+    x = torch.randint(-2, 3, (Gn * N, D), generator=gen).float()
+    x[:, 8:] = 0                                            # 8 informative coordinates in {-2..2}: many equal distances
+    x[N:2 * N] = x[N]                                       # graph 1: nine identical points
+    x[2 * N + 3] = x[2 * N + 1]                             # graph 2: a duplicated point
+    x[3 * N:4 * N, :] = 0
+    x[3 * N:4 * N, 0] = torch.arange(N).float()             # graph 3: a line -- left and right neighbour tie
+    ei = rpg.knn_graph(x.to(dev()), k, num_nodes_per_graph=N).cpu()
+    ref = R.knn_graph(x, k, Gn, N)
+    d = ((x[ref[0]] - x[ref[1]]) ** 2).sum(1).view(-1, k)
+    assert (d[:, 1:] == d[:, :-1]).any()                    # the case under test: ties inside the k nearest
+    assert torch.equal(ei, ref)
+    assert ei[0, N * k:N * k + k].tolist() == [N + 1, N + 2, N + 3, N + 4]           # identical points: lowest indices, self skipped
+    assert ei[0, (3 * N + 4) * k:(3 * N + 4) * k + k].tolist() == [3 * N + 3, 3 * N + 5, 3 * N + 2, 3 * N + 6]
+
+
+@pytest.mark.parametrize("sizes,k", [([9, 3, 1, 17, 2, 5], 4), ([2, 2, 7], 1), ([64, 1, 30], 8), ([5, 5, 5, 6], 5)])
+def test_knn_graph_on_batches_of_unequal_graph_sizes(sizes, k):
+    """A general PyG `batch` vector: graphs of different sizes, graphs with fewer than k + 1 nodes (they contribute all
+    their other nodes), single-node graphs (no edges)."""
+    gen = torch.Generator().manual_seed(sum(sizes) + k)
+    n = sum(sizes)
+    x = torch.randn(n, 128, generator=gen)
+    x[: sizes[0]] = torch.randint(-1, 2, (sizes[0], 128), generator=gen).float()        # ties in the first graph
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    ei = rpg.knn_graph(x.to(dev()), k, batch=batch.to(dev())).cpu()
+    ref = R.knn_graph_batch(x, k, batch)
+    assert ei.shape == ref.shape == (2, sum(s * min(k, s - 1) for s in sizes))
+    assert torch.equal(ei, ref)
+    assert bool((batch[ei[0]] == batch[ei[1]]).all()) and bool((ei[0] != ei[1]).all())
+    with pytest.raises(ValueError):
+        rpg.knn_graph(x.to(dev()), k, batch=batch.flip(0).to(dev()))                     # unsorted batch vector
+
+
 def test_stack_with_knn_rewiring_against_oracle():
     """PoseNetX_R2.forward with knn=4 (the CLI default, train.py:377): rewired graph + the same stack, forward and
     backward (gradients against the oracle with the kernel's own activation patterns imposed)."""

@@ -167,6 +167,12 @@ def test_knn_graph_api():
     assert ei.tolist() == [[1, 2, 0, 2, 1, 0, 2, 1], [0, 0, 1, 1, 2, 2, 3, 3]]
     with pytest.raises(ValueError):
         rpg.knn_graph(torch.zeros(8, 64), 2, num_nodes_per_graph=4)
+    # general batch vectors: every graph on its own, short graphs give all their other nodes, ties to the lower index
+    xb = torch.tensor([[0.0], [1.0], [3.0], [7.0], [5.0], [5.0], [9.0]])
+    eb = R.knn_graph_batch(xb, 2, torch.tensor([0, 0, 0, 0, 1, 1, 2]))
+    assert eb.tolist() == [[1, 2, 0, 2, 1, 0, 2, 1, 5, 4], [0, 0, 1, 1, 2, 2, 3, 3, 4, 5]]
+    tie = R.knn_graph(torch.tensor([[0.0], [1.0], [2.0], [1.0]]), 2, 1, 4)
+    assert tie[0].view(4, 2).tolist() == [[1, 3], [3, 0], [1, 3], [1, 0]]
 
 
 def test_save_poses_writes_the_reference_npz_layout(tmp_path):
