@@ -62,6 +62,21 @@ class AttentionBlock(nn.Module):
         self.W = Linear(in_channels // 8, in_channels)
 
 
+def fast_params(mod, names):
+    """{name: parameter} for dotted names without nn.Module.get_parameter's path parsing (a training step looks ~80
+    parameters up): the owning leaf modules are resolved once per (module, names) and cached on the module; the
+    parameter objects themselves are read from the leaves' `_parameters` every time, so re-assigned parameters are seen."""
+    cache = mod.__dict__.setdefault("_rpg_leaf_cache", {})
+    leaves = cache.get(names)
+    if leaves is None:
+        leaves = []
+        for n in names:
+            path, _, leaf = n.rpartition(".")
+            leaves.append((n, mod.get_submodule(path) if path else mod, leaf))
+        cache[names] = leaves
+    return {n: m._parameters[leaf] for n, m, leaf in leaves}
+
+
 class PackedLayerWeights:
     """bf16 operand copies of the fp32 master parameters, cut per input source and transposed for dgrad.
     Re-packed whenever any parameter's version counter changes (optimizer.step() bumps it in place)."""
@@ -94,13 +109,21 @@ class PackedLayerWeights:
         self.Wgtp_f32 = torch.zeros(3 * c, D, dtype=f32, device=device)   # att.g | att.theta | att.phi master weights
         self.one = torch.ones(1, dtype=f32, device=device)
         self.versions = None
+        self._replay = None           # (recorded pack batches, composed-operand product) of the last full refresh
         self.struct = _lib.LayerWeights()
 
     def refresh(self, mod):
         v1 = self.variant == 1
-        p = {n: mod.get_parameter(n) for n in (PARAM_ORDER_EDGE if v1 else PARAM_ORDER)}
-        versions = (getattr(mod, "_pack_epoch", 0),) + tuple((q.data_ptr(), q._version) for q in p.values())
+        p = fast_params(mod, PARAM_ORDER_EDGE if v1 else PARAM_ORDER)
+        ptrs = tuple(q.data_ptr() for q in p.values())
+        versions = (getattr(mod, "_pack_epoch", 0), ptrs, getattr(mod, "_value_epoch", 0)) + tuple(q._version for q in p.values())
         if versions == self.versions:
+            return self.struct
+        if self.versions is not None and self._replay is not None and versions[:2] == self.versions[:2]:
+            # same parameters at the same addresses, new values (an optimizer step): replay the recorded launches
+            ops.replay_packs(self._replay[0], self.flat)
+            _lib.check(_lib.load().rpg_sgemm_batch(C.byref(self._replay[1]), ops._stream(self.flat)), "rpg_sgemm_batch")
+            self.versions = versions
             return self.struct
         for q in p.values():
             if q.dtype != torch.float32 or not q.is_cuda or not q.is_contiguous():
@@ -108,7 +131,7 @@ class PackedLayerWeights:
         D, c, t = self.D, self.c, self.t
         W1e, W1m = p["edge_model.edge_mlp.0.weight"].data, p["mlp.0.weight"].data
         W2e, W2m = p["edge_model.edge_mlp.2.weight"].data, p["mlp.2.weight"].data
-        q = ops.PackQueue()                                    # every window below converts in ONE launch
+        q = ops.PackQueue(record=True)                         # every window below converts in ONE launch
         pk = q.add
         # mlp.0 columns: _upt = [x_j (src) | e'];  simpleConvEdge = [x_i (dst) | x_j (src) | e']  (my_gnn_layer.py:269,305)
         mj0, me0 = (D, 2 * D) if v1 else (0, D)
@@ -177,6 +200,7 @@ class PackedLayerWeights:
             s.b1u = p["mlp_updating.0.bias"].data_ptr()
             s.b2u = p["mlp_updating.2.bias"].data_ptr()
         self.versions = versions
+        self._replay = (q.recorded, sg)
         return s
 
 
@@ -207,7 +231,7 @@ class PackedLayerWeightsSplit:
 
     def refresh(self, mod, training=False):
         p = {n: mod.get_parameter(n) for n in PARAM_ORDER}
-        versions = (getattr(mod, "_pack_epoch", 0), bool(training)) + tuple((q.data_ptr(), q._version) for q in p.values())
+        versions = (getattr(mod, "_pack_epoch", 0), bool(training), getattr(mod, "_value_epoch", 0)) + tuple((q.data_ptr(), q._version) for q in p.values())
         if versions == self.versions:
             return self.struct
         D, c, cp, c3p, t = self.D, self.c, self.cp, self.c3p, self.t
@@ -387,6 +411,7 @@ class _LayerFnSplit(torch.autograd.Function):
     """simpleConvEdge_upt in fp32 mode (split-bf16 arithmetic) with its hand-written backward."""
 
     @staticmethod
+    @ops.scoped
     def forward(ctx, x, e, module, graph, *params):
         need_bwd = any(ctx.needs_input_grad)
         w = module._packed_split(x.device).refresh(module, training=need_bwd)
@@ -396,6 +421,7 @@ class _LayerFnSplit(torch.autograd.Function):
         return ops.from_split(*acts["out"]), ops.from_split(*acts["e_new"])
 
     @staticmethod
+    @ops.scoped
     def backward(ctx, d_out, d_e_new):
         dev = ctx.acts["x"][0].device
         grads = {n: torch.zeros(s, dtype=torch.float32, device=dev) for n, s in zip(PARAM_ORDER, ctx.param_shapes)}
@@ -507,6 +533,7 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
 
 class _LayerFn(torch.autograd.Function):
     @staticmethod
+    @ops.scoped
     def forward(ctx, x, e, module, graph, *params):
         weights = module._packed(x.device).refresh(module)
         acts = layer_forward_raw(weights, graph, ops.to_bf16(x), ops.to_bf16(e), for_backward=any(ctx.needs_input_grad))
@@ -521,6 +548,7 @@ class _LayerFn(torch.autograd.Function):
         return out, e_new
 
     @staticmethod
+    @ops.scoped
     def backward(ctx, d_out, d_e_new):
         dev = ctx.acts["x"].device
         order = ctx.module._param_order
@@ -576,11 +604,20 @@ class simpleConvEdge_upt(nn.Module):
         `load_state_dict` and every in-place op on a parameter automatically (version counters); writes that bypass
         the counter -- `p.data.copy_()`, `nn.init.*(p.data)`, a custom optimizer kernel -- need this call."""
         self._pack_epoch = self._pack_epoch + 1
+        self.__dict__.pop("_rpg_leaf_cache", None)
+
+    _value_epoch = 0
+
+    def mark_values_changed(self):
+        """The parameters kept their storage but were written behind autograd's version counters (FusedAdam's flat
+        update): the packed operands are re-converted at the next forward from the recorded descriptors."""
+        self._value_epoch = self._value_epoch + 1
 
     def __getstate__(self):
         # the packed operands and their ctypes structs are a cache: never pickled / deep-copied with the module
         state = dict(self.__dict__)
         state["_pack_cache"] = {}
+        state.pop("_rpg_leaf_cache", None)
         return state
 
     def _packed(self, device):
@@ -666,6 +703,7 @@ class _ConvFn(torch.autograd.Function):
     at node level (dm[e] = dan[dst(e)])."""
 
     @staticmethod
+    @ops.scoped
     def forward(ctx, x, module, graph, w1, b1, w2, b2):
         D = module.in_channels
         dev = x.device
@@ -686,6 +724,7 @@ class _ConvFn(torch.autograd.Function):
         return ops.to_f32(out) if x.dtype == torch.float32 else out
 
     @staticmethod
+    @ops.scoped
     def backward(ctx, d_out):
         module, graph = ctx.module, ctx.graph
         xb, h, hbits, pk = ctx.saved
@@ -748,6 +787,7 @@ class simpleConv(nn.Module):
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_pack_cache"] = {}
+        state.pop("_rpg_leaf_cache", None)
         return state
 
     def _packed_conv(self, device):

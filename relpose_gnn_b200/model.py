@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import graph as graph_mod, ops
-from .layers import (PARAM_ORDER, _invalidate_hook, layer_backward_raw, layer_backward_split_raw, layer_forward_raw,
+from .layers import (PARAM_ORDER, _invalidate_hook, fast_params, layer_backward_raw, layer_backward_split_raw, layer_forward_raw,
                      layer_forward_split_raw, simpleConvEdge_upt)
 from .ops import BF16
 
@@ -26,11 +26,20 @@ def _lib_ws_floats(D):
     return _lib.load().rpg_layer_bwd_ws_floats(D, 0, 0)
 
 
+def _arena_edge_rows(graph):
+    """Edge rows the per-step arenas are sized for: the full template of the batch shape when the batch is an
+    edge-dropped version of it (at most 4x the present edges), else the present edge count (kNN graphs: constant)."""
+    Et = graph.n_edge_rows
+    full = graph.G * graph.N * (graph.N - 1)
+    return full if Et <= full <= 4 * Et else Et
+
+
 class _StackFn(torch.autograd.Function):
     """proj_edge init -> R x (gnn1, ReLU, ReLU) -> feature dropout -> 4 pose heads, with a hand-written backward.
     ReLUs are folded into GEMM epilogues (forward: second store; backward: mask on the input that was a ReLU)."""
 
     @staticmethod
+    @ops.scoped
     def forward(ctx, x, model, graph, drop, *params):
         D, R = model.node_dim, model.gnn_recursion
         dev = x.device
@@ -38,8 +47,11 @@ class _StackFn(torch.autograd.Function):
         xb = ops.to_bf16(x)
         lw = model.gnn1._packed(dev).refresh(model.gnn1)
         sw = model._packed_stack(dev)
-        # one allocation for every activation of the forward (sizes change with the edge-dropout mask)
-        arena = ops.Arena(dev, R * ops.layer_fwd_bytes(D, Nt, Et) + Nt * 2 * D * 2 + Et * (D * 2 + D // 8) + 4096)
+        # one allocation for every activation of the forward.  Sized for the FULL template of this batch shape: the edge
+        # count changes with every edge-dropout mask, and a request of a new size each step sends the caching allocator
+        # down its slow path (split / merge, ~30 us); the same size every step is a free-list hit.
+        Ec = _arena_edge_rows(graph)
+        arena = ops.Arena(dev, R * ops.layer_fwd_bytes(D, Nt, Ec) + Nt * 2 * D * 2 + Ec * (D * 2 + D // 8) + 4096)
         # edge-feature initialiser (posenet.py:1014-1017,1053-1055), factorised per node
         pmm = arena.take(Nt, 2 * D)
         ops.gemm_nt(xb, sw["Wmm"], out=pmm)
@@ -79,6 +91,7 @@ class _StackFn(torch.autograd.Function):
         return pose_n, pose_e
 
     @staticmethod
+    @ops.scoped
     def backward(ctx, d_pose_n, d_pose_e):
         model, graph = ctx.model, ctx.graph
         xb, pmm, acts, x_last, e_last, lw, sw = ctx.saved
@@ -98,7 +111,8 @@ class _StackFn(torch.autograd.Function):
                 off += p.numel()
         lgrads = {n: grads["gnn1." + n] for n in PARAM_ORDER}
         Nt, Et = graph.n_node_rows, graph.n_edge_rows
-        arena = ops.Arena(dev, R * ops.layer_bwd_bytes(D, Nt, Et) + 4 * _lib_ws_floats(D) + Nt * 3 * D * 2 + 4096)
+        Ec = _arena_edge_rows(graph)                               # full-template size: see the forward
+        arena = ops.Arena(dev, R * ops.layer_bwd_bytes(D, Nt, Ec) + 4 * _lib_ws_floats(D) + Nt * 3 * D * 2 + 4096)
         ws = arena.take(1, _lib_ws_floats(D), torch.float32)
 
         # heads (posenet.py:1077-1086): gradient w.r.t. the pre-ReLU layer outputs (mask_relu)
@@ -156,6 +170,7 @@ class _StackFnSplit(torch.autograd.Function):
     gradients hi^T hi + lo^T hi + hi^T lo.  Feature dropout + heads run in the stand-alone head kernels (fp32 weights)."""
 
     @staticmethod
+    @ops.scoped
     def forward(ctx, x, model, graph, drop, *params):
         D, R = model.node_dim, model.gnn_recursion
         dev = x.device
@@ -188,6 +203,7 @@ class _StackFnSplit(torch.autograd.Function):
         return pose_n, pose_e
 
     @staticmethod
+    @ops.scoped
     def backward(ctx, d_pose_n, d_pose_e):
         model, graph = ctx.model, ctx.graph
         xs, acts, x_last, e_last, lw, sw = ctx.saved
@@ -292,7 +308,10 @@ class RelPoseGNN(nn.Module):
                 [f"{h}.{s}" for h in _HEADS for s in ("weight", "bias")])
 
     def _ordered_params(self):
-        return [self.get_parameter(n) for n in self._param_names()]
+        names = self.__dict__.get("_rpg_names")
+        if names is None:
+            names = self.__dict__["_rpg_names"] = tuple(self._param_names())
+        return list(fast_params(self, names).values())
 
     _pack_epoch = 0
 
@@ -300,21 +319,35 @@ class RelPoseGNN(nn.Module):
         """Forces every packed operand of the stack (and of gnn1..gnnL) to be rebuilt at the next forward; see
         simpleConvEdge_upt.invalidate_packed."""
         self._pack_epoch = self._pack_epoch + 1
+        self.__dict__.pop("_rpg_leaf_cache", None)
         for layer in range(self.n_layers):
             getattr(self, f"gnn{layer + 1}").invalidate_packed()
+
+    _value_epoch = 0
+
+    def mark_values_changed(self):
+        """See simpleConvEdge_upt.mark_values_changed (FusedAdam calls it after every step)."""
+        self._value_epoch = self._value_epoch + 1
+        for layer in range(self.n_layers):
+            getattr(self, f"gnn{layer + 1}").mark_values_changed()
 
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_stack_cache"] = {}                   # packed operands are a cache: not pickled / deep-copied
+        state.pop("_rpg_leaf_cache", None)
         return state
 
     def _packed_stack(self, device):
         """bf16 proj_edge operands and the [6, D] fp32 head matrices; refreshed (ONE launch) when parameters change."""
         D = self.node_dim
         ps = [self.proj_edge.weight] + [getattr(self, h).weight for h in _HEADS] + [getattr(self, h).bias for h in _HEADS]
-        versions = (self._pack_epoch,) + tuple((p.data_ptr(), p._version) for p in ps)
+        versions = (self._pack_epoch, tuple(p.data_ptr() for p in ps), self._value_epoch) + tuple(p._version for p in ps)
         ent = self._stack_cache.get(str(device))
         if ent is not None and ent["versions"] == versions:
+            return ent
+        if ent is not None and ent.get("replay") is not None and ent["versions"][:2] == versions[:2]:
+            ops.replay_packs(ent["replay"], ent["Wmm"])      # same addresses, new values: the recorded windows again
+            ent["versions"] = versions
             return ent
         if ent is None:
             f32 = torch.float32
@@ -329,7 +362,7 @@ class RelPoseGNN(nn.Module):
                 ent["b6%s_p" % tag] = torch.zeros(8, dtype=f32, device=device)
                 ent["w6%sT" % tag] = torch.zeros(D, 64, dtype=BF16, device=device)
             self._stack_cache[str(device)] = ent
-        q = ops.PackQueue()
+        q = ops.PackQueue(record=True)
         W = self.proj_edge.weight.data                                     # [D, 2D]: columns (min node | max node)
         q.add(W, ent["Wmm"][:D], c0=0, cols=D)
         q.add(W, ent["Wmm"][D:], c0=D, cols=D)
@@ -346,6 +379,7 @@ class RelPoseGNN(nn.Module):
                 q.add(w, ent["w6%sT" % tag][:, 8 + r0:8 + r0 + 3], transpose=True)
         q.flush()
         ent["versions"] = versions
+        ent["replay"] = q.recorded
         return ent
 
     def _drop_args(self, keep_x, keep_e):
@@ -382,6 +416,10 @@ class RelPoseGNN(nn.Module):
             raise ValueError("RelPoseGNN needs CUDA tensors: the sm_100a kernels are the only implementation")
         if x.dim() != 2 or x.size(1) != self.node_dim:
             raise ValueError(f"x must be [rows, {self.node_dim}]")
+        with ops.stream_scope(x.device):
+            return self._forward_scoped(x, edge_index, keep_x, keep_e, k)
+
+    def _forward_scoped(self, x, edge_index, keep_x, keep_e, k):
         graph = graph_mod.from_edge_index(edge_index, x.size(0))
         kk = self.knn if self.knn > 0 else k
         if kk is not None and kk > 0:
@@ -445,6 +483,7 @@ class PoseNetCriterion(nn.Module):
 
 class _PoseLossFn(torch.autograd.Function):
     @staticmethod
+    @ops.scoped
     def forward(ctx, pred, poses, graph, sax, saq):
         if pred.dtype != torch.float32 or pred.stride(1) != 1:      # row-pitched fp32 views (tensor-core heads) pass through
             pred = pred.float().contiguous()
@@ -455,6 +494,7 @@ class _PoseLossFn(torch.autograd.Function):
         return out7[2:3], out7[3], out7[4]
 
     @staticmethod
+    @ops.scoped
     def backward(ctx, g_loss, g_t, g_q):
         dpred, out7 = ctx.saved_tensors
         if g_loss is None:                       # only the logged t_loss / q_loss were used

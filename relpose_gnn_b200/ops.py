@@ -10,6 +10,10 @@ from ._lib import Gemm, check, ptr
 BF16 = torch.bfloat16
 
 
+_ELEMENT_SIZE = {BF16: 2, torch.float16: 2, torch.float32: 4, torch.float64: 8, torch.uint8: 1, torch.int8: 1,
+                 torch.int32: 4, torch.int64: 8}
+
+
 class Arena:
     """One caching-allocator block per forward (or backward) carved into 256-byte-aligned views.  A training step
     otherwise makes ~60 allocations whose sizes change with the edge-dropout mask; with the host running ahead of
@@ -21,7 +25,7 @@ class Arena:
         self.off = 0
 
     def take(self, rows, cols, dtype=BF16, zero=False):
-        n = rows * cols * torch.empty((), dtype=dtype).element_size()
+        n = rows * cols * _ELEMENT_SIZE[dtype]
         if self.off + n > self.buf.numel():                       # estimate too small: fall back to the allocator
             t = torch.empty(rows, cols, dtype=dtype, device=self.device)
         else:
@@ -44,7 +48,52 @@ def layer_bwd_bytes(D, Nt, Et):
             4 * lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, pad64(3 * c))) + 64 * 256)
 
 
+_scoped_stream = None       # (device index, c_void_p) while a stream_scope is open
+
+
+class stream_scope:
+    """Pins the stream handle the wrappers pass to the library for the duration of one top-level call (a stack forward,
+    its backward, an optimizer step): `torch.cuda.current_stream()` costs ~5 us and a training step asks ~80 times.  The
+    scope is opened by the entry points only, so a caller switching streams between calls is still honoured."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        global _scoped_stream
+        self.prev = _scoped_stream
+        _scoped_stream = (self.device.index, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        return self
+
+    def __exit__(self, *exc):
+        global _scoped_stream
+        _scoped_stream = self.prev
+        return False
+
+
+def scoped(fn):
+    """Decorator for autograd.Function forward / backward: one stream_scope per call (device of the first CUDA tensor
+    argument, remembered on ctx for the backward, whose gradient arguments may be None)."""
+    def wrapper(ctx, *args):
+        dev = getattr(ctx, "rpg_device", None)
+        if dev is None:
+            for t in args:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    dev = t.device
+                    break
+            ctx.rpg_device = dev
+        if dev is None:
+            return fn(ctx, *args)
+        with stream_scope(dev):
+            return fn(ctx, *args)
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
 def _stream(t):
+    sc = _scoped_stream
+    if sc is not None and t.device.index == sc[0]:
+        return sc[1]
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
@@ -165,11 +214,14 @@ class PackQueue:
     re-packs ~35 operand windows of the layer after every optimizer step.  dst dtype bf16 (operands) or fp32 (plain
     strided copies: head matrices, concatenated biases); lo=True writes the low bf16 plane of the fp32 mode."""
 
-    def __init__(self):
+    def __init__(self, record=False):
         self.batch = _lib.PackBatch()
         self.batch.n = 0
         self.stream = None
         self.keep = []
+        # record=True keeps every flushed batch: the windows of a re-pack are the same every optimizer step as long as
+        # the parameters stay where they are, so the caller replays the recorded descriptors instead of rebuilding them
+        self.recorded = [] if record else None
 
     def add(self, src, dst, r0=0, c0=0, rows=None, cols=None, transpose=False, lo=False):
         _require_cuda(src, dst)
@@ -202,8 +254,18 @@ class PackQueue:
     def flush(self):
         if self.batch.n:
             check(_lib.load().rpg_pack_weights_batch(C.byref(self.batch), self.stream), "rpg_pack_weights_batch")
+            if self.recorded is not None:
+                self.recorded.append(self.batch)
+                self.batch = _lib.PackBatch()
             self.batch.n = 0
             self.keep = []
+
+
+def replay_packs(batches, like):
+    """Re-runs recorded rpg_pack_weights_batch descriptors on the current stream of `like`'s device."""
+    lib, st = _lib.load(), _stream(like)
+    for b in batches:
+        check(lib.rpg_pack_weights_batch(C.byref(b), st), "rpg_pack_weights_batch")
 
 
 def to_bf16(t):

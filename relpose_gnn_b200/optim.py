@@ -59,8 +59,11 @@ class FusedAdam:
         _lib.check(lib.rpg_adam_step(self.flat.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
                                      self.exp_avg_sq.data_ptr(), self.numel, self.lr, self.betas[0], self.betas[1], self.eps,
                                      self.weight_decay, float(grad_scale), self.t, stream), "rpg_adam_step")
-        for m in self.modules:
-            m.invalidate_packed()
+        for m in self.modules:                           # same storage, new values: the recorded re-pack is replayed
+            if hasattr(m, "mark_values_changed"):
+                m.mark_values_changed()
+            else:
+                m.invalidate_packed()
 
     def state_dict(self):
         return {"t": self.t, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "lr": self.lr,

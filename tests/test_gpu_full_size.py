@@ -256,3 +256,34 @@ def test_zero_grad_set_to_none_does_not_detach_the_bucket():
     g1 = grads()                                        # autograd allocates fresh tensors; allreduce() copies them back
     assert torch.equal(g0, g1)
     assert all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+
+
+def test_replayed_repack_equals_a_full_rebuild_after_optimizer_steps():
+    """The bf16 operand copies are re-converted after every optimizer step from RECORDED descriptors (same parameter
+    storage, new values).  After FusedAdam steps and after an in-place torch update the forward must equal, bit for bit,
+    the forward of the same model with every packed operand rebuilt from scratch (`invalidate_packed`)."""
+    torch.manual_seed(3)
+    D, N, Gn = 128, 9, 33
+    model = rpg.RelPoseGNN(D, D, D, droprate=0.0).to(dev())
+    crit = rpg.PoseNetCriterion(0.0, -2.0).to(dev())
+    params = list(model.parameters()) + list(crit.parameters())
+    opt = rpg.FusedAdam(params, lr=1e-2, modules=[model])
+    src, dst = rpg.fc_template(N)
+    ei = rpg.batched_edge_index(src, dst, Gn, N).to(dev())
+    x = torch.randn(Gn * N, D, device=dev()).bfloat16()
+    poses = 0.1 * torch.randn(Gn * N, 6, device=dev())
+    for it in range(3):
+        opt.zero_grad()
+        pn, pe, eu = model(x, ei)
+        loss, _, _ = crit(pe, poses, eu)
+        loss.backward()
+        opt.step()
+        if it == 1:
+            with torch.no_grad():
+                model.gnn1.mlp[0].weight.mul_(1.01)           # version counter path (what torch optimizers do)
+        with torch.no_grad():
+            a_n, a_e, _ = model(x, ei)                          # replayed descriptors
+            model.invalidate_packed()
+            b_n, b_e, _ = model(x, ei)                          # rebuilt from scratch
+        assert torch.equal(a_n, b_n) and torch.equal(a_e, b_e), it
+    assert not torch.equal(a_e, torch.zeros_like(a_e))
