@@ -575,6 +575,12 @@ typedef struct {
   float* g_att_theta_w; float* g_att_theta_b;
   float* g_att_phi_w; float* g_att_phi_b;
   float* g_att_W_w; float* g_att_W_b;     /* [D, c], [D]    att.W            */
+  /* 0: dxu and dan are separate [Nt, D] tensors and dan = da / deg (mean backward applied by the producing GEMM).
+   * 2D (simpleConvEdge_upt only): dxu and dan are the column halves of ONE [Nt, 2D] tensor (dan == dxu + D, row pitch
+   * 2D) written by a single GEMM [dx_u | da] = dh3 W1u; dan then holds da UNSCALED and the 1/deg is applied where da
+   * is consumed (row scale of the dyn and Q GEMMs; the weight gradients contract da with the forward's means ybar,
+   * mbar instead of the in-edge sums; the bias sums skip nodes without in-edges).  h2sum / ysum are not used. */
+  int dxa_ld;
 } rpg_layer_grads_t;
 
 /* ------------------------------------------------------------------------------------------

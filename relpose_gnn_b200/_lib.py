@@ -95,7 +95,7 @@ class LayerGrads(C.Structure):
         "g_mlp0_w", "g_mlp0_b", "g_mlp2_w", "g_mlp2_b", "g_upd0_w", "g_upd0_b", "g_upd2_w", "g_upd2_b",
         "g_edge0_w", "g_edge0_b", "g_edge2_w", "g_edge2_b",
         "g_att_g_w", "g_att_g_b", "g_att_theta_w", "g_att_theta_b", "g_att_phi_w", "g_att_phi_b",
-        "g_att_W_w", "g_att_W_b")]
+        "g_att_W_w", "g_att_W_b")] + [("dxa_ld", I)]
 
 
 class PackDesc(C.Structure):

@@ -729,23 +729,36 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         RPG_TRY(rpg_scale_rows(b->d_out, D, Nt, D, gr->inv_deg, gr->N, b->dan, D, stream));
     }
     // ---- update MLP backward (only when a gradient reaches `out`)
+    // merged update-MLP dgrad (rpg_layer_grads_t.dxa_ld): da stays unscaled, its consumers apply 1 / deg
+    const bool merged = have_out && !v1 && b->dxa_ld != 0;
+    if (merged && (b->dxa_ld != 2 * D || b->dan != b->dxu + D || !gr->has_in))
+        return set_error(RPG_E_ARG, "layer_bwd: dxa_ld must be 2D with dan == dxu + D (and the graph needs has_in)");
+    const int ld_dan = merged ? 2 * D : D;
     if (have_out && !v1) {
         // dh3 = (d_out W2u) * [h3 > 0]
         g = nt((int)Nt, D, b->d_out, D, D, w->W2uT, D);
         if (t->h3_bits) { g.mask_bits = t->h3_bits; g.mask_bits_ld = D / 8; } else { g.mask = t->h3; g.mask_ld = D; }
         g.out = b->dh3; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
-        // [dx_u | da] = dh3 W1u ; da is scaled by 1/deg (mean backward) -> dan
-        g = nt((int)Nt, D, b->dh3, D, D, w->W1uT, D);
-        g.out = b->dxu; g.ldo = D;
-        RPG_TRY(gemm_launch(&g, s));
-        g = nt((int)Nt, D, b->dh3, D, D, w->W1uT + (size_t)D * D, D);
-        g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; g.out = b->dan; g.ldo = D;
-        RPG_TRY(gemm_launch(&g, s));
+        if (merged) {
+            // [dx_u | da] = dh3 W1u in one launch (N = 2D)
+            g = nt((int)Nt, 2 * D, b->dh3, D, D, w->W1uT, D);
+            g.out = b->dxu; g.ldo = 2 * D;
+            RPG_TRY(gemm_launch(&g, s));
+        } else {
+            // [dx_u | da] = dh3 W1u ; da is scaled by 1/deg (mean backward) -> dan
+            g = nt((int)Nt, D, b->dh3, D, D, w->W1uT, D);
+            g.out = b->dxu; g.ldo = D;
+            RPG_TRY(gemm_launch(&g, s));
+            g = nt((int)Nt, D, b->dh3, D, D, w->W1uT + (size_t)D * D, D);
+            g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; g.out = b->dan; g.ldo = D;
+            RPG_TRY(gemm_launch(&g, s));
+        }
     }
     if (have_out) {
         // dy per destination node: dyn = dan WW   fp32 [Nt, c]
-        g = nt((int)Nt, c, b->dan, D, D, w->WWT, D);
+        g = nt((int)Nt, c, b->dan, D, ld_dan, w->WWT, D);
+        if (merged) { g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; }
         g.out_f32 = b->dyn; g.ldo_f32 = c;
         RPG_TRY(gemm_launch(&g, s));
         // attention backward -> dgtp [Et, 3c]
@@ -756,7 +769,8 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         // dh2 = (dm W2m) * [h2 > 0] with dm = dgtp Wgtp + dan[dst] (never materialised):
         //     dh2 = (dgtp (Wgtp W2m) + Q[dst]) * [h2 > 0],  Q = dan W2m at node level
         if (!b->Q || !w->WgcT) return set_error(RPG_E_ARG, "layer_bwd: Q / WgcT missing");
-        g = nt((int)Nt, D, b->dan, D, D, w->W2mT, D);
+        g = nt((int)Nt, D, b->dan, D, ld_dan, w->W2mT, D);
+        if (merged) { g.row_scale = gr->inv_deg; g.row_scale_mod = gr->N; }
         g.out = b->Q; g.ldo = D;
         RPG_TRY(gemm_launch(&g, s));
         g = nt((int)Et, D, b->dgtp, c3p, c3p, w->WgcT, c3p);
@@ -799,7 +813,7 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 1, b->dP + 2 * D, ldP, stream));
         if (v1) RPG_TRY(rpg_edge_to_node_sum(b->dh2, D, gr, D, 0, b->dP + 3 * D, ldP, stream));
         g = nt((int)Nt, D, b->dP, ldP, ldP, w->WnT, ldP);
-        if (!v1) { g.resid = b->dxu; g.resid_ld = D; }
+        if (!v1) { g.resid = b->dxu; g.resid_ld = merged ? 2 * D : D; }
     } else {
         g = nt((int)Nt, D, b->dP, 2 * D, ldP, w->WnT, ldP);
     }
@@ -838,15 +852,24 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
         //   d att.{g,theta,phi}.weight = T W2m^T + csg b2m^T ;  bias = csg
         //   d mlp.2.weight = Wgtp^T T + dan^T h2sum ;  bias = Wgtp^T csg + sum_n deg(n) dan[n]
         // with h2sum[n] = sum over in-edges of h2 = deg(n) * mean(h2)[n] (the forward's node-level mean).
-        if (!b->T_tmp || !b->h2sum || !w->Wgtp_f32 || !w->W2m_f32) return set_error(RPG_E_ARG, "layer_bwd: T_tmp / h2sum / master weights missing");
+        if (!b->T_tmp || (!merged && !b->h2sum) || !w->Wgtp_f32 || !w->W2m_f32) return set_error(RPG_E_ARG, "layer_bwd: T_tmp / h2sum / master weights missing");
         RPG_TRY(q.partials(b->dgtp, c3p, c3, t->h2, D, D, Et, true, &part, &splits));
         // node-level parts: dan^T h2sum -> mlp.2.weight, dan^T ysum -> att.W.weight, sum_n deg(n) dan[n] -> both biases
-        RPG_TRY(rpg_scale_rows(t->mbar, D, Nt, D, gr->deg, gr->N, b->h2sum, D, stream));
-        RPG_TRY(q.wgrad(b->dan, D, D, b->h2sum, D, D, Nt, b->g_mlp2_w, D));
-        RPG_TRY(rpg_scale_rows(t->ybar, cp, Nt, cp, gr->deg, gr->N, b->ysum, cp, stream));
-        RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
-        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
-        RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
+        if (merged) {
+            // (da / deg)^T (deg * mean) = da^T mean: the forward's means as they are (0 for nodes without in-edges),
+            // and sum_n deg(n) dan[n] = sum over the nodes WITH in-edges of da[n]
+            RPG_TRY(q.wgrad(b->dan, ld_dan, D, t->mbar, D, D, Nt, b->g_mlp2_w, D));
+            RPG_TRY(q.wgrad(b->dan, ld_dan, D, t->ybar, cp, c, Nt, b->g_att_W_w, c));
+            RPG_TRY(rpg_colsum_bf16(b->dan, ld_dan, Nt, D, gr->has_in, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
+            RPG_TRY(rpg_colsum_bf16(b->dan, ld_dan, Nt, D, gr->has_in, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
+        } else {
+            RPG_TRY(rpg_scale_rows(t->mbar, D, Nt, D, gr->deg, gr->N, b->h2sum, D, stream));
+            RPG_TRY(q.wgrad(b->dan, D, D, b->h2sum, D, D, Nt, b->g_mlp2_w, D));
+            RPG_TRY(rpg_scale_rows(t->ybar, cp, Nt, cp, gr->deg, gr->N, b->ysum, cp, stream));
+            RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
+            RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
+            RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
+        }
         if (!v1) {
             // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]
             RPG_TRY(q.wgrad(b->d_out, D, D, t->h3, D, D, Nt, b->g_upd2_w, D, b->g_upd2_b));

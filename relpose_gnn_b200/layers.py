@@ -6,6 +6,7 @@ module can be assigned to `PoseNetX_R2.gnn1` in place of the torch_geometric lay
 in hand-written sm_100a kernels behind the C ABI of include/rpg.h; there is no PyG / PyTorch fallback.
 """
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -511,15 +512,22 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
     keep = {"dx": new(Nt, D), "de": new(Et, D), "dh1": new(Et, D), "dP": new(Nt, (4 if v1 else 3) * D),
             "split_ws": new(1, lib.rpg_layer_bwd_ws_floats(D, 0, 0), f32),
             "colsum_ws": new(1, lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), f32)}
+    merged = have_out and not v1 and os.environ.get("RPG_MERGED_UPDATE_DGRAD", "1") != "0"
     if have_out:
-        if not v1:
-            keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D)})
-        keep.update({"dan": new(Nt, D), "dyn": new(Nt, c, f32),
-                     "dgtp": new(Et, c3p, zero=(c3p != 3 * c)),
-                     "dh2": new(Et, D), "de_tot": new(Et, D), "Q": new(Nt, D), "h2sum": new(Nt, D),
-                     "ysum": new(Nt, cp), "gtp_bias_tmp": new(1, c3p, f32), "T_tmp": new(3 * c, D, f32)})
+        if merged:
+            # [dx_u | da] as the column halves of one buffer: a single GEMM writes both (rpg_layer_grads_t.dxa_ld)
+            dxa = new(Nt, 2 * D)
+            keep.update({"dh3": new(Nt, D), "dxu": dxa[:, :D], "dan": dxa[:, D:]})
+        else:
+            if not v1:
+                keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D)})
+            keep.update({"dan": new(Nt, D), "h2sum": new(Nt, D), "ysum": new(Nt, cp)})
+        keep.update({"dyn": new(Nt, c, f32), "dgtp": new(Et, c3p, zero=(c3p != 3 * c)),
+                     "dh2": new(Et, D), "de_tot": new(Et, D), "Q": new(Nt, D),
+                     "gtp_bias_tmp": new(1, c3p, f32), "T_tmp": new(3 * c, D, f32)})
     for k, v in keep.items():
         setattr(b, k, v.data_ptr())
+    b.dxa_ld = 2 * D if merged else 0
     b.d_out = ops.ptr(d_out)
     b.d_e_new = ops.ptr(d_e_new)
     b.mask_dx, b.mask_de = int(mask_dx), int(mask_de)

@@ -14,3 +14,6 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 2 -o 
 # (4) the bandwidth kernels of one step (full set)
 ncu --set full --clock-control none -k regex:"segment_sum|attention_series|edge_init|adam|pack_weights" -c 14 -o gpurun_out/${tag}_aux \
     python bench.py --steps 1 --warmup 1 --trials 1 --no-cpu-baseline --no-ref-eager > /dev/null 2>&1
+# (5) the grouped weight-gradient launch of a layer backward (full set)
+ncu --set full --clock-control none --import-source on -k regex:tn_pair -c 2 -o gpurun_out/${tag}_tn_group \
+    python bench.py --steps 1 --warmup 1 --trials 1 --no-cpu-baseline --no-ref-eager > /dev/null 2>&1
