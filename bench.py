@@ -47,12 +47,17 @@ def algorithmic_flops_per_graph(D, N, E, R=R_ROUNDS, train=True):
 
 
 def load_traffic():
-    """DRAM bytes per gemm_tc_kernel launch from the committed ncu launch list (profiles/, tools/summarize_launches.py)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
+    """DRAM bytes per tcgen05 GEMM launch (and the tensor-pipe counters) from the committed ncu launch list of the
+    training step (profiles/r2_launches_train_4096x9.csv -> tools/summarize_launches.py -> profiles/r2_gemm_traffic.json)."""
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            d["file"] = "profiles/" + name
+            return d
+        except Exception:
+            continue
+    return None
 
 
 def load_peaks():
@@ -388,6 +393,7 @@ def run_ours(args):
     mean_Ep = float(N * knn) if knn > 0 else float(np.mean([2 * m.sum() for m in masks[:args.steps]]))
 
     if rank == 0:
+        traffic = load_traffic() or {}
         value = world * G / (ms_step * 1e-3)
         e2e_value = world * G / (ms_e2e * 1e-3)
         ei_bytes = ei_host.numel() * 8
@@ -417,8 +423,10 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<NT|TN> (tcgen05)",
                          "achieved": alg_flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": alg_flops / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
-                         "traffic": (load_traffic() or {}).get("dram_bytes_per_launch") if args.workload == "train_4096x9" else None,
-                         "traffic_source": "profiles/r1_gemm_traffic.json (ncu dram__bytes_read+write per launch, train_4096x9)",
+                         "traffic": traffic.get("dram_bytes_per_launch") if args.workload == "train_4096x9" else None,
+                         "traffic_source": f"{traffic.get('file')} (ncu dram__bytes_read+write over the GEMM launches of one train_4096x9 step / launches)",
+                         "ncu_tensor_pipe_active_pct_gemm_time": traffic.get("tensor_pipe_active_pct_gemm_time") if args.workload == "train_4096x9" else None,
+                         "ncu_hw_counted_tflops_gemm_time": traffic.get("hw_counted_tflops_gemm_time") if args.workload == "train_4096x9" else None,
                          "peak_source": peaks["source"] + ", sustained bf16",
                          "algorithmic_flops_per_launch": alg_flops / max(len(gemms), 1),
                          "avg_launch_ms": gemm_ms / max(len(gemms), 1),

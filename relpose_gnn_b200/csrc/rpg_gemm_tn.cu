@@ -303,12 +303,12 @@ EncodeTiledFn encode_fn() {
 }
 
 int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box) {
+           const cuuint32_t* box, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(RPG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(tm, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char msg[128];
         snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) for a grouped weight-gradient operand", (int)r);

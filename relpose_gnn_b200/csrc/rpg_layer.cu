@@ -106,6 +106,17 @@ static int sm_count_cached() {
 
 // Weight gradients of one layer backward: every TN launch writes its split partials into its own slice of the workspace
 // and queues the fold; all folds run as ONE launch at the end (fixed order per element => deterministic).
+// RPG_TN_GROUP_MAX=k caps the problems per grouped launch (A/B comparisons; default: TN_GROUP_MAX)
+static int tn_group_limit() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("RPG_TN_GROUP_MAX");
+        v = e ? atoi(e) : TN_GROUP_MAX;
+        if (v < 1 || v > TN_GROUP_MAX) v = TN_GROUP_MAX;
+    }
+    return v;
+}
+
 struct WgradQueue {
     float* ws;
     size_t off;
@@ -130,7 +141,7 @@ struct WgradQueue {
         float* p = ws + off;
         *part = p;
         if (tn_group_supported(A, lda, M, B, ldb, N, R)) {
-            if (npend == TN_GROUP_MAX) {
+            if (npend >= tn_group_limit()) {
                 int rc = launch();
                 if (rc) return rc;
             }
@@ -210,13 +221,17 @@ int rpg_profile_end(double* nt_ms, double* tn_ms, int* nt_launches, int* tn_laun
 int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R, float* ws, float* out, int ldo,
               rpg_stream_t stream) {
     if (!A || !B || !ws || !out) return set_error(RPG_E_ARG, "wgrad: null pointer");
-    return wgrad(A, lda, M, B, ldb, N, R, ws, out, ldo, sm_count_cached(), as_stream(stream));
+    WgradQueue q(ws, sm_count_cached(), as_stream(stream));          // a group of one: the CTA-pair kernel when the shape qualifies
+    int rc = q.wgrad(A, lda, M, B, ldb, N, R, out, ldo);
+    return rc ? rc : q.flush();
 }
 
 int rpg_wgrad_bias(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R, float* ws, float* out,
                    int ldo, float* bias, rpg_stream_t stream) {
     if (!A || !B || !ws || !out) return set_error(RPG_E_ARG, "wgrad_bias: null pointer");
-    return wgrad(A, lda, M, B, ldb, N, R, ws, out, ldo, sm_count_cached(), as_stream(stream), bias);
+    WgradQueue q(ws, sm_count_cached(), as_stream(stream));
+    int rc = q.wgrad(A, lda, M, B, ldb, N, R, out, ldo, bias);
+    return rc ? rc : q.flush();
 }
 
 void rpg_struct_sizes(int32_t* out) {

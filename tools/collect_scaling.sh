@@ -6,6 +6,8 @@ run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-
 for w in train_4096x9 train_2048x17 train_2048x17_strong infer_8192x9 infer_65536x9_strong; do
   run --workload $w --trials 3 --no-ref-eager > gpurun_out/${tag}_n${N}_${w}.json 2> gpurun_out/${tag}_n${N}_${w}.err || echo "FAILED $w"
 done
+if [ "${NOOVERLAP:-0}" = "1" ]; then
 for w in train_4096x9 train_2048x17_strong; do
   run --workload $w --trials 3 --no-ref-eager --no-overlap-allreduce > gpurun_out/${tag}_n${N}_${w}_nooverlap.json 2> gpurun_out/${tag}_n${N}_${w}_nooverlap.err || echo "FAILED no-overlap $w"
 done
+fi

@@ -53,12 +53,12 @@ if have_tc:
 for k, (c, ns, by, tc, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     extra = f" {tc / ns:13.1f} {fl / ns / 1e3:8.0f}" if have_tc else ""
     out.append(f"{ns / 1e6:8.3f} {100 * ns / tot:5.1f}% {c:4d} {by / 1e6:9.1f}{extra}  {k}")
-gem = [v for k, v in agg.items() if k.startswith("gemm_tc_kernel")]
+gem = [v for k, v in agg.items() if k.startswith("gemm_tc_kernel") or k.startswith("tn_pair_group_kernel")]
 if gem:
     n = sum(v[0] for v in gem)
-    out.append(f"# gemm_tc_kernel: {n} launches, share {100 * sum(v[1] for v in gem) / tot:.1f}%, "
+    out.append(f"# tcgen05 GEMM kernels (gemm_tc_kernel<...> + tn_pair_group_kernel): {n} launches, share {100 * sum(v[1] for v in gem) / tot:.1f}%, "
                f"DRAM traffic per launch {sum(v[2] for v in gem) / n / 1e6:.1f} MB")
-    summary = {"kernel": "gemm_tc_kernel", "launches_per_step": n, "share_of_step": sum(v[1] for v in gem) / tot,
+    summary = {"kernel": "gemm_tc_kernel + tn_pair_group_kernel", "launches_per_step": n, "share_of_step": sum(v[1] for v in gem) / tot,
                "dram_bytes_per_launch": sum(v[2] for v in gem) / n}
     if have_tc:
         gns = sum(v[1] for v in gem)
