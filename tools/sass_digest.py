@@ -35,7 +35,7 @@ print("# " + " ".join(f"{w:>12}" for w in WATCH) + "  instr  kernel")
 for (name, c), nice in zip(per.items(), demangle):
     tot.update(c)
     if any(c[w] for w in WATCH if w not in ("SYNCS", "FFMA2", "LDGSTS", "MUFU.EX2")) or "attention" in nice or "gemm" in nice:
-        short = re.sub(r"\(.*", "", nice).replace("rpg::", "")
+        short = re.sub(r"\(.*", "", nice.replace("(anonymous namespace)::", "")).replace("rpg::", "")
         print("  " + " ".join(f"{c[w]:12d}" for w in WATCH) + f" {c['_total']:6d}  {short[:90]}")
 print("# total " + " ".join(f"{w}={tot[w]}" for w in WATCH))
 assert tot["HMMA"] == 0, "legacy mma.sync path found"
