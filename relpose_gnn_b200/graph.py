@@ -16,6 +16,11 @@ import torch
 from . import _lib
 
 
+def _stream_of(device):
+    from . import ops                      # ops does not import this module; resolved lazily to keep it that way
+    return ops.stream_of(device)
+
+
 def fc_template(n_nodes):
     """Closed form of the reference FC enumeration: forward half by offset d,
     then the same list with source and destination swapped.  Returns (src, dst) int32 arrays."""
@@ -308,7 +313,7 @@ def mask_edge_index(edge_index, keep_undirected, n_graphs):
     out = torch.empty(2, n_graphs * idx.size, dtype=torch.int64, device=ei.device)
     idx_dev = _uploader.upload(idx, ei.device)
     lib = _lib.load()
-    stream = C.c_void_p(torch.cuda.current_stream(ei.device).cuda_stream)
+    stream = _stream_of(ei.device)
     for r in range(2):
         _lib.check(lib.rpg_edge_mask_apply(ei[r].data_ptr(), n_graphs, Ep_full, int(idx.size), idx_dev.data_ptr(), 8,
                                            out[r].data_ptr(), stream), "rpg_edge_mask_apply")
@@ -414,42 +419,60 @@ def _device_graph(ei, G, N, Ep):
     Et = ei.size(1)
     words = lib.rpg_template_tables_words(N, Ep)
     al = lambda v: (v + 3) // 4 * 4                                       # noqa: E731
-    buf = torch.empty(words + 2 * al(Ep) + 4, dtype=torch.int32, device=dev)
-    tsrc, tdst = buf[words:words + Ep], buf[words + al(Ep):words + al(Ep) + Ep]
-    bad = buf[words + 2 * al(Ep):words + 2 * al(Ep) + 1]
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(lib.rpg_validate_edge_index(ei.data_ptr(), Et, G, N, Ep, tsrc.data_ptr(), tdst.data_ptr(), bad.data_ptr(),
+    g = int(np.gcd(128, Ep))
+    npat = Ep // g
+    panels = ((Ep - g + 127) // Ep) * N + N <= 64                         # same feasibility rule as GraphBatch._build_tables
+    sel_words = npat * 128 * 32 if panels else 0                          # one [npat*128, 64] bf16 selection matrix
+    # ONE allocation per batch: tables | template src | template dst | violation count | two selection matrices.
+    # Everything the kernels need is an address inside it (no per-table tensor views on the hot path).
+    o_src, o_dst = words, words + al(Ep)
+    o_bad = words + 2 * al(Ep)
+    o_sel = o_bad + 4
+    buf = torch.empty(o_sel + 2 * sel_words, dtype=torch.int32, device=dev)
+    base = buf.data_ptr()
+    bad = buf[o_bad:o_bad + 1]
+    stream = _stream_of(dev)
+    _lib.check(lib.rpg_validate_edge_index(ei.data_ptr(), Et, G, N, Ep, base + 4 * o_src, base + 4 * o_dst, bad.data_ptr(),
                                            stream), "rpg_validate_edge_index")
-    _lib.check(lib.rpg_template_tables(tsrc.data_ptr(), tdst.data_ptr(), N, Ep, buf.data_ptr(), stream), "rpg_template_tables")
+    _lib.check(lib.rpg_template_tables(base + 4 * o_src, base + 4 * o_dst, N, Ep, base, stream), "rpg_template_tables")
     self = GraphBatch.__new__(GraphBatch)
     self.G, self.N, self.Ep, self.device = G, N, Ep, dev
     self.src_np = self.dst_np = None
     self._edge_index = ei
-    tables, off = {"_buf": buf}, 0
-    for name, size, is_f in (("src", Ep, 0), ("dst", Ep, 0), ("in_ptr", N + 1, 0), ("in_idx", Ep, 0),
-                             ("out_ptr", N + 1, 0), ("out_idx", Ep, 0), ("min_ptr", N + 1, 0), ("min_idx", Ep, 0),
-                             ("max_ptr", N + 1, 0), ("max_idx", Ep, 0), ("inv_deg", N, 1), ("deg", N, 1), ("has_in", N, 1)):
-        t = buf[off:off + size]
-        tables[name] = t.view(torch.float32) if is_f else t
-        off += al(size)
     s = _lib.Graph()
     s.G, s.N, s.Ep = G, N, Ep
-    for name, t in tables.items():
-        if name != "_buf":
-            setattr(s, name, t.data_ptr())
-    g = int(np.gcd(128, Ep))
-    npat = Ep // g
-    if ((Ep - g + 127) // Ep) * N + N <= 64:                  # same feasibility rule as GraphBatch._build_tables
-        for name, tab in (("sel_src", "src"), ("sel_dst", "dst")):
-            sel = torch.empty(npat * 128, 64, dtype=torch.bfloat16, device=dev)
-            _lib.check(lib.rpg_selection_patterns(tables[tab].data_ptr(), Ep, N, g, npat, sel.data_ptr(), stream),
-                       "rpg_selection_patterns")
-            tables[name] = sel
-        s.sel_src, s.sel_dst = tables["sel_src"].data_ptr(), tables["sel_dst"].data_ptr()
+    offs, off = {}, 0
+    for name, size in (("src", Ep), ("dst", Ep), ("in_ptr", N + 1), ("in_idx", Ep), ("out_ptr", N + 1), ("out_idx", Ep),
+                       ("min_ptr", N + 1), ("min_idx", Ep), ("max_ptr", N + 1), ("max_idx", Ep), ("inv_deg", N), ("deg", N),
+                       ("has_in", N)):
+        setattr(s, name, base + 4 * off)
+        offs[name] = (off, size)
+        off += al(size)
+    if panels:
+        for i, (name, tab) in enumerate((("sel_src", "src"), ("sel_dst", "dst"))):
+            sel_ptr = base + 4 * (o_sel + i * sel_words)
+            _lib.check(lib.rpg_selection_patterns(base + 4 * offs[tab][0], Ep, N, g, npat, sel_ptr, stream), "rpg_selection_patterns")
+            setattr(s, name, sel_ptr)
+            offs[name] = (o_sel + i * sel_words, sel_words)
         s.sel_patterns, s.sel_div = npat, g
-    self._tables = tables
+    self._tables = _LazyTables(buf, offs)
     self.struct = s
     return self, bad
+
+
+class _LazyTables:
+    """Tensor views of the device-built template tables, made on demand (host_template, debugging): the hot path only
+    uses addresses inside the one buffer that holds them."""
+
+    def __init__(self, buf, offs):
+        self.buf, self.offs = buf, offs
+
+    def __getitem__(self, name):
+        off, size = self.offs[name]
+        t = self.buf[off:off + size]
+        if name.startswith("sel_"):
+            return t.view(torch.bfloat16).view(-1, 64)            # one-hot selection matrix [patterns * 128, 64]
+        return t.view(torch.float32) if name in ("inv_deg", "deg", "has_in") else t
 
 
 def _read_count_async(bad):

@@ -356,7 +356,7 @@ def layer_forward_split_raw(weights, graph, x, e, want_relu_copies=False, for_ba
             bits["e_bits"] = e_bits
         for k, v in bits.items():
             setattr(s, k, v.data_ptr())
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    stream = ops.stream_of(dev)
     _lib.check(_lib.load().rpg_layer_fwd_split(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd_split")
     a.update(bits)
     a["gtp"] = gtp
@@ -402,7 +402,7 @@ def layer_backward_split_raw(weights, graph, acts, d_out, d_e_new, grads, mask_d
     b.mask_dx, b.mask_de = int(mask_dx), int(mask_de)
     for name in PARAM_ORDER:
         setattr(b, _GRAD_FIELD_OF[name], grads[name].data_ptr())
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    stream = ops.stream_of(dev)
     _lib.check(lib.rpg_layer_bwd_split(C.byref(weights), graph.byref(), C.byref(acts["_struct"]), C.byref(b), stream),
                "rpg_layer_bwd_split")
     return keep["dx"], keep["de"]
@@ -445,46 +445,52 @@ def layer_forward_raw(weights, graph, x, e, want_relu_copies=False, x_bits=None,
     cp = pad64(c)
 
     arena = arena if arena is not None else ops.Arena(dev, ops.layer_fwd_bytes(D, Nt, Et))
-    new = arena.take
+    a = ops.LazyActs(arena)              # buffers become tensor views only when somebody asks for them
+    s = _lib.LayerActs()
+
+    def new(name, rows, cols, dtype=BF16):
+        setattr(s, name, a.take(name, rows, cols, dtype))
 
     v1 = weights.variant == 1
     series = bool(_lib.load().rpg_attention_series_enabled()) and c % 16 == 0 and c <= 256
-    a = {"x": x, "e": e, "P": new(Nt, (4 if v1 else 3) * D), "h1": new(Et, D), "e_new": new(Et, D), "h2": new(Et, D)}
+    a["x"], a["e"] = x, e
+    s.x, s.e = x.data_ptr(), e.data_ptr()
+    new("P", Nt, (4 if v1 else 3) * D); new("h1", Et, D); new("e_new", Et, D); new("h2", Et, D)
     # the attention projections (g | theta | phi): bf16 for the series attention, fp32 for the exp2 kernels;
     # the message m itself is never materialised (rpg.h: Wgc / WWM)
-    a["gtp16" if series else "gtp"] = new(Et, 3 * c, BF16 if series else torch.float32)
-    a.update({
-         "y": new(Et, cp, zero=(cp != c)),
-         "ybar": new(Nt, cp), "mbar": new(Nt, D), "a": new(Nt, D)})
+    new("gtp16" if series else "gtp", Et, 3 * c, BF16 if series else torch.float32)
+    if cp != c:                          # padding columns of y must be zero: a real tensor, zeroed
+        a["y"] = arena.take(Et, cp, zero=True)
+        s.y = a["y"].data_ptr()
+    else:
+        new("y", Et, cp)
+    new("ybar", Nt, cp); new("mbar", Nt, D); new("a", Nt, D)
     u8 = torch.uint8
     if for_backward:                     # ReLU patterns are only consumed by the backward epilogues
-        a.update({"h1_bits": new(Et, D // 8, u8), "h2_bits": new(Et, D // 8, u8)})
+        new("h1_bits", Et, D // 8, u8); new("h2_bits", Et, D // 8, u8)
     if not v1:
-        a.update({"h3": new(Nt, D), "out": new(Nt, D)})
+        new("h3", Nt, D); new("out", Nt, D)
         if for_backward:
-            a["h3_bits"] = new(Nt, D // 8, u8)
+            new("h3_bits", Nt, D // 8, u8)
     if for_backward and not _lib.load().rpg_attention_series_enabled():
-        a["att_aux"] = new(Et, 4 * c, torch.float32)           # exp2 attention only: row statistics, the backward skips a sweep
+        new("att_aux", Et, 4 * c, torch.float32)               # exp2 attention only: row statistics, the backward skips a sweep
     if want_relu_copies:
         if v1:
             raise ValueError("ReLU copies are a feature of the simpleConvEdge_upt stack path")
-        a["e_new_relu"] = new(Et, D)
-        a["out_relu"] = new(Nt, D)
+        new("e_new_relu", Et, D); new("out_relu", Nt, D)
         if for_backward:
-            a["e_new_bits"] = new(Et, D // 8, u8)
-            a["out_bits"] = new(Nt, D // 8, u8)
+            new("e_new_bits", Et, D // 8, u8); new("out_bits", Nt, D // 8, u8)
     if x_bits is not None:
         a["x_bits"] = x_bits
+        s.x_bits = x_bits.data_ptr()
     if e_bits is not None:
         a["e_bits"] = e_bits
-    s = _lib.LayerActs()
-    for k, v in a.items():
-        setattr(s, k, v.data_ptr())
+        s.e_bits = e_bits.data_ptr()
     if drop is not None:            # (p, seed_x, seed_e): the last round's ReLU copies leave the GEMMs dropped + rescaled
         if not want_relu_copies:
             raise ValueError("fused feature dropout acts on the ReLU copies")
         s.drop_p, s.drop_seed_x, s.drop_seed_e = float(drop[0]), int(drop[1]), int(drop[2])
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    stream = ops.stream_of(dev)
     _lib.check(_lib.load().rpg_layer_fwd(C.byref(weights), graph.byref(), C.byref(s), stream), "rpg_layer_fwd")
     a["_struct"] = s
     if v1:
@@ -503,40 +509,41 @@ def layer_backward_raw(weights, graph, acts, d_out, d_e_new, grads, mask_dx=Fals
     lib = _lib.load()
 
     arena = arena if arena is not None else ops.Arena(dev, ops.layer_bwd_bytes(D, Nt, Et))
-    new = arena.take
+    new, newp = arena.take, arena.take_ptr          # scratch the library alone touches is taken as an address
     f32 = torch.float32
 
     b = _lib.LayerGrads()
     have_out = d_out is not None
     v1 = weights.variant == 1
-    keep = {"dx": new(Nt, D), "de": new(Et, D), "dh1": new(Et, D), "dP": new(Nt, (4 if v1 else 3) * D),
-            "split_ws": new(1, lib.rpg_layer_bwd_ws_floats(D, 0, 0), f32),
-            "colsum_ws": new(1, lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), f32)}
+    dx, de = new(Nt, D), new(Et, D)
+    b.dx, b.de = dx.data_ptr(), de.data_ptr()
+    b.dh1, b.dP = newp(Et, D), newp(Nt, (4 if v1 else 3) * D)
+    b.split_ws = newp(1, lib.rpg_layer_bwd_ws_floats(D, 0, 0), f32)
+    b.colsum_ws = newp(1, lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, c3p)), f32)
     merged = have_out and not v1 and os.environ.get("RPG_MERGED_UPDATE_DGRAD", "1") != "0"
     if have_out:
         if merged:
             # [dx_u | da] as the column halves of one buffer: a single GEMM writes both (rpg_layer_grads_t.dxa_ld)
-            dxa = new(Nt, 2 * D)
-            keep.update({"dh3": new(Nt, D), "dxu": dxa[:, :D], "dan": dxa[:, D:]})
+            dxa = newp(Nt, 2 * D)
+            b.dh3, b.dxu, b.dan = newp(Nt, D), dxa, dxa + 2 * D
         else:
             if not v1:
-                keep.update({"dh3": new(Nt, D), "dxu": new(Nt, D)})
-            keep.update({"dan": new(Nt, D), "h2sum": new(Nt, D), "ysum": new(Nt, cp)})
-        keep.update({"dyn": new(Nt, c, f32), "dgtp": new(Et, c3p, zero=(c3p != 3 * c)),
-                     "dh2": new(Et, D), "de_tot": new(Et, D), "Q": new(Nt, D),
-                     "gtp_bias_tmp": new(1, c3p, f32), "T_tmp": new(3 * c, D, f32)})
-    for k, v in keep.items():
-        setattr(b, k, v.data_ptr())
+                b.dh3, b.dxu = newp(Nt, D), newp(Nt, D)
+            b.dan, b.h2sum, b.ysum = newp(Nt, D), newp(Nt, D), newp(Nt, cp)
+        b.dyn = newp(Nt, c, f32)
+        b.dgtp = new(Et, c3p, zero=True).data_ptr() if c3p != 3 * c else newp(Et, c3p)
+        b.dh2, b.de_tot, b.Q = newp(Et, D), newp(Et, D), newp(Nt, D)
+        b.gtp_bias_tmp, b.T_tmp = newp(1, c3p, f32), newp(3 * c, D, f32)
     b.dxa_ld = 2 * D if merged else 0
     b.d_out = ops.ptr(d_out)
     b.d_e_new = ops.ptr(d_e_new)
     b.mask_dx, b.mask_de = int(mask_dx), int(mask_de)
     for name in (PARAM_ORDER_EDGE if v1 else PARAM_ORDER):
         setattr(b, _GRAD_FIELD_OF[name], grads[name].data_ptr())
-    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    stream = ops.stream_of(dev)
     _lib.check(lib.rpg_layer_bwd(C.byref(weights), graph.byref(), C.byref(acts["_struct"]), C.byref(b), stream),
                "rpg_layer_bwd")
-    return keep["dx"], keep["de"]
+    return dx, de
 
 
 class _LayerFn(torch.autograd.Function):

@@ -303,3 +303,32 @@ def test_reference_graph_files_load_and_batch(tmp_path):
     with pytest.raises(ValueError):
         torch.save({"foo": 1}, str(tmp_path / "bad.pt"))
         graph_io.load_graph(str(tmp_path / "bad.pt"))
+
+
+def test_fast_params_sees_reassigned_parameters_and_survives_deepcopy():
+    """layers.fast_params caches the owning leaf modules (not the parameters): a re-assigned nn.Parameter is picked up at
+    once, the cache does not travel through deepcopy / pickle, and invalidate_packed() drops it."""
+    import copy
+    import pickle
+    from relpose_gnn_b200.layers import PARAM_ORDER, fast_params
+    m = rpg.simpleConvEdge_upt(128, 128, 128)
+    p = fast_params(m, PARAM_ORDER)
+    assert list(p) == list(PARAM_ORDER) and all(p[n] is m.get_parameter(n) for n in PARAM_ORDER)
+    new_w = torch.nn.Parameter(torch.zeros_like(m.mlp[0].weight))
+    m.mlp[0].weight = new_w
+    assert fast_params(m, PARAM_ORDER)["mlp.0.weight"] is new_w
+    m2 = copy.deepcopy(m)
+    assert "_rpg_leaf_cache" not in m2.__dict__ or all(
+        leaf is not m.mlp[0] for _, leaf, _ in m2.__dict__["_rpg_leaf_cache"].get(PARAM_ORDER, []))
+    assert fast_params(m2, PARAM_ORDER)["mlp.0.weight"] is m2.mlp[0].weight
+    m3 = pickle.loads(pickle.dumps(m))
+    assert fast_params(m3, PARAM_ORDER)["mlp.2.bias"] is m3.mlp[2].bias
+    m.invalidate_packed()
+    assert "_rpg_leaf_cache" not in m.__dict__
+    e0, v0 = m._pack_epoch, m._value_epoch
+    m.mark_values_changed()                      # optimizer-step notification: values only, the structure epoch stays
+    assert (m._pack_epoch, m._value_epoch) == (e0, v0 + 1)
+    g = rpg.RelPoseGNN(128, 128, 128)
+    assert [q is r for q, r in zip(g._ordered_params(), [g.get_parameter(n) for n in g._param_names()])] == [True] * len(g._param_names())
+    g.mark_values_changed()
+    assert g.gnn1._value_epoch == 1 and g._value_epoch == 1
