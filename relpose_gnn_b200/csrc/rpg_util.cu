@@ -200,27 +200,34 @@ int rpg_profile_records(rpg_prof_rec_t* out, int max_records, int* n_records) { 
 // Small fp32 products (weight composition Wgc = Wgtp W2m and the matching backward), ~50 MFLOP each.
 // ------------------------------------------------------------------------------------------------
 namespace rpg {
-// 64 x 64 output tile per block, 16-deep k chunks, 4 x 4 outputs per thread; the next chunk's global loads are issued
-// before the current chunk's FMAs (register prefetch), and the thread -> element mapping of the loads follows the
-// operand's storage order so that they coalesce for every transpose flag.
-constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+// BM x BN output tile per block (64 x 64, or 32 x 32 for launches that would leave most SMs idle), 32-deep k chunks,
+// (BM/16) x (BN/16) outputs per thread; the next chunk's global loads are issued before the current chunk's FMAs
+// (register prefetch), and the thread -> element mapping of the loads follows the operand's storage order so that they
+// coalesce for every transpose flag.  Fixed summation order: deterministic.
+constexpr int SG_BK = 32;
+template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 sgemm_batch_kernel(const __grid_constant__ rpg_sgemm_batch_t batch) {
+    constexpr int TM = BM / 16, TN = BN / 16;                        // outputs per thread
+    constexpr int LA = BM * SG_BK / 256, LB = BN * SG_BK / 256;      // operand elements per thread and chunk
     pdl_prologue();
     const rpg_sgemm_desc_t& d = batch.d[blockIdx.z];
-    const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if (m0 >= d.M || n0 >= d.N) return;
-    __shared__ __align__(16) float As[SG_BK][SG_BM + 4], Bs[SG_BK][SG_BN + 4];
+    __shared__ __align__(16) float As[SG_BK][BM + 4], Bs[SG_BK][BN + 4];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;                         // outputs: rows m0 + 4 ty + i, columns n0 + 4 tx + j
-    // load mapping: 1024 elements per operand tile, 4 per thread; `fast` runs along the operand's contiguous dimension
+    const int tx = tid & 15, ty = tid >> 4;                         // outputs: rows m0 + TM ty + i, columns n0 + TN tx + j
     // A tile element (m, k): stored A[m, k] (k contiguous) or, transA, A[k, m] (m contiguous)
-    int am[4], ak[4], bk[4], bn[4];
+    int am[LA], ak[LA], bk[LB], bn[LB];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < LA; ++i) {
         const int e = tid + 256 * i;
-        if (d.transA) { am[i] = e & 63; ak[i] = e >> 6; } else { ak[i] = e & 15; am[i] = e >> 4; }
-        if (d.transB) { bk[i] = e & 15; bn[i] = e >> 4; } else { bn[i] = e & 63; bk[i] = e >> 6; }
+        if (d.transA) { am[i] = e % BM; ak[i] = e / BM; } else { ak[i] = e % SG_BK; am[i] = e / SG_BK; }
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+        const int e = tid + 256 * i;
+        if (d.transB) { bk[i] = e % SG_BK; bn[i] = e / SG_BK; } else { bn[i] = e % BN; bk[i] = e / BN; }
     }
     auto ldA = [&](int k0, int i) -> float {
         const int m = m0 + am[i], k = k0 + ak[i];
@@ -232,40 +239,48 @@ sgemm_batch_kernel(const __grid_constant__ rpg_sgemm_batch_t batch) {
         if (n >= d.N || k >= d.K) return 0.f;
         return d.transB ? d.B[(size_t)n * d.ldb + k] : d.B[(size_t)k * d.ldb + n];
     };
-    float ra[4], rb[4], acc[4][4];
+    float ra[LA], rb[LB], acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        ra[i] = ldA(0, i); rb[i] = ldB(0, i);
+    for (int i = 0; i < LA; ++i) ra[i] = ldA(0, i);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    }
+    for (int i = 0; i < LB; ++i) rb[i] = ldB(0, i);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
     for (int k0 = 0; k0 < d.K; k0 += SG_BK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { As[ak[i]][am[i]] = ra[i]; Bs[bk[i]][bn[i]] = rb[i]; }
+        for (int i = 0; i < LA; ++i) As[ak[i]][am[i]] = ra[i];
+#pragma unroll
+        for (int i = 0; i < LB; ++i) Bs[bk[i]][bn[i]] = rb[i];
         __syncthreads();
         if (k0 + SG_BK < d.K) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ra[i] = ldA(k0 + SG_BK, i); rb[i] = ldB(k0 + SG_BK, i); }
+            for (int i = 0; i < LA; ++i) ra[i] = ldA(k0 + SG_BK, i);
+#pragma unroll
+            for (int i = 0; i < LB; ++i) rb[i] = ldB(k0 + SG_BK, i);
         }
 #pragma unroll
         for (int k = 0; k < SG_BK; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][4 * ty]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            float av[TM], bv[TN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; ++i) av[i] = As[k][TM * ty + i];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[k][TN * tx + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + 4 * ty + i;
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + TM * ty + i;
         if (m >= d.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + 4 * tx + j;
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + TN * tx + j;
             if (n >= d.N) continue;
             float v = acc[i][j];
             if (d.u && d.v) v = fmaf(d.u[m], d.v[n], v);
@@ -291,6 +306,13 @@ extern "C" int rpg_sgemm_batch(const rpg_sgemm_batch_t* batch, rpg_stream_t stre
         mx = d.M > mx ? d.M : mx;
         nx = d.N > nx ? d.N : nx;
     }
-    launch_pdl(sgemm_batch_kernel, dim3((nx + 63) / 64, (mx + 63) / 64, batch->n), dim3(256), 0, as_stream(stream), *batch);
+    // these products are small: with 64 x 64 tiles most SMs would idle behind a few long k loops, so launches of fewer than
+    // two waves of big tiles take 32 x 32 tiles (4x the blocks, a quarter of the work per k chunk each)
+    long long blocks64 = 0;
+    for (int i = 0; i < batch->n; ++i) blocks64 += (long long)((batch->d[i].M + 63) / 64) * ((batch->d[i].N + 63) / 64);
+    if (blocks64 < 2 * 148)
+        launch_pdl(sgemm_batch_kernel<32, 32>, dim3((nx + 31) / 32, (mx + 31) / 32, batch->n), dim3(256), 0, as_stream(stream), *batch);
+    else
+        launch_pdl(sgemm_batch_kernel<64, 64>, dim3((nx + 63) / 64, (mx + 63) / 64, batch->n), dim3(256), 0, as_stream(stream), *batch);
     return check_launch("sgemm_batch_kernel");
 }

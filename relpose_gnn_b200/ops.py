@@ -1,6 +1,7 @@
 """Thin tensor-level wrappers over the C ABI (include/rpg.h).  Every function enqueues on the current
 CUDA stream of the tensors' device and returns immediately; there is no CPU or PyTorch fallback."""
 import ctypes as C
+import threading
 
 import torch
 
@@ -101,7 +102,11 @@ def layer_bwd_bytes(D, Nt, Et):
             4 * lib.rpg_colsum_scratch_floats(max(Et, Nt), max(D, pad64(3 * c))) + 64 * 256)
 
 
-_scoped_stream = None       # (device index, c_void_p) while a stream_scope is open
+class _Tls(threading.local):
+    scoped = None           # (device index, c_void_p) while a stream_scope is open on THIS thread
+
+
+_tls = _Tls()
 
 
 class stream_scope:
@@ -113,14 +118,12 @@ class stream_scope:
         self.device = device
 
     def __enter__(self):
-        global _scoped_stream
-        self.prev = _scoped_stream
-        _scoped_stream = (self.device.index, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        self.prev = _tls.scoped
+        _tls.scoped = (self.device.index, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         return self
 
     def __exit__(self, *exc):
-        global _scoped_stream
-        _scoped_stream = self.prev
+        _tls.scoped = self.prev
         return False
 
 
@@ -145,14 +148,14 @@ def scoped(fn):
 
 def stream_of(device):
     """c_void_p handle of the stream to enqueue on for `device` (the open stream_scope's, else torch's current one)."""
-    sc = _scoped_stream
+    sc = _tls.scoped
     if sc is not None and device.index == sc[0]:
         return sc[1]
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _stream(t):
-    sc = _scoped_stream
+    sc = _tls.scoped
     if sc is not None and t.device.index == sc[0]:
         return sc[1]
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
