@@ -229,6 +229,11 @@ int rpg_wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int
 /* Same, and bias[m] += sum_r A[r, m] from the same pass (bias may be NULL).                            */
 int rpg_wgrad_bias(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, int64_t R,
                    float* ws, float* out, int ldo, float* bias, rpg_stream_t stream);
+/* Several weight gradients that share B and whose A operands are adjacent column blocks of ONE tensor (the two halves
+ * of proj_edge.weight, posenet.py:1014-1017: dW[:, blk] += A[:, blk*M:(blk+1)*M]^T B): one product of M * nblocks
+ * rows, folded block by block into outs[blk] (pitch ldo).  bias (optional) += column sums of block 0.  nblocks <= 4. */
+int rpg_wgrad_blocks(const rpg_bf16* A, int lda, int M, int nblocks, const rpg_bf16* B, int ldb, int N, int64_t R,
+                     float* ws, float* const* outs, int ldo, float* bias, rpg_stream_t stream);
 /* sizeof / offsetof probes so a foreign-language mirror of the structs can verify its layout.      */
 void rpg_struct_sizes(int32_t* out16);   /* 13 values used, 16 slots */
 

@@ -151,6 +151,7 @@ SIGNATURES = {
     "rpg_set_gemm_cluster": (I, [I]),
     "rpg_wgrad": (I, [P, I, I, P, I, I, I64, P, P, I, P]),
     "rpg_wgrad_bias": (I, [P, I, I, P, I, I, I64, P, P, I, P, P]),
+    "rpg_wgrad_blocks": (I, [P, I, I, I, P, I, I, I64, P, P, I, P, P]),
     "rpg_struct_sizes": (None, [C.POINTER(C.c_int32)]),
     "rpg_reduce_splits": (I, [P, I, I64, I, I, P, I, I, P]),
     "rpg_pack_weight": (I, [P, I, I, I, I, I, P, I, I, P]),

@@ -1443,7 +1443,7 @@ colsum_stage1_kernel(const bf16* __restrict__ v, int ldv, long long rows, int co
 // out[i] (+)= sum_b part[b, i] with the parts spread over 8 phases per column (fixed order => deterministic)
 __global__ void __launch_bounds__(256)
 reduce_partials_wide_kernel(const float* __restrict__ part, int nparts, long long stride, int n,
-                            float* __restrict__ out, int accumulate) {
+                            float* __restrict__ out, int accumulate, float* __restrict__ out2) {
     pdl_prologue();
     __shared__ float red[8][32];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31), ph = threadIdx.x >> 5;
@@ -1456,8 +1456,24 @@ reduce_partials_wide_kernel(const float* __restrict__ part, int nparts, long lon
 #pragma unroll
         for (int k = 1; k < 8; ++k) s += red[k][threadIdx.x & 31];
         out[col] = accumulate ? out[col] + s : s;
+        if (out2) out2[col] = accumulate ? out2[col] + s : s;      // the same sums into a second parameter gradient
     }
 }
+
+// column sums into one or two outputs (two parameter gradients that receive the same sums: one pass over the tensor)
+int colsum_bf16_2(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod, float* out,
+                       float* out2, int accumulate, float* scratch, cudaStream_t s) {
+    if (!v || !out || !scratch || rows <= 0 || cols % 8 || ldv % 8 || cols / 8 > COLSUM_THREADS)
+        return set_error(RPG_E_ARG, "colsum: bad arguments (cols must be a multiple of 8, at most 2048)");
+    const int slabs = (int)((rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
+    launch_pdl(colsum_stage1_kernel, dim3(slabs), dim3(COLSUM_THREADS), 0, s, reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
+                                                          row_w_mod > 0 ? row_w_mod : 1, scratch);
+    int rc = check_launch("colsum_stage1_kernel");
+    if (rc) return rc;
+    launch_pdl(reduce_partials_wide_kernel, dim3((cols + 31) / 32), dim3(256), 0, s, scratch, slabs, cols, cols, out, accumulate, out2);
+    return check_launch("reduce_partials_wide_kernel");
+}
+
 
 }  // namespace rpg
 
@@ -1801,16 +1817,7 @@ int64_t rpg_colsum_scratch_floats(int64_t rows, int cols) {
 
 int rpg_colsum_bf16(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod, float* out,
                     int accumulate, float* scratch, rpg_stream_t stream) {
-    if (!v || !out || !scratch || rows <= 0 || cols % 8 || ldv % 8 || cols / 8 > COLSUM_THREADS)
-        return set_error(RPG_E_ARG, "colsum: bad arguments (cols must be a multiple of 8, at most 2048)");
-    const int slabs = (int)((rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
-    cudaStream_t s = as_stream(stream);
-    launch_pdl(colsum_stage1_kernel, dim3(slabs), dim3(COLSUM_THREADS), 0, s, reinterpret_cast<const bf16*>(v), ldv, rows, cols, row_w,
-                                                          row_w_mod > 0 ? row_w_mod : 1, scratch);
-    int rc = check_launch("colsum_stage1_kernel");
-    if (rc) return rc;
-    launch_pdl(reduce_partials_wide_kernel, dim3((cols + 31) / 32), dim3(256), 0, s, scratch, slabs, cols, cols, out, accumulate);
-    return check_launch("reduce_partials_wide_kernel");
+    return colsum_bf16_2(v, ldv, rows, cols, row_w, row_w_mod, out, nullptr, accumulate, scratch, as_stream(stream));
 }
 
 int rpg_reduce_splits(const float* partial, int splits, int64_t split_stride, int rows, int cols, float* out, int ldo,

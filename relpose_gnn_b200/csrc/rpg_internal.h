@@ -55,6 +55,10 @@ bool tn_group_supported(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, in
 int tn_group_splits(int M, int N, long long R, int sm_count);
 int tn_group_launch(const TnDesc* d, int n, cudaStream_t stream);
 
+// rpg_colsum_bf16 with an optional second output that receives the same sums (rpg_aux.cu)
+int colsum_bf16_2(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod, float* out,
+                  float* out2, int accumulate, float* scratch, cudaStream_t s);
+
 inline cudaStream_t as_stream(rpg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Programmatic dependent launch: every kernel of the library starts with griddepcontrol.launch_dependents +

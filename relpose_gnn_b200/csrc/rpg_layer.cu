@@ -234,6 +234,22 @@ int rpg_wgrad_bias(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb
     return rc ? rc : q.flush();
 }
 
+int rpg_wgrad_blocks(const rpg_bf16* A, int lda, int M, int nblocks, const rpg_bf16* B, int ldb, int N, int64_t R, float* ws,
+                     float* const* outs, int ldo, float* bias, rpg_stream_t stream) {
+    if (!A || !B || !ws || !outs || nblocks < 1 || nblocks > 4 || M <= 0) return set_error(RPG_E_ARG, "wgrad_blocks: bad arguments");
+    for (int i = 0; i < nblocks; ++i)
+        if (!outs[i]) return set_error(RPG_E_ARG, "wgrad_blocks: null output");
+    WgradQueue q(ws, sm_count_cached(), as_stream(stream));
+    const int Mp = M * nblocks;
+    float* part = nullptr;
+    int splits = 0;
+    int rc = q.partials(A, lda, Mp, B, ldb, N, R, bias != nullptr, &part, &splits);
+    for (int i = 0; i < nblocks && !rc; ++i)
+        rc = q.add(part + (size_t)i * M * N, splits, (long long)Mp * N, M, N, outs[i], ldo);
+    if (!rc && bias) rc = q.add(part + (size_t)splits * Mp * N, splits, Mp, 1, M, bias, M);
+    return rc ? rc : q.flush();
+}
+
 void rpg_struct_sizes(int32_t* out) {
     out[0] = (int32_t)sizeof(rpg_graph_t);
     out[1] = (int32_t)sizeof(rpg_gemm_t);
@@ -875,15 +891,13 @@ int rpg_layer_bwd(const rpg_layer_weights_t* w, const rpg_graph_t* gr, const rpg
             // and sum_n deg(n) dan[n] = sum over the nodes WITH in-edges of da[n]
             RPG_TRY(q.wgrad(b->dan, ld_dan, D, t->mbar, D, D, Nt, b->g_mlp2_w, D));
             RPG_TRY(q.wgrad(b->dan, ld_dan, D, t->ybar, cp, c, Nt, b->g_att_W_w, c));
-            RPG_TRY(rpg_colsum_bf16(b->dan, ld_dan, Nt, D, gr->has_in, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
-            RPG_TRY(rpg_colsum_bf16(b->dan, ld_dan, Nt, D, gr->has_in, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
+            RPG_TRY(colsum_bf16_2(b->dan, ld_dan, Nt, D, gr->has_in, gr->N, b->g_att_W_b, b->g_mlp2_b, 1, b->colsum_ws, s));
         } else {
             RPG_TRY(rpg_scale_rows(t->mbar, D, Nt, D, gr->deg, gr->N, b->h2sum, D, stream));
             RPG_TRY(q.wgrad(b->dan, D, D, b->h2sum, D, D, Nt, b->g_mlp2_w, D));
             RPG_TRY(rpg_scale_rows(t->ybar, cp, Nt, cp, gr->deg, gr->N, b->ysum, cp, stream));
             RPG_TRY(q.wgrad(b->dan, D, D, b->ysum, cp, c, Nt, b->g_att_W_w, c));
-            RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, 1, b->colsum_ws, stream));
-            RPG_TRY(rpg_colsum_bf16(b->dan, D, Nt, D, gr->deg, gr->N, b->g_mlp2_b, 1, b->colsum_ws, stream));
+            RPG_TRY(colsum_bf16_2(b->dan, D, Nt, D, gr->deg, gr->N, b->g_att_W_b, b->g_mlp2_b, 1, b->colsum_ws, s));
         }
         if (!v1) {
             // mlp_updating.2: dW = d_out^T h3 ; mlp_updating.0: dW = dh3^T [x | a]

@@ -300,7 +300,7 @@ def apply_edge_mask(t, keep_undirected, n_graphs):
 def mask_edge_index(edge_index, keep_undirected, n_graphs):
     """train.py:238-245 (documented intent: `data.edge_index[:, surviving_edges]`) on the device: the batched
     edge_index [2, G*E] of full templates thinned by the batch-shared undirected keep mask -> [2, G*E_kept].
-    Two row-selection launches; the mask travels as kernel parameters (no copy engine, no synchronisation)."""
+    One row-selection launch; the mask travels as kernel parameters (no copy engine, no synchronisation)."""
     if not edge_index.is_cuda or edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise TypeError("edge_index must be a CUDA int64 tensor of shape [2, E]")
     keep = np.asarray(keep_undirected, dtype=bool)
@@ -314,9 +314,9 @@ def mask_edge_index(edge_index, keep_undirected, n_graphs):
     idx_dev = _uploader.upload(idx, ei.device)
     lib = _lib.load()
     stream = _stream_of(ei.device)
-    for r in range(2):
-        _lib.check(lib.rpg_edge_mask_apply(ei[r].data_ptr(), n_graphs, Ep_full, int(idx.size), idx_dev.data_ptr(), 8,
-                                           out[r].data_ptr(), stream), "rpg_edge_mask_apply")
+    # both rows in ONE launch: [2, G*E] contiguous is 2G "graphs" of E entries, and so is the output
+    _lib.check(lib.rpg_edge_mask_apply(ei.data_ptr(), 2 * n_graphs, Ep_full, int(idx.size), idx_dev.data_ptr(), 8,
+                                       out.data_ptr(), stream), "rpg_edge_mask_apply")
     return out
 
 

@@ -156,8 +156,9 @@ class _StackFn(torch.autograd.Function):
         dx = arena.take(Nt, D)
         ops.gemm_nt(dpmm, sw["WmmT"], resid=d_x, out=dx)
         gw = grads["proj_edge.weight"]
-        ops.wgrad(dpmm[:, :D], xb, gw[:, :D], ws, bias=grads["proj_edge.bias"])   # every edge has exactly one lower endpoint
-        ops.wgrad(dpmm[:, D:], xb, gw[:, D:], ws)
+        # both column halves of proj_edge.weight in one product; the bias sums come from the first half (every edge has
+        # exactly one lower endpoint)
+        ops.wgrad_blocks(dpmm, xb, [gw[:, :D], gw[:, D:]], ws, bias=grads["proj_edge.bias"])
         dx = ops.to_f32(dx) if ctx.x_dtype == torch.float32 else dx
         if direct:
             return (dx, None, None, None) + (None,) * len(names)

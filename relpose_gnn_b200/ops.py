@@ -265,6 +265,16 @@ def wgrad(A, B, out, ws, M=None, N=None, bias=None):
                              out.data_ptr(), out.stride(0), ptr(bias), _stream(A)), "rpg_wgrad")
 
 
+def wgrad_blocks(A, B, outs, ws, bias=None):
+    """outs[i][M, N] += A[:, i*M:(i+1)*M]^T @ B for the adjacent column blocks of A in ONE product (M = outs[i].size(0));
+    bias (optional) += column sums of block 0."""
+    lib = _lib.load()
+    M, N = outs[0].size(0), B.size(1)
+    arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    check(lib.rpg_wgrad_blocks(A.data_ptr(), A.stride(0), M, len(outs), B.data_ptr(), B.stride(0), N, A.size(0), ws.data_ptr(),
+                               arr, outs[0].stride(0), ptr(bias), _stream(A)), "rpg_wgrad_blocks")
+
+
 def pack_weight(src, dst, r0=0, c0=0, rows=None, cols=None, transpose=False):
     lib = _lib.load()
     rows = rows if rows is not None else src.size(0) - r0
