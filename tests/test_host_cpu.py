@@ -332,3 +332,32 @@ def test_fast_params_sees_reassigned_parameters_and_survives_deepcopy():
     assert [q is r for q, r in zip(g._ordered_params(), [g.get_parameter(n) for n in g._param_names()])] == [True] * len(g._param_names())
     g.mark_values_changed()
     assert g.gnn1._value_epoch == 1 and g._value_epoch == 1
+
+
+def test_arena_and_lazy_activation_views():
+    """ops.Arena / ops.LazyActs (host logic of the per-step allocations): blocks are 256-byte aligned slices of ONE buffer,
+    addresses taken without a tensor become views of the right shape and dtype on first access only, and a request the
+    arena cannot hold falls back to its own tensor (kept alive by the arena / the dictionary)."""
+    from relpose_gnn_b200 import ops
+    ar = ops.Arena(torch.device("cpu"), 4096)
+    t = ar.take(3, 5)                                   # bf16 [3, 5] = 30 bytes
+    assert t.dtype == torch.bfloat16 and tuple(t.shape) == (3, 5) and t.data_ptr() == ar.base
+    p = ar.take_ptr(2, 8, torch.float32)                # next block starts on the next 256-byte boundary
+    assert p == ar.base + 256 and ar.off == 512
+    acts = ops.LazyActs(ar)
+    q = acts.take("h1", 4, 16)                          # 128 bytes at offset 512
+    r = acts.take("bits", 4, 2, torch.uint8)
+    assert q == ar.base + 512 and r == ar.base + 768
+    assert "h1" in acts and "nope" not in acts and acts.get("nope") is None and not dict.__contains__(acts, "h1")
+    h1 = acts["h1"]
+    assert tuple(h1.shape) == (4, 16) and h1.dtype == torch.bfloat16 and h1.data_ptr() == q
+    assert acts["h1"] is h1 and dict.__contains__(acts, "h1")        # materialised once
+    assert acts["bits"].dtype == torch.uint8 and acts["bits"].data_ptr() == r
+    h1.fill_(1.0)                                       # a view of the arena buffer, not a copy
+    assert int(ar.buf[512:512 + 128].view(torch.bfloat16).float().sum()) == 64
+    big = acts.take("big", 64, 64, torch.float32)       # 16 KB does not fit the 4 KB arena: own tensor
+    assert dict.__contains__(acts, "big") and acts["big"].data_ptr() == big and tuple(acts["big"].shape) == (64, 64)
+    spill = ar.take_ptr(64, 64, torch.float32)
+    assert len(ar.spill) == 1 and ar.spill[0].data_ptr() == spill
+    with pytest.raises(KeyError):
+        acts["missing"]
