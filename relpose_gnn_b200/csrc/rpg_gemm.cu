@@ -868,46 +868,51 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D bf16 tensor map: inner extent `inner` (contiguous), outer extent `outer`, row pitch `ld` elements.
-static int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                     uint32_t box_inner, uint32_t box_outer) {
+// (Round 2 measured a per-thread memo table for the descriptors -- cuTensorMapEncodeTiled is a pure function of its
+// arguments and a step asks for the same ~400 every time: no difference in the host time of a step, 1.38-1.58 ms either
+// way; the driver encodes one in ~0.2 us.  Not kept.)
+// rank 2 or 3; dims / strides (bytes, rank - 1 of them) / box in the driver's order (innermost first); bf16 or fp32
+// elements; 128-byte swizzle, 256-byte L2 promotion, no OOB fill value (zeros).
+int tmap_encode(::CUtensorMap_st* tm, int f32, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return set_error(RPG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {ld * 2};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rank < 2 || rank > 3) return set_error(RPG_E_ARG, "tmap_encode: rank must be 2 or 3");
+    struct { uint64_t dims[3]; uint64_t strides[2]; uint32_t box[3]; } key;
+    memset(&key, 0, sizeof key);
+    for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides[i];
+    cuuint64_t d[3] = {key.dims[0], key.dims[1], key.dims[2]};
+    cuuint64_t st[2] = {key.strides[0], key.strides[1]};
+    cuuint32_t bx[3] = {key.box[0], key.box[1], key.box[2]};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        char msg[160];
-        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r,
-                 (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+        char msg[200];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d): rank=%d dims=%llu,%llu,%llu pitch=%llu box=%u,%u,%u %s", (int)r, rank,
+                 (unsigned long long)key.dims[0], (unsigned long long)key.dims[1], (unsigned long long)key.dims[2],
+                 (unsigned long long)key.strides[0], key.box[0], key.box[1], key.box[2], f32 ? "f32" : "bf16");
         return set_error((int)r, msg);
     }
     return 0;
 }
 
+// 2-D bf16 tensor map: inner extent `inner` (contiguous), outer extent `outer`, row pitch `ld` elements.
+static int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
+    const uint64_t dims[2] = {inner, outer}, strides[1] = {ld * 2};
+    const uint32_t box[2] = {box_inner, box_outer};
+    return tmap_encode(tm, 0, 2, base, dims, strides, box);
+}
+
 // 3-D fp32 tensor map [planes][rows][cols] for the epilogue's fp32 results (split-R partials are the planes).
 static int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t planes, uint64_t ld,
                             uint64_t plane_stride) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return set_error(RPG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[3] = {cols, rows, planes};
-    cuuint64_t strides[2] = {ld * 4, (planes > 1 ? plane_stride : ld * rows) * 4};
-    cuuint32_t box[3] = {32, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        char msg[160];
-        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(f32 out) failed (%d): cols=%llu rows=%llu planes=%llu ld=%llu", (int)r,
-                 (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)planes, (unsigned long long)ld);
-        return set_error((int)r, msg);
-    }
-    return 0;
+    const uint64_t dims[3] = {cols, rows, planes}, strides[2] = {ld * 4, (planes > 1 ? plane_stride : ld * rows) * 4};
+    const uint32_t box[3] = {32, 32, 1};
+    return tmap_encode(tm, 1, 3, base, dims, strides, box);
 }
 
 // ---- per-launch event timing (enabled only between rpg_profile_begin and rpg_profile_end / rpg_profile_records)

@@ -285,38 +285,6 @@ __global__ void __launch_bounds__(T_THREADS, 1) tn_pair_group_kernel(const __gri
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    });
-    return fn;
-}
-
-int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return set_error(RPG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        char msg[128];
-        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) for a grouped weight-gradient operand", (int)r);
-        return set_error((int)r, msg);
-    }
-    return 0;
-}
-
 bool tn_group_env() {
     static int on = -1;
     if (on < 0) {
@@ -386,22 +354,20 @@ int tn_group_launch(const TnDesc* d, int n, cudaStream_t stream) {
         p.num_n_blocks = (t.N + p.block_n - 1) / p.block_n;
         p.colsum = t.colsum;
         {
-            cuuint64_t dims[2] = {(cuuint64_t)t.M, (cuuint64_t)t.R};
-            cuuint64_t strides[1] = {(cuuint64_t)t.lda * 2};
-            cuuint32_t box[2] = {64, T_BLOCK_K};
-            if ((rc = encode(&p.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.A, dims, strides, box))) return rc;
+            const uint64_t dims[2] = {(uint64_t)t.M, (uint64_t)t.R}, strides[1] = {(uint64_t)t.lda * 2};
+            const uint32_t box[2] = {64, T_BLOCK_K};
+            if ((rc = tmap_encode(&p.a, 0, 2, t.A, dims, strides, box))) return rc;
         }
         {
-            cuuint64_t dims[2] = {(cuuint64_t)t.N, (cuuint64_t)t.R};
-            cuuint64_t strides[1] = {(cuuint64_t)t.ldb * 2};
-            cuuint32_t box[2] = {64, T_BLOCK_K};
-            if ((rc = encode(&p.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, t.B, dims, strides, box))) return rc;
+            const uint64_t dims[2] = {(uint64_t)t.N, (uint64_t)t.R}, strides[1] = {(uint64_t)t.ldb * 2};
+            const uint32_t box[2] = {64, T_BLOCK_K};
+            if ((rc = tmap_encode(&p.b, 0, 2, t.B, dims, strides, box))) return rc;
         }
         {
-            cuuint64_t dims[3] = {(cuuint64_t)t.N, (cuuint64_t)t.M, (cuuint64_t)t.splits};
-            cuuint64_t strides[2] = {(cuuint64_t)t.N * 4, (cuuint64_t)t.M * t.N * 4};
-            cuuint32_t box[3] = {32, 32, 1};
-            if ((rc = encode(&p.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.part, dims, strides, box))) return rc;
+            const uint64_t dims[3] = {(uint64_t)t.N, (uint64_t)t.M, (uint64_t)t.splits};
+            const uint64_t strides[2] = {(uint64_t)t.N * 4, (uint64_t)t.M * t.N * 4};
+            const uint32_t box[3] = {32, 32, 1};
+            if ((rc = tmap_encode(&p.o, 1, 3, t.part, dims, strides, box))) return rc;
         }
         const int m_units = (t.M + 2 * T_BLOCK_M - 1) / (2 * T_BLOCK_M);
         batch.item0[i + 1] = batch.item0[i] + m_units * p.num_n_blocks * p.splits;

@@ -7,6 +7,8 @@
 
 #include "../../include/rpg.h"
 
+struct CUtensorMap_st;      // <cuda.h>'s tensor-map descriptor (only rpg_gemm*.cu include that header)
+
 namespace rpg {
 
 // Records a message for rpg_last_error_string() (thread-local) and returns `code`.
@@ -54,6 +56,11 @@ struct TnDesc {
 bool tn_group_supported(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R);
 int tn_group_splits(int M, int N, long long R, int sm_count);
 int tn_group_launch(const TnDesc* d, int n, cudaStream_t stream);
+
+// cuTensorMapEncodeTiled with this library's fixed choices (rpg_gemm.cu): rank 2 or 3, bf16 or fp32 elements, 128-byte swizzle; dims / byte
+// strides / box innermost first.
+int tmap_encode(::CUtensorMap_st* tm, int f32, int rank, const void* base, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box);
 
 // rpg_colsum_bf16 with an optional second output that receives the same sums (rpg_aux.cu)
 int colsum_bf16_2(const rpg_bf16* v, int ldv, int64_t rows, int cols, const float* row_w, int row_w_mod, float* out,

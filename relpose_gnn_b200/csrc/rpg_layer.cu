@@ -72,17 +72,6 @@ static int wgrad_partials(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, 
     return gemm_launch(&g, s);
 }
 
-// dW[M,N] += A^T B, deterministic (fixed split order); optionally bias[M] += column sums of A from the same pass.
-static int wgrad(const rpg_bf16* A, int lda, int M, const rpg_bf16* B, int ldb, int N, long long R, float* ws,
-                 float* out, int ldo, int sm_count, cudaStream_t s, float* bias = nullptr) {
-    int splits = 0;
-    int rc = wgrad_partials(A, lda, M, B, ldb, N, R, ws, sm_count, s, &splits, bias != nullptr);
-    if (rc) return rc;
-    rc = rpg_reduce_splits(ws, splits, (long long)M * N, M, N, out, ldo, /*accumulate=*/1, s);
-    if (rc || !bias) return rc;
-    return rpg_reduce_splits(ws + (size_t)splits * M * N, splits, M, 1, M, bias, M, /*accumulate=*/1, s);
-}
-
 }  // namespace rpg
 bool rpg::pdl_enabled() {
     static int on = -1;
